@@ -1,0 +1,168 @@
+/* madm_b200 — C ABI of the B200-native MADM diffusion feature-extraction hot path.
+ *
+ * The reference (XiaRho/MADM) has no FFI for this path: its boundary is the Python nn.Module
+ *   AttentionFeatureExtractorBackbone.forward(img, input_modal, ema_forward, timestep, **kw)
+ *       (reference modeling/backbone/feature_extractor.py:280-284, :156-170, :367-396)
+ * which calls BasePromptTimeGenerator.forward (modeling/meta_arch/ldm_base.py:832-924) and
+ * LdmDiffusers.forward (modeling/meta_arch/ldm_diffusers.py:143-217).  This library is what the drop-in
+ * Python module (madm_b200/backbone.py) binds instead of diffusers/peft/detectron2: each entry point below
+ * names the reference code it replaces.
+ *
+ * Conventions: extern "C", POD structs, raw device pointers, no torch types.  Every call returns 0 on success
+ * or a negative MADM_E* code (never throws / aborts); madm_last_error() gives the message.  All device work is
+ * enqueued asynchronously on the caller's stream (pass torch.cuda.current_stream().cuda_stream); there are no
+ * hidden synchronisations.  The caller owns all memory: parameters (fp32, PyTorch layouts), the packed-weight
+ * arena, the workspace and the outputs.  One madm_ctx per (process, device); not thread-safe.
+ * Built for sm_100a only; there is no CPU fallback.
+ */
+#ifndef MADM_B200_H_
+#define MADM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MADM_VERSION 100 /* 0.1.0 */
+
+enum {
+  MADM_OK = 0,
+  MADM_EINVAL = -1,   /* bad argument / unsupported shape */
+  MADM_ENOTFOUND = -2,/* a required parameter tensor was not registered */
+  MADM_ECUDA = -3,    /* CUDA runtime / driver error */
+  MADM_ESTATE = -4,   /* call order violation (e.g. extract before pack) */
+  MADM_ENOMEM = -5    /* workspace or packed arena too small */
+};
+
+typedef struct madm_ctx madm_ctx;
+typedef void* madm_stream; /* cudaStream_t */
+
+/* A named fp32 device tensor in its PyTorch layout (Conv2d [out,in,kh,kw], Linear [out,in], vectors [n]).
+ * Names are the reference's state_dict keys relative to `backbone.`, e.g.
+ *   feature_extractor.ldm_extractor.unet.down_blocks.0.resnets.0.conv1.weight
+ *   feature_extractor.ldm_extractor.unet....attn1.to_q.base_layer.weight / .lora_A.<adapter>.weight
+ *   feature_extractor.ldm_extractor.vae.encoder.conv_in.weight
+ *   feature_projections.0.0.conv1.weight, feature_projections.0.0.conv1.norm.weight
+ *   ema_feature_projections.*  (EMA twins, reference modeling/meta_arch/cmdise.py:308) */
+typedef struct madm_tensor {
+  const char* name;
+  const void* data;
+  int32_t ndim;
+  int64_t shape[4];
+} madm_tensor;
+
+int madm_version(void);
+const char* madm_last_error(const madm_ctx* ctx); /* ctx may be NULL: error of the last failed madm_create */
+
+int madm_create(madm_ctx** out, int device);
+int madm_destroy(madm_ctx* ctx);
+
+/* Register / refresh parameter pointers.  Replaces nn.Module parameter ownership: the library never copies or
+ * owns model weights, it reads biases and norm affines in place and packs GEMM weights into the arena below. */
+int madm_set_tensors(madm_ctx* ctx, const madm_tensor* named, int32_t n);
+
+/* Bytes of the packed bf16 weight arena (K-major tiles for TMA) for the registered model. */
+size_t madm_packed_bytes(madm_ctx* ctx);
+
+/* fp32 -> bf16 K-major packing of every GEMM weight into `packed` (caller-allocated, madm_packed_bytes()).
+ * `adapter` names the active LoRA adapter to fold (W' = W + alpha/r * B@A; replaces peft's LoRA Linear.forward and
+ * MTMADISE.set_lora_adapter, reference modeling/meta_arch/mtmadise.py:115-147); NULL or "" = base weights.
+ * lora_alpha_over_r: scaling for that adapter.  lora_only != 0 repacks just the 128 LoRA-targeted projections
+ * (adapter switch); 0 repacks everything (after load_state_dict / optimizer step / EMA update). */
+int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float lora_alpha_over_r, int32_t lora_only,
+                      madm_stream stream);
+
+#define MADM_STAGE_VAE 1   /* vae_encoder           (reference ldm_diffusers.py:283-311) */
+#define MADM_STAGE_UNET 2  /* add_noise + diffusion_unet (ldm_diffusers.py:349-360, :454-616) */
+#define MADM_STAGE_PROJ 4  /* forward_features      (reference feature_extractor.py:367-396) */
+#define MADM_STAGE_ALL 7
+
+/* Workspace bytes needed by madm_extract for batch B (all stages). */
+size_t madm_workspace_bytes(madm_ctx* ctx, int32_t B);
+
+typedef struct madm_extract_args {
+  int32_t B;                   /* images (512x512 crops) in this call */
+  int32_t stages;              /* MADM_STAGE_* mask; intermediate results live in the workspace between calls */
+  int32_t ema;                 /* use ema_feature_projections (ema_forward=True) */
+  int32_t reserved;
+  const float* img;            /* [B,3,512,512] fp32 NCHW in [0,1] (LdmDiffusers.forward input, input_range '-1+1') */
+  const float* cond_inputs;    /* [B,77,768] fp32: batched_inputs['cond_inputs'] (ldm_base.py:915-917) */
+  const float* cond_emb;       /* [B,1280] fp32: batched_inputs['cond_emb'][:,0] */
+  const int64_t* timesteps;    /* [B] int64 device: torch.randint(lo,hi,(B,)) (ldm_diffusers.py:160) */
+  const float* shared_noise;   /* [1,4,64,64] fp32: buffer shared_noise (ldm_diffusers.py:73-75) */
+  const float* noisy_latents_in; /* optional [B,4,64,64] NCHW: overrides VAE+q-sample output for the UNet stage */
+  float* out[4];               /* s2 [B,512,128,128], s3 [B,512,64,64], s4 [B,512,32,32], s5 [B,512,16,16] fp32 NCHW */
+  /* optional debug / parity taps (NULL to skip), fp32 NCHW */
+  float* latents;              /* [B,4,64,64]  vae mean * 0.18215 */
+  float* noisy_latents;        /* [B,4,64,64] */
+  float* taps[4];              /* enc tap [B,512,128,128], unet taps [B,320,64,64], [B,640,32,32], [B,1280,16,16] */
+  const void* packed;          /* arena filled by madm_pack_weights */
+  void* workspace;
+  size_t workspace_bytes;
+  int32_t* range_flag;         /* optional device int: set to 1 if the normalised image leaves [-1,1]
+                                  (the reference asserts this with a host sync, ldm_diffusers.py:147) */
+} madm_extract_args;
+
+/* The whole path a-1..a-9 of SURVEY §8: VAE encode -> q-sample -> UNet forward with taps -> GN-bottleneck projections. */
+int madm_extract(madm_ctx* ctx, const madm_extract_args* args, madm_stream stream);
+
+/* Number of kernels one madm_extract call launches for batch B with the given stage mask (for bench accounting). */
+int madm_launch_count(madm_ctx* ctx, int32_t B, int32_t stages);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Operator-level entry points (the kernels the engine is built from), exposed so parity tests can check each one
+ * against the oracle through the same C ABI.  All pointers are device pointers.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct madm_gemm_seg {
+  const void* a;     /* bf16 NHWC activations [Bt,H,W,ld] */
+  int32_t Bt, H, W, C, ld, ntaps;
+  int8_t dx[9], dy[9];
+  int32_t b_off[9];
+} madm_gemm_seg;
+
+typedef struct madm_gemm_args {
+  madm_gemm_seg seg[2];
+  int32_t nseg, M, N, Nw, ldw;
+  const void* w;          /* bf16 [Nw, ldw] K-major */
+  const float* bias;      /* [N] or NULL */
+  const float* rowbias;   /* [nimg, ld_rowbias] or NULL */
+  int32_t rows_per_img, ld_rowbias;
+  const float* residual;  /* fp32 [M, ldr] or NULL */
+  int32_t ldr;
+  float* out_f32; int32_t ldo32;
+  void* out_bf16; int32_t ldo16;
+  int32_t act;            /* 0 none, 1 SiLU, 2 GEGLU (tile-interleaved weights), 3 ReLU */
+  float alpha;
+  int32_t bn;             /* N tile: 0 auto, else 16/32/64/128/160/192/256 */
+} madm_gemm_args;
+
+int madm_op_gemm(const madm_gemm_args* a, madm_stream stream);
+int madm_op_groupnorm(const float* x0, int32_t C0, const float* x1, int32_t C1, int32_t B, int32_t HW, const float* gamma,
+                      const float* beta, float eps, int32_t act, float* stats_scratch /*[B,32,2], zeroed by the call*/,
+                      void* y_bf16, void* raw_bf16, madm_stream stream);
+int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y_bf16,
+                      madm_stream stream);
+int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p_bf16, madm_stream stream);
+int madm_op_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o, int32_t ldo,
+                      int32_t B, int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bstride, int64_t kv_bstride,
+                      int64_t o_bstride, float scale, madm_stream stream);
+int madm_op_pack_linear(const float* w, int32_t N, int32_t K, const float* lora_a, const float* lora_b, int32_t r, float scale,
+                        void* out_bf16, int32_t ldo, madm_stream stream);
+int madm_op_pack_conv(const float* w, int32_t N, int32_t C, int32_t taps, int32_t Cpad, void* out_bf16, int32_t ldo,
+                      madm_stream stream);
+int madm_op_pack_geglu(const float* w, const float* bias, int32_t C4, int32_t K, void* out_bf16, float* out_bias,
+                       madm_stream stream);
+int madm_op_space_to_depth(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, madm_stream stream);
+int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, madm_stream stream);
+int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out_bf16, int32_t* range_flag,
+                         madm_stream stream);
+int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, const float* s, const float* gs, const float* bs,
+                             int32_t has_shortcut_norm, float eps, int32_t B, int32_t HW, int32_t C, float* stats_scratch /*[2,B,32,2]*/,
+                             float* out_nchw, madm_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MADM_B200_H_ */

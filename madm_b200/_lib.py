@@ -1,0 +1,111 @@
+"""ctypes binding of ``libmadm_b200.so`` (C ABI declared in ``include/madm_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C madm_b200/csrc``.  There is no
+fallback: if the shared object is missing, or no sm_100 device is present when a context is created,
+the product path raises.
+"""
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmadm_b200.so")
+
+MADM_OK = 0
+STAGE_VAE, STAGE_UNET, STAGE_PROJ, STAGE_ALL = 1, 2, 4, 7
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU = 0, 1, 2, 3
+
+c_void_p, c_int, c_int32, c_int64, c_float, c_size_t, c_char_p = (
+    C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_char_p)
+
+
+class MadmTensor(C.Structure):
+    _fields_ = [("name", c_char_p), ("data", c_void_p), ("ndim", c_int32), ("shape", c_int64 * 4)]
+
+
+class MadmExtractArgs(C.Structure):
+    _fields_ = [
+        ("B", c_int32), ("stages", c_int32), ("ema", c_int32), ("reserved", c_int32),
+        ("img", c_void_p), ("cond_inputs", c_void_p), ("cond_emb", c_void_p), ("timesteps", c_void_p),
+        ("shared_noise", c_void_p), ("noisy_latents_in", c_void_p),
+        ("out", c_void_p * 4),
+        ("latents", c_void_p), ("noisy_latents", c_void_p), ("taps", c_void_p * 4),
+        ("packed", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("range_flag", c_void_p),
+    ]
+
+
+class MadmGemmSeg(C.Structure):
+    _fields_ = [("a", c_void_p), ("Bt", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("ld", c_int32),
+                ("ntaps", c_int32), ("dx", C.c_int8 * 9), ("dy", C.c_int8 * 9), ("b_off", c_int32 * 9)]
+
+
+class MadmGemmArgs(C.Structure):
+    _fields_ = [
+        ("seg", MadmGemmSeg * 2), ("nseg", c_int32), ("M", c_int32), ("N", c_int32), ("Nw", c_int32), ("ldw", c_int32),
+        ("w", c_void_p), ("bias", c_void_p), ("rowbias", c_void_p), ("rows_per_img", c_int32), ("ld_rowbias", c_int32),
+        ("residual", c_void_p), ("ldr", c_int32), ("out_f32", c_void_p), ("ldo32", c_int32),
+        ("out_bf16", c_void_p), ("ldo16", c_int32), ("act", c_int32), ("alpha", c_float), ("bn", c_int32),
+    ]
+
+
+# every symbol include/madm_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "madm_version": (c_int, []),
+    "madm_last_error": (c_char_p, [c_void_p]),
+    "madm_create": (c_int, [C.POINTER(c_void_p), c_int]),
+    "madm_destroy": (c_int, [c_void_p]),
+    "madm_set_tensors": (c_int, [c_void_p, C.POINTER(MadmTensor), c_int32]),
+    "madm_packed_bytes": (c_size_t, [c_void_p]),
+    "madm_pack_weights": (c_int, [c_void_p, c_void_p, c_char_p, c_float, c_int32, c_void_p]),
+    "madm_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
+    "madm_extract": (c_int, [c_void_p, C.POINTER(MadmExtractArgs), c_void_p]),
+    "madm_launch_count": (c_int, [c_void_p, c_int32, c_int32]),
+    "madm_op_gemm": (c_int, [C.POINTER(MadmGemmArgs), c_void_p]),
+    "madm_op_groupnorm": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_float,
+                                  c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "madm_op_layernorm": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "madm_op_softmax_rows": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "madm_op_attention": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,
+                                  c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, c_float, c_void_p]),
+    "madm_op_pack_linear": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_int32,
+                                    c_void_p]),
+    "madm_op_pack_conv": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_pack_geglu": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "madm_op_space_to_depth": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "madm_op_upsample2x": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "madm_op_image_im2col": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "madm_op_gn_add_relu_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,
+                                         c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+class MadmError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the native library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MadmError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). madm_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, ctx=None, what: str = ""):
+    if rc != MADM_OK:
+        lib = load()
+        msg = lib.madm_last_error(ctx)
+        raise MadmError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,115 @@
+// C-ABI operator-level entry points (include/madm_b200.h, "Operator-level entry points"): thin adapters from the POD
+// argument structs to the kernel launchers, used by the parity tests and by nothing else in the product path.
+#include "../../include/madm_b200.h"
+#include "api_internal.h"
+#include "kernels.h"
+
+#include <string.h>
+
+using namespace madm;
+
+namespace madm {
+static thread_local char g_err[512] = "";
+void set_global_error(const char* msg) {
+  strncpy(g_err, msg ? msg : "", sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+}
+const char* global_error() { return g_err; }
+}  // namespace madm
+
+static int fail(const char* e) {
+  set_global_error(e);
+  return MADM_EINVAL;
+}
+#define RUN(expr)                      \
+  do {                                 \
+    const char* _e = (expr);           \
+    if (_e) return fail(_e);           \
+    return MADM_OK;                    \
+  } while (0)
+
+extern "C" {
+
+int madm_op_gemm(const madm_gemm_args* a, madm_stream stream) {
+  if (!a) return fail("madm_op_gemm: null args");
+  GemmDesc d;
+  d.nseg = a->nseg;
+  for (int s = 0; s < 2; ++s) {
+    const madm_gemm_seg& g = a->seg[s];
+    GemmASeg& t = d.seg[s];
+    t.ptr = g.a; t.Bt = g.Bt; t.H = g.H; t.W = g.W; t.C = g.C; t.ld = g.ld; t.ntaps = g.ntaps;
+    for (int i = 0; i < 9; ++i) { t.dx[i] = g.dx[i]; t.dy[i] = g.dy[i]; t.b_off[i] = g.b_off[i]; }
+  }
+  d.M = a->M; d.N = a->N; d.w = a->w; d.Nw = a->Nw; d.ldw = a->ldw;
+  d.bias = a->bias; d.rowbias = a->rowbias; d.rows_per_img = a->rows_per_img; d.ld_rowbias = a->ld_rowbias;
+  d.residual = a->residual; d.ldr = a->ldr;
+  d.out_f32 = a->out_f32; d.ldo32 = a->ldo32; d.out_bf16 = a->out_bf16; d.ldo16 = a->ldo16;
+  d.act = a->act; d.alpha = a->alpha; d.bn = a->bn;
+  GemmLaunch L;
+  if (const char* e = gemm_prepare(d, &L)) return fail(e);
+  RUN(gemm_launch(L, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_groupnorm(const float* x0, int32_t C0, const float* x1, int32_t C1, int32_t B, int32_t HW, const float* gamma,
+                      const float* beta, float eps, int32_t act, float* stats, void* y, void* raw, madm_stream stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(stats, 0, size_t(B) * 64 * sizeof(float), st) != cudaSuccess) return fail("memset failed");
+  if (const char* e = groupnorm_stats(x0, C0, x1, C1, B, HW, stats, st)) return fail(e);
+  RUN(groupnorm_apply(x0, C0, x1, C1, B, HW, stats, gamma, beta, eps, act, y, raw, st));
+}
+
+int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y,
+                      madm_stream stream) {
+  RUN(layernorm(x, M, C, gamma, beta, eps, y, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p, madm_stream stream) {
+  RUN(softmax_rows(s, R, L, p, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o, int32_t ldo,
+                      int32_t B, int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bs, int64_t kv_bs, int64_t o_bs,
+                      float scale, madm_stream stream) {
+  RUN(flash_attention(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_pack_linear(const float* w, int32_t N, int32_t K, const float* la, const float* lb, int32_t r, float scale, void* out,
+                        int32_t ldo, madm_stream stream) {
+  RUN(pack_linear_weight(w, N, K, la, lb, r, scale, ldo ? ldo : K, out, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_pack_conv(const float* w, int32_t N, int32_t C, int32_t taps, int32_t Cpad, void* out, int32_t ldo, madm_stream stream) {
+  const int Kpad = taps * Cpad;
+  RUN(pack_conv_weight(w, N, C, taps, Cpad, Kpad, ldo ? ldo : Kpad, out, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_pack_geglu(const float* w, const float* bias, int32_t C4, int32_t K, void* out, float* out_bias, madm_stream stream) {
+  RUN(pack_geglu_weight(w, bias, C4, K, out, out_bias, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_space_to_depth(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out, madm_stream stream) {
+  RUN(space_to_depth(x, B, H, W, C, out, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out, madm_stream stream) {
+  RUN(upsample_nearest2x(x, B, H, W, C, out, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out, int32_t* range_flag, madm_stream stream) {
+  RUN(image_im2col(img, B, H, W, out, range_flag, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, const float* s, const float* gs, const float* bs,
+                             int32_t has_shortcut_norm, float eps, int32_t B, int32_t HW, int32_t C, float* stats, float* out,
+                             madm_stream stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(stats, 0, size_t(2) * B * 64 * sizeof(float), st) != cudaSuccess) return fail("memset failed");
+  float* st_a = stats;
+  float* st_s = stats + size_t(B) * 64;
+  if (const char* e = groupnorm_stats(a, C, nullptr, 0, B, HW, st_a, st)) return fail(e);
+  if (has_shortcut_norm)
+    if (const char* e = groupnorm_stats(s, C, nullptr, 0, B, HW, st_s, st)) return fail(e);
+  RUN(gn_add_relu_nchw(a, st_a, ga, ba, s, has_shortcut_norm ? st_s : nullptr, gs, bs, eps, B, HW, C, out, st));
+}
+
+}  // extern "C"

@@ -1,0 +1,1118 @@
+// Host-side engine: owns no model memory.  It (1) keeps a registry of the caller's fp32 parameter pointers under their
+// reference state_dict names, (2) defines the packed bf16 weight arena layout and the pack pass (with LoRA folding),
+// (3) builds, per batch size, a static plan of kernel launches over a caller-provided workspace (TMA tensor maps are
+// encoded once at plan time), and (4) replays the plan on the caller's stream.
+//
+// The SD-1.4 topology below restates the control flow of the reference's own forward re-implementations:
+//   vae_encoder      modeling/meta_arch/ldm_diffusers.py:283-311
+//   add_noise        modeling/meta_arch/ldm_diffusers.py:349-360
+//   diffusion_unet   modeling/meta_arch/ldm_diffusers.py:454-616 (+ :363-451 up blocks, taps 'after' resnet+attn)
+//   forward_features modeling/backbone/feature_extractor.py:367-396 (+ detectron2 BottleneckBlock, norm="GN")
+#include "../../include/madm_b200.h"
+#include "api_internal.h"
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+#include <functional>
+#include <map>
+#include <math.h>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace madm;
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+using Op = std::function<const char*(cudaStream_t)>;
+
+struct ParamRef {
+  const float* p = nullptr;
+  int ndim = 0;
+  int64_t shape[4] = {0, 0, 0, 0};
+  int64_t numel() const {
+    int64_t n = 1;
+    for (int i = 0; i < ndim; ++i) n *= shape[i];
+    return n;
+  }
+};
+
+// ---- packed arena entries
+enum PackKind { PK_CONV, PK_LINEAR, PK_GEGLU, PK_VAE_HEAD, PK_F32_COPY, PK_F32_SUM2, PK_F32_GEGLU_BIAS };
+struct PackEntry {
+  PackKind kind;
+  std::string src, src2, src3, src4;  // parameter names
+  size_t off = 0;                     // byte offset in arena
+  int N = 0, C = 0, taps = 1, Cpad = 0, Kpad = 0, ldo = 0;
+  bool lora = false;                  // LoRA-targeted linear (src is the module path)
+  size_t bias_off = 0;                // for GEGLU / VAE head: fp32 bias region
+};
+
+struct IoBind {  // per-call pointers read by the plan's first/last ops
+  madm_extract_args a;
+};
+
+struct F32T { float* p = nullptr; size_t off = 0; size_t bytes = 0; };
+struct B16T { bf16* p = nullptr; size_t off = 0; size_t bytes = 0; };
+
+// fp32 residual-stream activation, NHWC, optionally with a bf16 copy for consumers that take it as a GEMM operand
+struct Act {
+  F32T f; B16T h;
+  int B = 0, H = 0, W = 0, C = 0;
+  int HW() const { return H * W; }
+  long M() const { return long(B) * H * W; }
+};
+
+struct Plan {
+  int B = 0;
+  bool ema = false;
+  const void* packed = nullptr;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  std::vector<Op> ops;
+  std::vector<int> stage_of;  // stage bit per op
+  std::vector<char> optional; // debug/taps ops that launch only when the caller asks for the extra output
+  std::shared_ptr<IoBind> io = std::make_shared<IoBind>();
+  size_t stats_off = 0, stats_bytes = 0;
+};
+
+}  // namespace
+
+struct madm_ctx {
+  int device = 0;
+  std::string err;
+  std::unordered_map<std::string, ParamRef> params;
+  std::vector<PackEntry> pack;
+  std::map<std::string, size_t> pack_index;  // key -> index in pack
+  size_t packed_bytes = 0;
+  bool layout_done = false;
+  float* alphas_cumprod = nullptr;  // [1000] device
+  std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;  // (B, ema)
+  std::map<int, size_t> ws_bytes_cache;
+};
+
+namespace {
+
+const std::string kUnet = "feature_extractor.ldm_extractor.unet.";
+const std::string kVae = "feature_extractor.ldm_extractor.vae.";
+
+struct BuildError {
+  std::string msg;
+  int code;
+};
+
+// ------------------------------------------------------------------------------------------------ builder
+// One traversal of the model serves three purposes, selected by `mode`:
+//   LAYOUT: register packed-arena entries (B-independent)      SIZE: compute workspace bytes for B
+//   PLAN:   emit launches with real pointers
+enum Mode { LAYOUT, SIZE, PLAN };
+
+struct Builder {
+  madm_ctx* ctx;
+  Mode mode;
+  int B;
+  bool ema;
+  Plan* plan = nullptr;
+  uint8_t* ws = nullptr;
+  const uint8_t* packed = nullptr;
+  int cur_stage = MADM_STAGE_VAE;
+  int n_ops = 0;
+
+  // ---- workspace allocator (first-fit free list, 1 KB granularity); identical sequence in SIZE and PLAN modes
+  struct Blk { size_t off, bytes; };
+  std::vector<Blk> free_list;
+  size_t top = 0, peak = 0;
+  size_t alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    for (size_t i = 0; i < free_list.size(); ++i) {
+      if (free_list[i].bytes >= bytes) {
+        size_t off = free_list[i].off;
+        if (free_list[i].bytes == bytes) free_list.erase(free_list.begin() + i);
+        else { free_list[i].off += bytes; free_list[i].bytes -= bytes; }
+        return off;
+      }
+    }
+    size_t off = top;
+    top += bytes;
+    if (top > peak) peak = top;
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    if (bytes == 0) return;
+    bytes = (bytes + 1023) & ~size_t(1023);
+    if (off + bytes == top) {  // shrink the top, merging trailing free blocks
+      top = off;
+      bool merged = true;
+      while (merged) {
+        merged = false;
+        for (size_t i = 0; i < free_list.size(); ++i)
+          if (free_list[i].off + free_list[i].bytes == top) {
+            top = free_list[i].off;
+            free_list.erase(free_list.begin() + i);
+            merged = true;
+            break;
+          }
+      }
+      return;
+    }
+    // insert + coalesce neighbours
+    Blk nb{off, bytes};
+    for (size_t i = 0; i < free_list.size();) {
+      if (free_list[i].off + free_list[i].bytes == nb.off) { nb.off = free_list[i].off; nb.bytes += free_list[i].bytes; free_list.erase(free_list.begin() + i); }
+      else if (nb.off + nb.bytes == free_list[i].off) { nb.bytes += free_list[i].bytes; free_list.erase(free_list.begin() + i); }
+      else ++i;
+    }
+    free_list.push_back(nb);
+  }
+  F32T f32(size_t n) { F32T t; t.bytes = n * 4; t.off = alloc(t.bytes); t.p = reinterpret_cast<float*>(ws + t.off); return t; }
+  B16T b16(size_t n) { B16T t; t.bytes = n * 2; t.off = alloc(t.bytes); t.p = reinterpret_cast<bf16*>(ws + t.off); return t; }
+  // pinned buffers (feature taps) survive free(): they are consumed by the projection stage
+  std::vector<size_t> pinned;
+  bool is_pinned(size_t off, size_t bytes) const {
+    if (bytes == 0) return false;
+    for (size_t o : pinned) if (o == off) return true;
+    return false;
+  }
+  void pin(const Act& a) {
+    if (a.f.bytes) pinned.push_back(a.f.off);
+    if (a.h.bytes) pinned.push_back(a.h.off);
+  }
+  void free(F32T& t) { if (!is_pinned(t.off, t.bytes)) release(t.off, t.bytes); t.bytes = 0; t.p = nullptr; }
+  void free(B16T& t) { if (!is_pinned(t.off, t.bytes)) release(t.off, t.bytes); t.bytes = 0; t.p = nullptr; }
+  void free(Act& a) { free(a.f); free(a.h); }
+  Act act(int B_, int H, int W, int C, bool with_f32, bool with_b16) {
+    Act a; a.B = B_; a.H = H; a.W = W; a.C = C;
+    if (with_f32) a.f = f32(size_t(a.M()) * C);
+    if (with_b16) a.h = b16(size_t(a.M()) * C);
+    return a;
+  }
+
+  // ---- per-GroupNorm statistics slots ([B,32,2] fp32 each), zeroed by one memset at the start of each stage
+  size_t stats_used = 0;
+  float* stats_base = nullptr;
+  float* new_stats() {
+    float* p = stats_base ? stats_base + stats_used : nullptr;
+    stats_used += size_t(B) * 64;
+    return p;
+  }
+
+  // ---- parameters
+  [[noreturn]] void fail(int code, const std::string& m) { throw BuildError{m, code}; }
+  const ParamRef* find(const std::string& name) {
+    auto it = ctx->params.find(name);
+    return it == ctx->params.end() ? nullptr : &it->second;
+  }
+  const float* param(const std::string& name, int64_t numel = -1) {
+    const ParamRef* r = find(name);
+    if (!r) fail(MADM_ENOTFOUND, "parameter not registered: " + name);
+    if (numel >= 0 && r->numel() != numel) fail(MADM_EINVAL, "parameter has unexpected size: " + name);
+    return r->p;
+  }
+
+  // ---- packed arena
+  size_t pack_reserve(size_t bytes) {
+    size_t off = ctx->packed_bytes;
+    ctx->packed_bytes += (bytes + 1023) & ~size_t(1023);
+    return off;
+  }
+  // returns arena offset of an entry, registering it in LAYOUT mode
+  const PackEntry& entry(const std::string& key, const std::function<PackEntry()>& make) {
+    auto it = ctx->pack_index.find(key);
+    if (it != ctx->pack_index.end()) return ctx->pack[it->second];
+    if (mode != LAYOUT) fail(MADM_ESTATE, "packed entry missing from layout: " + key);
+    ctx->pack.push_back(make());
+    ctx->pack_index[key] = ctx->pack.size() - 1;
+    return ctx->pack.back();
+  }
+  const bf16* pw(size_t off) const { return reinterpret_cast<const bf16*>(packed + off); }
+  const float* pf(size_t off) const { return reinterpret_cast<const float*>(packed + off); }
+
+  // conv weight [N,C,k,k] -> [N, taps*Cpad] (optionally inside a wider row of pitch ldo at column col_off)
+  size_t conv_w(const std::string& name, int N, int C, int taps, int Cpad = 0) {
+    if (Cpad == 0) Cpad = (C + 63) / 64 * 64;
+    const int Kpad = (taps * Cpad + 63) / 64 * 64;
+    return entry("conv:" + name, [&] {
+      PackEntry e; e.kind = PK_CONV; e.src = name + ".weight"; e.N = N; e.C = C; e.taps = taps; e.Cpad = Cpad; e.Kpad = Kpad; e.ldo = Kpad;
+      e.off = pack_reserve(size_t(N) * Kpad * 2);
+      return e;
+    }).off;
+  }
+  // conv3x3 (Cout -> Cout) and 1x1 shortcut (Cin -> Cout) packed side by side: [Cout, 9*Cout + Cin]; bias = b_conv + b_sc
+  struct Fused { size_t w_off, b_off; };
+  Fused conv_plus_shortcut(const std::string& conv, const std::string& sc, int Cout, int Cin) {
+    const int K0 = 9 * Cout, K = K0 + Cin;
+    const PackEntry& e0 = entry("convsc:" + conv, [&] {
+      PackEntry e; e.kind = PK_CONV; e.src = conv + ".weight"; e.N = Cout; e.C = Cout; e.taps = 9; e.Cpad = Cout; e.Kpad = K0; e.ldo = K;
+      e.off = pack_reserve(size_t(Cout) * K * 2);
+      return e;
+    });
+    const size_t w_off = e0.off;
+    entry("convsc_sc:" + conv, [&] {
+      PackEntry e; e.kind = PK_CONV; e.src = sc + ".weight"; e.N = Cout; e.C = Cin; e.taps = 1; e.Cpad = Cin; e.Kpad = Cin; e.ldo = K;
+      e.off = w_off + size_t(K0) * 2;
+      return e;
+    });
+    const size_t b_off = entry("convsc_b:" + conv, [&] {
+      PackEntry e; e.kind = PK_F32_SUM2; e.src = conv + ".bias"; e.src2 = sc + ".bias"; e.N = Cout;
+      e.off = pack_reserve(size_t(Cout) * 4);
+      return e;
+    }).off;
+    return Fused{w_off, b_off};
+  }
+  // a region holding several linears stacked along N (fused QKV, all cross-attn K/V, all time_emb_proj)
+  size_t region(const std::string& key, size_t bytes) {
+    return entry("region:" + key, [&] { PackEntry e; e.kind = PK_F32_COPY; e.N = 0; e.off = pack_reserve(bytes); return e; }).off;
+  }
+  void linear_part(const std::string& module, size_t region_off, int row_off, int N, int K, bool lora) {
+    entry("lin:" + module, [&] {
+      PackEntry e; e.kind = PK_LINEAR; e.src = module; e.N = N; e.C = K; e.ldo = K; e.lora = lora;
+      e.off = region_off + size_t(row_off) * K * 2;
+      return e;
+    });
+  }
+  size_t linear_w(const std::string& module, int N, int K, bool lora) {
+    return entry("lin:" + module, [&] {
+      PackEntry e; e.kind = PK_LINEAR; e.src = module; e.N = N; e.C = K; e.ldo = K; e.lora = lora;
+      e.off = pack_reserve(size_t(N) * K * 2);
+      return e;
+    }).off;
+  }
+  void f32_part(const std::string& name, size_t region_off, int elem_off, int n) {
+    entry("f32:" + name, [&] { PackEntry e; e.kind = PK_F32_COPY; e.src = name; e.N = n; e.off = region_off + size_t(elem_off) * 4; return e; });
+  }
+
+  // ---- op emission
+  void emit(Op op, bool optional = false) {
+    ++n_ops;
+    if (mode == PLAN) {
+      plan->ops.push_back(std::move(op));
+      plan->stage_of.push_back(cur_stage);
+      plan->optional.push_back(optional ? 1 : 0);
+    }
+  }
+  void gemm(const GemmDesc& d) {
+    if (mode != PLAN) { ++n_ops; return; }
+    GemmLaunch L;
+    if (const char* e = gemm_prepare(d, &L)) fail(MADM_EINVAL, std::string(e));
+    emit([L](cudaStream_t st) { return gemm_launch(L, st); });
+  }
+
+  static GemmASeg seg_1x1(const bf16* p, int Bn, int H, int W, int C, int ld = 0) {
+    GemmASeg s; s.ptr = p; s.Bt = Bn; s.H = H; s.W = W; s.C = C; s.ld = ld; s.ntaps = 1;
+    return s;
+  }
+  static GemmASeg seg_3x3(const bf16* p, int Bn, int H, int W, int C) {
+    GemmASeg s; s.ptr = p; s.Bt = Bn; s.H = H; s.W = W; s.C = C; s.ntaps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) { s.dy[ky * 3 + kx] = int8_t(ky - 1); s.dx[ky * 3 + kx] = int8_t(kx - 1); }
+    return s;
+  }
+  static GemmASeg seg_plain(const bf16* p, long M, int K, int ld = 0) {
+    GemmASeg s; s.ptr = p; s.Bt = 1; s.H = 1; s.W = int(M); s.C = K; s.ld = ld; s.ntaps = 1;
+    return s;
+  }
+  // stride-2 3x3 conv over the space-to-depth tensor [4][B][Ho][Wo][C]; pad1: PyTorch padding=1; else F.pad(0,1,0,1)+padding 0
+  static GemmASeg seg_s2(const bf16* p, int Bn, int Ho, int Wo, int C, bool pad1) {
+    GemmASeg s; s.ptr = p; s.Bt = 4 * Bn; s.H = Ho; s.W = Wo; s.C = C; s.ntaps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        int py, dy, px, dx;
+        if (pad1) { py = (ky == 1) ? 0 : 1; dy = (ky == 0) ? -1 : 0; px = (kx == 1) ? 0 : 1; dx = (kx == 0) ? -1 : 0; }
+        else      { py = (ky == 1) ? 1 : 0; dy = (ky == 2) ? 1 : 0;  px = (kx == 1) ? 1 : 0; dx = (kx == 2) ? 1 : 0; }
+        s.dy[ky * 3 + kx] = int8_t(dy); s.dx[ky * 3 + kx] = int8_t(dx); s.b_off[ky * 3 + kx] = (py * 2 + px) * Bn;
+      }
+    return s;
+  }
+
+  // GroupNorm(32) over fp32 NHWC (optionally the channel concat of two sources) -> bf16 (+ raw bf16 copy)
+  void groupnorm(const Act& x0, const Act* x1, const std::string& norm, float eps, int actfn, bf16* y, bf16* raw) {
+    const int C0 = x0.C, C1 = x1 ? x1->C : 0;
+    const float* g = (mode == LAYOUT) ? nullptr : param(norm + ".weight", C0 + C1);
+    const float* b = (mode == LAYOUT) ? nullptr : param(norm + ".bias", C0 + C1);
+    float* stats = new_stats();
+    const float* p0 = x0.f.p; const float* p1 = x1 ? x1->f.p : nullptr;
+    const int Bn = x0.B, HW = x0.HW();
+    emit([=](cudaStream_t st) { return groupnorm_stats(p0, C0, p1, C1, Bn, HW, stats, st); });
+    emit([=](cudaStream_t st) { return groupnorm_apply(p0, C0, p1, C1, Bn, HW, stats, g, b, eps, actfn, y, raw, st); });
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ model pieces
+struct Model {
+  Builder& b;
+  explicit Model(Builder& bb) : b(bb) {}
+  bool dry() const { return b.mode != PLAN; }
+  const float* P(const std::string& n, int64_t numel = -1) { return b.mode == LAYOUT ? nullptr : b.param(n, numel); }
+
+  // ---- time embedding projections of all 22 UNet ResBlocks, stacked along N
+  std::vector<std::pair<std::string, int>> temb_layers;  // (resnet prefix, Cout)
+  std::map<std::string, int> temb_off;
+  int temb_total = 0;
+  F32T temb_all;  // [B, temb_total]
+  // ---- cross-attention K/V of all 16 transformer blocks, stacked along N
+  std::vector<std::pair<std::string, int>> xattn_layers;  // (attn2 prefix, C)
+  std::map<std::string, int> kv_off;
+  int kv_total = 0;
+  B16T kv_all;  // [B*77, kv_total]
+
+  void enumerate_unet() {
+    auto res = [&](const std::string& p, int cout) { temb_layers.push_back({p, cout}); temb_off[p] = temb_total; temb_total += cout; };
+    auto att = [&](const std::string& p, int c) { xattn_layers.push_back({p + ".transformer_blocks.0.attn2", c}); kv_off[p + ".transformer_blocks.0.attn2"] = kv_total; kv_total += 2 * c; };
+    const int ch[4] = {320, 640, 1280, 1280};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 2; ++j) {
+        res(kUnet + "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), ch[i]);
+        if (i < 3) att(kUnet + "down_blocks." + std::to_string(i) + ".attentions." + std::to_string(j), ch[i]);
+      }
+    res(kUnet + "mid_block.resnets.0", 1280);
+    att(kUnet + "mid_block.attentions.0", 1280);
+    res(kUnet + "mid_block.resnets.1", 1280);
+    const int rev[4] = {1280, 1280, 640, 320};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 3; ++j) {
+        res(kUnet + "up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), rev[i]);
+        if (i > 0) att(kUnet + "up_blocks." + std::to_string(i) + ".attentions." + std::to_string(j), rev[i]);
+      }
+  }
+
+  // ---- ResnetBlock2D.  x = channel concat of x0 (and x1).  Returns fp32 (+bf16 copy if want_b16) output.
+  Act resblock(const std::string& p, const Act& x0, const Act* x1, int Cout, float eps, bool has_temb, bool want_b16) {
+    const int Bn = x0.B, H = x0.H, W = x0.W, Cin = x0.C + (x1 ? x1->C : 0);
+    const bool shortcut = Cin != Cout;
+    if (x1 && !shortcut) b.fail(MADM_EINVAL, "resblock: concat input without shortcut");
+    B16T n1 = b.b16(size_t(x0.M()) * Cin);
+    B16T raw; if (shortcut) raw = b.b16(size_t(x0.M()) * Cin);
+    b.groupnorm(x0, x1, p + ".norm1", eps, ACT_SILU, n1.p, shortcut ? raw.p : nullptr);
+    // conv1 (+ bias + time embedding row bias) -> fp32 intermediate
+    Act h1 = b.act(Bn, H, W, Cout, true, false);
+    {
+      GemmDesc d; d.seg[0] = Builder::seg_3x3(n1.p, Bn, H, W, Cin); d.M = int(x0.M()); d.N = Cout;
+      d.w = b.pw(b.conv_w(p + ".conv1", Cout, Cin, 9)); d.Nw = Cout;
+      d.bias = P(p + ".conv1.bias", Cout);
+      if (has_temb) { d.rowbias = temb_all.p ? temb_all.p + temb_off[p] : nullptr; d.ld_rowbias = temb_total; d.rows_per_img = H * W;
+                      if (dry()) d.rowbias = nullptr; }
+      d.out_f32 = h1.f.p; d.ldo32 = Cout;
+      b.gemm(d);
+    }
+    b.free(n1);
+    B16T n2 = b.b16(size_t(x0.M()) * Cout);
+    b.groupnorm(h1, nullptr, p + ".norm2", eps, ACT_SILU, n2.p, nullptr);
+    b.free(h1);
+    Act out = b.act(Bn, H, W, Cout, true, want_b16);
+    {
+      GemmDesc d; d.seg[0] = Builder::seg_3x3(n2.p, Bn, H, W, Cout); d.M = int(x0.M()); d.N = Cout; d.Nw = Cout;
+      if (shortcut) {  // out = conv2(n2) + conv_shortcut(x): one GEMM, K = 9*Cout + Cin
+        Builder::Fused f = b.conv_plus_shortcut(p + ".conv2", p + ".conv_shortcut", Cout, Cin);
+        d.nseg = 2; d.seg[1] = Builder::seg_1x1(raw.p, Bn, H, W, Cin);
+        d.w = b.pw(f.w_off); d.bias = b.pf(f.b_off);
+      } else {
+        d.w = b.pw(b.conv_w(p + ".conv2", Cout, Cout, 9)); d.bias = P(p + ".conv2.bias", Cout);
+        d.residual = x0.f.p; d.ldr = Cout;
+      }
+      d.out_f32 = out.f.p; d.ldo32 = Cout; d.out_bf16 = out.h.p; d.ldo16 = Cout;
+      b.gemm(d);
+    }
+    b.free(n2);
+    if (shortcut) b.free(raw);
+    return out;
+  }
+
+  // ---- Transformer2DModel (one BasicTransformerBlock): returns fp32 (+bf16) output; x is NOT freed
+  Act transformer(const std::string& p, const Act& x, bool want_b16) {
+    const int Bn = x.B, H = x.H, W = x.W, C = x.C;
+    const long M = x.M();
+    const int heads = 8, d_head = C / heads;
+    const std::string tb = p + ".transformer_blocks.0";
+    B16T n = b.b16(size_t(M) * C);
+    b.groupnorm(x, nullptr, p + ".norm", 1e-6f, ACT_NONE, n.p, nullptr);
+    F32T hs = b.f32(size_t(M) * C);
+    { GemmDesc d; d.seg[0] = Builder::seg_1x1(n.p, Bn, H, W, C); d.M = int(M); d.N = C; d.Nw = C;
+      d.w = b.pw(b.conv_w(p + ".proj_in", C, C, 1)); d.bias = P(p + ".proj_in.bias", C); d.out_f32 = hs.p; d.ldo32 = C; b.gemm(d); }
+    b.free(n);
+    auto ln = [&](const std::string& name, bf16* y) {
+      const float* g = P(name + ".weight", C); const float* be = P(name + ".bias", C);
+      const float* src = hs.p; const int Mi = int(M);
+      b.emit([=](cudaStream_t st) { return layernorm(src, Mi, C, g, be, 1e-5f, y, st); });
+    };
+    // --- self attention
+    B16T l1 = b.b16(size_t(M) * C);
+    ln(tb + ".norm1", l1.p);
+    B16T qkv = b.b16(size_t(M) * 3 * C);
+    { const size_t reg = b.region("qkv:" + tb, size_t(3) * C * C * 2);
+      b.linear_part(tb + ".attn1.to_q", reg, 0, C, C, true);
+      b.linear_part(tb + ".attn1.to_k", reg, C, C, C, true);
+      b.linear_part(tb + ".attn1.to_v", reg, 2 * C, C, C, true);
+      GemmDesc d; d.seg[0] = Builder::seg_plain(l1.p, M, C); d.M = int(M); d.N = 3 * C; d.Nw = 3 * C; d.w = b.pw(reg);
+      d.out_bf16 = qkv.p; d.ldo16 = 3 * C; b.gemm(d); }
+    b.free(l1);
+    B16T att = b.b16(size_t(M) * C);
+    { const bf16* q = qkv.p; bf16* o = att.p; const int n_tok = H * W; const float sc = 1.0f / sqrtf(float(d_head));
+      b.emit([=](cudaStream_t st) {
+        return flash_attention(q, 3 * C, q + C, 3 * C, q + 2 * C, 3 * C, o, C, Bn, heads, d_head, n_tok, n_tok, long(n_tok) * 3 * C,
+                               long(n_tok) * 3 * C, long(n_tok) * C, sc, st);
+      }); }
+    b.free(qkv);
+    { GemmDesc d; d.seg[0] = Builder::seg_plain(att.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
+      d.w = b.pw(b.linear_w(tb + ".attn1.to_out.0", C, C, true)); d.bias = lora_bias(tb + ".attn1.to_out.0", C);
+      d.residual = hs.p; d.ldr = C; d.out_f32 = hs.p; d.ldo32 = C; b.gemm(d); }
+    // --- cross attention (K/V precomputed for all layers in kv_all)
+    B16T l2 = b.b16(size_t(M) * C);
+    ln(tb + ".norm2", l2.p);
+    B16T q2 = b.b16(size_t(M) * C);
+    { GemmDesc d; d.seg[0] = Builder::seg_plain(l2.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
+      d.w = b.pw(b.linear_w(tb + ".attn2.to_q", C, C, true)); d.out_bf16 = q2.p; d.ldo16 = C; b.gemm(d); }
+    b.free(l2);
+    { const bf16* q = q2.p; bf16* o = att.p; const int n_tok = H * W; const float sc = 1.0f / sqrtf(float(d_head));
+      const int off = kv_off[tb + ".attn2"]; const bf16* kv = kv_all.p; const int ldkv = kv_total;
+      b.emit([=](cudaStream_t st) {
+        return flash_attention(q, C, kv + off, ldkv, kv + off + C, ldkv, o, C, Bn, heads, d_head, n_tok, 77, long(n_tok) * C,
+                               long(77) * ldkv, long(n_tok) * C, sc, st);
+      }); }
+    b.free(q2);
+    { GemmDesc d; d.seg[0] = Builder::seg_plain(att.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
+      d.w = b.pw(b.linear_w(tb + ".attn2.to_out.0", C, C, true)); d.bias = lora_bias(tb + ".attn2.to_out.0", C);
+      d.residual = hs.p; d.ldr = C; d.out_f32 = hs.p; d.ldo32 = C; b.gemm(d); }
+    b.free(att);
+    // --- feed-forward (GEGLU fused in the first GEMM's epilogue)
+    B16T l3 = b.b16(size_t(M) * C);
+    ln(tb + ".norm3", l3.p);
+    B16T ff = b.b16(size_t(M) * 4 * C);
+    { const PackEntry& e = b.entry("geglu:" + tb, [&] {
+        PackEntry pe; pe.kind = PK_GEGLU; pe.src = tb + ".ff.net.0.proj.weight"; pe.src2 = tb + ".ff.net.0.proj.bias"; pe.N = 4 * C; pe.C = C;
+        pe.off = b.pack_reserve(size_t(8) * C * C * 2); pe.bias_off = b.pack_reserve(size_t(8) * C * 4);
+        return pe; });
+      GemmDesc d; d.seg[0] = Builder::seg_plain(l3.p, M, C); d.M = int(M); d.N = 4 * C; d.Nw = 8 * C; d.w = b.pw(e.off);
+      d.bias = b.pf(e.bias_off); d.act = ACT_GEGLU; d.out_bf16 = ff.p; d.ldo16 = 4 * C; b.gemm(d); }
+    b.free(l3);
+    B16T hsb = b.b16(size_t(M) * C);
+    { GemmDesc d; d.seg[0] = Builder::seg_plain(ff.p, M, 4 * C); d.M = int(M); d.N = C; d.Nw = C;
+      d.w = b.pw(b.linear_w(tb + ".ff.net.2", C, 4 * C, false)); d.bias = P(tb + ".ff.net.2.bias", C);
+      d.residual = hs.p; d.ldr = C; d.out_bf16 = hsb.p; d.ldo16 = C; b.gemm(d); }
+    b.free(ff);
+    b.free(hs);
+    Act out = b.act(Bn, H, W, C, true, want_b16);
+    { GemmDesc d; d.seg[0] = Builder::seg_1x1(hsb.p, Bn, H, W, C); d.M = int(M); d.N = C; d.Nw = C;
+      d.w = b.pw(b.conv_w(p + ".proj_out", C, C, 1)); d.bias = P(p + ".proj_out.bias", C);
+      d.residual = x.f.p; d.ldr = C; d.out_f32 = out.f.p; d.ldo32 = C; d.out_bf16 = out.h.p; d.ldo16 = C; b.gemm(d); }
+    b.free(hsb);
+    return out;
+  }
+
+  // bias of a (possibly LoRA-wrapped) Linear: "<m>.base_layer.bias" if wrapped else "<m>.bias"
+  const float* lora_bias(const std::string& module, int n) {
+    if (b.mode == LAYOUT) return nullptr;
+    if (b.find(module + ".base_layer.bias")) return b.param(module + ".base_layer.bias", n);
+    return b.param(module + ".bias", n);
+  }
+
+  Act downsample(const std::string& p, const Act& x, bool pad1) {
+    const int Bn = x.B, H = x.H, W = x.W, C = x.C;
+    B16T s2d = b.b16(size_t(x.M()) * C);
+    { const float* src = x.f.p; bf16* dst = s2d.p;
+      b.emit([=](cudaStream_t st) { return space_to_depth(src, Bn, H, W, C, dst, st); }); }
+    Act out = b.act(Bn, H / 2, W / 2, C, true, false);
+    { GemmDesc d; d.seg[0] = Builder::seg_s2(s2d.p, Bn, H / 2, W / 2, C, pad1); d.M = int(out.M()); d.N = C; d.Nw = C;
+      d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C; b.gemm(d); }
+    b.free(s2d);
+    return out;
+  }
+
+  Act upsample(const std::string& p, const Act& x) {
+    const int Bn = x.B, H = x.H, W = x.W, C = x.C;
+    B16T up = b.b16(size_t(x.M()) * 4 * C);
+    { const float* src = x.f.p; bf16* dst = up.p;
+      b.emit([=](cudaStream_t st) { return upsample_nearest2x(src, Bn, H, W, C, dst, st); }); }
+    Act out = b.act(Bn, 2 * H, 2 * W, C, true, false);
+    { GemmDesc d; d.seg[0] = Builder::seg_3x3(up.p, Bn, 2 * H, 2 * W, C); d.M = int(out.M()); d.N = C; d.Nw = C;
+      d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C; b.gemm(d); }
+    b.free(up);
+    return out;
+  }
+
+  // ---- VAE mid-block attention (1 head, d = 512, 4096 tokens): QK^T / softmax / PV as three GEMM passes per image
+  Act vae_attention(const std::string& p, const Act& x) {
+    const int Bn = x.B, H = x.H, W = x.W, C = x.C, T = H * W;
+    const long M = x.M();
+    B16T n = b.b16(size_t(M) * C);
+    b.groupnorm(x, nullptr, p + ".group_norm", 1e-6f, ACT_NONE, n.p, nullptr);
+    B16T qk = b.b16(size_t(M) * 2 * C);
+    { const size_t reg = b.region("vae_qk", size_t(2) * C * C * 2);
+      b.linear_part(p + ".to_q", reg, 0, C, C, false);
+      b.linear_part(p + ".to_k", reg, C, C, C, false);
+      const size_t breg = b.region("vae_qk_bias", size_t(2) * C * 4);
+      b.f32_part(p + ".to_q.bias", breg, 0, C);
+      b.f32_part(p + ".to_k.bias", breg, C, C);
+      GemmDesc d; d.seg[0] = Builder::seg_plain(n.p, M, C); d.M = int(M); d.N = 2 * C; d.Nw = 2 * C; d.w = b.pw(reg); d.bias = b.pf(breg);
+      d.out_bf16 = qk.p; d.ldo16 = 2 * C; b.gemm(d); }
+    const size_t wv = b.linear_w(p + ".to_v", C, C, false);
+    B16T o = b.b16(size_t(M) * C);
+    B16T vt = b.b16(size_t(C) * T);
+    F32T S = b.f32(size_t(T) * T);
+    B16T Pm = b.b16(size_t(T) * T);
+    for (int i = 0; i < Bn; ++i) {
+      const bf16* ni = n.p ? n.p + size_t(i) * T * C : nullptr;
+      const bf16* qi = qk.p ? qk.p + size_t(i) * T * 2 * C : nullptr;
+      { // V^T[c, t] = sum_k Wv[c,k] * n[t,k]   (bias added after PV: softmax rows sum to 1)
+        GemmDesc d; d.seg[0] = Builder::seg_plain(b.pw(wv), C, C); d.M = C; d.N = T; d.Nw = T; d.w = ni; d.ldw = C;
+        d.out_bf16 = vt.p; d.ldo16 = T; b.gemm(d); }
+      { GemmDesc d; d.seg[0] = Builder::seg_plain(qi, T, C, 2 * C); d.M = T; d.N = T; d.Nw = T; d.w = qi ? qi + C : nullptr; d.ldw = 2 * C;
+        d.alpha = 1.0f / sqrtf(float(C)); d.out_f32 = S.p; d.ldo32 = T; b.gemm(d); }
+      { const float* s = S.p; bf16* pm = Pm.p;
+        b.emit([=](cudaStream_t st) { return softmax_rows(s, T, T, pm, st); }); }
+      { GemmDesc d; d.seg[0] = Builder::seg_plain(Pm.p, T, T); d.M = T; d.N = C; d.Nw = C; d.w = vt.p; d.ldw = T;
+        d.bias = P(p + ".to_v.bias", C); d.out_bf16 = o.p ? o.p + size_t(i) * T * C : nullptr; d.ldo16 = C; b.gemm(d); }
+    }
+    b.free(Pm); b.free(S); b.free(vt); b.free(qk); b.free(n);
+    Act out = b.act(Bn, H, W, C, true, false);
+    { GemmDesc d; d.seg[0] = Builder::seg_plain(o.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
+      d.w = b.pw(b.linear_w(p + ".to_out.0", C, C, false)); d.bias = P(p + ".to_out.0.bias", C);
+      d.residual = x.f.p; d.ldr = C; d.out_f32 = out.f.p; d.ldo32 = C; b.gemm(d); }
+    b.free(o);
+    return out;
+  }
+
+  // persistent cross-stage buffers
+  Act enc_tap;           // [B,128,128,512] fp32 + bf16
+  F32T latents;          // [B*4096, 4]
+  Act unet_tap[3];       // 64x64x320, 32x32x640, 16x16x1280 (fp32 + bf16)
+
+  void nchw_debug(const Act& a, int which) {  // taps[which] if requested
+    if (dry()) { b.emit(nullptr, true); return; }
+    std::shared_ptr<IoBind> io = b.plan->io;
+    const float* src = a.f.p; const int Bn = a.B, HW = a.HW(), C = a.C;
+    b.emit([=](cudaStream_t st) -> const char* {
+      float* dst = io->a.taps[which];
+      return dst ? nhwc_to_nchw(src, Bn, HW, C, dst, st) : nullptr;
+    }, true);
+  }
+
+  // =========================================================================== VAE encoder
+  void build_vae() {
+    b.cur_stage = MADM_STAGE_VAE;
+    const int Bn = b.B, R = 512;
+    const std::string e = kVae + "encoder.";
+    std::shared_ptr<IoBind> io = dry() ? nullptr : b.plan->io;
+    B16T col = b.b16(size_t(Bn) * R * R * 64);
+    if (dry()) b.emit(nullptr);
+    else { bf16* dst = col.p;
+      b.emit([=](cudaStream_t st) { return image_im2col(io->a.img, Bn, R, R, dst, io->a.range_flag, st); }); }
+    Act x = b.act(Bn, R, R, 128, true, false);
+    { GemmDesc d; d.seg[0] = Builder::seg_plain(col.p, long(Bn) * R * R, 64); d.M = Bn * R * R; d.N = 128; d.Nw = 128;
+      d.w = b.pw(b.conv_w(e + "conv_in", 128, 3, 9, /*Cpad=*/3)); d.bias = P(e + "conv_in.bias", 128); d.out_f32 = x.f.p; d.ldo32 = 128; b.gemm(d); }
+    b.free(col);
+    const int ch[4] = {128, 256, 512, 512};
+    int index = 0;
+    for (int i = 0; i < 4; ++i) {
+      for (int j = 0; j < 2; ++j) {
+        const std::string p = e + "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j);
+        ++index;
+        const bool is_tap = index == 5;  // encoder_block_indices=[5] (counter increments before the check, :289-293)
+        Act y = resblock(p, x, nullptr, ch[i], 1e-6f, false, is_tap);
+        b.free(x);
+        x = y;
+        if (is_tap) {  // keep the tap alive for the projection stage
+          enc_tap = x;
+          b.pin(enc_tap);
+          nchw_debug(enc_tap, 0);
+        }
+      }
+      if (i < 3) {
+        Act y = downsample(e + "down_blocks." + std::to_string(i) + ".downsamplers.0", x, /*pad1=*/false);
+        b.free(x);
+        x = y;
+      }
+    }
+    {
+      Act y = resblock(e + "mid_block.resnets.0", x, nullptr, 512, 1e-6f, false, false); b.free(x); x = y;
+      y = vae_attention(e + "mid_block.attentions.0", x); b.free(x); x = y;
+      y = resblock(e + "mid_block.resnets.1", x, nullptr, 512, 1e-6f, false, false); b.free(x); x = y;
+    }
+    B16T n = b.b16(size_t(x.M()) * 512);
+    b.groupnorm(x, nullptr, e + "conv_norm_out", 1e-6f, ACT_SILU, n.p, nullptr);
+    latents = b.f32(size_t(x.M()) * 4);
+    { const PackEntry& pe = b.entry("vae_head", [&] {
+        PackEntry q; q.kind = PK_VAE_HEAD; q.src = e + "conv_out.weight"; q.src2 = e + "conv_out.bias"; q.src3 = kVae + "quant_conv.weight";
+        q.src4 = kVae + "quant_conv.bias"; q.C = 512; q.off = b.pack_reserve(size_t(16) * 9 * 512 * 2); q.bias_off = b.pack_reserve(64);
+        return q; });
+      GemmDesc d; d.seg[0] = Builder::seg_3x3(n.p, Bn, x.H, x.W, 512); d.M = int(x.M()); d.N = 4; d.Nw = 16; d.w = b.pw(pe.off);
+      d.bias = b.pf(pe.bias_off); d.out_f32 = latents.p; d.ldo32 = 4; d.bn = 16; b.gemm(d); }
+    b.free(n);
+    b.free(x);
+    if (dry()) b.emit(nullptr, true);
+    else { const float* src = latents.p;
+      b.emit([=](cudaStream_t st) -> const char* {
+        return io->a.latents ? nhwc_to_nchw(src, Bn, 64 * 64, 4, io->a.latents, st) : nullptr; }, true); }
+  }
+
+  // =========================================================================== UNet
+  void build_unet() {
+    b.cur_stage = MADM_STAGE_UNET;
+    const int Bn = b.B;
+    std::shared_ptr<IoBind> io = dry() ? nullptr : b.plan->io;
+    // ---- q-sample (or external noisy latents) + conv_in im2col
+    F32T noisy = b.f32(size_t(Bn) * 4096 * 4);
+    B16T col = b.b16(size_t(Bn) * 4096 * 64);
+    if (dry()) { b.emit(nullptr); b.emit(nullptr); }
+    else {
+      const float* lat = latents.p; float* nz = noisy.p; bf16* cdst = col.p; const float* ac = b.ctx->alphas_cumprod;
+      b.emit([=](cudaStream_t st) -> const char* {
+        if (io->a.noisy_latents_in) return nchw_to_nhwc4(io->a.noisy_latents_in, Bn, 4096, nz, st);
+        return qsample(lat, io->a.shared_noise, io->a.timesteps, ac, Bn, 4096, nz, io->a.noisy_latents, st);
+      });
+      b.emit([=](cudaStream_t st) { return latent_im2col(nz, Bn, 64, 64, cdst, st); });
+    }
+    // ---- time embedding: sinusoid -> linear_1 -> SiLU -> linear_2 (+ cond_emb) -> SiLU -> all 22 time_emb_proj at once
+    B16T sinus = b.b16(size_t(Bn) * 320);
+    if (dry()) b.emit(nullptr);
+    else { bf16* dst = sinus.p; b.emit([=](cudaStream_t st) { return timestep_sinusoid(io->a.timesteps, Bn, dst, st); }); }
+    B16T e1 = b.b16(size_t(Bn) * 1280);
+    { GemmDesc d; d.seg[0] = Builder::seg_plain(sinus.p, Bn, 320); d.M = Bn; d.N = 1280; d.Nw = 1280;
+      d.w = b.pw(b.linear_w(kUnet + "time_embedding.linear_1", 1280, 320, false)); d.bias = P(kUnet + "time_embedding.linear_1.bias", 1280);
+      d.act = ACT_SILU; d.out_bf16 = e1.p; d.ldo16 = 1280; b.gemm(d); }
+    F32T emb = b.f32(size_t(Bn) * 1280);
+    { GemmDesc d; d.seg[0] = Builder::seg_plain(e1.p, Bn, 1280); d.M = Bn; d.N = 1280; d.Nw = 1280;
+      d.w = b.pw(b.linear_w(kUnet + "time_embedding.linear_2", 1280, 1280, false)); d.bias = P(kUnet + "time_embedding.linear_2.bias", 1280);
+      d.out_f32 = emb.p; d.ldo32 = 1280; b.gemm(d); }
+    B16T emb_act = b.b16(size_t(Bn) * 1280);
+    if (dry()) b.emit(nullptr);
+    else { const float* src = emb.p; bf16* dst = emb_act.p;
+      b.emit([=](cudaStream_t st) { return f32_to_bf16(src, io->a.cond_emb, long(Bn) * 1280, ACT_SILU, dst, nullptr, st); }); }
+    temb_all = b.f32(size_t(Bn) * temb_total);
+    { const size_t reg = b.region("temb_w", size_t(temb_total) * 1280 * 2);
+      const size_t breg = b.region("temb_b", size_t(temb_total) * 4);
+      for (auto& l : temb_layers) {
+        b.linear_part(l.first + ".time_emb_proj", reg, temb_off[l.first], l.second, 1280, false);
+        b.f32_part(l.first + ".time_emb_proj.bias", breg, temb_off[l.first], l.second);
+      }
+      GemmDesc d; d.seg[0] = Builder::seg_plain(emb_act.p, Bn, 1280); d.M = Bn; d.N = temb_total; d.Nw = temb_total; d.w = b.pw(reg);
+      d.bias = b.pf(breg); d.out_f32 = temb_all.p; d.ldo32 = temb_total; b.gemm(d); }
+    b.free(sinus); b.free(e1); b.free(emb); b.free(emb_act);
+    // ---- cross-attention K/V of every transformer block in one GEMM
+    B16T ctx16 = b.b16(size_t(Bn) * 77 * 768);
+    if (dry()) b.emit(nullptr);
+    else { bf16* dst = ctx16.p;
+      b.emit([=](cudaStream_t st) { return f32_to_bf16(io->a.cond_inputs, nullptr, long(Bn) * 77 * 768, ACT_NONE, dst, nullptr, st); }); }
+    kv_all = b.b16(size_t(Bn) * 77 * kv_total);
+    { const size_t reg = b.region("xattn_kv", size_t(kv_total) * 768 * 2);
+      for (auto& l : xattn_layers) {
+        b.linear_part(l.first + ".to_k", reg, kv_off[l.first], l.second, 768, true);
+        b.linear_part(l.first + ".to_v", reg, kv_off[l.first] + l.second, l.second, 768, true);
+      }
+      GemmDesc d; d.seg[0] = Builder::seg_plain(ctx16.p, long(Bn) * 77, 768); d.M = Bn * 77; d.N = kv_total; d.Nw = kv_total; d.w = b.pw(reg);
+      d.out_bf16 = kv_all.p; d.ldo16 = kv_total; b.gemm(d); }
+    b.free(ctx16);
+    // ---- conv_in
+    Act x = b.act(Bn, 64, 64, 320, true, false);
+    { GemmDesc d; d.seg[0] = Builder::seg_plain(col.p, long(Bn) * 4096, 64); d.M = Bn * 4096; d.N = 320; d.Nw = 320;
+      d.w = b.pw(b.conv_w(kUnet + "conv_in", 320, 4, 9, /*Cpad=*/4)); d.bias = P(kUnet + "conv_in.bias", 320); d.out_f32 = x.f.p; d.ldo32 = 320; b.gemm(d); }
+    b.free(col); b.free(noisy);
+    // ---- down path
+    std::vector<Act> skips;
+    skips.push_back(x);
+    const int ch[4] = {320, 640, 1280, 1280};
+    for (int i = 0; i < 4; ++i) {
+      const std::string blk = kUnet + "down_blocks." + std::to_string(i);
+      for (int j = 0; j < 2; ++j) {
+        Act y = resblock(blk + ".resnets." + std::to_string(j), x, nullptr, ch[i], 1e-5f, true, false);
+        if (i < 3) { Act z = transformer(blk + ".attentions." + std::to_string(j), y, false); b.free(y); y = z; }
+        x = y;
+        skips.push_back(x);
+      }
+      if (i < 3) { x = downsample(blk + ".downsamplers.0", x, /*pad1=*/true); skips.push_back(x); }
+    }
+    // ---- mid
+    {
+      Act y = resblock(kUnet + "mid_block.resnets.0", x, nullptr, 1280, 1e-5f, true, false);
+      Act z = transformer(kUnet + "mid_block.attentions.0", y, false); b.free(y);
+      x = resblock(kUnet + "mid_block.resnets.1", z, nullptr, 1280, 1e-5f, true, false); b.free(z);
+      // (the mid input is skips.back(); it is freed when popped below)
+    }
+    // ---- up path; taps after layers 5, 8, 11 (unet_block_indices=[5,8,11], type 'after')
+    const int rev[4] = {1280, 1280, 640, 320};
+    int idx = 0;
+    for (int i = 0; i < 4; ++i) {
+      const std::string blk = kUnet + "up_blocks." + std::to_string(i);
+      for (int j = 0; j < 3; ++j) {
+        Act skip = skips.back(); skips.pop_back();
+        const bool is_tap = (idx == 5 || idx == 8 || idx == 11);
+        Act y = resblock(blk + ".resnets." + std::to_string(j), x, &skip, rev[i], 1e-5f, true, is_tap && i == 0);
+        b.free(x); b.free(skip);
+        if (i > 0) { Act z = transformer(blk + ".attentions." + std::to_string(j), y, is_tap); b.free(y); y = z; }
+        x = y;
+        if (is_tap) {
+          const int t = (idx == 5) ? 2 : (idx == 8 ? 1 : 0);
+          unet_tap[t] = x;
+          b.pin(x);
+          nchw_debug(x, 1 + t);
+        }
+        ++idx;
+      }
+      if (i < 3) {
+        Act y = upsample(blk + ".upsamplers.0", x);
+        b.free(x);  // (pinned taps stay alive for the projection stage)
+        x = y;
+      }
+    }
+    b.free(temb_all);
+    b.free(kv_all);
+  }
+
+  static const char* nchw_to_nhwc4(const float* src, int Bn, int HW, float* dst, cudaStream_t st);
+
+  // =========================================================================== feature projections
+  void build_proj() {
+    b.cur_stage = MADM_STAGE_PROJ;
+    std::shared_ptr<IoBind> io = dry() ? nullptr : b.plan->io;
+    const std::string root = b.ema ? "ema_feature_projections." : "feature_projections.";
+    const Act* taps[4] = {&enc_tap, &unet_tap[0], &unet_tap[1], &unet_tap[2]};
+    for (int i = 0; i < 4; ++i) {
+      const Act& x = *taps[i];
+      const std::string p = root + std::to_string(i) + ".0.";
+      const int Bn = x.B, H = x.H, W = x.W, Cin = x.C, Cb = 128, Cout = 512;
+      const long M = x.M();
+      const bool shortcut = Cin != Cout;
+      auto gn = [&](const F32T& src, const std::string& norm, int C, bf16* y) {
+        Act a; a.f = src; a.B = Bn; a.H = H; a.W = W; a.C = C;
+        b.groupnorm(a, nullptr, norm, 1e-5f, ACT_RELU, y, nullptr);
+      };
+      F32T c1 = b.f32(size_t(M) * Cb);
+      { GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cin); d.M = int(M); d.N = Cb; d.Nw = Cb;
+        d.w = b.pw(b.conv_w(p + "conv1", Cb, Cin, 1)); d.out_f32 = c1.p; d.ldo32 = Cb; b.gemm(d); }
+      B16T a1 = b.b16(size_t(M) * Cb);
+      gn(c1, p + "conv1.norm", Cb, a1.p);
+      b.free(c1);
+      F32T c2 = b.f32(size_t(M) * Cb);
+      { GemmDesc d; d.seg[0] = Builder::seg_3x3(a1.p, Bn, H, W, Cb); d.M = int(M); d.N = Cb; d.Nw = Cb;
+        d.w = b.pw(b.conv_w(p + "conv2", Cb, Cb, 9)); d.out_f32 = c2.p; d.ldo32 = Cb; b.gemm(d); }
+      b.free(a1);
+      B16T a2 = b.b16(size_t(M) * Cb);
+      gn(c2, p + "conv2.norm", Cb, a2.p);
+      b.free(c2);
+      F32T c3 = b.f32(size_t(M) * Cout);
+      { GemmDesc d; d.seg[0] = Builder::seg_1x1(a2.p, Bn, H, W, Cb); d.M = int(M); d.N = Cout; d.Nw = Cout;
+        d.w = b.pw(b.conv_w(p + "conv3", Cout, Cb, 1)); d.out_f32 = c3.p; d.ldo32 = Cout; b.gemm(d); }
+      b.free(a2);
+      F32T sc;
+      if (shortcut) {
+        sc = b.f32(size_t(M) * Cout);
+        GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cin); d.M = int(M); d.N = Cout; d.Nw = Cout;
+        d.w = b.pw(b.conv_w(p + "shortcut", Cout, Cin, 1)); d.out_f32 = sc.p; d.ldo32 = Cout; b.gemm(d);
+      }
+      float* st3 = b.new_stats();
+      float* sts = shortcut ? b.new_stats() : nullptr;
+      const float* c3p = c3.p; const float* scp = shortcut ? sc.p : x.f.p; const int HW = H * W;
+      b.emit([=](cudaStream_t st) { return groupnorm_stats(c3p, Cout, nullptr, 0, Bn, HW, st3, st); });
+      if (shortcut) b.emit([=](cudaStream_t st) { return groupnorm_stats(scp, Cout, nullptr, 0, Bn, HW, sts, st); });
+      const float* g3 = P(p + "conv3.norm.weight", Cout); const float* b3 = P(p + "conv3.norm.bias", Cout);
+      const float* gs = shortcut ? P(p + "shortcut.norm.weight", Cout) : nullptr;
+      const float* bs = shortcut ? P(p + "shortcut.norm.bias", Cout) : nullptr;
+      if (dry()) b.emit(nullptr);
+      else b.emit([=](cudaStream_t st) -> const char* {
+        float* dst = io->a.out[i];
+        if (!dst) return "madm_extract: output pointer is null";
+        return gn_add_relu_nchw(c3p, st3, g3, b3, scp, sts, gs, bs, 1e-5f, Bn, HW, Cout, dst, st);
+      });
+      b.free(c3);
+      if (shortcut) b.free(sc);
+    }
+  }
+
+  void build_all() {
+    enumerate_unet();
+    build_vae();
+    build_unet();
+    build_proj();
+  }
+};
+
+__global__ void nchw_to_nhwc4_kernel(const float* __restrict__ src, int Bn, int HW, float* __restrict__ dst) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= long(Bn) * HW) return;
+  const int p = int(i % HW), bb = int(i / HW);
+  const float* s = src + size_t(bb) * 4 * HW + p;
+  *reinterpret_cast<float4*>(dst + i * 4) = make_float4(s[0], s[HW], s[2 * HW], s[3 * HW]);
+}
+const char* Model::nchw_to_nhwc4(const float* src, int Bn, int HW, float* dst, cudaStream_t st) {
+  const long total = long(Bn) * HW;
+  nchw_to_nhwc4_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(src, Bn, HW, dst);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "nchw_to_nhwc4 launch failed";
+}
+
+__global__ void f32_sum2_kernel(const float* a, const float* b2, int n, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + b2[i];
+}
+
+int set_err(madm_ctx* ctx, int code, const std::string& m) {
+  if (ctx) ctx->err = m;
+  set_global_error(m.c_str());
+  return code;
+}
+
+// Runs the traversal in a dry mode; returns workspace bytes (peak + stats region) and op count.
+int dry_run(madm_ctx* ctx, Mode mode, int B, size_t* ws_bytes, int* n_ops) {
+  Builder bld{ctx, mode, B, false};
+  Model m(bld);
+  try {
+    m.build_all();
+  } catch (const BuildError& e) {
+    return set_err(ctx, e.code, e.msg);
+  }
+  if (ws_bytes) *ws_bytes = bld.peak + ((bld.stats_used * 4 + 1023) & ~size_t(1023)) + 1024;
+  if (n_ops) *n_ops = bld.n_ops;
+  return MADM_OK;
+}
+
+int ensure_layout(madm_ctx* ctx) {
+  if (ctx->layout_done) return MADM_OK;
+  ctx->pack.clear(); ctx->pack_index.clear(); ctx->packed_bytes = 0;
+  int rc = dry_run(ctx, LAYOUT, 1, nullptr, nullptr);
+  if (rc != MADM_OK) return rc;
+  // EMA projection twins share the layout pass (registered only if the caller provided them)
+  if (ctx->params.count("ema_feature_projections.0.0.conv1.weight")) {
+    Builder bld{ctx, LAYOUT, 1, true};
+    Model m(bld);
+    try {
+      m.enumerate_unet();
+      // projections need tap shapes only
+      m.enc_tap.B = 1; m.enc_tap.H = 128; m.enc_tap.W = 128; m.enc_tap.C = 512;
+      const int hw[3] = {64, 32, 16}, cc[3] = {320, 640, 1280};
+      for (int i = 0; i < 3; ++i) { m.unet_tap[i].B = 1; m.unet_tap[i].H = hw[i]; m.unet_tap[i].W = hw[i]; m.unet_tap[i].C = cc[i]; }
+      m.build_proj();
+    } catch (const BuildError& e) {
+      return set_err(ctx, e.code, e.msg);
+    }
+  }
+  ctx->layout_done = true;
+  return MADM_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int madm_version(void) { return MADM_VERSION; }
+
+const char* madm_last_error(const madm_ctx* ctx) { return ctx ? ctx->err.c_str() : global_error(); }
+
+int madm_create(madm_ctx** out, int device) {
+  if (!out) return set_err(nullptr, MADM_EINVAL, "madm_create: null out");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_err(nullptr, MADM_ECUDA, "madm_create: no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return set_err(nullptr, MADM_EINVAL, "madm_create: bad device index");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return set_err(nullptr, MADM_ECUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10) return set_err(nullptr, MADM_ECUDA, "madm_create: device is not sm_100 (B200); kernels are built for sm_100a only");
+  if (cudaSetDevice(device) != cudaSuccess) return set_err(nullptr, MADM_ECUDA, "cudaSetDevice failed");
+  std::unique_ptr<madm_ctx> c(new madm_ctx());
+  c->device = device;
+  // DDPM alphas_cumprod (scaled_linear 0.00085..0.012, 1000 steps; fp32 like DDPMScheduler) — SURVEY Appendix A.3
+  std::vector<float> ac(1000);
+  {
+    const float s0 = sqrtf(0.00085f), s1 = sqrtf(0.012f);
+    float prod = 1.0f;
+    for (int i = 0; i < 1000; ++i) {
+      const float step = (s1 - s0) / 999.0f;
+      // torch.linspace computes the upper half from the end point for symmetry
+      const float v = (i < 500) ? s0 + step * float(i) : s1 - step * float(999 - i);
+      const float beta = v * v;
+      prod *= (1.0f - beta);
+      ac[i] = prod;
+    }
+  }
+  if (cudaMalloc(&c->alphas_cumprod, 1000 * sizeof(float)) != cudaSuccess) return set_err(nullptr, MADM_ECUDA, "cudaMalloc failed");
+  if (cudaMemcpy(c->alphas_cumprod, ac.data(), 1000 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+    return set_err(nullptr, MADM_ECUDA, "cudaMemcpy failed");
+  *out = c.release();
+  return MADM_OK;
+}
+
+int madm_destroy(madm_ctx* ctx) {
+  if (!ctx) return MADM_OK;
+  if (ctx->alphas_cumprod) cudaFree(ctx->alphas_cumprod);
+  delete ctx;
+  return MADM_OK;
+}
+
+int madm_set_tensors(madm_ctx* ctx, const madm_tensor* named, int32_t n) {
+  if (!ctx || (!named && n > 0)) return set_err(ctx, MADM_EINVAL, "madm_set_tensors: null argument");
+  for (int i = 0; i < n; ++i) {
+    const madm_tensor& t = named[i];
+    if (!t.name || !t.data || t.ndim < 0 || t.ndim > 4) return set_err(ctx, MADM_EINVAL, "madm_set_tensors: bad tensor record");
+    ParamRef r;
+    r.p = static_cast<const float*>(t.data);
+    r.ndim = t.ndim;
+    for (int k = 0; k < t.ndim; ++k) r.shape[k] = t.shape[k];
+    const bool is_new = ctx->params.find(t.name) == ctx->params.end();
+    ctx->params[t.name] = r;
+    if (is_new && ctx->layout_done) {  // model changed shape (e.g. adapters / EMA twins added): rebuild layout and plans
+      ctx->layout_done = false;
+    }
+  }
+  ctx->plans.clear();  // plans capture parameter pointers
+  return MADM_OK;
+}
+
+size_t madm_packed_bytes(madm_ctx* ctx) {
+  if (!ctx) return 0;
+  if (ensure_layout(ctx) != MADM_OK) return 0;
+  return ctx->packed_bytes;
+}
+
+int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float scale, int32_t lora_only, madm_stream stream) {
+  if (!ctx || !packed) return set_err(ctx, MADM_EINVAL, "madm_pack_weights: null argument");
+  int rc = ensure_layout(ctx);
+  if (rc != MADM_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* base = static_cast<uint8_t*>(packed);
+  const std::string ad = adapter ? adapter : "";
+  auto get = [&](const std::string& name) -> const ParamRef* {
+    auto it = ctx->params.find(name);
+    return it == ctx->params.end() ? nullptr : &it->second;
+  };
+  for (const PackEntry& e : ctx->pack) {
+    const char* err = nullptr;
+    if (lora_only && !(e.kind == PK_LINEAR && e.lora)) continue;
+    switch (e.kind) {
+      case PK_CONV: {
+        const ParamRef* w = get(e.src);
+        if (!w) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
+        if (w->numel() != int64_t(e.N) * e.C * e.taps) return set_err(ctx, MADM_EINVAL, "unexpected shape: " + e.src);
+        err = pack_conv_weight(w->p, e.N, e.C, e.taps, e.Cpad, e.Kpad, e.ldo, base + e.off, st);
+        break;
+      }
+      case PK_LINEAR: {
+        const ParamRef* w = get(e.src + ".base_layer.weight");
+        const bool wrapped = w != nullptr;
+        if (!w) w = get(e.src + ".weight");
+        if (!w) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src + ".weight");
+        if (w->numel() != int64_t(e.N) * e.C) return set_err(ctx, MADM_EINVAL, "unexpected shape: " + e.src);
+        const float *la = nullptr, *lb = nullptr;
+        int r = 0;
+        if (wrapped && !ad.empty()) {
+          const ParamRef* A = get(e.src + ".lora_A." + ad + ".weight");
+          const ParamRef* Bm = get(e.src + ".lora_B." + ad + ".weight");
+          if (!A || !Bm) return set_err(ctx, MADM_ENOTFOUND, "LoRA adapter '" + ad + "' not registered for " + e.src);
+          r = int(A->shape[0]);
+          if (A->shape[1] != e.C || Bm->shape[0] != e.N || Bm->shape[1] != r) return set_err(ctx, MADM_EINVAL, "LoRA shape mismatch: " + e.src);
+          la = A->p; lb = Bm->p;
+        }
+        err = pack_linear_weight(w->p, e.N, e.C, la, lb, r, scale, e.ldo, base + e.off, st);
+        break;
+      }
+      case PK_GEGLU: {
+        const ParamRef* w = get(e.src); const ParamRef* bb = get(e.src2);
+        if (!w || !bb) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
+        err = pack_geglu_weight(w->p, bb->p, e.N, e.C, base + e.off, reinterpret_cast<float*>(base + e.bias_off), st);
+        break;
+      }
+      case PK_VAE_HEAD: {
+        const ParamRef *w = get(e.src), *b1 = get(e.src2), *wq = get(e.src3), *bq = get(e.src4);
+        if (!w || !b1 || !wq || !bq) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
+        err = pack_vae_latent_head(w->p, b1->p, wq->p, bq->p, 0.18215f, e.C, base + e.off, reinterpret_cast<float*>(base + e.bias_off), st);
+        break;
+      }
+      case PK_F32_COPY: {
+        if (e.N == 0) break;  // pure region reservation
+        const ParamRef* s = get(e.src);
+        if (!s) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
+        if (cudaMemcpyAsync(base + e.off, s->p, size_t(e.N) * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) err = "cudaMemcpyAsync failed";
+        break;
+      }
+      case PK_F32_SUM2: {
+        const ParamRef *a = get(e.src), *b2 = get(e.src2);
+        if (!a || !b2) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
+        f32_sum2_kernel<<<(e.N + 255) / 256, 256, 0, st>>>(a->p, b2->p, e.N, reinterpret_cast<float*>(base + e.off));
+        if (cudaGetLastError() != cudaSuccess) err = "f32_sum2 launch failed";
+        break;
+      }
+      default: break;
+    }
+    if (err) return set_err(ctx, MADM_ECUDA, err);
+  }
+  return MADM_OK;
+}
+
+size_t madm_workspace_bytes(madm_ctx* ctx, int32_t B) {
+  if (!ctx || B < 1) return 0;
+  if (ensure_layout(ctx) != MADM_OK) return 0;
+  auto it = ctx->ws_bytes_cache.find(B);
+  if (it != ctx->ws_bytes_cache.end()) return it->second;
+  size_t bytes = 0;
+  if (dry_run(ctx, SIZE, B, &bytes, nullptr) != MADM_OK) return 0;
+  ctx->ws_bytes_cache[B] = bytes;
+  return bytes;
+}
+
+int madm_launch_count(madm_ctx* ctx, int32_t B, int32_t stages) {
+  if (!ctx || B < 1) return -1;
+  auto it = ctx->plans.find({B, 0});
+  if (it == ctx->plans.end()) it = ctx->plans.find({B, 1});
+  if (it == ctx->plans.end()) return -1;
+  int n = 0;
+  for (size_t i = 0; i < it->second->ops.size(); ++i)
+    if ((it->second->stage_of[i] & stages) && it->second->ops[i] && !it->second->optional[i]) ++n;
+  return n + 1;  // + the statistics memset
+}
+
+int madm_extract(madm_ctx* ctx, const madm_extract_args* a, madm_stream stream) {
+  if (!ctx || !a) return set_err(ctx, MADM_EINVAL, "madm_extract: null argument");
+  if (a->B < 1) return set_err(ctx, MADM_EINVAL, "madm_extract: B must be >= 1");
+  if (!a->packed || !a->workspace) return set_err(ctx, MADM_ESTATE, "madm_extract: packed arena and workspace are required");
+  if ((a->stages & MADM_STAGE_VAE) && !a->img) return set_err(ctx, MADM_EINVAL, "madm_extract: img is null");
+  if ((a->stages & MADM_STAGE_UNET) && (!a->cond_inputs || !a->cond_emb || !a->timesteps || (!a->shared_noise && !a->noisy_latents_in)))
+    return set_err(ctx, MADM_EINVAL, "madm_extract: conditioning / timesteps / shared_noise are required for the UNet stage");
+  int rc = ensure_layout(ctx);
+  if (rc != MADM_OK) return rc;
+  const size_t need = madm_workspace_bytes(ctx, a->B);
+  if (need == 0) return MADM_EINVAL;
+  if (a->workspace_bytes < need) return set_err(ctx, MADM_ENOMEM, "madm_extract: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  const std::pair<int, int> key{a->B, a->ema ? 1 : 0};
+  Plan* plan = nullptr;
+  auto it = ctx->plans.find(key);
+  if (it != ctx->plans.end() && it->second->packed == a->packed && it->second->ws == a->workspace) plan = it->second.get();
+  if (!plan) {
+    std::unique_ptr<Plan> np(new Plan());
+    np->B = a->B; np->ema = a->ema != 0; np->packed = a->packed; np->ws = a->workspace; np->ws_bytes = a->workspace_bytes;
+    Builder bld{ctx, PLAN, a->B, a->ema != 0};
+    bld.plan = np.get();
+    bld.packed = static_cast<const uint8_t*>(a->packed);
+    // statistics slots live at the start of the workspace; activations after them
+    size_t total = 0; int nops = 0;
+    {
+      Builder probe{ctx, SIZE, a->B, a->ema != 0};
+      Model pm(probe);
+      try { pm.build_all(); } catch (const BuildError& e) { return set_err(ctx, e.code, e.msg); }
+      total = probe.stats_used; nops = probe.n_ops;
+      (void)nops;
+    }
+    np->stats_off = 0;
+    np->stats_bytes = (total * 4 + 1023) & ~size_t(1023);
+    bld.stats_base = reinterpret_cast<float*>(static_cast<uint8_t*>(a->workspace));
+    bld.ws = static_cast<uint8_t*>(a->workspace) + np->stats_bytes;
+    Model m(bld);
+    try {
+      m.build_all();
+    } catch (const BuildError& e) {
+      return set_err(ctx, e.code, e.msg);
+    }
+    if (np->stats_bytes + bld.peak > a->workspace_bytes) return set_err(ctx, MADM_ENOMEM, "madm_extract: workspace too small for plan");
+    plan = np.get();
+    ctx->plans[key] = std::move(np);
+  }
+  plan->io->a = *a;
+  if (cudaMemsetAsync(plan->ws, 0, plan->stats_bytes, st) != cudaSuccess) return set_err(ctx, MADM_ECUDA, "cudaMemsetAsync failed");
+  for (size_t i = 0; i < plan->ops.size(); ++i) {
+    if (!(plan->stage_of[i] & a->stages) || !plan->ops[i]) continue;
+    if (const char* e = plan->ops[i](st)) return set_err(ctx, MADM_ECUDA, std::string(e) + " (op " + std::to_string(i) + ")");
+  }
+  return MADM_OK;
+}
+
+}  // extern "C"

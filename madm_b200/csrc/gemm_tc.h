@@ -1,0 +1,62 @@
+// Host-side interface of the tcgen05 implicit-GEMM kernel family (gemm_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace madm {
+
+enum Act : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2, ACT_RELU = 3 };
+
+// One K-segment of the A operand: an NHWC bf16 activation tensor read through `ntaps` shifted TMA boxes
+// (implicit im2col).  K extent of the segment = ntaps * C.  A plain [M,K] matrix is {B=1,H=1,W=M,C=K,ntaps=1}.
+struct GemmASeg {
+  const void* ptr = nullptr;  // bf16, [Bt, H, W, ld] with C <= ld used channels
+  int Bt = 1;                 // images in the tensor (for stride-2 phase tensors: 4*B, see taps[].b_off)
+  int H = 1, W = 1, C = 0;    // C % 64 == 0
+  int ld = 0;                 // channel pitch in elements (0 -> C)
+  int ntaps = 1;              // 1 (1x1 / linear) or 9 (3x3)
+  int8_t dx[9] = {0}, dy[9] = {0};
+  int b_off[9] = {0};         // image offset added per tap (space-to-depth phase * B)
+};
+
+struct GemmDesc {
+  GemmASeg seg[2];
+  int nseg = 1;
+  int M = 0;                  // output rows = B*H*W of the output grid (== grid of seg[0])
+  int N = 0;                  // output columns (weights rows)
+  const void* w = nullptr;    // bf16 [Nw, Ktot] K-major; Ktot = sum_seg ntaps*C ; Nw >= N (Nw = 2N for GEGLU-interleaved)
+  int Nw = 0;
+  int ldw = 0;                // weight row pitch in elements (0 -> Ktot)
+  const float* bias = nullptr;      // [N] (GEGLU: [2N] tile-interleaved) or null
+  const float* rowbias = nullptr;   // [nimg, N] added per image (time-embedding projection) or null
+  int rows_per_img = 1;             // H*W of the output grid (for rowbias)
+  int ld_rowbias = 0;               // row pitch of rowbias (0 -> N)
+  const float* residual = nullptr;  // fp32 [M, ldr] or null (may alias out_f32)
+  int ldr = 0;
+  float* out_f32 = nullptr;         // fp32 [M, ldo32] or null
+  int ldo32 = 0;
+  void* out_bf16 = nullptr;         // bf16 [M, ldo16] or null
+  int ldo16 = 0;
+  int act = ACT_NONE;
+  float alpha = 1.0f;               // scales the accumulator before bias
+  int bn = 0;                       // N tile (0 = auto)
+};
+
+struct GemmLaunch {  // prepared launch: tensor maps encoded once, replayed per forward
+  alignas(64) CUtensorMap tmA[2];
+  alignas(64) CUtensorMap tmB;
+  GemmDesc d;
+  int bn = 128;
+  int kchunks[2] = {0, 0};   // 64-wide K chunks per segment
+  int cpt[2] = {1, 1};       // chunks per tap
+  int box_w = 128, box_h = 1, box_b = 1;
+  dim3 grid;
+  size_t smem = 0;
+};
+
+// Returns nullptr on success, else a static error string.
+const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out);
+const char* gemm_launch(const GemmLaunch& l, cudaStream_t stream);
+
+}  // namespace madm

@@ -1,0 +1,318 @@
+// HBM-bound normalisation kernels over the fp32 NHWC residual stream: GroupNorm(32) statistics + apply
+// (+SiLU / ReLU, dual-source channel concat, optional raw bf16 copy), LayerNorm, row softmax, and the fused
+// relu(GN(a)+GN(b)) -> NCHW fp32 output of the feature projections.  All loads/stores are 16-byte vectorised and
+// coalesced along the channel axis; statistics are accumulated in fp32 (sum, sum of squares) per (image, group).
+#include "kernels.h"
+
+#include <cuda_bf16.h>
+
+namespace madm {
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == ACT_SILU) return v / (1.0f + __expf(-v));
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  return v;
+}
+
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
+  __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&lo);
+  r.y = *reinterpret_cast<uint32_t*>(&hi);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm statistics
+// grid = (slabs, B); block = Q*P threads, Q = C/4 channel quads, P pixel lanes.  Thread (q, pl) owns channels 4q..4q+3
+// and walks pixels pl, pl+P, ... of its slab, so its per-channel partial sums stay in registers.
+__global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int HW,
+                                int pix_per_cta, int P, float* __restrict__ stats /*[B,32,2]*/) {
+  extern __shared__ float sm[];  // [2][P][C]
+  const int C = C0 + C1;
+  const int Q = C >> 2;
+  const int q = threadIdx.x % Q;
+  const int pl = threadIdx.x / Q;
+  const int b = blockIdx.y;
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(HW, p_begin + pix_per_cta);
+  const int c = q * 4;
+  const float* src;
+  int ld, cc;
+  if (c < C0) { src = x0 + size_t(b) * HW * C0; ld = C0; cc = c; }
+  else        { src = x1 + size_t(b) * HW * C1; ld = C1; cc = c - C0; }
+  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  for (int p = p_begin + pl; p < p_end; p += P) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + size_t(p) * ld + cc));
+    s[0] += v.x; ss[0] += v.x * v.x;
+    s[1] += v.y; ss[1] += v.y * v.y;
+    s[2] += v.z; ss[2] += v.z * v.z;
+    s[3] += v.w; ss[3] += v.w * v.w;
+  }
+  float* sm_s = sm;
+  float* sm_ss = sm + P * C;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    sm_s[pl * C + c + t] = s[t];
+    sm_ss[pl * C + c + t] = ss[t];
+  }
+  __syncthreads();
+  // 32 groups: warp w of the first 32 warps... keep it simple: threads 0..63 each reduce one (group, moment)
+  const int cpg = C / 32;
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x & 31;
+    const float* base = (threadIdx.x < 32) ? sm_s : sm_ss;
+    float acc = 0.f;
+    for (int pp = 0; pp < P; ++pp)
+      for (int k = 0; k < cpg; ++k) acc += base[pp * C + g * cpg + k];
+    atomicAdd(stats + (size_t(b) * 32 + g) * 2 + (threadIdx.x < 32 ? 0 : 1), acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm apply
+// grid = (slabs, B); block 256.  Per-channel scale/shift for this image are built once in shared memory, then the slab
+// is streamed: y = act(x*scale + shift) -> bf16 (and optionally the un-normalised x -> bf16 for a 1x1 shortcut conv).
+__global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int HW,
+                                int pix_per_cta, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int act, __nv_bfloat16* __restrict__ y,
+                                __nv_bfloat16* __restrict__ raw) {
+  extern __shared__ float sm[];  // scale[C], shift[C]
+  const int C = C0 + C1;
+  const int b = blockIdx.y;
+  const int cpg = C / 32;
+  const float inv_n = 1.0f / (float(HW) * float(cpg));
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float su = stats[(size_t(b) * 32 + g) * 2 + 0];
+    const float sq = stats[(size_t(b) * 32 + g) * 2 + 1];
+    const float mean = su * inv_n;
+    const float var = fmaxf(sq * inv_n - mean * mean, 0.0f);
+    const float rstd = rsqrtf(var + eps);
+    const float ga = gamma ? gamma[c] : 1.0f;
+    const float be = beta ? beta[c] : 0.0f;
+    sm[c] = rstd * ga;
+    sm[C + c] = be - mean * rstd * ga;
+  }
+  __syncthreads();
+  const int Q = C >> 2;
+  const int p_begin = blockIdx.x * pix_per_cta;
+  const int p_end = min(HW, p_begin + pix_per_cta);
+  const long total = long(p_end - p_begin) * Q;
+  const float* s0 = x0 + size_t(b) * HW * C0;
+  const float* s1 = x1 ? x1 + size_t(b) * HW * C1 : nullptr;
+  for (long i = threadIdx.x; i < total; i += blockDim.x) {
+    const int p = p_begin + int(i / Q);
+    const int c = int(i % Q) * 4;
+    const float4 v = (c < C0) ? __ldg(reinterpret_cast<const float4*>(s0 + size_t(p) * C0 + c))
+                              : __ldg(reinterpret_cast<const float4*>(s1 + size_t(p) * C1 + (c - C0)));
+    const float4 sc = *reinterpret_cast<const float4*>(sm + c);
+    const float4 sh = *reinterpret_cast<const float4*>(sm + C + c);
+    const size_t o = (size_t(b) * HW + p) * C + c;
+    *reinterpret_cast<uint2*>(y + o) = pack4_bf16(act_apply(v.x * sc.x + sh.x, act), act_apply(v.y * sc.y + sh.y, act),
+                                                  act_apply(v.z * sc.z + sh.z, act), act_apply(v.w * sc.w + sh.w, act));
+    if (raw) *reinterpret_cast<uint2*>(raw + o) = pack4_bf16(v.x, v.y, v.z, v.w);
+  }
+}
+
+static void gn_geometry(int B, int HW, int C, int* P, int* threads, int* ppc, int* slabs) {
+  const int Q = C / 4;
+  int p = (256 + Q - 1) / Q;
+  if (p < 1) p = 1;
+  while (Q * p > 1024) --p;
+  *P = p;
+  *threads = Q * p;
+  const long total = long(B) * HW;
+  long per = (total + 591) / 592;  // ~4 CTAs per SM
+  if (per < 4L * p) per = 4L * p;
+  per = ((per + p - 1) / p) * p;
+  if (per > HW) per = HW;
+  *ppc = int(per);
+  *slabs = (HW + int(per) - 1) / int(per);
+}
+
+const char* groupnorm_stats(const float* x0, int C0, const float* x1, int C1, int B, int HW, float* stats, cudaStream_t st) {
+  const int C = C0 + C1;
+  if (C % 128 != 0 && (C % 32 != 0 || C % 4 != 0)) return "groupnorm: C must be a multiple of 32";
+  if (C0 % 4 != 0 || C1 % 4 != 0) return "groupnorm: source channel counts must be multiples of 4";
+  if (C / 4 > 1024) return "groupnorm: C too large";
+  int P, threads, ppc, slabs;
+  gn_geometry(B, HW, C, &P, &threads, &ppc, &slabs);
+  const size_t smem = size_t(2) * P * C * sizeof(float);
+  gn_stats_kernel<<<dim3(slabs, B), threads, smem, st>>>(x0, C0, x1, C1, HW, ppc, P, stats);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_stats launch failed";
+}
+
+const char* groupnorm_apply(const float* x0, int C0, const float* x1, int C1, int B, int HW, const float* stats,
+                            const float* gamma, const float* beta, float eps, int act, void* y, void* raw, cudaStream_t st) {
+  const int C = C0 + C1;
+  int P, threads, ppc, slabs;
+  gn_geometry(B, HW, C, &P, &threads, &ppc, &slabs);
+  const size_t smem = size_t(2) * C * sizeof(float);
+  gn_apply_kernel<<<dim3(slabs, B), 256, smem, st>>>(x0, C0, x1, C1, HW, ppc, stats, gamma, beta, eps, act,
+                                                     reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(raw));
+  return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_apply launch failed";
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm (warp per row)
+__global__ void layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int Q = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + size_t(row) * C);
+  float4 v[10];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const int q = i * 32 + lane;
+    if (q < Q) {
+      v[i] = __ldg(xr + q);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / float(C);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const int q = i * 32 + lane;
+    if (q < Q) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += a * a + b * b + c * c + d * d;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / float(C) + eps);
+  __nv_bfloat16* yr = y + size_t(row) * C;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const int q = i * 32 + lane;
+    if (q < Q) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
+      *reinterpret_cast<uint2*>(yr + q * 4) =
+          pack4_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                     (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    }
+  }
+}
+
+const char* layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y, cudaStream_t st) {
+  if (C % 4 != 0 || C > 1280) return "layernorm: C must be a multiple of 4 and <= 1280";
+  const int rows_per_cta = 8;
+  layernorm_kernel<<<(M + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, st>>>(x, M, C, gamma, beta, eps,
+                                                                                      reinterpret_cast<__nv_bfloat16*>(y));
+  return cudaGetLastError() == cudaSuccess ? nullptr : "layernorm launch failed";
+}
+
+// ---------------------------------------------------------------------------------------------- row softmax fp32 -> bf16
+// one CTA (256 threads) per row; L <= 256*32.
+__global__ void softmax_rows_kernel(const float* __restrict__ s, int L, __nv_bfloat16* __restrict__ p) {
+  __shared__ float red[8];
+  const float* sr = s + size_t(blockIdx.x) * L;
+  __nv_bfloat16* pr = p + size_t(blockIdx.x) * L;
+  float v[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = i * 256 + threadIdx.x;
+    v[i] = (j < L) ? sr[j] : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = __expf(v[i] - mx);
+    sum += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = i * 256 + threadIdx.x;
+    if (j < L) pr[j] = __float2bfloat16_rn(v[i] * inv);
+  }
+}
+
+const char* softmax_rows(const float* s, int R, int L, void* p, cudaStream_t st) {
+  if (L > 256 * 32) return "softmax_rows: row too long";
+  softmax_rows_kernel<<<R, 256, 0, st>>>(s, L, reinterpret_cast<__nv_bfloat16*>(p));
+  return cudaGetLastError() == cudaSuccess ? nullptr : "softmax_rows launch failed";
+}
+
+// ---------------------------------------------------------------------------------------------- projection tail
+// out[b, c, p] (NCHW fp32) = relu( GN(a)[b,p,c] + (GN(s) or s)[b,p,c] ); 32x32 (pixel x channel) tiles through smem.
+__global__ void gn_add_relu_nchw_kernel(const float* __restrict__ a, const float* __restrict__ stats_a,
+                                        const float* __restrict__ ga, const float* __restrict__ ba,
+                                        const float* __restrict__ s, const float* __restrict__ stats_s,
+                                        const float* __restrict__ gs, const float* __restrict__ bs, float eps, int HW, int C,
+                                        float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const int p0 = blockIdx.x * 32;
+  const int cpg = C / 32;
+  const float inv_n = 1.0f / (float(HW) * float(cpg));
+  const int tx = threadIdx.x;  // 0..31
+  const int ty = threadIdx.y;  // 0..7
+  // read: channel fastest
+  const int c = c0 + tx;
+  const int g = c / cpg;
+  float sca, sha, scs = 1.f, shs = 0.f;
+  {
+    const float mean = stats_a[(size_t(b) * 32 + g) * 2] * inv_n;
+    const float var = fmaxf(stats_a[(size_t(b) * 32 + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    sca = rstd * ga[c];
+    sha = ba[c] - mean * sca;
+  }
+  if (stats_s) {
+    const float mean = stats_s[(size_t(b) * 32 + g) * 2] * inv_n;
+    const float var = fmaxf(stats_s[(size_t(b) * 32 + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    scs = rstd * gs[c];
+    shs = bs[c] - mean * scs;
+  }
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r;
+    float v = 0.f;
+    if (p < HW) {
+      const size_t i = (size_t(b) * HW + p) * C + c;
+      v = fmaxf(a[i] * sca + sha + s[i] * scs + shs, 0.f);
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {  // r = channel within tile, tx = pixel
+    const int p = p0 + tx;
+    if (p < HW) out[(size_t(b) * C + c0 + r) * HW + p] = tile[tx][r];
+  }
+}
+
+const char* gn_add_relu_nchw(const float* a, const float* stats_a, const float* ga, const float* ba, const float* s,
+                             const float* stats_s, const float* gs, const float* bs, float eps, int B, int HW, int C,
+                             float* out, cudaStream_t st) {
+  if (C % 32 != 0) return "gn_add_relu_nchw: C must be a multiple of 32";
+  dim3 grid((HW + 31) / 32, C / 32, B);
+  gn_add_relu_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(a, stats_a, ga, ba, s, stats_s, gs, bs, eps, HW, C, out);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "gn_add_relu_nchw launch failed";
+}
+
+}  // namespace madm

@@ -1,0 +1,165 @@
+"""Operator-level wrappers over the C ABI (``madm_op_*``): torch tensors are used only as device memory.
+
+These are the kernels the engine is composed of; the parity tests drive them through the same C ABI the
+engine uses internally.  No PyTorch compute happens here.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import MadmGemmArgs, MadmGemmSeg
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def taps_3x3():
+    return [(kx - 1, ky - 1, 0) for ky in range(3) for kx in range(3)]  # (dx, dy, b_off)
+
+
+def taps_stride2(B: int, pad1: bool):
+    """Tap table of a stride-2 3x3 conv over the space-to-depth tensor [4][B][H/2][W/2][C]."""
+    out = []
+    for ky in range(3):
+        for kx in range(3):
+            if pad1:
+                py, dy = (0 if ky == 1 else 1), (-1 if ky == 0 else 0)
+                px, dx = (0 if kx == 1 else 1), (-1 if kx == 0 else 0)
+            else:
+                py, dy = (1 if ky == 1 else 0), (1 if ky == 2 else 0)
+                px, dx = (1 if kx == 1 else 0), (1 if kx == 2 else 0)
+            out.append((dx, dy, (py * 2 + px) * B))
+    return out
+
+
+def make_seg(a: torch.Tensor, Bt: int, H: int, W: int, Cc: int, ld: int = 0, taps: Optional[Sequence] = None) -> MadmGemmSeg:
+    s = MadmGemmSeg()
+    s.a = a.data_ptr()
+    s.Bt, s.H, s.W, s.C, s.ld = Bt, H, W, Cc, ld
+    taps = taps or [(0, 0, 0)]
+    s.ntaps = len(taps)
+    for i, (dx, dy, bo) in enumerate(taps):
+        s.dx[i], s.dy[i], s.b_off[i] = dx, dy, bo
+    return s
+
+
+def gemm(segs: Sequence[MadmGemmSeg], M: int, N: int, w: torch.Tensor, *, Nw: int = 0, ldw: int = 0,
+         bias=None, rowbias=None, rows_per_img: int = 1, ld_rowbias: int = 0, residual=None, ldr: int = 0,
+         out_f32=None, ldo32: int = 0, out_bf16=None, ldo16: int = 0, act: int = 0, alpha: float = 1.0, bn: int = 0):
+    a = MadmGemmArgs()
+    a.nseg = len(segs)
+    for i, s in enumerate(segs):
+        a.seg[i] = s
+    a.M, a.N, a.Nw, a.ldw = M, N, Nw or N, ldw
+    a.w = w.data_ptr()
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.rowbias = rowbias.data_ptr() if rowbias is not None else None
+    a.rows_per_img, a.ld_rowbias = rows_per_img, ld_rowbias
+    a.residual = residual.data_ptr() if residual is not None else None
+    a.ldr = ldr
+    a.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+    a.ldo32 = ldo32
+    a.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+    a.ldo16 = ldo16
+    a.act, a.alpha, a.bn = act, alpha, bn
+    lib = _lib.load()
+    _lib.check(lib.madm_op_gemm(C.byref(a), _stream()), None, "madm_op_gemm")
+
+
+def groupnorm(x0, x1, B, HW, gamma, beta, eps, act, y, raw=None):
+    lib = _lib.load()
+    stats = torch.empty(B * 64, dtype=torch.float32, device=x0.device)
+    C0 = x0.shape[-1]
+    C1 = x1.shape[-1] if x1 is not None else 0
+    _lib.check(lib.madm_op_groupnorm(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(gamma), _ptr(beta), eps, act, _ptr(stats),
+                                     _ptr(y), _ptr(raw), _stream()), None, "madm_op_groupnorm")
+    return stats
+
+
+def layernorm(x, gamma, beta, eps, y):
+    lib = _lib.load()
+    M, Cc = x.shape
+    _lib.check(lib.madm_op_layernorm(_ptr(x), M, Cc, _ptr(gamma), _ptr(beta), eps, _ptr(y), _stream()), None, "madm_op_layernorm")
+
+
+def softmax_rows(s, p):
+    lib = _lib.load()
+    R, L = s.shape
+    _lib.check(lib.madm_op_softmax_rows(_ptr(s), R, L, _ptr(p), _stream()), None, "madm_op_softmax_rows")
+
+
+def attention(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale):
+    lib = _lib.load()
+    _lib.check(lib.madm_op_attention(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(o), ldo, B, heads, d, Nq, Nk, q_bs, kv_bs,
+                                     o_bs, scale, _stream()), None, "madm_op_attention")
+
+
+def pack_linear(w, lora_a=None, lora_b=None, scale=0.0, out=None, ldo=0):
+    lib = _lib.load()
+    N, K = w.shape
+    r = lora_a.shape[0] if lora_a is not None else 0
+    if out is None:
+        out = torch.empty(N, K, dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.madm_op_pack_linear(_ptr(w), N, K, _ptr(lora_a), _ptr(lora_b), r, scale, _ptr(out), ldo, _stream()), None,
+               "madm_op_pack_linear")
+    return out
+
+
+def pack_conv(w, Cpad=0, out=None, ldo=0):
+    lib = _lib.load()
+    N, Cc, kh, kw = w.shape
+    taps = kh * kw
+    Cpad = Cpad or (Cc + 63) // 64 * 64
+    if out is None:
+        out = torch.empty(N, taps * Cpad, dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.madm_op_pack_conv(_ptr(w), N, Cc, taps, Cpad, _ptr(out), ldo, _stream()), None, "madm_op_pack_conv")
+    return out
+
+
+def pack_geglu(w, bias):
+    lib = _lib.load()
+    N2, K = w.shape
+    out = torch.empty(N2, K, dtype=torch.bfloat16, device=w.device)
+    ob = torch.empty(N2, dtype=torch.float32, device=w.device)
+    _lib.check(lib.madm_op_pack_geglu(_ptr(w), _ptr(bias), N2 // 2, K, _ptr(out), _ptr(ob), _stream()), None, "madm_op_pack_geglu")
+    return out, ob
+
+
+def space_to_depth(x):
+    lib = _lib.load()
+    B, H, W, Cc = x.shape
+    out = torch.empty(4, B, H // 2, W // 2, Cc, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.madm_op_space_to_depth(_ptr(x), B, H, W, Cc, _ptr(out), _stream()), None, "madm_op_space_to_depth")
+    return out
+
+
+def upsample2x(x):
+    lib = _lib.load()
+    B, H, W, Cc = x.shape
+    out = torch.empty(B, 2 * H, 2 * W, Cc, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.madm_op_upsample2x(_ptr(x), B, H, W, Cc, _ptr(out), _stream()), None, "madm_op_upsample2x")
+    return out
+
+
+def image_im2col(img, range_flag=None):
+    lib = _lib.load()
+    B, _, H, W = img.shape
+    out = torch.empty(B * H * W, 64, dtype=torch.bfloat16, device=img.device)
+    _lib.check(lib.madm_op_image_im2col(_ptr(img), B, H, W, _ptr(out), _ptr(range_flag), _stream()), None, "madm_op_image_im2col")
+    return out
+
+
+def gn_add_relu_nchw(a, ga, ba, s, gs, bs, eps, B, HW, Cc):
+    lib = _lib.load()
+    stats = torch.empty(2 * B * 64, dtype=torch.float32, device=a.device)
+    out = torch.empty(B, Cc, HW, dtype=torch.float32, device=a.device)
+    _lib.check(lib.madm_op_gn_add_relu_nchw(_ptr(a), _ptr(ga), _ptr(ba), _ptr(s), _ptr(gs), _ptr(bs), 1 if gs is not None else 0,
+                                            eps, B, HW, Cc, _ptr(stats), _ptr(out), _stream()), None, "madm_op_gn_add_relu_nchw")
+    return out

@@ -1,0 +1,289 @@
+"""Kernel-level parity (GPU): every CUDA kernel of the hot path, called through the C ABI (madm_op_*), against a
+plain PyTorch fp32 restatement of the same op on the same (bf16-rounded) inputs.
+
+Tolerances: GEMM/conv fp32 outputs rel 2e-3 of max|ref| (fp32 accumulation order), bf16 outputs 1e-2;
+norms 1e-2 (bf16 output rounding); attention 2e-2 (bf16 P).  Byte/index kernels (pack, s2d, upsample) bit-exact.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+def relerr(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    from madm_b200 import ops as o
+    return o
+
+
+def nhwc(x):  # NCHW -> NHWC contiguous
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------- plain GEMM
+@pytest.mark.parametrize("M,K,N,bn", [(300, 320, 320, 0), (300, 320, 320, 64), (1024, 1280, 640, 128), (77, 768, 1920, 192),
+                                      (8, 320, 1280, 0), (256, 64, 128, 0), (512, 2560, 1280, 256), (130, 128, 96, 32),
+                                      (4096, 512, 4096, 0)])
+def test_gemm_plain(ops, cuda_device, M, K, N, bn):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    a = bf(torch.randn(M, K, device=cuda_device, generator=g))
+    w = bf(torch.randn(N, K, device=cuda_device, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=cuda_device, generator=g)
+    o32 = torch.full((M, N), float("nan"), device=cuda_device)
+    o16 = torch.empty(M, N, dtype=torch.bfloat16, device=cuda_device)
+    ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, N, w, bias=bias, out_f32=o32, ldo32=N, out_bf16=o16, ldo16=N, bn=bn)
+    ref = a.float() @ w.float().t() + bias
+    assert relerr(o32, ref) < 2e-3
+    assert relerr(o16, ref) < 1e-2
+
+
+def test_gemm_epilogue_variants(ops, cuda_device):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, HW, K, N = 3, 256, 128, 320
+    M = B * HW
+    a = bf(torch.randn(M, K, device=cuda_device, generator=g))
+    w = bf(torch.randn(N, K, device=cuda_device, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=cuda_device, generator=g)
+    rowbias = torch.randn(B, 1000, device=cuda_device, generator=g)
+    res = torch.randn(M, N, device=cuda_device, generator=g)
+    # row bias (time embedding), residual in place, SiLU, alpha
+    out = res.clone()
+    ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, N, w, bias=bias, rowbias=rowbias[:, 40:], rows_per_img=HW, ld_rowbias=1000,
+             residual=out, ldr=N, out_f32=out, ldo32=N, alpha=0.5)
+    ref = 0.5 * (a.float() @ w.float().t()) + bias + rowbias[:, 40:40 + N].repeat_interleave(HW, 0) + res
+    assert relerr(out, ref) < 2e-3
+    o16 = torch.empty(M, N, dtype=torch.bfloat16, device=cuda_device)
+    ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, N, w, bias=bias, out_bf16=o16, ldo16=N, act=1)
+    assert relerr(o16, F.silu(a.float() @ w.float().t() + bias)) < 1e-2
+    ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, N, w, bias=bias, out_bf16=o16, ldo16=N, act=3)
+    assert relerr(o16, F.relu(a.float() @ w.float().t() + bias)) < 1e-2
+    # narrow N (latent head): N=4 of a 16-row padded weight, scalar epilogue path, pitch 4
+    w16 = torch.zeros(16, K, dtype=torch.bfloat16, device=cuda_device)
+    w16[:4] = w[:4]
+    o4 = torch.empty(M, 4, device=cuda_device)
+    ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, 4, w16, Nw=16, bias=bias[:16].contiguous(), out_f32=o4, ldo32=4, bn=16)
+    assert relerr(o4, a.float() @ w[:4].float().t() + bias[:4]) < 2e-3
+
+
+def test_gemm_strided_operands(ops, cuda_device):
+    """A and W read out of wider buffers (q | k halves of a fused projection), as the VAE attention does."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    T, Cc = 512, 128
+    qk = bf(torch.randn(T, 2 * Cc, device=cuda_device, generator=g))
+    S = torch.empty(T, T, device=cuda_device)
+    ops.gemm([ops.make_seg(qk, 1, 1, T, Cc, ld=2 * Cc)], T, T, qk[:, Cc:], ldw=2 * Cc, out_f32=S, ldo32=T, alpha=0.125)
+    ref = 0.125 * (qk[:, :Cc].float() @ qk[:, Cc:].float().t())
+    assert relerr(S, ref) < 2e-3
+
+
+def test_gemm_geglu(ops, cuda_device):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, Cc = 384, 320
+    x = bf(torch.randn(M, Cc, device=cuda_device, generator=g))
+    w = torch.randn(8 * Cc, Cc, device=cuda_device, generator=g) / math.sqrt(Cc)
+    b = torch.randn(8 * Cc, device=cuda_device, generator=g)
+    wp, bp = ops.pack_geglu(w, b)
+    out = torch.empty(M, 4 * Cc, dtype=torch.bfloat16, device=cuda_device)
+    ops.gemm([ops.make_seg(x, 1, 1, M, Cc)], M, 4 * Cc, wp, Nw=8 * Cc, bias=bp, out_bf16=out, ldo16=4 * Cc, act=2)
+    p = x.float() @ bf(w).float().t() + b
+    h, gate = p.chunk(2, dim=-1)
+    assert relerr(out, h * F.gelu(gate)) < 1e-2
+
+
+# ---------------------------------------------------------------------------------------------- implicit-GEMM convs
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 128, 192), (1, 8, 128, 64, 128), (3, 8, 8, 128, 320), (1, 64, 64, 320, 320),
+                                            (2, 32, 32, 192, 640), (1, 4, 256, 64, 128)])
+def test_conv3x3(ops, cuda_device, B, H, W, Cin, Cout):
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + H)
+    x = bf(torch.randn(B, Cin, H, W, device=cuda_device, generator=g))
+    w = torch.randn(Cout, Cin, 3, 3, device=cuda_device, generator=g) / math.sqrt(9 * Cin)
+    bias = torch.randn(Cout, device=cuda_device, generator=g)
+    wp = ops.pack_conv(w)
+    a = nhwc(x)
+    M = B * H * W
+    out = torch.empty(M, Cout, device=cuda_device)
+    ops.gemm([ops.make_seg(a, B, H, W, Cin, taps=ops.taps_3x3())], M, Cout, wp, bias=bias, out_f32=out, ldo32=Cout)
+    ref = nhwc(F.conv2d(x.float(), bf(w).float(), bias, padding=1)).reshape(M, Cout)
+    assert relerr(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("pad1", [True, False])
+@pytest.mark.parametrize("B,H,W,Cc", [(2, 32, 32, 64), (1, 16, 16, 128), (2, 256, 256, 64)])
+def test_conv3x3_stride2(ops, cuda_device, pad1, B, H, W, Cc):
+    g = torch.Generator(device="cuda").manual_seed(H + (1 if pad1 else 0))
+    x = torch.randn(B, Cc, H, W, device=cuda_device, generator=g)
+    w = torch.randn(Cc, Cc, 3, 3, device=cuda_device, generator=g) / math.sqrt(9 * Cc)
+    bias = torch.randn(Cc, device=cuda_device, generator=g)
+    s2d = ops.space_to_depth(nhwc(x))
+    # space-to-depth is pure data movement: bit-exact
+    xb = bf(nhwc(x))
+    for ph in range(4):
+        assert torch.equal(s2d[ph], xb[:, (ph // 2)::2, (ph % 2)::2, :])
+    wp = ops.pack_conv(w)
+    Ho, Wo = H // 2, W // 2
+    M = B * Ho * Wo
+    out = torch.empty(M, Cc, device=cuda_device)
+    ops.gemm([ops.make_seg(s2d, 4 * B, Ho, Wo, Cc, taps=ops.taps_stride2(B, pad1))], M, Cc, wp, bias=bias, out_f32=out, ldo32=Cc)
+    xr = bf(x).float()
+    if pad1:
+        ref = F.conv2d(xr, bf(w).float(), bias, stride=2, padding=1)
+    else:
+        ref = F.conv2d(F.pad(xr, (0, 1, 0, 1)), bf(w).float(), bias, stride=2, padding=0)
+    assert relerr(out, nhwc(ref).reshape(M, Cc)) < 2e-3
+
+
+def test_conv_plus_shortcut_two_segments(ops, cuda_device):
+    """out = conv3x3(h) + conv1x1(x) as one GEMM with K = 9*Cout + Cin (ResBlock conv2 + conv_shortcut)."""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    B, H, W, Cin, Cout = 2, 16, 16, 192, 128
+    h = bf(torch.randn(B, Cout, H, W, device=cuda_device, generator=g))
+    x = bf(torch.randn(B, Cin, H, W, device=cuda_device, generator=g))
+    w2 = torch.randn(Cout, Cout, 3, 3, device=cuda_device, generator=g) / math.sqrt(9 * Cout)
+    ws = torch.randn(Cout, Cin, 1, 1, device=cuda_device, generator=g) / math.sqrt(Cin)
+    K = 9 * Cout + Cin
+    wp = torch.empty(Cout, K, dtype=torch.bfloat16, device=cuda_device)
+    ops.pack_conv(w2, out=wp, ldo=K)
+    ops.pack_conv(ws, out=wp[:, 9 * Cout:], ldo=K)
+    M = B * H * W
+    out = torch.empty(M, Cout, device=cuda_device)
+    hn, xn = nhwc(h), nhwc(x)  # keep the NHWC copies alive: segments hold raw pointers
+    ops.gemm([ops.make_seg(hn, B, H, W, Cout, taps=ops.taps_3x3()), ops.make_seg(xn, B, H, W, Cin)], M, Cout, wp,
+             out_f32=out, ldo32=Cout)
+    ref = F.conv2d(h.float(), bf(w2).float(), padding=1) + F.conv2d(x.float(), bf(ws).float())
+    assert relerr(out, nhwc(ref).reshape(M, Cout)) < 2e-3
+
+
+def test_upsample_conv(ops, cuda_device):
+    g = torch.Generator(device="cuda").manual_seed(31)
+    B, H, W, Cc = 2, 8, 8, 128
+    x = torch.randn(B, Cc, H, W, device=cuda_device, generator=g)
+    up = ops.upsample2x(nhwc(x))
+    assert torch.equal(up, bf(nhwc(F.interpolate(x, scale_factor=2.0, mode="nearest"))))
+
+
+def test_image_im2col_first_conv(ops, cuda_device):
+    g = torch.Generator(device="cuda").manual_seed(41)
+    B, H, W = 2, 64, 128
+    img = torch.rand(B, 3, H, W, device=cuda_device, generator=g)
+    w = torch.randn(128, 3, 3, 3, device=cuda_device, generator=g) / math.sqrt(27)
+    bias = torch.randn(128, device=cuda_device, generator=g)
+    flag = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    col = ops.image_im2col(img, flag)
+    wp = ops.pack_conv(w, Cpad=3)  # K = 27 -> padded to 64 by the packer
+    wp64 = torch.zeros(128, 64, dtype=torch.bfloat16, device=cuda_device)
+    wp64[:, :27] = wp[:, :27]
+    M = B * H * W
+    out = torch.empty(M, 128, device=cuda_device)
+    ops.gemm([ops.make_seg(col, 1, 1, M, 64)], M, 128, wp64, bias=bias, out_f32=out, ldo32=128)
+    xn = bf((img - 0.5) / 0.5).float()
+    ref = nhwc(F.conv2d(xn, bf(w).float(), bias, padding=1)).reshape(M, 128)
+    assert relerr(out, ref) < 2e-3
+    assert flag.item() == 0
+    ops.image_im2col(img * 1.5, flag)
+    assert flag.item() == 1  # out-of-range input is reported (reference asserts, ldm_diffusers.py:147)
+
+
+# ---------------------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("B,HW,C0,C1,act", [(2, 4096, 320, 0, 1), (2, 256, 1280, 640, 1), (1, 64, 1280, 1280, 1), (3, 1024, 128, 0, 3),
+                                            (1, 16384, 512, 0, 0), (2, 1024, 640, 320, 1)])
+def test_groupnorm(ops, cuda_device, B, HW, C0, C1, act):
+    g = torch.Generator(device="cuda").manual_seed(C0 + C1)
+    x0 = torch.randn(B, HW, C0, device=cuda_device, generator=g) * 2 + 0.5
+    x1 = torch.randn(B, HW, C1, device=cuda_device, generator=g) - 0.3 if C1 else None
+    Cc = C0 + C1
+    gamma = torch.randn(Cc, device=cuda_device, generator=g)
+    beta = torch.randn(Cc, device=cuda_device, generator=g)
+    y = torch.empty(B, HW, Cc, dtype=torch.bfloat16, device=cuda_device)
+    raw = torch.empty_like(y)
+    ops.groupnorm(x0, x1, B, HW, gamma, beta, 1e-5, act, y, raw)
+    x = torch.cat([x0, x1], -1) if C1 else x0
+    ref = F.group_norm(x.permute(0, 2, 1), 32, gamma, beta, 1e-5).permute(0, 2, 1)
+    ref = {0: ref, 1: F.silu(ref), 3: F.relu(ref)}[act]
+    assert relerr(y, ref) < 1e-2
+    assert torch.equal(raw, bf(x))
+
+
+@pytest.mark.parametrize("M,Cc", [(4096, 320), (1000, 640), (77, 1280)])
+def test_layernorm(ops, cuda_device, M, Cc):
+    g = torch.Generator(device="cuda").manual_seed(Cc)
+    x = torch.randn(M, Cc, device=cuda_device, generator=g) * 3 + 1
+    gamma = torch.randn(Cc, device=cuda_device, generator=g)
+    beta = torch.randn(Cc, device=cuda_device, generator=g)
+    y = torch.empty(M, Cc, dtype=torch.bfloat16, device=cuda_device)
+    ops.layernorm(x, gamma, beta, 1e-5, y)
+    assert relerr(y, F.layer_norm(x, (Cc,), gamma, beta, 1e-5)) < 1e-2
+
+
+def test_softmax_rows(ops, cuda_device):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    s = torch.randn(300, 4096, device=cuda_device, generator=g) * 4
+    p = torch.empty(300, 4096, dtype=torch.bfloat16, device=cuda_device)
+    ops.softmax_rows(s, p)
+    assert relerr(p, torch.softmax(s, -1)) < 1e-2
+
+
+def test_gn_add_relu_nchw(ops, cuda_device):
+    g = torch.Generator(device="cuda").manual_seed(13)
+    B, HW, Cc = 2, 1024, 512
+    a = torch.randn(B, HW, Cc, device=cuda_device, generator=g)
+    s = torch.randn(B, HW, Cc, device=cuda_device, generator=g) * 2
+    ga, ba, gs, bs = (torch.randn(Cc, device=cuda_device, generator=g) for _ in range(4))
+    out = ops.gn_add_relu_nchw(a, ga, ba, s, gs, bs, 1e-5, B, HW, Cc)
+    gn = lambda t, w, b: F.group_norm(t.permute(0, 2, 1), 32, w, b, 1e-5)  # noqa: E731
+    ref = F.relu(gn(a, ga, ba) + gn(s, gs, bs))
+    assert relerr(out, ref) < 1e-4
+    out2 = ops.gn_add_relu_nchw(a, ga, ba, s, None, None, 1e-5, B, HW, Cc)
+    assert relerr(out2, F.relu(gn(a, ga, ba) + s.permute(0, 2, 1))) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,heads,d,Nq,Nk", [(2, 8, 40, 4096, 4096), (1, 8, 80, 1024, 1024), (2, 8, 160, 256, 256), (1, 8, 160, 64, 64),
+                                             (2, 8, 40, 4096, 77), (2, 8, 160, 64, 77), (1, 8, 80, 1024, 77)])
+def test_attention(ops, cuda_device, B, heads, d, Nq, Nk):
+    g = torch.Generator(device="cuda").manual_seed(d + Nk)
+    Cc = heads * d
+    self_attn = Nq == Nk
+    if self_attn:  # fused qkv buffer [B, N, 3C]
+        qkv = bf(torch.randn(B, Nq, 3 * Cc, device=cuda_device, generator=g))
+        q, k, v = qkv[..., :Cc], qkv[..., Cc:2 * Cc], qkv[..., 2 * Cc:]
+        ldq = ldk = 3 * Cc
+        q_bs, kv_bs = Nq * 3 * Cc, Nk * 3 * Cc
+    else:  # q [B,N,C]; k,v inside a wide per-layer-stacked buffer [B,77,ldkv]
+        ldkv = 2 * Cc + 256
+        qb = bf(torch.randn(B, Nq, Cc, device=cuda_device, generator=g))
+        kvb = bf(torch.randn(B, Nk, ldkv, device=cuda_device, generator=g))
+        q, k, v = qb, kvb[..., 128:128 + Cc], kvb[..., 128 + Cc:128 + 2 * Cc]
+        ldq, ldk = Cc, ldkv
+        q_bs, kv_bs = Nq * Cc, Nk * ldkv
+    o = torch.empty(B, Nq, Cc, dtype=torch.bfloat16, device=cuda_device)
+    ops.attention(q, ldq, k, ldk, v, ldk, o, Cc, B, heads, d, Nq, Nk, q_bs, kv_bs, Nq * Cc, 1.0 / math.sqrt(d))
+    split = lambda t: t.float().reshape(B, -1, heads, d).transpose(1, 2)  # noqa: E731
+    ref = F.scaled_dot_product_attention(split(q), split(k), split(v)).transpose(1, 2).reshape(B, Nq, Cc)
+    assert relerr(o, ref) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------- packing (LoRA fold)
+def test_pack_linear_lora_fold(ops, cuda_device):
+    g = torch.Generator(device="cuda").manual_seed(17)
+    N, K, r = 320, 768, 16
+    w = torch.randn(N, K, device=cuda_device, generator=g)
+    A = torch.randn(r, K, device=cuda_device, generator=g) / r
+    Bm = torch.randn(N, r, device=cuda_device, generator=g) * 0.02
+    out = ops.pack_linear(w, A, Bm, scale=2.0)
+    ref = bf(w + 2.0 * (Bm @ A))
+    # fp32 sum order may differ by an ulp before the bf16 rounding: allow 1 bf16 ulp on <0.1% of entries
+    diff = (out.float() - ref.float()).abs()
+    assert (diff > 0).float().mean().item() < 1e-3
+    assert relerr(out, ref) < 1e-2
+    assert torch.equal(ops.pack_linear(w), bf(w))
