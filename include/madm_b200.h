@@ -36,6 +36,13 @@ enum {
   MADM_ENOMEM = -5    /* workspace or packed arena too small */
 };
 
+/* Compute dtype of the GEMM / attention operands (accumulation, norms, softmax and the residual stream are always fp32).
+ * fp16 is the default: it is the reference's own AMP dtype (engine/train_loop.py:277, evaluation/evaluator.py:62-86) and it
+ * meets the 2e-2 parity gate with margin; bf16 runs at the same tensor-core rate but its 8-bit mantissa puts the projected
+ * maps at ~2.1e-2 on the synthetic model (DESIGN.md "Numerics"). */
+#define MADM_DTYPE_BF16 0
+#define MADM_DTYPE_FP16 1
+
 typedef struct madm_ctx madm_ctx;
 typedef void* madm_stream; /* cudaStream_t */
 
@@ -58,6 +65,11 @@ const char* madm_last_error(const madm_ctx* ctx); /* ctx may be NULL: error of t
 
 int madm_create(madm_ctx** out, int device);
 int madm_destroy(madm_ctx* ctx);
+
+/* Select MADM_DTYPE_FP16 (default) or MADM_DTYPE_BF16.  Invalidates packed weights and plans: call before
+ * madm_pack_weights. */
+int madm_set_compute_dtype(madm_ctx* ctx, int32_t dtype);
+int madm_get_compute_dtype(const madm_ctx* ctx);
 
 /* Register / refresh parameter pointers.  Replaces nn.Module parameter ownership: the library never copies or
  * owns model weights, it reads biases and norm affines in place and packs GEMM weights into the arena below. */
@@ -113,7 +125,8 @@ int madm_launch_count(madm_ctx* ctx, int32_t B, int32_t stages);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Operator-level entry points (the kernels the engine is built from), exposed so parity tests can check each one
- * against the oracle through the same C ABI.  All pointers are device pointers.
+ * against the oracle through the same C ABI.  All pointers are device pointers.  "*_bf16" parameters are 16-bit operand
+ * tensors whose element type is given by `dtype` (MADM_DTYPE_*).
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct madm_gemm_seg {
   const void* a;     /* bf16 NHWC activations [Bt,H,W,ld] */
@@ -136,28 +149,31 @@ typedef struct madm_gemm_args {
   int32_t act;            /* 0 none, 1 SiLU, 2 GEGLU (tile-interleaved weights), 3 ReLU */
   float alpha;
   int32_t bn;             /* N tile: 0 auto, else 16/32/64/128/160/192/256 */
+  int32_t dtype;          /* MADM_DTYPE_* of a, w and out_bf16 */
 } madm_gemm_args;
 
 int madm_op_gemm(const madm_gemm_args* a, madm_stream stream);
 int madm_op_groupnorm(const float* x0, int32_t C0, const float* x1, int32_t C1, int32_t B, int32_t HW, const float* gamma,
                       const float* beta, float eps, int32_t act, float* stats_scratch /*[B,32,2], zeroed by the call*/,
-                      void* y_bf16, void* raw_bf16, madm_stream stream);
+                      void* y_bf16, void* raw_bf16, int32_t dtype, madm_stream stream);
 int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y_bf16,
-                      madm_stream stream);
-int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p_bf16, madm_stream stream);
+                      int32_t dtype, madm_stream stream);
+int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p_bf16, int32_t dtype, madm_stream stream);
 int madm_op_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o, int32_t ldo,
                       int32_t B, int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bstride, int64_t kv_bstride,
-                      int64_t o_bstride, float scale, madm_stream stream);
+                      int64_t o_bstride, float scale, int32_t dtype, madm_stream stream);
 int madm_op_pack_linear(const float* w, int32_t N, int32_t K, const float* lora_a, const float* lora_b, int32_t r, float scale,
-                        void* out_bf16, int32_t ldo, madm_stream stream);
+                        void* out_bf16, int32_t ldo, int32_t dtype, madm_stream stream);
 int madm_op_pack_conv(const float* w, int32_t N, int32_t C, int32_t taps, int32_t Cpad, void* out_bf16, int32_t ldo,
-                      madm_stream stream);
+                      int32_t dtype, madm_stream stream);
 int madm_op_pack_geglu(const float* w, const float* bias, int32_t C4, int32_t K, void* out_bf16, float* out_bias,
+                       int32_t dtype, madm_stream stream);
+int madm_op_space_to_depth(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, int32_t dtype,
+                           madm_stream stream);
+int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, int32_t dtype,
                        madm_stream stream);
-int madm_op_space_to_depth(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, madm_stream stream);
-int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, madm_stream stream);
 int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out_bf16, int32_t* range_flag,
-                         madm_stream stream);
+                         int32_t dtype, madm_stream stream);
 int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, const float* s, const float* gs, const float* bs,
                              int32_t has_shortcut_norm, float eps, int32_t B, int32_t HW, int32_t C, float* stats_scratch /*[2,B,32,2]*/,
                              float* out_nchw, madm_stream stream);

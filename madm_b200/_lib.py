@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libmadm_b200.so")
 MADM_OK = 0
 STAGE_VAE, STAGE_UNET, STAGE_PROJ, STAGE_ALL = 1, 2, 4, 7
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU = 0, 1, 2, 3
+DTYPE_BF16, DTYPE_FP16 = 0, 1
 
 c_void_p, c_int, c_int32, c_int64, c_float, c_size_t, c_char_p = (
     C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_char_p)
@@ -45,7 +46,7 @@ class MadmGemmArgs(C.Structure):
         ("seg", MadmGemmSeg * 2), ("nseg", c_int32), ("M", c_int32), ("N", c_int32), ("Nw", c_int32), ("ldw", c_int32),
         ("w", c_void_p), ("bias", c_void_p), ("rowbias", c_void_p), ("rows_per_img", c_int32), ("ld_rowbias", c_int32),
         ("residual", c_void_p), ("ldr", c_int32), ("out_f32", c_void_p), ("ldo32", c_int32),
-        ("out_bf16", c_void_p), ("ldo16", c_int32), ("act", c_int32), ("alpha", c_float), ("bn", c_int32),
+        ("out_bf16", c_void_p), ("ldo16", c_int32), ("act", c_int32), ("alpha", c_float), ("bn", c_int32), ("dtype", c_int32),
     ]
 
 
@@ -55,6 +56,8 @@ SYMBOLS = {
     "madm_last_error": (c_char_p, [c_void_p]),
     "madm_create": (c_int, [C.POINTER(c_void_p), c_int]),
     "madm_destroy": (c_int, [c_void_p]),
+    "madm_set_compute_dtype": (c_int, [c_void_p, c_int32]),
+    "madm_get_compute_dtype": (c_int, [c_void_p]),
     "madm_set_tensors": (c_int, [c_void_p, C.POINTER(MadmTensor), c_int32]),
     "madm_packed_bytes": (c_size_t, [c_void_p]),
     "madm_pack_weights": (c_int, [c_void_p, c_void_p, c_char_p, c_float, c_int32, c_void_p]),
@@ -63,18 +66,18 @@ SYMBOLS = {
     "madm_launch_count": (c_int, [c_void_p, c_int32, c_int32]),
     "madm_op_gemm": (c_int, [C.POINTER(MadmGemmArgs), c_void_p]),
     "madm_op_groupnorm": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_float,
-                                  c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "madm_op_layernorm": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
-    "madm_op_softmax_rows": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+                                  c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "madm_op_layernorm": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
+    "madm_op_softmax_rows": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_attention": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,
-                                  c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, c_float, c_void_p]),
+                                  c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, c_float, c_int32, c_void_p]),
     "madm_op_pack_linear": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_int32,
-                                    c_void_p]),
-    "madm_op_pack_conv": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
-    "madm_op_pack_geglu": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
-    "madm_op_space_to_depth": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
-    "madm_op_upsample2x": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
-    "madm_op_image_im2col": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+                                    c_int32, c_void_p]),
+    "madm_op_pack_conv": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    "madm_op_pack_geglu": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
+    "madm_op_space_to_depth": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_upsample2x": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_image_im2col": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
     "madm_op_gn_add_relu_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,
                                          c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }

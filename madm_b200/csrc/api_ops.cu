@@ -44,59 +44,63 @@ int madm_op_gemm(const madm_gemm_args* a, madm_stream stream) {
   d.bias = a->bias; d.rowbias = a->rowbias; d.rows_per_img = a->rows_per_img; d.ld_rowbias = a->ld_rowbias;
   d.residual = a->residual; d.ldr = a->ldr;
   d.out_f32 = a->out_f32; d.ldo32 = a->ldo32; d.out_bf16 = a->out_bf16; d.ldo16 = a->ldo16;
-  d.act = a->act; d.alpha = a->alpha; d.bn = a->bn;
+  d.act = a->act; d.alpha = a->alpha; d.bn = a->bn; d.fp16 = a->dtype == MADM_DTYPE_FP16;
   GemmLaunch L;
   if (const char* e = gemm_prepare(d, &L)) return fail(e);
   RUN(gemm_launch(L, static_cast<cudaStream_t>(stream)));
 }
 
 int madm_op_groupnorm(const float* x0, int32_t C0, const float* x1, int32_t C1, int32_t B, int32_t HW, const float* gamma,
-                      const float* beta, float eps, int32_t act, float* stats, void* y, void* raw, madm_stream stream) {
+                      const float* beta, float eps, int32_t act, float* stats, void* y, void* raw, int32_t dtype, madm_stream stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(stats, 0, size_t(B) * 64 * sizeof(float), st) != cudaSuccess) return fail("memset failed");
   if (const char* e = groupnorm_stats(x0, C0, x1, C1, B, HW, stats, st)) return fail(e);
-  RUN(groupnorm_apply(x0, C0, x1, C1, B, HW, stats, gamma, beta, eps, act, y, raw, st));
+  RUN(groupnorm_apply(x0, C0, x1, C1, B, HW, stats, gamma, beta, eps, act, y, raw, dtype == MADM_DTYPE_FP16, st));
 }
 
 int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y,
-                      madm_stream stream) {
-  RUN(layernorm(x, M, C, gamma, beta, eps, y, static_cast<cudaStream_t>(stream)));
+                      int32_t dtype, madm_stream stream) {
+  RUN(layernorm(x, M, C, gamma, beta, eps, y, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
-int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p, madm_stream stream) {
-  RUN(softmax_rows(s, R, L, p, static_cast<cudaStream_t>(stream)));
+int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p, int32_t dtype, madm_stream stream) {
+  RUN(softmax_rows(s, R, L, p, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
 int madm_op_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o, int32_t ldo,
                       int32_t B, int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bs, int64_t kv_bs, int64_t o_bs,
-                      float scale, madm_stream stream) {
-  RUN(flash_attention(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, static_cast<cudaStream_t>(stream)));
+                      float scale, int32_t dtype, madm_stream stream) {
+  RUN(flash_attention(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, dtype == MADM_DTYPE_FP16,
+                      static_cast<cudaStream_t>(stream)));
 }
 
 int madm_op_pack_linear(const float* w, int32_t N, int32_t K, const float* la, const float* lb, int32_t r, float scale, void* out,
-                        int32_t ldo, madm_stream stream) {
-  RUN(pack_linear_weight(w, N, K, la, lb, r, scale, ldo ? ldo : K, out, static_cast<cudaStream_t>(stream)));
+                        int32_t ldo, int32_t dtype, madm_stream stream) {
+  RUN(pack_linear_weight(w, N, K, la, lb, r, scale, ldo ? ldo : K, out, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
-int madm_op_pack_conv(const float* w, int32_t N, int32_t C, int32_t taps, int32_t Cpad, void* out, int32_t ldo, madm_stream stream) {
+int madm_op_pack_conv(const float* w, int32_t N, int32_t C, int32_t taps, int32_t Cpad, void* out, int32_t ldo, int32_t dtype,
+                      madm_stream stream) {
   const int Kpad = taps * Cpad;
-  RUN(pack_conv_weight(w, N, C, taps, Cpad, Kpad, ldo ? ldo : Kpad, out, static_cast<cudaStream_t>(stream)));
+  RUN(pack_conv_weight(w, N, C, taps, Cpad, Kpad, ldo ? ldo : Kpad, out, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
-int madm_op_pack_geglu(const float* w, const float* bias, int32_t C4, int32_t K, void* out, float* out_bias, madm_stream stream) {
-  RUN(pack_geglu_weight(w, bias, C4, K, out, out_bias, static_cast<cudaStream_t>(stream)));
+int madm_op_pack_geglu(const float* w, const float* bias, int32_t C4, int32_t K, void* out, float* out_bias, int32_t dtype,
+                       madm_stream stream) {
+  RUN(pack_geglu_weight(w, bias, C4, K, out, out_bias, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
-int madm_op_space_to_depth(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out, madm_stream stream) {
-  RUN(space_to_depth(x, B, H, W, C, out, static_cast<cudaStream_t>(stream)));
+int madm_op_space_to_depth(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out, int32_t dtype, madm_stream stream) {
+  RUN(space_to_depth(x, B, H, W, C, out, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
-int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out, madm_stream stream) {
-  RUN(upsample_nearest2x(x, B, H, W, C, out, static_cast<cudaStream_t>(stream)));
+int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out, int32_t dtype, madm_stream stream) {
+  RUN(upsample_nearest2x(x, B, H, W, C, out, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
-int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out, int32_t* range_flag, madm_stream stream) {
-  RUN(image_im2col(img, B, H, W, out, range_flag, static_cast<cudaStream_t>(stream)));
+int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out, int32_t* range_flag, int32_t dtype,
+                         madm_stream stream) {
+  RUN(image_im2col(img, B, H, W, out, range_flag, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
 int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, const float* s, const float* gs, const float* bs,

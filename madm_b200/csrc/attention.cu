@@ -3,9 +3,8 @@
 // are double-buffered in shared memory with cp.async; S = QK^T and O += PV run on the warp-level tensor-core path
 // (mma.sync m16n8k16 bf16, fp32 accumulate) with an online softmax in registers (exp2, fp32 running max/sum).
 // Round-1 implementation: the tcgen05/TMEM version (S and O accumulators in TMEM) is the planned replacement.
+#include "cvt.cuh"
 #include "kernels.h"
-
-#include <cuda_bf16.h>
 
 namespace madm {
 
@@ -27,15 +26,23 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t&
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+template <bool FP16>
+__device__ __forceinline__ void mma_16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  if constexpr (FP16) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  } else {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
 }
+template <bool FP16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
+  return pack2_16(a, b, FP16 ? 1 : 0);
 }
 
 template <int D>
@@ -48,22 +55,22 @@ struct AttnCfg {
 };
 
 template <int D>
-__device__ __forceinline__ void load_tile(uint8_t* smem, const __nv_bfloat16* g, int ld, int row0, int nrows_total, int tid) {
+__device__ __forceinline__ void load_tile(uint8_t* smem, const uint16_t* g, int ld, int row0, int nrows_total, int tid) {
   using C = AttnCfg<D>;
   for (int i = tid; i < 64 * C::CHUNKS; i += 128) {
     const int r = i / C::CHUNKS;
     const int ch = i - r * C::CHUNKS;
     const int gr = row0 + r;
     const bool ok = gr < nrows_total;
-    const __nv_bfloat16* src = g + size_t(ok ? gr : 0) * ld + ch * 8;
+    const uint16_t* src = g + size_t(ok ? gr : 0) * ld + ch * 8;
     cp_async16(s_u32(smem + r * C::RS + ch * 16), src, ok ? 16 : 0);
   }
 }
 
-template <int D>
-__global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ K,
-                                                         int ldk, const __nv_bfloat16* __restrict__ V, int ldv,
-                                                         __nv_bfloat16* __restrict__ O, int ldo, int Nq, int Nk, long q_bs, long kv_bs,
+template <int D, bool FP16>
+__global__ void __launch_bounds__(128) flash_attn_kernel(const uint16_t* __restrict__ Q, int ldq, const uint16_t* __restrict__ K,
+                                                         int ldk, const uint16_t* __restrict__ V, int ldv,
+                                                         uint16_t* __restrict__ O, int ldo, int Nq, int Nk, long q_bs, long kv_bs,
                                                          long o_bs, float scale_log2) {
   using C = AttnCfg<D>;
   constexpr int DP = C::DP;
@@ -75,9 +82,9 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __
   uint8_t* sV = smem + 3 * C::TILE;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
-  const __nv_bfloat16* Qg = Q + size_t(b) * q_bs + h * D;
-  const __nv_bfloat16* Kg = K + size_t(b) * kv_bs + h * D;
-  const __nv_bfloat16* Vg = V + size_t(b) * kv_bs + h * D;
+  const uint16_t* Qg = Q + size_t(b) * q_bs + h * D;
+  const uint16_t* Kg = K + size_t(b) * kv_bs + h * D;
+  const uint16_t* Vg = V + size_t(b) * kv_bs + h * D;
 
   // zero the padded head-dim columns once (cp.async never writes them)
   if (DP > D) {
@@ -130,8 +137,8 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __
         uint32_t b0, b1, b2, b3;
         const uint32_t addr = kb + (np * 16 + (lane & 7) + ((lane >> 4) << 3)) * C::RS + ks * 32 + ((lane >> 3) & 1) * 16;
         ldsm_x4(addr, b0, b1, b2, b3);
-        mma_bf16(s[2 * np], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
-        mma_bf16(s[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
+        mma_16<FP16>(s[2 * np], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b0, b1);
+        mma_16<FP16>(s[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
       }
     }
     // ---- online softmax (rows lane/4 and lane/4+8)
@@ -166,8 +173,8 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __
       const float p2 = exp2f(s[i][2] - mx[1]), p3 = exp2f(s[i][3] - mx[1]);
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
-      pf[i][0] = pack2(p0, p1);
-      pf[i][1] = pack2(p2, p3);
+      pf[i][0] = pack2<FP16>(p0, p1);
+      pf[i][1] = pack2<FP16>(p2, p3);
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -189,8 +196,8 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __
         uint32_t b0, b1, b2, b3;
         const uint32_t addr = vb + (kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3)) * C::RS + np * 32 + (lane >> 4) * 16;
         ldsm_x4_t(addr, b0, b1, b2, b3);
-        mma_bf16(o[2 * np], a0, a1, a2, a3, b0, b1);
-        mma_bf16(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
+        mma_16<FP16>(o[2 * np], a0, a1, a2, a3, b0, b1);
+        mma_16<FP16>(o[2 * np + 1], a0, a1, a2, a3, b2, b3);
       }
     }
     __syncthreads();  // everyone done with buf before it is refilled two iterations later
@@ -199,42 +206,42 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __
   // ---- normalise and store
   const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
   const int r0 = q0 + warp * 16 + (lane >> 2);
-  __nv_bfloat16* Og = O + size_t(b) * o_bs + h * D;
+  uint16_t* Og = O + size_t(b) * o_bs + h * D;
 #pragma unroll
   for (int i = 0; i < NT; ++i) {
     const int col = i * 8 + 2 * (lane & 3);
     if (col < D) {
-      if (r0 < Nq) *reinterpret_cast<uint32_t*>(Og + size_t(r0) * ldo + col) = pack2(o[i][0] * inv0, o[i][1] * inv0);
-      if (r0 + 8 < Nq) *reinterpret_cast<uint32_t*>(Og + size_t(r0 + 8) * ldo + col) = pack2(o[i][2] * inv1, o[i][3] * inv1);
+      if (r0 < Nq) *reinterpret_cast<uint32_t*>(Og + size_t(r0) * ldo + col) = pack2<FP16>(o[i][0] * inv0, o[i][1] * inv0);
+      if (r0 + 8 < Nq) *reinterpret_cast<uint32_t*>(Og + size_t(r0 + 8) * ldo + col) = pack2<FP16>(o[i][2] * inv1, o[i][3] * inv1);
     }
   }
 }
 
-template <int D>
+template <int D, bool FP16>
 static const char* launch_attn(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
                                int heads, int Nq, int Nk, long q_bs, long kv_bs, long o_bs, float scale, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(flash_attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<D>::SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(flash_attn_kernel<D, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<D>::SMEM) != cudaSuccess)
       return "attention: cudaFuncSetAttribute failed";
     attr = true;
   }
   dim3 grid((Nq + 63) / 64, heads, B);
-  flash_attn_kernel<D><<<grid, 128, AttnCfg<D>::SMEM, st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(k), ldk,
-      reinterpret_cast<const __nv_bfloat16*>(v), ldv, reinterpret_cast<__nv_bfloat16*>(o), ldo, Nq, Nk, q_bs, kv_bs, o_bs,
+  flash_attn_kernel<D, FP16><<<grid, 128, AttnCfg<D>::SMEM, st>>>(
+      reinterpret_cast<const uint16_t*>(q), ldq, reinterpret_cast<const uint16_t*>(k), ldk,
+      reinterpret_cast<const uint16_t*>(v), ldv, reinterpret_cast<uint16_t*>(o), ldo, Nq, Nk, q_bs, kv_bs, o_bs,
       scale * 1.4426950408889634f);
   return cudaGetLastError() == cudaSuccess ? nullptr : "attention: launch failed";
 }
 
 const char* flash_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
-                            int heads, int d, int Nq, int Nk, long q_bs, long kv_bs, long o_bs, float scale, cudaStream_t st) {
+                            int heads, int d, int Nq, int Nk, long q_bs, long kv_bs, long o_bs, float scale, int fp16, cudaStream_t st) {
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 2) return "attention: row pitches must be multiples of 8 elements";
   if (Nk < 1 || Nq < 1) return "attention: empty problem";
   switch (d) {
-    case 40: return launch_attn<40>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, q_bs, kv_bs, o_bs, scale, st);
-    case 80: return launch_attn<80>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, q_bs, kv_bs, o_bs, scale, st);
-    case 160: return launch_attn<160>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, q_bs, kv_bs, o_bs, scale, st);
+    case 40: return fp16 ? launch_attn<40, true>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, q_bs, kv_bs, o_bs, scale, st) : launch_attn<40, false>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, q_bs, kv_bs, o_bs, scale, st);
+    case 80: return fp16 ? launch_attn<80, true>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, q_bs, kv_bs, o_bs, scale, st) : launch_attn<80, false>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, q_bs, kv_bs, o_bs, scale, st);
+    case 160: return fp16 ? launch_attn<160, true>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, q_bs, kv_bs, o_bs, scale, st) : launch_attn<160, false>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nk, q_bs, kv_bs, o_bs, scale, st);
   }
   return "attention: unsupported head dim (40, 80, 160)";
 }

@@ -1,24 +1,15 @@
 // Small HBM-bound data-movement kernels around the GEMM path: input normalisation + first-layer im2col,
 // q-sample (DDPM add_noise with the shared noise) fused with the UNet conv_in im2col, timestep sinusoid,
 // space-to-depth for the stride-2 convs, nearest-2x upsample, and layout conversions.
+#include "cvt.cuh"
 #include "kernels.h"
-
-#include <cuda_bf16.h>
 
 namespace madm {
 
-__device__ __forceinline__ uint2 pack4(float a, float b, float c, float d) {
-  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
-  __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
-  uint2 r;
-  r.x = *reinterpret_cast<uint32_t*>(&lo);
-  r.y = *reinterpret_cast<uint32_t*>(&hi);
-  return r;
-}
 
 // ------------------------------------------------------------------ image -> normalised 3x3 im2col rows (K padded to 64)
 // One thread per output pixel writes its 128-byte row: k = (ky*3+kx)*3 + c for k < 27, zeros after.
-__global__ void image_im2col_kernel(const float* __restrict__ img, int B, int H, int W, __nv_bfloat16* __restrict__ out,
+__global__ void image_im2col_kernel(const float* __restrict__ img, int B, int H, int W, int fp16, uint16_t* __restrict__ out,
                                     int* __restrict__ range_flag) {
   const long idx = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const long total = long(B) * H * W;
@@ -51,9 +42,9 @@ __global__ void image_im2col_kernel(const float* __restrict__ img, int B, int H,
 #pragma unroll
   for (int j = 0; j < 28; j += 8) {
     uint4 pk;
-    const uint2 a = pack4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    const uint2 a = pack4_16(v[j], v[j + 1], v[j + 2], v[j + 3], fp16);
     uint2 c2 = make_uint2(0u, 0u);
-    if (j + 4 < 28) c2 = pack4(v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+    if (j + 4 < 28) c2 = pack4_16(v[j + 4], v[j + 5], v[j + 6], v[j + 7], fp16);
     pk.x = a.x; pk.y = a.y; pk.z = c2.x; pk.w = c2.y;
     o[j / 8] = pk;
   }
@@ -61,9 +52,9 @@ __global__ void image_im2col_kernel(const float* __restrict__ img, int B, int H,
   for (int j = 4; j < 8; ++j) o[j] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-const char* image_im2col(const float* img, int B, int H, int W, void* out, int* range_flag, cudaStream_t st) {
+const char* image_im2col(const float* img, int B, int H, int W, void* out, int* range_flag, int fp16, cudaStream_t st) {
   const long total = long(B) * H * W;
-  image_im2col_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(img, B, H, W, reinterpret_cast<__nv_bfloat16*>(out), range_flag);
+  image_im2col_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(img, B, H, W, fp16, reinterpret_cast<uint16_t*>(out), range_flag);
   return cudaGetLastError() == cudaSuccess ? nullptr : "image_im2col launch failed";
 }
 
@@ -90,8 +81,8 @@ __global__ void qsample_kernel(const float* __restrict__ lat, const float* __res
   }
 }
 
-__global__ void latent_im2col_kernel(const float* __restrict__ noisy /*[B,H,W,4]*/, int B, int H, int W,
-                                     __nv_bfloat16* __restrict__ out) {
+__global__ void latent_im2col_kernel(const float* __restrict__ noisy /*[B,H,W,4]*/, int B, int H, int W, int fp16,
+                                     uint16_t* __restrict__ out) {
   const long idx = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= long(B) * H * W) return;
   const int x = int(idx % W);
@@ -105,7 +96,7 @@ __global__ void latent_im2col_kernel(const float* __restrict__ noisy /*[B,H,W,4]
       const int yy = y + ky - 1, xx = x + kx - 1;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = *reinterpret_cast<const float4*>(noisy + ((size_t(b) * H + yy) * W + xx) * 4);
-      o[ky * 3 + kx] = pack4(v.x, v.y, v.z, v.w);
+      o[ky * 3 + kx] = pack4_16(v.x, v.y, v.z, v.w, fp16);
     }
 #pragma unroll
   for (int j = 9; j < 16; ++j) o[j] = make_uint2(0u, 0u);
@@ -118,48 +109,48 @@ const char* qsample(const float* lat, const float* noise_nchw, const int64_t* t,
   return cudaGetLastError() == cudaSuccess ? nullptr : "qsample launch failed";
 }
 
-const char* latent_im2col(const float* noisy_nhwc, int B, int H, int W, void* out_bf16, cudaStream_t st) {
+const char* latent_im2col(const float* noisy_nhwc, int B, int H, int W, void* out_bf16, int fp16, cudaStream_t st) {
   const long total = long(B) * H * W;
-  latent_im2col_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(noisy_nhwc, B, H, W, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  latent_im2col_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(noisy_nhwc, B, H, W, fp16, reinterpret_cast<uint16_t*>(out_bf16));
   return cudaGetLastError() == cudaSuccess ? nullptr : "latent_im2col launch failed";
 }
 
 // ------------------------------------------------------------------ timestep sinusoid
-__global__ void timestep_sinusoid_kernel(const int64_t* __restrict__ t, int B, __nv_bfloat16* __restrict__ out) {
+__global__ void timestep_sinusoid_kernel(const int64_t* __restrict__ t, int B, int fp16, uint16_t* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 160) return;
   const int b = i / 160, k = i % 160;
   const float freq = expf(-9.210340371976184f * float(k) / 160.0f);  // ln(10000)
   const float ang = float(t[b]) * freq;
-  out[size_t(b) * 320 + k] = __float2bfloat16_rn(cosf(ang));
-  out[size_t(b) * 320 + 160 + k] = __float2bfloat16_rn(sinf(ang));
+  out[size_t(b) * 320 + k] = cvt_16(cosf(ang), fp16);
+  out[size_t(b) * 320 + 160 + k] = cvt_16(sinf(ang), fp16);
 }
 
-const char* timestep_sinusoid(const int64_t* t, int B, void* out_bf16, cudaStream_t st) {
-  timestep_sinusoid_kernel<<<(B * 160 + 127) / 128, 128, 0, st>>>(t, B, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+const char* timestep_sinusoid(const int64_t* t, int B, void* out_bf16, int fp16, cudaStream_t st) {
+  timestep_sinusoid_kernel<<<(B * 160 + 127) / 128, 128, 0, st>>>(t, B, fp16, reinterpret_cast<uint16_t*>(out_bf16));
   return cudaGetLastError() == cudaSuccess ? nullptr : "timestep_sinusoid launch failed";
 }
 
 // ------------------------------------------------------------------ fp32 (+add) (+act) -> bf16 / fp32
-__global__ void f32_to_bf16_kernel(const float* __restrict__ x, const float* __restrict__ add, long n, int act,
-                                   __nv_bfloat16* __restrict__ y, float* __restrict__ yf) {
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, const float* __restrict__ add, long n, int act, int fp16,
+                                   uint16_t* __restrict__ y, float* __restrict__ yf) {
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = x[i];
   if (add) v += add[i];
   if (yf) yf[i] = v;
   if (act == ACT_SILU) v = v / (1.0f + __expf(-v));
-  if (y) y[i] = __float2bfloat16_rn(v);
+  if (y) y[i] = cvt_16(v, fp16);
 }
 
-const char* f32_to_bf16(const float* x, const float* add, long n, int act, void* y, float* yf, cudaStream_t st) {
-  f32_to_bf16_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(x, add, n, act, reinterpret_cast<__nv_bfloat16*>(y), yf);
+const char* f32_to_bf16(const float* x, const float* add, long n, int act, void* y, float* yf, int fp16, cudaStream_t st) {
+  f32_to_bf16_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(x, add, n, act, fp16, reinterpret_cast<uint16_t*>(y), yf);
   return cudaGetLastError() == cudaSuccess ? nullptr : "f32_to_bf16 launch failed";
 }
 
 // ------------------------------------------------------------------ space-to-depth (stride-2 conv input), fp32 -> bf16
 // out[phase][b][y/2][x/2][c], phase = (y&1)*2 + (x&1)
-__global__ void space_to_depth_kernel(const float* __restrict__ x, int B, int H, int W, int C, __nv_bfloat16* __restrict__ out) {
+__global__ void space_to_depth_kernel(const float* __restrict__ x, int B, int H, int W, int C, int fp16, uint16_t* __restrict__ out) {
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;  // one float4 per thread
   const int Q = C >> 2;
   const long total = long(B) * H * W * Q;
@@ -173,18 +164,18 @@ __global__ void space_to_depth_kernel(const float* __restrict__ x, int B, int H,
   const int ph = (yy & 1) * 2 + (xx & 1);
   const int H2 = H >> 1, W2 = W >> 1;
   const size_t o = (((size_t(ph) * B + b) * H2 + (yy >> 1)) * W2 + (xx >> 1)) * C + c;
-  *reinterpret_cast<uint2*>(out + o) = pack4(v.x, v.y, v.z, v.w);
+  *reinterpret_cast<uint2*>(out + o) = pack4_16(v.x, v.y, v.z, v.w, fp16);
 }
 
-const char* space_to_depth(const float* x, int B, int H, int W, int C, void* out, cudaStream_t st) {
+const char* space_to_depth(const float* x, int B, int H, int W, int C, void* out, int fp16, cudaStream_t st) {
   if ((H | W) & 1 || C % 4) return "space_to_depth: H, W must be even and C % 4 == 0";
   const long total = long(B) * H * W * (C / 4);
-  space_to_depth_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(x, B, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
+  space_to_depth_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(x, B, H, W, C, fp16, reinterpret_cast<uint16_t*>(out));
   return cudaGetLastError() == cudaSuccess ? nullptr : "space_to_depth launch failed";
 }
 
 // ------------------------------------------------------------------ nearest 2x upsample, fp32 -> bf16
-__global__ void upsample2x_kernel(const float* __restrict__ x, int B, int H, int W, int C, __nv_bfloat16* __restrict__ out) {
+__global__ void upsample2x_kernel(const float* __restrict__ x, int B, int H, int W, int C, int fp16, uint16_t* __restrict__ out) {
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;  // one float4 of the INPUT per thread -> 4 outputs
   const int Q = C >> 2;
   const long total = long(B) * H * W * Q;
@@ -195,7 +186,7 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, int B, int H, int
   const int yy = int((pix / W) % H);
   const int b = int(pix / (long(W) * H));
   const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
-  const uint2 pk = pack4(v.x, v.y, v.z, v.w);
+  const uint2 pk = pack4_16(v.x, v.y, v.z, v.w, fp16);
   const int W2 = W * 2;
   const size_t row0 = ((size_t(b) * H * 2 + yy * 2) * W2 + xx * 2) * C + c;
   *reinterpret_cast<uint2*>(out + row0) = pk;
@@ -204,10 +195,10 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, int B, int H, int
   *reinterpret_cast<uint2*>(out + row0 + size_t(W2) * C + C) = pk;
 }
 
-const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void* out, cudaStream_t st) {
+const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void* out, int fp16, cudaStream_t st) {
   if (C % 4) return "upsample_nearest2x: C % 4 != 0";
   const long total = long(B) * H * W * (C / 4);
-  upsample2x_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(x, B, H, W, C, reinterpret_cast<__nv_bfloat16*>(out));
+  upsample2x_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(x, B, H, W, C, fp16, reinterpret_cast<uint16_t*>(out));
   return cudaGetLastError() == cudaSuccess ? nullptr : "upsample_nearest2x launch failed";
 }
 

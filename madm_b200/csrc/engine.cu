@@ -82,6 +82,7 @@ struct Plan {
 
 struct madm_ctx {
   int device = 0;
+  int fp16 = 1;  // compute dtype of GEMM operands (MADM_DTYPE_FP16 default)
   std::string err;
   std::unordered_map<std::string, ParamRef> params;
   std::vector<PackEntry> pack;
@@ -292,8 +293,10 @@ struct Builder {
       plan->optional.push_back(optional ? 1 : 0);
     }
   }
-  void gemm(const GemmDesc& d) {
+  void gemm(const GemmDesc& d0) {
     if (mode != PLAN) { ++n_ops; return; }
+    GemmDesc d = d0;
+    d.fp16 = ctx->fp16;
     GemmLaunch L;
     if (const char* e = gemm_prepare(d, &L)) fail(MADM_EINVAL, std::string(e));
     emit([L](cudaStream_t st) { return gemm_launch(L, st); });
@@ -335,7 +338,8 @@ struct Builder {
     const float* p0 = x0.f.p; const float* p1 = x1 ? x1->f.p : nullptr;
     const int Bn = x0.B, HW = x0.HW();
     emit([=](cudaStream_t st) { return groupnorm_stats(p0, C0, p1, C1, Bn, HW, stats, st); });
-    emit([=](cudaStream_t st) { return groupnorm_apply(p0, C0, p1, C1, Bn, HW, stats, g, b, eps, actfn, y, raw, st); });
+    const int f16 = ctx->fp16;
+    emit([=](cudaStream_t st) { return groupnorm_apply(p0, C0, p1, C1, Bn, HW, stats, g, b, eps, actfn, y, raw, f16, st); });
   }
 };
 
@@ -344,6 +348,7 @@ struct Model {
   Builder& b;
   explicit Model(Builder& bb) : b(bb) {}
   bool dry() const { return b.mode != PLAN; }
+  int f16() const { return b.ctx->fp16; }
   const float* P(const std::string& n, int64_t numel = -1) { return b.mode == LAYOUT ? nullptr : b.param(n, numel); }
 
   // ---- time embedding projections of all 22 UNet ResBlocks, stacked along N
@@ -434,7 +439,8 @@ struct Model {
     auto ln = [&](const std::string& name, bf16* y) {
       const float* g = P(name + ".weight", C); const float* be = P(name + ".bias", C);
       const float* src = hs.p; const int Mi = int(M);
-      b.emit([=](cudaStream_t st) { return layernorm(src, Mi, C, g, be, 1e-5f, y, st); });
+      const int h16 = f16();
+      b.emit([=](cudaStream_t st) { return layernorm(src, Mi, C, g, be, 1e-5f, y, h16, st); });
     };
     // --- self attention
     B16T l1 = b.b16(size_t(M) * C);
@@ -448,10 +454,10 @@ struct Model {
       d.out_bf16 = qkv.p; d.ldo16 = 3 * C; b.gemm(d); }
     b.free(l1);
     B16T att = b.b16(size_t(M) * C);
-    { const bf16* q = qkv.p; bf16* o = att.p; const int n_tok = H * W; const float sc = 1.0f / sqrtf(float(d_head));
+    { const bf16* q = qkv.p; bf16* o = att.p; const int n_tok = H * W; const float sc = 1.0f / sqrtf(float(d_head)); const int h16 = f16();
       b.emit([=](cudaStream_t st) {
         return flash_attention(q, 3 * C, q + C, 3 * C, q + 2 * C, 3 * C, o, C, Bn, heads, d_head, n_tok, n_tok, long(n_tok) * 3 * C,
-                               long(n_tok) * 3 * C, long(n_tok) * C, sc, st);
+                               long(n_tok) * 3 * C, long(n_tok) * C, sc, h16, st);
       }); }
     b.free(qkv);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(att.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
@@ -465,10 +471,10 @@ struct Model {
       d.w = b.pw(b.linear_w(tb + ".attn2.to_q", C, C, true)); d.out_bf16 = q2.p; d.ldo16 = C; b.gemm(d); }
     b.free(l2);
     { const bf16* q = q2.p; bf16* o = att.p; const int n_tok = H * W; const float sc = 1.0f / sqrtf(float(d_head));
-      const int off = kv_off[tb + ".attn2"]; const bf16* kv = kv_all.p; const int ldkv = kv_total;
+      const int off = kv_off[tb + ".attn2"]; const bf16* kv = kv_all.p; const int ldkv = kv_total; const int h16 = f16();
       b.emit([=](cudaStream_t st) {
         return flash_attention(q, C, kv + off, ldkv, kv + off + C, ldkv, o, C, Bn, heads, d_head, n_tok, 77, long(n_tok) * C,
-                               long(77) * ldkv, long(n_tok) * C, sc, st);
+                               long(77) * ldkv, long(n_tok) * C, sc, h16, st);
       }); }
     b.free(q2);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(att.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
@@ -511,7 +517,8 @@ struct Model {
     const int Bn = x.B, H = x.H, W = x.W, C = x.C;
     B16T s2d = b.b16(size_t(x.M()) * C);
     { const float* src = x.f.p; bf16* dst = s2d.p;
-      b.emit([=](cudaStream_t st) { return space_to_depth(src, Bn, H, W, C, dst, st); }); }
+      const int h16 = f16();
+      b.emit([=](cudaStream_t st) { return space_to_depth(src, Bn, H, W, C, dst, h16, st); }); }
     Act out = b.act(Bn, H / 2, W / 2, C, true, false);
     { GemmDesc d; d.seg[0] = Builder::seg_s2(s2d.p, Bn, H / 2, W / 2, C, pad1); d.M = int(out.M()); d.N = C; d.Nw = C;
       d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C; b.gemm(d); }
@@ -523,7 +530,8 @@ struct Model {
     const int Bn = x.B, H = x.H, W = x.W, C = x.C;
     B16T up = b.b16(size_t(x.M()) * 4 * C);
     { const float* src = x.f.p; bf16* dst = up.p;
-      b.emit([=](cudaStream_t st) { return upsample_nearest2x(src, Bn, H, W, C, dst, st); }); }
+      const int h16 = f16();
+      b.emit([=](cudaStream_t st) { return upsample_nearest2x(src, Bn, H, W, C, dst, h16, st); }); }
     Act out = b.act(Bn, 2 * H, 2 * W, C, true, false);
     { GemmDesc d; d.seg[0] = Builder::seg_3x3(up.p, Bn, 2 * H, 2 * W, C); d.M = int(out.M()); d.N = C; d.Nw = C;
       d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C; b.gemm(d); }
@@ -560,7 +568,8 @@ struct Model {
       { GemmDesc d; d.seg[0] = Builder::seg_plain(qi, T, C, 2 * C); d.M = T; d.N = T; d.Nw = T; d.w = qi ? qi + C : nullptr; d.ldw = 2 * C;
         d.alpha = 1.0f / sqrtf(float(C)); d.out_f32 = S.p; d.ldo32 = T; b.gemm(d); }
       { const float* s = S.p; bf16* pm = Pm.p;
-        b.emit([=](cudaStream_t st) { return softmax_rows(s, T, T, pm, st); }); }
+        const int h16 = f16();
+        b.emit([=](cudaStream_t st) { return softmax_rows(s, T, T, pm, h16, st); }); }
       { GemmDesc d; d.seg[0] = Builder::seg_plain(Pm.p, T, T); d.M = T; d.N = C; d.Nw = C; d.w = vt.p; d.ldw = T;
         d.bias = P(p + ".to_v.bias", C); d.out_bf16 = o.p ? o.p + size_t(i) * T * C : nullptr; d.ldo16 = C; b.gemm(d); }
     }
@@ -596,8 +605,8 @@ struct Model {
     std::shared_ptr<IoBind> io = dry() ? nullptr : b.plan->io;
     B16T col = b.b16(size_t(Bn) * R * R * 64);
     if (dry()) b.emit(nullptr);
-    else { bf16* dst = col.p;
-      b.emit([=](cudaStream_t st) { return image_im2col(io->a.img, Bn, R, R, dst, io->a.range_flag, st); }); }
+    else { bf16* dst = col.p; const int h16 = f16();
+      b.emit([=](cudaStream_t st) { return image_im2col(io->a.img, Bn, R, R, dst, io->a.range_flag, h16, st); }); }
     Act x = b.act(Bn, R, R, 128, true, false);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(col.p, long(Bn) * R * R, 64); d.M = Bn * R * R; d.N = 128; d.Nw = 128;
       d.w = b.pw(b.conv_w(e + "conv_in", 128, 3, 9, /*Cpad=*/3)); d.bias = P(e + "conv_in.bias", 128); d.out_f32 = x.f.p; d.ldo32 = 128; b.gemm(d); }
@@ -661,12 +670,13 @@ struct Model {
         if (io->a.noisy_latents_in) return nchw_to_nhwc4(io->a.noisy_latents_in, Bn, 4096, nz, st);
         return qsample(lat, io->a.shared_noise, io->a.timesteps, ac, Bn, 4096, nz, io->a.noisy_latents, st);
       });
-      b.emit([=](cudaStream_t st) { return latent_im2col(nz, Bn, 64, 64, cdst, st); });
+      const int h16 = f16();
+      b.emit([=](cudaStream_t st) { return latent_im2col(nz, Bn, 64, 64, cdst, h16, st); });
     }
     // ---- time embedding: sinusoid -> linear_1 -> SiLU -> linear_2 (+ cond_emb) -> SiLU -> all 22 time_emb_proj at once
     B16T sinus = b.b16(size_t(Bn) * 320);
     if (dry()) b.emit(nullptr);
-    else { bf16* dst = sinus.p; b.emit([=](cudaStream_t st) { return timestep_sinusoid(io->a.timesteps, Bn, dst, st); }); }
+    else { bf16* dst = sinus.p; const int h16 = f16(); b.emit([=](cudaStream_t st) { return timestep_sinusoid(io->a.timesteps, Bn, dst, h16, st); }); }
     B16T e1 = b.b16(size_t(Bn) * 1280);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(sinus.p, Bn, 320); d.M = Bn; d.N = 1280; d.Nw = 1280;
       d.w = b.pw(b.linear_w(kUnet + "time_embedding.linear_1", 1280, 320, false)); d.bias = P(kUnet + "time_embedding.linear_1.bias", 1280);
@@ -677,8 +687,8 @@ struct Model {
       d.out_f32 = emb.p; d.ldo32 = 1280; b.gemm(d); }
     B16T emb_act = b.b16(size_t(Bn) * 1280);
     if (dry()) b.emit(nullptr);
-    else { const float* src = emb.p; bf16* dst = emb_act.p;
-      b.emit([=](cudaStream_t st) { return f32_to_bf16(src, io->a.cond_emb, long(Bn) * 1280, ACT_SILU, dst, nullptr, st); }); }
+    else { const float* src = emb.p; bf16* dst = emb_act.p; const int h16 = f16();
+      b.emit([=](cudaStream_t st) { return f32_to_bf16(src, io->a.cond_emb, long(Bn) * 1280, ACT_SILU, dst, nullptr, h16, st); }); }
     temb_all = b.f32(size_t(Bn) * temb_total);
     { const size_t reg = b.region("temb_w", size_t(temb_total) * 1280 * 2);
       const size_t breg = b.region("temb_b", size_t(temb_total) * 4);
@@ -692,8 +702,8 @@ struct Model {
     // ---- cross-attention K/V of every transformer block in one GEMM
     B16T ctx16 = b.b16(size_t(Bn) * 77 * 768);
     if (dry()) b.emit(nullptr);
-    else { bf16* dst = ctx16.p;
-      b.emit([=](cudaStream_t st) { return f32_to_bf16(io->a.cond_inputs, nullptr, long(Bn) * 77 * 768, ACT_NONE, dst, nullptr, st); }); }
+    else { bf16* dst = ctx16.p; const int h16 = f16();
+      b.emit([=](cudaStream_t st) { return f32_to_bf16(io->a.cond_inputs, nullptr, long(Bn) * 77 * 768, ACT_NONE, dst, nullptr, h16, st); }); }
     kv_all = b.b16(size_t(Bn) * 77 * kv_total);
     { const size_t reg = b.region("xattn_kv", size_t(kv_total) * 768 * 2);
       for (auto& l : xattn_layers) {
@@ -938,6 +948,18 @@ int madm_destroy(madm_ctx* ctx) {
   return MADM_OK;
 }
 
+int madm_set_compute_dtype(madm_ctx* ctx, int32_t dtype) {
+  if (!ctx || (dtype != MADM_DTYPE_BF16 && dtype != MADM_DTYPE_FP16)) return set_err(ctx, MADM_EINVAL, "madm_set_compute_dtype: bad argument");
+  const int f = dtype == MADM_DTYPE_FP16 ? 1 : 0;
+  if (f != ctx->fp16) {
+    ctx->fp16 = f;
+    ctx->plans.clear();
+  }
+  return MADM_OK;
+}
+
+int madm_get_compute_dtype(const madm_ctx* ctx) { return ctx && !ctx->fp16 ? MADM_DTYPE_BF16 : MADM_DTYPE_FP16; }
+
 int madm_set_tensors(madm_ctx* ctx, const madm_tensor* named, int32_t n) {
   if (!ctx || (!named && n > 0)) return set_err(ctx, MADM_EINVAL, "madm_set_tensors: null argument");
   for (int i = 0; i < n; ++i) {
@@ -982,7 +1004,7 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float sc
         const ParamRef* w = get(e.src);
         if (!w) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
         if (w->numel() != int64_t(e.N) * e.C * e.taps) return set_err(ctx, MADM_EINVAL, "unexpected shape: " + e.src);
-        err = pack_conv_weight(w->p, e.N, e.C, e.taps, e.Cpad, e.Kpad, e.ldo, base + e.off, st);
+        err = pack_conv_weight(w->p, e.N, e.C, e.taps, e.Cpad, e.Kpad, e.ldo, base + e.off, ctx->fp16, st);
         break;
       }
       case PK_LINEAR: {
@@ -1001,19 +1023,20 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float sc
           if (A->shape[1] != e.C || Bm->shape[0] != e.N || Bm->shape[1] != r) return set_err(ctx, MADM_EINVAL, "LoRA shape mismatch: " + e.src);
           la = A->p; lb = Bm->p;
         }
-        err = pack_linear_weight(w->p, e.N, e.C, la, lb, r, scale, e.ldo, base + e.off, st);
+        err = pack_linear_weight(w->p, e.N, e.C, la, lb, r, scale, e.ldo, base + e.off, ctx->fp16, st);
         break;
       }
       case PK_GEGLU: {
         const ParamRef* w = get(e.src); const ParamRef* bb = get(e.src2);
         if (!w || !bb) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
-        err = pack_geglu_weight(w->p, bb->p, e.N, e.C, base + e.off, reinterpret_cast<float*>(base + e.bias_off), st);
+        err = pack_geglu_weight(w->p, bb->p, e.N, e.C, base + e.off, reinterpret_cast<float*>(base + e.bias_off), ctx->fp16, st);
         break;
       }
       case PK_VAE_HEAD: {
         const ParamRef *w = get(e.src), *b1 = get(e.src2), *wq = get(e.src3), *bq = get(e.src4);
         if (!w || !b1 || !wq || !bq) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
-        err = pack_vae_latent_head(w->p, b1->p, wq->p, bq->p, 0.18215f, e.C, base + e.off, reinterpret_cast<float*>(base + e.bias_off), st);
+        err = pack_vae_latent_head(w->p, b1->p, wq->p, bq->p, 0.18215f, e.C, base + e.off, reinterpret_cast<float*>(base + e.bias_off),
+                                   ctx->fp16, st);
         break;
       }
       case PK_F32_COPY: {

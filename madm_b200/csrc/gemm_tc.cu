@@ -12,6 +12,7 @@
 // (tcgen05.ld -> registers -> fused bias / time-embedding row bias / fp32 residual / SiLU / GEGLU -> fp32 and/or bf16 stores).
 // Two CTAs are resident per SM (<=113 KB smem, <=256 TMEM columns each) so one CTA's epilogue overlaps the other's mainloop.
 #include "gemm_tc.h"
+#include "cvt.cuh"
 #include "ptx.cuh"
 
 #include <mutex>
@@ -50,6 +51,7 @@ struct GemmParams {
   float alpha;
   int vec_ok;
   int n_tiles;
+  int fp16;
 };
 
 template <int BN>
@@ -65,10 +67,6 @@ struct Cfg {
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 __device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -148,7 +146,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      const uint32_t idesc = make_idesc_16(BM, BN, p.fp16);
       int stage = 0;
       uint32_t phase = 0;
       for (int kc = 0; kc < total_chunks; ++kc) {
@@ -210,10 +208,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
                 v[t] = h * gelu_erf_f(gt);
               }
               uint4 pk;
-              pk.x = pack_bf16x2(v[0], v[1]);
-              pk.y = pack_bf16x2(v[2], v[3]);
-              pk.z = pack_bf16x2(v[4], v[5]);
-              pk.w = pack_bf16x2(v[6], v[7]);
+              pk.x = pack2_16(v[0], v[1], p.fp16);
+              pk.y = pack2_16(v[2], v[3], p.fp16);
+              pk.z = pack2_16(v[4], v[5], p.fp16);
+              pk.w = pack2_16(v[6], v[7], p.fp16);
               *reinterpret_cast<uint4*>(o16 + j) = pk;
             }
           }
@@ -273,10 +271,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
             }
             if (p.out_bf16) {
               uint4 pk;
-              pk.x = pack_bf16x2(v[0], v[1]);
-              pk.y = pack_bf16x2(v[2], v[3]);
-              pk.z = pack_bf16x2(v[4], v[5]);
-              pk.w = pack_bf16x2(v[6], v[7]);
+              pk.x = pack2_16(v[0], v[1], p.fp16);
+              pk.y = pack2_16(v[2], v[3], p.fp16);
+              pk.z = pack2_16(v[4], v[5], p.fp16);
+              pk.w = pack2_16(v[6], v[7], p.fp16);
               *reinterpret_cast<uint4*>(p.out_bf16 + size_t(m) * p.ldo16 + n) = pk;
             }
           }
@@ -292,7 +290,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
             if (p.act == ACT_SILU) v = silu_f(v);
             else if (p.act == ACT_RELU) v = fmaxf(v, 0.0f);
             if (p.out_f32) p.out_f32[size_t(m) * p.ldo32 + n] = v;
-            if (p.out_bf16) p.out_bf16[size_t(m) * p.ldo16 + n] = __float2bfloat16_rn(v);
+            if (p.out_bf16) reinterpret_cast<uint16_t*>(p.out_bf16)[size_t(m) * p.ldo16 + n] = cvt_16(v, p.fp16);
           }
         }
       }
@@ -330,7 +328,7 @@ static const char* encode_map(CUtensorMap* tm, const void* ptr, int rank, const 
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return "cuTensorMapEncodeTiled unavailable (no CUDA driver)";
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -477,6 +475,7 @@ const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
              (!d.out_bf16 || (al16(d.out_bf16) && d.ldo16 % 8 == 0));
   if (d.act == ACT_GEGLU && !p.vec_ok) return "gemm: GEGLU epilogue needs 16B-aligned outputs";
   p.n_tiles = (p.N + L.bn - 1) / L.bn;
+  p.fp16 = d.fp16;
   switch (L.bn) {
     case 16: return launch_bn<16>(L, p, stream);
     case 32: return launch_bn<32>(L, p, stream);

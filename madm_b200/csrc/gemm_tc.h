@@ -41,6 +41,7 @@ struct GemmDesc {
   int act = ACT_NONE;
   float alpha = 1.0f;               // scales the accumulator before bias
   int bn = 0;                       // N tile (0 = auto)
+  int fp16 = 0;                     // operand / 16-bit output dtype: 0 = bf16, 1 = fp16
 };
 
 struct GemmLaunch {  // prepared launch: tensor maps encoded once, replayed per forward

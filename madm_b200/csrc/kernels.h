@@ -1,4 +1,6 @@
-// Host-side launchers of the non-GEMM kernels.  Every function enqueues on `st`, never synchronises, and returns
+// Host-side launchers of the non-GEMM kernels.  "_bf16" in a parameter name means "16-bit operand tensor": its element
+// type is bf16 or fp16 according to the `fp16` flag (the compute dtype is a per-context runtime choice).
+//  Every function enqueues on `st`, never synchronises, and returns
 // nullptr on success or a static error string.
 #pragma once
 #include <cuda_runtime.h>
@@ -12,10 +14,10 @@ namespace madm {
 const char* groupnorm_stats(const float* x0, int C0, const float* x1, int C1, int B, int HW, float* stats, cudaStream_t st);
 const char* groupnorm_apply(const float* x0, int C0, const float* x1, int C1, int B, int HW, const float* stats,
                             const float* gamma, const float* beta, float eps, int act, void* y_bf16, void* raw_bf16,
-                            cudaStream_t st);
+                            int fp16, cudaStream_t st);
 const char* layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y_bf16,
-                      cudaStream_t st);
-const char* softmax_rows(const float* s, int R, int L, void* p_bf16, cudaStream_t st);
+                      int fp16, cudaStream_t st);
+const char* softmax_rows(const float* s, int R, int L, void* p_bf16, int fp16, cudaStream_t st);
 const char* gn_add_relu_nchw(const float* a, const float* stats_a, const float* ga, const float* ba, const float* s,
                              const float* stats_s, const float* gs, const float* bs, float eps, int B, int HW, int C,
                              float* out_nchw, cudaStream_t st);
@@ -23,40 +25,41 @@ const char* gn_add_relu_nchw(const float* a, const float* stats_a, const float* 
 // ---- attention.cu : O[b, i, h*d:(h+1)*d] = softmax(Q K^T * scale) V per (image, head); bf16 in/out, fp32 softmax
 const char* flash_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                             int B, int heads, int d, int Nq, int Nk, long q_bstride, long kv_bstride, long o_bstride,
-                            float scale, cudaStream_t st);
+                            float scale, int fp16, cudaStream_t st);
 
 // ---- elementwise.cu
 // img NCHW fp32 in [0,1] -> (img-0.5)/0.5 -> 3x3 im2col rows [B*H*W, 64] bf16 (27 real columns, tap-major (ky,kx,c))
-const char* image_im2col(const float* img, int B, int H, int W, void* out_bf16, int* range_flag, cudaStream_t st);
+const char* image_im2col(const float* img, int B, int H, int W, void* out_bf16, int* range_flag, int fp16, cudaStream_t st);
 // noisy[b,p,:] = sqrt(ac[t_b])*lat[b,p,:] + sqrt(1-ac[t_b])*noise[:,p]  (latents NHWC fp32 [B*HW,4], noise NCHW [4,HW])
 const char* qsample(const float* lat, const float* noise_nchw, const int64_t* t, const float* alphas_cumprod, int B, int HW,
                     float* noisy_nhwc, float* noisy_nchw_or_null, cudaStream_t st);
 // noisy NHWC fp32 [B,H,W,4] -> 3x3 im2col rows [B*H*W, 64] bf16 (36 real columns, tap-major)
-const char* latent_im2col(const float* noisy_nhwc, int B, int H, int W, void* out_bf16, cudaStream_t st);
+const char* latent_im2col(const float* noisy_nhwc, int B, int H, int W, void* out_bf16, int fp16, cudaStream_t st);
 // t[B] -> [B,320] bf16 sinusoid (cos | sin), diffusers Timesteps(320, flip_sin_to_cos=True, shift 0)
-const char* timestep_sinusoid(const int64_t* t, int B, void* out_bf16, cudaStream_t st);
+const char* timestep_sinusoid(const int64_t* t, int B, void* out_bf16, int fp16, cudaStream_t st);
 // generic fp32 -> bf16 with optional SiLU and per-row add (emb + cond_emb)
 const char* f32_to_bf16(const float* x, const float* add_or_null, long n, int act, void* y_bf16, float* y_f32_or_null,
-                        cudaStream_t st);
+                        int fp16, cudaStream_t st);
 // fp32 NHWC [B,H,W,C] -> 4 stride-2 phase images bf16 [4][B][H/2][W/2][C]; phase = (y&1)*2 + (x&1)
-const char* space_to_depth(const float* x, int B, int H, int W, int C, void* out_bf16, cudaStream_t st);
+const char* space_to_depth(const float* x, int B, int H, int W, int C, void* out_bf16, int fp16, cudaStream_t st);
 // fp32 NHWC [B,H,W,C] -> nearest 2x bf16 [B,2H,2W,C]
-const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void* out_bf16, cudaStream_t st);
+const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void* out_bf16, int fp16, cudaStream_t st);
 // fp32 NHWC [B,HW,C] -> NCHW fp32 [B,C,HW]
 const char* nhwc_to_nchw(const float* x, int B, int HW, int C, float* out, cudaStream_t st);
 
 // ---- pack.cu (weight packing; fp32 PyTorch layouts -> bf16 K-major GEMM operands)
 // conv weight [N, C, kh, kw] fp32 -> [N, kh*kw*Cpad] bf16 with K index = tap*Cpad + c (zero fill for c >= C)
-const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out_bf16, cudaStream_t st);
+const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out_bf16, int fp16,
+                             cudaStream_t st);
 // linear weight [N, K] (+ LoRA: + scale * B[N,r] @ A[r,K]) -> bf16 [N, K] written at row offset / interleave
 const char* pack_linear_weight(const float* w, int N, int K, const float* lora_a, const float* lora_b, int r, float scale,
-                               int ldo, void* out_bf16, cudaStream_t st);
+                               int ldo, void* out_bf16, int fp16, cudaStream_t st);
 // GEGLU: rows of W[8C, C] reordered so each 128-row tile holds 64 value rows then their 64 gate rows (bias likewise)
 const char* pack_geglu_weight(const float* w, const float* bias, int C4 /* = 4C */, int K, void* out_bf16, float* out_bias,
-                              cudaStream_t st);
+                              int fp16, cudaStream_t st);
 // fold quant_conv(8->8, 1x1) and the 0.18215 scale into conv_out(512->8, 3x3): rows 0..3 of the product, N padded to 16
 const char* pack_vae_latent_head(const float* w_out /*[8,512,3,3]*/, const float* b_out, const float* w_q /*[8,8]*/,
                                  const float* b_q, float scale, int C, void* out_bf16 /*[16, 9*C]*/, float* out_bias /*[16]*/,
-                                 cudaStream_t st);
+                                 int fp16, cudaStream_t st);
 
 }  // namespace madm

@@ -2,9 +2,8 @@
 // (+SiLU / ReLU, dual-source channel concat, optional raw bf16 copy), LayerNorm, row softmax, and the fused
 // relu(GN(a)+GN(b)) -> NCHW fp32 output of the feature projections.  All loads/stores are 16-byte vectorised and
 // coalesced along the channel axis; statistics are accumulated in fp32 (sum, sum of squares) per (image, group).
+#include "cvt.cuh"
 #include "kernels.h"
-
-#include <cuda_bf16.h>
 
 namespace madm {
 
@@ -14,14 +13,6 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
-__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
-  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b);
-  __nv_bfloat162 hi = __floats2bfloat162_rn(c, d);
-  uint2 r;
-  r.x = *reinterpret_cast<uint32_t*>(&lo);
-  r.y = *reinterpret_cast<uint32_t*>(&hi);
-  return r;
-}
 
 // ---------------------------------------------------------------------------------------------- GroupNorm statistics
 // grid = (slabs, B); block = Q*P threads, Q = C/4 channel quads, P pixel lanes.  Thread (q, pl) owns channels 4q..4q+3
@@ -74,8 +65,8 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
 // is streamed: y = act(x*scale + shift) -> bf16 (and optionally the un-normalised x -> bf16 for a 1x1 shortcut conv).
 __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int HW,
                                 int pix_per_cta, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int act, __nv_bfloat16* __restrict__ y,
-                                __nv_bfloat16* __restrict__ raw) {
+                                const float* __restrict__ beta, float eps, int act, int fp16, uint16_t* __restrict__ y,
+                                uint16_t* __restrict__ raw) {
   extern __shared__ float sm[];  // scale[C], shift[C]
   const int C = C0 + C1;
   const int b = blockIdx.y;
@@ -108,9 +99,9 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
     const float4 sc = *reinterpret_cast<const float4*>(sm + c);
     const float4 sh = *reinterpret_cast<const float4*>(sm + C + c);
     const size_t o = (size_t(b) * HW + p) * C + c;
-    *reinterpret_cast<uint2*>(y + o) = pack4_bf16(act_apply(v.x * sc.x + sh.x, act), act_apply(v.y * sc.y + sh.y, act),
-                                                  act_apply(v.z * sc.z + sh.z, act), act_apply(v.w * sc.w + sh.w, act));
-    if (raw) *reinterpret_cast<uint2*>(raw + o) = pack4_bf16(v.x, v.y, v.z, v.w);
+    *reinterpret_cast<uint2*>(y + o) = pack4_16(act_apply(v.x * sc.x + sh.x, act), act_apply(v.y * sc.y + sh.y, act),
+                                                act_apply(v.z * sc.z + sh.z, act), act_apply(v.w * sc.w + sh.w, act), fp16);
+    if (raw) *reinterpret_cast<uint2*>(raw + o) = pack4_16(v.x, v.y, v.z, v.w, fp16);
   }
 }
 
@@ -143,19 +134,19 @@ const char* groupnorm_stats(const float* x0, int C0, const float* x1, int C1, in
 }
 
 const char* groupnorm_apply(const float* x0, int C0, const float* x1, int C1, int B, int HW, const float* stats,
-                            const float* gamma, const float* beta, float eps, int act, void* y, void* raw, cudaStream_t st) {
+                            const float* gamma, const float* beta, float eps, int act, void* y, void* raw, int fp16, cudaStream_t st) {
   const int C = C0 + C1;
   int P, threads, ppc, slabs;
   gn_geometry(B, HW, C, &P, &threads, &ppc, &slabs);
   const size_t smem = size_t(2) * C * sizeof(float);
-  gn_apply_kernel<<<dim3(slabs, B), 256, smem, st>>>(x0, C0, x1, C1, HW, ppc, stats, gamma, beta, eps, act,
-                                                     reinterpret_cast<__nv_bfloat16*>(y), reinterpret_cast<__nv_bfloat16*>(raw));
+  gn_apply_kernel<<<dim3(slabs, B), 256, smem, st>>>(x0, C0, x1, C1, HW, ppc, stats, gamma, beta, eps, act, fp16,
+                                                     reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_apply launch failed";
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm (warp per row)
 __global__ void layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
+                                 const float* __restrict__ beta, float eps, int fp16, uint16_t* __restrict__ y) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -186,7 +177,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int M, int C, cons
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float rstd = rsqrtf(ss / float(C) + eps);
-  __nv_bfloat16* yr = y + size_t(row) * C;
+  uint16_t* yr = y + size_t(row) * C;
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
     const int q = i * 32 + lane;
@@ -194,26 +185,26 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int M, int C, cons
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
       const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
       *reinterpret_cast<uint2*>(yr + q * 4) =
-          pack4_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
-                     (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+          pack4_16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                   (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w, fp16);
     }
   }
 }
 
-const char* layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y, cudaStream_t st) {
+const char* layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y, int fp16, cudaStream_t st) {
   if (C % 4 != 0 || C > 1280) return "layernorm: C must be a multiple of 4 and <= 1280";
   const int rows_per_cta = 8;
-  layernorm_kernel<<<(M + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, st>>>(x, M, C, gamma, beta, eps,
-                                                                                      reinterpret_cast<__nv_bfloat16*>(y));
+  layernorm_kernel<<<(M + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, st>>>(x, M, C, gamma, beta, eps, fp16,
+                                                                                      reinterpret_cast<uint16_t*>(y));
   return cudaGetLastError() == cudaSuccess ? nullptr : "layernorm launch failed";
 }
 
 // ---------------------------------------------------------------------------------------------- row softmax fp32 -> bf16
 // one CTA (256 threads) per row; L <= 256*32.
-__global__ void softmax_rows_kernel(const float* __restrict__ s, int L, __nv_bfloat16* __restrict__ p) {
+__global__ void softmax_rows_kernel(const float* __restrict__ s, int L, int fp16, uint16_t* __restrict__ p) {
   __shared__ float red[8];
   const float* sr = s + size_t(blockIdx.x) * L;
-  __nv_bfloat16* pr = p + size_t(blockIdx.x) * L;
+  uint16_t* pr = p + size_t(blockIdx.x) * L;
   float v[32];
   float mx = -INFINITY;
 #pragma unroll
@@ -247,13 +238,13 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, int L, __nv_bfl
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     const int j = i * 256 + threadIdx.x;
-    if (j < L) pr[j] = __float2bfloat16_rn(v[i] * inv);
+    if (j < L) pr[j] = cvt_16(v[i] * inv, fp16);
   }
 }
 
-const char* softmax_rows(const float* s, int R, int L, void* p, cudaStream_t st) {
+const char* softmax_rows(const float* s, int R, int L, void* p, int fp16, cudaStream_t st) {
   if (L > 256 * 32) return "softmax_rows: row too long";
-  softmax_rows_kernel<<<R, 256, 0, st>>>(s, L, reinterpret_cast<__nv_bfloat16*>(p));
+  softmax_rows_kernel<<<R, 256, 0, st>>>(s, L, fp16, reinterpret_cast<uint16_t*>(p));
   return cudaGetLastError() == cudaSuccess ? nullptr : "softmax_rows launch failed";
 }
 

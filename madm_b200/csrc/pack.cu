@@ -2,15 +2,14 @@
 // The LoRA update of the active adapter is folded here, once per adapter switch: W' = W + (alpha/r) * B @ A in fp32,
 // rounded to bf16 once, so the forward path runs the plain projection with no extra skinny GEMMs
 // (reference: peft LoRA Linear on to_q/to_k/to_v/to_out.0, modeling/meta_arch/mtmadise.py:115-147).
+#include "cvt.cuh"
 #include "kernels.h"
-
-#include <cuda_bf16.h>
 
 namespace madm {
 
 // out[n, tap*Cpad + c] = w[n, c, tap]  (w is [N, C, taps] contiguous = [N,C,kh,kw]); zero for c >= C and k >= taps*Cpad
-__global__ void pack_conv_kernel(const float* __restrict__ w, int N, int C, int taps, int Cpad, int Kpad, int ldo,
-                                 __nv_bfloat16* __restrict__ out) {
+__global__ void pack_conv_kernel(const float* __restrict__ w, int N, int C, int taps, int Cpad, int Kpad, int ldo, int fp16,
+                                 uint16_t* __restrict__ out) {
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const long total = long(N) * Kpad;
   if (i >= total) return;
@@ -21,18 +20,18 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int N, int C, int 
     const int tap = k / Cpad, c = k % Cpad;
     if (c < C) v = w[(size_t(n) * C + c) * taps + tap];
   }
-  out[size_t(n) * ldo + k] = __float2bfloat16_rn(v);
+  out[size_t(n) * ldo + k] = cvt_16(v, fp16);
 }
 
-const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out, cudaStream_t st) {
+const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out, int fp16, cudaStream_t st) {
   const long total = long(N) * Kpad;
-  pack_conv_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w, N, C, taps, Cpad, Kpad, ldo, reinterpret_cast<__nv_bfloat16*>(out));
+  pack_conv_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w, N, C, taps, Cpad, Kpad, ldo, fp16, reinterpret_cast<uint16_t*>(out));
   return cudaGetLastError() == cudaSuccess ? nullptr : "pack_conv_weight launch failed";
 }
 
 // out[n, k] = bf16( w[n,k] + scale * sum_j lb[n,j] * la[j,k] )
 __global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ la,
-                                   const float* __restrict__ lb, int r, float scale, int ldo, __nv_bfloat16* __restrict__ out) {
+                                   const float* __restrict__ lb, int r, float scale, int ldo, int fp16, uint16_t* __restrict__ out) {
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= long(N) * K) return;
   const int k = int(i % K);
@@ -43,20 +42,20 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, co
     for (int j = 0; j < r; ++j) acc += lb[size_t(n) * r + j] * la[size_t(j) * K + k];
     v += scale * acc;
   }
-  out[size_t(n) * ldo + k] = __float2bfloat16_rn(v);
+  out[size_t(n) * ldo + k] = cvt_16(v, fp16);
 }
 
 const char* pack_linear_weight(const float* w, int N, int K, const float* la, const float* lb, int r, float scale, int ldo, void* out,
-                               cudaStream_t st) {
+                               int fp16, cudaStream_t st) {
   const long total = long(N) * K;
-  pack_linear_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w, N, K, la, lb, r, scale, ldo, reinterpret_cast<__nv_bfloat16*>(out));
+  pack_linear_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w, N, K, la, lb, r, scale, ldo, fp16, reinterpret_cast<uint16_t*>(out));
   return cudaGetLastError() == cudaSuccess ? nullptr : "pack_linear_weight launch failed";
 }
 
 // GEGLU proj weight W[2*C4, K]: value rows [0,C4), gate rows [C4, 2*C4).  Packed row 128*t + j (j<64) = value row 64*t + j,
 // packed row 128*t + 64 + j = gate row C4 + 64*t + j.
-__global__ void pack_geglu_kernel(const float* __restrict__ w, const float* __restrict__ bias, int C4, int K,
-                                  __nv_bfloat16* __restrict__ out, float* __restrict__ out_bias) {
+__global__ void pack_geglu_kernel(const float* __restrict__ w, const float* __restrict__ bias, int C4, int K, int fp16,
+                                  uint16_t* __restrict__ out, float* __restrict__ out_bias) {
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const long total = long(2 * C4) * K;
   if (i >= total) return;
@@ -64,21 +63,21 @@ __global__ void pack_geglu_kernel(const float* __restrict__ w, const float* __re
   const int pr = int(i / K);
   const int t = pr / 128, j = pr % 128;
   const int src = (j < 64) ? (64 * t + j) : (C4 + 64 * t + (j - 64));
-  out[i] = __float2bfloat16_rn(w[size_t(src) * K + k]);
+  out[i] = cvt_16(w[size_t(src) * K + k], fp16);
   if (k == 0 && out_bias) out_bias[pr] = bias ? bias[src] : 0.f;
 }
 
-const char* pack_geglu_weight(const float* w, const float* bias, int C4, int K, void* out, float* out_bias, cudaStream_t st) {
+const char* pack_geglu_weight(const float* w, const float* bias, int C4, int K, void* out, float* out_bias, int fp16, cudaStream_t st) {
   if (C4 % 64 != 0) return "pack_geglu_weight: 4C must be a multiple of 64";
   const long total = long(2 * C4) * K;
-  pack_geglu_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w, bias, C4, K, reinterpret_cast<__nv_bfloat16*>(out), out_bias);
+  pack_geglu_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w, bias, C4, K, fp16, reinterpret_cast<uint16_t*>(out), out_bias);
   return cudaGetLastError() == cudaSuccess ? nullptr : "pack_geglu_weight launch failed";
 }
 
 // latents = scale * (Wq[0:4,:] @ (conv_out(x) ) + bq[0:4]) ; conv_out(x) = Wout * x + bout
 //   => W'[o, tap*C + c] = scale * sum_j Wq[o,j] * Wout[j,c,tap],  b'[o] = scale * (sum_j Wq[o,j]*bout[j] + bq[o]);  rows 4..15 zero.
 __global__ void pack_vae_head_kernel(const float* __restrict__ w_out, const float* __restrict__ b_out, const float* __restrict__ w_q,
-                                     const float* __restrict__ b_q, float scale, int C, __nv_bfloat16* __restrict__ out,
+                                     const float* __restrict__ b_q, float scale, int C, int fp16, uint16_t* __restrict__ out,
                                      float* __restrict__ out_bias) {
   const int K = 9 * C;
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -91,7 +90,7 @@ __global__ void pack_vae_head_kernel(const float* __restrict__ w_out, const floa
     for (int j = 0; j < 8; ++j) v += w_q[o * 8 + j] * w_out[(size_t(j) * C + c) * 9 + tap];
     v *= scale;
   }
-  out[i] = __float2bfloat16_rn(v);
+  out[i] = cvt_16(v, fp16);
   if (k == 0) {
     float b = 0.f;
     if (o < 4) {
@@ -103,10 +102,10 @@ __global__ void pack_vae_head_kernel(const float* __restrict__ w_out, const floa
 }
 
 const char* pack_vae_latent_head(const float* w_out, const float* b_out, const float* w_q, const float* b_q, float scale, int C,
-                                 void* out, float* out_bias, cudaStream_t st) {
+                                 void* out, float* out_bias, int fp16, cudaStream_t st) {
   const long total = long(16) * 9 * C;
-  pack_vae_head_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w_out, b_out, w_q, b_q, scale, C,
-                                                                      reinterpret_cast<__nv_bfloat16*>(out), out_bias);
+  pack_vae_head_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w_out, b_out, w_q, b_q, scale, C, fp16,
+                                                                      reinterpret_cast<uint16_t*>(out), out_bias);
   return cudaGetLastError() == cudaSuccess ? nullptr : "pack_vae_latent_head launch failed";
 }
 

@@ -97,7 +97,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate.
+// D[tmem] (+)= A[smem] * B[smem]^T, f16/bf16 inputs (per idesc), fp32 accumulate.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -123,10 +123,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor for kind::f16: c_format[4,6)=1 (f32), a_format[7,10)=1 (bf16), b_format[10,13)=1 (bf16),
+// Instruction descriptor for kind::f16: c_format[4,6)=1 (f32), a_format[7,10), b_format[10,13) (0 = f16, 1 = bf16),
 // a_major[15]=0 (K), b_major[16]=0 (K), n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+// a_format / b_format: 0 = f16, 1 = bf16.
+__host__ __device__ constexpr uint32_t make_idesc_16(int m, int n, int fp16) {
+  return (1u << 4) | ((fp16 ? 0u : 1u) << 7) | ((fp16 ? 0u : 1u) << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (one row per thread).

@@ -1,0 +1,163 @@
+"""Python-side owner of one ``madm_ctx``: registers parameter pointers, keeps the packed-weight arena and the
+workspace (torch tensors used purely as device memory), tracks parameter versions / the active LoRA adapter, and
+calls ``madm_extract`` on torch's current stream.  No PyTorch compute on the path; no fallback."""
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import MadmExtractArgs, MadmTensor, STAGE_ALL, STAGE_PROJ, STAGE_UNET, STAGE_VAE
+
+TAP_SHAPES = ((512, 128), (320, 64), (640, 32), (1280, 16))  # enc tap, unet taps (C, HW side)
+OUT_SIDES = (128, 64, 32, 16)                                  # s2..s5
+
+
+class Engine:
+    def __init__(self, device: torch.device, compute_dtype: str = "fp16"):
+        if device.type != "cuda":
+            raise _lib.MadmError("madm_b200 runs on sm_100a CUDA devices only (no CPU fallback)")
+        self.lib = _lib.load()
+        self.device = device
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        h = C.c_void_p()
+        _lib.check(self.lib.madm_create(C.byref(h), self.index), None, "madm_create")
+        self.ctx = h
+        if compute_dtype not in ("fp16", "bf16"):
+            raise _lib.MadmError(f"compute_dtype must be 'fp16' or 'bf16', got {compute_dtype!r}")
+        self.compute_dtype = compute_dtype
+        _lib.check(self.lib.madm_set_compute_dtype(self.ctx, _lib.DTYPE_FP16 if compute_dtype == "fp16" else _lib.DTYPE_BF16),
+                   self.ctx, "madm_set_compute_dtype")
+        self._named: List[Tuple[str, torch.Tensor]] = []
+        self._sig = None
+        self._versions = None
+        self._packed: Optional[torch.Tensor] = None
+        self._packed_adapter: Optional[str] = "\0unset"
+        self._ws: Optional[torch.Tensor] = None
+        self._keep = []
+        self.range_flag = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                self.lib.madm_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameters
+    def bind(self, named: Sequence[Tuple[str, torch.Tensor]]):
+        """(Re)register fp32 CUDA parameter tensors under their reference state_dict names."""
+        named = [(n, t) for n, t in named]
+        sig = tuple((n, t.data_ptr(), tuple(t.shape)) for n, t in named)
+        if sig == self._sig:
+            return False
+        for n, t in named:
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise _lib.MadmError(f"parameter {n} must be a contiguous fp32 tensor on {self.device} (got {t.dtype} on {t.device})")
+        arr = (MadmTensor * len(named))()
+        names = [n.encode() for n, _ in named]
+        for i, (n, t) in enumerate(named):
+            arr[i].name = names[i]
+            arr[i].data = t.data_ptr()
+            arr[i].ndim = t.dim()
+            for k, s in enumerate(t.shape):
+                arr[i].shape[k] = s
+        _lib.check(self.lib.madm_set_tensors(self.ctx, arr, len(named)), self.ctx, "madm_set_tensors")
+        self._named, self._sig = named, sig
+        self._versions = None  # force a full repack
+        return True
+
+    def _version_vector(self):
+        return tuple(t._version for _, t in self._named)
+
+    def ensure_packed(self, adapter: Optional[str], scaling: float):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        need = self.lib.madm_packed_bytes(self.ctx)
+        if need == 0:
+            _lib.check(-1, self.ctx, "madm_packed_bytes")
+        if self._packed is None or self._packed.numel() != need:
+            self._packed = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._versions = None
+        vers = self._version_vector()
+        ad = (adapter or "").encode()
+        if vers != self._versions:
+            _lib.check(self.lib.madm_pack_weights(self.ctx, C.c_void_p(self._packed.data_ptr()), ad, scaling, 0, st), self.ctx,
+                       "madm_pack_weights")
+            self._versions, self._packed_adapter = vers, adapter
+        elif adapter != self._packed_adapter:  # adapter switch: re-fold only the 128 LoRA-targeted projections
+            _lib.check(self.lib.madm_pack_weights(self.ctx, C.c_void_p(self._packed.data_ptr()), ad, scaling, 1, st), self.ctx,
+                       "madm_pack_weights(lora_only)")
+            self._packed_adapter = adapter
+
+    def workspace(self, B: int) -> torch.Tensor:
+        need = self.lib.madm_workspace_bytes(self.ctx, B)
+        if need == 0:
+            _lib.check(-1, self.ctx, "madm_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ the hot path
+    def extract(self, img: Optional[torch.Tensor], cond_inputs: torch.Tensor, cond_emb: torch.Tensor, timesteps: torch.Tensor,
+                shared_noise: torch.Tensor, *, ema: bool = False, stages: int = STAGE_ALL, want_taps: bool = False,
+                want_latents: bool = False, noisy_latents_in: Optional[torch.Tensor] = None, B: Optional[int] = None,
+                out: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, object]:
+        if self._packed is None:
+            raise _lib.MadmError("Engine.extract called before ensure_packed()")
+        B = B if B is not None else (img.shape[0] if img is not None else noisy_latents_in.shape[0])
+        dev = self.device
+
+        def f32c(t, shape, name):
+            if t is None:
+                return None
+            if t.device != dev:
+                raise _lib.MadmError(f"{name} must be on {dev}")
+            t = t.to(torch.float32).contiguous()
+            if tuple(t.shape) != tuple(shape):
+                raise _lib.MadmError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+            return t
+
+        img = f32c(img, (B, 3, 512, 512), "img")
+        cond_inputs = f32c(cond_inputs, (B, 77, 768), "cond_inputs")
+        cond_emb = f32c(cond_emb, (B, 1280), "cond_emb")
+        shared_noise = f32c(shared_noise, (1, 4, 64, 64), "shared_noise")
+        noisy_latents_in = f32c(noisy_latents_in, (B, 4, 64, 64), "noisy_latents_in")
+        timesteps = timesteps.to(device=dev, dtype=torch.int64).contiguous()
+        ws = self.workspace(B)
+        a = MadmExtractArgs()
+        a.B, a.stages, a.ema = B, stages, 1 if ema else 0
+        a.img = img.data_ptr() if img is not None else None
+        a.cond_inputs, a.cond_emb, a.timesteps = cond_inputs.data_ptr(), cond_emb.data_ptr(), timesteps.data_ptr()
+        a.shared_noise = shared_noise.data_ptr() if shared_noise is not None else None
+        a.noisy_latents_in = noisy_latents_in.data_ptr() if noisy_latents_in is not None else None
+        res: Dict[str, object] = {}
+        outs = []
+        if stages & STAGE_PROJ:
+            for i, side in enumerate(OUT_SIDES):
+                t = out[i] if out is not None else torch.empty(B, 512, side, side, dtype=torch.float32, device=dev)
+                outs.append(t)
+                a.out[i] = t.data_ptr()
+            res["features"] = outs
+        if want_taps:
+            taps = [torch.empty(B, c, s, s, dtype=torch.float32, device=dev) for c, s in TAP_SHAPES]
+            for i, t in enumerate(taps):
+                a.taps[i] = t.data_ptr()
+            res["taps"] = taps
+        if want_latents:
+            res["latents"] = torch.empty(B, 4, 64, 64, dtype=torch.float32, device=dev)
+            res["noisy_latents"] = torch.empty(B, 4, 64, 64, dtype=torch.float32, device=dev)
+            a.latents, a.noisy_latents = res["latents"].data_ptr(), res["noisy_latents"].data_ptr()
+        a.packed = self._packed.data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        a.range_flag = self.range_flag.data_ptr()
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(self.lib.madm_extract(self.ctx, C.byref(a), st), self.ctx, "madm_extract")
+        # inputs must outlive the asynchronous launches: park references until the next call
+        self._keep = [img, cond_inputs, cond_emb, timesteps, shared_noise, noisy_latents_in]
+        return res
+
+    def launch_count(self, B: int, stages: int = STAGE_ALL) -> int:
+        return int(self.lib.madm_launch_count(self.ctx, B, stages))

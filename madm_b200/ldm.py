@@ -1,0 +1,336 @@
+"""Drop-in mirrors of the reference's ``LdmDiffusers`` (``modeling/meta_arch/ldm_diffusers.py:17-217``) and
+``BasePromptTimeGenerator`` / ``ClipFeatureProject`` (``modeling/meta_arch/ldm_base.py:632-924``).
+
+Same constructor kwargs, attribute names and state_dict keys; the forward pass is the CUDA engine
+(``madm_extract``), not diffusers.  The tiny batch-invariant conditioning arithmetic
+(``tanh(alpha) * embed`` on ``[1,77,768]`` / ``[1,1,1280]``) stays in PyTorch, as SURVEY §8 a-2 prescribes.
+"""
+import logging
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .engine import Engine
+from .sd14_params import UNetParams, VAEParams
+
+logger = logging.getLogger(__name__)
+
+
+def _load_sd_component(root: str, sub: str) -> Optional[Dict[str, torch.Tensor]]:
+    """Read ``<root>/<sub>/diffusion_pytorch_model.{safetensors,bin}`` of a local SD-1.4 snapshot, if present."""
+    d = os.path.join(root, sub)
+    st = os.path.join(d, "diffusion_pytorch_model.safetensors")
+    if os.path.exists(st):
+        from safetensors.torch import load_file
+        return load_file(st)
+    pt = os.path.join(d, "diffusion_pytorch_model.bin")
+    if os.path.exists(pt):
+        return torch.load(pt, map_location="cpu")
+    return None
+
+
+class FeatureTaps(list):
+    """What ``LdmDiffusers.forward`` returns: the reference's ``[*encoder_features, *unet_features]`` list
+    (``ldm_diffusers.py:217``) — NCHW fp32 tensors — plus the engine token that lets the backbone run the
+    projection stage on the workspace-resident NHWC taps without a round trip."""
+    token: Optional[Tuple] = None
+
+
+class LdmDiffusers(nn.Module):
+    latent_image_size = (64, 64)
+    text_embed_shape = torch.Size([77, 768])
+    unet_time_embed_out_features = 1280
+    uncond_inputs_size = torch.Size([1, 77, 768])
+    feature_size = (512, 512)
+    feature_dims = [512, 512, 2560, 1920, 960, 640, 512, 512]
+    feature_strides = [4, 8, 64, 32, 16, 8, 8, 4]
+    num_groups = 8
+    grouped_indices = [[0], [1], [2], [3], [4], [5], [6], [7]]
+    timesteps = 0
+    input_mean = 0.5
+    input_std = 0.5
+
+    def __init__(self, stable_diffusion_name_or_path, encoder_block_indices, unet_block_indices, decoder_block_indices,
+                 input_range="01", unet_block_indices_type="in", finetune_unet="no", concat_pixel_shuffle=False,
+                 add_latent_noise=-1, norm_latent_noise=False, vae_decoder_loss=False, input_channel_plus=0,
+                 final_fuse_vae_decoder_feat=False, device=None, uncond_inputs: Optional[torch.Tensor] = None,
+                 compute_dtype: str = "fp16"):
+        super().__init__()
+        self.stable_diffusion_name_or_path = os.path.expanduser(stable_diffusion_name_or_path) if stable_diffusion_name_or_path else None
+        self.encoder_block_indices = list(encoder_block_indices)
+        self.unet_block_indices = list(unet_block_indices)
+        self.decoder_block_indices = list(decoder_block_indices)
+        self.input_range = input_range
+        assert self.input_range in {"01", "-1+1"}
+        self.unet_block_indices_type = unet_block_indices_type
+        assert self.unet_block_indices_type in {"in", "after"}
+        self.finetune_unet = finetune_unet
+        assert self.finetune_unet in {"no", "all", "attention", "without cross-attention"}
+        self.add_latent_noise = add_latent_noise
+        self.norm_latent_noise = norm_latent_noise
+        self.vae_decoder_loss = vae_decoder_loss
+        self.final_fuse_vae_decoder_feat = final_fuse_vae_decoder_feat
+        # rows of SURVEY §8 that are "next" / out of scope fail loudly instead of silently computing something else
+        unsupported = []
+        if self.encoder_block_indices != [5]: unsupported.append("encoder_block_indices != [5]")
+        if self.unet_block_indices != [5, 8, 11] or unet_block_indices_type != "after": unsupported.append("unet taps != [5,8,11]/'after'")
+        if self.decoder_block_indices: unsupported.append("decoder_block_indices")
+        if input_range != "-1+1": unsupported.append("input_range='01'")
+        if concat_pixel_shuffle or input_channel_plus or norm_latent_noise or add_latent_noise != -1:
+            unsupported.append("concat_pixel_shuffle / input_channel_plus / latent-noise variants")
+        if vae_decoder_loss or final_fuse_vae_decoder_feat: unsupported.append("vae_decoder_loss / s0 variant (SURVEY §8 f-1)")
+        if unsupported:
+            raise NotImplementedError("madm_b200 implements the base hot-path configuration "
+                                      "(config_files/common/models/mtmadise_multi_lora.py:14-41); unsupported: " + ", ".join(unsupported))
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.vae = VAEParams(device=device)
+        self.unet = UNetParams(device=device)
+        loaded = False
+        if self.stable_diffusion_name_or_path and os.path.isdir(self.stable_diffusion_name_or_path):
+            for sub, mod in (("vae", self.vae), ("unet", self.unet)):
+                sd = _load_sd_component(self.stable_diffusion_name_or_path, sub)
+                if sd is not None:
+                    own = mod.state_dict()
+                    mod.load_state_dict({k: v.float() for k, v in sd.items() if k in own}, strict=False)
+                    loaded = True
+        if not loaded:
+            logger.warning("SD-1.4 snapshot not found at %s: UNet/VAE are randomly initialised (load a MADM checkpoint "
+                           "with load_state_dict to set them)", self.stable_diffusion_name_or_path)
+        rng = torch.Generator().manual_seed(42)  # reference ldm_diffusers.py:73-75 (CPU generator -> bit-reproducible)
+        self.register_buffer("shared_noise", torch.randn(1, 4, *self.latent_image_size, generator=rng).to(device))
+        if uncond_inputs is None:
+            # CLIP('') embedding (ldm_diffusers.py:76,219-243) comes from the checkpoint buffer; until one is loaded a seeded
+            # stand-in keeps the module usable (SURVEY §8d synthetic recipe)
+            uncond_inputs = torch.randn(1, 77, 768, generator=torch.Generator().manual_seed(7))
+        self.register_buffer("uncond_inputs", uncond_inputs.detach().to(device))
+        self.compute_dtype = compute_dtype  # 'fp16' (reference AMP dtype, default) or 'bf16'; see DESIGN.md Numerics
+        self._engine: Optional[Engine] = None
+        self._bound_extra: List[Tuple[str, torch.Tensor]] = []
+        self._serial = 0
+        self._freeze()
+
+    # ---------------------------------------------------------------------------- reference surface
+    def _freeze(self):  # ldm_diffusers.py:101-121
+        super().train(mode=False)
+        for p in self.parameters():
+            p.requires_grad = False
+        if self.finetune_unet != "no":
+            for name, p in self.unet.named_parameters():
+                if self.finetune_unet == "all":
+                    p.requires_grad = True
+                elif self.finetune_unet == "attention" and "attentions" in name:
+                    p.requires_grad = True
+                elif self.finetune_unet == "without cross-attention" and not ("attentions" in name and "attn2" in name):
+                    p.requires_grad = True
+
+    def train(self, mode: bool = True):
+        super().train(False)
+        return self
+
+    @property
+    def device(self):
+        return self.shared_noise.device
+
+    # ---------------------------------------------------------------------------- engine plumbing
+    def engine(self) -> Engine:
+        if self._engine is None:
+            self._engine = Engine(self.device, self.compute_dtype)
+        return self._engine
+
+    def named_engine_tensors(self) -> List[Tuple[str, torch.Tensor]]:
+        pre = "feature_extractor.ldm_extractor."
+        out = [(pre + "unet." + n, p.data) for n, p in self.unet.named_parameters()]
+        out += [(pre + "vae." + n, p.data) for n, p in self.vae.named_parameters()]
+        return out
+
+    def prepare(self, extra: Sequence[Tuple[str, torch.Tensor]] = ()):
+        """Bind parameter pointers and (re)pack weights if anything changed (version counters, adapter switch)."""
+        eng = self.engine()
+        eng.bind(self.named_engine_tensors() + list(extra))
+        adapter = self.unet.active_adapter()
+        eng.ensure_packed(adapter, self.unet.scaling_of(adapter) if adapter else 0.0)
+        return eng
+
+    def sample_timesteps(self, batched_inputs, bsz: int) -> torch.Tensor:
+        lo, hi = batched_inputs["timestep"] if "timestep" in batched_inputs else (0, 1)  # ldm_diffusers.py:156-161
+        return torch.randint(low=int(lo), high=int(hi), size=(bsz,), device=self.device).long()
+
+    def run(self, batched_inputs, input_modal, *, stages, ema_projections=False, extra=(), want_taps=False, want_latents=False,
+            timesteps: Optional[torch.Tensor] = None, out=None, **kwargs):
+        if kwargs.get("ema_forward") and hasattr(self, "ema_unet"):
+            raise NotImplementedError("ema_unet (ema_w_unet) is not part of the base hot path")
+        if "modality_mask" in kwargs or kwargs.get("return_unet_final_output"):
+            raise NotImplementedError("modality_mask / return_unet_final_output belong to the s0 / vae_decoder variant (SURVEY §8 f-1)")
+        images = batched_inputs["img"]
+        bsz = images.shape[0]
+        eng = self.prepare(extra)
+        if timesteps is None:
+            timesteps = self.sample_timesteps(batched_inputs, bsz)
+        cond_inputs = batched_inputs["cond_inputs"]
+        cond_emb = batched_inputs["cond_emb"]
+        if cond_emb.dim() == 3:  # [B,1,1280] -> [B,1280]  (ldm_diffusers.py:507-508)
+            cond_emb = cond_emb[:, 0]
+        if cond_inputs.shape[0] == 1 and bsz > 1:
+            cond_inputs = cond_inputs.expand(bsz, -1, -1)
+        if cond_emb.shape[0] == 1 and bsz > 1:
+            cond_emb = cond_emb.expand(bsz, -1)
+        self._serial += 1
+        return eng.extract(images, cond_inputs, cond_emb, timesteps, self.shared_noise, ema=ema_projections, stages=stages,
+                           want_taps=want_taps, want_latents=want_latents, out=out)
+
+    def forward(self, batched_inputs, input_modal, **kwargs):
+        """Reference semantics: returns ``[enc_tap, unet_tap16, unet_tap32, unet_tap64]`` as NCHW fp32 tensors
+        (order of ldm_diffusers.py:217: encoder features, then unet features in up-path order 16, 32, 64)."""
+        res = self.run(batched_inputs, input_modal, stages=_lib.STAGE_VAE | _lib.STAGE_UNET, want_taps=True, **kwargs)
+        enc, t64, t32, t16 = res["taps"]
+        taps = FeatureTaps([enc, t16, t32, t64])
+        taps.token = (id(self), self._serial)
+        return taps
+
+
+class ClipFeatureProject(nn.Module):
+    """ldm_base.py:632-717 for ``input_prefix=False`` (``clip_state='no'``)."""
+
+    def __init__(self, learnable_cond_prompt=False, prompt_in_features=None, prompt_out_features=None, prompt_seq_len=None,
+                 learnable_cond_time=False, time_in_features=None, time_out_features=None, time_seq_len=None,
+                 time_alpha_cond_size=None, input_prefix=False, without_prompt_alpha=True, multi_layer_prompt=False,
+                 init_uncond_prompt=False, uncond_prompt=None):
+        super().__init__()
+        if input_prefix or multi_layer_prompt or init_uncond_prompt:
+            raise NotImplementedError("clip prefix / multi-layer / uncond-initialised prompts are outside the shipped config")
+        self.learnable_cond_prompt = learnable_cond_prompt
+        self.learnable_cond_time = learnable_cond_time
+        self.input_prefix = input_prefix
+        self.without_prompt_alpha = without_prompt_alpha
+        if self.learnable_cond_prompt:
+            pe = torch.zeros(1, prompt_seq_len, prompt_out_features)
+            nn.init.trunc_normal_(pe, std=0.02, a=-2.0, b=2.0)
+            self.prompt_embed = nn.Parameter(pe)
+            if not self.without_prompt_alpha:
+                shape = [1, prompt_seq_len, prompt_out_features]
+                self.alpha_cond_prompt = nn.Parameter(torch.rand(shape))
+                self.alpha_uncond_prompt = nn.Parameter(torch.rand(shape))
+        if self.learnable_cond_time:
+            self.alpha_cond_time = nn.Parameter(torch.zeros(time_alpha_cond_size))
+            te = torch.zeros(1, time_seq_len, time_out_features)
+            nn.init.trunc_normal_(te, std=0.02, a=-2.0, b=2.0)
+            self.time_embed = nn.Parameter(te)
+
+    def get_cond_prompt(self, uncond_prompt, prefix=None):
+        if not self.learnable_cond_prompt:
+            return uncond_prompt
+        if self.without_prompt_alpha:
+            return self.prompt_embed
+        return torch.tanh(self.alpha_uncond_prompt) * uncond_prompt + torch.tanh(self.alpha_cond_prompt) * self.prompt_embed
+
+    def get_cond_time(self, prefix=None):
+        return torch.tanh(self.alpha_cond_time) * self.time_embed if self.learnable_cond_time else None
+
+    def forward(self, uncond_prompt, prefix=None):
+        return self.get_cond_prompt(uncond_prompt, prefix), self.get_cond_time(prefix)
+
+
+class BasePromptTimeGenerator(nn.Module):
+    cross_attention_out_dim = [320, 320, 640, 640, 1280, 1280, 1280, 1280, 1280, 1280, 640, 640, 640, 320, 320, 320]
+
+    def __init__(self, learnable_cond_prompt=True, learnable_cond_time=True, same_cond_params=False,
+                 detach_prompt_for_mixed_data=False, clip_state="no", num_timesteps=1, clip_model_name="", ldm_extractor=None,
+                 without_prompt_alpha=False, multi_layer_prompt=False, mix_source_target_prompt=False, init_uncond_prompt=False,
+                 mask_prompt_ratio=False, detach_mask_prompt=False, prompt_perturbation=False, rand_prompt_scale=None, **kwargs):
+        super().__init__()
+        assert clip_state in {"no", "learnable_clip", "no_learnable_clip"}
+        if clip_state != "no":
+            raise NotImplementedError("clip_state != 'no' (OpenCLIP prefix) is out of scope; the shipped config sets 'no'")
+        if ldm_extractor is None:
+            raise NotImplementedError("the legacy CompVis LdmExtractor path is out of scope; pass ldm_extractor=LdmDiffusers(...)")
+        self.learnable_cond_prompt = learnable_cond_prompt
+        self.learnable_cond_time = learnable_cond_time
+        self.same_cond_params = same_cond_params
+        self.detach_prompt_for_mixed_data = detach_prompt_for_mixed_data
+        self.clip_state = clip_state
+        self.multi_layer_prompt = multi_layer_prompt
+        self.without_prompt_alpha = without_prompt_alpha
+        self.mix_source_target_prompt = mix_source_target_prompt
+        self.init_uncond_prompt = init_uncond_prompt
+        self.mask_prompt_ratio = mask_prompt_ratio
+        self.detach_mask_prompt = detach_mask_prompt
+        assert not (self.detach_mask_prompt and (not self.mask_prompt_ratio))
+        self.prompt_perturbation = prompt_perturbation
+        self.rand_prompt_scale = rand_prompt_scale
+        self.ldm_extractor = ldm_extractor
+        self.text_embed_shape = ldm_extractor.text_embed_shape
+        t_out = ldm_extractor.unet_time_embed_out_features
+        seq = kwargs.get("prompt_seq_len", self.text_embed_shape[0])
+
+        def mk():
+            return ClipFeatureProject(
+                learnable_cond_prompt=learnable_cond_prompt, prompt_in_features=None, prompt_out_features=self.text_embed_shape[1],
+                prompt_seq_len=seq, without_prompt_alpha=without_prompt_alpha, multi_layer_prompt=multi_layer_prompt,
+                init_uncond_prompt=init_uncond_prompt, uncond_prompt=None, learnable_cond_time=learnable_cond_time,
+                time_in_features=None, time_out_features=t_out, time_seq_len=num_timesteps, time_alpha_cond_size=t_out,
+                input_prefix=False).to(ldm_extractor.device)
+
+        self.clip_project_rgb = mk()
+        self.clip_project_others = self.clip_project_rgb if same_cond_params else mk()
+
+    @property
+    def uncond_inputs(self):
+        return self.ldm_extractor.uncond_inputs
+
+    def conditioning(self, batched_inputs, input_modal, ema_forward=False, timestep=None):
+        """ldm_base.py:832-917: fills cond_inputs / cond_emb / timestep into ``batched_inputs``."""
+        assert input_modal in {"rgb", "others", "mixed", "masked_prompt", "prompt_perturbation", "rand_prompt"}
+        image = batched_inputs["img"]
+        if input_modal == "rgb":
+            assert ema_forward is False
+            ci, ce = self.clip_project_rgb(self.uncond_inputs, None)
+        elif input_modal == "mixed" and self.mix_source_target_prompt:
+            s_ci, s_ce = self.clip_project_rgb(self.uncond_inputs, None)
+            t_ci, t_ce = self.clip_project_others(self.uncond_inputs, None)
+            ci, ce = (s_ci + t_ci) / 2, (s_ce + t_ce) / 2
+        else:
+            proj = self.ema_clip_project_others if ema_forward else self.clip_project_others
+            ci, ce = proj(self.uncond_inputs, None)
+        if input_modal == "mixed" and self.detach_prompt_for_mixed_data:
+            ci = ci.detach()
+        if input_modal == "masked_prompt" and self.mask_prompt_ratio:
+            ci = self.mask_prompt(ci).detach() if self.detach_mask_prompt else self.mask_prompt(ci)
+        elif input_modal == "prompt_perturbation" and self.prompt_perturbation:
+            ci = (ci + torch.randn(ci.shape, device=ci.device) * self.prompt_perturbation).detach()
+        elif input_modal == "rand_prompt":
+            ci = torch.rand_like(ci) * self.rand_prompt_scale
+        if timestep is not None:
+            batched_inputs["timestep"] = timestep
+        if image.shape[0] != 1:
+            ci = torch.repeat_interleave(ci, repeats=image.shape[0], dim=0)
+            ce = torch.repeat_interleave(ce, repeats=image.shape[0], dim=0)
+        batched_inputs["cond_inputs"], batched_inputs["cond_emb"] = ci, ce
+        return batched_inputs
+
+    def forward(self, batched_inputs, input_modal, ema_forward=False, timestep=None, return_unet_feats=False, **kwargs):
+        assert not return_unet_feats
+        with torch.no_grad():
+            batched_inputs = self.conditioning(batched_inputs, input_modal, ema_forward, timestep)
+        return self.ldm_extractor(batched_inputs, input_modal, ema_forward=ema_forward, **kwargs)
+
+    def mask_prompt(self, prompt):  # ldm_base.py:926-938
+        assert prompt.dim() == 3
+        mask = (torch.rand((prompt.shape[0], prompt.shape[1], 1), device=prompt.device) > self.mask_prompt_ratio).float()
+        return prompt * mask
+
+    feature_size = property(lambda self: self.ldm_extractor.feature_size)
+    feature_dims = property(lambda self: self.ldm_extractor.feature_dims)
+    feature_strides = property(lambda self: self.ldm_extractor.feature_strides)
+    num_groups = property(lambda self: self.ldm_extractor.num_groups)
+    grouped_indices = property(lambda self: self.ldm_extractor.grouped_indices)
+
+    def extra_repr(self):
+        return f"learnable_time_embed={self.learnable_cond_time}"
+
+    def set_requires_grad(self, requires_grad):
+        for p in self.ldm_extractor.unet.parameters():
+            p.requires_grad = requires_grad

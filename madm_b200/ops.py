@@ -16,6 +16,15 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _dt(dtype) -> int:
+    """torch dtype of the 16-bit operand tensors -> MADM_DTYPE_*."""
+    if dtype == torch.float16:
+        return _lib.DTYPE_FP16
+    if dtype == torch.bfloat16:
+        return _lib.DTYPE_BF16
+    raise _lib.MadmError(f"operand dtype must be torch.float16 or torch.bfloat16, got {dtype}")
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -69,6 +78,7 @@ def gemm(segs: Sequence[MadmGemmSeg], M: int, N: int, w: torch.Tensor, *, Nw: in
     a.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
     a.ldo16 = ldo16
     a.act, a.alpha, a.bn = act, alpha, bn
+    a.dtype = _dt(w.dtype)
     lib = _lib.load()
     _lib.check(lib.madm_op_gemm(C.byref(a), _stream()), None, "madm_op_gemm")
 
@@ -79,80 +89,80 @@ def groupnorm(x0, x1, B, HW, gamma, beta, eps, act, y, raw=None):
     C0 = x0.shape[-1]
     C1 = x1.shape[-1] if x1 is not None else 0
     _lib.check(lib.madm_op_groupnorm(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(gamma), _ptr(beta), eps, act, _ptr(stats),
-                                     _ptr(y), _ptr(raw), _stream()), None, "madm_op_groupnorm")
+                                     _ptr(y), _ptr(raw), _dt(y.dtype), _stream()), None, "madm_op_groupnorm")
     return stats
 
 
 def layernorm(x, gamma, beta, eps, y):
     lib = _lib.load()
     M, Cc = x.shape
-    _lib.check(lib.madm_op_layernorm(_ptr(x), M, Cc, _ptr(gamma), _ptr(beta), eps, _ptr(y), _stream()), None, "madm_op_layernorm")
+    _lib.check(lib.madm_op_layernorm(_ptr(x), M, Cc, _ptr(gamma), _ptr(beta), eps, _ptr(y), _dt(y.dtype), _stream()), None, "madm_op_layernorm")
 
 
 def softmax_rows(s, p):
     lib = _lib.load()
     R, L = s.shape
-    _lib.check(lib.madm_op_softmax_rows(_ptr(s), R, L, _ptr(p), _stream()), None, "madm_op_softmax_rows")
+    _lib.check(lib.madm_op_softmax_rows(_ptr(s), R, L, _ptr(p), _dt(p.dtype), _stream()), None, "madm_op_softmax_rows")
 
 
 def attention(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale):
     lib = _lib.load()
     _lib.check(lib.madm_op_attention(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(o), ldo, B, heads, d, Nq, Nk, q_bs, kv_bs,
-                                     o_bs, scale, _stream()), None, "madm_op_attention")
+                                     o_bs, scale, _dt(o.dtype), _stream()), None, "madm_op_attention")
 
 
-def pack_linear(w, lora_a=None, lora_b=None, scale=0.0, out=None, ldo=0):
+def pack_linear(w, lora_a=None, lora_b=None, scale=0.0, out=None, ldo=0, dtype=torch.float16):
     lib = _lib.load()
     N, K = w.shape
     r = lora_a.shape[0] if lora_a is not None else 0
     if out is None:
-        out = torch.empty(N, K, dtype=torch.bfloat16, device=w.device)
-    _lib.check(lib.madm_op_pack_linear(_ptr(w), N, K, _ptr(lora_a), _ptr(lora_b), r, scale, _ptr(out), ldo, _stream()), None,
+        out = torch.empty(N, K, dtype=dtype, device=w.device)
+    _lib.check(lib.madm_op_pack_linear(_ptr(w), N, K, _ptr(lora_a), _ptr(lora_b), r, scale, _ptr(out), ldo, _dt(out.dtype), _stream()), None,
                "madm_op_pack_linear")
     return out
 
 
-def pack_conv(w, Cpad=0, out=None, ldo=0):
+def pack_conv(w, Cpad=0, out=None, ldo=0, dtype=torch.float16):
     lib = _lib.load()
     N, Cc, kh, kw = w.shape
     taps = kh * kw
     Cpad = Cpad or (Cc + 63) // 64 * 64
     if out is None:
-        out = torch.empty(N, taps * Cpad, dtype=torch.bfloat16, device=w.device)
-    _lib.check(lib.madm_op_pack_conv(_ptr(w), N, Cc, taps, Cpad, _ptr(out), ldo, _stream()), None, "madm_op_pack_conv")
+        out = torch.empty(N, taps * Cpad, dtype=dtype, device=w.device)
+    _lib.check(lib.madm_op_pack_conv(_ptr(w), N, Cc, taps, Cpad, _ptr(out), ldo, _dt(out.dtype), _stream()), None, "madm_op_pack_conv")
     return out
 
 
-def pack_geglu(w, bias):
+def pack_geglu(w, bias, dtype=torch.float16):
     lib = _lib.load()
     N2, K = w.shape
-    out = torch.empty(N2, K, dtype=torch.bfloat16, device=w.device)
+    out = torch.empty(N2, K, dtype=dtype, device=w.device)
     ob = torch.empty(N2, dtype=torch.float32, device=w.device)
-    _lib.check(lib.madm_op_pack_geglu(_ptr(w), _ptr(bias), N2 // 2, K, _ptr(out), _ptr(ob), _stream()), None, "madm_op_pack_geglu")
+    _lib.check(lib.madm_op_pack_geglu(_ptr(w), _ptr(bias), N2 // 2, K, _ptr(out), _ptr(ob), _dt(dtype), _stream()), None, "madm_op_pack_geglu")
     return out, ob
 
 
-def space_to_depth(x):
+def space_to_depth(x, dtype=torch.float16):
     lib = _lib.load()
     B, H, W, Cc = x.shape
-    out = torch.empty(4, B, H // 2, W // 2, Cc, dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.madm_op_space_to_depth(_ptr(x), B, H, W, Cc, _ptr(out), _stream()), None, "madm_op_space_to_depth")
+    out = torch.empty(4, B, H // 2, W // 2, Cc, dtype=dtype, device=x.device)
+    _lib.check(lib.madm_op_space_to_depth(_ptr(x), B, H, W, Cc, _ptr(out), _dt(dtype), _stream()), None, "madm_op_space_to_depth")
     return out
 
 
-def upsample2x(x):
+def upsample2x(x, dtype=torch.float16):
     lib = _lib.load()
     B, H, W, Cc = x.shape
-    out = torch.empty(B, 2 * H, 2 * W, Cc, dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.madm_op_upsample2x(_ptr(x), B, H, W, Cc, _ptr(out), _stream()), None, "madm_op_upsample2x")
+    out = torch.empty(B, 2 * H, 2 * W, Cc, dtype=dtype, device=x.device)
+    _lib.check(lib.madm_op_upsample2x(_ptr(x), B, H, W, Cc, _ptr(out), _dt(dtype), _stream()), None, "madm_op_upsample2x")
     return out
 
 
-def image_im2col(img, range_flag=None):
+def image_im2col(img, range_flag=None, dtype=torch.float16):
     lib = _lib.load()
     B, _, H, W = img.shape
-    out = torch.empty(B * H * W, 64, dtype=torch.bfloat16, device=img.device)
-    _lib.check(lib.madm_op_image_im2col(_ptr(img), B, H, W, _ptr(out), _ptr(range_flag), _stream()), None, "madm_op_image_im2col")
+    out = torch.empty(B * H * W, 64, dtype=dtype, device=img.device)
+    _lib.check(lib.madm_op_image_im2col(_ptr(img), B, H, W, _ptr(out), _ptr(range_flag), _dt(dtype), _stream()), None, "madm_op_image_im2col")
     return out
 
 

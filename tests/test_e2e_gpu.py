@@ -1,0 +1,101 @@
+"""End-to-end parity (GPU): the product backbone (CUDA engine through the C ABI) against the fp32 oracle run on the
+same device with TF32 off, on the same seeded synthetic inputs and weights.
+
+Gates (BASELINE.json north_star): per tensor cosine >= 0.999 and max|a-b|/max|b| <= 2e-2 versus the fp32 oracle, for the
+encoder tap, the three UNet taps and the four projected maps.  The default compute dtype (fp16 operands, fp32
+accumulate / norms / residual stream) must meet that gate.  The optional bf16 mode is checked against cosine >= 0.999 and
+max-rel <= 3e-2: an *ideal* bf16-operand pipeline already sits at 2.2e-2 on the projected maps of this synthetic model
+(oracle storage-rounding emulation, tests/test_oracle_cpu.py::test_bf16_error_budget and DESIGN.md "Numerics").
+"""
+import pytest
+import torch
+
+from helpers import build_product_backbone, cosine, max_rel, set_lora_adapter
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN = 0.999
+REL_MAX = {"fp16": 2e-2, "bf16": 3e-2}
+_MODE = "fp16"
+
+
+@pytest.fixture(scope="module")
+def oracle_backbone(cuda_device):
+    from oracle import synthetic
+    return synthetic.build_backbone().to(cuda_device)
+
+
+@pytest.fixture(scope="module", params=["fp16", "bf16"])
+def pair(request, oracle_backbone, cuda_device):
+    global _MODE
+    _MODE = request.param
+    ob = oracle_backbone
+    pb = build_product_backbone(cuda_device, compute_dtype=request.param)
+    missing, unexpected = pb.load_state_dict(ob.state_dict(), strict=False)
+    assert not missing and not unexpected, (missing[:5], unexpected[:5])
+    yield ob, pb
+    del pb
+    torch.cuda.empty_cache()
+
+
+def _oracle_taps(ob, img, modal, ema=False):
+    with torch.no_grad():
+        taps = ob.feature_extractor(dict(img=img), modal, ema)
+        feats = ob.forward_features(taps, None, ema)["output_features"]
+    return taps, feats
+
+
+def _check(name, got, ref):
+    c, r = cosine(got, ref), max_rel(got, ref)
+    print(f"[{_MODE}] {name}: cos={c:.6f} max_rel={r:.5f}")
+    assert c >= COS_MIN, f"{name}: cosine {c}"
+    assert r <= REL_MAX[_MODE], f"{name}: max rel err {r} > {REL_MAX[_MODE]} ({_MODE})"
+
+
+def test_full_path_parity_others(pair, cuda_device):
+    from oracle import synthetic
+    from oracle.lora import set_adapter
+    ob, pb = pair
+    img = synthetic.synthetic_images(2).to(cuda_device)
+    set_adapter(ob.feature_extractor.ldm_extractor.unet, ["Depth"])
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    taps, feats = _oracle_taps(ob, img, "others")
+    with torch.no_grad():
+        res = pb._extract(img, "others", False, None, want_taps=True)
+    enc, t64, t32, t16 = res["taps"]
+    _check("enc_tap", enc, taps[0])
+    _check("unet_tap16", t16, taps[1])
+    _check("unet_tap32", t32, taps[2])
+    _check("unet_tap64", t64, taps[3])
+    for k, got in zip(["s2", "s3", "s4", "s5"], res["features"]):
+        _check(k, got, feats[k])
+    out = pb(img, input_modal="others")["output_features"]
+    assert list(out.keys()) == ["s2", "s3", "s4", "s5"]
+    assert out["s2"].shape == (2, 512, 128, 128) and out["s5"].shape == (2, 512, 16, 16)
+
+
+def test_adapter_switch_and_rgb(pair, cuda_device):
+    """'rgb' conditioning with the 'default' adapter: exercises the LoRA re-fold on adapter switch."""
+    from oracle import synthetic
+    from oracle.lora import set_adapter
+    ob, pb = pair
+    img = synthetic.synthetic_images(1, seed=3).to(cuda_device)
+    set_adapter(ob.feature_extractor.ldm_extractor.unet, ["default"])
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "default")
+    _, feats = _oracle_taps(ob, img, "rgb")
+    out = pb(img, input_modal="rgb")["output_features"]
+    for k in out:
+        _check("rgb/" + k, out[k], feats[k])
+
+
+def test_ema_forward(pair, cuda_device):
+    from oracle import synthetic
+    from oracle.lora import set_adapter
+    ob, pb = pair
+    img = synthetic.synthetic_images(1, seed=5).to(cuda_device)
+    set_adapter(ob.feature_extractor.ldm_extractor.unet, ["Depth"])
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    _, feats = _oracle_taps(ob, img, "others", ema=True)
+    out = pb(img, input_modal="others", ema_forward=True)["output_features"]
+    for k in out:
+        _check("ema/" + k, out[k], feats[k])

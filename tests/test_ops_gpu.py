@@ -13,16 +13,23 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
+DT = torch.float16  # operand dtype under test; the module is re-run for bf16 through the `dt` fixture
+
+
 def bf(t):
-    return t.to(torch.bfloat16)
+    """Round to the 16-bit operand dtype under test."""
+    return t.to(DT)
 
 
 def relerr(a, b):
     return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
 
 
-@pytest.fixture(scope="module")
-def ops(cuda_device):
+@pytest.fixture(scope="module", params=["fp16", "bf16"])
+def ops(request, cuda_device):
+    """The op wrappers, with the module-level operand dtype switched for the whole parametrised pass."""
+    global DT
+    DT = torch.float16 if request.param == "fp16" else torch.bfloat16
     from madm_b200 import ops as o
     return o
 
@@ -41,7 +48,7 @@ def test_gemm_plain(ops, cuda_device, M, K, N, bn):
     w = bf(torch.randn(N, K, device=cuda_device, generator=g) / math.sqrt(K))
     bias = torch.randn(N, device=cuda_device, generator=g)
     o32 = torch.full((M, N), float("nan"), device=cuda_device)
-    o16 = torch.empty(M, N, dtype=torch.bfloat16, device=cuda_device)
+    o16 = torch.empty(M, N, dtype=DT, device=cuda_device)
     ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, N, w, bias=bias, out_f32=o32, ldo32=N, out_bf16=o16, ldo16=N, bn=bn)
     ref = a.float() @ w.float().t() + bias
     assert relerr(o32, ref) < 2e-3
@@ -63,13 +70,13 @@ def test_gemm_epilogue_variants(ops, cuda_device):
              residual=out, ldr=N, out_f32=out, ldo32=N, alpha=0.5)
     ref = 0.5 * (a.float() @ w.float().t()) + bias + rowbias[:, 40:40 + N].repeat_interleave(HW, 0) + res
     assert relerr(out, ref) < 2e-3
-    o16 = torch.empty(M, N, dtype=torch.bfloat16, device=cuda_device)
+    o16 = torch.empty(M, N, dtype=DT, device=cuda_device)
     ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, N, w, bias=bias, out_bf16=o16, ldo16=N, act=1)
     assert relerr(o16, F.silu(a.float() @ w.float().t() + bias)) < 1e-2
     ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, N, w, bias=bias, out_bf16=o16, ldo16=N, act=3)
     assert relerr(o16, F.relu(a.float() @ w.float().t() + bias)) < 1e-2
     # narrow N (latent head): N=4 of a 16-row padded weight, scalar epilogue path, pitch 4
-    w16 = torch.zeros(16, K, dtype=torch.bfloat16, device=cuda_device)
+    w16 = torch.zeros(16, K, dtype=DT, device=cuda_device)
     w16[:4] = w[:4]
     o4 = torch.empty(M, 4, device=cuda_device)
     ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, 4, w16, Nw=16, bias=bias[:16].contiguous(), out_f32=o4, ldo32=4, bn=16)
@@ -93,8 +100,8 @@ def test_gemm_geglu(ops, cuda_device):
     x = bf(torch.randn(M, Cc, device=cuda_device, generator=g))
     w = torch.randn(8 * Cc, Cc, device=cuda_device, generator=g) / math.sqrt(Cc)
     b = torch.randn(8 * Cc, device=cuda_device, generator=g)
-    wp, bp = ops.pack_geglu(w, b)
-    out = torch.empty(M, 4 * Cc, dtype=torch.bfloat16, device=cuda_device)
+    wp, bp = ops.pack_geglu(w, b, dtype=DT)
+    out = torch.empty(M, 4 * Cc, dtype=DT, device=cuda_device)
     ops.gemm([ops.make_seg(x, 1, 1, M, Cc)], M, 4 * Cc, wp, Nw=8 * Cc, bias=bp, out_bf16=out, ldo16=4 * Cc, act=2)
     p = x.float() @ bf(w).float().t() + b
     h, gate = p.chunk(2, dim=-1)
@@ -109,7 +116,7 @@ def test_conv3x3(ops, cuda_device, B, H, W, Cin, Cout):
     x = bf(torch.randn(B, Cin, H, W, device=cuda_device, generator=g))
     w = torch.randn(Cout, Cin, 3, 3, device=cuda_device, generator=g) / math.sqrt(9 * Cin)
     bias = torch.randn(Cout, device=cuda_device, generator=g)
-    wp = ops.pack_conv(w)
+    wp = ops.pack_conv(w, dtype=DT)
     a = nhwc(x)
     M = B * H * W
     out = torch.empty(M, Cout, device=cuda_device)
@@ -125,12 +132,12 @@ def test_conv3x3_stride2(ops, cuda_device, pad1, B, H, W, Cc):
     x = torch.randn(B, Cc, H, W, device=cuda_device, generator=g)
     w = torch.randn(Cc, Cc, 3, 3, device=cuda_device, generator=g) / math.sqrt(9 * Cc)
     bias = torch.randn(Cc, device=cuda_device, generator=g)
-    s2d = ops.space_to_depth(nhwc(x))
+    s2d = ops.space_to_depth(nhwc(x), dtype=DT)
     # space-to-depth is pure data movement: bit-exact
     xb = bf(nhwc(x))
     for ph in range(4):
         assert torch.equal(s2d[ph], xb[:, (ph // 2)::2, (ph % 2)::2, :])
-    wp = ops.pack_conv(w)
+    wp = ops.pack_conv(w, dtype=DT)
     Ho, Wo = H // 2, W // 2
     M = B * Ho * Wo
     out = torch.empty(M, Cc, device=cuda_device)
@@ -152,7 +159,7 @@ def test_conv_plus_shortcut_two_segments(ops, cuda_device):
     w2 = torch.randn(Cout, Cout, 3, 3, device=cuda_device, generator=g) / math.sqrt(9 * Cout)
     ws = torch.randn(Cout, Cin, 1, 1, device=cuda_device, generator=g) / math.sqrt(Cin)
     K = 9 * Cout + Cin
-    wp = torch.empty(Cout, K, dtype=torch.bfloat16, device=cuda_device)
+    wp = torch.empty(Cout, K, dtype=DT, device=cuda_device)
     ops.pack_conv(w2, out=wp, ldo=K)
     ops.pack_conv(ws, out=wp[:, 9 * Cout:], ldo=K)
     M = B * H * W
@@ -168,7 +175,7 @@ def test_upsample_conv(ops, cuda_device):
     g = torch.Generator(device="cuda").manual_seed(31)
     B, H, W, Cc = 2, 8, 8, 128
     x = torch.randn(B, Cc, H, W, device=cuda_device, generator=g)
-    up = ops.upsample2x(nhwc(x))
+    up = ops.upsample2x(nhwc(x), dtype=DT)
     assert torch.equal(up, bf(nhwc(F.interpolate(x, scale_factor=2.0, mode="nearest"))))
 
 
@@ -179,9 +186,9 @@ def test_image_im2col_first_conv(ops, cuda_device):
     w = torch.randn(128, 3, 3, 3, device=cuda_device, generator=g) / math.sqrt(27)
     bias = torch.randn(128, device=cuda_device, generator=g)
     flag = torch.zeros(1, dtype=torch.int32, device=cuda_device)
-    col = ops.image_im2col(img, flag)
-    wp = ops.pack_conv(w, Cpad=3)  # K = 27 -> padded to 64 by the packer
-    wp64 = torch.zeros(128, 64, dtype=torch.bfloat16, device=cuda_device)
+    col = ops.image_im2col(img, flag, dtype=DT)
+    wp = ops.pack_conv(w, Cpad=3, dtype=DT)  # K = 27 -> padded to 64 by the packer
+    wp64 = torch.zeros(128, 64, dtype=DT, device=cuda_device)
     wp64[:, :27] = wp[:, :27]
     M = B * H * W
     out = torch.empty(M, 128, device=cuda_device)
@@ -190,7 +197,7 @@ def test_image_im2col_first_conv(ops, cuda_device):
     ref = nhwc(F.conv2d(xn, bf(w).float(), bias, padding=1)).reshape(M, 128)
     assert relerr(out, ref) < 2e-3
     assert flag.item() == 0
-    ops.image_im2col(img * 1.5, flag)
+    ops.image_im2col(img * 1.5, flag, dtype=DT)
     assert flag.item() == 1  # out-of-range input is reported (reference asserts, ldm_diffusers.py:147)
 
 
@@ -204,7 +211,7 @@ def test_groupnorm(ops, cuda_device, B, HW, C0, C1, act):
     Cc = C0 + C1
     gamma = torch.randn(Cc, device=cuda_device, generator=g)
     beta = torch.randn(Cc, device=cuda_device, generator=g)
-    y = torch.empty(B, HW, Cc, dtype=torch.bfloat16, device=cuda_device)
+    y = torch.empty(B, HW, Cc, dtype=DT, device=cuda_device)
     raw = torch.empty_like(y)
     ops.groupnorm(x0, x1, B, HW, gamma, beta, 1e-5, act, y, raw)
     x = torch.cat([x0, x1], -1) if C1 else x0
@@ -220,7 +227,7 @@ def test_layernorm(ops, cuda_device, M, Cc):
     x = torch.randn(M, Cc, device=cuda_device, generator=g) * 3 + 1
     gamma = torch.randn(Cc, device=cuda_device, generator=g)
     beta = torch.randn(Cc, device=cuda_device, generator=g)
-    y = torch.empty(M, Cc, dtype=torch.bfloat16, device=cuda_device)
+    y = torch.empty(M, Cc, dtype=DT, device=cuda_device)
     ops.layernorm(x, gamma, beta, 1e-5, y)
     assert relerr(y, F.layer_norm(x, (Cc,), gamma, beta, 1e-5)) < 1e-2
 
@@ -228,7 +235,7 @@ def test_layernorm(ops, cuda_device, M, Cc):
 def test_softmax_rows(ops, cuda_device):
     g = torch.Generator(device="cuda").manual_seed(3)
     s = torch.randn(300, 4096, device=cuda_device, generator=g) * 4
-    p = torch.empty(300, 4096, dtype=torch.bfloat16, device=cuda_device)
+    p = torch.empty(300, 4096, dtype=DT, device=cuda_device)
     ops.softmax_rows(s, p)
     assert relerr(p, torch.softmax(s, -1)) < 1e-2
 
@@ -266,7 +273,7 @@ def test_attention(ops, cuda_device, B, heads, d, Nq, Nk):
         q, k, v = qb, kvb[..., 128:128 + Cc], kvb[..., 128 + Cc:128 + 2 * Cc]
         ldq, ldk = Cc, ldkv
         q_bs, kv_bs = Nq * Cc, Nk * ldkv
-    o = torch.empty(B, Nq, Cc, dtype=torch.bfloat16, device=cuda_device)
+    o = torch.empty(B, Nq, Cc, dtype=DT, device=cuda_device)
     ops.attention(q, ldq, k, ldk, v, ldk, o, Cc, B, heads, d, Nq, Nk, q_bs, kv_bs, Nq * Cc, 1.0 / math.sqrt(d))
     split = lambda t: t.float().reshape(B, -1, heads, d).transpose(1, 2)  # noqa: E731
     ref = F.scaled_dot_product_attention(split(q), split(k), split(v)).transpose(1, 2).reshape(B, Nq, Cc)
@@ -280,10 +287,10 @@ def test_pack_linear_lora_fold(ops, cuda_device):
     w = torch.randn(N, K, device=cuda_device, generator=g)
     A = torch.randn(r, K, device=cuda_device, generator=g) / r
     Bm = torch.randn(N, r, device=cuda_device, generator=g) * 0.02
-    out = ops.pack_linear(w, A, Bm, scale=2.0)
+    out = ops.pack_linear(w, A, Bm, scale=2.0, dtype=DT)
     ref = bf(w + 2.0 * (Bm @ A))
     # fp32 sum order may differ by an ulp before the bf16 rounding: allow 1 bf16 ulp on <0.1% of entries
     diff = (out.float() - ref.float()).abs()
     assert (diff > 0).float().mean().item() < 1e-3
     assert relerr(out, ref) < 1e-2
-    assert torch.equal(ops.pack_linear(w), bf(w))
+    assert torch.equal(ops.pack_linear(w, dtype=DT), bf(w))
