@@ -120,6 +120,21 @@ typedef struct madm_extract_args {
 /* The whole path a-1..a-9 of SURVEY §8: VAE encode -> q-sample -> UNet forward with taps -> GN-bottleneck projections. */
 int madm_extract(madm_ctx* ctx, const madm_extract_args* args, madm_stream stream);
 
+/* Per-kernel-family device timing of the last madm_extract call (CUDA events recorded on the launch stream around every
+ * launch while profiling is on), with the algorithmic FLOPs / HBM bytes of those launches: the inputs of the roofline
+ * line bench.py prints.  madm_get_profile synchronises the device. */
+#define MADM_KIND_GEMM 0        /* gemm_tc_kernel: all convs / linears (tensor-bound) */
+#define MADM_KIND_ATTENTION 1   /* flash_attn_kernel */
+#define MADM_KIND_GROUPNORM 2   /* gn_stats / gn_apply / gn_add_relu_nchw (HBM-bound) */
+#define MADM_KIND_LAYERNORM 3
+#define MADM_KIND_ELEMENTWISE 4 /* im2col, q-sample, space-to-depth, upsample, softmax rows, casts */
+#define MADM_NUM_KINDS 5
+typedef struct madm_profile {
+  struct { char name[32]; int32_t launches; double ms; double flops; double bytes; } kind[MADM_NUM_KINDS];
+} madm_profile;
+int madm_set_profiling(madm_ctx* ctx, int32_t on);
+int madm_get_profile(madm_ctx* ctx, madm_profile* out);
+
 /* Number of kernels one madm_extract call launches for batch B with the given stage mask (for bench accounting). */
 int madm_launch_count(madm_ctx* ctx, int32_t B, int32_t stages);
 
@@ -154,8 +169,9 @@ typedef struct madm_gemm_args {
 
 int madm_op_gemm(const madm_gemm_args* a, madm_stream stream);
 int madm_op_groupnorm(const float* x0, int32_t C0, const float* x1, int32_t C1, int32_t B, int32_t HW, const float* gamma,
-                      const float* beta, float eps, int32_t act, float* stats_scratch /*[B,32,2], zeroed by the call*/,
+                      const float* beta, float eps, int32_t act, float* stats_scratch /* madm_op_groupnorm_scratch_floats() */,
                       void* y_bf16, void* raw_bf16, int32_t dtype, madm_stream stream);
+int madm_op_groupnorm_scratch_floats(int32_t B, int32_t HW, int32_t C); /* scratch size (floats) for the two GN ops */
 int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y_bf16,
                       int32_t dtype, madm_stream stream);
 int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p_bf16, int32_t dtype, madm_stream stream);
@@ -175,7 +191,7 @@ int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t 
 int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out_bf16, int32_t* range_flag,
                          int32_t dtype, madm_stream stream);
 int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, const float* s, const float* gs, const float* bs,
-                             int32_t has_shortcut_norm, float eps, int32_t B, int32_t HW, int32_t C, float* stats_scratch /*[2,B,32,2]*/,
+                             int32_t has_shortcut_norm, float eps, int32_t B, int32_t HW, int32_t C, float* stats_scratch,
                              float* out_nchw, madm_stream stream);
 
 #ifdef __cplusplus

@@ -36,6 +36,14 @@ class MadmExtractArgs(C.Structure):
     ]
 
 
+class _MadmProfileKind(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", c_int32), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
+
+
+class MadmProfile(C.Structure):
+    _fields_ = [("kind", _MadmProfileKind * 5)]
+
+
 class MadmGemmSeg(C.Structure):
     _fields_ = [("a", c_void_p), ("Bt", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("ld", c_int32),
                 ("ntaps", c_int32), ("dx", C.c_int8 * 9), ("dy", C.c_int8 * 9), ("b_off", c_int32 * 9)]
@@ -64,9 +72,12 @@ SYMBOLS = {
     "madm_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
     "madm_extract": (c_int, [c_void_p, C.POINTER(MadmExtractArgs), c_void_p]),
     "madm_launch_count": (c_int, [c_void_p, c_int32, c_int32]),
+    "madm_set_profiling": (c_int, [c_void_p, c_int32]),
+    "madm_get_profile": (c_int, [c_void_p, C.POINTER(MadmProfile)]),
     "madm_op_gemm": (c_int, [C.POINTER(MadmGemmArgs), c_void_p]),
     "madm_op_groupnorm": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_float,
                                   c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "madm_op_groupnorm_scratch_floats": (c_int, [c_int32, c_int32, c_int32]),
     "madm_op_layernorm": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
     "madm_op_softmax_rows": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_attention": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,

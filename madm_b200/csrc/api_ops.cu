@@ -53,7 +53,6 @@ int madm_op_gemm(const madm_gemm_args* a, madm_stream stream) {
 int madm_op_groupnorm(const float* x0, int32_t C0, const float* x1, int32_t C1, int32_t B, int32_t HW, const float* gamma,
                       const float* beta, float eps, int32_t act, float* stats, void* y, void* raw, int32_t dtype, madm_stream stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (cudaMemsetAsync(stats, 0, size_t(B) * 64 * sizeof(float), st) != cudaSuccess) return fail("memset failed");
   if (const char* e = groupnorm_stats(x0, C0, x1, C1, B, HW, stats, st)) return fail(e);
   RUN(groupnorm_apply(x0, C0, x1, C1, B, HW, stats, gamma, beta, eps, act, y, raw, dtype == MADM_DTYPE_FP16, st));
 }
@@ -103,16 +102,25 @@ int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void
   RUN(image_im2col(img, B, H, W, out, range_flag, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
+int madm_op_groupnorm_scratch_floats(int32_t B, int32_t HW, int32_t C) {
+  return int(size_t(2) * B * groupnorm_slabs(HW, C) * 64 + size_t(2) * B * 64);
+}
+
 int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, const float* s, const float* gs, const float* bs,
                              int32_t has_shortcut_norm, float eps, int32_t B, int32_t HW, int32_t C, float* stats, float* out,
                              madm_stream stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (cudaMemsetAsync(stats, 0, size_t(2) * B * 64 * sizeof(float), st) != cudaSuccess) return fail("memset failed");
-  float* st_a = stats;
-  float* st_s = stats + size_t(B) * 64;
-  if (const char* e = groupnorm_stats(a, C, nullptr, 0, B, HW, st_a, st)) return fail(e);
-  if (has_shortcut_norm)
-    if (const char* e = groupnorm_stats(s, C, nullptr, 0, B, HW, st_s, st)) return fail(e);
+  const size_t per = size_t(B) * groupnorm_slabs(HW, C) * 64;  // scratch: partials(a), partials(s), final(a), final(s)
+  float* pa = stats;
+  float* ps = stats + per;
+  float* st_a = stats + 2 * per;
+  float* st_s = st_a + size_t(B) * 64;
+  if (const char* e = groupnorm_stats(a, C, nullptr, 0, B, HW, pa, st)) return fail(e);
+  if (const char* e = groupnorm_finalize(pa, B, HW, C, st_a, st)) return fail(e);
+  if (has_shortcut_norm) {
+    if (const char* e = groupnorm_stats(s, C, nullptr, 0, B, HW, ps, st)) return fail(e);
+    if (const char* e = groupnorm_finalize(ps, B, HW, C, st_s, st)) return fail(e);
+  }
   RUN(gn_add_relu_nchw(a, st_a, ga, ba, s, has_shortcut_norm ? st_s : nullptr, gs, bs, eps, B, HW, C, out, st));
 }
 

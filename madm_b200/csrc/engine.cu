@@ -16,6 +16,7 @@
 #include <functional>
 #include <map>
 #include <math.h>
+#include <stdio.h>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -74,6 +75,11 @@ struct Plan {
   std::vector<Op> ops;
   std::vector<int> stage_of;  // stage bit per op
   std::vector<char> optional; // debug/taps ops that launch only when the caller asks for the extra output
+  std::vector<int> kind;      // MADM_KIND_* per op
+  std::vector<double> flops;  // algorithmic FLOPs per op (2*MAC)
+  std::vector<double> bytes;  // algorithmic HBM bytes per op (HBM-bound kernels)
+  std::vector<cudaEvent_t> ev;  // 2 per op, created on demand when profiling
+  ~Plan() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
   std::shared_ptr<IoBind> io = std::make_shared<IoBind>();
   size_t stats_off = 0, stats_bytes = 0;
 };
@@ -90,6 +96,9 @@ struct madm_ctx {
   size_t packed_bytes = 0;
   bool layout_done = false;
   float* alphas_cumprod = nullptr;  // [1000] device
+  bool profiling = false;
+  Plan* last_plan = nullptr;
+  int last_stages = 0;
   std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;  // (B, ema)
   std::map<int, size_t> ws_bytes_cache;
 };
@@ -190,12 +199,13 @@ struct Builder {
     return a;
   }
 
-  // ---- per-GroupNorm statistics slots ([B,32,2] fp32 each), zeroed by one memset at the start of each stage
+  // ---- per-GroupNorm statistics slots: per-slab partial sums [B, slabs, 32, 2] fp32 (each slot written by exactly one CTA
+  // per call, so no zeroing and no atomics) or finalised [B,32,2] (slabs = 1)
   size_t stats_used = 0;
   float* stats_base = nullptr;
-  float* new_stats() {
+  float* new_stats(int slabs) {
     float* p = stats_base ? stats_base + stats_used : nullptr;
-    stats_used += size_t(B) * 64;
+    stats_used += size_t(B) * slabs * 64;
     return p;
   }
 
@@ -285,21 +295,31 @@ struct Builder {
   }
 
   // ---- op emission
-  void emit(Op op, bool optional = false) {
+  void emit(Op op, bool optional = false, int kind = MADM_KIND_ELEMENTWISE, double flops = 0.0, double bytes = 0.0) {
     ++n_ops;
     if (mode == PLAN) {
       plan->ops.push_back(std::move(op));
       plan->stage_of.push_back(cur_stage);
       plan->optional.push_back(optional ? 1 : 0);
+      plan->kind.push_back(kind);
+      plan->flops.push_back(flops);
+      plan->bytes.push_back(bytes);
     }
   }
-  void gemm(const GemmDesc& d0) {
+  // algo_flops < 0: 2*M*N*K from the descriptor (K counts real channels only when k_real is given)
+  void gemm(const GemmDesc& d0, double algo_flops = -1.0) {
     if (mode != PLAN) { ++n_ops; return; }
     GemmDesc d = d0;
     d.fp16 = ctx->fp16;
     GemmLaunch L;
     if (const char* e = gemm_prepare(d, &L)) fail(MADM_EINVAL, std::string(e));
-    emit([L](cudaStream_t st) { return gemm_launch(L, st); });
+    if (algo_flops < 0) {
+      double K = 0;
+      for (int sgi = 0; sgi < d.nseg; ++sgi) K += double(d.seg[sgi].ntaps) * d.seg[sgi].C;
+      const double N = (d.act == ACT_GEGLU) ? 2.0 * d.N : double(d.N);
+      algo_flops = 2.0 * double(d.M) * N * K;
+    }
+    emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, 0.0);
   }
 
   static GemmASeg seg_1x1(const bf16* p, int Bn, int H, int W, int C, int ld = 0) {
@@ -334,12 +354,14 @@ struct Builder {
     const int C0 = x0.C, C1 = x1 ? x1->C : 0;
     const float* g = (mode == LAYOUT) ? nullptr : param(norm + ".weight", C0 + C1);
     const float* b = (mode == LAYOUT) ? nullptr : param(norm + ".bias", C0 + C1);
-    float* stats = new_stats();
+    float* stats = new_stats(groupnorm_slabs(x0.HW(), C0 + C1));
     const float* p0 = x0.f.p; const float* p1 = x1 ? x1->f.p : nullptr;
     const int Bn = x0.B, HW = x0.HW();
-    emit([=](cudaStream_t st) { return groupnorm_stats(p0, C0, p1, C1, Bn, HW, stats, st); });
+    const double elems = double(Bn) * HW * (C0 + C1);
+    emit([=](cudaStream_t st) { return groupnorm_stats(p0, C0, p1, C1, Bn, HW, stats, st); }, false, MADM_KIND_GROUPNORM, 0.0, elems * 4);
     const int f16 = ctx->fp16;
-    emit([=](cudaStream_t st) { return groupnorm_apply(p0, C0, p1, C1, Bn, HW, stats, g, b, eps, actfn, y, raw, f16, st); });
+    emit([=](cudaStream_t st) { return groupnorm_apply(p0, C0, p1, C1, Bn, HW, stats, g, b, eps, actfn, y, raw, f16, st); }, false,
+         MADM_KIND_GROUPNORM, 0.0, elems * (4 + 2 + (raw ? 2 : 0)));
   }
 };
 
@@ -440,7 +462,8 @@ struct Model {
       const float* g = P(name + ".weight", C); const float* be = P(name + ".bias", C);
       const float* src = hs.p; const int Mi = int(M);
       const int h16 = f16();
-      b.emit([=](cudaStream_t st) { return layernorm(src, Mi, C, g, be, 1e-5f, y, h16, st); });
+      b.emit([=](cudaStream_t st) { return layernorm(src, Mi, C, g, be, 1e-5f, y, h16, st); }, false, MADM_KIND_LAYERNORM, 0.0,
+             double(Mi) * C * 6);
     };
     // --- self attention
     B16T l1 = b.b16(size_t(M) * C);
@@ -458,7 +481,7 @@ struct Model {
       b.emit([=](cudaStream_t st) {
         return flash_attention(q, 3 * C, q + C, 3 * C, q + 2 * C, 3 * C, o, C, Bn, heads, d_head, n_tok, n_tok, long(n_tok) * 3 * C,
                                long(n_tok) * 3 * C, long(n_tok) * C, sc, h16, st);
-      }); }
+      }, false, MADM_KIND_ATTENTION, 4.0 * double(Bn) * n_tok * n_tok * C, 0.0); }
     b.free(qkv);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(att.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
       d.w = b.pw(b.linear_w(tb + ".attn1.to_out.0", C, C, true)); d.bias = lora_bias(tb + ".attn1.to_out.0", C);
@@ -475,7 +498,7 @@ struct Model {
       b.emit([=](cudaStream_t st) {
         return flash_attention(q, C, kv + off, ldkv, kv + off + C, ldkv, o, C, Bn, heads, d_head, n_tok, 77, long(n_tok) * C,
                                long(77) * ldkv, long(n_tok) * C, sc, h16, st);
-      }); }
+      }, false, MADM_KIND_ATTENTION, 4.0 * double(Bn) * n_tok * 77 * C, 0.0); }
     b.free(q2);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(att.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
       d.w = b.pw(b.linear_w(tb + ".attn2.to_out.0", C, C, true)); d.bias = lora_bias(tb + ".attn2.to_out.0", C);
@@ -569,7 +592,7 @@ struct Model {
         d.alpha = 1.0f / sqrtf(float(C)); d.out_f32 = S.p; d.ldo32 = T; b.gemm(d); }
       { const float* s = S.p; bf16* pm = Pm.p;
         const int h16 = f16();
-        b.emit([=](cudaStream_t st) { return softmax_rows(s, T, T, pm, h16, st); }); }
+        b.emit([=](cudaStream_t st) { return softmax_rows(s, T, T, pm, h16, st); }, false, MADM_KIND_ELEMENTWISE, 0.0, double(T) * T * 6); }
       { GemmDesc d; d.seg[0] = Builder::seg_plain(Pm.p, T, T); d.M = T; d.N = C; d.Nw = C; d.w = vt.p; d.ldw = T;
         d.bias = P(p + ".to_v.bias", C); d.out_bf16 = o.p ? o.p + size_t(i) * T * C : nullptr; d.ldo16 = C; b.gemm(d); }
     }
@@ -609,7 +632,8 @@ struct Model {
       b.emit([=](cudaStream_t st) { return image_im2col(io->a.img, Bn, R, R, dst, io->a.range_flag, h16, st); }); }
     Act x = b.act(Bn, R, R, 128, true, false);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(col.p, long(Bn) * R * R, 64); d.M = Bn * R * R; d.N = 128; d.Nw = 128;
-      d.w = b.pw(b.conv_w(e + "conv_in", 128, 3, 9, /*Cpad=*/3)); d.bias = P(e + "conv_in.bias", 128); d.out_f32 = x.f.p; d.ldo32 = 128; b.gemm(d); }
+      d.w = b.pw(b.conv_w(e + "conv_in", 128, 3, 9, /*Cpad=*/3)); d.bias = P(e + "conv_in.bias", 128); d.out_f32 = x.f.p; d.ldo32 = 128;
+      b.gemm(d, 2.0 * double(d.M) * 128 * 27); }
     b.free(col);
     const int ch[4] = {128, 256, 512, 512};
     int index = 0;
@@ -646,7 +670,8 @@ struct Model {
         q.src4 = kVae + "quant_conv.bias"; q.C = 512; q.off = b.pack_reserve(size_t(16) * 9 * 512 * 2); q.bias_off = b.pack_reserve(64);
         return q; });
       GemmDesc d; d.seg[0] = Builder::seg_3x3(n.p, Bn, x.H, x.W, 512); d.M = int(x.M()); d.N = 4; d.Nw = 16; d.w = b.pw(pe.off);
-      d.bias = b.pf(pe.bias_off); d.out_f32 = latents.p; d.ldo32 = 4; d.bn = 16; b.gemm(d); }
+      d.bias = b.pf(pe.bias_off); d.out_f32 = latents.p; d.ldo32 = 4; d.bn = 16;
+      b.gemm(d, 2.0 * double(d.M) * 8 * (9 * 512 + 8)); }  // algorithmic: conv_out 512->8 (3x3) + quant_conv 8->8
     b.free(n);
     b.free(x);
     if (dry()) b.emit(nullptr, true);
@@ -716,7 +741,8 @@ struct Model {
     // ---- conv_in
     Act x = b.act(Bn, 64, 64, 320, true, false);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(col.p, long(Bn) * 4096, 64); d.M = Bn * 4096; d.N = 320; d.Nw = 320;
-      d.w = b.pw(b.conv_w(kUnet + "conv_in", 320, 4, 9, /*Cpad=*/4)); d.bias = P(kUnet + "conv_in.bias", 320); d.out_f32 = x.f.p; d.ldo32 = 320; b.gemm(d); }
+      d.w = b.pw(b.conv_w(kUnet + "conv_in", 320, 4, 9, /*Cpad=*/4)); d.bias = P(kUnet + "conv_in.bias", 320); d.out_f32 = x.f.p; d.ldo32 = 320;
+      b.gemm(d, 2.0 * double(d.M) * 320 * 36); }
     b.free(col); b.free(noisy);
     // ---- down path
     std::vector<Act> skips;
@@ -810,11 +836,20 @@ struct Model {
         GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cin); d.M = int(M); d.N = Cout; d.Nw = Cout;
         d.w = b.pw(b.conv_w(p + "shortcut", Cout, Cin, 1)); d.out_f32 = sc.p; d.ldo32 = Cout; b.gemm(d);
       }
-      float* st3 = b.new_stats();
-      float* sts = shortcut ? b.new_stats() : nullptr;
-      const float* c3p = c3.p; const float* scp = shortcut ? sc.p : x.f.p; const int HW = H * W;
-      b.emit([=](cudaStream_t st) { return groupnorm_stats(c3p, Cout, nullptr, 0, Bn, HW, st3, st); });
-      if (shortcut) b.emit([=](cudaStream_t st) { return groupnorm_stats(scp, Cout, nullptr, 0, Bn, HW, sts, st); });
+      const int HW = H * W;
+      const int slabs = groupnorm_slabs(HW, Cout);
+      float* pt3 = b.new_stats(slabs);
+      float* pts = shortcut ? b.new_stats(slabs) : nullptr;
+      float* st3 = b.new_stats(1);
+      float* sts = shortcut ? b.new_stats(1) : nullptr;
+      const float* c3p = c3.p; const float* scp = shortcut ? sc.p : x.f.p;
+      const double pel = double(Bn) * HW * Cout;
+      b.emit([=](cudaStream_t st) { return groupnorm_stats(c3p, Cout, nullptr, 0, Bn, HW, pt3, st); }, false, MADM_KIND_GROUPNORM, 0.0, pel * 4);
+      b.emit([=](cudaStream_t st) { return groupnorm_finalize(pt3, Bn, HW, Cout, st3, st); }, false, MADM_KIND_GROUPNORM, 0.0, 0.0);
+      if (shortcut) {
+        b.emit([=](cudaStream_t st) { return groupnorm_stats(scp, Cout, nullptr, 0, Bn, HW, pts, st); }, false, MADM_KIND_GROUPNORM, 0.0, pel * 4);
+        b.emit([=](cudaStream_t st) { return groupnorm_finalize(pts, Bn, HW, Cout, sts, st); }, false, MADM_KIND_GROUPNORM, 0.0, 0.0);
+      }
       const float* g3 = P(p + "conv3.norm.weight", Cout); const float* b3 = P(p + "conv3.norm.bias", Cout);
       const float* gs = shortcut ? P(p + "shortcut.norm.weight", Cout) : nullptr;
       const float* bs = shortcut ? P(p + "shortcut.norm.bias", Cout) : nullptr;
@@ -823,7 +858,7 @@ struct Model {
         float* dst = io->a.out[i];
         if (!dst) return "madm_extract: output pointer is null";
         return gn_add_relu_nchw(c3p, st3, g3, b3, scp, sts, gs, bs, 1e-5f, Bn, HW, Cout, dst, st);
-      });
+      }, false, MADM_KIND_GROUPNORM, 0.0, pel * 12);
       b.free(c3);
       if (shortcut) b.free(sc);
     }
@@ -954,6 +989,7 @@ int madm_set_compute_dtype(madm_ctx* ctx, int32_t dtype) {
   if (f != ctx->fp16) {
     ctx->fp16 = f;
     ctx->plans.clear();
+    ctx->last_plan = nullptr;
   }
   return MADM_OK;
 }
@@ -976,6 +1012,7 @@ int madm_set_tensors(madm_ctx* ctx, const madm_tensor* named, int32_t n) {
     }
   }
   ctx->plans.clear();  // plans capture parameter pointers
+  ctx->last_plan = nullptr;
   return MADM_OK;
 }
 
@@ -1071,6 +1108,32 @@ size_t madm_workspace_bytes(madm_ctx* ctx, int32_t B) {
   return bytes;
 }
 
+int madm_set_profiling(madm_ctx* ctx, int32_t on) {
+  if (!ctx) return MADM_EINVAL;
+  ctx->profiling = on != 0;
+  return MADM_OK;
+}
+
+int madm_get_profile(madm_ctx* ctx, madm_profile* out) {
+  if (!ctx || !out) return set_err(ctx, MADM_EINVAL, "madm_get_profile: null argument");
+  Plan* plan = ctx->last_plan;
+  if (!plan || plan->ev.size() != 2 * plan->ops.size()) return set_err(ctx, MADM_ESTATE, "madm_get_profile: no profiled madm_extract call");
+  static const char* names[MADM_NUM_KINDS] = {"gemm_tc", "flash_attention", "groupnorm", "layernorm", "elementwise"};
+  for (int k = 0; k < MADM_NUM_KINDS; ++k) {
+    snprintf(out->kind[k].name, sizeof(out->kind[k].name), "%s", names[k]);
+    out->kind[k].launches = 0; out->kind[k].ms = 0; out->kind[k].flops = 0; out->kind[k].bytes = 0;
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) return set_err(ctx, MADM_ECUDA, "cudaDeviceSynchronize failed");
+  for (size_t i = 0; i < plan->ops.size(); ++i) {
+    if (!(plan->stage_of[i] & ctx->last_stages) || !plan->ops[i] || plan->optional[i]) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, plan->ev[2 * i], plan->ev[2 * i + 1]) != cudaSuccess) continue;
+    const int k = plan->kind[i];
+    out->kind[k].launches += 1; out->kind[k].ms += ms; out->kind[k].flops += plan->flops[i]; out->kind[k].bytes += plan->bytes[i];
+  }
+  return MADM_OK;
+}
+
 int madm_launch_count(madm_ctx* ctx, int32_t B, int32_t stages) {
   if (!ctx || B < 1) return -1;
   auto it = ctx->plans.find({B, 0});
@@ -1079,7 +1142,7 @@ int madm_launch_count(madm_ctx* ctx, int32_t B, int32_t stages) {
   int n = 0;
   for (size_t i = 0; i < it->second->ops.size(); ++i)
     if ((it->second->stage_of[i] & stages) && it->second->ops[i] && !it->second->optional[i]) ++n;
-  return n + 1;  // + the statistics memset
+  return n;
 }
 
 int madm_extract(madm_ctx* ctx, const madm_extract_args* a, madm_stream stream) {
@@ -1130,11 +1193,20 @@ int madm_extract(madm_ctx* ctx, const madm_extract_args* a, madm_stream stream) 
     ctx->plans[key] = std::move(np);
   }
   plan->io->a = *a;
-  if (cudaMemsetAsync(plan->ws, 0, plan->stats_bytes, st) != cudaSuccess) return set_err(ctx, MADM_ECUDA, "cudaMemsetAsync failed");
+  const bool prof = ctx->profiling;
+  if (prof && plan->ev.size() != 2 * plan->ops.size()) {
+    plan->ev.resize(2 * plan->ops.size());
+    for (cudaEvent_t& e : plan->ev)
+      if (cudaEventCreate(&e) != cudaSuccess) return set_err(ctx, MADM_ECUDA, "cudaEventCreate failed");
+  }
   for (size_t i = 0; i < plan->ops.size(); ++i) {
     if (!(plan->stage_of[i] & a->stages) || !plan->ops[i]) continue;
+    if (prof) cudaEventRecord(plan->ev[2 * i], st);
     if (const char* e = plan->ops[i](st)) return set_err(ctx, MADM_ECUDA, std::string(e) + " (op " + std::to_string(i) + ")");
+    if (prof) cudaEventRecord(plan->ev[2 * i + 1], st);
   }
+  ctx->last_plan = plan;
+  ctx->last_stages = a->stages;
   return MADM_OK;
 }
 

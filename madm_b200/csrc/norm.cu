@@ -18,7 +18,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // grid = (slabs, B); block = Q*P threads, Q = C/4 channel quads, P pixel lanes.  Thread (q, pl) owns channels 4q..4q+3
 // and walks pixels pl, pl+P, ... of its slab, so its per-channel partial sums stay in registers.
 __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int HW,
-                                int pix_per_cta, int P, float* __restrict__ stats /*[B,32,2]*/) {
+                                int pix_per_cta, int P, float* __restrict__ partial /*[B,slabs,32,2]*/) {
   extern __shared__ float sm[];  // [2][P][C]
   const int C = C0 + C1;
   const int Q = C >> 2;
@@ -56,26 +56,47 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
     float acc = 0.f;
     for (int pp = 0; pp < P; ++pp)
       for (int k = 0; k < cpg; ++k) acc += base[pp * C + g * cpg + k];
-    atomicAdd(stats + (size_t(b) * 32 + g) * 2 + (threadIdx.x < 32 ? 0 : 1), acc);
+    // one slot per (image, slab, group, moment): no atomics, so the statistics are bit-reproducible run to run and
+    // independent of the batch size (the slab geometry depends on HW and C only)
+    partial[((size_t(b) * gridDim.x + blockIdx.x) * 32 + g) * 2 + (threadIdx.x < 32 ? 0 : 1)] = acc;
   }
+}
+
+// fixed-order reduction of the per-slab partial sums -> smem[64] = {sum_g, sumsq_g}
+__device__ __forceinline__ void gn_reduce_partials(const float* __restrict__ partial, int b, int slabs, float* red /*[64]*/) {
+  if (threadIdx.x < 64) {
+    const float* p = partial + size_t(b) * slabs * 64 + threadIdx.x;
+    float acc = 0.f;
+    for (int sidx = 0; sidx < slabs; ++sidx) acc += p[size_t(sidx) * 64];
+    red[threadIdx.x] = acc;
+  }
+  __syncthreads();
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int slabs, float* __restrict__ stats /*[B,32,2]*/) {
+  __shared__ float red[64];
+  gn_reduce_partials(partial, blockIdx.x, slabs, red);
+  if (threadIdx.x < 64) stats[size_t(blockIdx.x) * 64 + threadIdx.x] = red[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm apply
 // grid = (slabs, B); block 256.  Per-channel scale/shift for this image are built once in shared memory, then the slab
 // is streamed: y = act(x*scale + shift) -> bf16 (and optionally the un-normalised x -> bf16 for a 1x1 shortcut conv).
 __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int HW,
-                                int pix_per_cta, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                int pix_per_cta, const float* __restrict__ partial, int slabs, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int act, int fp16, uint16_t* __restrict__ y,
                                 uint16_t* __restrict__ raw) {
-  extern __shared__ float sm[];  // scale[C], shift[C]
+  extern __shared__ float sm[];  // scale[C], shift[C], red[64]
   const int C = C0 + C1;
   const int b = blockIdx.y;
   const int cpg = C / 32;
   const float inv_n = 1.0f / (float(HW) * float(cpg));
+  float* red = sm + 2 * C;
+  gn_reduce_partials(partial, b, slabs, red);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float su = stats[(size_t(b) * 32 + g) * 2 + 0];
-    const float sq = stats[(size_t(b) * 32 + g) * 2 + 1];
+    const float su = red[g * 2 + 0];
+    const float sq = red[g * 2 + 1];
     const float mean = su * inv_n;
     const float var = fmaxf(sq * inv_n - mean * mean, 0.0f);
     const float rstd = rsqrtf(var + eps);
@@ -105,15 +126,16 @@ __global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const floa
   }
 }
 
-static void gn_geometry(int B, int HW, int C, int* P, int* threads, int* ppc, int* slabs) {
+// Slab geometry depends on (HW, C) only, never on the batch size: image i of a batch-8 call reduces in exactly the same
+// order as a batch-1 call on that image.
+static void gn_geometry(int HW, int C, int* P, int* threads, int* ppc, int* slabs) {
   const int Q = C / 4;
   int p = (256 + Q - 1) / Q;
   if (p < 1) p = 1;
   while (Q * p > 1024) --p;
   *P = p;
   *threads = Q * p;
-  const long total = long(B) * HW;
-  long per = (total + 591) / 592;  // ~4 CTAs per SM
+  long per = (HW + 73) / 74;  // up to 74 slabs per image: 592 CTAs (4 per SM) at the benchmark batch of 8
   if (per < 4L * p) per = 4L * p;
   per = ((per + p - 1) / p) * p;
   if (per > HW) per = HW;
@@ -121,25 +143,36 @@ static void gn_geometry(int B, int HW, int C, int* P, int* threads, int* ppc, in
   *slabs = (HW + int(per) - 1) / int(per);
 }
 
-const char* groupnorm_stats(const float* x0, int C0, const float* x1, int C1, int B, int HW, float* stats, cudaStream_t st) {
+int groupnorm_slabs(int HW, int C) {
+  int P, threads, ppc, slabs;
+  gn_geometry(HW, C, &P, &threads, &ppc, &slabs);
+  return slabs;
+}
+
+const char* groupnorm_stats(const float* x0, int C0, const float* x1, int C1, int B, int HW, float* partial, cudaStream_t st) {
   const int C = C0 + C1;
   if (C % 128 != 0 && (C % 32 != 0 || C % 4 != 0)) return "groupnorm: C must be a multiple of 32";
   if (C0 % 4 != 0 || C1 % 4 != 0) return "groupnorm: source channel counts must be multiples of 4";
   if (C / 4 > 1024) return "groupnorm: C too large";
   int P, threads, ppc, slabs;
-  gn_geometry(B, HW, C, &P, &threads, &ppc, &slabs);
+  gn_geometry(HW, C, &P, &threads, &ppc, &slabs);
   const size_t smem = size_t(2) * P * C * sizeof(float);
-  gn_stats_kernel<<<dim3(slabs, B), threads, smem, st>>>(x0, C0, x1, C1, HW, ppc, P, stats);
+  gn_stats_kernel<<<dim3(slabs, B), threads, smem, st>>>(x0, C0, x1, C1, HW, ppc, P, partial);
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_stats launch failed";
 }
 
-const char* groupnorm_apply(const float* x0, int C0, const float* x1, int C1, int B, int HW, const float* stats,
+const char* groupnorm_finalize(const float* partial, int B, int HW, int C, float* stats, cudaStream_t st) {
+  gn_finalize_kernel<<<B, 64, 0, st>>>(partial, groupnorm_slabs(HW, C), stats);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_finalize launch failed";
+}
+
+const char* groupnorm_apply(const float* x0, int C0, const float* x1, int C1, int B, int HW, const float* partial,
                             const float* gamma, const float* beta, float eps, int act, void* y, void* raw, int fp16, cudaStream_t st) {
   const int C = C0 + C1;
   int P, threads, ppc, slabs;
-  gn_geometry(B, HW, C, &P, &threads, &ppc, &slabs);
-  const size_t smem = size_t(2) * C * sizeof(float);
-  gn_apply_kernel<<<dim3(slabs, B), 256, smem, st>>>(x0, C0, x1, C1, HW, ppc, stats, gamma, beta, eps, act, fp16,
+  gn_geometry(HW, C, &P, &threads, &ppc, &slabs);
+  const size_t smem = size_t(2 * C + 64) * sizeof(float);
+  gn_apply_kernel<<<dim3(slabs, B), 256, smem, st>>>(x0, C0, x1, C1, HW, ppc, partial, slabs, gamma, beta, eps, act, fp16,
                                                      reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_apply launch failed";
 }

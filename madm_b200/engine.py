@@ -159,5 +159,14 @@ class Engine:
         self._keep = [img, cond_inputs, cond_emb, timesteps, shared_noise, noisy_latents_in]
         return res
 
+    def set_profiling(self, on: bool):
+        _lib.check(self.lib.madm_set_profiling(self.ctx, 1 if on else 0), self.ctx, "madm_set_profiling")
+
+    def profile(self) -> Dict[str, Dict[str, float]]:
+        """Per kernel family: launches, device ms (CUDA events on the launch stream), algorithmic FLOPs / bytes."""
+        p = _lib.MadmProfile()
+        _lib.check(self.lib.madm_get_profile(self.ctx, C.byref(p)), self.ctx, "madm_get_profile")
+        return {k.name.decode(): dict(launches=k.launches, ms=k.ms, flops=k.flops, bytes=k.bytes) for k in p.kind}
+
     def launch_count(self, B: int, stages: int = STAGE_ALL) -> int:
         return int(self.lib.madm_launch_count(self.ctx, B, stages))

@@ -85,9 +85,9 @@ def gemm(segs: Sequence[MadmGemmSeg], M: int, N: int, w: torch.Tensor, *, Nw: in
 
 def groupnorm(x0, x1, B, HW, gamma, beta, eps, act, y, raw=None):
     lib = _lib.load()
-    stats = torch.empty(B * 64, dtype=torch.float32, device=x0.device)
     C0 = x0.shape[-1]
     C1 = x1.shape[-1] if x1 is not None else 0
+    stats = torch.empty(lib.madm_op_groupnorm_scratch_floats(B, HW, C0 + C1), dtype=torch.float32, device=x0.device)
     _lib.check(lib.madm_op_groupnorm(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(gamma), _ptr(beta), eps, act, _ptr(stats),
                                      _ptr(y), _ptr(raw), _dt(y.dtype), _stream()), None, "madm_op_groupnorm")
     return stats
@@ -168,7 +168,7 @@ def image_im2col(img, range_flag=None, dtype=torch.float16):
 
 def gn_add_relu_nchw(a, ga, ba, s, gs, bs, eps, B, HW, Cc):
     lib = _lib.load()
-    stats = torch.empty(2 * B * 64, dtype=torch.float32, device=a.device)
+    stats = torch.empty(lib.madm_op_groupnorm_scratch_floats(B, HW, Cc), dtype=torch.float32, device=a.device)
     out = torch.empty(B, Cc, HW, dtype=torch.float32, device=a.device)
     _lib.check(lib.madm_op_gn_add_relu_nchw(_ptr(a), _ptr(ga), _ptr(ba), _ptr(s), _ptr(gs), _ptr(bs), 1 if gs is not None else 0,
                                             eps, B, HW, Cc, _ptr(stats), _ptr(out), _stream()), None, "madm_op_gn_add_relu_nchw")

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Generates tests/golden/config1_b1.npz from the fp32 oracle on CPU (BASELINE config 1: 1x3x512x512, seed 0,
+input_modal='others', adapter Depth_r16_a16, synthetic weights of oracle/synthetic.py).
+
+The reference (XiaRho/MADM) cannot be imported here (diffusers / peft / detectron2 absent), so these vectors are outputs of
+the oracle restatement, not of the reference: PARITY UNPINNED (see oracle/__init__.py).  They pin the oracle against
+silent drift and let the GPU tests check the product without re-running the oracle.
+
+Run:  python tests/golden/make_golden.py     (about 30 s on 8 cores; deterministic for a given torch build)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import synthetic  # noqa: E402
+from oracle.lora import set_adapter  # noqa: E402
+
+SUB = {"s2": 4, "s3": 2, "s4": 1, "s5": 1, "enc_tap": 4, "unet_tap16": 1, "unet_tap32": 1, "unet_tap64": 2}
+
+
+def subsample(name, t):
+    s = SUB[name]
+    return t[:, :, ::s, ::s].contiguous()
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    bb = synthetic.build_backbone()
+    set_adapter(bb.feature_extractor.ldm_extractor.unet, ["Depth"])
+    img = synthetic.synthetic_images(1)
+    with torch.no_grad():
+        taps = bb.feature_extractor(dict(img=img), "others")
+        feats = bb.forward_features(taps)["output_features"]
+    inter = bb.feature_extractor.ldm_extractor.last_intermediates
+    out = {"latents": inter["latents"].numpy(), "noisy_latents": inter["noisy_latents"].numpy()}
+    for name, t in zip(["enc_tap", "unet_tap16", "unet_tap32", "unet_tap64"], taps):
+        out[name] = subsample(name, t).numpy().astype(np.float16)
+        out[name + "_absmax"] = np.float32(t.abs().max().item())
+    for name, t in feats.items():
+        out[name] = subsample(name, t).numpy().astype(np.float16)
+        out[name + "_absmax"] = np.float32(t.abs().max().item())
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "config1_b1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

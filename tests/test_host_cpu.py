@@ -1,0 +1,138 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the parameter holders expose the
+reference's state_dict keys, LoRA adapter bookkeeping, loud failure without a GPU, and the batch-sharding helper under a
+world_size-2 gloo group."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_all_declared_symbols():
+    from madm_b200 import _lib
+    lib = _lib.load()
+    assert lib.madm_version() >= 100
+    hdr = open(os.path.join(ROOT, "include", "madm_b200.h")).read()
+    declared = set(re.findall(r"\b(madm_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"madm_ctx", "madm_stream"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libmadm_b200.so does not export {name}"
+        assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype"
+
+
+def test_struct_layouts_match_header_sizes():
+    """ctypes mirrors of the POD structs must have the C sizes (compiled check through a tiny C program is overkill:
+    the fields are all 4/8-byte scalars and pointers, so sizes are deterministic)."""
+    import ctypes as C
+    from madm_b200 import _lib
+    assert C.sizeof(_lib.MadmTensor) == 8 + 8 + 8 + 32  # name, data, ndim(+pad), shape[4]
+    assert C.sizeof(_lib.MadmGemmSeg) == 8 + 6 * 4 + 9 + 9 + 2 + 9 * 4  # a, 6 ints, dx, dy, pad, b_off
+    assert C.sizeof(_lib.MadmProfile) == 5 * (32 + 8 + 3 * 8)
+
+
+def test_create_without_gpu_fails_loudly():
+    """No CPU fallback: without a CUDA device madm_create must fail with a message, and the Engine must raise."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ctypes as C
+    from madm_b200 import _lib
+    from madm_b200.engine import Engine
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.madm_create(C.byref(h), 0)
+    assert rc != 0 and b"no CUDA device" in lib.madm_last_error(None)
+    with pytest.raises(_lib.MadmError):
+        Engine(torch.device("cpu"))
+
+
+def test_state_dict_keys_match_oracle_and_reference_names():
+    """Product holders expose exactly the oracle's (= diffusers / peft / detectron2) state_dict keys."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import build_product_backbone
+    pb = build_product_backbone(torch.device("cpu"))
+    keys = set(pb.state_dict().keys())
+    pre = "feature_extractor.ldm_extractor."
+    for k in [pre + "unet.conv_in.weight", pre + "unet.time_embedding.linear_1.weight",
+              pre + "unet.down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.base_layer.weight",
+              pre + "unet.down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q.lora_A.Depth.weight",
+              pre + "unet.up_blocks.3.attentions.2.transformer_blocks.0.attn2.to_out.0.lora_B.default.weight",
+              pre + "unet.up_blocks.3.attentions.2.transformer_blocks.0.ff.net.0.proj.weight",
+              pre + "vae.encoder.mid_block.attentions.0.to_q.bias", pre + "vae.quant_conv.weight",
+              pre + "shared_noise", pre + "uncond_inputs",
+              "feature_extractor.clip_project_rgb.prompt_embed", "feature_extractor.clip_project_others.alpha_cond_time",
+              "feature_extractor.ema_clip_project_others.time_embed",
+              "feature_projections.0.0.conv1.weight", "feature_projections.1.0.shortcut.norm.bias",
+              "ema_feature_projections.3.0.conv3.norm.weight"]:
+        assert k in keys, k
+    assert "feature_projections.0.0.shortcut.weight" not in keys  # s2: 512 -> 512 has an identity shortcut
+    unet = pb.feature_extractor.ldm_extractor.unet
+    assert sum(p.numel() for n, p in unet.named_parameters() if "lora" not in n) == 859_520_964
+    assert len(list(unet.lora_layers())) == 128
+    shared = pb.feature_extractor.ldm_extractor.shared_noise
+    assert torch.equal(shared.cpu(), torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(42)))
+
+
+def test_adapter_selection_follows_reference_semantics():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import set_lora_adapter
+    from madm_b200.sd14_params import UNetParams
+    from types import SimpleNamespace
+    with torch.device("meta"):
+        unet = UNetParams(device="meta")
+    cfg = SimpleNamespace(r=16, lora_alpha=32, init_lora_weights="gaussian", target_modules=["to_k", "to_q", "to_v", "to_out.0"])
+    assert unet.active_adapter() is None  # no adapters: set_lora_adapter is a no-op in the reference (mtmadise.py:131-132)
+    unet.add_adapter(cfg, "default")
+    unet.add_adapter(cfg, "Depth")
+    set_lora_adapter(unet, "Depth")
+    assert unet.active_adapter() == "Depth" and unet.scaling_of("Depth") == 2.0
+    set_lora_adapter(unet, ["default", "Depth"])
+    with pytest.raises(NotImplementedError):
+        unet.active_adapter()
+
+
+def test_unsupported_configs_fail_loudly():
+    from madm_b200.ldm import LdmDiffusers
+    with pytest.raises(NotImplementedError):
+        LdmDiffusers(None, [5], [5, 8, 11], (), input_range="-1+1", unet_block_indices_type="after", vae_decoder_loss=True, device="cpu")
+    with pytest.raises(NotImplementedError):
+        LdmDiffusers(None, [], [5, 8, 11], (), input_range="-1+1", unet_block_indices_type="after", device="cpu")
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from madm_b200.sharding import shard_items, gather_max
+    items = list(range(21))  # e.g. the 21 crops of one 1024x2048 image
+    mine = shard_items(items, rank, world)
+    ms = gather_max(10.0 + rank)  # max-over-ranks timing reduction used by bench.py
+    allv = [None] * world
+    dist.all_gather_object(allv, mine)
+    q.put((rank, mine, ms, allv))
+    dist.destroy_process_group()
+
+
+def test_batch_sharding_world_size_2_gloo():
+    """The N>1 path: images / crops are split in contiguous blocks over ranks with no data-path collective; timing is the
+    max over ranks.  Exercised with a real 2-process gloo group on CPU."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, m0, t0, all0), (r1, m1, t1, all1) = res
+    assert m0 == list(range(0, 11)) and m1 == list(range(11, 21))
+    assert sorted(m0 + m1) == list(range(21))
+    assert t0 == t1 == 11.0
+    assert all0 == all1 == [m0, m1]

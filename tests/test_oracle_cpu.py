@@ -1,0 +1,176 @@
+"""CPU tests of the oracle (the checker itself): self-made known-answer tests (the reference ships no golden vectors —
+PARITY UNPINNED) and the committed golden fixture."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import backbone as ob
+from oracle import lora, sd14, synthetic
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_b1.npz")
+
+
+def nparams(m):
+    return sum(p.numel() for p in m.parameters())
+
+
+def test_sd14_parameter_counts():
+    """SD-1.4 known parameter totals (SURVEY §8c pin 1): UNet 859,520,964; VAE encoder 34,163,592; quant 72; post_quant 20."""
+    with torch.device("meta"):
+        unet = sd14.UNet2DConditionModel()
+        vae = sd14.AutoencoderKL()
+    assert nparams(unet) == 859_520_964
+    assert nparams(vae.encoder) == 34_163_592
+    assert nparams(vae.quant_conv) == 72
+    assert nparams(vae.post_quant_conv) == 20
+
+
+def test_lora_layer_count_and_params():
+    """128 wrapped projections; r * 199,296 parameters per adapter."""
+    with torch.device("meta"):
+        unet = sd14.UNet2DConditionModel()
+        n = lora.add_adapter(unet, "default", 16, 16)
+    assert n == 128
+    assert sum(p.numel() for k, p in unet.named_parameters() if "lora" in k) == 16 * 199_296
+    keys = dict(unet.named_parameters())
+    p = "down_blocks.0.attentions.0.transformer_blocks.0.attn1."
+    assert p + "to_q.base_layer.weight" in keys and p + "to_q.lora_A.default.weight" in keys
+    assert p + "to_out.0.base_layer.bias" in keys and p + "to_out.0.lora_B.default.weight" in keys
+
+
+def test_ddpm_alphas_and_reference_schedule():
+    """alpha_bar_0 = 0.99915 and equality with the reference's in-tree `ldm_linear` schedule
+    (modeling/diffusion/gaussian_diffusion.py:111-121: linspace(sqrt(b0), sqrt(b1), T)**2 in float64)."""
+    ac = sd14.ddpm_alphas_cumprod()
+    assert abs(ac[0].item() - 0.99915) < 1e-6
+    assert abs(ac[0].sqrt().item() - 0.999575) < 1e-6
+    assert abs((1 - ac[0]).sqrt().item() - 0.029155) < 1e-6
+    betas64 = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=np.float64) ** 2
+    ref = np.cumprod(1.0 - betas64)
+    assert np.allclose(ac.numpy(), ref, rtol=2e-5)
+
+
+def test_q_sample_matches_closed_form():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 4, 8, 8, generator=g)
+    noise = torch.randn(1, 4, 8, 8, generator=g)
+    t = torch.tensor([0, 500, 999])
+    ac = sd14.ddpm_alphas_cumprod()
+    y = sd14.add_noise(x, t, noise)
+    for i in range(3):
+        ref = ac[t[i]].sqrt() * x[i] + (1 - ac[t[i]]).sqrt() * noise[0]
+        assert torch.allclose(y[i], ref, atol=1e-6)
+
+
+def test_shared_noise_is_seed_42():
+    with torch.device("cpu"):
+        ldm = ob.LdmDiffusers.__new__(ob.LdmDiffusers)
+    ref = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(42))
+    torch.nn.Module.__init__(ldm)
+    ldm.register_buffer("shared_noise", torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(42)))
+    assert torch.equal(ldm.shared_noise, ref)
+
+
+def test_timestep_sinusoid_layout():
+    e = sd14.timestep_sinusoid(torch.tensor([0, 7]), 320)
+    assert e.shape == (2, 320)
+    assert torch.allclose(e[0, :160], torch.ones(160)) and torch.allclose(e[0, 160:], torch.zeros(160))  # cos | sin
+    assert abs(e[1, 0].item() - math.cos(7.0)) < 1e-6 and abs(e[1, 160].item() - math.sin(7.0)) < 1e-6
+
+
+def test_lora_merged_equals_unmerged():
+    """W' = W + alpha/r * B@A reproduces the unmerged peft forward (SURVEY §8c pin 5)."""
+    torch.manual_seed(0)
+    lin = lora.LoraLinear(torch.nn.Linear(64, 48, bias=True))
+    lin.update_layer("Depth", 16, 32)
+    with torch.no_grad():
+        lin.lora_B["Depth"].weight.normal_(0, 0.02)
+    lin._active_adapter = ["Depth"]
+    x = torch.randn(5, 64)
+    y = lin(x)
+    y2 = torch.nn.functional.linear(x, lin.merged_weight("Depth"), lin.base_layer.bias)
+    assert torch.allclose(y, y2, atol=1e-5)
+    lin._active_adapter = ["other"]  # inactive adapter -> base layer only
+    assert torch.allclose(lin(x), lin.base_layer(x))
+
+
+def test_bottleneck_block_matches_manual():
+    torch.manual_seed(0)
+    blk = ob.BottleneckBlock(96, 64, 32)
+    x = torch.randn(2, 96, 8, 8)
+    F = torch.nn.functional
+    o = F.relu(blk.conv1.norm(F.conv2d(x, blk.conv1.weight)))
+    o = F.relu(blk.conv2.norm(F.conv2d(o, blk.conv2.weight, padding=1)))
+    o = blk.conv3.norm(F.conv2d(o, blk.conv3.weight))
+    s = blk.shortcut.norm(F.conv2d(x, blk.shortcut.weight))
+    assert torch.allclose(blk(x), F.relu(o + s), atol=1e-6)
+    assert ob.BottleneckBlock(64, 64, 32).shortcut is None
+
+
+def test_slide_windows_reduce_to_reference_triplet():
+    """On 512x1024 the stride-256 windows are exactly the reference's hard-coded three (feature_extractor.py:75)."""
+    with torch.device("meta"):
+        bb = ob.AttentionFeatureExtractorBackbone.__new__(ob.AttentionFeatureExtractorBackbone)
+    assert ob.AttentionFeatureExtractorBackbone.slide_windows(bb, 512, 1024) == [(0, 512, 0, 512), (0, 512, 256, 768), (0, 512, 512, 1024)]
+    assert len(ob.AttentionFeatureExtractorBackbone.slide_windows(bb, 1024, 1024)) == 9
+    assert len(ob.AttentionFeatureExtractorBackbone.slide_windows(bb, 1024, 2048)) == 21
+
+
+@pytest.fixture(scope="module")
+def oracle_run():
+    torch.set_num_threads(os.cpu_count() or 1)
+    bb = synthetic.build_backbone()
+    lora.set_adapter(bb.feature_extractor.ldm_extractor.unet, ["Depth"])
+    img = synthetic.synthetic_images(1)
+    with torch.no_grad():
+        taps = bb.feature_extractor(dict(img=img), "others")
+        feats = bb.forward_features(taps)["output_features"]
+    return bb, img, taps, feats
+
+
+def test_oracle_tap_shapes_and_golden(oracle_run):
+    """Tap shapes (reference comments feature_extractor.py:321-346) and the committed golden fixture."""
+    bb, img, taps, feats = oracle_run
+    assert [tuple(t.shape) for t in taps] == [(1, 512, 128, 128), (1, 1280, 16, 16), (1, 640, 32, 32), (1, 320, 64, 64)]
+    assert {k: tuple(v.shape) for k, v in feats.items()} == {"s2": (1, 512, 128, 128), "s3": (1, 512, 64, 64), "s4": (1, 512, 32, 32),
+                                                             "s5": (1, 512, 16, 16)}
+    g = np.load(GOLDEN)
+    inter = bb.feature_extractor.ldm_extractor.last_intermediates
+    assert np.allclose(inter["latents"].numpy(), g["latents"], atol=2e-4)
+    sub = {"s2": 4, "s3": 2, "s4": 1, "s5": 1}
+    for k, s in sub.items():
+        got = feats[k][:, :, ::s, ::s].numpy()
+        ref = g[k].astype(np.float32)
+        assert np.abs(got - ref).max() <= 2e-3 * float(g[k + "_absmax"]) + 2e-3, k  # fp16 storage of the fixture + thread-count jitter
+
+
+def test_bf16_error_budget(oracle_run):
+    """Error budget of an IDEAL 16-bit-operand pipeline, emulated by rounding every GEMM operand (weights + activations) in
+    the oracle while keeping accumulation, norms and the residual stream in fp32 — exactly the product's storage plan.
+    bf16 operands put the projected maps at ~2.2e-2 (above the 2e-2 gate); fp16 operands at ~3e-3.  This is why the product
+    defaults to fp16 operands (the reference's own AMP dtype) and offers bf16 as an option (Numerics)."""
+    bb, img, taps, feats = oracle_run
+    import copy
+    res = {}
+    for name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        b2 = copy.deepcopy(bb)
+        rnd = lambda t, dt=dt: t.to(dt).to(torch.float32)  # noqa: E731
+        with torch.no_grad():
+            for n, p in b2.named_parameters():
+                if p.dim() >= 2 and "norm" not in n and "prompt" not in n and "time_embed" not in n and "alpha" not in n:
+                    p.copy_(rnd(p))
+        sd14.set_storage_rounding(operand=rnd)
+        try:
+            with torch.no_grad():
+                t2 = b2.feature_extractor(dict(img=img), "others")
+                f2 = b2.forward_features(t2)["output_features"]
+        finally:
+            sd14.set_storage_rounding()
+        res[name] = max(((f2[k] - feats[k]).abs().max() / feats[k].abs().max()).item() for k in feats)
+        del b2
+    print("ideal-pipeline max-rel error on projected maps:", res)
+    assert res["fp16"] < 6e-3
+    assert 1.2e-2 < res["bf16"] < 3.5e-2
