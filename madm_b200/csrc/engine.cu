@@ -17,6 +17,7 @@
 #include <map>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -318,6 +319,12 @@ struct Builder {
       for (int sgi = 0; sgi < d.nseg; ++sgi) K += double(d.seg[sgi].ntaps) * d.seg[sgi].C;
       const double N = (d.act == ACT_GEGLU) ? 2.0 * d.N : double(d.N);
       algo_flops = 2.0 * double(d.M) * N * K;
+    }
+    if (getenv("MADM_DUMP_PLAN")) {
+      int K = 0;
+      for (int sgi = 0; sgi < d.nseg; ++sgi) K += d.seg[sgi].ntaps * d.seg[sgi].C;
+      fprintf(stderr, "MADM_PLAN gemm M=%d N=%d K=%d bn=%d tiles=%d taps=%d nseg=%d act=%d res=%d f32=%d h16=%d gflop=%.3f\n", d.M, d.N, K, L.bn,
+              L.num_tiles, d.seg[0].ntaps, d.nseg, d.act, d.residual ? 1 : 0, d.out_f32 ? 1 : 0, d.out_bf16 ? 1 : 0, algo_flops / 1e9);
     }
     emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, 0.0);
   }

@@ -22,8 +22,11 @@ namespace madm {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int kThreads = 192;
+static constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quarter, interleaved over 32-column chunks
+static constexpr int kThreads = 64 + 32 * kEpiWarps;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+static constexpr int STG_LD = 36;                   // floats per staging row (32 + 4 pad: conflict-free 128-bit access)
+static constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
 
 struct GemmParams {
   CUtensorMap tmA[2];
@@ -52,43 +55,88 @@ struct GemmParams {
   int vec_ok;
   int n_tiles;
   int fp16;
+  int num_tiles;
 };
 
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  // keep <= ~110 KB so two CTAs fit in one SM's 227 KB
-  static constexpr int STAGES = (110 * 1024 / STAGE_BYTES) > 6 ? 6 : (110 * 1024 / STAGE_BYTES);
-  static constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
-  static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = kEpiWarps * STG_WARP_BYTES;  // per-epilogue-warp transpose staging
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - EPI_BYTES;
+  static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
+  static constexpr int ACC_STRIDE = BN <= 16 ? 16 : (BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256)));
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE < 32 ? 32 : 2 * ACC_STRIDE;  // two accumulator stages
+  static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 };
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 __device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
+// Fused epilogue of one 32x32 fp32 block that sits transposed in this warp's staging buffer: lane = (row sub-index, 4
+// columns), 8 iterations of 4 rows -> every global access is a full 128-byte row segment.  `bb` already holds
+// bias (+ the per-image time-embedding row bias).  Compile-time flags keep the loop free of uniform branches.
+template <bool RES, bool O32, bool O16>
+__device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int M, float alpha, float4 bb, int act, int fp16,
+                                          const float* __restrict__ res, int ldr, float* o32, int ldo32, uint16_t* o16, int ldo16) {
+  const int rsub = lane >> 3;
+  const int cc = (lane & 7) * 4;
+  float4 resv[8];
+  if constexpr (RES) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + rsub;
+      resv[it] = (row0 + r < M) ? *reinterpret_cast<const float4*>(res + size_t(r) * ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + rsub;
+    float4 v = ld_shared_f4(stg + uint32_t(r * STG_LD + cc) * 4);
+    v.x = fmaf(v.x, alpha, bb.x); v.y = fmaf(v.y, alpha, bb.y); v.z = fmaf(v.z, alpha, bb.z); v.w = fmaf(v.w, alpha, bb.w);
+    if constexpr (RES) { v.x += resv[it].x; v.y += resv[it].y; v.z += resv[it].z; v.w += resv[it].w; }
+    if (act == ACT_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+    else if (act == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (row0 + r < M) {
+      if constexpr (O32) *reinterpret_cast<float4*>(o32 + size_t(r) * ldo32) = v;
+      if constexpr (O16) *reinterpret_cast<uint2*>(o16 + size_t(r) * ldo16) = pack4_16(v.x, v.y, v.z, v.w, fp16);
+    }
+  }
+}
 
+// Persistent, warp-specialised kernel: one CTA per SM walks the tile list (tile = blockIdx.x + i*gridDim.x, N fastest).
+//   warp 0      TMA producer: fills the STAGES-deep smem ring (A box + W box per 64-wide K chunk)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; two accumulator stages in TMEM so the MMAs of tile
+//               i+1 overlap the epilogue of tile i
+//   warps 2..5  epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> coalesced fused epilogue
+//               (bias / time-embedding row bias / fp32 residual / SiLU / ReLU / GEGLU) -> fp32 and/or 16-bit stores
 template <int BN>
-__global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + C::STAGES * A_STAGE_BYTES;
-  const uint32_t sBar = sB + C::STAGES * C::B_STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full, tmem_addr
+  const uint32_t sEpi = sB + C::STAGES * C::B_STAGE_BYTES;
+  const uint32_t sBar = sEpi + C::EPI_BYTES;  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_addr
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (C::STAGES + s); };
-  const uint32_t tmem_full_bar = sBar + 8u * (2 * C::STAGES);
-  const uint32_t tmem_slot = sBar + 8u * (2 * C::STAGES + 1);
+  auto tmem_full_bar = [&](int a) { return sBar + 8u * (2 * C::STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return sBar + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_slot = sBar + 8u * (2 * C::STAGES + 4);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x % p.n_tiles;
-  const int tile_m = blockIdx.x / p.n_tiles;
-  const int m0 = tile_m * BM;
-  const int n0 = tile_n * BN;
   const int total_chunks = p.kchunks[0] + (p.nseg > 1 ? p.kchunks[1] : 0);
 
   if (warp == 0 && lane == 0) {
@@ -99,7 +147,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), kEpiWarps);  // one arrival per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -114,32 +165,37 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int x0, y0, b0;
-      if (p.pix >= BM) {
-        b0 = m0 / p.pix;
-        const int rem = m0 - b0 * p.pix;
-        y0 = rem / p.W;
-        x0 = rem - y0 * p.W;
-      } else {
-        b0 = m0 / p.pix;
-        y0 = 0;
-        x0 = 0;
-      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int kc = 0; kc < total_chunks; ++kc) {
-        const int seg = (kc < p.kchunks[0]) ? 0 : 1;
-        const int lk = seg ? kc - p.kchunks[0] : kc;
-        const int tap = lk / p.cpt[seg];
-        const int cc = lk - tap * p.cpt[seg];
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-        tma_load_4d(sA + stage * A_STAGE_BYTES, &p.tmA[seg], full_bar(stage), cc * BK, x0 + p.dx[seg][tap],
-                    y0 + p.dy[seg][tap], b0 + p.boff[seg][tap]);
-        tma_load_2d(sB + stage * C::B_STAGE_BYTES, &p.tmB, full_bar(stage), kc * BK, n0);
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1u;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int tile_n = t % p.n_tiles;
+        const int m0 = (t / p.n_tiles) * BM;
+        const int n0 = tile_n * BN;
+        int x0, y0, b0;
+        if (p.pix >= BM) {
+          b0 = m0 / p.pix;
+          const int rem = m0 - b0 * p.pix;
+          y0 = rem / p.W;
+          x0 = rem - y0 * p.W;
+        } else {
+          b0 = m0 / p.pix;
+          y0 = 0;
+          x0 = 0;
+        }
+        for (int kc = 0; kc < total_chunks; ++kc) {
+          const int seg = (kc < p.kchunks[0]) ? 0 : 1;
+          const int lk = seg ? kc - p.kchunks[0] : kc;
+          const int tap = lk / p.cpt[seg];
+          const int cc = lk - tap * p.cpt[seg];
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          tma_load_4d(sA + stage * A_STAGE_BYTES, &p.tmA[seg], full_bar(stage), cc * BK, x0 + p.dx[seg][tap],
+                      y0 + p.dy[seg][tap], b0 + p.boff[seg][tap]);
+          tma_load_2d(sB + stage * C::B_STAGE_BYTES, &p.tmB, full_bar(stage), kc * BK, n0);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -149,150 +205,183 @@ __global__ void __launch_bounds__(kThreads) gemm_tc_kernel(const __grid_constant
       const uint32_t idesc = make_idesc_16(BM, BN, p.fp16);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kc = 0; kc < total_chunks; ++kc) {
-        mbar_wait(full_bar(stage), phase);
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint64_t adesc = make_smem_desc_sw128(sA + stage * A_STAGE_BYTES);
-        const uint64_t bdesc = make_smem_desc_sw128(sB + stage * C::B_STAGE_BYTES);
+        const uint32_t tacc = tmem_base + uint32_t(acc * C::ACC_STRIDE);
+        for (int kc = 0; kc < total_chunks; ++kc) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc_sw128(sA + stage * A_STAGE_BYTES);
+          const uint64_t bdesc = make_smem_desc_sw128(sB + stage * C::B_STAGE_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 32 B (16 bf16) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          umma_bf16_ss(tmem_base, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kc | k) != 0);
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 32 B (16 elements) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16_ss(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kc | k) != 0);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-        if (++stage == C::STAGES) {
-          stage = 0;
-          phase ^= 1u;
+        umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
         }
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = m < p.M;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16);
-    const float* rb = nullptr;
-    if (p.rowbias != nullptr && row_ok) rb = p.rowbias + size_t(m / p.rows_per_img) * p.ld_rowbias;
+    // ===================== epilogue (warps 2..9) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int par = (warp - 2) >> 2;        // which half of the 32-column chunks this warp takes
+    const uint32_t stg = sEpi + uint32_t(warp - 2) * STG_WARP_BYTES;
+    // kernel parameters -> registers once (the asm volatile memory clobbers would otherwise force constant re-loads)
     const float alpha = p.alpha;
+    const int fp16 = p.fp16, act = p.act, M = p.M, N = p.N, vec_ok = p.vec_ok, n_tiles = p.n_tiles;
+    const float* const bias = p.bias;
+    const float* const rowbias = p.rowbias;
+    const int rows_per_img = p.rows_per_img, ld_rowbias = p.ld_rowbias;
+    const float* const residual = p.residual;
+    float* const out32 = p.out_f32;
+    uint16_t* const out16 = reinterpret_cast<uint16_t*>(p.out_bf16);
+    const int ldr = p.ldr, ldo32 = p.ldo32, ldo16 = p.ldo16;
+    const int mode = (residual ? 4 : 0) | (out32 ? 2 : 0) | (out16 ? 1 : 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
     uint32_t r[32];
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int tile_n = t % n_tiles;
+      const int m0 = (t / n_tiles) * BM;
+      const int n0 = tile_n * BN;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * C::ACC_STRIDE);
+      const int row0 = m0 + q * 32;  // first row of this warp's 32-row block
 
-    if (p.act == ACT_GEGLU) {
-      // weight rows are tile-interleaved: columns [0,64) of this tile = h, [64,128) = gate, for output cols [64*tile_n, +64)
-      if constexpr (BN == 128) {
-        uint32_t g[32];
-        const int on0 = tile_n * 64;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
+      if constexpr (BN < 32) {
+        // narrow tile (latent head, N = 4 of 16): one row per thread, scalar stores
+        if (par == 0) {
+          const int m = row0 + lane;
+          __syncwarp();
+          tmem_ld16(taddr, r);
+          tmem_ld_wait();
+          if (m < M) {
+            const float* rb = rowbias ? rowbias + size_t(m / rows_per_img) * ld_rowbias : nullptr;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + j;
+              if (n >= N) continue;
+              float v = __uint_as_float(r[j]) * alpha;
+              if (bias) v += __ldg(bias + n);
+              if (rb) v += __ldg(rb + n);
+              if (residual) v += residual[size_t(m) * ldr + n];
+              if (act == ACT_SILU) v = silu_f(v);
+              else if (act == ACT_RELU) v = fmaxf(v, 0.0f);
+              if (out32) out32[size_t(m) * ldo32 + n] = v;
+              if (out16) out16[size_t(m) * ldo16 + n] = cvt_16(v, fp16);
+            }
+          }
+        }
+      } else if (act == ACT_GEGLU) {
+        // weight rows are tile-interleaved: columns [0,64) of this tile = value, [64,128) = gate, for output cols [64*tile_n, +64)
+        if constexpr (BN == 128) {
+          uint32_t g[32];
+          const int on0 = tile_n * 64;
+          const int half = par;
           __syncwarp();
           tmem_ld32(taddr + half * 32, r);
           tmem_ld32(taddr + 64 + half * 32, g);
           tmem_ld_wait();
-          if (row_ok) {
-            __nv_bfloat16* o16 = p.out_bf16 + size_t(m) * p.ldo16 + on0 + half * 32;
+          // value * gelu(gate) in the row-per-thread layout, then transpose through smem for coalesced 16-bit stores
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float v[8];
+          for (int j = 0; j < 32; j += 4) {
+            float v[4];
 #pragma unroll
-              for (int t = 0; t < 8; ++t) {
-                float h = __uint_as_float(r[j + t]) * alpha;
-                float gt = __uint_as_float(g[j + t]) * alpha;
-                if (p.bias) {
-                  h += __ldg(p.bias + n0 + half * 32 + j + t);
-                  gt += __ldg(p.bias + n0 + 64 + half * 32 + j + t);
-                }
-                v[t] = h * gelu_erf_f(gt);
+            for (int e = 0; e < 4; ++e) {
+              float h = __uint_as_float(r[j + e]) * alpha;
+              float gt = __uint_as_float(g[j + e]) * alpha;
+              if (bias) {
+                h += __ldg(bias + n0 + half * 32 + j + e);
+                gt += __ldg(bias + n0 + 64 + half * 32 + j + e);
               }
-              uint4 pk;
-              pk.x = pack2_16(v[0], v[1], p.fp16);
-              pk.y = pack2_16(v[2], v[3], p.fp16);
-              pk.z = pack2_16(v[4], v[5], p.fp16);
-              pk.w = pack2_16(v[6], v[7], p.fp16);
-              *reinterpret_cast<uint4*>(o16 + j) = pk;
+              v[e] = h * gelu_erf_f(gt);
+            }
+            st_shared_f4(stg + uint32_t(lane * STG_LD + j) * 4, v[0], v[1], v[2], v[3]);
+          }
+          __syncwarp();
+          const int cc = (lane & 7) * 4;
+          epi_block<false, false, true>(stg, lane, row0, M, 1.0f, make_float4(0.f, 0.f, 0.f, 0.f), ACT_NONE, fp16, nullptr, 0, nullptr, 0,
+                                        out16 + size_t(row0 + (lane >> 3) * 0) * ldo16 + on0 + half * 32 + cc, ldo16);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = par * 32; c < BN; c += 64) {
+          __syncwarp();  // previous chunk's smem reads are done; warp converged for the aligned tcgen05.ld
+          tmem_ld32(taddr + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            st_shared_f4(stg + uint32_t(lane * STG_LD + j) * 4, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          __syncwarp();
+          const int cc = (lane & 7) * 4;
+          const int n = n0 + c + cc;
+          if (vec_ok && n0 + c + 32 <= N) {
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) bb = __ldg(reinterpret_cast<const float4*>(bias + n));
+            if (rowbias) {  // a 32-row block never straddles images (rows_per_img % 32 == 0, checked on the host)
+              const int img = min(row0, M - 1) / rows_per_img;
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(rowbias + size_t(img) * ld_rowbias + n));
+              bb.x += t4.x; bb.y += t4.y; bb.z += t4.z; bb.w += t4.w;
+            }
+            const float* resp = residual ? residual + size_t(row0) * ldr + n : nullptr;
+            float* o32p = out32 ? out32 + size_t(row0) * ldo32 + n : nullptr;
+            uint16_t* o16p = out16 ? out16 + size_t(row0) * ldo16 + n : nullptr;
+            switch (mode) {
+              case 1: epi_block<false, false, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
+              case 2: epi_block<false, true, false>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
+              case 3: epi_block<false, true, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
+              case 5: epi_block<true, false, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
+              case 6: epi_block<true, true, false>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
+              default: epi_block<true, true, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
+            }
+          } else {
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3);
+              const int m = row0 + rr;
+              const float4 v4 = ld_shared_f4(stg + uint32_t(rr * STG_LD + cc) * 4);
+              const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+              if (m < M) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int ne = n + e;
+                  if (ne >= N) continue;
+                  float v = vv[e] * alpha;
+                  if (bias) v += __ldg(bias + ne);
+                  if (rowbias) v += __ldg(rowbias + size_t(m / rows_per_img) * ld_rowbias + ne);
+                  if (residual) v += residual[size_t(m) * ldr + ne];
+                  if (act == ACT_SILU) v = silu_f(v);
+                  else if (act == ACT_RELU) v = fmaxf(v, 0.0f);
+                  if (out32) out32[size_t(m) * ldo32 + ne] = v;
+                  if (out16) out16[size_t(m) * ldo16 + ne] = cvt_16(v, fp16);
+                }
+              }
             }
           }
         }
       }
-    } else {
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        __syncwarp();
-        if constexpr (BN % 32 != 0) {
-          tmem_ld16(taddr + c, r);
-        } else {
-          tmem_ld32(taddr + c, r);
-        }
-        tmem_ld_wait();
-        constexpr int CW = (BN % 32 != 0) ? 16 : 32;
-        const int nb = n0 + c;
-        if (!row_ok) {
-          // nothing to store for padded rows; fall through to the warp-converged loop head
-        } else if (p.vec_ok && nb + CW <= p.N) {
-#pragma unroll
-          for (int j = 0; j < CW; j += 8) {
-            const int n = nb + j;
-            float v[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[j + t]) * alpha;
-            if (p.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (rb) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + n + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (p.residual) {
-              const float* rp = p.residual + size_t(m) * p.ldr + n;
-              const float4 b0 = *reinterpret_cast<const float4*>(rp);
-              const float4 b1 = *reinterpret_cast<const float4*>(rp + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (p.act == ACT_SILU) {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) v[t] = silu_f(v[t]);
-            } else if (p.act == ACT_RELU) {
-#pragma unroll
-              for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.0f);
-            }
-            if (p.out_f32) {
-              float* op = p.out_f32 + size_t(m) * p.ldo32 + n;
-              *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            if (p.out_bf16) {
-              uint4 pk;
-              pk.x = pack2_16(v[0], v[1], p.fp16);
-              pk.y = pack2_16(v[2], v[3], p.fp16);
-              pk.z = pack2_16(v[4], v[5], p.fp16);
-              pk.w = pack2_16(v[6], v[7], p.fp16);
-              *reinterpret_cast<uint4*>(p.out_bf16 + size_t(m) * p.ldo16 + n) = pk;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const int n = nb + j;
-            if (n >= p.N) continue;
-            float v = __uint_as_float(r[j]) * alpha;
-            if (p.bias) v += __ldg(p.bias + n);
-            if (rb) v += __ldg(rb + n);
-            if (p.residual) v += p.residual[size_t(m) * p.ldr + n];
-            if (p.act == ACT_SILU) v = silu_f(v);
-            else if (p.act == ACT_RELU) v = fmaxf(v, 0.0f);
-            if (p.out_f32) p.out_f32[size_t(m) * p.ldo32 + n] = v;
-            if (p.out_bf16) reinterpret_cast<uint16_t*>(p.out_bf16)[size_t(m) * p.ldo16 + n] = cvt_16(v, p.fp16);
-          }
-        }
+      // release this accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
       }
     }
   }
@@ -340,17 +429,40 @@ static const char* encode_map(CUtensorMap* tm, const void* ptr, int rank, const 
   return nullptr;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// N-tile choice: fewest waves of the persistent grid, preferring wide tiles (a 128xBN UMMA reads (128+BN)*32 B of smem per
+// 128*BN*16 MACs, so BN >= 160 keeps the tensor pipe ahead of the 128 B/clk smem port; BN = 64 cannot).
 static int pick_bn(const GemmDesc& d) {
   if (d.act == ACT_GEGLU) return 128;
   const int N = d.N;
   if (N <= 16) return 16;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  if (N % 128 == 0) return 128;
-  if (N % 160 == 0) return 160;
-  if (N % 192 == 0) return 192;
-  if (N % 64 == 0 && N < 512) return 64;
-  return 128;
+  const int m_tiles = (d.M + BM - 1) / BM;
+  const int cand[5] = {256, 192, 160, 128, 64};
+  const double eff[5] = {1.0, 1.0, 1.0, 1.08, 1.5};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cand[i];
+    if (bn > N && bn != 128 && !(bn == 64)) continue;
+    const long tiles = long(m_tiles) * ((N + bn - 1) / bn);
+    const long waves = (tiles + num_sms() - 1) / num_sms();
+    const double cost = double(waves) * (bn * eff[i] + 24.0);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
 }
 
 const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
@@ -361,6 +473,7 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   if (!d.out_f32 && !d.out_bf16) return "gemm: no output";
   if (d.act == ACT_GEGLU && (!d.out_bf16 || d.out_f32 || d.residual || d.rowbias)) return "gemm: GEGLU epilogue writes bf16 only";
   if (d.act == ACT_GEGLU && d.N % 64 != 0) return "gemm: GEGLU needs N % 64 == 0";
+  if (d.rowbias && d.rows_per_img % 32 != 0) return "gemm: rows_per_img must be a multiple of 32 when a row bias is given";
   L.bn = d.bn ? d.bn : pick_bn(d);
   const GemmASeg& s0 = d.seg[0];
   const int pix = s0.H * s0.W;
@@ -413,7 +526,8 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   const int Ncols = (d.act == ACT_GEGLU) ? 2 * d.N : d.N;
   const int n_tiles = (Ncols + L.bn - 1) / L.bn;
   const int m_tiles = (d.M + BM - 1) / BM;
-  L.grid = dim3(unsigned(n_tiles) * unsigned(m_tiles));
+  L.num_tiles = n_tiles * m_tiles;
+  L.grid = dim3(unsigned(L.num_tiles < num_sms() ? L.num_tiles : num_sms()));
   switch (L.bn) {
     case 16: L.smem = Cfg<16>::SMEM; break;
     case 32: L.smem = Cfg<32>::SMEM; break;
@@ -476,6 +590,7 @@ const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   if (d.act == ACT_GEGLU && !p.vec_ok) return "gemm: GEGLU epilogue needs 16B-aligned outputs";
   p.n_tiles = (p.N + L.bn - 1) / L.bn;
   p.fp16 = d.fp16;
+  p.num_tiles = L.num_tiles;
   switch (L.bn) {
     case 16: return launch_bn<16>(L, p, stream);
     case 32: return launch_bn<32>(L, p, stream);

@@ -53,6 +53,7 @@ struct GemmLaunch {  // prepared launch: tensor maps encoded once, replayed per 
   int cpt[2] = {1, 1};       // chunks per tap
   int box_w = 128, box_h = 1, box_b = 1;
   dim3 grid;
+  int num_tiles = 0;
   size_t smem = 0;
 };
 
