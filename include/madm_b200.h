@@ -168,7 +168,8 @@ typedef struct madm_gemm_args {
 } madm_gemm_args;
 
 int madm_op_gemm(const madm_gemm_args* a, madm_stream stream);
-int madm_op_groupnorm(const float* x0, int32_t C0, const float* x1, int32_t C1, int32_t B, int32_t HW, const float* gamma,
+int madm_op_groupnorm(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW,
+                      int32_t in16 /* inputs are 16-bit (dtype) instead of fp32 */, const float* gamma,
                       const float* beta, float eps, int32_t act, float* stats_scratch /* madm_op_groupnorm_scratch_floats() */,
                       void* y_bf16, void* raw_bf16, int32_t dtype, madm_stream stream);
 int madm_op_groupnorm_scratch_floats(int32_t B, int32_t HW, int32_t C); /* scratch size (floats) for the two GN ops */

@@ -75,7 +75,7 @@ SYMBOLS = {
     "madm_set_profiling": (c_int, [c_void_p, c_int32]),
     "madm_get_profile": (c_int, [c_void_p, C.POINTER(MadmProfile)]),
     "madm_op_gemm": (c_int, [C.POINTER(MadmGemmArgs), c_void_p]),
-    "madm_op_groupnorm": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_float,
+    "madm_op_groupnorm": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_float,
                                   c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "madm_op_groupnorm_scratch_floats": (c_int, [c_int32, c_int32, c_int32]),
     "madm_op_layernorm": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),

@@ -50,11 +50,12 @@ int madm_op_gemm(const madm_gemm_args* a, madm_stream stream) {
   RUN(gemm_launch(L, static_cast<cudaStream_t>(stream)));
 }
 
-int madm_op_groupnorm(const float* x0, int32_t C0, const float* x1, int32_t C1, int32_t B, int32_t HW, const float* gamma,
+int madm_op_groupnorm(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW, int32_t in16, const float* gamma,
                       const float* beta, float eps, int32_t act, float* stats, void* y, void* raw, int32_t dtype, madm_stream stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (const char* e = groupnorm_stats(x0, C0, x1, C1, B, HW, stats, st)) return fail(e);
-  RUN(groupnorm_apply(x0, C0, x1, C1, B, HW, stats, gamma, beta, eps, act, y, raw, dtype == MADM_DTYPE_FP16, st));
+  const int f16 = dtype == MADM_DTYPE_FP16;
+  if (const char* e = groupnorm_stats(x0, C0, x1, C1, B, HW, in16, f16, stats, st)) return fail(e);
+  RUN(groupnorm_apply(x0, C0, x1, C1, B, HW, in16, stats, gamma, beta, eps, act, y, raw, f16, st));
 }
 
 int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y,
@@ -115,10 +116,10 @@ int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, c
   float* ps = stats + per;
   float* st_a = stats + 2 * per;
   float* st_s = st_a + size_t(B) * 64;
-  if (const char* e = groupnorm_stats(a, C, nullptr, 0, B, HW, pa, st)) return fail(e);
+  if (const char* e = groupnorm_stats(a, C, nullptr, 0, B, HW, 0, 0, pa, st)) return fail(e);
   if (const char* e = groupnorm_finalize(pa, B, HW, C, st_a, st)) return fail(e);
   if (has_shortcut_norm) {
-    if (const char* e = groupnorm_stats(s, C, nullptr, 0, B, HW, ps, st)) return fail(e);
+    if (const char* e = groupnorm_stats(s, C, nullptr, 0, B, HW, 0, 0, ps, st)) return fail(e);
     if (const char* e = groupnorm_finalize(ps, B, HW, C, st_s, st)) return fail(e);
   }
   RUN(gn_add_relu_nchw(a, st_a, ga, ba, s, has_shortcut_norm ? st_s : nullptr, gs, bs, eps, B, HW, C, out, st));

@@ -356,19 +356,23 @@ struct Builder {
     return s;
   }
 
-  // GroupNorm(32) over fp32 NHWC (optionally the channel concat of two sources) -> bf16 (+ raw bf16 copy)
-  void groupnorm(const Act& x0, const Act* x1, const std::string& norm, float eps, int actfn, bf16* y, bf16* raw) {
+  // GroupNorm(32) over an NHWC tensor (fp32 stream, or a 16-bit intermediate when in16; optionally the channel concat of
+  // two fp32 sources) -> 16-bit operand tensor (+ raw 16-bit copy of the input)
+  void groupnorm(const Act& x0, const Act* x1, const std::string& norm, float eps, int actfn, bf16* y, bf16* raw, bool in16 = false) {
     const int C0 = x0.C, C1 = x1 ? x1->C : 0;
     const float* g = (mode == LAYOUT) ? nullptr : param(norm + ".weight", C0 + C1);
     const float* b = (mode == LAYOUT) ? nullptr : param(norm + ".bias", C0 + C1);
     float* stats = new_stats(groupnorm_slabs(x0.HW(), C0 + C1));
-    const float* p0 = x0.f.p; const float* p1 = x1 ? x1->f.p : nullptr;
+    const void* p0 = in16 ? static_cast<const void*>(x0.h.p) : static_cast<const void*>(x0.f.p);
+    const void* p1 = x1 ? static_cast<const void*>(x1->f.p) : nullptr;
     const int Bn = x0.B, HW = x0.HW();
     const double elems = double(Bn) * HW * (C0 + C1);
-    emit([=](cudaStream_t st) { return groupnorm_stats(p0, C0, p1, C1, Bn, HW, stats, st); }, false, MADM_KIND_GROUPNORM, 0.0, elems * 4);
-    const int f16 = ctx->fp16;
-    emit([=](cudaStream_t st) { return groupnorm_apply(p0, C0, p1, C1, Bn, HW, stats, g, b, eps, actfn, y, raw, f16, st); }, false,
-         MADM_KIND_GROUPNORM, 0.0, elems * (4 + 2 + (raw ? 2 : 0)));
+    const int f16 = ctx->fp16, i16 = in16 ? 1 : 0;
+    const double in_b = in16 ? 2 : 4;
+    emit([=](cudaStream_t st) { return groupnorm_stats(p0, C0, p1, C1, Bn, HW, i16, f16, stats, st); }, false, MADM_KIND_GROUPNORM, 0.0,
+         elems * in_b);
+    emit([=](cudaStream_t st) { return groupnorm_apply(p0, C0, p1, C1, Bn, HW, i16, stats, g, b, eps, actfn, y, raw, f16, st); }, false,
+         MADM_KIND_GROUPNORM, 0.0, elems * (in_b + 2 + (raw ? 2 : 0)));
   }
 };
 
@@ -419,20 +423,20 @@ struct Model {
     B16T n1 = b.b16(size_t(x0.M()) * Cin);
     B16T raw; if (shortcut) raw = b.b16(size_t(x0.M()) * Cin);
     b.groupnorm(x0, x1, p + ".norm1", eps, ACT_SILU, n1.p, shortcut ? raw.p : nullptr);
-    // conv1 (+ bias + time embedding row bias) -> fp32 intermediate
-    Act h1 = b.act(Bn, H, W, Cout, true, false);
+    // conv1 (+ bias + time embedding row bias) -> 16-bit intermediate (it only feeds norm2)
+    Act h1 = b.act(Bn, H, W, Cout, false, true);
     {
       GemmDesc d; d.seg[0] = Builder::seg_3x3(n1.p, Bn, H, W, Cin); d.M = int(x0.M()); d.N = Cout;
       d.w = b.pw(b.conv_w(p + ".conv1", Cout, Cin, 9)); d.Nw = Cout;
       d.bias = P(p + ".conv1.bias", Cout);
       if (has_temb) { d.rowbias = temb_all.p ? temb_all.p + temb_off[p] : nullptr; d.ld_rowbias = temb_total; d.rows_per_img = H * W;
                       if (dry()) d.rowbias = nullptr; }
-      d.out_f32 = h1.f.p; d.ldo32 = Cout;
+      d.out_bf16 = h1.h.p; d.ldo16 = Cout;
       b.gemm(d);
     }
     b.free(n1);
     B16T n2 = b.b16(size_t(x0.M()) * Cout);
-    b.groupnorm(h1, nullptr, p + ".norm2", eps, ACT_SILU, n2.p, nullptr);
+    b.groupnorm(h1, nullptr, p + ".norm2", eps, ACT_SILU, n2.p, nullptr, /*in16=*/true);
     b.free(h1);
     Act out = b.act(Bn, H, W, Cout, true, want_b16);
     {
@@ -816,19 +820,19 @@ struct Model {
       const int Bn = x.B, H = x.H, W = x.W, Cin = x.C, Cb = 128, Cout = 512;
       const long M = x.M();
       const bool shortcut = Cin != Cout;
-      auto gn = [&](const F32T& src, const std::string& norm, int C, bf16* y) {
-        Act a; a.f = src; a.B = Bn; a.H = H; a.W = W; a.C = C;
-        b.groupnorm(a, nullptr, norm, 1e-5f, ACT_RELU, y, nullptr);
+      auto gn = [&](const B16T& src, const std::string& norm, int C, bf16* y) {
+        Act a; a.h = src; a.B = Bn; a.H = H; a.W = W; a.C = C;
+        b.groupnorm(a, nullptr, norm, 1e-5f, ACT_RELU, y, nullptr, /*in16=*/true);
       };
-      F32T c1 = b.f32(size_t(M) * Cb);
+      B16T c1 = b.b16(size_t(M) * Cb);
       { GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cin); d.M = int(M); d.N = Cb; d.Nw = Cb;
-        d.w = b.pw(b.conv_w(p + "conv1", Cb, Cin, 1)); d.out_f32 = c1.p; d.ldo32 = Cb; b.gemm(d); }
+        d.w = b.pw(b.conv_w(p + "conv1", Cb, Cin, 1)); d.out_bf16 = c1.p; d.ldo16 = Cb; b.gemm(d); }
       B16T a1 = b.b16(size_t(M) * Cb);
       gn(c1, p + "conv1.norm", Cb, a1.p);
       b.free(c1);
-      F32T c2 = b.f32(size_t(M) * Cb);
+      B16T c2 = b.b16(size_t(M) * Cb);
       { GemmDesc d; d.seg[0] = Builder::seg_3x3(a1.p, Bn, H, W, Cb); d.M = int(M); d.N = Cb; d.Nw = Cb;
-        d.w = b.pw(b.conv_w(p + "conv2", Cb, Cb, 9)); d.out_f32 = c2.p; d.ldo32 = Cb; b.gemm(d); }
+        d.w = b.pw(b.conv_w(p + "conv2", Cb, Cb, 9)); d.out_bf16 = c2.p; d.ldo16 = Cb; b.gemm(d); }
       b.free(a1);
       B16T a2 = b.b16(size_t(M) * Cb);
       gn(c2, p + "conv2.norm", Cb, a2.p);
@@ -851,10 +855,10 @@ struct Model {
       float* sts = shortcut ? b.new_stats(1) : nullptr;
       const float* c3p = c3.p; const float* scp = shortcut ? sc.p : x.f.p;
       const double pel = double(Bn) * HW * Cout;
-      b.emit([=](cudaStream_t st) { return groupnorm_stats(c3p, Cout, nullptr, 0, Bn, HW, pt3, st); }, false, MADM_KIND_GROUPNORM, 0.0, pel * 4);
+      b.emit([=](cudaStream_t st) { return groupnorm_stats(c3p, Cout, nullptr, 0, Bn, HW, 0, 0, pt3, st); }, false, MADM_KIND_GROUPNORM, 0.0, pel * 4);
       b.emit([=](cudaStream_t st) { return groupnorm_finalize(pt3, Bn, HW, Cout, st3, st); }, false, MADM_KIND_GROUPNORM, 0.0, 0.0);
       if (shortcut) {
-        b.emit([=](cudaStream_t st) { return groupnorm_stats(scp, Cout, nullptr, 0, Bn, HW, pts, st); }, false, MADM_KIND_GROUPNORM, 0.0, pel * 4);
+        b.emit([=](cudaStream_t st) { return groupnorm_stats(scp, Cout, nullptr, 0, Bn, HW, 0, 0, pts, st); }, false, MADM_KIND_GROUPNORM, 0.0, pel * 4);
         b.emit([=](cudaStream_t st) { return groupnorm_finalize(pts, Bn, HW, Cout, sts, st); }, false, MADM_KIND_GROUPNORM, 0.0, 0.0);
       }
       const float* g3 = P(p + "conv3.norm.weight", Cout); const float* b3 = P(p + "conv3.norm.bias", Cout);

@@ -14,9 +14,11 @@ namespace madm {
 // GroupNorm(32) statistics are per-slab partial sums [B, slabs, 32, 2] (no atomics: deterministic, batch-size invariant);
 // groupnorm_apply reduces them in fixed order, groupnorm_finalize produces [B,32,2] for gn_add_relu_nchw.
 int groupnorm_slabs(int HW, int C);
-const char* groupnorm_stats(const float* x0, int C0, const float* x1, int C1, int B, int HW, float* partial, cudaStream_t st);
+// x0 / x1: fp32 NHWC, or 16-bit (dtype per `fp16`) when in16 != 0
+const char* groupnorm_stats(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, int fp16, float* partial,
+                            cudaStream_t st);
 const char* groupnorm_finalize(const float* partial, int B, int HW, int C, float* stats, cudaStream_t st);
-const char* groupnorm_apply(const float* x0, int C0, const float* x1, int C1, int B, int HW, const float* partial,
+const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, const float* partial,
                             const float* gamma, const float* beta, float eps, int act, void* y_bf16, void* raw_bf16,
                             int fp16, cudaStream_t st);
 const char* layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y_bf16,

@@ -15,10 +15,32 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 
 
 // ---------------------------------------------------------------------------------------------- GroupNorm statistics
+// 4 consecutive channels of one pixel from an fp32 or 16-bit (fp16 / bf16) NHWC tensor
+template <bool IN16>
+__device__ __forceinline__ float4 ld4(const void* base, size_t elem_off, int fp16) {
+  if constexpr (!IN16) {
+    return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
+  } else {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + elem_off));
+    float4 v;
+    if (fp16) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      v = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      v = make_float4(a.x, a.y, b.x, b.y);
+    }
+    return v;
+  }
+}
+
 // grid = (slabs, B); block = Q*P threads, Q = C/4 channel quads, P pixel lanes.  Thread (q, pl) owns channels 4q..4q+3
-// and walks pixels pl, pl+P, ... of its slab, so its per-channel partial sums stay in registers.
-__global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int HW,
-                                int pix_per_cta, int P, float* __restrict__ partial /*[B,slabs,32,2]*/) {
+// and walks pixels pl, pl+P, ... of its slab (4 loads in flight), so its per-channel partial sums stay in registers.
+template <bool IN16>
+__global__ void gn_stats_kernel(const void* __restrict__ x0, int C0, const void* __restrict__ x1, int C1, int HW,
+                                int pix_per_cta, int P, int fp16, float* __restrict__ partial /*[B,slabs,32,2]*/) {
   extern __shared__ float sm[];  // [2][P][C]
   const int C = C0 + C1;
   const int Q = C >> 2;
@@ -28,13 +50,27 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(HW, p_begin + pix_per_cta);
   const int c = q * 4;
-  const float* src;
+  const void* src;
   int ld, cc;
-  if (c < C0) { src = x0 + size_t(b) * HW * C0; ld = C0; cc = c; }
-  else        { src = x1 + size_t(b) * HW * C1; ld = C1; cc = c - C0; }
+  if (c < C0) { src = x0; ld = C0; cc = c; }
+  else        { src = x1; ld = C1; cc = c - C0; }
+  const size_t img_off = size_t(b) * HW * ld + cc;
   float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-  for (int p = p_begin + pl; p < p_end; p += P) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src + size_t(p) * ld + cc));
+  int p = p_begin + pl;
+  for (; p + 3 * P < p_end; p += 4 * P) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld4<IN16>(src, img_off + size_t(p + u * P) * ld, fp16);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[0] += v[u].x; ss[0] += v[u].x * v[u].x;
+      s[1] += v[u].y; ss[1] += v[u].y * v[u].y;
+      s[2] += v[u].z; ss[2] += v[u].z * v[u].z;
+      s[3] += v[u].w; ss[3] += v[u].w * v[u].w;
+    }
+  }
+  for (; p < p_end; p += P) {
+    const float4 v = ld4<IN16>(src, img_off + size_t(p) * ld, fp16);
     s[0] += v.x; ss[0] += v.x * v.x;
     s[1] += v.y; ss[1] += v.y * v.y;
     s[2] += v.z; ss[2] += v.z * v.z;
@@ -48,7 +84,6 @@ __global__ void gn_stats_kernel(const float* __restrict__ x0, int C0, const floa
     sm_ss[pl * C + c + t] = ss[t];
   }
   __syncthreads();
-  // 32 groups: warp w of the first 32 warps... keep it simple: threads 0..63 each reduce one (group, moment)
   const int cpg = C / 32;
   if (threadIdx.x < 64) {
     const int g = threadIdx.x & 31;
@@ -80,48 +115,62 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int slabs,
 }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm apply
-// grid = (slabs, B); block 256.  Per-channel scale/shift for this image are built once in shared memory, then the slab
-// is streamed: y = act(x*scale + shift) -> bf16 (and optionally the un-normalised x -> bf16 for a 1x1 shortcut conv).
-__global__ void gn_apply_kernel(const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, int HW,
-                                int pix_per_cta, const float* __restrict__ partial, int slabs, const float* __restrict__ gamma,
+// Same (slab, image) x (channel quad, pixel lane) decomposition as the statistics kernel: each thread keeps the scale /
+// shift of its 4 channels in registers and streams its pixels with 4 loads in flight:
+// y = act(x*scale + shift) -> 16-bit (and optionally the un-normalised x -> 16-bit for a 1x1 shortcut conv).
+template <bool IN16>
+__global__ void gn_apply_kernel(const void* __restrict__ x0, int C0, const void* __restrict__ x1, int C1, int HW,
+                                int pix_per_cta, int P, const float* __restrict__ partial, int slabs, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int act, int fp16, uint16_t* __restrict__ y,
                                 uint16_t* __restrict__ raw) {
-  extern __shared__ float sm[];  // scale[C], shift[C], red[64]
+  __shared__ float red[64];
   const int C = C0 + C1;
+  const int Q = C >> 2;
+  const int q = threadIdx.x % Q;
+  const int pl = threadIdx.x / Q;
   const int b = blockIdx.y;
   const int cpg = C / 32;
-  const float inv_n = 1.0f / (float(HW) * float(cpg));
-  float* red = sm + 2 * C;
   gn_reduce_partials(partial, b, slabs, red);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float su = red[g * 2 + 0];
-    const float sq = red[g * 2 + 1];
-    const float mean = su * inv_n;
-    const float var = fmaxf(sq * inv_n - mean * mean, 0.0f);
+  const int c = q * 4;
+  const float inv_n = 1.0f / (float(HW) * float(cpg));
+  float sc[4], sh[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int g = (c + t) / cpg;
+    const float mean = red[g * 2] * inv_n;
+    const float var = fmaxf(red[g * 2 + 1] * inv_n - mean * mean, 0.0f);
     const float rstd = rsqrtf(var + eps);
-    const float ga = gamma ? gamma[c] : 1.0f;
-    const float be = beta ? beta[c] : 0.0f;
-    sm[c] = rstd * ga;
-    sm[C + c] = be - mean * rstd * ga;
+    const float ga = gamma ? gamma[c + t] : 1.0f;
+    const float be = beta ? beta[c + t] : 0.0f;
+    sc[t] = rstd * ga;
+    sh[t] = be - mean * rstd * ga;
   }
-  __syncthreads();
-  const int Q = C >> 2;
+  const void* src;
+  int ld, cc;
+  if (c < C0) { src = x0; ld = C0; cc = c; }
+  else        { src = x1; ld = C1; cc = c - C0; }
+  const size_t img_off = size_t(b) * HW * ld + cc;
+  const size_t out_off = size_t(b) * HW * C + c;
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(HW, p_begin + pix_per_cta);
-  const long total = long(p_end - p_begin) * Q;
-  const float* s0 = x0 + size_t(b) * HW * C0;
-  const float* s1 = x1 ? x1 + size_t(b) * HW * C1 : nullptr;
-  for (long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = p_begin + int(i / Q);
-    const int c = int(i % Q) * 4;
-    const float4 v = (c < C0) ? __ldg(reinterpret_cast<const float4*>(s0 + size_t(p) * C0 + c))
-                              : __ldg(reinterpret_cast<const float4*>(s1 + size_t(p) * C1 + (c - C0)));
-    const float4 sc = *reinterpret_cast<const float4*>(sm + c);
-    const float4 sh = *reinterpret_cast<const float4*>(sm + C + c);
-    const size_t o = (size_t(b) * HW + p) * C + c;
-    *reinterpret_cast<uint2*>(y + o) = pack4_16(act_apply(v.x * sc.x + sh.x, act), act_apply(v.y * sc.y + sh.y, act),
-                                                act_apply(v.z * sc.z + sh.z, act), act_apply(v.w * sc.w + sh.w, act), fp16);
+  int p = p_begin + pl;
+  for (; p + 3 * P < p_end; p += 4 * P) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld4<IN16>(src, img_off + size_t(p + u * P) * ld, fp16);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t o = out_off + size_t(p + u * P) * C;
+      *reinterpret_cast<uint2*>(y + o) = pack4_16(act_apply(v[u].x * sc[0] + sh[0], act), act_apply(v[u].y * sc[1] + sh[1], act),
+                                                  act_apply(v[u].z * sc[2] + sh[2], act), act_apply(v[u].w * sc[3] + sh[3], act), fp16);
+      if (raw) *reinterpret_cast<uint2*>(raw + o) = pack4_16(v[u].x, v[u].y, v[u].z, v[u].w, fp16);
+    }
+  }
+  for (; p < p_end; p += P) {
+    const float4 v = ld4<IN16>(src, img_off + size_t(p) * ld, fp16);
+    const size_t o = out_off + size_t(p) * C;
+    *reinterpret_cast<uint2*>(y + o) = pack4_16(act_apply(v.x * sc[0] + sh[0], act), act_apply(v.y * sc[1] + sh[1], act),
+                                                act_apply(v.z * sc[2] + sh[2], act), act_apply(v.w * sc[3] + sh[3], act), fp16);
     if (raw) *reinterpret_cast<uint2*>(raw + o) = pack4_16(v.x, v.y, v.z, v.w, fp16);
   }
 }
@@ -149,15 +198,17 @@ int groupnorm_slabs(int HW, int C) {
   return slabs;
 }
 
-const char* groupnorm_stats(const float* x0, int C0, const float* x1, int C1, int B, int HW, float* partial, cudaStream_t st) {
+const char* groupnorm_stats(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, int fp16, float* partial,
+                            cudaStream_t st) {
   const int C = C0 + C1;
-  if (C % 128 != 0 && (C % 32 != 0 || C % 4 != 0)) return "groupnorm: C must be a multiple of 32";
+  if (C % 32 != 0 || C % 4 != 0) return "groupnorm: C must be a multiple of 32";
   if (C0 % 4 != 0 || C1 % 4 != 0) return "groupnorm: source channel counts must be multiples of 4";
   if (C / 4 > 1024) return "groupnorm: C too large";
   int P, threads, ppc, slabs;
   gn_geometry(HW, C, &P, &threads, &ppc, &slabs);
   const size_t smem = size_t(2) * P * C * sizeof(float);
-  gn_stats_kernel<<<dim3(slabs, B), threads, smem, st>>>(x0, C0, x1, C1, HW, ppc, P, partial);
+  if (in16) gn_stats_kernel<true><<<dim3(slabs, B), threads, smem, st>>>(x0, C0, x1, C1, HW, ppc, P, fp16, partial);
+  else gn_stats_kernel<false><<<dim3(slabs, B), threads, smem, st>>>(x0, C0, x1, C1, HW, ppc, P, fp16, partial);
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_stats launch failed";
 }
 
@@ -166,14 +217,17 @@ const char* groupnorm_finalize(const float* partial, int B, int HW, int C, float
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_finalize launch failed";
 }
 
-const char* groupnorm_apply(const float* x0, int C0, const float* x1, int C1, int B, int HW, const float* partial,
+const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, const float* partial,
                             const float* gamma, const float* beta, float eps, int act, void* y, void* raw, int fp16, cudaStream_t st) {
   const int C = C0 + C1;
   int P, threads, ppc, slabs;
   gn_geometry(HW, C, &P, &threads, &ppc, &slabs);
-  const size_t smem = size_t(2 * C + 64) * sizeof(float);
-  gn_apply_kernel<<<dim3(slabs, B), 256, smem, st>>>(x0, C0, x1, C1, HW, ppc, partial, slabs, gamma, beta, eps, act, fp16,
-                                                     reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
+  if (in16)
+    gn_apply_kernel<true><<<dim3(slabs, B), threads, 0, st>>>(x0, C0, x1, C1, HW, ppc, P, partial, slabs, gamma, beta, eps, act, fp16,
+                                                              reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
+  else
+    gn_apply_kernel<false><<<dim3(slabs, B), threads, 0, st>>>(x0, C0, x1, C1, HW, ppc, P, partial, slabs, gamma, beta, eps, act, fp16,
+                                                               reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_apply launch failed";
 }
 

@@ -88,7 +88,8 @@ def groupnorm(x0, x1, B, HW, gamma, beta, eps, act, y, raw=None):
     C0 = x0.shape[-1]
     C1 = x1.shape[-1] if x1 is not None else 0
     stats = torch.empty(lib.madm_op_groupnorm_scratch_floats(B, HW, C0 + C1), dtype=torch.float32, device=x0.device)
-    _lib.check(lib.madm_op_groupnorm(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(gamma), _ptr(beta), eps, act, _ptr(stats),
+    in16 = 0 if x0.dtype == torch.float32 else 1
+    _lib.check(lib.madm_op_groupnorm(_ptr(x0), C0, _ptr(x1), C1, B, HW, in16, _ptr(gamma), _ptr(beta), eps, act, _ptr(stats),
                                      _ptr(y), _ptr(raw), _dt(y.dtype), _stream()), None, "madm_op_groupnorm")
     return stats
 

@@ -221,6 +221,19 @@ def test_groupnorm(ops, cuda_device, B, HW, C0, C1, act):
     assert torch.equal(raw, bf(x))
 
 
+@pytest.mark.parametrize("B,HW,Cc", [(2, 4096, 320), (1, 16384, 128), (3, 64, 1280)])
+def test_groupnorm_16bit_input(ops, cuda_device, B, HW, Cc):
+    """GroupNorm over a 16-bit intermediate (conv1 output feeding norm2)."""
+    g = torch.Generator(device="cuda").manual_seed(Cc + HW)
+    x = bf(torch.randn(B, HW, Cc, device=cuda_device, generator=g) * 1.5 + 0.25)
+    gamma = torch.randn(Cc, device=cuda_device, generator=g)
+    beta = torch.randn(Cc, device=cuda_device, generator=g)
+    y = torch.empty(B, HW, Cc, dtype=DT, device=cuda_device)
+    ops.groupnorm(x, None, B, HW, gamma, beta, 1e-6, 1, y)
+    ref = F.silu(F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-6).permute(0, 2, 1))
+    assert relerr(y, ref) < 1e-2
+
+
 @pytest.mark.parametrize("M,Cc", [(4096, 320), (1000, 640), (77, 1280)])
 def test_layernorm(ops, cuda_device, M, Cc):
     g = torch.Generator(device="cuda").manual_seed(Cc)
