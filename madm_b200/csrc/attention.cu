@@ -40,6 +40,11 @@ __device__ __forceinline__ void mma_16(float (&c)[4], uint32_t a0, uint32_t a1, 
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
   }
 }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <bool FP16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return pack2_16(a, b, FP16 ? 1 : 0);
@@ -141,36 +146,38 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const uint16_t* __restr
         mma_16<FP16>(s[2 * np + 1], qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3], b2, b3);
       }
     }
-    // ---- online softmax (rows lane/4 and lane/4+8)
-    const int key_base = kt * 64 + 2 * (lane & 3);
+    // ---- online softmax (rows lane/4 and lane/4+8): max on the raw scores, then p = 2^(s*c - m*c) as one FFMA + MUFU
+    if (kt == ntiles - 1 && (Nk & 63) != 0) {  // only the last, ragged key tile needs masking
+      const int key_base = kt * 64 + 2 * (lane & 3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (key_base + i * 8 + (e & 1) >= Nk) s[i][e] = -INFINITY;
+    }
     float mx[2] = {m_run[0], m_run[1]};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = key_base + i * 8 + (e & 1);
-        float v = s[i][e] * scale_log2;
-        if (key >= Nk) v = -INFINITY;
-        s[i][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
-      }
+      mx[0] = fmaxf(mx[0], fmaxf(s[i][0], s[i][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[i][2], s[i][3]));
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
     }
-    float corr[2], rs[2] = {0.f, 0.f};
+    float corr[2], rs[2] = {0.f, 0.f}, ms[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      corr[r] = exp2f(m_run[r] - mx[r]);
+      corr[r] = ex2((m_run[r] - mx[r]) * scale_log2);
       m_run[r] = mx[r];
+      ms[r] = -mx[r] * scale_log2;
     }
     uint32_t pf[8][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float p0 = exp2f(s[i][0] - mx[0]), p1 = exp2f(s[i][1] - mx[0]);
-      const float p2 = exp2f(s[i][2] - mx[1]), p3 = exp2f(s[i][3] - mx[1]);
+      const float p0 = ex2(fmaf(s[i][0], scale_log2, ms[0])), p1 = ex2(fmaf(s[i][1], scale_log2, ms[0]));
+      const float p2 = ex2(fmaf(s[i][2], scale_log2, ms[1])), p3 = ex2(fmaf(s[i][3], scale_log2, ms[1]));
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
       pf[i][0] = pack2<FP16>(p0, p1);
