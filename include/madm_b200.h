@@ -178,7 +178,8 @@ int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, 
 int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p_bf16, int32_t dtype, madm_stream stream);
 int madm_op_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o, int32_t ldo,
                       int32_t B, int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bstride, int64_t kv_bstride,
-                      int64_t o_bstride, float scale, int32_t dtype, madm_stream stream);
+                      int64_t o_bstride, float scale, int32_t dtype, int32_t impl /* 0 = tcgen05/TMEM kernel, 1 = mma.sync kernel */,
+                      madm_stream stream);
 int madm_op_pack_linear(const float* w, int32_t N, int32_t K, const float* lora_a, const float* lora_b, int32_t r, float scale,
                         void* out_bf16, int32_t ldo, int32_t dtype, madm_stream stream);
 int madm_op_pack_conv(const float* w, int32_t N, int32_t C, int32_t taps, int32_t Cpad, void* out_bf16, int32_t ldo,

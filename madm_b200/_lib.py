@@ -81,7 +81,7 @@ SYMBOLS = {
     "madm_op_layernorm": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
     "madm_op_softmax_rows": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_attention": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,
-                                  c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, c_float, c_int32, c_void_p]),
+                                  c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, c_float, c_int32, c_int32, c_void_p]),
     "madm_op_pack_linear": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_int32,
                                     c_int32, c_void_p]),
     "madm_op_pack_conv": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),

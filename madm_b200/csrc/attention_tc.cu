@@ -1,0 +1,462 @@
+// tcgen05 / TMEM flash attention for the SD-1.4 UNet (self: n in {4096,1024,256,64}; cross: 77 keys; 8 heads, d in {40,80,160}).
+//
+// One CTA = 128 query rows of one (image, head).  Per 128-key tile:
+//   S = Q K^T          tcgen05.mma 128x128xd   (Q, K tiles K-major in 128B-swizzled smem, loaded by 4-D TMA boxes over the
+//                                               [d, heads, tokens, batch] view; head-dim columns past d are zero-filled by TMA)
+//   softmax            4 warps, thread = query row: tcgen05.ld the fp32 scores, online max / sum in registers (no shuffles),
+//                      p = 2^(s*c - m*c) as one FFMA + MUFU, written as 16-bit P into swizzled smem (A operand of the next MMA)
+//   O_tile = P V       tcgen05.mma 128xdx128   (V tile used as an MN-major B operand: no transpose pass)
+//   O = O*corr + O_tile in registers (fp32), deferred by one tile so the P V latency is hidden behind the next tile's softmax.
+// Warp roles: warp 0 TMA producer (double-buffered K/V), warp 1 TMEM allocator + single-thread MMA issuer (two S buffers in
+// TMEM so Q K^T of tile j+1 overlaps the softmax of tile j), warps 2..5 softmax / output.
+#include "cvt.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+#include <mutex>
+#include <stdio.h>
+
+namespace madm {
+
+static constexpr int FA_BM = 128;     // queries per CTA
+static constexpr int FA_BN = 128;     // keys per tile
+static constexpr int FA_TILE = 128 * 128;  // bytes of one [128 rows][64 x 16-bit] swizzled sub-tile
+
+template <int D, int NQT>
+struct FaCfg {
+  static constexpr int KC = (D + 63) / 64;          // 64-wide head-dim chunks
+  static constexpr int DV = (D + 15) / 16 * 16;     // P V output columns (UMMA N)
+  static constexpr int KSTEPS = (D + 15) / 16;      // 16-wide k-steps of Q K^T that carry data
+  // d <= 80: the softmax thread pulls its whole 128-score row into registers with one TMEM round trip and releases the S
+  // buffer immediately, so one S buffer per query tile suffices.  d = 160 keeps its registers for the O accumulator and
+  // re-reads S in two passes from two S buffers.
+  static constexpr bool REG_S = D <= 80;
+  static constexpr int NSB = REG_S ? 1 : 2;         // S buffers per query tile
+  static constexpr int Q_BYTES = NQT * KC * FA_TILE;
+  static constexpr int KV_BYTES = KC * FA_TILE;     // per stage, per operand
+  static constexpr int P_BYTES = NQT * 2 * FA_TILE;
+  static constexpr int STAGES = (Q_BYTES + P_BYTES + 4 * KV_BYTES + 2048 <= 227 * 1024) ? 2 : 1;  // K/V ring depth
+  static constexpr size_t SMEM = Q_BYTES + 2 * STAGES * KV_BYTES + P_BYTES + 1024 + 512;
+  static constexpr int S_COLS = NQT * NSB * 128;    // S buffers first, then one O tile per query tile
+  static constexpr int O_STRIDE = (DV + 31) / 32 * 32;
+  static constexpr int TMEM_NEED = S_COLS + NQT * O_STRIDE;
+  static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
+  static constexpr int THREADS = 64 + NQT * 128;
+  static_assert(TMEM_NEED <= 512, "TMEM budget");
+  static_assert(SMEM <= 227 * 1024, "smem budget");
+};
+
+struct FaParams {
+  CUtensorMap tmQ, tmK, tmV;
+  uint16_t* O;
+  int ldo;
+  long o_bs;
+  int Nq, Nk;
+  float scale_log2;
+  int fp16;
+};
+
+__device__ __forceinline__ float fa_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// smem descriptor of an MN-major (N contiguous) 128B-swizzled B operand: 8-row (K) atoms of 1024 B (SBO), 64-element N groups
+// `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// NQT query tiles (128 rows each) per CTA share every K/V tile; each query tile has its own softmax warpgroup, S / O tiles in
+// TMEM and P buffer, so the softmax of one tile overlaps the MMAs (and the softmax) of the other.
+template <int D, int NQT>
+__global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const __grid_constant__ FaParams p) {
+  using C = FaCfg<D, NQT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + C::Q_BYTES;
+  const uint32_t sV = sK + C::STAGES * C::KV_BYTES;
+  const uint32_t sP = sV + C::STAGES * C::KV_BYTES;
+  const uint32_t sBar = sP + C::P_BYTES;
+  // barriers: q_full | k_full[2] k_empty[2] v_full[2] v_empty[2] | per group g: s_full[2] s_empty[2] p_full p_empty o_full o_empty
+  const uint32_t q_full = sBar;
+  auto k_full = [&](int s) { return sBar + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return sBar + 8u * (3 + s); };
+  auto v_full = [&](int s) { return sBar + 8u * (5 + s); };
+  auto v_empty = [&](int s) { return sBar + 8u * (7 + s); };
+  auto gbar = [&](int g, int i) { return sBar + 8u * (9 + g * 8 + i); };
+  auto s_full = [&](int g, int a) { return gbar(g, a); };
+  auto s_empty = [&](int g, int a) { return gbar(g, 2 + a); };
+  auto p_full = [&](int g) { return gbar(g, 4); };
+  auto p_empty = [&](int g) { return gbar(g, 5); };
+  auto o_full = [&](int g) { return gbar(g, 6); };
+  auto o_empty = [&](int g) { return gbar(g, 7); };
+  const uint32_t tmem_slot = sBar + 8u * (9 + 16);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (FA_BM * NQT), h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (p.Nk + FA_BN - 1) / FA_BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+    }
+    for (int g = 0; g < NQT; ++g) {
+      for (int a = 0; a < 2; ++a) { mbar_init(s_full(g, a), 1); mbar_init(s_empty(g, a), 4); }
+      mbar_init(p_full(g), 4); mbar_init(p_empty(g), 1); mbar_init(o_full(g), 1); mbar_init(o_empty(g), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, C::Q_BYTES);
+#pragma unroll
+      for (int g = 0; g < NQT; ++g)
+#pragma unroll
+        for (int kc = 0; kc < C::KC; ++kc)
+          tma_load_4d(sQ + (g * C::KC + kc) * FA_TILE, &p.tmQ, q_full, kc * 64, h, q0 + g * FA_BM, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        mbar_wait(k_empty(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(k_full(stage), C::KV_BYTES);
+#pragma unroll
+        for (int kc = 0; kc < C::KC; ++kc) tma_load_4d(sK + stage * C::KV_BYTES + kc * FA_TILE, &p.tmK, k_full(stage), kc * 64, h, j * FA_BN, b);
+        mbar_wait(v_empty(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(v_full(stage), C::KV_BYTES);
+#pragma unroll
+        for (int kc = 0; kc < C::KC; ++kc) tma_load_4d(sV + stage * C::KV_BYTES + kc * FA_TILE, &p.tmV, v_full(stage), kc * 64, h, j * FA_BN, b);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_16(FA_BM, FA_BN, p.fp16);
+      const uint32_t idesc_o = make_idesc_16(FA_BM, C::DV, p.fp16) | (1u << 16);  // B (= V) is MN-major
+      auto issue_s = [&](int j) {  // S_g = Q_g K(j)^T for every query tile; K(j) is released after the last one
+        const int stage = j % C::STAGES;
+        const int sb = j % C::NSB;
+        mbar_wait(k_full(stage), (j / C::STAGES) & 1);
+#pragma unroll
+        for (int g = 0; g < NQT; ++g) {
+          mbar_wait(s_empty(g, sb), ((j / C::NSB) & 1) ^ 1u);
+          tc_fence_after();
+          const uint32_t ts = tmem + uint32_t((g * C::NSB + sb) * 128);
+#pragma unroll
+          for (int ks = 0; ks < C::KSTEPS; ++ks) {
+            const int kc = ks >> 2, k = ks & 3;
+            const uint64_t ad = make_smem_desc_sw128(sQ + (g * C::KC + kc) * FA_TILE) + uint64_t(2 * k);
+            const uint64_t bd = make_smem_desc_sw128(sK + stage * C::KV_BYTES + kc * FA_TILE) + uint64_t(2 * k);
+            umma_bf16_ss(ts, ad, bd, idesc_s, ks != 0);
+          }
+          umma_commit(s_full(g, sb));
+        }
+        umma_commit(k_empty(stage));
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_s(j + 1);
+        // O_g tile = P_g(j) V(j)
+        const int stage = j % C::STAGES;
+        mbar_wait(v_full(stage), (j / C::STAGES) & 1);
+        int keys = p.Nk - j * FA_BN;
+        if (keys > FA_BN) keys = FA_BN;
+        const int ksteps = (keys + 15) >> 4;
+#pragma unroll
+        for (int g = 0; g < NQT; ++g) {
+          mbar_wait(p_full(g), j & 1);
+          mbar_wait(o_empty(g), (j & 1) ^ 1u);
+          tc_fence_after();
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t ad = make_smem_desc_sw128(sP + (g * 2 + (kk >> 2)) * FA_TILE) + uint64_t(2 * (kk & 3));
+            const uint64_t bd = make_smem_desc_sw128_mn(sV + stage * C::KV_BYTES + kk * 2048, FA_TILE);
+            umma_bf16_ss(tmem + C::S_COLS + g * C::O_STRIDE, ad, bd, idesc_o, kk != 0);
+          }
+          umma_commit(p_empty(g));
+          umma_commit(o_full(g));
+        }
+        umma_commit(v_empty(stage));
+      }
+    }
+  } else {
+    // ===================== softmax / output (one warpgroup per query tile, thread = query row) =====================
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = uint32_t(q * 32) << 16;
+    const uint32_t sPg = sP + uint32_t(g * 2) * FA_TILE;
+    const uint32_t tmem_o = tmem + lane_base + C::S_COLS + g * C::O_STRIDE;
+    const float sl = p.scale_log2;
+    const int fp16 = p.fp16;
+    float o_acc[C::DV];
+#pragma unroll
+    for (int i = 0; i < C::DV; ++i) o_acc[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+    uint32_t r[32];
+
+    auto o_update = [&](int j, float corr) {  // O = O*corr + (P V)(j)
+      mbar_wait(o_full(g), j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < C::DV; c += 16) {
+        __syncwarp();
+        tmem_ld16(tmem_o + c, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o_acc[c + i] = fmaf(o_acc[c + i], corr, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty(g));
+    };
+
+    for (int j = 0; j < ntiles; ++j) {
+      const int sb = j % C::NSB;
+      mbar_wait(s_full(g, sb), (j / C::NSB) & 1);
+      tc_fence_after();
+      const uint32_t ts = tmem + lane_base + uint32_t((g * C::NSB + sb) * 128);
+      const int kvalid = p.Nk - j * FA_BN;  // keys >= kvalid are masked (only the last tile can be ragged)
+      const bool ragged = kvalid < FA_BN;
+      float corr, rs = 0.f;
+      if constexpr (C::REG_S) {
+        // whole score row -> registers (4 loads in flight, one wait), then hand the S buffer back to the MMA warp
+        uint32_t sc[4][32];
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(ts + c * 32, sc[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(g, sb));
+        if (ragged) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= kvalid) sc[c][i] = 0xff800000u;  // -inf
+        }
+        float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(sc[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sc[1][i]));
+          mx2 = fmaxf(mx2, __uint_as_float(sc[2][i]));
+          mx3 = fmaxf(mx3, __uint_as_float(sc[3][i]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        corr = fa_ex2((m_run - mx) * sl);
+        m_run = mx;
+        const float ms = -mx * sl;
+        mbar_wait(p_empty(g), (j & 1) ^ 1u);  // P buffer consumed by the previous P V
+        float rs1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fa_ex2(fmaf(__uint_as_float(sc[c][i]), sl, ms));
+            const float p1 = fa_ex2(fmaf(__uint_as_float(sc[c][i + 1]), sl, ms));
+            rs += p0;
+            rs1 += p1;
+            pk[i >> 1] = pack2_16(p0, p1, fp16);
+          }
+          const uint32_t chunk_base = sPg + uint32_t(c >> 1) * FA_TILE + uint32_t(row) * 128;
+          const int u0 = (c & 1) * 4;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t addr = chunk_base + uint32_t(((u0 + u) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]),
+                         "r"(pk[4 * u + 3]) : "memory");
+          }
+        }
+        rs += rs1;
+      } else {
+        // pass 1: row max
+        float mx = m_run;
+#pragma unroll 1
+        for (int c = 0; c < FA_BN; c += 32) {
+          __syncwarp();
+          tmem_ld32(ts + c, r);
+          tmem_ld_wait();
+          if (c + 32 <= kvalid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c + i < kvalid) mx = fmaxf(mx, __uint_as_float(r[i]));
+          }
+        }
+        corr = fa_ex2((m_run - mx) * sl);
+        m_run = mx;
+        const float ms = -mx * sl;
+        mbar_wait(p_empty(g), (j & 1) ^ 1u);  // P buffer consumed by the previous P V
+        // pass 2: p = 2^(s*sl - m*sl), row sum, 16-bit P into swizzled smem
+#pragma unroll 1
+        for (int c = 0; c < FA_BN; c += 32) {
+          __syncwarp();
+          tmem_ld32(ts + c, r);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = fa_ex2(fmaf(__uint_as_float(r[i]), sl, ms));
+            float p1 = fa_ex2(fmaf(__uint_as_float(r[i + 1]), sl, ms));
+            if (c + i >= kvalid) p0 = 0.f;
+            if (c + i + 1 >= kvalid) p1 = 0.f;
+            rs += p0 + p1;
+            pk[i >> 1] = pack2_16(p0, p1, fp16);
+          }
+          // 32 keys = 4 x 16-byte units of this row; unit index XOR (row & 7) inside the 128-byte swizzle row
+          const uint32_t chunk_base = sPg + uint32_t(c >> 6) * FA_TILE + uint32_t(row) * 128;
+          const int u0 = (c & 63) >> 3;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t addr = chunk_base + uint32_t(((u0 + u) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]),
+                         "r"(pk[4 * u + 3]) : "memory");
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(g, sb));
+      }
+      l_run = l_run * corr + rs;
+      // P ready (generic -> async proxy fence before the MMA reads it)
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(g));
+      // deferred accumulation of the previous tile's P V (its MMA ran while this tile's softmax was computed)
+      if (j > 0) o_update(j - 1, corr_prev);
+      corr_prev = corr;
+    }
+    o_update(ntiles - 1, corr_prev);
+    // normalise and store this row
+    const int m = q0 + g * FA_BM + row;
+    if (m < p.Nq) {
+      const float inv = 1.0f / l_run;
+      uint16_t* op = p.O + size_t(b) * p.o_bs + size_t(m) * p.ldo + h * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 8) {
+        uint4 v;
+        v.x = pack2_16(o_acc[c] * inv, o_acc[c + 1] * inv, fp16);
+        v.y = pack2_16(o_acc[c + 2] * inv, o_acc[c + 3] * inv, fp16);
+        v.z = pack2_16(o_acc[c + 4] * inv, o_acc[c + 5] * inv, fp16);
+        v.w = pack2_16(o_acc[c + 6] * inv, o_acc[c + 7] * inv, fp16);
+        *reinterpret_cast<uint4*>(op + c) = v;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn fa_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// [d, heads, tokens, batch] view of a [batch, tokens, ld] buffer whose head h occupies columns [h*d, (h+1)*d)
+static const char* fa_map(CUtensorMap* tm, const void* ptr, int d, int heads, int ntok, int B, int ld, long bstride) {
+  EncodeTiledFn fn = fa_encode_fn();
+  if (!fn) return "cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[4] = {cuuint64_t(d), cuuint64_t(heads), cuuint64_t(ntok), cuuint64_t(B)};
+  cuuint64_t strides[3] = {cuuint64_t(d) * 2, cuuint64_t(ld) * 2, cuuint64_t(bstride) * 2};
+  if (B == 1) strides[2] = cuuint64_t(ntok) * ld * 2;
+  cuuint32_t box[4] = {64, 1, 128, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    static thread_local char buf[128];
+    snprintf(buf, sizeof(buf), "attention: cuTensorMapEncodeTiled failed (CUresult %d)", int(r));
+    return buf;
+  }
+  return nullptr;
+}
+
+const char* flash_attention_tc_prepare(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
+                                       int heads, int d, int Nq, int Nk, long q_bs, long kv_bs, long o_bs, float scale, int fp16,
+                                       FaLaunch* L) {
+  if (d != 40 && d != 80 && d != 160) return "attention: unsupported head dim (40, 80, 160)";
+  if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || q_bs % 8 || kv_bs % 8) return "attention: pitches must be multiples of 8 elements";
+  if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15)
+    return "attention: pointers must be 16-byte aligned";
+  if (Nq < 1 || Nk < 1) return "attention: empty problem";
+  static_assert(sizeof(FaParams) <= sizeof(L->params), "FaLaunch::params too small");
+  FaParams* p = reinterpret_cast<FaParams*>(L->params);
+  if (const char* e = fa_map(&p->tmQ, q, d, heads, Nq, B, ldq, q_bs)) return e;
+  if (const char* e = fa_map(&p->tmK, k, d, heads, Nk, B, ldk, kv_bs)) return e;
+  if (const char* e = fa_map(&p->tmV, v, d, heads, Nk, B, ldv, kv_bs)) return e;
+  p->O = reinterpret_cast<uint16_t*>(o);
+  p->ldo = ldo; p->o_bs = o_bs; p->Nq = Nq; p->Nk = Nk;
+  p->scale_log2 = scale * 1.4426950408889634f;
+  p->fp16 = fp16;
+  L->d = d;
+  L->nqt = (d <= 80 && Nq >= 2 * FA_BM) ? 2 : 1;  // two query tiles per CTA when there are enough rows (d=160: TMEM/regs allow one)
+  L->grid = dim3((Nq + FA_BM * L->nqt - 1) / (FA_BM * L->nqt), heads, B);
+  return nullptr;
+}
+
+template <int D, int NQT>
+static const char* fa_launch_d(const FaLaunch& L, cudaStream_t st) {
+  using C = FaCfg<D, NQT>;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(fa_tc_kernel<D, NQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)) != cudaSuccess)
+      return "attention: cudaFuncSetAttribute failed";
+    attr = true;
+  }
+  fa_tc_kernel<D, NQT><<<L.grid, C::THREADS, C::SMEM, st>>>(*reinterpret_cast<const FaParams*>(L.params));
+  return cudaGetLastError() == cudaSuccess ? nullptr : "attention: launch failed";
+}
+
+const char* flash_attention_tc_launch(const FaLaunch& L, cudaStream_t st) {
+  switch (L.d) {
+    case 40: return L.nqt == 2 ? fa_launch_d<40, 2>(L, st) : fa_launch_d<40, 1>(L, st);
+    case 80: return L.nqt == 2 ? fa_launch_d<80, 2>(L, st) : fa_launch_d<80, 1>(L, st);
+    case 160: return fa_launch_d<160, 1>(L, st);
+  }
+  return "attention: unsupported head dim";
+}
+
+}  // namespace madm

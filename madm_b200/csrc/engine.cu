@@ -329,6 +329,23 @@ struct Builder {
     emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, 0.0);
   }
 
+  // fused attention: tcgen05/TMEM kernel (tensor maps encoded at plan time); MADM_ATTN_LEGACY=1 selects the mma.sync kernel
+  void attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, int Bn, int heads, int d, int Nq,
+                 int Nk, long q_bs, long kv_bs, long o_bs, float scale) {
+    const double flops = 4.0 * double(Bn) * Nq * Nk * heads * d;
+    if (mode != PLAN) { ++n_ops; return; }
+    const int h16 = ctx->fp16;
+    if (getenv("MADM_ATTN_LEGACY")) {
+      emit([=](cudaStream_t st) { return flash_attention(q, ldq, k, ldk, v, ldv, o, ldo, Bn, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, h16, st); },
+           false, MADM_KIND_ATTENTION, flops, 0.0);
+      return;
+    }
+    FaLaunch L;
+    if (const char* e = flash_attention_tc_prepare(q, ldq, k, ldk, v, ldv, o, ldo, Bn, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, h16, &L))
+      fail(MADM_EINVAL, std::string(e));
+    emit([L](cudaStream_t st) { return flash_attention_tc_launch(L, st); }, false, MADM_KIND_ATTENTION, flops, 0.0);
+  }
+
   static GemmASeg seg_1x1(const bf16* p, int Bn, int H, int W, int C, int ld = 0) {
     GemmASeg s; s.ptr = p; s.Bt = Bn; s.H = H; s.W = W; s.C = C; s.ld = ld; s.ntaps = 1;
     return s;
@@ -488,11 +505,9 @@ struct Model {
       d.out_bf16 = qkv.p; d.ldo16 = 3 * C; b.gemm(d); }
     b.free(l1);
     B16T att = b.b16(size_t(M) * C);
-    { const bf16* q = qkv.p; bf16* o = att.p; const int n_tok = H * W; const float sc = 1.0f / sqrtf(float(d_head)); const int h16 = f16();
-      b.emit([=](cudaStream_t st) {
-        return flash_attention(q, 3 * C, q + C, 3 * C, q + 2 * C, 3 * C, o, C, Bn, heads, d_head, n_tok, n_tok, long(n_tok) * 3 * C,
-                               long(n_tok) * 3 * C, long(n_tok) * C, sc, h16, st);
-      }, false, MADM_KIND_ATTENTION, 4.0 * double(Bn) * n_tok * n_tok * C, 0.0); }
+    { const bf16* q = qkv.p; bf16* o = att.p; const int n_tok = H * W; const float sc = 1.0f / sqrtf(float(d_head));
+      b.attention(q, 3 * C, q + C, 3 * C, q + 2 * C, 3 * C, o, C, Bn, heads, d_head, n_tok, n_tok, long(n_tok) * 3 * C, long(n_tok) * 3 * C,
+                  long(n_tok) * C, sc); }
     b.free(qkv);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(att.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
       d.w = b.pw(b.linear_w(tb + ".attn1.to_out.0", C, C, true)); d.bias = lora_bias(tb + ".attn1.to_out.0", C);
@@ -505,11 +520,9 @@ struct Model {
       d.w = b.pw(b.linear_w(tb + ".attn2.to_q", C, C, true)); d.out_bf16 = q2.p; d.ldo16 = C; b.gemm(d); }
     b.free(l2);
     { const bf16* q = q2.p; bf16* o = att.p; const int n_tok = H * W; const float sc = 1.0f / sqrtf(float(d_head));
-      const int off = kv_off[tb + ".attn2"]; const bf16* kv = kv_all.p; const int ldkv = kv_total; const int h16 = f16();
-      b.emit([=](cudaStream_t st) {
-        return flash_attention(q, C, kv + off, ldkv, kv + off + C, ldkv, o, C, Bn, heads, d_head, n_tok, 77, long(n_tok) * C,
-                               long(77) * ldkv, long(n_tok) * C, sc, h16, st);
-      }, false, MADM_KIND_ATTENTION, 4.0 * double(Bn) * n_tok * 77 * C, 0.0); }
+      const int off = kv_off[tb + ".attn2"]; const bf16* kv = kv_all.p; const int ldkv = kv_total;
+      b.attention(q, C, kv ? kv + off : nullptr, ldkv, kv ? kv + off + C : nullptr, ldkv, o, C, Bn, heads, d_head, n_tok, 77, long(n_tok) * C,
+                  long(77) * ldkv, long(n_tok) * C, sc); }
     b.free(q2);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(att.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
       d.w = b.pw(b.linear_w(tb + ".attn2.to_out.0", C, C, true)); d.bias = lora_bias(tb + ".attn2.to_out.0", C);

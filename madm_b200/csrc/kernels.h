@@ -33,6 +33,18 @@ const char* flash_attention(const void* q, int ldq, const void* k, int ldk, cons
                             int B, int heads, int d, int Nq, int Nk, long q_bstride, long kv_bstride, long o_bstride,
                             float scale, int fp16, cudaStream_t st);
 
+// ---- attention_tc.cu : the same contract on tcgen05 / TMEM (prepared launch: TMA tensor maps encoded once)
+struct FaLaunch {
+  alignas(64) unsigned char params[512];
+  int d = 0;
+  int nqt = 1;  // query tiles (128 rows) per CTA
+  dim3 grid;
+};
+const char* flash_attention_tc_prepare(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
+                                       int heads, int d, int Nq, int Nk, long q_bstride, long kv_bstride, long o_bstride, float scale,
+                                       int fp16, FaLaunch* out);
+const char* flash_attention_tc_launch(const FaLaunch& l, cudaStream_t st);
+
 // ---- elementwise.cu
 // img NCHW fp32 in [0,1] -> (img-0.5)/0.5 -> 3x3 im2col rows [B*H*W, 64] bf16 (27 real columns, tap-major (ky,kx,c))
 const char* image_im2col(const float* img, int B, int H, int W, void* out_bf16, int* range_flag, int fp16, cudaStream_t st);

@@ -106,10 +106,10 @@ def softmax_rows(s, p):
     _lib.check(lib.madm_op_softmax_rows(_ptr(s), R, L, _ptr(p), _dt(p.dtype), _stream()), None, "madm_op_softmax_rows")
 
 
-def attention(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale):
+def attention(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, impl=0):
     lib = _lib.load()
     _lib.check(lib.madm_op_attention(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(o), ldo, B, heads, d, Nq, Nk, q_bs, kv_bs,
-                                     o_bs, scale, _dt(o.dtype), _stream()), None, "madm_op_attention")
+                                     o_bs, scale, _dt(o.dtype), impl, _stream()), None, "madm_op_attention")
 
 
 def pack_linear(w, lora_a=None, lora_b=None, scale=0.0, out=None, ldo=0, dtype=torch.float16):

@@ -268,9 +268,10 @@ def test_gn_add_relu_nchw(ops, cuda_device):
 
 
 # ---------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("impl", [0, 1])  # 0 = tcgen05/TMEM kernel (product path), 1 = mma.sync kernel
 @pytest.mark.parametrize("B,heads,d,Nq,Nk", [(2, 8, 40, 4096, 4096), (1, 8, 80, 1024, 1024), (2, 8, 160, 256, 256), (1, 8, 160, 64, 64),
                                              (2, 8, 40, 4096, 77), (2, 8, 160, 64, 77), (1, 8, 80, 1024, 77)])
-def test_attention(ops, cuda_device, B, heads, d, Nq, Nk):
+def test_attention(ops, cuda_device, B, heads, d, Nq, Nk, impl):
     g = torch.Generator(device="cuda").manual_seed(d + Nk)
     Cc = heads * d
     self_attn = Nq == Nk
@@ -287,7 +288,7 @@ def test_attention(ops, cuda_device, B, heads, d, Nq, Nk):
         ldq, ldk = Cc, ldkv
         q_bs, kv_bs = Nq * Cc, Nk * ldkv
     o = torch.empty(B, Nq, Cc, dtype=DT, device=cuda_device)
-    ops.attention(q, ldq, k, ldk, v, ldk, o, Cc, B, heads, d, Nq, Nk, q_bs, kv_bs, Nq * Cc, 1.0 / math.sqrt(d))
+    ops.attention(q, ldq, k, ldk, v, ldk, o, Cc, B, heads, d, Nq, Nk, q_bs, kv_bs, Nq * Cc, 1.0 / math.sqrt(d), impl=impl)
     split = lambda t: t.float().reshape(B, -1, heads, d).transpose(1, 2)  # noqa: E731
     ref = F.scaled_dot_product_attention(split(q), split(k), split(v)).transpose(1, 2).reshape(B, Nq, Cc)
     assert relerr(o, ref) < 2e-2
