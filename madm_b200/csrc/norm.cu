@@ -15,71 +15,86 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 
 
 // ---------------------------------------------------------------------------------------------- GroupNorm statistics
-// 4 consecutive channels of one pixel from an fp32 or 16-bit (fp16 / bf16) NHWC tensor
+// V consecutive channels of one pixel: V = 4 from an fp32 tensor (one 16-byte load) or V = 8 from a 16-bit tensor (one
+// 16-byte load), so both variants keep the same number of bytes in flight per thread.
 template <bool IN16>
-__device__ __forceinline__ float4 ld4(const void* base, size_t elem_off, int fp16) {
+struct GnVec {
+  static constexpr int V = IN16 ? 8 : 4;
+};
+
+template <bool IN16>
+__device__ __forceinline__ void ldv(const void* base, size_t elem_off, int fp16, float (&v)[GnVec<IN16>::V]) {
   if constexpr (!IN16) {
-    return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
+    const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   } else {
-    const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + elem_off));
-    float4 v;
-    if (fp16) {
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-      v = make_float4(a.x, a.y, b.x, b.y);
-    } else {
-      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-      v = make_float4(a.x, a.y, b.x, b.y);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + elem_off));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f;
+      if (fp16) f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
     }
-    return v;
   }
 }
 
-// grid = (slabs, B); block = Q*P threads, Q = C/4 channel quads, P pixel lanes.  Thread (q, pl) owns channels 4q..4q+3
+template <int V>
+__device__ __forceinline__ void stv16(uint16_t* dst, const float (&v)[V], int fp16) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<uint2*>(dst) = pack4_16(v[0], v[1], v[2], v[3], fp16);
+  } else {
+    uint4 o;
+    o.x = pack2_16(v[0], v[1], fp16); o.y = pack2_16(v[2], v[3], fp16);
+    o.z = pack2_16(v[4], v[5], fp16); o.w = pack2_16(v[6], v[7], fp16);
+    *reinterpret_cast<uint4*>(dst) = o;
+  }
+}
+
+// grid = (slabs, B); block = Q*P threads, Q = C/V channel vectors, P pixel lanes.  Thread (q, pl) owns channels Vq..Vq+V-1
 // and walks pixels pl, pl+P, ... of its slab (4 loads in flight), so its per-channel partial sums stay in registers.
 template <bool IN16>
 __global__ void gn_stats_kernel(const void* __restrict__ x0, int C0, const void* __restrict__ x1, int C1, int HW,
                                 int pix_per_cta, int P, int fp16, float* __restrict__ partial /*[B,slabs,32,2]*/) {
+  constexpr int V = GnVec<IN16>::V;
   extern __shared__ float sm[];  // [2][P][C]
   const int C = C0 + C1;
-  const int Q = C >> 2;
+  const int Q = C / V;
   const int q = threadIdx.x % Q;
   const int pl = threadIdx.x / Q;
   const int b = blockIdx.y;
   const int p_begin = blockIdx.x * pix_per_cta;
   const int p_end = min(HW, p_begin + pix_per_cta);
-  const int c = q * 4;
+  const int c = q * V;
   const void* src;
   int ld, cc;
   if (c < C0) { src = x0; ld = C0; cc = c; }
   else        { src = x1; ld = C1; cc = c - C0; }
   const size_t img_off = size_t(b) * HW * ld + cc;
-  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  float s[V], ss[V];
+#pragma unroll
+  for (int t = 0; t < V; ++t) s[t] = ss[t] = 0.f;
   int p = p_begin + pl;
   for (; p + 3 * P < p_end; p += 4 * P) {
-    float4 v[4];
+    float v[4][V];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld4<IN16>(src, img_off + size_t(p + u * P) * ld, fp16);
+    for (int u = 0; u < 4; ++u) ldv<IN16>(src, img_off + size_t(p + u * P) * ld, fp16, v[u]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      s[0] += v[u].x; ss[0] += v[u].x * v[u].x;
-      s[1] += v[u].y; ss[1] += v[u].y * v[u].y;
-      s[2] += v[u].z; ss[2] += v[u].z * v[u].z;
-      s[3] += v[u].w; ss[3] += v[u].w * v[u].w;
-    }
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int t = 0; t < V; ++t) { s[t] += v[u][t]; ss[t] += v[u][t] * v[u][t]; }
   }
   for (; p < p_end; p += P) {
-    const float4 v = ld4<IN16>(src, img_off + size_t(p) * ld, fp16);
-    s[0] += v.x; ss[0] += v.x * v.x;
-    s[1] += v.y; ss[1] += v.y * v.y;
-    s[2] += v.z; ss[2] += v.z * v.z;
-    s[3] += v.w; ss[3] += v.w * v.w;
+    float v[V];
+    ldv<IN16>(src, img_off + size_t(p) * ld, fp16, v);
+#pragma unroll
+    for (int t = 0; t < V; ++t) { s[t] += v[t]; ss[t] += v[t] * v[t]; }
   }
   float* sm_s = sm;
   float* sm_ss = sm + P * C;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < V; ++t) {
     sm_s[pl * C + c + t] = s[t];
     sm_ss[pl * C + c + t] = ss[t];
   }
@@ -115,27 +130,28 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int slabs,
 }
 
 // ---------------------------------------------------------------------------------------------- GroupNorm apply
-// Same (slab, image) x (channel quad, pixel lane) decomposition as the statistics kernel: each thread keeps the scale /
-// shift of its 4 channels in registers and streams its pixels with 4 loads in flight:
+// Same (slab, image) x (channel vector, pixel lane) decomposition as the statistics kernel: each thread keeps the scale /
+// shift of its channels in registers and streams its pixels with 4 loads in flight:
 // y = act(x*scale + shift) -> 16-bit (and optionally the un-normalised x -> 16-bit for a 1x1 shortcut conv).
 template <bool IN16>
 __global__ void gn_apply_kernel(const void* __restrict__ x0, int C0, const void* __restrict__ x1, int C1, int HW,
                                 int pix_per_cta, int P, const float* __restrict__ partial, int slabs, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int act, int fp16, uint16_t* __restrict__ y,
                                 uint16_t* __restrict__ raw) {
+  constexpr int V = GnVec<IN16>::V;
   __shared__ float red[64];
   const int C = C0 + C1;
-  const int Q = C >> 2;
+  const int Q = C / V;
   const int q = threadIdx.x % Q;
   const int pl = threadIdx.x / Q;
   const int b = blockIdx.y;
   const int cpg = C / 32;
   gn_reduce_partials(partial, b, slabs, red);
-  const int c = q * 4;
+  const int c = q * V;
   const float inv_n = 1.0f / (float(HW) * float(cpg));
-  float sc[4], sh[4];
+  float sc[V], sh[V];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < V; ++t) {
     const int g = (c + t) / cpg;
     const float mean = red[g * 2] * inv_n;
     const float var = fmaxf(red[g * 2 + 1] * inv_n - mean * mean, 0.0f);
@@ -155,30 +171,33 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, int C0, const void*
   const int p_end = min(HW, p_begin + pix_per_cta);
   int p = p_begin + pl;
   for (; p + 3 * P < p_end; p += 4 * P) {
-    float4 v[4];
+    float v[4][V];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld4<IN16>(src, img_off + size_t(p + u * P) * ld, fp16);
+    for (int u = 0; u < 4; ++u) ldv<IN16>(src, img_off + size_t(p + u * P) * ld, fp16, v[u]);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const size_t o = out_off + size_t(p + u * P) * C;
-      *reinterpret_cast<uint2*>(y + o) = pack4_16(act_apply(v[u].x * sc[0] + sh[0], act), act_apply(v[u].y * sc[1] + sh[1], act),
-                                                  act_apply(v[u].z * sc[2] + sh[2], act), act_apply(v[u].w * sc[3] + sh[3], act), fp16);
-      if (raw) *reinterpret_cast<uint2*>(raw + o) = pack4_16(v[u].x, v[u].y, v[u].z, v[u].w, fp16);
+      if (raw) stv16<V>(raw + o, v[u], fp16);
+#pragma unroll
+      for (int t = 0; t < V; ++t) v[u][t] = act_apply(v[u][t] * sc[t] + sh[t], act);
+      stv16<V>(y + o, v[u], fp16);
     }
   }
   for (; p < p_end; p += P) {
-    const float4 v = ld4<IN16>(src, img_off + size_t(p) * ld, fp16);
+    float v[V];
+    ldv<IN16>(src, img_off + size_t(p) * ld, fp16, v);
     const size_t o = out_off + size_t(p) * C;
-    *reinterpret_cast<uint2*>(y + o) = pack4_16(act_apply(v.x * sc[0] + sh[0], act), act_apply(v.y * sc[1] + sh[1], act),
-                                                act_apply(v.z * sc[2] + sh[2], act), act_apply(v.w * sc[3] + sh[3], act), fp16);
-    if (raw) *reinterpret_cast<uint2*>(raw + o) = pack4_16(v.x, v.y, v.z, v.w, fp16);
+    if (raw) stv16<V>(raw + o, v, fp16);
+#pragma unroll
+    for (int t = 0; t < V; ++t) v[t] = act_apply(v[t] * sc[t] + sh[t], act);
+    stv16<V>(y + o, v, fp16);
   }
 }
 
 // Slab geometry depends on (HW, C) only, never on the batch size: image i of a batch-8 call reduces in exactly the same
 // order as a batch-1 call on that image.
-static void gn_geometry(int HW, int C, int* P, int* threads, int* ppc, int* slabs) {
-  const int Q = C / 4;
+static void gn_geometry(int HW, int C, int V, int* P, int* threads, int* ppc, int* slabs) {
+  const int Q = C / V;
   int p = (256 + Q - 1) / Q;
   if (p < 1) p = 1;
   while (Q * p > 1024) --p;
@@ -192,10 +211,22 @@ static void gn_geometry(int HW, int C, int* P, int* threads, int* ppc, int* slab
   *slabs = (HW + int(per) - 1) / int(per);
 }
 
+// the slab count must not depend on the input dtype (the partial-sum buffers are sized before it is known): the pixel-lane
+// count P of the fp32 geometry is used for both
 int groupnorm_slabs(int HW, int C) {
   int P, threads, ppc, slabs;
-  gn_geometry(HW, C, &P, &threads, &ppc, &slabs);
+  gn_geometry(HW, C, 4, &P, &threads, &ppc, &slabs);
   return slabs;
+}
+static void gn_launch_geometry(int HW, int C, int in16, int* P, int* threads, int* ppc, int* slabs) {
+  int P4, t4;
+  gn_geometry(HW, C, 4, &P4, &t4, ppc, slabs);  // slabs / pixels per CTA: dtype independent
+  const int V = in16 ? 8 : 4;
+  const int Q = C / V;
+  int p = (256 + Q - 1) / Q;
+  while (Q * p > 1024) --p;
+  *P = p;
+  *threads = Q * p;
 }
 
 const char* groupnorm_stats(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, int fp16, float* partial,
@@ -204,8 +235,9 @@ const char* groupnorm_stats(const void* x0, int C0, const void* x1, int C1, int 
   if (C % 32 != 0 || C % 4 != 0) return "groupnorm: C must be a multiple of 32";
   if (C0 % 4 != 0 || C1 % 4 != 0) return "groupnorm: source channel counts must be multiples of 4";
   if (C / 4 > 1024) return "groupnorm: C too large";
+  if (in16 && C % 8 != 0) return "groupnorm: C must be a multiple of 8 for 16-bit inputs";
   int P, threads, ppc, slabs;
-  gn_geometry(HW, C, &P, &threads, &ppc, &slabs);
+  gn_launch_geometry(HW, C, in16, &P, &threads, &ppc, &slabs);
   const size_t smem = size_t(2) * P * C * sizeof(float);
   if (in16) gn_stats_kernel<true><<<dim3(slabs, B), threads, smem, st>>>(x0, C0, x1, C1, HW, ppc, P, fp16, partial);
   else gn_stats_kernel<false><<<dim3(slabs, B), threads, smem, st>>>(x0, C0, x1, C1, HW, ppc, P, fp16, partial);
@@ -221,7 +253,7 @@ const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int 
                             const float* gamma, const float* beta, float eps, int act, void* y, void* raw, int fp16, cudaStream_t st) {
   const int C = C0 + C1;
   int P, threads, ppc, slabs;
-  gn_geometry(HW, C, &P, &threads, &ppc, &slabs);
+  gn_launch_geometry(HW, C, in16, &P, &threads, &ppc, &slabs);
   if (in16)
     gn_apply_kernel<true><<<dim3(slabs, B), threads, 0, st>>>(x0, C0, x1, C1, HW, ppc, P, partial, slabs, gamma, beta, eps, act, fp16,
                                                               reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
