@@ -178,3 +178,28 @@ def test_slide_forward_512x1024(pair, cuda_device):
     for k in ref:
         assert out[k].shape == ref[k].shape
         _check("slide/" + k, out[k], ref[k])
+
+
+def test_head_argmax_agreement(pair, cuda_device):
+    """North-star gate: argmax segmentation from the UNCHANGED head (oracle restatement of DAFormerHead) fed with the product's
+    features is >= 99.5 % pixel-identical to the one fed with the fp32 oracle's features, after the meta-arch's bilinear
+    upsampling to the input size (mtmadise.py:685-688)."""
+    import torch.nn.functional as F
+    from oracle import synthetic
+    from oracle.daformer_head import build_head
+    from oracle.lora import set_adapter
+    ob, pb = pair
+    head = build_head().to(cuda_device)
+    set_adapter(ob.feature_extractor.ldm_extractor.unet, ["Depth"])
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    img = synthetic.synthetic_images(2, seed=41).to(cuda_device)
+    with torch.no_grad():
+        ref = ob(img, input_modal="others")
+        out = pb(img, input_modal="others")
+        seg_ref = F.interpolate(head(ref), size=img.shape[-2:], mode="bilinear", align_corners=False).argmax(1)
+        seg_out = F.interpolate(head(out), size=img.shape[-2:], mode="bilinear", align_corners=False).argmax(1)
+    agree = (seg_ref == seg_out).float().mean().item()
+    ncls = seg_ref.unique().numel()
+    print(f"[{_MODE}] head argmax agreement {100 * agree:.3f} % over {seg_ref.numel()} pixels, {ncls} classes present")
+    assert ncls >= 5, "degenerate head: too few classes predicted for the test to be meaningful"
+    assert agree >= (0.995 if _MODE == "fp16" else 0.97)
