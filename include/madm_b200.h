@@ -165,6 +165,9 @@ typedef struct madm_gemm_args {
   float alpha;
   int32_t bn;             /* N tile: 0 auto, else 16/32/64/128/160/192/256 */
   int32_t dtype;          /* MADM_DTYPE_* of a, w and out_bf16 */
+  float* colstats;        /* optional [ceil(M/32)][N][2]: per-column (sum, sum of squares) of the stored outputs per 32-row block,
+                             i.e. the GroupNorm statistics of the consumer fused into this epilogue (no atomics) */
+  int32_t stat_rows;      /* 32 (0 = 32) */
 } madm_gemm_args;
 
 int madm_op_gemm(const madm_gemm_args* a, madm_stream stream);
@@ -172,6 +175,10 @@ int madm_op_groupnorm(const void* x0, int32_t C0, const void* x1, int32_t C1, in
                       int32_t in16 /* inputs are 16-bit (dtype) instead of fp32 */, const float* gamma,
                       const float* beta, float eps, int32_t act, float* stats_scratch /* madm_op_groupnorm_scratch_floats() */,
                       void* y_bf16, void* raw_bf16, int32_t dtype, madm_stream stream);
+/* GroupNorm whose statistics come from a producing GEMM's `colstats` instead of a statistics pass */
+int madm_op_groupnorm_from_colstats(const void* x, int32_t C, int32_t B, int32_t HW, int32_t in16, const float* colstats,
+                                    int32_t stat_rows, const float* gamma, const float* beta, float eps, int32_t act,
+                                    float* scratch /*[B,32,32,2]*/, void* y_bf16, int32_t dtype, madm_stream stream);
 int madm_op_groupnorm_scratch_floats(int32_t B, int32_t HW, int32_t C); /* scratch size (floats) for the two GN ops */
 int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y_bf16,
                       int32_t dtype, madm_stream stream);

@@ -45,6 +45,7 @@ int madm_op_gemm(const madm_gemm_args* a, madm_stream stream) {
   d.residual = a->residual; d.ldr = a->ldr;
   d.out_f32 = a->out_f32; d.ldo32 = a->ldo32; d.out_bf16 = a->out_bf16; d.ldo16 = a->ldo16;
   d.act = a->act; d.alpha = a->alpha; d.bn = a->bn; d.fp16 = a->dtype == MADM_DTYPE_FP16;
+  d.colstats = a->colstats; d.stat_rows = a->stat_rows ? a->stat_rows : 32;
   GemmLaunch L;
   if (const char* e = gemm_prepare(d, &L)) return fail(e);
   RUN(gemm_launch(L, static_cast<cudaStream_t>(stream)));
@@ -55,7 +56,7 @@ int madm_op_groupnorm(const void* x0, int32_t C0, const void* x1, int32_t C1, in
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int f16 = dtype == MADM_DTYPE_FP16;
   if (const char* e = groupnorm_stats(x0, C0, x1, C1, B, HW, in16, f16, stats, st)) return fail(e);
-  RUN(groupnorm_apply(x0, C0, x1, C1, B, HW, in16, stats, gamma, beta, eps, act, y, raw, f16, st));
+  RUN(groupnorm_apply(x0, C0, x1, C1, B, HW, in16, stats, 0, gamma, beta, eps, act, y, raw, f16, st));
 }
 
 int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y,
@@ -107,6 +108,18 @@ int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t 
 int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out, int32_t* range_flag, int32_t dtype,
                          madm_stream stream) {
   RUN(image_im2col(img, B, H, W, out, range_flag, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_groupnorm_from_colstats(const void* x, int32_t C, int32_t B, int32_t HW, int32_t in16, const float* colstats, int32_t stat_rows,
+                                    const float* gamma, const float* beta, float eps, int32_t act, float* scratch /*[B,32 chunks,32,2]*/, void* y,
+                                    int32_t dtype, madm_stream stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int f16 = dtype == MADM_DTYPE_FP16;
+  if (HW % stat_rows != 0) return fail("groupnorm_from_colstats: HW must be a multiple of stat_rows");
+  if (stat_rows != 32) return fail("groupnorm_from_colstats: stat_rows must be 32");
+  const int nb = HW / stat_rows;
+  if (const char* e = groupnorm_colstats_reduce(colstats, C, nullptr, 0, B, nb, scratch, st)) return fail(e);
+  RUN(groupnorm_apply(x, C, nullptr, 0, B, HW, in16, scratch, groupnorm_colstats_chunks(nb), gamma, beta, eps, act, y, nullptr, f16, st));
 }
 
 int madm_op_groupnorm_scratch_floats(int32_t B, int32_t HW, int32_t C) {

@@ -62,6 +62,9 @@ struct B16T { bf16* p = nullptr; size_t off = 0; size_t bytes = 0; };
 // fp32 residual-stream activation, NHWC, optionally with a bf16 copy for consumers that take it as a GEMM operand
 struct Act {
   F32T f; B16T h;
+  float* cs = nullptr;  // per-column statistics written by the producing GEMM's epilogue ([M/sr][C][2]), if any
+  int sr = 0;           // rows per statistics block (64 or 128)
+  bool has_cs = false;  // valid in every builder mode (cs itself is null outside PLAN mode)
   int B = 0, H = 0, W = 0, C = 0;
   int HW() const { return H * W; }
   long M() const { return long(B) * H * W; }
@@ -208,6 +211,25 @@ struct Builder {
     float* p = stats_base ? stats_base + stats_used : nullptr;
     stats_used += size_t(B) * slabs * 64;
     return p;
+  }
+
+  // per-column statistics buffer for a GEMM whose output feeds a GroupNorm; lives in the statistics arena
+  void attach_colstats(Act& a, GemmDesc& d) {
+    a.sr = 32;
+    if (a.HW() % a.sr != 0 || a.C % 32 != 0) return;  // shape not eligible: the consumer falls back to a statistics pass
+    // The fused statistics add ~25 % to the epilogue's instruction count (separate kernel variant, gemm_tc_kernel<BN,true>):
+    // measured +0.25 ms on the GEMM family against -1.0 ms of statistics passes, at every K; MADM_FUSE_STATS_KMIN can
+    // restrict the fusion to long-K producers.
+    int K = 0;
+    for (int sgi = 0; sgi < d.nseg; ++sgi) K += d.seg[sgi].ntaps * d.seg[sgi].C;
+    static const int kmin = getenv("MADM_FUSE_STATS_KMIN") ? atoi(getenv("MADM_FUSE_STATS_KMIN")) : 0;
+    if (K < kmin) return;
+    const size_t n = size_t((a.M() + a.sr - 1) / a.sr) * a.C * 2;
+    a.cs = stats_base ? stats_base + stats_used : nullptr;
+    stats_used += n;
+    a.has_cs = true;
+    d.colstats = a.cs;
+    d.stat_rows = a.sr;
   }
 
   // ---- parameters
@@ -379,16 +401,29 @@ struct Builder {
     const int C0 = x0.C, C1 = x1 ? x1->C : 0;
     const float* g = (mode == LAYOUT) ? nullptr : param(norm + ".weight", C0 + C1);
     const float* b = (mode == LAYOUT) ? nullptr : param(norm + ".bias", C0 + C1);
-    float* stats = new_stats(groupnorm_slabs(x0.HW(), C0 + C1));
     const void* p0 = in16 ? static_cast<const void*>(x0.h.p) : static_cast<const void*>(x0.f.p);
     const void* p1 = x1 ? static_cast<const void*>(x1->f.p) : nullptr;
     const int Bn = x0.B, HW = x0.HW();
     const double elems = double(Bn) * HW * (C0 + C1);
     const int f16 = ctx->fp16, i16 = in16 ? 1 : 0;
     const double in_b = in16 ? 2 : 4;
-    emit([=](cudaStream_t st) { return groupnorm_stats(p0, C0, p1, C1, Bn, HW, i16, f16, stats, st); }, false, MADM_KIND_GROUPNORM, 0.0,
-         elems * in_b);
-    emit([=](cudaStream_t st) { return groupnorm_apply(p0, C0, p1, C1, Bn, HW, i16, stats, g, b, eps, actfn, y, raw, f16, st); }, false,
+    const bool fused = x0.has_cs && (!x1 || (x1->has_cs && x1->sr == x0.sr));
+    float* stats;
+    int slabs;
+    if (fused) {  // statistics came out of the producing GEMM epilogues: one small fixed-order reduction, no pass over x
+      const int nb = HW / x0.sr;
+      slabs = groupnorm_colstats_chunks(nb);
+      stats = new_stats(slabs);
+      const float* c0 = x0.cs; const float* c1 = x1 ? x1->cs : nullptr;
+      emit([=](cudaStream_t st) { return groupnorm_colstats_reduce(c0, C0, c1, C1, Bn, nb, stats, st); }, false, MADM_KIND_GROUPNORM, 0.0,
+           double(Bn) * nb * (C0 + C1) * 8);
+    } else {
+      slabs = groupnorm_slabs(HW, C0 + C1);
+      stats = new_stats(slabs);
+      emit([=](cudaStream_t st) { return groupnorm_stats(p0, C0, p1, C1, Bn, HW, i16, f16, stats, st); }, false, MADM_KIND_GROUPNORM, 0.0,
+           elems * in_b);
+    }
+    emit([=](cudaStream_t st) { return groupnorm_apply(p0, C0, p1, C1, Bn, HW, i16, stats, slabs, g, b, eps, actfn, y, raw, f16, st); }, false,
          MADM_KIND_GROUPNORM, 0.0, elems * (in_b + 2 + (raw ? 2 : 0)));
   }
 };
@@ -449,6 +484,7 @@ struct Model {
       if (has_temb) { d.rowbias = temb_all.p ? temb_all.p + temb_off[p] : nullptr; d.ld_rowbias = temb_total; d.rows_per_img = H * W;
                       if (dry()) d.rowbias = nullptr; }
       d.out_bf16 = h1.h.p; d.ldo16 = Cout;
+      b.attach_colstats(h1, d);  // norm2 statistics come out of this epilogue
       b.gemm(d);
     }
     b.free(n1);
@@ -467,6 +503,7 @@ struct Model {
         d.residual = x0.f.p; d.ldr = Cout;
       }
       d.out_f32 = out.f.p; d.ldo32 = Cout; d.out_bf16 = out.h.p; d.ldo16 = Cout;
+      b.attach_colstats(out, d);  // statistics for whichever GroupNorm consumes this block's output
       b.gemm(d);
     }
     b.free(n2);
@@ -548,7 +585,8 @@ struct Model {
     Act out = b.act(Bn, H, W, C, true, want_b16);
     { GemmDesc d; d.seg[0] = Builder::seg_1x1(hsb.p, Bn, H, W, C); d.M = int(M); d.N = C; d.Nw = C;
       d.w = b.pw(b.conv_w(p + ".proj_out", C, C, 1)); d.bias = P(p + ".proj_out.bias", C);
-      d.residual = x.f.p; d.ldr = C; d.out_f32 = out.f.p; d.ldo32 = C; d.out_bf16 = out.h.p; d.ldo16 = C; b.gemm(d); }
+      d.residual = x.f.p; d.ldr = C; d.out_f32 = out.f.p; d.ldo32 = C; d.out_bf16 = out.h.p; d.ldo16 = C;
+      b.attach_colstats(out, d); b.gemm(d); }
     b.free(hsb);
     return out;
   }
@@ -568,7 +606,8 @@ struct Model {
       b.emit([=](cudaStream_t st) { return space_to_depth(src, Bn, H, W, C, dst, h16, st); }); }
     Act out = b.act(Bn, H / 2, W / 2, C, true, false);
     { GemmDesc d; d.seg[0] = Builder::seg_s2(s2d.p, Bn, H / 2, W / 2, C, pad1); d.M = int(out.M()); d.N = C; d.Nw = C;
-      d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C; b.gemm(d); }
+      d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C;
+      b.attach_colstats(out, d); b.gemm(d); }
     b.free(s2d);
     return out;
   }
@@ -581,7 +620,8 @@ struct Model {
       b.emit([=](cudaStream_t st) { return upsample_nearest2x(src, Bn, H, W, C, dst, h16, st); }); }
     Act out = b.act(Bn, 2 * H, 2 * W, C, true, false);
     { GemmDesc d; d.seg[0] = Builder::seg_3x3(up.p, Bn, 2 * H, 2 * W, C); d.M = int(out.M()); d.N = C; d.Nw = C;
-      d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C; b.gemm(d); }
+      d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C;
+      b.attach_colstats(out, d); b.gemm(d); }
     b.free(up);
     return out;
   }
@@ -624,7 +664,7 @@ struct Model {
     Act out = b.act(Bn, H, W, C, true, false);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(o.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
       d.w = b.pw(b.linear_w(p + ".to_out.0", C, C, false)); d.bias = P(p + ".to_out.0.bias", C);
-      d.residual = x.f.p; d.ldr = C; d.out_f32 = out.f.p; d.ldo32 = C; b.gemm(d); }
+      d.residual = x.f.p; d.ldr = C; d.out_f32 = out.f.p; d.ldo32 = C; b.attach_colstats(out, d); b.gemm(d); }
     b.free(o);
     return out;
   }
@@ -657,6 +697,7 @@ struct Model {
     Act x = b.act(Bn, R, R, 128, true, false);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(col.p, long(Bn) * R * R, 64); d.M = Bn * R * R; d.N = 128; d.Nw = 128;
       d.w = b.pw(b.conv_w(e + "conv_in", 128, 3, 9, /*Cpad=*/3)); d.bias = P(e + "conv_in.bias", 128); d.out_f32 = x.f.p; d.ldo32 = 128;
+      b.attach_colstats(x, d);
       b.gemm(d, 2.0 * double(d.M) * 128 * 27); }
     b.free(col);
     const int ch[4] = {128, 256, 512, 512};
@@ -766,6 +807,7 @@ struct Model {
     Act x = b.act(Bn, 64, 64, 320, true, false);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(col.p, long(Bn) * 4096, 64); d.M = Bn * 4096; d.N = 320; d.Nw = 320;
       d.w = b.pw(b.conv_w(kUnet + "conv_in", 320, 4, 9, /*Cpad=*/4)); d.bias = P(kUnet + "conv_in.bias", 320); d.out_f32 = x.f.p; d.ldo32 = 320;
+      b.attach_colstats(x, d);
       b.gemm(d, 2.0 * double(d.M) * 320 * 36); }
     b.free(col); b.free(noisy);
     // ---- down path
@@ -833,47 +875,51 @@ struct Model {
       const int Bn = x.B, H = x.H, W = x.W, Cin = x.C, Cb = 128, Cout = 512;
       const long M = x.M();
       const bool shortcut = Cin != Cout;
-      auto gn = [&](const B16T& src, const std::string& norm, int C, bf16* y) {
-        Act a; a.h = src; a.B = Bn; a.H = H; a.W = W; a.C = C;
-        b.groupnorm(a, nullptr, norm, 1e-5f, ACT_RELU, y, nullptr, /*in16=*/true);
-      };
-      B16T c1 = b.b16(size_t(M) * Cb);
+      // every GroupNorm of the bottleneck takes its statistics from the producing GEMM's epilogue
+      Act c1 = b.act(Bn, H, W, Cb, false, true);
       { GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cin); d.M = int(M); d.N = Cb; d.Nw = Cb;
-        d.w = b.pw(b.conv_w(p + "conv1", Cb, Cin, 1)); d.out_bf16 = c1.p; d.ldo16 = Cb; b.gemm(d); }
+        d.w = b.pw(b.conv_w(p + "conv1", Cb, Cin, 1)); d.out_bf16 = c1.h.p; d.ldo16 = Cb; b.attach_colstats(c1, d); b.gemm(d); }
       B16T a1 = b.b16(size_t(M) * Cb);
-      gn(c1, p + "conv1.norm", Cb, a1.p);
+      b.groupnorm(c1, nullptr, p + "conv1.norm", 1e-5f, ACT_RELU, a1.p, nullptr, /*in16=*/true);
       b.free(c1);
-      B16T c2 = b.b16(size_t(M) * Cb);
+      Act c2 = b.act(Bn, H, W, Cb, false, true);
       { GemmDesc d; d.seg[0] = Builder::seg_3x3(a1.p, Bn, H, W, Cb); d.M = int(M); d.N = Cb; d.Nw = Cb;
-        d.w = b.pw(b.conv_w(p + "conv2", Cb, Cb, 9)); d.out_bf16 = c2.p; d.ldo16 = Cb; b.gemm(d); }
+        d.w = b.pw(b.conv_w(p + "conv2", Cb, Cb, 9)); d.out_bf16 = c2.h.p; d.ldo16 = Cb; b.attach_colstats(c2, d); b.gemm(d); }
       b.free(a1);
       B16T a2 = b.b16(size_t(M) * Cb);
-      gn(c2, p + "conv2.norm", Cb, a2.p);
+      b.groupnorm(c2, nullptr, p + "conv2.norm", 1e-5f, ACT_RELU, a2.p, nullptr, /*in16=*/true);
       b.free(c2);
-      F32T c3 = b.f32(size_t(M) * Cout);
+      Act c3 = b.act(Bn, H, W, Cout, true, false);
       { GemmDesc d; d.seg[0] = Builder::seg_1x1(a2.p, Bn, H, W, Cb); d.M = int(M); d.N = Cout; d.Nw = Cout;
-        d.w = b.pw(b.conv_w(p + "conv3", Cout, Cb, 1)); d.out_f32 = c3.p; d.ldo32 = Cout; b.gemm(d); }
+        d.w = b.pw(b.conv_w(p + "conv3", Cout, Cb, 1)); d.out_f32 = c3.f.p; d.ldo32 = Cout; b.attach_colstats(c3, d); b.gemm(d); }
       b.free(a2);
-      F32T sc;
+      Act sc;
       if (shortcut) {
-        sc = b.f32(size_t(M) * Cout);
+        sc = b.act(Bn, H, W, Cout, true, false);
         GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cin); d.M = int(M); d.N = Cout; d.Nw = Cout;
-        d.w = b.pw(b.conv_w(p + "shortcut", Cout, Cin, 1)); d.out_f32 = sc.p; d.ldo32 = Cout; b.gemm(d);
+        d.w = b.pw(b.conv_w(p + "shortcut", Cout, Cin, 1)); d.out_f32 = sc.f.p; d.ldo32 = Cout; b.attach_colstats(sc, d); b.gemm(d);
       }
       const int HW = H * W;
-      const int slabs = groupnorm_slabs(HW, Cout);
-      float* pt3 = b.new_stats(slabs);
-      float* pts = shortcut ? b.new_stats(slabs) : nullptr;
       float* st3 = b.new_stats(1);
       float* sts = shortcut ? b.new_stats(1) : nullptr;
-      const float* c3p = c3.p; const float* scp = shortcut ? sc.p : x.f.p;
+      const float* c3p = c3.f.p; const float* scp = shortcut ? sc.f.p : x.f.p;
       const double pel = double(Bn) * HW * Cout;
-      b.emit([=](cudaStream_t st) { return groupnorm_stats(c3p, Cout, nullptr, 0, Bn, HW, 0, 0, pt3, st); }, false, MADM_KIND_GROUPNORM, 0.0, pel * 4);
-      b.emit([=](cudaStream_t st) { return groupnorm_finalize(pt3, Bn, HW, Cout, st3, st); }, false, MADM_KIND_GROUPNORM, 0.0, 0.0);
-      if (shortcut) {
-        b.emit([=](cudaStream_t st) { return groupnorm_stats(scp, Cout, nullptr, 0, Bn, HW, 0, 0, pts, st); }, false, MADM_KIND_GROUPNORM, 0.0, pel * 4);
-        b.emit([=](cudaStream_t st) { return groupnorm_finalize(pts, Bn, HW, Cout, sts, st); }, false, MADM_KIND_GROUPNORM, 0.0, 0.0);
-      }
+      auto tail_stats = [&](const Act& t, const float* src, float* dst) {  // [B,32,2] group sums of a fp32 [M,Cout] tensor
+        if (t.has_cs) {
+          const float* cst = t.cs; const int nb = HW / t.sr; const int S = groupnorm_colstats_chunks(nb);
+          float* part = b.new_stats(S);
+          b.emit([=](cudaStream_t st) { return groupnorm_colstats_reduce(cst, Cout, nullptr, 0, Bn, nb, part, st); }, false, MADM_KIND_GROUPNORM,
+                 0.0, double(Bn) * nb * Cout * 8);
+          b.emit([=](cudaStream_t st) { return groupnorm_finalize_slabs(part, Bn, S, dst, st); }, false, MADM_KIND_GROUPNORM, 0.0, 0.0);
+        } else {
+          float* part = b.new_stats(groupnorm_slabs(HW, Cout));
+          b.emit([=](cudaStream_t st) { return groupnorm_stats(src, Cout, nullptr, 0, Bn, HW, 0, 0, part, st); }, false, MADM_KIND_GROUPNORM, 0.0,
+                 pel * 4);
+          b.emit([=](cudaStream_t st) { return groupnorm_finalize(part, Bn, HW, Cout, dst, st); }, false, MADM_KIND_GROUPNORM, 0.0, 0.0);
+        }
+      };
+      tail_stats(c3, c3p, st3);
+      if (shortcut) tail_stats(sc, scp, sts);
       const float* g3 = P(p + "conv3.norm.weight", Cout); const float* b3 = P(p + "conv3.norm.bias", Cout);
       const float* gs = shortcut ? P(p + "shortcut.norm.weight", Cout) : nullptr;
       const float* bs = shortcut ? P(p + "shortcut.norm.bias", Cout) : nullptr;

@@ -56,6 +56,8 @@ struct GemmParams {
   int n_tiles;
   int fp16;
   int num_tiles;
+  float* colstats;   // [ceil(M/32)][N][2] per-column (sum, sum of squares) of the stored outputs per 32-row block, or null
+  int stat_rows;     // always 32 (one block per epilogue warp)
 };
 
 template <int BN>
@@ -86,7 +88,8 @@ __device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, fl
 // bias (+ the per-image time-embedding row bias).  Compile-time flags keep the loop free of uniform branches.
 template <bool RES, bool O32, bool O16>
 __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int M, float alpha, float4 bb, int act, int fp16,
-                                          const float* __restrict__ res, int ldr, float* o32, int ldo32, uint16_t* o16, int ldo16) {
+                                          const float* __restrict__ res, int ldr, float* o32, int ldo32, uint16_t* o16, int ldo16,
+                                          bool do_stats, float (&cs)[8]) {
   const int rsub = lane >> 3;
   const int cc = (lane & 7) * 4;
   float4 resv[8];
@@ -108,6 +111,17 @@ __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int 
     if (row0 + r < M) {
       if constexpr (O32) *reinterpret_cast<float4*>(o32 + size_t(r) * ldo32) = v;
       if constexpr (O16) *reinterpret_cast<uint2*>(o16 + size_t(r) * ldo16) = pack4_16(v.x, v.y, v.z, v.w, fp16);
+      if (do_stats) {  // GroupNorm statistics of the consumer, fused here: per-column sum / sum of squares of what is stored
+        cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
+        cs[4] = fmaf(v.x, v.x, cs[4]); cs[5] = fmaf(v.y, v.y, cs[5]); cs[6] = fmaf(v.z, v.z, cs[6]); cs[7] = fmaf(v.w, v.w, cs[7]);
+      }
+    }
+  }
+  if (do_stats) {  // fold the 4 row sub-groups of this warp: lanes 0..7 end up with the totals of their 4 columns over 32 rows
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+      cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
     }
   }
 }
@@ -118,7 +132,7 @@ __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int 
 //               i+1 overlap the epilogue of tile i
 //   warps 2..5  epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> coalesced fused epilogue
 //               (bias / time-embedding row bias / fp32 residual / SiLU / ReLU / GEGLU) -> fp32 and/or 16-bit stores
-template <int BN>
+template <int BN, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -250,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint16_t* const out16 = reinterpret_cast<uint16_t*>(p.out_bf16);
     const int ldr = p.ldr, ldo32 = p.ldo32, ldo16 = p.ldo16;
     const int mode = (residual ? 4 : 0) | (out32 ? 2 : 0) | (out16 ? 1 : 0);
+    constexpr bool do_stats = STATS;  // compile-time: the statistics-free variant keeps the tighter rolled chunk loop
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t r[32];
@@ -314,12 +329,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
           __syncwarp();
           const int cc = (lane & 7) * 4;
+          float nostats[8];
           epi_block<false, false, true>(stg, lane, row0, M, 1.0f, make_float4(0.f, 0.f, 0.f, 0.f), ACT_NONE, fp16, nullptr, 0, nullptr, 0,
-                                        out16 + size_t(row0 + (lane >> 3) * 0) * ldo16 + on0 + half * 32 + cc, ldo16);
+                                        out16 + size_t(row0) * ldo16 + on0 + half * 32 + cc, ldo16, false, nostats);
         }
       } else {
+        float cs1[8];  // column statistics of the current chunk (STATS variant only)
 #pragma unroll 1
         for (int c = par * 32; c < BN; c += 64) {
+          if constexpr (STATS) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cs1[i] = 0.f;
+          }
           __syncwarp();  // previous chunk's smem reads are done; warp converged for the aligned tcgen05.ld
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
@@ -342,12 +363,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             float* o32p = out32 ? out32 + size_t(row0) * ldo32 + n : nullptr;
             uint16_t* o16p = out16 ? out16 + size_t(row0) * ldo16 + n : nullptr;
             switch (mode) {
-              case 1: epi_block<false, false, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
-              case 2: epi_block<false, true, false>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
-              case 3: epi_block<false, true, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
-              case 5: epi_block<true, false, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
-              case 6: epi_block<true, true, false>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
-              default: epi_block<true, true, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16); break;
+              case 1: epi_block<false, false, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+              case 2: epi_block<false, true, false>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+              case 3: epi_block<false, true, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+              case 5: epi_block<true, false, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+              case 6: epi_block<true, true, false>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+              default: epi_block<true, true, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+            }
+            if (do_stats && lane < 8 && row0 < M) {
+              // one (sum, sumsq) pair per column for this warp's 32-row block: 8 lanes x 32 B = 256 contiguous bytes, written by
+              // exactly one warp -> no atomics, no cross-warp synchronisation, bit-reproducible
+              float4* dst = reinterpret_cast<float4*>(p.colstats + (size_t(row0 >> 5) * N + n) * 2);
+              dst[0] = make_float4(cs1[0], cs1[4], cs1[1], cs1[5]);
+              dst[1] = make_float4(cs1[2], cs1[6], cs1[3], cs1[7]);
             }
           } else {
 #pragma unroll 1
@@ -474,6 +502,10 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   if (d.act == ACT_GEGLU && (!d.out_bf16 || d.out_f32 || d.residual || d.rowbias)) return "gemm: GEGLU epilogue writes bf16 only";
   if (d.act == ACT_GEGLU && d.N % 64 != 0) return "gemm: GEGLU needs N % 64 == 0";
   if (d.rowbias && d.rows_per_img % 32 != 0) return "gemm: rows_per_img must be a multiple of 32 when a row bias is given";
+  if (d.colstats) {
+    if (d.stat_rows != 32) return "gemm: stat_rows must be 32";
+    if (d.N % 32 != 0 || d.act == ACT_GEGLU) return "gemm: column statistics need N % 32 == 0 and a plain epilogue";
+  }
   L.bn = d.bn ? d.bn : pick_bn(d);
   const GemmASeg& s0 = d.seg[0];
   const int pix = s0.H * s0.W;
@@ -541,16 +573,20 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   return nullptr;
 }
 
-template <int BN>
-static const char* launch_bn(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
+template <int BN, bool STATS>
+static const char* launch_bn_s(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BN>::SMEM)) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BN>::SMEM)) != cudaSuccess)
       return "gemm: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     attr_set = true;
   }
-  gemm_tc_kernel<BN><<<L.grid, kThreads, Cfg<BN>::SMEM, stream>>>(p);
+  gemm_tc_kernel<BN, STATS><<<L.grid, kThreads, Cfg<BN>::SMEM, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? nullptr : "gemm: kernel launch failed";
+}
+template <int BN>
+static const char* launch_bn(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
+  return p.colstats ? launch_bn_s<BN, true>(L, p, stream) : launch_bn_s<BN, false>(L, p, stream);
 }
 
 const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
@@ -591,6 +627,8 @@ const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   p.n_tiles = (p.N + L.bn - 1) / L.bn;
   p.fp16 = d.fp16;
   p.num_tiles = L.num_tiles;
+  p.colstats = d.colstats;
+  p.stat_rows = d.stat_rows;
   switch (L.bn) {
     case 16: return launch_bn<16>(L, p, stream);
     case 32: return launch_bn<32>(L, p, stream);

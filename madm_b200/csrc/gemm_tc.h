@@ -42,6 +42,8 @@ struct GemmDesc {
   float alpha = 1.0f;               // scales the accumulator before bias
   int bn = 0;                       // N tile (0 = auto)
   int fp16 = 0;                     // operand / 16-bit output dtype: 0 = bf16, 1 = fp16
+  float* colstats = nullptr;        // optional [ceil(M/32)][N][2] per-column (sum, sumsq) of the outputs per 32-row block (fused GN statistics)
+  int stat_rows = 32;               // rows per statistics block (32: one block per epilogue warp)
 };
 
 struct GemmLaunch {  // prepared launch: tensor maps encoded once, replayed per forward

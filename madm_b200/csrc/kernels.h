@@ -18,7 +18,13 @@ int groupnorm_slabs(int HW, int C);
 const char* groupnorm_stats(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, int fp16, float* partial,
                             cudaStream_t st);
 const char* groupnorm_finalize(const float* partial, int B, int HW, int C, float* stats, cudaStream_t st);
-const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, const float* partial,
+// per-column statistics from a GEMM epilogue (GemmDesc::colstats, 32-row blocks) -> slab partials [B, S, 32, 2] with
+// S = groupnorm_colstats_chunks(nblocks); feed groupnorm_apply(stats_slabs = S) or groupnorm_finalize_slabs
+int groupnorm_colstats_chunks(int nblocks);
+const char* groupnorm_finalize_slabs(const float* partial, int B, int slabs, float* stats, cudaStream_t st);
+const char* groupnorm_colstats_reduce(const float* cs0, int C0, const float* cs1, int C1, int B, int nblocks, float* out, cudaStream_t st);
+// stats_slabs: number of slabs behind `partial` (0 = the geometry of groupnorm_stats for this shape)
+const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, const float* partial, int stats_slabs,
                             const float* gamma, const float* beta, float eps, int act, void* y_bf16, void* raw_bf16,
                             int fp16, cudaStream_t st);
 const char* layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y_bf16,

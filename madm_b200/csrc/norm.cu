@@ -123,6 +123,47 @@ __device__ __forceinline__ void gn_reduce_partials(const float* __restrict__ par
   __syncthreads();
 }
 
+// Statistics fused into the producing GEMM's epilogue arrive as per-column (sum, sumsq) pairs per block of 32 rows:
+// cs[block][c][2].  grid = (S chunks of blocks, B): thread <-> channel (coalesced rows), fixed-order accumulation over the
+// chunk's blocks, then per-group sums -> out[b][chunk][32][2], i.e. the same "slab partial" format gn_stats_kernel writes.
+// The input may be the channel concat of two producers.
+__global__ void gn_colstats_reduce_kernel(const float* __restrict__ cs0, int C0, const float* __restrict__ cs1, int C1, int nb,
+                                          int blocks_per_chunk, float* __restrict__ out /*[B,S,32,2]*/) {
+  extern __shared__ float sm[];  // [C][2]
+  const int chunk = blockIdx.x, S = gridDim.x, b = blockIdx.y;
+  const int C = C0 + C1, cpg = C / 32;
+  const int blk0 = chunk * blocks_per_chunk;
+  const int blk1 = min(nb, blk0 + blocks_per_chunk);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* src = (c < C0) ? cs0 + (size_t(b) * nb * C0 + c) * 2 : cs1 + (size_t(b) * nb * C1 + (c - C0)) * 2;
+    const size_t stride = size_t(c < C0 ? C0 : C1) * 2;
+    float s = 0.f, ss = 0.f;
+    int blk = blk0;
+    for (; blk + 3 < blk1; blk += 4) {
+      const float2 v0 = __ldg(reinterpret_cast<const float2*>(src + size_t(blk) * stride));
+      const float2 v1 = __ldg(reinterpret_cast<const float2*>(src + size_t(blk + 1) * stride));
+      const float2 v2 = __ldg(reinterpret_cast<const float2*>(src + size_t(blk + 2) * stride));
+      const float2 v3 = __ldg(reinterpret_cast<const float2*>(src + size_t(blk + 3) * stride));
+      s += (v0.x + v1.x) + (v2.x + v3.x);
+      ss += (v0.y + v1.y) + (v2.y + v3.y);
+    }
+    for (; blk < blk1; ++blk) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(src + size_t(blk) * stride));
+      s += v.x;
+      ss += v.y;
+    }
+    sm[2 * c] = s;
+    sm[2 * c + 1] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, mom = threadIdx.x & 1;
+    float acc = 0.f;
+    for (int k = 0; k < cpg; ++k) acc += sm[2 * (g * cpg + k) + mom];
+    out[((size_t(b) * S + chunk) * 32 + g) * 2 + mom] = acc;
+  }
+}
+
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int slabs, float* __restrict__ stats /*[B,32,2]*/) {
   __shared__ float red[64];
   gn_reduce_partials(partial, blockIdx.x, slabs, red);
@@ -244,21 +285,44 @@ const char* groupnorm_stats(const void* x0, int C0, const void* x1, int C1, int 
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_stats launch failed";
 }
 
+const char* groupnorm_finalize_slabs(const float* partial, int B, int slabs, float* stats, cudaStream_t st) {
+  gn_finalize_kernel<<<B, 64, 0, st>>>(partial, slabs, stats);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_finalize launch failed";
+}
+
 const char* groupnorm_finalize(const float* partial, int B, int HW, int C, float* stats, cudaStream_t st) {
   gn_finalize_kernel<<<B, 64, 0, st>>>(partial, groupnorm_slabs(HW, C), stats);
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_finalize launch failed";
 }
 
+int groupnorm_colstats_chunks(int nblocks) {
+  int S = nblocks / 8;
+  if (S < 1) S = 1;
+  if (S > 32) S = 32;
+  return S;
+}
+
+const char* groupnorm_colstats_reduce(const float* cs0, int C0, const float* cs1, int C1, int B, int nblocks, float* out, cudaStream_t st) {
+  const int C = C0 + C1;
+  if (C % 32 != 0) return "groupnorm: C must be a multiple of 32";
+  const int S = groupnorm_colstats_chunks(nblocks);
+  const int bpc = (nblocks + S - 1) / S;
+  gn_colstats_reduce_kernel<<<dim3(S, B), 256, size_t(C) * 2 * sizeof(float), st>>>(cs0, C0, cs1, C1, nblocks, bpc, out);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_colstats_reduce launch failed";
+}
+
 const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, const float* partial,
-                            const float* gamma, const float* beta, float eps, int act, void* y, void* raw, int fp16, cudaStream_t st) {
+                            int stats_slabs, const float* gamma, const float* beta, float eps, int act, void* y, void* raw, int fp16,
+                            cudaStream_t st) {
   const int C = C0 + C1;
   int P, threads, ppc, slabs;
   gn_launch_geometry(HW, C, in16, &P, &threads, &ppc, &slabs);
+  const int pslabs = stats_slabs > 0 ? stats_slabs : slabs;  // number of partial-sum slabs behind `partial`
   if (in16)
-    gn_apply_kernel<true><<<dim3(slabs, B), threads, 0, st>>>(x0, C0, x1, C1, HW, ppc, P, partial, slabs, gamma, beta, eps, act, fp16,
+    gn_apply_kernel<true><<<dim3(slabs, B), threads, 0, st>>>(x0, C0, x1, C1, HW, ppc, P, partial, pslabs, gamma, beta, eps, act, fp16,
                                                               reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
   else
-    gn_apply_kernel<false><<<dim3(slabs, B), threads, 0, st>>>(x0, C0, x1, C1, HW, ppc, P, partial, slabs, gamma, beta, eps, act, fp16,
+    gn_apply_kernel<false><<<dim3(slabs, B), threads, 0, st>>>(x0, C0, x1, C1, HW, ppc, P, partial, pslabs, gamma, beta, eps, act, fp16,
                                                                reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_apply launch failed";
 }

@@ -61,7 +61,8 @@ def make_seg(a: torch.Tensor, Bt: int, H: int, W: int, Cc: int, ld: int = 0, tap
 
 def gemm(segs: Sequence[MadmGemmSeg], M: int, N: int, w: torch.Tensor, *, Nw: int = 0, ldw: int = 0,
          bias=None, rowbias=None, rows_per_img: int = 1, ld_rowbias: int = 0, residual=None, ldr: int = 0,
-         out_f32=None, ldo32: int = 0, out_bf16=None, ldo16: int = 0, act: int = 0, alpha: float = 1.0, bn: int = 0):
+         out_f32=None, ldo32: int = 0, out_bf16=None, ldo16: int = 0, act: int = 0, alpha: float = 1.0, bn: int = 0,
+         colstats=None, stat_rows: int = 0):
     a = MadmGemmArgs()
     a.nseg = len(segs)
     for i, s in enumerate(segs):
@@ -79,6 +80,8 @@ def gemm(segs: Sequence[MadmGemmSeg], M: int, N: int, w: torch.Tensor, *, Nw: in
     a.ldo16 = ldo16
     a.act, a.alpha, a.bn = act, alpha, bn
     a.dtype = _dt(w.dtype)
+    a.colstats = colstats.data_ptr() if colstats is not None else None
+    a.stat_rows = stat_rows
     lib = _lib.load()
     _lib.check(lib.madm_op_gemm(C.byref(a), _stream()), None, "madm_op_gemm")
 
@@ -92,6 +95,15 @@ def groupnorm(x0, x1, B, HW, gamma, beta, eps, act, y, raw=None):
     _lib.check(lib.madm_op_groupnorm(_ptr(x0), C0, _ptr(x1), C1, B, HW, in16, _ptr(gamma), _ptr(beta), eps, act, _ptr(stats),
                                      _ptr(y), _ptr(raw), _dt(y.dtype), _stream()), None, "madm_op_groupnorm")
     return stats
+
+
+def groupnorm_from_colstats(x, B, HW, colstats, stat_rows, gamma, beta, eps, act, y):
+    lib = _lib.load()
+    Cc = x.shape[-1]
+    scratch = torch.empty(B * 32 * 64, dtype=torch.float32, device=x.device)
+    in16 = 0 if x.dtype == torch.float32 else 1
+    _lib.check(lib.madm_op_groupnorm_from_colstats(_ptr(x), Cc, B, HW, in16, _ptr(colstats), stat_rows, _ptr(gamma), _ptr(beta), eps, act,
+                                                   _ptr(scratch), _ptr(y), _dt(y.dtype), _stream()), None, "madm_op_groupnorm_from_colstats")
 
 
 def layernorm(x, gamma, beta, eps, y):

@@ -234,6 +234,39 @@ def test_groupnorm_16bit_input(ops, cuda_device, B, HW, Cc):
     assert relerr(y, ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,bn", [(2, 32, 32, 128, 320, 0), (3, 8, 8, 128, 1280, 0), (1, 64, 64, 64, 128, 0), (2, 16, 16, 128, 640, 128),
+                                                (2, 16, 16, 64, 512, 256)])
+def test_gemm_fused_groupnorm_statistics(ops, cuda_device, B, H, W, Cin, Cout, bn):
+    """The GEMM epilogue emits per-column (sum, sumsq) of its outputs; GroupNorm of the consumer uses them instead of a
+    statistics pass.  Checked against F.group_norm on the GEMM's own fp32 output, and for bit-exact repeatability."""
+    g = torch.Generator(device="cuda").manual_seed(Cout + H)
+    x = bf(torch.randn(B, Cin, H, W, device=cuda_device, generator=g))
+    w = torch.randn(Cout, Cin, 3, 3, device=cuda_device, generator=g) / math.sqrt(9 * Cin)
+    bias = torch.randn(Cout, device=cuda_device, generator=g)
+    res = torch.randn(B * H * W, Cout, device=cuda_device, generator=g)
+    wp = ops.pack_conv(w, dtype=DT)
+    a = nhwc(x)
+    M, HW = B * H * W, H * W
+    sr = 32
+    out = torch.empty(M, Cout, device=cuda_device)
+    cs = torch.full((M // sr, Cout, 2), float("nan"), device=cuda_device)
+    ops.gemm([ops.make_seg(a, B, H, W, Cin, taps=ops.taps_3x3())], M, Cout, wp, bias=bias, residual=res, ldr=Cout, out_f32=out, ldo32=Cout,
+             colstats=cs, stat_rows=sr, bn=bn)
+    blocks = out.reshape(M // sr, sr, Cout)
+    assert relerr(cs[..., 0], blocks.sum(1)) < 1e-4
+    assert relerr(cs[..., 1], (blocks * blocks).sum(1)) < 1e-4
+    gamma = torch.randn(Cout, device=cuda_device, generator=g)
+    beta = torch.randn(Cout, device=cuda_device, generator=g)
+    y = torch.empty(B, HW, Cout, dtype=DT, device=cuda_device)
+    ops.groupnorm_from_colstats(out.reshape(B, HW, Cout), B, HW, cs, sr, gamma, beta, 1e-5, 1, y)
+    ref = F.silu(F.group_norm(out.reshape(B, HW, Cout).permute(0, 2, 1), 32, gamma, beta, 1e-5).permute(0, 2, 1))
+    assert relerr(y, ref) < 1e-2
+    cs2 = torch.empty_like(cs)
+    ops.gemm([ops.make_seg(a, B, H, W, Cin, taps=ops.taps_3x3())], M, Cout, wp, bias=bias, residual=res, ldr=Cout, out_f32=out, ldo32=Cout,
+             colstats=cs2, stat_rows=sr, bn=bn)
+    assert torch.equal(cs, cs2)
+
+
 @pytest.mark.parametrize("M,Cc", [(4096, 320), (1000, 640), (77, 1280)])
 def test_layernorm(ops, cuda_device, M, Cc):
     g = torch.Generator(device="cuda").manual_seed(Cc)
