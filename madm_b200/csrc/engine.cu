@@ -224,6 +224,7 @@ struct Builder {
     for (int sgi = 0; sgi < d.nseg; ++sgi) K += d.seg[sgi].ntaps * d.seg[sgi].C;
     static const int kmin = getenv("MADM_FUSE_STATS_KMIN") ? atoi(getenv("MADM_FUSE_STATS_KMIN")) : 0;
     if (K < kmin) return;
+    if (!getenv("MADM_NO_SPLITK") && choose_splits(d) > 1) return;  // split-K launches leave the statistics to a separate pass
     const size_t n = size_t((a.M() + a.sr - 1) / a.sr) * a.C * 2;
     a.cs = stats_base ? stats_base + stats_used : nullptr;
     stats_used += n;
@@ -330,7 +331,48 @@ struct Builder {
     }
   }
   // algo_flops < 0: 2*M*N*K from the descriptor (K counts real channels only when k_real is given)
+  // split-K factor for a GEMM whose M x N tiling cannot fill the 148 SMs (8x8-resolution convs, small batches): the K range
+  // is divided over `splits` CTAs per output tile; raw fp32 partials are reduced in fixed order by splitk_reduce, which
+  // also applies the fused epilogue.  Deterministic (no atomics).
+  static int choose_splits(const GemmDesc& d) {
+    if (d.act == ACT_GEGLU || d.N % 4 != 0 || d.N < 128) return 1;
+    const int tiles = ((d.M + 127) / 128) * ((d.N + 127) / 128);  // the split launch uses 128-wide N tiles
+    int chunks = 0;
+    for (int sgi = 0; sgi < d.nseg; ++sgi) chunks += d.seg[sgi].ntaps * d.seg[sgi].C / 64;
+    if (tiles > 74 || chunks < 32) return 1;
+    int s = 148 / tiles;
+    if (s > chunks / 16) s = chunks / 16;
+    if (s > 8) s = 8;
+    return s < 2 ? 1 : s;
+  }
+
   void gemm(const GemmDesc& d0, double algo_flops = -1.0) {
+    const int splits = getenv("MADM_NO_SPLITK") ? 1 : choose_splits(d0);
+    if (splits > 1) {  // identical allocation sequence in every builder mode
+      F32T part = f32(size_t(splits) * d0.M * d0.N);
+      if (mode == PLAN) {
+        GemmDesc d = d0;
+        d.fp16 = ctx->fp16;
+        d.bias = nullptr; d.rowbias = nullptr; d.residual = nullptr; d.out_bf16 = nullptr; d.act = ACT_NONE; d.colstats = nullptr; d.alpha = 1.0f;
+        d.out_f32 = part.p; d.ldo32 = d0.N; d.splits = splits; d.split_stride = long(d0.M) * d0.N; d.bn = 128;
+        GemmLaunch L;
+        if (const char* e = gemm_prepare(d, &L)) fail(MADM_EINVAL, std::string(e));
+        double K = 0;
+        for (int sgi = 0; sgi < d.nseg; ++sgi) K += double(d.seg[sgi].ntaps) * d.seg[sgi].C;
+        if (algo_flops < 0) algo_flops = 2.0 * double(d.M) * d.N * K;
+        emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, 0.0);
+        const GemmDesc e0 = d0; const float* pp = part.p; const int f16 = ctx->fp16; const long ss = d.split_stride;
+        if (e0.alpha != 1.0f) fail(MADM_EINVAL, "split-K with alpha != 1 is not supported");
+        emit([=](cudaStream_t st) {
+          return splitk_reduce(pp, splits, ss, e0.M, e0.N, e0.bias, e0.rowbias, e0.rows_per_img, e0.ld_rowbias, e0.residual, e0.ldr, e0.out_f32,
+                               e0.ldo32, e0.out_bf16, e0.ldo16, e0.act, f16, st);
+        }, false, MADM_KIND_ELEMENTWISE, 0.0, double(splits + 2) * e0.M * e0.N * 4);
+      } else {
+        n_ops += 2;
+      }
+      free(part);
+      return;
+    }
     if (mode != PLAN) { ++n_ops; return; }
     GemmDesc d = d0;
     d.fp16 = ctx->fp16;

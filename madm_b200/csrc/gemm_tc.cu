@@ -56,6 +56,8 @@ struct GemmParams {
   int n_tiles;
   int fp16;
   int num_tiles;
+  int splits;        // split-K factor: tile t covers K range (t % splits) of output tile (t / splits) and writes raw partials
+  long split_stride; // elements between the partial outputs of consecutive splits (out_f32 + split * split_stride)
   float* colstats;   // [ceil(M/32)][N][2] per-column (sum, sum of squares) of the stored outputs per 32-row block, or null
   int stat_rows;     // always 32 (one block per epilogue warp)
 };
@@ -182,9 +184,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const int tile_n = t % p.n_tiles;
-        const int m0 = (t / p.n_tiles) * BM;
+        const int mn = t / p.splits, sp = t - mn * p.splits;
+        const int tile_n = mn % p.n_tiles;
+        const int m0 = (mn / p.n_tiles) * BM;
         const int n0 = tile_n * BN;
+        const int kc0 = (total_chunks * sp) / p.splits, kc1 = (total_chunks * (sp + 1)) / p.splits;
         int x0, y0, b0;
         if (p.pix >= BM) {
           b0 = m0 / p.pix;
@@ -196,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           y0 = 0;
           x0 = 0;
         }
-        for (int kc = 0; kc < total_chunks; ++kc) {
+        for (int kc = kc0; kc < kc1; ++kc) {
           const int seg = (kc < p.kchunks[0]) ? 0 : 1;
           const int lk = seg ? kc - p.kchunks[0] : kc;
           const int tap = lk / p.cpt[seg];
@@ -225,7 +229,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + uint32_t(acc * C::ACC_STRIDE);
-        for (int kc = 0; kc < total_chunks; ++kc) {
+        const int sp = t % p.splits;
+        const int kc0 = (total_chunks * sp) / p.splits, kc1 = (total_chunks * (sp + 1)) / p.splits;
+        for (int kc = kc0; kc < kc1; ++kc) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc_sw128(sA + stage * A_STAGE_BYTES);
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 32 B (16 elements) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16_ss(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kc | k) != 0);
+            umma_bf16_ss(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kc > kc0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
           if (++stage == C::STAGES) {
@@ -260,18 +266,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const float* const rowbias = p.rowbias;
     const int rows_per_img = p.rows_per_img, ld_rowbias = p.ld_rowbias;
     const float* const residual = p.residual;
-    float* const out32 = p.out_f32;
     uint16_t* const out16 = reinterpret_cast<uint16_t*>(p.out_bf16);
     const int ldr = p.ldr, ldo32 = p.ldo32, ldo16 = p.ldo16;
-    const int mode = (residual ? 4 : 0) | (out32 ? 2 : 0) | (out16 ? 1 : 0);
+    const int mode = (residual ? 4 : 0) | (p.out_f32 ? 2 : 0) | (out16 ? 1 : 0);
     constexpr bool do_stats = STATS;  // compile-time: the statistics-free variant keeps the tighter rolled chunk loop
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t r[32];
+    float* const out32_base = p.out_f32;
+    const int splits = p.splits;
+    const long split_stride = p.split_stride;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const int tile_n = t % n_tiles;
-      const int m0 = (t / n_tiles) * BM;
+      const int mn = t / splits;
+      const int tile_n = mn % n_tiles;
+      const int m0 = (mn / n_tiles) * BM;
       const int n0 = tile_n * BN;
+      float* const out32 = out32_base ? out32_base + long(t - mn * splits) * split_stride : nullptr;
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * C::ACC_STRIDE);
@@ -493,6 +503,12 @@ static int pick_bn(const GemmDesc& d) {
   return best;
 }
 
+int gemm_auto_tiles(const GemmDesc& d) {
+  const int bn = d.bn ? d.bn : pick_bn(d);
+  const int Ncols = (d.act == ACT_GEGLU) ? 2 * d.N : d.N;
+  return ((d.M + BM - 1) / BM) * ((Ncols + bn - 1) / bn);
+}
+
 const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   GemmLaunch& L = *out;
   L.d = d;
@@ -558,7 +574,15 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   const int Ncols = (d.act == ACT_GEGLU) ? 2 * d.N : d.N;
   const int n_tiles = (Ncols + L.bn - 1) / L.bn;
   const int m_tiles = (d.M + BM - 1) / BM;
-  L.num_tiles = n_tiles * m_tiles;
+  L.splits = 1;
+  L.split_stride = 0;
+  if (d.splits > 1) {  // split-K: raw fp32 partials, reduced (with the fused epilogue) by splitk_reduce
+    if (d.bias || d.rowbias || d.residual || d.out_bf16 || d.act != ACT_NONE || d.colstats || d.alpha != 1.0f || !d.out_f32)
+      return "gemm: a split-K launch writes raw fp32 partials only";
+    L.splits = d.splits;
+    L.split_stride = d.split_stride;
+  }
+  L.num_tiles = n_tiles * m_tiles * L.splits;
   L.grid = dim3(unsigned(L.num_tiles < num_sms() ? L.num_tiles : num_sms()));
   switch (L.bn) {
     case 16: L.smem = Cfg<16>::SMEM; break;
@@ -629,6 +653,8 @@ const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   p.num_tiles = L.num_tiles;
   p.colstats = d.colstats;
   p.stat_rows = d.stat_rows;
+  p.splits = L.splits;
+  p.split_stride = L.split_stride;
   switch (L.bn) {
     case 16: return launch_bn<16>(L, p, stream);
     case 32: return launch_bn<32>(L, p, stream);

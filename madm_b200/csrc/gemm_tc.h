@@ -42,6 +42,8 @@ struct GemmDesc {
   float alpha = 1.0f;               // scales the accumulator before bias
   int bn = 0;                       // N tile (0 = auto)
   int fp16 = 0;                     // operand / 16-bit output dtype: 0 = bf16, 1 = fp16
+  int splits = 1;                   // split-K factor (>1: raw fp32 partial outputs at out_f32 + split * split_stride)
+  long split_stride = 0;
   float* colstats = nullptr;        // optional [ceil(M/32)][N][2] per-column (sum, sumsq) of the outputs per 32-row block (fused GN statistics)
   int stat_rows = 32;               // rows per statistics block (32: one block per epilogue warp)
 };
@@ -56,11 +58,15 @@ struct GemmLaunch {  // prepared launch: tensor maps encoded once, replayed per 
   int box_w = 128, box_h = 1, box_b = 1;
   dim3 grid;
   int num_tiles = 0;
+  int splits = 1;
+  long split_stride = 0;
   size_t smem = 0;
 };
 
 // Returns nullptr on success, else a static error string.
 const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out);
 const char* gemm_launch(const GemmLaunch& l, cudaStream_t stream);
+// tiles (M/128 x N/BN) the auto-selected N tile would give: used by the planner to decide on split-K
+int gemm_auto_tiles(const GemmDesc& d);
 
 }  // namespace madm

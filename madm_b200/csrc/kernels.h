@@ -68,6 +68,10 @@ const char* f32_to_bf16(const float* x, const float* add_or_null, long n, int ac
 const char* space_to_depth(const float* x, int B, int H, int W, int C, void* out_bf16, int fp16, cudaStream_t st);
 // fp32 NHWC [B,H,W,C] -> nearest 2x bf16 [B,2H,2W,C]
 const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void* out_bf16, int fp16, cudaStream_t st);
+// split-K: out = act(sum_s partial[s] + bias + rowbias + residual), partial[s] = part + s*split_stride, each [M,N] fp32
+const char* splitk_reduce(const float* part, int splits, long split_stride, int M, int N, const float* bias, const float* rowbias,
+                          int rows_per_img, int ld_rowbias, const float* residual, int ldr, float* out32, int ldo32, void* out16, int ldo16,
+                          int act, int fp16, cudaStream_t st);
 // fp32 NHWC [B,HW,C] -> NCHW fp32 [B,C,HW]
 const char* nhwc_to_nchw(const float* x, int B, int HW, int C, float* out, cudaStream_t st);
 

@@ -127,9 +127,10 @@ def test_golden_fixture_config1(pair, cuda_device):
 
 
 def test_batch_independence_at_full_batch(pair, cuda_device):
-    """Size-independent property at BASELINE configs[1] size (8x3x512x512): every image is processed independently and no
-    kernel uses atomics (GroupNorm statistics are fixed-order per-slab partial sums whose geometry does not depend on B),
-    so image i of a batch-8 call is BIT-IDENTICAL to the batch-1 call on that image, and repeated calls are bit-identical."""
+    """Size-independent property at BASELINE configs[1] size (8x3x512x512): every image is processed independently, so image i
+    of a batch-8 call must equal the batch-1 call on that image.  No kernel uses atomics, so repeated calls are BIT-IDENTICAL;
+    across batch sizes the only difference is the split-K factor the planner picks for under-filled GEMMs (fp32 summation
+    order), i.e. rounding-level noise far below the parity gate (bit-identical with MADM_NO_SPLITK=1)."""
     from oracle import synthetic
     ob, pb = pair
     set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
@@ -139,7 +140,7 @@ def test_batch_independence_at_full_batch(pair, cuda_device):
         for i in (0, 7):
             f1 = pb._extract(img8[i:i + 1], "others", False, None)["features"]
             for a, b in zip(f8, f1):
-                assert torch.equal(a[i:i + 1], b)
+                assert max_rel(a[i:i + 1], b) < (3e-3 if _MODE == "fp16" else REL_MAX[_MODE])  # operand-rounding noise level
         f8b = pb._extract(img8, "others", False, None)["features"]
         for a, b in zip(f8, f8b):
             assert torch.equal(a, b)  # run-to-run determinism
