@@ -37,6 +37,10 @@ class Engine:
         self._ws: Optional[torch.Tensor] = None
         self._keep = []
         self.range_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        # CUDA graphs: at small batch the ~550 launches of one forward are CPU-launch-bound; one graph per call signature
+        # replays them.  graph_max_batch: largest B that is graphed (0 disables).
+        self.graph_max_batch = 4
+        self._graphs: Dict[Tuple, Dict[str, object]] = {}
 
     def __del__(self):
         try:
@@ -97,8 +101,42 @@ class Engine:
             _lib.check(-1, self.ctx, "madm_workspace_bytes")
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
+            self._graphs.clear()  # captured graphs hold the old workspace pointer
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
+
+    def extract_graphed(self, img, cond_inputs, cond_emb, timesteps, shared_noise, *, ema=False, stages=STAGE_ALL, want_taps=False,
+                        want_latents=False):
+        """`extract` through a captured CUDA graph (static input / output buffers, one graph per call signature)."""
+        B = img.shape[0]
+        key = (B, bool(ema), stages, bool(want_taps), bool(want_latents), self._packed.data_ptr(), shared_noise.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            st = dict(img=torch.empty_like(img, dtype=torch.float32), cond_inputs=torch.empty(B, 77, 768, device=self.device),
+                      cond_emb=torch.empty(B, 1280, device=self.device), timesteps=torch.zeros(B, dtype=torch.int64, device=self.device))
+            for k, v in (("img", img), ("cond_inputs", cond_inputs), ("cond_emb", cond_emb), ("timesteps", timesteps)):
+                st[k].copy_(v)
+            kw = dict(ema=ema, stages=stages, want_taps=want_taps, want_latents=want_latents)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside capture: plan build, cudaFuncSetAttribute, allocations
+                self.extract(st["img"], st["cond_inputs"], st["cond_emb"], st["timesteps"], shared_noise, **kw)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                res = self.extract(st["img"], st["cond_inputs"], st["cond_emb"], st["timesteps"], shared_noise, **kw)
+            g = dict(graph=graph, static=st, res=res)
+            self._graphs[key] = g
+        st = g["static"]
+        st["img"].copy_(img)
+        st["cond_inputs"].copy_(cond_inputs)
+        st["cond_emb"].copy_(cond_emb)
+        st["timesteps"].copy_(timesteps)
+        g["graph"].replay()
+        out = {}
+        for k, v in g["res"].items():  # fresh tensors, like the eager path: the static buffers are overwritten by the next replay
+            out[k] = [t.clone() for t in v] if isinstance(v, list) else v.clone()
+        return out
 
     # ------------------------------------------------------------------ the hot path
     def extract(self, img: Optional[torch.Tensor], cond_inputs: torch.Tensor, cond_emb: torch.Tensor, timesteps: torch.Tensor,

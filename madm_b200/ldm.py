@@ -179,6 +179,9 @@ class LdmDiffusers(nn.Module):
         if cond_emb.shape[0] == 1 and bsz > 1:
             cond_emb = cond_emb.expand(bsz, -1)
         self._serial += 1
+        if out is None and 0 < bsz <= eng.graph_max_batch and stages == _lib.STAGE_ALL and tuple(images.shape[1:]) == (3, 512, 512):
+            return eng.extract_graphed(images.float(), cond_inputs, cond_emb, timesteps, self.shared_noise, ema=ema_projections,
+                                       stages=stages, want_taps=want_taps, want_latents=want_latents)
         return eng.extract(images, cond_inputs, cond_emb, timesteps, self.shared_noise, ema=ema_projections, stages=stages,
                            want_taps=want_taps, want_latents=want_latents, out=out)
 
