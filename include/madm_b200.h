@@ -168,6 +168,7 @@ typedef struct madm_gemm_args {
   float* colstats;        /* optional [ceil(M/32)][N][2]: per-column (sum, sum of squares) of the stored outputs per 32-row block,
                              i.e. the GroupNorm statistics of the consumer fused into this epilogue (no atomics) */
   int32_t stat_rows;      /* 32 (0 = 32) */
+  int32_t mt;             /* M sub-tiles per CTA tile when bn = 128: 0 auto, 1 (128-row tiles), 2 (256-row tiles) */
 } madm_gemm_args;
 
 int madm_op_gemm(const madm_gemm_args* a, madm_stream stream);

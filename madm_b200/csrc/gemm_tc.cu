@@ -62,20 +62,40 @@ struct GemmParams {
   int stat_rows;     // always 32 (one block per epilogue warp)
 };
 
-template <int BN>
+// MT = M sub-tiles (128 rows each) per CTA tile.  MT = 2 loads one W box per K chunk for two A boxes (tile 256 x BN): the
+// L2->SM operand traffic per FLOP drops from (128+BN) to (256+BN)/2 bytes-equivalents, which is what bounds the BN = 128
+// layers (measured 12.7 TB/s of L2->SM reads at 42 % tensor-pipe activity on the VAE 512^2 convs).
+template <int BN, int MT>
 struct Cfg {
+  static constexpr int A_BYTES = MT * A_STAGE_BYTES;
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_BYTES = kEpiWarps * STG_WARP_BYTES;  // per-epilogue-warp transpose staging
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - EPI_BYTES;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
   static constexpr int ACC_STRIDE = BN <= 16 ? 16 : (BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256)));
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE < 32 ? 32 : 2 * ACC_STRIDE;  // two accumulator stages
+  static constexpr int TMEM_COLS = 2 * MT * ACC_STRIDE < 32 ? 32 : 2 * MT * ACC_STRIDE;  // two accumulator stages x MT sub-tiles
   static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+  static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
-__device__ __forceinline__ float gelu_erf_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+// exact (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. fp32-exact for a 16-bit output):
+// 5 FMAs + one MUFU.RCP + one MUFU.EX2 instead of libdevice erff's branchy ~25-instruction polynomial.
+__device__ __forceinline__ float gelu_erf_f(float v) {
+  const float x = fabsf(v) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, x, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-x * x * 1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  return 0.5f * v * (1.0f + copysignf(erf_abs, v));
+}
 __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -134,13 +154,13 @@ __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int 
 //               i+1 overlap the epilogue of tile i
 //   warps 2..5  epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> coalesced fused epilogue
 //               (bias / time-embedding row bias / fp32 residual / SiLU / ReLU / GEGLU) -> fp32 and/or 16-bit stores
-template <int BN, bool STATS>
+template <int BN, int MT, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
-  const uint32_t sB = smem_base + C::STAGES * A_STAGE_BYTES;
+  const uint32_t sB = smem_base + C::STAGES * C::A_BYTES;
   const uint32_t sEpi = sB + C::STAGES * C::B_STAGE_BYTES;
   const uint32_t sBar = sEpi + C::EPI_BYTES;  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_addr
   auto full_bar = [&](int s) { return sBar + 8u * s; };
@@ -186,19 +206,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const int mn = t / p.splits, sp = t - mn * p.splits;
         const int tile_n = mn % p.n_tiles;
-        const int m0 = (mn / p.n_tiles) * BM;
+        const int m0 = (mn / p.n_tiles) * (BM * MT);
         const int n0 = tile_n * BN;
         const int kc0 = (total_chunks * sp) / p.splits, kc1 = (total_chunks * (sp + 1)) / p.splits;
-        int x0, y0, b0;
-        if (p.pix >= BM) {
-          b0 = m0 / p.pix;
-          const int rem = m0 - b0 * p.pix;
-          y0 = rem / p.W;
-          x0 = rem - y0 * p.W;
-        } else {
-          b0 = m0 / p.pix;
-          y0 = 0;
-          x0 = 0;
+        int x0[MT], y0[MT], b0[MT];
+#pragma unroll
+        for (int s = 0; s < MT; ++s) {
+          const int ms = m0 + s * BM;
+          if (p.pix >= BM) {
+            b0[s] = ms / p.pix;
+            const int rem = ms - b0[s] * p.pix;
+            y0[s] = rem / p.W;
+            x0[s] = rem - y0[s] * p.W;
+          } else {
+            b0[s] = ms / p.pix;
+            y0[s] = 0;
+            x0[s] = 0;
+          }
         }
         for (int kc = kc0; kc < kc1; ++kc) {
           const int seg = (kc < p.kchunks[0]) ? 0 : 1;
@@ -207,8 +231,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int cc = lk - tap * p.cpt[seg];
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          tma_load_4d(sA + stage * A_STAGE_BYTES, &p.tmA[seg], full_bar(stage), cc * BK, x0 + p.dx[seg][tap],
-                      y0 + p.dy[seg][tap], b0 + p.boff[seg][tap]);
+#pragma unroll
+          for (int s = 0; s < MT; ++s)
+            tma_load_4d(sA + stage * C::A_BYTES + s * A_STAGE_BYTES, &p.tmA[seg], full_bar(stage), cc * BK, x0[s] + p.dx[seg][tap],
+                        y0[s] + p.dy[seg][tap], b0[s] + p.boff[seg][tap]);
           tma_load_2d(sB + stage * C::B_STAGE_BYTES, &p.tmB, full_bar(stage), kc * BK, n0);
           if (++stage == C::STAGES) {
             stage = 0;
@@ -228,18 +254,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t tacc = tmem_base + uint32_t(acc * C::ACC_STRIDE);
+        const uint32_t tacc = tmem_base + uint32_t(acc * MT * C::ACC_STRIDE);
         const int sp = t % p.splits;
         const int kc0 = (total_chunks * sp) / p.splits, kc1 = (total_chunks * (sp + 1)) / p.splits;
         for (int kc = kc0; kc < kc1; ++kc) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc_sw128(sA + stage * A_STAGE_BYTES);
           const uint64_t bdesc = make_smem_desc_sw128(sB + stage * C::B_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 32 B (16 elements) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16_ss(tacc, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+          for (int s = 0; s < MT; ++s) {
+            const uint64_t adesc = make_smem_desc_sw128(sA + stage * C::A_BYTES + s * A_STAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 32 B (16 elements) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+              umma_bf16_ss(tacc + uint32_t(s * C::ACC_STRIDE), adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
+                           (kc > kc0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
           if (++stage == C::STAGES) {
@@ -279,13 +309,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const int mn = t / splits;
       const int tile_n = mn % n_tiles;
-      const int m0 = (mn / n_tiles) * BM;
+      const int m0 = (mn / n_tiles) * (BM * MT);
       const int n0 = tile_n * BN;
       float* const out32 = out32_base ? out32_base + long(t - mn * splits) * split_stride : nullptr;
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * C::ACC_STRIDE);
-      const int row0 = m0 + q * 32;  // first row of this warp's 32-row block
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {  // M sub-tiles of this CTA tile
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t((acc * MT + sub) * C::ACC_STRIDE);
+      const int row0 = m0 + sub * BM + q * 32;  // first row of this warp's 32-row block
 
       if constexpr (BN < 32) {
         // narrow tile (latent head, N = 4 of 16): one row per thread, scalar stores
@@ -413,6 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
         }
       }
+      }  // sub-tiles
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -573,7 +606,14 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   }
   const int Ncols = (d.act == ACT_GEGLU) ? 2 * d.N : d.N;
   const int n_tiles = (Ncols + L.bn - 1) / L.bn;
-  const int m_tiles = (d.M + BM - 1) / BM;
+  // 256-row CTA tiles (two M sub-tiles sharing each W box) for the 128-wide N tile when there is enough work to keep every SM
+  // busy with the larger tiles
+  L.mt = 1;
+  if (L.bn == 128 && d.mt != 1) {
+    const long tiles2 = long((d.M + 2 * BM - 1) / (2 * BM)) * n_tiles;
+    if (d.mt == 2 || tiles2 >= 2L * num_sms()) L.mt = 2;
+  }
+  const int m_tiles = (d.M + BM * L.mt - 1) / (BM * L.mt);
   L.splits = 1;
   L.split_stride = 0;
   if (d.splits > 1) {  // split-K: raw fp32 partials, reduced (with the fused epilogue) by splitk_reduce
@@ -585,32 +625,35 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   L.num_tiles = n_tiles * m_tiles * L.splits;
   L.grid = dim3(unsigned(L.num_tiles < num_sms() ? L.num_tiles : num_sms()));
   switch (L.bn) {
-    case 16: L.smem = Cfg<16>::SMEM; break;
-    case 32: L.smem = Cfg<32>::SMEM; break;
-    case 64: L.smem = Cfg<64>::SMEM; break;
-    case 128: L.smem = Cfg<128>::SMEM; break;
-    case 160: L.smem = Cfg<160>::SMEM; break;
-    case 192: L.smem = Cfg<192>::SMEM; break;
-    case 256: L.smem = Cfg<256>::SMEM; break;
+    case 16: L.smem = Cfg<16, 1>::SMEM; break;
+    case 32: L.smem = Cfg<32, 1>::SMEM; break;
+    case 64: L.smem = Cfg<64, 1>::SMEM; break;
+    case 128: L.smem = L.mt == 2 ? Cfg<128, 2>::SMEM : Cfg<128, 1>::SMEM; break;
+    case 160: L.smem = Cfg<160, 1>::SMEM; break;
+    case 192: L.smem = Cfg<192, 1>::SMEM; break;
+    case 256: L.smem = Cfg<256, 1>::SMEM; break;
     default: return "gemm: unsupported N tile";
   }
   return nullptr;
 }
 
-template <int BN, bool STATS>
+template <int BN, int MT, bool STATS>
 static const char* launch_bn_s(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BN>::SMEM)) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, MT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BN, MT>::SMEM)) != cudaSuccess)
       return "gemm: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     attr_set = true;
   }
-  gemm_tc_kernel<BN, STATS><<<L.grid, kThreads, Cfg<BN>::SMEM, stream>>>(p);
+  gemm_tc_kernel<BN, MT, STATS><<<L.grid, kThreads, Cfg<BN, MT>::SMEM, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? nullptr : "gemm: kernel launch failed";
 }
 template <int BN>
 static const char* launch_bn(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
-  return p.colstats ? launch_bn_s<BN, true>(L, p, stream) : launch_bn_s<BN, false>(L, p, stream);
+  if constexpr (BN == 128) {
+    if (L.mt == 2) return p.colstats ? launch_bn_s<BN, 2, true>(L, p, stream) : launch_bn_s<BN, 2, false>(L, p, stream);
+  }
+  return p.colstats ? launch_bn_s<BN, 1, true>(L, p, stream) : launch_bn_s<BN, 1, false>(L, p, stream);
 }
 
 const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {

@@ -42,6 +42,7 @@ struct GemmDesc {
   float alpha = 1.0f;               // scales the accumulator before bias
   int bn = 0;                       // N tile (0 = auto)
   int fp16 = 0;                     // operand / 16-bit output dtype: 0 = bf16, 1 = fp16
+  int mt = 0;                       // M sub-tiles per CTA tile for the 128-wide N tile: 0 auto, 1, or 2 (256-row tiles)
   int splits = 1;                   // split-K factor (>1: raw fp32 partial outputs at out_f32 + split * split_stride)
   long split_stride = 0;
   float* colstats = nullptr;        // optional [ceil(M/32)][N][2] per-column (sum, sumsq) of the outputs per 32-row block (fused GN statistics)
@@ -58,6 +59,7 @@ struct GemmLaunch {  // prepared launch: tensor maps encoded once, replayed per 
   int box_w = 128, box_h = 1, box_b = 1;
   dim3 grid;
   int num_tiles = 0;
+  int mt = 1;
   int splits = 1;
   long split_stride = 0;
   size_t smem = 0;

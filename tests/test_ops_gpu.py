@@ -55,6 +55,35 @@ def test_gemm_plain(ops, cuda_device, M, K, N, bn):
     assert relerr(o16, ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 128, 128), (1, 8, 128, 64, 128), (3, 8, 8, 128, 256), (1, 16, 16, 64, 640), (1, 16, 24, 64, 128)])
+def test_conv3x3_256row_tiles(ops, cuda_device, B, H, W, Cin, Cout):
+    """bn = 128 with two M sub-tiles per CTA (256-row tiles sharing each weight box), incl. ragged M and fused statistics."""
+    g = torch.Generator(device="cuda").manual_seed(B * 10 + H + Cout)
+    if W == 24:  # plain matrix with M not a multiple of 256
+        M, K = 1000, 320
+        a = bf(torch.randn(M, K, device=cuda_device, generator=g))
+        w = bf(torch.randn(Cout, K, device=cuda_device, generator=g) / math.sqrt(K))
+        out = torch.empty(M, Cout, device=cuda_device)
+        ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, Cout, w, out_f32=out, ldo32=Cout, bn=128, mt=2)
+        assert relerr(out, a.float() @ w.float().t()) < 2e-3
+        return
+    x = bf(torch.randn(B, Cin, H, W, device=cuda_device, generator=g))
+    w = torch.randn(Cout, Cin, 3, 3, device=cuda_device, generator=g) / math.sqrt(9 * Cin)
+    bias = torch.randn(Cout, device=cuda_device, generator=g)
+    wp = ops.pack_conv(w, dtype=DT)
+    a = nhwc(x)
+    M = B * H * W
+    out = torch.empty(M, Cout, device=cuda_device)
+    o16 = torch.empty(M, Cout, dtype=DT, device=cuda_device)
+    cs = torch.full((M // 32, Cout, 2), float("nan"), device=cuda_device)
+    ops.gemm([ops.make_seg(a, B, H, W, Cin, taps=ops.taps_3x3())], M, Cout, wp, bias=bias, out_f32=out, ldo32=Cout, out_bf16=o16, ldo16=Cout,
+             colstats=cs, stat_rows=32, bn=128, mt=2)
+    ref = nhwc(F.conv2d(x.float(), bf(w).float(), bias, padding=1)).reshape(M, Cout)
+    assert relerr(out, ref) < 2e-3
+    assert relerr(o16, ref) < 1e-2
+    assert relerr(cs[..., 0], out.reshape(M // 32, 32, Cout).sum(1)) < 1e-4
+
+
 def test_gemm_epilogue_variants(ops, cuda_device):
     g = torch.Generator(device="cuda").manual_seed(5)
     B, HW, K, N = 3, 256, 128, 320
