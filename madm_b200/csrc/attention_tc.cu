@@ -62,6 +62,27 @@ __device__ __forceinline__ float fa_ex2(float x) {
   return y;
 }
 
+// p = 2^x for two arguments at once on the packed 16-bit MUFU path (one MUFU op per pair instead of two, and the result is
+// already the 16-bit operand the P V MMA consumes).  The subtraction of the running max is done in fp32 by the caller, so
+// x <= 0 and the arguments that matter (x near 0) are converted with an absolute error <= 2^-12.
+template <bool FP16>
+__device__ __forceinline__ uint32_t ex2_pair16(float x0, float x1) {
+  uint32_t h, r;
+  if constexpr (FP16) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
+  } else {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+    asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(h));
+  }
+  return r;
+}
+template <bool FP16>
+__device__ __forceinline__ float2 unpack16(uint32_t v) {
+  if constexpr (FP16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+  else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
+
 // smem descriptor of an MN-major (N contiguous) 128B-swizzled B operand: 8-row (K) atoms of 1024 B (SBO), 64-element N groups
 // `lbo_bytes` apart.
 __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -76,7 +97,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, 
 
 // NQT query tiles (128 rows each) per CTA share every K/V tile; each query tile has its own softmax warpgroup, S / O tiles in
 // TMEM and P buffer, so the softmax of one tile overlaps the MMAs (and the softmax) of the other.
-template <int D, int NQT>
+template <int D, int NQT, bool FP16>
 __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const __grid_constant__ FaParams p) {
   using C = FaCfg<D, NQT>;
   extern __shared__ uint8_t smem_raw[];
@@ -153,8 +174,8 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_16(FA_BM, FA_BN, p.fp16);
-      const uint32_t idesc_o = make_idesc_16(FA_BM, C::DV, p.fp16) | (1u << 16);  // B (= V) is MN-major
+      const uint32_t idesc_s = make_idesc_16(FA_BM, FA_BN, FP16 ? 1 : 0);
+      const uint32_t idesc_o = make_idesc_16(FA_BM, C::DV, FP16 ? 1 : 0) | (1u << 16);  // B (= V) is MN-major
       auto issue_s = [&](int j) {  // S_g = Q_g K(j)^T for every query tile; K(j) is released after the last one
         const int stage = j % C::STAGES;
         const int sb = j % C::NSB;
@@ -210,7 +231,7 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
     const uint32_t sPg = sP + uint32_t(g * 2) * FA_TILE;
     const uint32_t tmem_o = tmem + lane_base + C::S_COLS + g * C::O_STRIDE;
     const float sl = p.scale_log2;
-    const int fp16 = p.fp16;
+    constexpr int fp16 = FP16 ? 1 : 0;
     float o_acc[C::DV];
 #pragma unroll
     for (int i = 0; i < C::DV; ++i) o_acc[i] = 0.f;
@@ -277,11 +298,10 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = fa_ex2(fmaf(__uint_as_float(sc[c][i]), sl, ms));
-            const float p1 = fa_ex2(fmaf(__uint_as_float(sc[c][i + 1]), sl, ms));
-            rs += p0;
-            rs1 += p1;
-            pk[i >> 1] = pack2_16(p0, p1, fp16);
+            pk[i >> 1] = ex2_pair16<FP16>(fmaf(__uint_as_float(sc[c][i]), sl, ms), fmaf(__uint_as_float(sc[c][i + 1]), sl, ms));
+            const float2 pf = unpack16<FP16>(pk[i >> 1]);  // the row sum uses exactly the rounded P the MMA will see
+            rs += pf.x;
+            rs1 += pf.y;
           }
           const uint32_t chunk_base = sPg + uint32_t(c >> 1) * FA_TILE + uint32_t(row) * 128;
           const int u0 = (c & 1) * 4;
@@ -437,17 +457,21 @@ const char* flash_attention_tc_prepare(const void* q, int ldq, const void* k, in
   return nullptr;
 }
 
-template <int D, int NQT>
-static const char* fa_launch_d(const FaLaunch& L, cudaStream_t st) {
+template <int D, int NQT, bool FP16>
+static const char* fa_launch_t(const FaLaunch& L, cudaStream_t st) {
   using C = FaCfg<D, NQT>;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(fa_tc_kernel<D, NQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)) != cudaSuccess)
+    if (cudaFuncSetAttribute(fa_tc_kernel<D, NQT, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)) != cudaSuccess)
       return "attention: cudaFuncSetAttribute failed";
     attr = true;
   }
-  fa_tc_kernel<D, NQT><<<L.grid, C::THREADS, C::SMEM, st>>>(*reinterpret_cast<const FaParams*>(L.params));
+  fa_tc_kernel<D, NQT, FP16><<<L.grid, C::THREADS, C::SMEM, st>>>(*reinterpret_cast<const FaParams*>(L.params));
   return cudaGetLastError() == cudaSuccess ? nullptr : "attention: launch failed";
+}
+template <int D, int NQT>
+static const char* fa_launch_d(const FaLaunch& L, cudaStream_t st) {
+  return reinterpret_cast<const FaParams*>(L.params)->fp16 ? fa_launch_t<D, NQT, true>(L, st) : fa_launch_t<D, NQT, false>(L, st);
 }
 
 const char* flash_attention_tc_launch(const FaLaunch& L, cudaStream_t st) {
