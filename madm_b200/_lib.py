@@ -9,7 +9,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmadm_b200.so")
+# MADM_B200_LIB points at another build of the same C ABI (A/B runs of two kernel versions on one box)
+LIB_PATH = os.environ.get("MADM_B200_LIB") or os.path.join(_HERE, "libmadm_b200.so")
 
 MADM_OK = 0
 STAGE_VAE, STAGE_UNET, STAGE_PROJ, STAGE_ALL = 1, 2, 4, 7
@@ -55,7 +56,7 @@ class MadmGemmArgs(C.Structure):
         ("w", c_void_p), ("bias", c_void_p), ("rowbias", c_void_p), ("rows_per_img", c_int32), ("ld_rowbias", c_int32),
         ("residual", c_void_p), ("ldr", c_int32), ("out_f32", c_void_p), ("ldo32", c_int32),
         ("out_bf16", c_void_p), ("ldo16", c_int32), ("act", c_int32), ("alpha", c_float), ("bn", c_int32), ("dtype", c_int32),
-        ("colstats", c_void_p), ("stat_rows", c_int32), ("mt", c_int32),
+        ("colstats", c_void_p), ("stat_rows", c_int32), ("mt", c_int32), ("s2d_H", c_int32), ("s2d_W", c_int32),
     ]
 
 

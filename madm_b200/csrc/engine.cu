@@ -65,6 +65,7 @@ struct Act {
   float* cs = nullptr;  // per-column statistics written by the producing GEMM's epilogue ([M/sr][C][2]), if any
   int sr = 0;           // rows per statistics block (64 or 128)
   bool has_cs = false;  // valid in every builder mode (cs itself is null outside PLAN mode)
+  bool h_s2d = false;   // the 16-bit copy `h` is stored in space-to-depth layout [4][B][H/2][W/2][C] (input of a stride-2 conv)
   int B = 0, H = 0, W = 0, C = 0;
   int HW() const { return H * W; }
   long M() const { return long(B) * H * W; }
@@ -514,7 +515,8 @@ struct Model {
   }
 
   // ---- ResnetBlock2D.  x = channel concat of x0 (and x1).  Returns fp32 (+bf16 copy if want_b16) output.
-  Act resblock(const std::string& p, const Act& x0, const Act* x1, int Cout, float eps, bool has_temb, bool want_b16) {
+  Act resblock(const std::string& p, const Act& x0, const Act* x1, int Cout, float eps, bool has_temb, bool want_b16, bool want_s2d = false) {
+    if (getenv("MADM_NO_S2D_FUSE")) want_s2d = false;
     const int Bn = x0.B, H = x0.H, W = x0.W, Cin = x0.C + (x1 ? x1->C : 0);
     const bool shortcut = Cin != Cout;
     if (x1 && !shortcut) b.fail(MADM_EINVAL, "resblock: concat input without shortcut");
@@ -537,9 +539,11 @@ struct Model {
     B16T n2 = b.b16(size_t(x0.M()) * Cout);
     b.groupnorm(h1, nullptr, p + ".norm2", eps, ACT_SILU, n2.p, nullptr, /*in16=*/true);
     b.free(h1);
-    Act out = b.act(Bn, H, W, Cout, true, want_b16);
+    Act out = b.act(Bn, H, W, Cout, true, want_b16 || want_s2d);
+    out.h_s2d = want_s2d;
     {
       GemmDesc d; d.seg[0] = Builder::seg_3x3(n2.p, Bn, H, W, Cout); d.M = int(x0.M()); d.N = Cout; d.Nw = Cout;
+      if (want_s2d) { d.s2d_H = H; d.s2d_W = W; }
       if (shortcut) {  // out = conv2(n2) + conv_shortcut(x): one GEMM, K = 9*Cout + Cin
         Builder::Fused f = b.conv_plus_shortcut(p + ".conv2", p + ".conv_shortcut", Cout, Cin);
         d.nseg = 2; d.seg[1] = Builder::seg_1x1(raw.p, Bn, H, W, Cin);
@@ -558,7 +562,8 @@ struct Model {
   }
 
   // ---- Transformer2DModel (one BasicTransformerBlock): returns fp32 (+bf16) output; x is NOT freed
-  Act transformer(const std::string& p, const Act& x, bool want_b16) {
+  Act transformer(const std::string& p, const Act& x, bool want_b16, bool want_s2d = false) {
+    if (getenv("MADM_NO_S2D_FUSE")) want_s2d = false;
     const int Bn = x.B, H = x.H, W = x.W, C = x.C;
     const long M = x.M();
     const int heads = 8, d_head = C / heads;
@@ -628,8 +633,10 @@ struct Model {
       d.residual = hs.p; d.ldr = C; d.out_bf16 = hsb.p; d.ldo16 = C; b.gemm(d); }
     b.free(ff);
     b.free(hs);
-    Act out = b.act(Bn, H, W, C, true, want_b16);
+    Act out = b.act(Bn, H, W, C, true, want_b16 || want_s2d);
+    out.h_s2d = want_s2d;
     { GemmDesc d; d.seg[0] = Builder::seg_1x1(hsb.p, Bn, H, W, C); d.M = int(M); d.N = C; d.Nw = C;
+      if (want_s2d) { d.s2d_H = H; d.s2d_W = W; }
       d.w = b.pw(b.conv_w(p + ".proj_out", C, C, 1)); d.bias = P(p + ".proj_out.bias", C);
       d.residual = x.f.p; d.ldr = C; d.out_f32 = out.f.p; d.ldo32 = C; d.out_bf16 = out.h.p; d.ldo16 = C;
       b.attach_colstats(out, d); b.gemm(d); }
@@ -646,15 +653,23 @@ struct Model {
 
   Act downsample(const std::string& p, const Act& x, bool pad1) {
     const int Bn = x.B, H = x.H, W = x.W, C = x.C;
-    B16T s2d = b.b16(size_t(x.M()) * C);
-    { const float* src = x.f.p; bf16* dst = s2d.p;
+    B16T s2d;
+    const bf16* s2dp;
+    if (x.h_s2d) {  // the producer's epilogue already wrote the space-to-depth operand
+      s2dp = x.h.p;
+    } else {
+      s2d = b.b16(size_t(x.M()) * C);
+      s2dp = s2d.p;
+      const float* src = x.f.p; bf16* dst = s2d.p;
       const int h16 = f16();
-      b.emit([=](cudaStream_t st) { return space_to_depth(src, Bn, H, W, C, dst, h16, st); }); }
+      b.emit([=](cudaStream_t st) { return space_to_depth(src, Bn, H, W, C, dst, h16, st); }, false, MADM_KIND_ELEMENTWISE, 0.0,
+             double(x.M()) * C * 6);
+    }
     Act out = b.act(Bn, H / 2, W / 2, C, true, false);
-    { GemmDesc d; d.seg[0] = Builder::seg_s2(s2d.p, Bn, H / 2, W / 2, C, pad1); d.M = int(out.M()); d.N = C; d.Nw = C;
+    { GemmDesc d; d.seg[0] = Builder::seg_s2(s2dp, Bn, H / 2, W / 2, C, pad1); d.M = int(out.M()); d.N = C; d.Nw = C;
       d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C;
       b.attach_colstats(out, d); b.gemm(d); }
-    b.free(s2d);
+    if (!x.h_s2d) b.free(s2d);
     return out;
   }
 
@@ -753,7 +768,8 @@ struct Model {
         const std::string p = e + "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j);
         ++index;
         const bool is_tap = index == 5;  // encoder_block_indices=[5] (counter increments before the check, :289-293)
-        Act y = resblock(p, x, nullptr, ch[i], 1e-6f, false, is_tap);
+        const bool feeds_down = (j == 1 && i < 3);  // its output is the input of this stage's stride-2 conv
+        Act y = resblock(p, x, nullptr, ch[i], 1e-6f, false, is_tap, feeds_down && !is_tap);
         b.free(x);
         x = y;
         if (is_tap) {  // keep the tap alive for the projection stage
@@ -864,7 +880,7 @@ struct Model {
       const std::string blk = kUnet + "down_blocks." + std::to_string(i);
       for (int j = 0; j < 2; ++j) {
         Act y = resblock(blk + ".resnets." + std::to_string(j), x, nullptr, ch[i], 1e-5f, true, false);
-        if (i < 3) { Act z = transformer(blk + ".attentions." + std::to_string(j), y, false); b.free(y); y = z; }
+        if (i < 3) { Act z = transformer(blk + ".attentions." + std::to_string(j), y, false, /*want_s2d=*/j == 1); b.free(y); y = z; }
         x = y;
         skips.push_back(x);
       }

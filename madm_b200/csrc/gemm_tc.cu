@@ -56,6 +56,8 @@ struct GemmParams {
   int n_tiles;
   int fp16;
   int num_tiles;
+  int s2d_H, s2d_W;  // if s2d_W > 0 the 16-bit output is written in space-to-depth layout [4 phases][B][H/2][W/2][N] of an HxW image grid
+  int s2d_B;
   int splits;        // split-K factor: tile t covers K range (t % splits) of output tile (t / splits) and writes raw partials
   long split_stride; // elements between the partial outputs of consecutive splits (out_f32 + split * split_stride)
   float* colstats;   // [ceil(M/32)][N][2] per-column (sum, sum of squares) of the stored outputs per 32-row block, or null
@@ -65,6 +67,8 @@ struct GemmParams {
 // MT = M sub-tiles (128 rows each) per CTA tile.  MT = 2 loads one W box per K chunk for two A boxes (tile 256 x BN): the
 // L2->SM operand traffic per FLOP drops from (128+BN) to (256+BN)/2 bytes-equivalents, which is what bounds the BN = 128
 // layers (measured 12.7 TB/s of L2->SM reads at 42 % tensor-pipe activity on the VAE 512^2 convs).
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_S2D = 2 };  // epilogue variants (bit mask) compiled as separate kernels
+
 template <int BN, int MT>
 struct Cfg {
   static constexpr int A_BYTES = MT * A_STAGE_BYTES;
@@ -108,10 +112,10 @@ __device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, fl
 // Fused epilogue of one 32x32 fp32 block that sits transposed in this warp's staging buffer: lane = (row sub-index, 4
 // columns), 8 iterations of 4 rows -> every global access is a full 128-byte row segment.  `bb` already holds
 // bias (+ the per-image time-embedding row bias).  Compile-time flags keep the loop free of uniform branches.
-template <bool RES, bool O32, bool O16>
+template <bool RES, bool O32, int O16>
 __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int M, float alpha, float4 bb, int act, int fp16,
                                           const float* __restrict__ res, int ldr, float* o32, int ldo32, uint16_t* o16, int ldo16,
-                                          bool do_stats, float (&cs)[8]) {
+                                          bool do_stats, float (&cs)[8], int s2d_H = 0, int s2d_W = 0, int s2d_B = 0, int N = 0) {
   const int rsub = lane >> 3;
   const int cc = (lane & 7) * 4;
   float4 resv[8];
@@ -132,7 +136,16 @@ __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int 
     else if (act == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
     if (row0 + r < M) {
       if constexpr (O32) *reinterpret_cast<float4*>(o32 + size_t(r) * ldo32) = v;
-      if constexpr (O16) *reinterpret_cast<uint2*>(o16 + size_t(r) * ldo16) = pack4_16(v.x, v.y, v.z, v.w, fp16);
+      if constexpr (O16 == 1) *reinterpret_cast<uint2*>(o16 + size_t(r) * ldo16) = pack4_16(v.x, v.y, v.z, v.w, fp16);
+      if constexpr (O16 == 2) {  // the consumer is a stride-2 conv: write its space-to-depth operand [4][B][H/2][W/2][N] directly
+        // H and W are powers of two (checked on the host): s2d_H / s2d_W carry log2(H) / log2(W)
+        const int m = row0 + r;
+        const int x = m & ((1 << s2d_W) - 1), y = (m >> s2d_W) & ((1 << s2d_H) - 1), bimg = m >> (s2d_W + s2d_H);
+        const int ph = (y & 1) * 2 + (x & 1);
+        const long off = ((((long(ph) * s2d_B + bimg) << (s2d_H - 1)) + (y >> 1)) << (s2d_W - 1)) + (x >> 1);
+        const long offN = off * long(N);
+        *reinterpret_cast<uint2*>(o16 + offN) = pack4_16(v.x, v.y, v.z, v.w, fp16);
+      }
       if (do_stats) {  // GroupNorm statistics of the consumer, fused here: per-column sum / sum of squares of what is stored
         cs[0] += v.x; cs[1] += v.y; cs[2] += v.z; cs[3] += v.w;
         cs[4] = fmaf(v.x, v.x, cs[4]); cs[5] = fmaf(v.y, v.y, cs[5]); cs[6] = fmaf(v.z, v.z, cs[6]); cs[7] = fmaf(v.w, v.w, cs[7]);
@@ -154,7 +167,7 @@ __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int 
 //               i+1 overlap the epilogue of tile i
 //   warps 2..5  epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> coalesced fused epilogue
 //               (bias / time-embedding row bias / fp32 residual / SiLU / ReLU / GEGLU) -> fp32 and/or 16-bit stores
-template <int BN, int MT, bool STATS>
+template <int BN, int MT, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, MT>;
   extern __shared__ uint8_t smem_raw[];
@@ -299,6 +312,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint16_t* const out16 = reinterpret_cast<uint16_t*>(p.out_bf16);
     const int ldr = p.ldr, ldo32 = p.ldo32, ldo16 = p.ldo16;
     const int mode = (residual ? 4 : 0) | (p.out_f32 ? 2 : 0) | (out16 ? 1 : 0);
+    constexpr bool STATS = (EPI & EPI_STATS) != 0;
+    constexpr bool S2D = (EPI & EPI_S2D) != 0;  // separate instantiation: its extra live values would otherwise spill in every variant
     constexpr bool do_stats = STATS;  // compile-time: the statistics-free variant keeps the tighter rolled chunk loop
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -372,8 +387,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           __syncwarp();
           const int cc = (lane & 7) * 4;
           float nostats[8];
-          epi_block<false, false, true>(stg, lane, row0, M, 1.0f, make_float4(0.f, 0.f, 0.f, 0.f), ACT_NONE, fp16, nullptr, 0, nullptr, 0,
-                                        out16 + size_t(row0) * ldo16 + on0 + half * 32 + cc, ldo16, false, nostats);
+          epi_block<false, false, 1>(stg, lane, row0, M, 1.0f, make_float4(0.f, 0.f, 0.f, 0.f), ACT_NONE, fp16, nullptr, 0, nullptr, 0,
+                                     out16 + size_t(row0) * ldo16 + on0 + half * 32 + cc, ldo16, false, nostats);
         }
       } else {
         float cs1[8];  // column statistics of the current chunk (STATS variant only)
@@ -403,14 +418,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
             const float* resp = residual ? residual + size_t(row0) * ldr + n : nullptr;
             float* o32p = out32 ? out32 + size_t(row0) * ldo32 + n : nullptr;
-            uint16_t* o16p = out16 ? out16 + size_t(row0) * ldo16 + n : nullptr;
-            switch (mode) {
-              case 1: epi_block<false, false, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-              case 2: epi_block<false, true, false>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-              case 3: epi_block<false, true, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-              case 5: epi_block<true, false, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-              case 6: epi_block<true, true, false>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-              default: epi_block<true, true, true>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+            if constexpr (S2D) {  // 16-bit output in space-to-depth layout (row offsets computed per row inside)
+              const int s2d_W = p.s2d_W, s2d_H = p.s2d_H, s2d_B = p.s2d_B;
+              uint16_t* o16p = out16 + n;
+              if (residual) epi_block<true, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
+              else epi_block<false, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
+            } else {
+              uint16_t* o16p = out16 ? out16 + size_t(row0) * ldo16 + n : nullptr;
+              switch (mode) {
+                case 1: epi_block<false, false, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 2: epi_block<false, true, 0>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 3: epi_block<false, true, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 5: epi_block<true, false, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 6: epi_block<true, true, 0>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                default: epi_block<true, true, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+              }
             }
             if (do_stats && lane < 8 && row0 < M) {
               // one (sum, sumsq) pair per column for this warp's 32-row block: 8 lanes x 32 B = 256 contiguous bytes, written by
@@ -551,6 +573,11 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   if (d.act == ACT_GEGLU && (!d.out_bf16 || d.out_f32 || d.residual || d.rowbias)) return "gemm: GEGLU epilogue writes bf16 only";
   if (d.act == ACT_GEGLU && d.N % 64 != 0) return "gemm: GEGLU needs N % 64 == 0";
   if (d.rowbias && d.rows_per_img % 32 != 0) return "gemm: rows_per_img must be a multiple of 32 when a row bias is given";
+  if (d.s2d_W > 0) {
+    if (!d.out_f32) return "gemm: the space-to-depth 16-bit output is a secondary output (out_f32 required)";
+    if (!d.out_bf16 || (d.s2d_W & 1) || (d.s2d_H & 1) || d.M % (d.s2d_H * d.s2d_W) != 0 || d.N % 32 != 0 || d.act == ACT_GEGLU)
+      return "gemm: space-to-depth output needs a 16-bit output, even H/W, M = B*H*W and N % 32 == 0";
+  }
   if (d.colstats) {
     if (d.stat_rows != 32) return "gemm: stat_rows must be 32";
     if (d.N % 32 != 0 || d.act == ACT_GEGLU) return "gemm: column statistics need N % 32 == 0 and a plain epilogue";
@@ -637,23 +664,36 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   return nullptr;
 }
 
-template <int BN, int MT, bool STATS>
+template <int BN, int MT, int EPI>
 static const char* launch_bn_s(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, MT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BN, MT>::SMEM)) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BN, MT>::SMEM)) != cudaSuccess)
       return "gemm: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     attr_set = true;
   }
-  gemm_tc_kernel<BN, MT, STATS><<<L.grid, kThreads, Cfg<BN, MT>::SMEM, stream>>>(p);
+  gemm_tc_kernel<BN, MT, EPI><<<L.grid, kThreads, Cfg<BN, MT>::SMEM, stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? nullptr : "gemm: kernel launch failed";
 }
 template <int BN>
 static const char* launch_bn(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
+  const int epi = (p.s2d_W > 0 ? EPI_S2D : 0) | (p.colstats ? EPI_STATS : 0);
   if constexpr (BN == 128) {
-    if (L.mt == 2) return p.colstats ? launch_bn_s<BN, 2, true>(L, p, stream) : launch_bn_s<BN, 2, false>(L, p, stream);
+    if (L.mt == 2) {
+      switch (epi) {
+        case 0: return launch_bn_s<BN, 2, 0>(L, p, stream);
+        case 1: return launch_bn_s<BN, 2, 1>(L, p, stream);
+        case 2: return launch_bn_s<BN, 2, 2>(L, p, stream);
+        default: return launch_bn_s<BN, 2, 3>(L, p, stream);
+      }
+    }
   }
-  return p.colstats ? launch_bn_s<BN, 1, true>(L, p, stream) : launch_bn_s<BN, 1, false>(L, p, stream);
+  switch (epi) {
+    case 0: return launch_bn_s<BN, 1, 0>(L, p, stream);
+    case 1: return launch_bn_s<BN, 1, 1>(L, p, stream);
+    case 2: return launch_bn_s<BN, 1, 2>(L, p, stream);
+    default: return launch_bn_s<BN, 1, 3>(L, p, stream);
+  }
 }
 
 const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
@@ -691,6 +731,7 @@ const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
              (!d.residual || (al16(d.residual) && d.ldr % 4 == 0)) && (!d.out_f32 || (al16(d.out_f32) && d.ldo32 % 4 == 0)) &&
              (!d.out_bf16 || (al16(d.out_bf16) && d.ldo16 % 8 == 0));
   if (d.act == ACT_GEGLU && !p.vec_ok) return "gemm: GEGLU epilogue needs 16B-aligned outputs";
+  if (d.s2d_W > 0 && !p.vec_ok) return "gemm: space-to-depth output needs 16B-aligned operands";
   p.n_tiles = (p.N + L.bn - 1) / L.bn;
   p.fp16 = d.fp16;
   p.num_tiles = L.num_tiles;
@@ -698,6 +739,14 @@ const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   p.stat_rows = d.stat_rows;
   p.splits = L.splits;
   p.split_stride = L.split_stride;
+  p.s2d_H = 0; p.s2d_W = 0; p.s2d_B = 0;
+  if (d.s2d_W > 0) {  // the kernel takes log2(H), log2(W)
+    int lh = 0, lw = 0;
+    while ((1 << lh) < d.s2d_H) ++lh;
+    while ((1 << lw) < d.s2d_W) ++lw;
+    if ((1 << lh) != d.s2d_H || (1 << lw) != d.s2d_W) return "gemm: space-to-depth output needs power-of-two H and W";
+    p.s2d_H = lh; p.s2d_W = lw; p.s2d_B = d.M / (d.s2d_H * d.s2d_W);
+  }
   switch (L.bn) {
     case 16: return launch_bn<16>(L, p, stream);
     case 32: return launch_bn<32>(L, p, stream);

@@ -42,6 +42,7 @@ struct GemmDesc {
   float alpha = 1.0f;               // scales the accumulator before bias
   int bn = 0;                       // N tile (0 = auto)
   int fp16 = 0;                     // operand / 16-bit output dtype: 0 = bf16, 1 = fp16
+  int s2d_H = 0, s2d_W = 0;         // >0: write out_bf16 in space-to-depth layout [4][B][H/2][W/2][N] (operand of a stride-2 conv)
   int mt = 0;                       // M sub-tiles per CTA tile for the 128-wide N tile: 0 auto, 1, or 2 (256-row tiles)
   int splits = 1;                   // split-K factor (>1: raw fp32 partial outputs at out_f32 + split * split_stride)
   long split_stride = 0;

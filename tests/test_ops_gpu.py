@@ -179,6 +179,21 @@ def test_conv3x3_stride2(ops, cuda_device, pad1, B, H, W, Cc):
     assert relerr(out, nhwc(ref).reshape(M, Cc)) < 2e-3
 
 
+@pytest.mark.parametrize("B,H,W,Cc,bn", [(2, 16, 16, 128, 0), (1, 8, 128, 256, 128), (3, 8, 8, 320, 0)])
+def test_gemm_space_to_depth_output(ops, cuda_device, B, H, W, Cc, bn):
+    """The epilogue can write its 16-bit output directly in the space-to-depth layout the following stride-2 conv reads."""
+    g = torch.Generator(device="cuda").manual_seed(H * W + Cc)
+    M, K = B * H * W, 128
+    a = bf(torch.randn(M, K, device=cuda_device, generator=g))
+    w = bf(torch.randn(Cc, K, device=cuda_device, generator=g) / math.sqrt(K))
+    out = torch.empty(M, Cc, device=cuda_device)
+    s2d = torch.full((4, B, H // 2, W // 2, Cc), float("nan"), dtype=DT, device=cuda_device)
+    ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, Cc, w, out_f32=out, ldo32=Cc, out_bf16=s2d, ldo16=Cc, s2d_hw=(H, W), bn=bn)
+    ref16 = bf(out).reshape(B, H, W, Cc)
+    for ph in range(4):
+        assert torch.equal(s2d[ph], ref16[:, (ph // 2)::2, (ph % 2)::2, :])
+
+
 def test_conv_plus_shortcut_two_segments(ops, cuda_device):
     """out = conv3x3(h) + conv1x1(x) as one GEMM with K = 9*Cout + Cin (ResBlock conv2 + conv_shortcut)."""
     g = torch.Generator(device="cuda").manual_seed(21)
