@@ -1,14 +1,16 @@
 // tcgen05 / TMEM flash attention for the SD-1.4 UNet (self: n in {4096,1024,256,64}; cross: 77 keys; 8 heads, d in {40,80,160}).
 //
-// One CTA = 128 query rows of one (image, head).  Per 128-key tile:
+// One CTA = NQT (2, or 1 for d = 160) tiles of 128 query rows of one (image, head).  Per 128-key tile and query tile:
 //   S = Q K^T          tcgen05.mma 128x128xd   (Q, K tiles K-major in 128B-swizzled smem, loaded by 4-D TMA boxes over the
 //                                               [d, heads, tokens, batch] view; head-dim columns past d are zero-filled by TMA)
-//   softmax            4 warps, thread = query row: tcgen05.ld the fp32 scores, online max / sum in registers (no shuffles),
-//                      p = 2^(s*c - m*c) as one FFMA + MUFU, written as 16-bit P into swizzled smem (A operand of the next MMA)
-//   O_tile = P V       tcgen05.mma 128xdx128   (V tile used as an MN-major B operand: no transpose pass)
+//   softmax            4 warps, thread = query row: one tcgen05.ld round trip pulls the fp32 score row into registers, online
+//                      max in registers (no shuffles), p = 2^(s*c - m*c) as one FFMA + MUFU, packed to 16 bits
+//   O_tile = P V       tcgen05.mma 128xdx128   (V tile used as an MN-major B operand: no transpose pass).  d = 40: P is handed
+//                      over through TMEM (tcgen05.st, A operand from tensor memory) and column d of V is set to 1, so the MMA
+//                      also accumulates the softmax denominator.  d = 80 / 160: P goes through swizzled smem.
 //   O = O*corr + O_tile in registers (fp32), deferred by one tile so the P V latency is hidden behind the next tile's softmax.
-// Warp roles: warp 0 TMA producer (double-buffered K/V), warp 1 TMEM allocator + single-thread MMA issuer (two S buffers in
-// TMEM so Q K^T of tile j+1 overlaps the softmax of tile j), warps 2..5 softmax / output.
+// Warp roles: warp 0 TMA producer (double-buffered K/V), warps 1..NQT MMA issuers (one per query tile, also TMEM allocator),
+// then one softmax / output warpgroup per query tile.
 #include "cvt.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
@@ -31,17 +33,26 @@ struct FaCfg {
   // buffer immediately, so one S buffer per query tile suffices.  d = 160 keeps its registers for the O accumulator and
   // re-reads S in two passes from two S buffers.
   static constexpr bool REG_S = D <= 80;
+  // d = 40 pads its P V tile to 48 columns: column d of the V tile is set to 1 so that the MMA accumulates the softmax
+  // denominator (the row sum of exactly the rounded P it multiplies) for free; no per-score add in the softmax warps.
+  static constexpr bool ONES = REG_S && DV > D;
   static constexpr int NSB = REG_S ? 1 : 2;         // S buffers per query tile
+  // d = 40 also has the TMEM room (2 x 128 S + 2 x 64 P + 2 x 64 O = 512 columns) to hand P to the P V MMA through tensor
+  // memory (A operand from TMEM): the 16-bit P tile never touches shared memory, whose port is the bottleneck of the narrow
+  // (N = 48) P V MMAs -- each k-step would re-read 4 KB of P for 1.5 KB of V.
+  static constexpr bool P_TMEM = ONES && NQT == 2;
   static constexpr int Q_BYTES = NQT * KC * FA_TILE;
   static constexpr int KV_BYTES = KC * FA_TILE;     // per stage, per operand
-  static constexpr int P_BYTES = NQT * 2 * FA_TILE;
+  static constexpr int P_BYTES = P_TMEM ? 0 : NQT * 2 * FA_TILE;
   static constexpr int STAGES = (Q_BYTES + P_BYTES + 4 * KV_BYTES + 2048 <= 227 * 1024) ? 2 : 1;  // K/V ring depth
   static constexpr size_t SMEM = Q_BYTES + 2 * STAGES * KV_BYTES + P_BYTES + 1024 + 512;
-  static constexpr int S_COLS = NQT * NSB * 128;    // S buffers first, then one O tile per query tile
+  static constexpr int S_COLS = NQT * NSB * 128;    // S buffers first, then (P_TMEM) one 64-column P tile, then one O tile per query tile
+  static constexpr int P_COLS = P_TMEM ? NQT * 64 : 0;
+  static constexpr int O_BASE = S_COLS + P_COLS;
   static constexpr int O_STRIDE = (DV + 31) / 32 * 32;
-  static constexpr int TMEM_NEED = S_COLS + NQT * O_STRIDE;
+  static constexpr int TMEM_NEED = O_BASE + NQT * O_STRIDE;
   static constexpr int TMEM_COLS = TMEM_NEED <= 256 ? 256 : 512;
-  static constexpr int THREADS = 64 + NQT * 128;
+  static constexpr int THREADS = 32 * (1 + NQT) + NQT * 128;  // TMA producer, one MMA issuer per query tile, softmax warpgroups
   static_assert(TMEM_NEED <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "smem budget");
 };
@@ -60,27 +71,6 @@ __device__ __forceinline__ float fa_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-
-// p = 2^x for two arguments at once on the packed 16-bit MUFU path (one MUFU op per pair instead of two, and the result is
-// already the 16-bit operand the P V MMA consumes).  The subtraction of the running max is done in fp32 by the caller, so
-// x <= 0 and the arguments that matter (x near 0) are converted with an absolute error <= 2^-12.
-template <bool FP16>
-__device__ __forceinline__ uint32_t ex2_pair16(float x0, float x1) {
-  uint32_t h, r;
-  if constexpr (FP16) {
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
-    asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
-  } else {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
-    asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(h));
-  }
-  return r;
-}
-template <bool FP16>
-__device__ __forceinline__ float2 unpack16(uint32_t v) {
-  if constexpr (FP16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
-  else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
 }
 
 // smem descriptor of an MN-major (N contiguous) 128B-swizzled B operand: 8-row (K) atoms of 1024 B (SBO), 64-element N groups
@@ -107,7 +97,7 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
   const uint32_t sV = sK + C::STAGES * C::KV_BYTES;
   const uint32_t sP = sV + C::STAGES * C::KV_BYTES;
   const uint32_t sBar = sP + C::P_BYTES;
-  // barriers: q_full | k_full[2] k_empty[2] v_full[2] v_empty[2] | per group g: s_full[2] s_empty[2] p_full p_empty o_full o_empty
+  // barriers: q_full | k_full[2] k_empty[2] v_full[2] v_empty[2] | per group g: s_full[2] s_empty[2] pv_go pv_done
   const uint32_t q_full = sBar;
   auto k_full = [&](int s) { return sBar + 8u * (1 + s); };
   auto k_empty = [&](int s) { return sBar + 8u * (3 + s); };
@@ -116,10 +106,10 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
   auto gbar = [&](int g, int i) { return sBar + 8u * (9 + g * 8 + i); };
   auto s_full = [&](int g, int a) { return gbar(g, a); };
   auto s_empty = [&](int g, int a) { return gbar(g, 2 + a); };
-  auto p_full = [&](int g) { return gbar(g, 4); };
-  auto p_empty = [&](int g) { return gbar(g, 5); };
-  auto o_full = [&](int g) { return gbar(g, 6); };
-  auto o_empty = [&](int g) { return gbar(g, 7); };
+  // pv_go(j):   softmax -> issuer: P(j) is posted, V(j) has landed and O(j-1) has been consumed, so P V(j) may run
+  // pv_done(j): issuer -> softmax (tcgen05.commit): P V(j) has retired, i.e. the P buffer is free and the O tile holds P V(j)
+  auto pv_go = [&](int g) { return gbar(g, 4); };
+  auto pv_done = [&](int g) { return gbar(g, 5); };
   const uint32_t tmem_slot = sBar + 8u * (9 + 16);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -131,11 +121,11 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
     prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), NQT); mbar_init(v_full(s), 1); mbar_init(v_empty(s), NQT);
     }
     for (int g = 0; g < NQT; ++g) {
       for (int a = 0; a < 2; ++a) { mbar_init(s_full(g, a), 1); mbar_init(s_empty(g, a), 4); }
-      mbar_init(p_full(g), 4); mbar_init(p_empty(g), 1); mbar_init(o_full(g), 1); mbar_init(o_empty(g), 4);
+      mbar_init(pv_go(g), 4); mbar_init(pv_done(g), 1);
     }
     fence_mbar_init();
   }
@@ -171,29 +161,39 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp <= NQT) {
+    // ===================== MMA issuers: one warp per query tile =====================
+    // A single thread issues ~60-70 clk per tcgen05.mma (descriptor set-up on the uniform datapath, barrier polls, commits);
+    // with 22 small MMAs per 128-key step that thread, not the tensor pipe, bounded the kernel.  Each query tile therefore has
+    // its own issuer, and every smem descriptor is computed once up front.
     if (lane == 0) {
+      const int g = warp - 1;
       const uint32_t idesc_s = make_idesc_16(FA_BM, FA_BN, FP16 ? 1 : 0);
       const uint32_t idesc_o = make_idesc_16(FA_BM, C::DV, FP16 ? 1 : 0) | (1u << 16);  // B (= V) is MN-major
-      auto issue_s = [&](int j) {  // S_g = Q_g K(j)^T for every query tile; K(j) is released after the last one
+      uint64_t qd[C::KSTEPS], kd[C::STAGES][C::KSTEPS], vd[C::STAGES], pd[2];
+#pragma unroll
+      for (int ks = 0; ks < C::KSTEPS; ++ks) {
+        const int kc = ks >> 2, k = ks & 3;
+        qd[ks] = make_smem_desc_sw128(sQ + (g * C::KC + kc) * FA_TILE) + uint64_t(2 * k);
+#pragma unroll
+        for (int st = 0; st < C::STAGES; ++st) kd[st][ks] = make_smem_desc_sw128(sK + st * C::KV_BYTES + kc * FA_TILE) + uint64_t(2 * k);
+      }
+#pragma unroll
+      for (int st = 0; st < C::STAGES; ++st) vd[st] = make_smem_desc_sw128_mn(sV + st * C::KV_BYTES, FA_TILE);
+      pd[0] = make_smem_desc_sw128(sP + (g * 2) * FA_TILE);
+      pd[1] = make_smem_desc_sw128(sP + (g * 2 + 1) * FA_TILE);
+      const uint32_t tmem_og = tmem + C::O_BASE + g * C::O_STRIDE;
+      const uint32_t tmem_pg = tmem + C::S_COLS + g * 64;
+      auto issue_s = [&](int j) {  // S_g = Q_g K(j)^T; K(j) is released once every issuer has committed its MMAs
         const int stage = j % C::STAGES;
         const int sb = j % C::NSB;
         mbar_wait(k_full(stage), (j / C::STAGES) & 1);
+        mbar_wait(s_empty(g, sb), ((j / C::NSB) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t ts = tmem + uint32_t((g * C::NSB + sb) * 128);
 #pragma unroll
-        for (int g = 0; g < NQT; ++g) {
-          mbar_wait(s_empty(g, sb), ((j / C::NSB) & 1) ^ 1u);
-          tc_fence_after();
-          const uint32_t ts = tmem + uint32_t((g * C::NSB + sb) * 128);
-#pragma unroll
-          for (int ks = 0; ks < C::KSTEPS; ++ks) {
-            const int kc = ks >> 2, k = ks & 3;
-            const uint64_t ad = make_smem_desc_sw128(sQ + (g * C::KC + kc) * FA_TILE) + uint64_t(2 * k);
-            const uint64_t bd = make_smem_desc_sw128(sK + stage * C::KV_BYTES + kc * FA_TILE) + uint64_t(2 * k);
-            umma_bf16_ss(ts, ad, bd, idesc_s, ks != 0);
-          }
-          umma_commit(s_full(g, sb));
-        }
+        for (int ks = 0; ks < C::KSTEPS; ++ks) umma_bf16_ss(ts, qd[ks], stage == 0 ? kd[0][ks] : kd[C::STAGES - 1][ks], idesc_s, ks != 0);
+        umma_commit(s_full(g, sb));
         umma_commit(k_empty(stage));
       };
       mbar_wait(q_full, 0);
@@ -202,34 +202,33 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
         if (j + 1 < ntiles) issue_s(j + 1);
         // O_g tile = P_g(j) V(j)
         const int stage = j % C::STAGES;
-        mbar_wait(v_full(stage), (j / C::STAGES) & 1);
         int keys = p.Nk - j * FA_BN;
         if (keys > FA_BN) keys = FA_BN;
         const int ksteps = (keys + 15) >> 4;
+        mbar_wait(pv_go(g), j & 1);
+        tc_fence_after();
+        const uint64_t vds = stage == 0 ? vd[0] : vd[C::STAGES - 1];
 #pragma unroll
-        for (int g = 0; g < NQT; ++g) {
-          mbar_wait(p_full(g), j & 1);
-          mbar_wait(o_empty(g), (j & 1) ^ 1u);
-          tc_fence_after();
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t ad = make_smem_desc_sw128(sP + (g * 2 + (kk >> 2)) * FA_TILE) + uint64_t(2 * (kk & 3));
-            const uint64_t bd = make_smem_desc_sw128_mn(sV + stage * C::KV_BYTES + kk * 2048, FA_TILE);
-            umma_bf16_ss(tmem + C::S_COLS + g * C::O_STRIDE, ad, bd, idesc_o, kk != 0);
+        for (int kk = 0; kk < FA_BN / 16; ++kk) {
+          if (kk < ksteps) {
+            const uint64_t bd = vds + uint64_t(kk * (2048 >> 4));
+            if constexpr (C::P_TMEM) umma_f16_ts(tmem_og, tmem_pg + kk * 8, bd, idesc_o, kk != 0);
+            else umma_bf16_ss(tmem_og, pd[kk >> 2] + uint64_t(2 * (kk & 3)), bd, idesc_o, kk != 0);
           }
-          umma_commit(p_empty(g));
-          umma_commit(o_full(g));
         }
+        umma_commit(pv_done(g));
         umma_commit(v_empty(stage));
       }
     }
   } else {
     // ===================== softmax / output (one warpgroup per query tile, thread = query row) =====================
-    const int g = (warp - 2) >> 2;
+    const int g = (warp - (1 + NQT)) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = uint32_t(q * 32) << 16;
     const uint32_t sPg = sP + uint32_t(g * 2) * FA_TILE;
-    const uint32_t tmem_o = tmem + lane_base + C::S_COLS + g * C::O_STRIDE;
+    const uint32_t tmem_o = tmem + lane_base + C::O_BASE + g * C::O_STRIDE;
+    const uint32_t tmem_p = tmem + lane_base + C::S_COLS + g * 64;
     const float sl = p.scale_log2;
     constexpr int fp16 = FP16 ? 1 : 0;
     float o_acc[C::DV];
@@ -238,20 +237,22 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
     float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
     uint32_t r[32];
 
-    auto o_update = [&](int j, float corr) {  // O = O*corr + (P V)(j)
-      mbar_wait(o_full(g), j & 1);
+    auto o_update = [&](float corr) {  // O = O*corr + (P V) of the tile whose pv_done has been observed
       tc_fence_after();
+      constexpr int OB = (C::DV % 48 == 0) ? 48 : 32;  // columns per TMEM round trip (all their loads in flight, one wait)
 #pragma unroll
-      for (int c = 0; c < C::DV; c += 16) {
+      for (int c0 = 0; c0 < C::DV; c0 += OB) {
+        uint32_t ro[OB];
         __syncwarp();
-        tmem_ld16(tmem_o + c, r);
+        if (c0 + 0 < C::DV) tmem_ld16_at<0>(tmem_o + c0, ro);
+        if (c0 + 16 < C::DV) tmem_ld16_at<16>(tmem_o + c0 + 16, ro);
+        if constexpr (OB == 48) { if (c0 + 32 < C::DV) tmem_ld16_at<32>(tmem_o + c0 + 32, ro); }
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o_acc[c + i] = fmaf(o_acc[c + i], corr, __uint_as_float(r[i]));
+        for (int i = 0; i < OB; ++i)
+          if (c0 + i < C::DV) o_acc[c0 + i] = fmaf(o_acc[c0 + i], corr, __uint_as_float(ro[i]));
       }
       tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty(g));
     };
 
     for (int j = 0; j < ntiles; ++j) {
@@ -291,27 +292,47 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
         corr = fa_ex2((m_run - mx) * sl);
         m_run = mx;
         const float ms = -mx * sl;
-        mbar_wait(p_empty(g), (j & 1) ^ 1u);  // P buffer consumed by the previous P V
+        {  // every softmax thread observes V(j) before P(j) is posted, so the issuer needs no wait of its own on v_full
+          const int stage = j % C::STAGES;
+          mbar_wait(v_full(stage), (j / C::STAGES) & 1);
+          if constexpr (C::ONES) {
+            if (g == 0) {  // V(j)[key = row][column D] = 1 (the TMA zero-filled the head-dim padding); published with P below
+              const uint32_t addr = sV + stage * C::KV_BYTES + uint32_t(D >> 6) * FA_TILE + uint32_t(row) * 128 +
+                                    uint32_t((((D & 63) >> 3) ^ (row & 7)) << 4) + uint32_t((D & 7) * 2);
+              const uint16_t one = FP16 ? 0x3C00 : 0x3F80;
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(one) : "memory");
+            }
+          }
+        }
         float rs1 = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            pk[i >> 1] = ex2_pair16<FP16>(fmaf(__uint_as_float(sc[c][i]), sl, ms), fmaf(__uint_as_float(sc[c][i + 1]), sl, ms));
-            const float2 pf = unpack16<FP16>(pk[i >> 1]);  // the row sum uses exactly the rounded P the MMA will see
-            rs += pf.x;
-            rs1 += pf.y;
+            const float p0 = fa_ex2(fmaf(__uint_as_float(sc[c][i]), sl, ms));
+            const float p1 = fa_ex2(fmaf(__uint_as_float(sc[c][i + 1]), sl, ms));
+            pk[i >> 1] = pack2_16(p0, p1, fp16);
+            if constexpr (!C::ONES) { rs += p0; rs1 += p1; }
           }
-          const uint32_t chunk_base = sPg + uint32_t(c >> 1) * FA_TILE + uint32_t(row) * 128;
-          const int u0 = (c & 1) * 4;
+          if (c == 0) {  // the first quarter of the exponentials is computed before the P buffer has to be free
+            if (j > 0) mbar_wait(pv_done(g), (j - 1) & 1);
+            if constexpr (C::P_TMEM) { tc_fence_after(); __syncwarp(); }
+          }
+          if constexpr (C::P_TMEM) {
+            tmem_st16(tmem_p + c * 16, pk);  // keys [32c, 32c+32) of this row = 16 packed columns of the A operand
+          } else {
+            const uint32_t chunk_base = sPg + uint32_t(c >> 1) * FA_TILE + uint32_t(row) * 128;
+            const int u0 = (c & 1) * 4;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t addr = chunk_base + uint32_t(((u0 + u) ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]),
-                         "r"(pk[4 * u + 3]) : "memory");
+            for (int u = 0; u < 4; ++u) {
+              const uint32_t addr = chunk_base + uint32_t(((u0 + u) ^ (row & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]),
+                           "r"(pk[4 * u + 3]) : "memory");
+            }
           }
         }
+        if constexpr (C::P_TMEM) { tmem_st_wait(); tc_fence_before(); }
         rs += rs1;
       } else {
         // pass 1: row max
@@ -333,7 +354,8 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
         corr = fa_ex2((m_run - mx) * sl);
         m_run = mx;
         const float ms = -mx * sl;
-        mbar_wait(p_empty(g), (j & 1) ^ 1u);  // P buffer consumed by the previous P V
+        mbar_wait(v_full(j % C::STAGES), (j / C::STAGES) & 1);
+        if (j > 0) mbar_wait(pv_done(g), (j - 1) & 1);  // P buffer consumed by the previous P V, whose O tile is now complete
         // pass 2: p = 2^(s*sl - m*sl), row sum, 16-bit P into swizzled smem
 #pragma unroll 1
         for (int c = 0; c < FA_BN; c += 32) {
@@ -367,17 +389,19 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
       l_run = l_run * corr + rs;
       // P ready (generic -> async proxy fence before the MMA reads it)
       fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(g));
       // deferred accumulation of the previous tile's P V (its MMA ran while this tile's softmax was computed)
-      if (j > 0) o_update(j - 1, corr_prev);
+      if (j > 0) o_update(corr_prev);
       corr_prev = corr;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pv_go(g));
     }
-    o_update(ntiles - 1, corr_prev);
+    mbar_wait(pv_done(g), (ntiles - 1) & 1);
+    o_update(corr_prev);
     // normalise and store this row
     const int m = q0 + g * FA_BM + row;
     if (m < p.Nq) {
-      const float inv = 1.0f / l_run;
+      const float inv = 1.0f / (C::ONES ? o_acc[C::ONES ? D : 0] : l_run);
       uint16_t* op = p.O + size_t(b) * p.o_bs + size_t(m) * p.ldo + h * D;
 #pragma unroll
       for (int c = 0; c < D; c += 8) {

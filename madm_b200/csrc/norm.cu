@@ -8,7 +8,7 @@
 namespace madm {
 
 __device__ __forceinline__ float act_apply(float v, int act) {
-  if (act == ACT_SILU) return v / (1.0f + __expf(-v));
+  if (act == ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));  // MUFU ex2 + rcp; the result is rounded to 16 bits anyway
   if (act == ACT_RELU) return fmaxf(v, 0.0f);
   return v;
 }
@@ -123,6 +123,29 @@ __device__ __forceinline__ void gn_reduce_partials(const float* __restrict__ par
   __syncthreads();
 }
 
+// the same sums for the short-lived CTAs of the apply pass: up to 4 lane groups take interleaved slabs (independent loads in
+// flight instead of one serial chain), combined in a fixed order that depends on the block size (i.e. on C) only
+__device__ __forceinline__ void gn_reduce_partials_wide(const float* __restrict__ partial, int b, int slabs, float* red /*[64]*/,
+                                                        float* tmp /*[4*64]*/) {
+  const int ng = min(4, int(blockDim.x >> 6));
+  const int lg = threadIdx.x >> 6, j = threadIdx.x & 63;
+  if (lg < ng) {
+    const float* p = partial + size_t(b) * slabs * 64 + j;
+    float a0 = 0.f, a1 = 0.f;
+    int sidx = lg;
+    for (; sidx + ng < slabs; sidx += 2 * ng) { a0 += p[size_t(sidx) * 64]; a1 += p[size_t(sidx + ng) * 64]; }
+    if (sidx < slabs) a0 += p[size_t(sidx) * 64];
+    tmp[lg * 64 + j] = a0 + a1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float acc = tmp[threadIdx.x];
+    for (int g = 1; g < ng; ++g) acc += tmp[g * 64 + threadIdx.x];
+    red[threadIdx.x] = acc;
+  }
+  __syncthreads();
+}
+
 // Statistics fused into the producing GEMM's epilogue arrive as per-column (sum, sumsq) pairs per block of 32 rows:
 // cs[block][c][2].  grid = (S chunks of blocks, B): thread <-> channel (coalesced rows), fixed-order accumulation over the
 // chunk's blocks, then per-group sums -> out[b][chunk][32][2], i.e. the same "slab partial" format gn_stats_kernel writes.
@@ -181,13 +204,14 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, int C0, const void*
                                 uint16_t* __restrict__ raw) {
   constexpr int V = GnVec<IN16>::V;
   __shared__ float red[64];
+  __shared__ float red_tmp[4 * 64];
   const int C = C0 + C1;
   const int Q = C / V;
   const int q = threadIdx.x % Q;
   const int pl = threadIdx.x / Q;
   const int b = blockIdx.y;
   const int cpg = C / 32;
-  gn_reduce_partials(partial, b, slabs, red);
+  gn_reduce_partials_wide(partial, b, slabs, red, red_tmp);
   const int c = q * V;
   const float inv_n = 1.0f / (float(HW) * float(cpg));
   float sc[V], sh[V];
@@ -318,6 +342,12 @@ const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int 
   int P, threads, ppc, slabs;
   gn_launch_geometry(HW, C, in16, &P, &threads, &ppc, &slabs);
   const int pslabs = stats_slabs > 0 ? stats_slabs : slabs;  // number of partial-sum slabs behind `partial`
+  // The apply pass is elementwise, so its own split is free to differ from the statistics slabs: many short CTAs
+  // (16 rounds of the 4-deep unrolled loop each) instead of one wave of long ones -- with 3 resident CTAs per SM the
+  // 592-CTA statistics geometry ran 1.33 waves (a 2/3-empty tail).
+  ppc = 64 * P;
+  if (ppc > HW) ppc = HW;
+  slabs = (HW + ppc - 1) / ppc;
   if (in16)
     gn_apply_kernel<true><<<dim3(slabs, B), threads, 0, st>>>(x0, C0, x1, C1, HW, ppc, P, partial, pslabs, gamma, beta, eps, act, fp16,
                                                               reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
