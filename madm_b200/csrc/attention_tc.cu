@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync (not lane == 0) lets the compiler issue UTMALDG / UTCHMMA without per-lane waterfall loops
       mbar_arrive_expect_tx(q_full, C::Q_BYTES);
 #pragma unroll
       for (int g = 0; g < NQT; ++g)
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
     // A single thread issues ~60-70 clk per tcgen05.mma (descriptor set-up on the uniform datapath, barrier polls, commits);
     // with 22 small MMAs per 128-key step that thread, not the tensor pipe, bounded the kernel.  Each query tile therefore has
     // its own issuer, and every smem descriptor is computed once up front.
-    if (lane == 0) {
+    if (elect_one()) {
       const int g = warp - 1;
       const uint32_t idesc_s = make_idesc_16(FA_BM, FA_BN, FP16 ? 1 : 0);
       const uint32_t idesc_o = make_idesc_16(FA_BM, C::DV, FP16 ? 1 : 0) | (1u << 16);  // B (= V) is MN-major
@@ -296,12 +296,12 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
           const int stage = j % C::STAGES;
           mbar_wait(v_full(stage), (j / C::STAGES) & 1);
           if constexpr (C::ONES) {
-            if (g == 0) {  // V(j)[key = row][column D] = 1 (the TMA zero-filled the head-dim padding); published with P below
-              const uint32_t addr = sV + stage * C::KV_BYTES + uint32_t(D >> 6) * FA_TILE + uint32_t(row) * 128 +
-                                    uint32_t((((D & 63) >> 3) ^ (row & 7)) << 4) + uint32_t((D & 7) * 2);
-              const uint16_t one = FP16 ? 0x3C00 : 0x3F80;
-              asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(one) : "memory");
-            }
+            // V(j)[key = row][column D] = 1 (the TMA zero-filled the head-dim padding); published with P below.  Every query
+            // tile writes it (same value, same place): its own issuer must not depend on another tile's progress.
+            const uint32_t addr = sV + stage * C::KV_BYTES + uint32_t(D >> 6) * FA_TILE + uint32_t(row) * 128 +
+                                  uint32_t((((D & 63) >> 3) ^ (row & 7)) << 4) + uint32_t((D & 7) * 2);
+            const uint16_t one = FP16 ? 0x3C00 : 0x3F80;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(one) : "memory");
           }
         }
         float rs1 = 0.f;

@@ -213,9 +213,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // elect_one(), not lane == 0: behind elect.sync the compiler knows a single lane is active and feeds the uniform-datapath
+    // instructions (UTMALDG / UTCHMMA / UTCBAR) directly instead of wrapping each one in a per-lane "waterfall" loop
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+#ifdef GEMM_INSTR
+      long long pw = 0, pt0 = clock64();
+#define GI(acc, ...) { const long long t0_ = clock64(); __VA_ARGS__; acc += clock64() - t0_; }
+#else
+#define GI(acc, ...) __VA_ARGS__
+#endif
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const int mn = t / p.splits, sp = t - mn * p.splits;
         const int tile_n = mn % p.n_tiles;
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int lk = seg ? kc - p.kchunks[0] : kc;
           const int tap = lk / p.cpt[seg];
           const int cc = lk - tap * p.cpt[seg];
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+          GI(pw, mbar_wait(empty_bar(stage), phase ^ 1u));
           mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
 #pragma unroll
           for (int s = 0; s < MT; ++s)
@@ -255,25 +263,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           }
         }
       }
+#ifdef GEMM_INSTR
+      if (blockIdx.x == 5) printf("producer: total %lld clk, waiting for empty slots %lld\n", clock64() - pt0, pw);
+#endif
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_16(BM, BN, p.fp16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+#ifdef GEMM_INSTR
+      long long w_full = 0, w_acc = 0, t_issue = 0, t_commit = 0, mt0 = clock64(), n_mma = 0, n_chunks = 0, n_tiles_done = 0;
+#endif
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator stage
+        GI(w_acc, mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u));  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + uint32_t(acc * MT * C::ACC_STRIDE);
         const int sp = t % p.splits;
         const int kc0 = (total_chunks * sp) / p.splits, kc1 = (total_chunks * (sp + 1)) / p.splits;
         for (int kc = kc0; kc < kc1; ++kc) {
-          mbar_wait(full_bar(stage), phase);
+          GI(w_full, mbar_wait(full_bar(stage), phase));
           tc_fence_after();
           const uint64_t bdesc = make_smem_desc_sw128(sB + stage * C::B_STAGE_BYTES);
+#ifdef GEMM_INSTR
+          const long long ti0 = clock64();
+          n_mma += MT * (BK / 16); ++n_chunks;
+#endif
 #pragma unroll
           for (int s = 0; s < MT; ++s) {
             const uint64_t adesc = make_smem_desc_sw128(sA + stage * C::A_BYTES + s * A_STAGE_BYTES);
@@ -284,7 +302,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                            (kc > kc0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+#ifdef GEMM_INSTR
+          t_issue += clock64() - ti0;
+#endif
+          GI(t_commit, umma_commit(empty_bar(stage)));  // frees the smem slot when these MMAs retire
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -295,7 +316,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           acc = 0;
           acc_phase ^= 1u;
         }
+#ifdef GEMM_INSTR
+        ++n_tiles_done;
+#endif
       }
+#ifdef GEMM_INSTR
+      if (blockIdx.x == 5)
+        printf("mma: total %lld clk, %lld tiles %lld chunks %lld mmas (BN=%d MT=%d) | wait full %lld wait acc %lld issue %lld commit %lld | ideal tensor clk %lld\n",
+               clock64() - mt0, n_tiles_done, n_chunks, n_mma, BN, MT, w_full, w_acc, t_issue, t_commit, n_mma * BN / 2);
+#endif
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================

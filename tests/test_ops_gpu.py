@@ -369,6 +369,11 @@ def test_attention(ops, cuda_device, B, heads, d, Nq, Nk, impl):
     split = lambda t: t.float().reshape(B, -1, heads, d).transpose(1, 2)  # noqa: E731
     ref = F.scaled_dot_product_attention(split(q), split(k), split(v)).transpose(1, 2).reshape(B, Nq, Cc)
     assert relerr(o, ref) < 2e-2
+    # the warp-specialised pipeline (independent MMA issuers per query tile, shared K/V ring) must be race-free: bit-identical reruns
+    for _ in range(3):
+        o2 = torch.empty_like(o)
+        ops.attention(q, ldq, k, ldk, v, ldk, o2, Cc, B, heads, d, Nq, Nk, q_bs, kv_bs, Nq * Cc, 1.0 / math.sqrt(d), impl=impl)
+        assert torch.equal(o, o2)
 
 
 # ---------------------------------------------------------------------------------------------- packing (LoRA fold)
