@@ -343,9 +343,15 @@ const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int 
   gn_launch_geometry(HW, C, in16, &P, &threads, &ppc, &slabs);
   const int pslabs = stats_slabs > 0 ? stats_slabs : slabs;  // number of partial-sum slabs behind `partial`
   // The apply pass is elementwise, so its own split is free to differ from the statistics slabs: many short CTAs
-  // (16 rounds of the 4-deep unrolled loop each) instead of one wave of long ones -- with 3 resident CTAs per SM the
+  // (at most 16 rounds of the 4-deep unrolled loop each) instead of one wave of long ones -- with 3 resident CTAs per SM the
   // 592-CTA statistics geometry ran 1.33 waves (a 2/3-empty tail).
-  ppc = 64 * P;
+  {
+    long want = (long(HW) * B + 148L * 8 - 1) / (148L * 8);  // ~8 CTAs per SM on small tensors ...
+    want = (want + 4L * P - 1) / (4L * P) * (4L * P);
+    if (want < 4L * P) want = 4L * P;
+    if (want > 64L * P) want = 64L * P;                      // ... at most 16 rounds per CTA on large ones
+    ppc = int(want);
+  }
   if (ppc > HW) ppc = HW;
   slabs = (HW + ppc - 1) / ppc;
   if (in16)
