@@ -170,6 +170,7 @@ typedef struct madm_gemm_args {
   int32_t stat_rows;      /* 32 (0 = 32) */
   int32_t mt;             /* M sub-tiles per CTA tile when bn = 128: 0 auto, 1 (128-row tiles), 2 (256-row tiles) */
   int32_t s2d_H, s2d_W;   /* > 0: out_bf16 is written in space-to-depth layout [4][B][H/2][W/2][N] (operand of a stride-2 conv) */
+  int32_t pair;           /* CTA pairs (tcgen05 cta_group::2, 256-row MMAs): 0 auto, 1 force, -1 never */
 } madm_gemm_args;
 
 int madm_op_gemm(const madm_gemm_args* a, madm_stream stream);

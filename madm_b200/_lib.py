@@ -56,7 +56,7 @@ class MadmGemmArgs(C.Structure):
         ("w", c_void_p), ("bias", c_void_p), ("rowbias", c_void_p), ("rows_per_img", c_int32), ("ld_rowbias", c_int32),
         ("residual", c_void_p), ("ldr", c_int32), ("out_f32", c_void_p), ("ldo32", c_int32),
         ("out_bf16", c_void_p), ("ldo16", c_int32), ("act", c_int32), ("alpha", c_float), ("bn", c_int32), ("dtype", c_int32),
-        ("colstats", c_void_p), ("stat_rows", c_int32), ("mt", c_int32), ("s2d_H", c_int32), ("s2d_W", c_int32),
+        ("colstats", c_void_p), ("stat_rows", c_int32), ("mt", c_int32), ("s2d_H", c_int32), ("s2d_W", c_int32), ("pair", c_int32),
     ]
 
 

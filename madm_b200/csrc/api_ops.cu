@@ -45,7 +45,7 @@ int madm_op_gemm(const madm_gemm_args* a, madm_stream stream) {
   d.residual = a->residual; d.ldr = a->ldr;
   d.out_f32 = a->out_f32; d.ldo32 = a->ldo32; d.out_bf16 = a->out_bf16; d.ldo16 = a->ldo16;
   d.act = a->act; d.alpha = a->alpha; d.bn = a->bn; d.fp16 = a->dtype == MADM_DTYPE_FP16;
-  d.colstats = a->colstats; d.stat_rows = a->stat_rows ? a->stat_rows : 32; d.mt = a->mt; d.s2d_H = a->s2d_H; d.s2d_W = a->s2d_W;
+  d.colstats = a->colstats; d.stat_rows = a->stat_rows ? a->stat_rows : 32; d.mt = a->mt; d.s2d_H = a->s2d_H; d.s2d_W = a->s2d_W; d.pair = a->pair;
   GemmLaunch L;
   if (const char* e = gemm_prepare(d, &L)) return fail(e);
   RUN(gemm_launch(L, static_cast<cudaStream_t>(stream)));

@@ -69,10 +69,14 @@ struct GemmParams {
 // layers (measured 12.7 TB/s of L2->SM reads at 42 % tensor-pipe activity on the VAE 512^2 convs).
 enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_S2D = 2 };  // epilogue variants (bit mask) compiled as separate kernels
 
-template <int BN, int MT>
+// PAIR: the CTA is one half of a cta_group::2 pair (cluster of 2): the pair's tile is 2*MT*128 rows x BN, each CTA stages its own
+// A rows and HALF of the W tile (BN/2 rows), and the leader's tcgen05.mma.cta_group::2 (M = 256) reads both halves.  Per CTA the
+// TMA fill per tensor-clock drops from (128*MT + BN) to (128*MT + BN/2) rows, which is what bounds these tiles.
+template <int BN, int MT, bool PAIR = false>
 struct Cfg {
   static constexpr int A_BYTES = MT * A_STAGE_BYTES;
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;  // W rows staged by this CTA
+  static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_BYTES = kEpiWarps * STG_WARP_BYTES;  // per-epilogue-warp transpose staging
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - EPI_BYTES;
@@ -167,9 +171,9 @@ __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int 
 //               i+1 overlap the epilogue of tile i
 //   warps 2..5  epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> coalesced fused epilogue
 //               (bias / time-embedding row bias / fp32 residual / SiLU / ReLU / GEGLU) -> fp32 and/or 16-bit stores
-template <int BN, int MT, int EPI>
+template <int BN, int MT, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN, MT>;
+  using C = Cfg<BN, MT, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -187,6 +191,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_chunks = p.kchunks[0] + (p.nseg > 1 ? p.kchunks[1] : 0);
+  // persistent tile walk: a CTA (or a CTA pair) starts at its index and strides by the number of CTAs (pairs)
+  const int rank = PAIR ? int(cluster_ctarank()) : 0;
+  const int walker = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int walkers = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA[0]);
@@ -198,16 +206,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), kEpiWarps);  // one arrival per epilogue warp
+      mbar_init(tmem_empty_bar(a), PAIR ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) { tmem_alloc_pair(tmem_slot, C::TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, C::TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before remote arrivals / TMA bytes reach them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -224,11 +233,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #else
 #define GI(acc, ...) __VA_ARGS__
 #endif
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int t = walker; t < p.num_tiles; t += walkers) {
         const int mn = t / p.splits, sp = t - mn * p.splits;
         const int tile_n = mn % p.n_tiles;
-        const int m0 = (mn / p.n_tiles) * (BM * MT);
-        const int n0 = tile_n * BN;
+        const int m0 = ((mn / p.n_tiles) * (PAIR ? 2 : 1) + rank) * (BM * MT);
+        const int n0 = tile_n * BN + rank * C::B_ROWS;
         const int kc0 = (total_chunks * sp) / p.splits, kc1 = (total_chunks * (sp + 1)) / p.splits;
         int x0[MT], y0[MT], b0[MT];
 #pragma unroll
@@ -251,12 +260,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const int tap = lk / p.cpt[seg];
           const int cc = lk - tap * p.cpt[seg];
           GI(pw, mbar_wait(empty_bar(stage), phase ^ 1u));
-          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          if constexpr (PAIR) {  // both CTAs' bytes are counted on the leader's barrier; only the leader arms it
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
 #pragma unroll
-          for (int s = 0; s < MT; ++s)
-            tma_load_4d(sA + stage * C::A_BYTES + s * A_STAGE_BYTES, &p.tmA[seg], full_bar(stage), cc * BK, x0[s] + p.dx[seg][tap],
-                        y0[s] + p.dy[seg][tap], b0[s] + p.boff[seg][tap]);
-          tma_load_2d(sB + stage * C::B_STAGE_BYTES, &p.tmB, full_bar(stage), kc * BK, n0);
+            for (int s = 0; s < MT; ++s)
+              tma_load_4d_pair(sA + stage * C::A_BYTES + s * A_STAGE_BYTES, &p.tmA[seg], full_bar(stage), cc * BK, x0[s] + p.dx[seg][tap],
+                               y0[s] + p.dy[seg][tap], b0[s] + p.boff[seg][tap]);
+            tma_load_2d_pair(sB + stage * C::B_STAGE_BYTES, &p.tmB, full_bar(stage), kc * BK, n0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+#pragma unroll
+            for (int s = 0; s < MT; ++s)
+              tma_load_4d(sA + stage * C::A_BYTES + s * A_STAGE_BYTES, &p.tmA[seg], full_bar(stage), cc * BK, x0[s] + p.dx[seg][tap],
+                          y0[s] + p.dy[seg][tap], b0[s] + p.boff[seg][tap]);
+            tma_load_2d(sB + stage * C::B_STAGE_BYTES, &p.tmB, full_bar(stage), kc * BK, n0);
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -268,9 +286,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #endif
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (elect_one()) {
-      const uint32_t idesc = make_idesc_16(BM, BN, p.fp16);
+    // ===================== MMA issuer (one thread; in a pair only the leader CTA issues) =====================
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = make_idesc_16(PAIR ? 2 * BM : BM, BN, p.fp16);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -278,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #ifdef GEMM_INSTR
       long long w_full = 0, w_acc = 0, t_issue = 0, t_commit = 0, mt0 = clock64(), n_mma = 0, n_chunks = 0, n_tiles_done = 0;
 #endif
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int t = walker; t < p.num_tiles; t += walkers) {
         GI(w_acc, mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u));  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tacc = tmem_base + uint32_t(acc * MT * C::ACC_STRIDE);
@@ -298,20 +316,27 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 32 B (16 elements) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-              umma_bf16_ss(tacc + uint32_t(s * C::ACC_STRIDE), adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
-                           (kc > kc0 || k > 0) ? 1u : 0u);
+              if constexpr (PAIR)
+                umma_f16_ss_pair(tacc + uint32_t(s * C::ACC_STRIDE), adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
+                                 (kc > kc0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16_ss(tacc + uint32_t(s * C::ACC_STRIDE), adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc,
+                             (kc > kc0 || k > 0) ? 1u : 0u);
             }
           }
 #ifdef GEMM_INSTR
           t_issue += clock64() - ti0;
 #endif
-          GI(t_commit, umma_commit(empty_bar(stage)));  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (PAIR) { GI(t_commit, umma_commit_pair(empty_bar(stage))); }
+          else { GI(t_commit, umma_commit(empty_bar(stage))); }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+        if constexpr (PAIR) umma_commit_pair(tmem_full_bar(acc));  // accumulator complete -> epilogue (of both CTAs)
+        else umma_commit(tmem_full_bar(acc));
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -350,10 +375,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     float* const out32_base = p.out_f32;
     const int splits = p.splits;
     const long split_stride = p.split_stride;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int t = walker; t < p.num_tiles; t += walkers) {
       const int mn = t / splits;
       const int tile_n = mn % n_tiles;
-      const int m0 = (mn / n_tiles) * (BM * MT);
+      const int m0 = ((mn / n_tiles) * (PAIR ? 2 : 1) + rank) * (BM * MT);
       const int n0 = tile_n * BN;
       float* const out32 = out32_base ? out32_base + long(t - mn * splits) * split_stride : nullptr;
       mbar_wait(tmem_full_bar(acc), acc_phase);
@@ -500,7 +525,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_leader(tmem_empty_bar(acc));  // the issuing thread lives in the leader CTA
+        else mbar_arrive(tmem_empty_bar(acc));
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -509,10 +537,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer may still be reading this CTA's smem / arriving on its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -650,16 +680,6 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
     cuuint32_t box[4] = {cuuint32_t(BK), cuuint32_t(L.box_w), cuuint32_t(L.box_h), cuuint32_t(L.box_b)};
     if (const char* e = encode_map(&L.tmA[s], sg.ptr, 4, dims, strides, box)) return e;
   }
-  {
-    const int Nw = d.Nw ? d.Nw : d.N;
-    if ((reinterpret_cast<uintptr_t>(d.w) & 15) != 0) return "gemm: W pointer must be 16B aligned";
-    cuuint64_t dims[2] = {cuuint64_t(ktot), cuuint64_t(Nw)};
-    const int ldw = d.ldw ? d.ldw : ktot;
-    if (ldw % 8 != 0 || ldw < ktot) return "gemm: weight pitch must be >= Ktot and a multiple of 8";
-    cuuint64_t strides[1] = {cuuint64_t(ldw) * 2};
-    cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(L.bn)};
-    if (const char* e = encode_map(&L.tmB, d.w, 2, dims, strides, box)) return e;
-  }
   const int Ncols = (d.act == ACT_GEGLU) ? 2 * d.N : d.N;
   const int n_tiles = (Ncols + L.bn - 1) / L.bn;
   // 256-row CTA tiles (two M sub-tiles sharing each W box) for the 128-wide N tile when there is enough work to keep every SM
@@ -669,7 +689,26 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
     const long tiles2 = long((d.M + 2 * BM - 1) / (2 * BM)) * n_tiles;
     if (d.mt == 2 || tiles2 >= 2L * num_sms()) L.mt = 2;
   }
-  const int m_tiles = (d.M + BM * L.mt - 1) / (BM * L.mt);
+  int m_tiles = (d.M + BM * L.mt - 1) / (BM * L.mt);
+  // CTA pairs: worthwhile when every pair still gets at least one full tile; needs an even CTA count
+  L.pair = 0;
+  {
+    static const int env_pair = getenv("MADM_GEMM_PAIR") ? atoi(getenv("MADM_GEMM_PAIR")) : 1;
+    const bool shape_ok = (L.bn >= 160 || (L.bn == 128 && L.mt == 2)) && d.act != ACT_GEGLU && num_sms() % 2 == 0;
+    const long pair_tiles = long((m_tiles + 1) / 2) * n_tiles;
+    if (shape_ok && d.pair >= 0 && (d.pair == 1 || (env_pair > 0 && pair_tiles >= num_sms() / 2))) L.pair = 1;
+  }
+  if (L.pair) m_tiles = (m_tiles + 1) / 2;  // tiles of the pair
+  {
+    const int Nw = d.Nw ? d.Nw : d.N;
+    if ((reinterpret_cast<uintptr_t>(d.w) & 15) != 0) return "gemm: W pointer must be 16B aligned";
+    cuuint64_t dims[2] = {cuuint64_t(ktot), cuuint64_t(Nw)};
+    const int ldw = d.ldw ? d.ldw : ktot;
+    if (ldw % 8 != 0 || ldw < ktot) return "gemm: weight pitch must be >= Ktot and a multiple of 8";
+    cuuint64_t strides[1] = {cuuint64_t(ldw) * 2};
+    cuuint32_t box[2] = {cuuint32_t(BK), cuuint32_t(L.pair ? L.bn / 2 : L.bn)};  // a pair's CTAs stage half of the W tile each
+    if (const char* e = encode_map(&L.tmB, d.w, 2, dims, strides, box)) return e;
+  }
   L.splits = 1;
   L.split_stride = 0;
   if (d.splits > 1) {  // split-K: raw fp32 partials, reduced (with the fused epilogue) by splitk_reduce
@@ -679,50 +718,71 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
     L.split_stride = d.split_stride;
   }
   L.num_tiles = n_tiles * m_tiles * L.splits;
-  L.grid = dim3(unsigned(L.num_tiles < num_sms() ? L.num_tiles : num_sms()));
+  if (L.pair) {
+    const int pairs = L.num_tiles < num_sms() / 2 ? L.num_tiles : num_sms() / 2;
+    L.grid = dim3(unsigned(2 * pairs));
+  } else {
+    L.grid = dim3(unsigned(L.num_tiles < num_sms() ? L.num_tiles : num_sms()));
+  }
   switch (L.bn) {
     case 16: L.smem = Cfg<16, 1>::SMEM; break;
     case 32: L.smem = Cfg<32, 1>::SMEM; break;
     case 64: L.smem = Cfg<64, 1>::SMEM; break;
-    case 128: L.smem = L.mt == 2 ? Cfg<128, 2>::SMEM : Cfg<128, 1>::SMEM; break;
-    case 160: L.smem = Cfg<160, 1>::SMEM; break;
-    case 192: L.smem = Cfg<192, 1>::SMEM; break;
-    case 256: L.smem = Cfg<256, 1>::SMEM; break;
+    case 128: L.smem = L.mt == 2 ? (L.pair ? Cfg<128, 2, true>::SMEM : Cfg<128, 2>::SMEM) : Cfg<128, 1>::SMEM; break;
+    case 160: L.smem = L.pair ? Cfg<160, 1, true>::SMEM : Cfg<160, 1>::SMEM; break;
+    case 192: L.smem = L.pair ? Cfg<192, 1, true>::SMEM : Cfg<192, 1>::SMEM; break;
+    case 256: L.smem = L.pair ? Cfg<256, 1, true>::SMEM : Cfg<256, 1>::SMEM; break;
     default: return "gemm: unsupported N tile";
   }
   return nullptr;
 }
 
-template <int BN, int MT, int EPI>
+template <int BN, int MT, int EPI, bool PAIR>
 static const char* launch_bn_s(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, MT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BN, MT>::SMEM)) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_tc_kernel<BN, MT, EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(Cfg<BN, MT, PAIR>::SMEM)) != cudaSuccess)
       return "gemm: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed";
     attr_set = true;
   }
-  gemm_tc_kernel<BN, MT, EPI><<<L.grid, kThreads, Cfg<BN, MT>::SMEM, stream>>>(p);
-  return cudaGetLastError() == cudaSuccess ? nullptr : "gemm: kernel launch failed";
+  if constexpr (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = L.grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<BN, MT, PAIR>::SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MT, EPI, PAIR>, p) != cudaSuccess) return "gemm: cluster launch failed";
+    return nullptr;
+  } else {
+    gemm_tc_kernel<BN, MT, EPI, PAIR><<<L.grid, kThreads, Cfg<BN, MT, PAIR>::SMEM, stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? nullptr : "gemm: kernel launch failed";
+  }
+}
+template <int BN, int MT, bool PAIR>
+static const char* launch_epi(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
+  const int epi = (p.s2d_W > 0 ? EPI_S2D : 0) | (p.colstats ? EPI_STATS : 0);
+  switch (epi) {
+    case 0: return launch_bn_s<BN, MT, 0, PAIR>(L, p, stream);
+    case 1: return launch_bn_s<BN, MT, 1, PAIR>(L, p, stream);
+    case 2: return launch_bn_s<BN, MT, 2, PAIR>(L, p, stream);
+    default: return launch_bn_s<BN, MT, 3, PAIR>(L, p, stream);
+  }
 }
 template <int BN>
 static const char* launch_bn(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
-  const int epi = (p.s2d_W > 0 ? EPI_S2D : 0) | (p.colstats ? EPI_STATS : 0);
   if constexpr (BN == 128) {
-    if (L.mt == 2) {
-      switch (epi) {
-        case 0: return launch_bn_s<BN, 2, 0>(L, p, stream);
-        case 1: return launch_bn_s<BN, 2, 1>(L, p, stream);
-        case 2: return launch_bn_s<BN, 2, 2>(L, p, stream);
-        default: return launch_bn_s<BN, 2, 3>(L, p, stream);
-      }
-    }
+    if (L.mt == 2) return L.pair ? launch_epi<BN, 2, true>(L, p, stream) : launch_epi<BN, 2, false>(L, p, stream);
   }
-  switch (epi) {
-    case 0: return launch_bn_s<BN, 1, 0>(L, p, stream);
-    case 1: return launch_bn_s<BN, 1, 1>(L, p, stream);
-    case 2: return launch_bn_s<BN, 1, 2>(L, p, stream);
-    default: return launch_bn_s<BN, 1, 3>(L, p, stream);
+  if constexpr (BN >= 160) {
+    if (L.pair) return launch_epi<BN, 1, true>(L, p, stream);
   }
+  return launch_epi<BN, 1, false>(L, p, stream);
 }
 
 const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {

@@ -43,6 +43,7 @@ struct GemmDesc {
   int bn = 0;                       // N tile (0 = auto)
   int fp16 = 0;                     // operand / 16-bit output dtype: 0 = bf16, 1 = fp16
   int s2d_H = 0, s2d_W = 0;         // >0: write out_bf16 in space-to-depth layout [4][B][H/2][W/2][N] (operand of a stride-2 conv)
+  int pair = 0;                     // CTA pairs (cta_group::2): 0 auto, 1 force, -1 never
   int mt = 0;                       // M sub-tiles per CTA tile for the 128-wide N tile: 0 auto, 1, or 2 (256-row tiles)
   int splits = 1;                   // split-K factor (>1: raw fp32 partial outputs at out_f32 + split * split_stride)
   long split_stride = 0;
@@ -61,6 +62,7 @@ struct GemmLaunch {  // prepared launch: tensor maps encoded once, replayed per 
   dim3 grid;
   int num_tiles = 0;
   int mt = 1;
+  int pair = 0;              // launched as cta_group::2 pairs (cluster of 2): tiles are 2*mt*128 rows
   int splits = 1;
   long split_stride = 0;
   size_t smem = 0;

@@ -62,7 +62,7 @@ def make_seg(a: torch.Tensor, Bt: int, H: int, W: int, Cc: int, ld: int = 0, tap
 def gemm(segs: Sequence[MadmGemmSeg], M: int, N: int, w: torch.Tensor, *, Nw: int = 0, ldw: int = 0,
          bias=None, rowbias=None, rows_per_img: int = 1, ld_rowbias: int = 0, residual=None, ldr: int = 0,
          out_f32=None, ldo32: int = 0, out_bf16=None, ldo16: int = 0, act: int = 0, alpha: float = 1.0, bn: int = 0,
-         colstats=None, stat_rows: int = 0, mt: int = 0, s2d_hw=None):
+         colstats=None, stat_rows: int = 0, mt: int = 0, s2d_hw=None, pair: int = 0):
     a = MadmGemmArgs()
     a.nseg = len(segs)
     for i, s in enumerate(segs):
@@ -83,6 +83,7 @@ def gemm(segs: Sequence[MadmGemmSeg], M: int, N: int, w: torch.Tensor, *, Nw: in
     a.colstats = colstats.data_ptr() if colstats is not None else None
     a.stat_rows = stat_rows
     a.mt = mt
+    a.pair = pair
     if s2d_hw is not None:
         a.s2d_H, a.s2d_W = s2d_hw
     lib = _lib.load()
