@@ -694,7 +694,7 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   L.pair = 0;
   {
     static const int env_pair = getenv("MADM_GEMM_PAIR") ? atoi(getenv("MADM_GEMM_PAIR")) : 1;
-    const bool shape_ok = (L.bn >= 160 || (L.bn == 128 && L.mt == 2)) && d.act != ACT_GEGLU && num_sms() % 2 == 0;
+    const bool shape_ok = L.bn >= 128 && num_sms() % 2 == 0;
     const long pair_tiles = long((m_tiles + 1) / 2) * n_tiles;
     if (shape_ok && d.pair >= 0 && (d.pair == 1 || (env_pair > 0 && pair_tiles >= num_sms() / 2))) L.pair = 1;
   }
@@ -728,7 +728,7 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
     case 16: L.smem = Cfg<16, 1>::SMEM; break;
     case 32: L.smem = Cfg<32, 1>::SMEM; break;
     case 64: L.smem = Cfg<64, 1>::SMEM; break;
-    case 128: L.smem = L.mt == 2 ? (L.pair ? Cfg<128, 2, true>::SMEM : Cfg<128, 2>::SMEM) : Cfg<128, 1>::SMEM; break;
+    case 128: L.smem = L.mt == 2 ? (L.pair ? Cfg<128, 2, true>::SMEM : Cfg<128, 2>::SMEM) : (L.pair ? Cfg<128, 1, true>::SMEM : Cfg<128, 1>::SMEM); break;
     case 160: L.smem = L.pair ? Cfg<160, 1, true>::SMEM : Cfg<160, 1>::SMEM; break;
     case 192: L.smem = L.pair ? Cfg<192, 1, true>::SMEM : Cfg<192, 1>::SMEM; break;
     case 256: L.smem = L.pair ? Cfg<256, 1, true>::SMEM : Cfg<256, 1>::SMEM; break;
@@ -779,7 +779,7 @@ static const char* launch_bn(const GemmLaunch& L, const GemmParams& p, cudaStrea
   if constexpr (BN == 128) {
     if (L.mt == 2) return L.pair ? launch_epi<BN, 2, true>(L, p, stream) : launch_epi<BN, 2, false>(L, p, stream);
   }
-  if constexpr (BN >= 160) {
+  if constexpr (BN >= 128) {
     if (L.pair) return launch_epi<BN, 1, true>(L, p, stream);
   }
   return launch_epi<BN, 1, false>(L, p, stream);

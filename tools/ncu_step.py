@@ -21,6 +21,7 @@ args = ap.parse_args()
 dev = torch.device("cuda:0")
 bb = build_product_backbone(dev, compute_dtype=args.dtype)
 set_lora_adapter(bb.feature_extractor.ldm_extractor.unet, "Depth")
+bb.feature_extractor.ldm_extractor.engine().graph_max_batch = 0  # profile the stream launches, not a graph replay
 img = torch.rand(args.batch, 3, 512, 512, device=dev)
 with torch.no_grad():
     for _ in range(2):
