@@ -90,6 +90,10 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float lo
 #define MADM_STAGE_UNET 2  /* add_noise + diffusion_unet (ldm_diffusers.py:349-360, :454-616) */
 #define MADM_STAGE_PROJ 4  /* forward_features      (reference feature_extractor.py:367-396) */
 #define MADM_STAGE_ALL 7
+/* SURVEY §8 row f-2 (next after the path): DAFormerHead.forward (modeling/sem_seg_head/daformer_head.py:702-749) on the feature
+ * dict: reads args.out[0..3] (s2..s5, produced by MADM_STAGE_PROJ in the same call or supplied by the caller) and writes
+ * args.logits.  Needs the head's parameters registered under "sem_seg_head." (a context may hold only those). */
+#define MADM_STAGE_HEAD 8
 
 /* Workspace bytes needed by madm_extract for batch B (all stages). */
 size_t madm_workspace_bytes(madm_ctx* ctx, int32_t B);
@@ -115,6 +119,7 @@ typedef struct madm_extract_args {
   size_t workspace_bytes;
   int32_t* range_flag;         /* optional device int: set to 1 if the normalised image leaves [-1,1]
                                   (the reference asserts this with a host sync, ldm_diffusers.py:147) */
+  float* logits;               /* MADM_STAGE_HEAD: [B,num_classes,128,128] fp32 NCHW (DAFormerHead output, before any resize) */
 } madm_extract_args;
 
 /* The whole path a-1..a-9 of SURVEY §8: VAE encode -> q-sample -> UNet forward with taps -> GN-bottleneck projections. */
@@ -198,6 +203,12 @@ int madm_op_pack_geglu(const float* w, const float* bias, int32_t C4, int32_t K,
                        int32_t dtype, madm_stream stream);
 int madm_op_space_to_depth(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, int32_t dtype,
                            madm_stream stream);
+/* head stage kernels (reference daformer_head.py:702-749, mmseg resize, mmcv DepthwiseSeparableConvModule) */
+int madm_op_nchw_to_nhwc16(const float* x, int32_t B, int32_t C, int32_t HW, void* out16, int32_t dtype, madm_stream stream);
+int madm_op_bilinear_resize(const void* src16, int32_t B, int32_t Hs, int32_t Ws, int32_t C, void* dst16, int32_t Hd, int32_t Wd,
+                            int32_t dst_pitch, int32_t dtype, madm_stream stream); /* F.interpolate(bilinear, align_corners=False), NHWC */
+int madm_op_depthwise3x3(const void* src16, int32_t B, int32_t H, int32_t W, int32_t C, int32_t dilation, const float* w9 /*[9][C]*/,
+                         const float* shift /*[C]*/, void* dst16, int32_t dtype, madm_stream stream); /* + shift + ReLU */
 int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, int32_t dtype,
                        madm_stream stream);
 int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out_bf16, int32_t* range_flag,

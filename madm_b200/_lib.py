@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("MADM_B200_LIB") or os.path.join(_HERE, "libmadm_b200.
 
 MADM_OK = 0
 STAGE_VAE, STAGE_UNET, STAGE_PROJ, STAGE_ALL = 1, 2, 4, 7
+STAGE_HEAD = 8
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU = 0, 1, 2, 3
 DTYPE_BF16, DTYPE_FP16 = 0, 1
 
@@ -33,7 +34,7 @@ class MadmExtractArgs(C.Structure):
         ("out", c_void_p * 4),
         ("latents", c_void_p), ("noisy_latents", c_void_p), ("taps", c_void_p * 4),
         ("packed", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
-        ("range_flag", c_void_p),
+        ("range_flag", c_void_p), ("logits", c_void_p),
     ]
 
 
@@ -91,6 +92,9 @@ SYMBOLS = {
     "madm_op_pack_conv": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
     "madm_op_pack_geglu": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
     "madm_op_space_to_depth": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_nchw_to_nhwc16": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_bilinear_resize": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "madm_op_depthwise3x3": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "madm_op_upsample2x": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_image_im2col": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
     "madm_op_gn_add_relu_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,

@@ -125,10 +125,10 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
 
     # ------------------------------------------------------------------ engine plumbing
     def _projection_tensors(self) -> List[Tuple[str, torch.Tensor]]:
-        out = [("feature_projections." + n, p.data) for n, p in self.feature_projections.named_parameters()]
+        out = [("feature_projections." + n, p.detach()) for n, p in self.feature_projections.named_parameters()]
         ema = getattr(self, "ema_feature_projections", None)  # set by CMDISE._inti_ema_weights (cmdise.py:308)
         if ema is not None:
-            out += [("ema_feature_projections." + n, p.data) for n, p in ema.named_parameters()]
+            out += [("ema_feature_projections." + n, p.detach()) for n, p in ema.named_parameters()]
         return out
 
     def _extract(self, img, input_modal, ema_forward, timestep, want_taps=False, timesteps=None, **kwargs):

@@ -105,6 +105,20 @@ int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t 
   RUN(upsample_nearest2x(x, B, H, W, C, out, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
+int madm_op_nchw_to_nhwc16(const float* x, int32_t B, int32_t C, int32_t HW, void* out, int32_t dtype, madm_stream stream) {
+  RUN(nchw_to_nhwc16(x, B, C, HW, out, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_bilinear_resize(const void* src, int32_t B, int32_t Hs, int32_t Ws, int32_t C, void* dst, int32_t Hd, int32_t Wd, int32_t ldd,
+                            int32_t dtype, madm_stream stream) {
+  RUN(bilinear_resize_nhwc16(src, B, Hs, Ws, C, dst, Hd, Wd, ldd, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_depthwise3x3(const void* src, int32_t B, int32_t H, int32_t W, int32_t C, int32_t dilation, const float* w9, const float* shift,
+                         void* dst, int32_t dtype, madm_stream stream) {
+  RUN(depthwise3x3_nhwc16(src, B, H, W, C, dilation, w9, shift, dst, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+}
+
 int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out, int32_t* range_flag, int32_t dtype,
                          madm_stream stream) {
   RUN(image_im2col(img, B, H, W, out, range_flag, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));

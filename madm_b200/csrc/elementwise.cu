@@ -255,6 +255,27 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int HW, int C, 
   }
 }
 
+// the same from rows of pitch ld >= C (padded GEMM output, e.g. 19 class logits in 32 columns)
+__global__ void nhwc_to_nchw_strided_kernel(const float* __restrict__ x, int HW, int C, int ld, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    tile[r][tx] = (p < HW && c < C) ? x[(size_t(b) * HW + p) * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    if (p < HW && c < C) out[(size_t(b) * C + c) * HW + p] = tile[tx][r];
+  }
+}
+const char* nhwc_to_nchw_strided(const float* x, int B, int HW, int C, int ld, float* out, cudaStream_t st) {
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+  nhwc_to_nchw_strided_kernel<<<grid, dim3(32, 8), 0, st>>>(x, HW, C, ld, out);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "nhwc_to_nchw_strided launch failed";
+}
+
 const char* nhwc_to_nchw(const float* x, int B, int HW, int C, float* out, cudaStream_t st) {
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
   nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(x, HW, C, out);

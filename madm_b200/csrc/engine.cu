@@ -42,7 +42,10 @@ struct ParamRef {
 };
 
 // ---- packed arena entries
-enum PackKind { PK_CONV, PK_LINEAR, PK_GEGLU, PK_VAE_HEAD, PK_F32_COPY, PK_F32_SUM2, PK_F32_GEGLU_BIAS };
+enum PackKind { PK_CONV, PK_LINEAR, PK_GEGLU, PK_VAE_HEAD, PK_F32_COPY, PK_F32_SUM2, PK_F32_GEGLU_BIAS,
+                PK_BN_FOLD,   // eval-mode BatchNorm -> fp32 [scale | shift] (bias_off = N floats each)
+                PK_CONV_BN,   // conv weight with the BatchNorm scale (at bias_off) folded into its rows
+                PK_DW_BN };   // depthwise 3x3 weight * BatchNorm scale -> fp32 [9][C]
 struct PackEntry {
   PackKind kind;
   std::string src, src2, src3, src4;  // parameter names
@@ -314,6 +317,33 @@ struct Builder {
       e.off = pack_reserve(size_t(N) * K * 2);
       return e;
     }).off;
+  }
+  // mmcv ConvModule (conv without bias -> BatchNorm(eval) -> ReLU): BN scale folded into the packed weight rows, shift = epilogue bias
+  struct ConvBn { size_t w_off, shift_off; };
+  ConvBn conv_bn(const std::string& mod, int N, int C, int taps) {
+    const size_t fold = entry("bnfold:" + mod, [&] {
+      PackEntry e; e.kind = PK_BN_FOLD; e.src = mod + ".bn"; e.N = N; e.off = pack_reserve(size_t(2) * N * 4);
+      return e;
+    }).off;
+    const int Kpad = taps * C;
+    const size_t w = entry("convbn:" + mod, [&] {
+      PackEntry e; e.kind = PK_CONV_BN; e.src = mod + ".conv.weight"; e.N = N; e.C = C; e.taps = taps; e.Cpad = C; e.Kpad = Kpad; e.ldo = Kpad;
+      e.bias_off = fold; e.off = pack_reserve(size_t(N) * Kpad * 2);
+      return e;
+    }).off;
+    return ConvBn{w, fold + size_t(N) * 4};
+  }
+  // depthwise ConvModule: fp32 [9][C] weights (scale folded) + shift
+  ConvBn depthwise_bn(const std::string& mod, int C) {
+    const size_t fold = entry("bnfold:" + mod, [&] {
+      PackEntry e; e.kind = PK_BN_FOLD; e.src = mod + ".bn"; e.N = C; e.off = pack_reserve(size_t(2) * C * 4);
+      return e;
+    }).off;
+    const size_t w = entry("dwbn:" + mod, [&] {
+      PackEntry e; e.kind = PK_DW_BN; e.src = mod + ".conv.weight"; e.C = C; e.bias_off = fold; e.off = pack_reserve(size_t(9) * C * 4);
+      return e;
+    }).off;
+    return ConvBn{w, fold + size_t(C) * 4};
   }
   void f32_part(const std::string& name, size_t region_off, int elem_off, int n) {
     entry("f32:" + name, [&] { PackEntry e; e.kind = PK_F32_COPY; e.src = name; e.N = n; e.off = region_off + size_t(elem_off) * 4; return e; });
@@ -996,11 +1026,115 @@ struct Model {
     }
   }
 
+  // ---- DAFormerHead.forward (reference modeling/sem_seg_head/daformer_head.py:702-749) on the feature dict
+  // s2..s5 (fp32 NCHW, args.out[0..3]): MLP embeds 512 -> E at native resolution, bilinear resize (align_corners=False) to the s2
+  // grid, concat, depthwise-separable ASPP (1x1 + 3 dilated branches) with eval-mode BatchNorm folded + ReLU, 3x3 bottleneck,
+  // 1x1 classifier -> args.logits [B, classes, 128, 128].
+  bool has_head() const { return b.ctx->params.count("sem_seg_head.conv_seg.weight") != 0; }
+  void build_head() {
+    b.cur_stage = MADM_STAGE_HEAD;
+    std::shared_ptr<IoBind> io = dry() ? nullptr : b.plan->io;
+    const std::string h = "sem_seg_head.";
+    const ParamRef* cs = b.find(h + "conv_seg.weight");
+    const ParamRef* e0 = b.find(h + "embed_layers.0.proj.weight");
+    if (!cs || !e0) b.fail(MADM_ENOTFOUND, "sem_seg_head parameters are not registered");
+    const int ncls = int(cs->shape[0]), CH = int(cs->shape[1]), E = int(e0->shape[0]), Cin = int(e0->shape[1]);
+    if (Cin != 512 || E % 64 != 0 || CH % 64 != 0 || ncls > 32) b.fail(MADM_EINVAL, "sem_seg_head: unsupported channel configuration");
+    const int Bn = b.B, side[4] = {128, 64, 32, 16}, H = 128, W = 128, CAT = 4 * E;
+    const long M = long(Bn) * H * W;
+    const int f16v = f16();
+    B16T cat = b.b16(size_t(M) * CAT);
+    for (int i = 0; i < 4; ++i) {
+      const int Hi = side[i], HWi = Hi * Hi;
+      const long Mi = long(Bn) * HWi;
+      B16T x = b.b16(size_t(Mi) * Cin);
+      if (dry()) b.emit(nullptr);
+      else {
+        bf16* xp = x.p;
+        b.emit([=](cudaStream_t st) -> const char* {
+          const float* src = io->a.out[i];
+          if (!src) return "madm_extract: the head stage needs the feature maps in args.out[0..3]";
+          return nchw_to_nhwc16(src, Bn, Cin, HWi, xp, f16v, st);
+        }, false, MADM_KIND_ELEMENTWISE, 0.0, double(Mi) * Cin * 6);
+      }
+      const std::string lin = h + "embed_layers." + std::to_string(i) + ".proj";
+      GemmDesc d; d.seg[0] = Builder::seg_plain(x.p, Mi, Cin); d.M = int(Mi); d.N = E; d.Nw = E;
+      d.w = b.pw(b.linear_w(lin, E, Cin, false)); d.bias = P(lin + ".bias", E);
+      if (i == 0) {  // already on the s2 grid: straight into its slice of the concat buffer
+        d.out_bf16 = cat.p; d.ldo16 = CAT;
+        b.gemm(d);
+      } else {
+        B16T e = b.b16(size_t(Mi) * E);
+        d.out_bf16 = e.p; d.ldo16 = E;
+        b.gemm(d);
+        bf16* ep = e.p; bf16* dst = cat.p + size_t(i) * E;
+        b.emit([=](cudaStream_t st) { return bilinear_resize_nhwc16(ep, Bn, Hi, Hi, E, dst, H, W, CAT, f16v, st); }, false, MADM_KIND_ELEMENTWISE,
+               0.0, double(M) * E * 2 + double(Mi) * E * 2);
+        b.free(e);
+      }
+      b.free(x);
+    }
+    // ASPP: branch 0 = 1x1 ConvModule, branches 1..3 = depthwise 3x3 (dilation 6/12/18) -> pointwise 1x1; outputs concatenated
+    const std::string as = h + "fuse_layer.aspp_modules.";
+    B16T aspp = b.b16(size_t(M) * 4 * CH);
+    {
+      const Builder::ConvBn c = b.conv_bn(as + "0", CH, CAT, 1);
+      GemmDesc d; d.seg[0] = Builder::seg_1x1(cat.p, Bn, H, W, CAT); d.M = int(M); d.N = CH; d.Nw = CH;
+      d.w = b.pw(c.w_off); d.bias = b.pf(c.shift_off); d.act = ACT_RELU; d.out_bf16 = aspp.p; d.ldo16 = 4 * CH;
+      b.gemm(d);
+    }
+    const int dil[3] = {6, 12, 18};
+    for (int j = 1; j <= 3; ++j) {
+      const std::string m = as + std::to_string(j);
+      const Builder::ConvBn dw = b.depthwise_bn(m + ".depthwise_conv", CAT);
+      B16T t = b.b16(size_t(M) * CAT);
+      { const bf16* src = cat.p; bf16* dst = t.p; const float* w9 = b.pf(dw.w_off); const float* sh = b.pf(dw.shift_off); const int dl = dil[j - 1];
+        b.emit([=](cudaStream_t st) { return depthwise3x3_nhwc16(src, Bn, H, W, CAT, dl, w9, sh, dst, f16v, st); }, false, MADM_KIND_ELEMENTWISE, 0.0,
+               double(M) * CAT * 4); }
+      const Builder::ConvBn pwc = b.conv_bn(m + ".pointwise_conv", CH, CAT, 1);
+      GemmDesc d; d.seg[0] = Builder::seg_1x1(t.p, Bn, H, W, CAT); d.M = int(M); d.N = CH; d.Nw = CH;
+      d.w = b.pw(pwc.w_off); d.bias = b.pf(pwc.shift_off); d.act = ACT_RELU; d.out_bf16 = aspp.p + size_t(j) * CH; d.ldo16 = 4 * CH;
+      b.gemm(d);
+      b.free(t);
+    }
+    b.free(cat);
+    B16T bott = b.b16(size_t(M) * CH);
+    {
+      const Builder::ConvBn c = b.conv_bn(h + "fuse_layer.bottleneck", CH, 4 * CH, 9);
+      GemmDesc d; d.seg[0] = Builder::seg_3x3(aspp.p, Bn, H, W, 4 * CH); d.M = int(M); d.N = CH; d.Nw = CH;
+      d.w = b.pw(c.w_off); d.bias = b.pf(c.shift_off); d.act = ACT_RELU; d.out_bf16 = bott.p; d.ldo16 = CH;
+      b.gemm(d);
+    }
+    b.free(aspp);
+    // classifier: 1x1 conv CH -> classes (+bias); N padded to 32 columns in the fp32 NHWC scratch, then NCHW into args.logits
+    F32T lg = b.f32(size_t(M) * 32);
+    {
+      GemmDesc d; d.seg[0] = Builder::seg_1x1(bott.p, Bn, H, W, CH); d.M = int(M); d.N = ncls; d.Nw = ncls;
+      d.w = b.pw(b.conv_w(h + "conv_seg", ncls, CH, 1)); d.bias = P(h + "conv_seg.bias", ncls); d.out_f32 = lg.p; d.ldo32 = 32; d.bn = 32;
+      b.gemm(d);
+    }
+    b.free(bott);
+    if (dry()) b.emit(nullptr);
+    else {
+      const float* lp = lg.p;
+      b.emit([=](cudaStream_t st) -> const char* {
+        float* dst = io->a.logits;
+        if (!dst) return "madm_extract: logits pointer is null";
+        return nhwc_to_nchw_strided(lp, Bn, H * W, ncls, 32, dst, st);
+      }, false, MADM_KIND_ELEMENTWISE, 0.0, double(M) * ncls * 8);
+    }
+    b.free(lg);
+  }
+
+  bool has_path() const { return b.ctx->params.count(kUnet + "conv_in.weight") != 0; }
   void build_all() {
-    enumerate_unet();
-    build_vae();
-    build_unet();
-    build_proj();
+    if (has_path() || !has_head()) {  // a context that holds only sem_seg_head.* runs the head alone
+      enumerate_unet();
+      build_vae();
+      build_unet();
+      build_proj();
+    }
+    if (has_head()) build_head();
   }
 };
 
@@ -1213,6 +1347,29 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float sc
         const ParamRef* s = get(e.src);
         if (!s) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
         if (cudaMemcpyAsync(base + e.off, s->p, size_t(e.N) * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) err = "cudaMemcpyAsync failed";
+        break;
+      }
+      case PK_BN_FOLD: {
+        const ParamRef *g = get(e.src + ".weight"), *bt = get(e.src + ".bias"), *mu = get(e.src + ".running_mean"), *var = get(e.src + ".running_var");
+        if (!g || !bt || !mu || !var) return set_err(ctx, MADM_ENOTFOUND, "BatchNorm parameters / running statistics not registered: " + e.src);
+        if (g->numel() != e.N || bt->numel() != e.N || mu->numel() != e.N || var->numel() != e.N)
+          return set_err(ctx, MADM_EINVAL, "unexpected shape: " + e.src);
+        err = bn_fold(g->p, bt->p, mu->p, var->p, nullptr, 1e-5f, e.N, reinterpret_cast<float*>(base + e.off), st);
+        break;
+      }
+      case PK_CONV_BN: {
+        const ParamRef* w = get(e.src);
+        if (!w) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
+        if (w->numel() != int64_t(e.N) * e.C * e.taps) return set_err(ctx, MADM_EINVAL, "unexpected shape: " + e.src);
+        err = pack_conv_weight(w->p, e.N, e.C, e.taps, e.Cpad, e.Kpad, e.ldo, base + e.off, ctx->fp16, st,
+                               reinterpret_cast<const float*>(base + e.bias_off));
+        break;
+      }
+      case PK_DW_BN: {
+        const ParamRef* w = get(e.src);
+        if (!w) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
+        if (w->numel() != int64_t(e.C) * 9) return set_err(ctx, MADM_EINVAL, "unexpected shape: " + e.src);
+        err = pack_depthwise(w->p, reinterpret_cast<const float*>(base + e.bias_off), e.C, reinterpret_cast<float*>(base + e.off), st);
         break;
       }
       case PK_F32_SUM2: {

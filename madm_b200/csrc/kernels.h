@@ -74,11 +74,26 @@ const char* splitk_reduce(const float* part, int splits, long split_stride, int 
                           int act, int fp16, cudaStream_t st);
 // fp32 NHWC [B,HW,C] -> NCHW fp32 [B,C,HW]
 const char* nhwc_to_nchw(const float* x, int B, int HW, int C, float* out, cudaStream_t st);
+const char* nhwc_to_nchw_strided(const float* x, int B, int HW, int C, int ld, float* out, cudaStream_t st);
+
+// ---- head.cu (DAFormer head stage)
+// fp32 NCHW [B,C,HW] -> 16-bit NHWC [B,HW,C]
+const char* nchw_to_nhwc16(const float* x, int B, int C, int HW, void* out16, int fp16, cudaStream_t st);
+// bilinear resize (align_corners=False) of 16-bit NHWC [B,Hs,Ws,C] -> [B,Hd,Wd,C] written with channel pitch ldd
+const char* bilinear_resize_nhwc16(const void* src, int B, int Hs, int Ws, int C, void* dst, int Hd, int Wd, int ldd, int fp16, cudaStream_t st);
+// depthwise 3x3 conv, dilation = padding = dil, + shift + ReLU; w9 fp32 [9][C] (BatchNorm scale folded), shift fp32 [C]
+const char* depthwise3x3_nhwc16(const void* src, int B, int H, int W, int C, int dil, const float* w9, const float* shift, void* dst, int fp16,
+                                cudaStream_t st);
+// eval-mode BatchNorm -> out[0..N) = scale, out[N..2N) = shift (conv_bias optional)
+const char* bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, const float* conv_bias, float eps, int N,
+                    float* out, cudaStream_t st);
+// depthwise weight [C,1,3,3] * scale[c] -> fp32 [9][C]
+const char* pack_depthwise(const float* w, const float* scale, int C, float* out, cudaStream_t st);
 
 // ---- pack.cu (weight packing; fp32 PyTorch layouts -> bf16 K-major GEMM operands)
 // conv weight [N, C, kh, kw] fp32 -> [N, kh*kw*Cpad] bf16 with K index = tap*Cpad + c (zero fill for c >= C)
 const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out_bf16, int fp16,
-                             cudaStream_t st);
+                             cudaStream_t st, const float* row_scale = nullptr);
 // linear weight [N, K] (+ LoRA: + scale * B[N,r] @ A[r,K]) -> bf16 [N, K] written at row offset / interleave
 const char* pack_linear_weight(const float* w, int N, int K, const float* lora_a, const float* lora_b, int r, float scale,
                                int ldo, void* out_bf16, int fp16, cudaStream_t st);

@@ -9,7 +9,7 @@ namespace madm {
 
 // out[n, tap*Cpad + c] = w[n, c, tap]  (w is [N, C, taps] contiguous = [N,C,kh,kw]); zero for c >= C and k >= taps*Cpad
 __global__ void pack_conv_kernel(const float* __restrict__ w, int N, int C, int taps, int Cpad, int Kpad, int ldo, int fp16,
-                                 uint16_t* __restrict__ out) {
+                                 uint16_t* __restrict__ out, const float* __restrict__ row_scale) {
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const long total = long(N) * Kpad;
   if (i >= total) return;
@@ -20,12 +20,15 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int N, int C, int 
     const int tap = k / Cpad, c = k % Cpad;
     if (c < C) v = w[(size_t(n) * C + c) * taps + tap];
   }
+  if (row_scale) v *= row_scale[n];  // eval-mode BatchNorm scale of output channel n folded into the weight (fp32, before rounding)
   out[size_t(n) * ldo + k] = cvt_16(v, fp16);
 }
 
-const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out, int fp16, cudaStream_t st) {
+const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out, int fp16, cudaStream_t st,
+                             const float* row_scale) {
   const long total = long(N) * Kpad;
-  pack_conv_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w, N, C, taps, Cpad, Kpad, ldo, fp16, reinterpret_cast<uint16_t*>(out));
+  pack_conv_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w, N, C, taps, Cpad, Kpad, ldo, fp16, reinterpret_cast<uint16_t*>(out),
+                                                                  row_scale);
   return cudaGetLastError() == cudaSuccess ? nullptr : "pack_conv_weight launch failed";
 }
 

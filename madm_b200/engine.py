@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import MadmExtractArgs, MadmTensor, STAGE_ALL, STAGE_PROJ, STAGE_UNET, STAGE_VAE
+from ._lib import MadmExtractArgs, MadmTensor, STAGE_ALL, STAGE_HEAD, STAGE_PROJ, STAGE_UNET, STAGE_VAE
 
 TAP_SHAPES = ((512, 128), (320, 64), (640, 32), (1280, 16))  # enc tap, unet taps (C, HW side)
 OUT_SIDES = (128, 64, 32, 16)                                  # s2..s5
@@ -138,6 +138,33 @@ class Engine:
         for k, v in g["res"].items():  # fresh tensors, like the eager path: the static buffers are overwritten by the next replay
             out[k] = [t.clone() for t in v] if isinstance(v, list) else v.clone()
         return out
+
+    # ------------------------------------------------------------------ DAFormer head
+    def head(self, feats: Sequence[torch.Tensor], num_classes: int) -> torch.Tensor:
+        """``MADM_STAGE_HEAD`` on the feature dict: s2..s5 fp32 NCHW [B,512,side,side] -> logits [B,num_classes,128,128]."""
+        if self._packed is None:
+            raise _lib.MadmError("Engine.head called before ensure_packed()")
+        dev = self.device
+        B = feats[0].shape[0]
+        a = MadmExtractArgs()
+        a.B, a.stages, a.ema = B, STAGE_HEAD, 0
+        keep = []
+        for i, side in enumerate(OUT_SIDES):
+            t = feats[i]
+            if t.device != dev or tuple(t.shape) != (B, 512, side, side):
+                raise _lib.MadmError(f"feature map {i} must be [{B},512,{side},{side}] on {dev}, got {tuple(t.shape)} on {t.device}")
+            t = t.to(torch.float32).contiguous()
+            keep.append(t)
+            a.out[i] = t.data_ptr()
+        logits = torch.empty(B, num_classes, OUT_SIDES[0], OUT_SIDES[0], dtype=torch.float32, device=dev)
+        a.logits = logits.data_ptr()
+        ws = self.workspace(B)
+        a.packed = self._packed.data_ptr()
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(self.lib.madm_extract(self.ctx, C.byref(a), st), self.ctx, "madm_extract(head)")
+        self._keep = keep
+        return logits
 
     # ------------------------------------------------------------------ the hot path
     def extract(self, img: Optional[torch.Tensor], cond_inputs: torch.Tensor, cond_emb: torch.Tensor, timesteps: torch.Tensor,

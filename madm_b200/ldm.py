@@ -143,8 +143,8 @@ class LdmDiffusers(nn.Module):
 
     def named_engine_tensors(self) -> List[Tuple[str, torch.Tensor]]:
         pre = "feature_extractor.ldm_extractor."
-        out = [(pre + "unet." + n, p.data) for n, p in self.unet.named_parameters()]
-        out += [(pre + "vae." + n, p.data) for n, p in self.vae.named_parameters()]
+        out = [(pre + "unet." + n, p.detach()) for n, p in self.unet.named_parameters()]
+        out += [(pre + "vae." + n, p.detach()) for n, p in self.vae.named_parameters()]
         return out
 
     def prepare(self, extra: Sequence[Tuple[str, torch.Tensor]] = ()):

@@ -175,6 +175,35 @@ def upsample2x(x, dtype=torch.float16):
     return out
 
 
+def nchw_to_nhwc16(x, dtype=torch.float16):
+    lib = _lib.load()
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, H, W, Cc, dtype=dtype, device=x.device)
+    _lib.check(lib.madm_op_nchw_to_nhwc16(_ptr(x), B, Cc, H * W, _ptr(out), _dt(dtype), _stream()), None, "madm_op_nchw_to_nhwc16")
+    return out
+
+
+def bilinear_resize(x, Hd, Wd, out=None, pitch=0):
+    """x: 16-bit NHWC [B,Hs,Ws,C] -> [B,Hd,Wd,C] (F.interpolate bilinear, align_corners=False), optionally into a wider buffer."""
+    lib = _lib.load()
+    B, Hs, Ws, Cc = x.shape
+    if out is None:
+        out = torch.empty(B, Hd, Wd, Cc, dtype=x.dtype, device=x.device)
+    _lib.check(lib.madm_op_bilinear_resize(_ptr(x), B, Hs, Ws, Cc, _ptr(out), Hd, Wd, pitch or Cc, _dt(x.dtype), _stream()), None,
+               "madm_op_bilinear_resize")
+    return out
+
+
+def depthwise3x3(x, w9, shift, dilation):
+    """x: 16-bit NHWC; w9 fp32 [9,C]; shift fp32 [C] -> relu(depthwise_conv(x) + shift), 16-bit NHWC."""
+    lib = _lib.load()
+    B, H, W, Cc = x.shape
+    out = torch.empty_like(x)
+    _lib.check(lib.madm_op_depthwise3x3(_ptr(x), B, H, W, Cc, dilation, _ptr(w9), _ptr(shift), _ptr(out), _dt(x.dtype), _stream()), None,
+               "madm_op_depthwise3x3")
+    return out
+
+
 def image_im2col(img, range_flag=None, dtype=torch.float16):
     lib = _lib.load()
     B, _, H, W = img.shape

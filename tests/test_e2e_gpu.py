@@ -181,6 +181,34 @@ def test_slide_forward_512x1024(pair, cuda_device):
         _check("slide/" + k, out[k], ref[k])
 
 
+def test_inplace_parameter_update_repacks(pair, cuda_device):
+    """The engine keeps 16-bit packed copies of the weights; an in-place update of a parameter after the first forward (optimizer
+    step, load_state_dict -> copy_) must be seen through the shared version counter and trigger a repack."""
+    from oracle import synthetic
+    from oracle.lora import set_adapter
+    ob, pb = pair
+    set_adapter(ob.feature_extractor.ldm_extractor.unet, ["Depth"])
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    img = synthetic.synthetic_images(1, seed=5).to(cuda_device)
+    wo = ob.feature_projections[1][0].conv1.weight
+    wp = pb.feature_projections[1][0].conv1.weight
+    uo = ob.feature_extractor.ldm_extractor.unet.conv_in.weight
+    up = pb.feature_extractor.ldm_extractor.unet.conv_in.weight
+    with torch.no_grad():
+        before = pb(img, input_modal="others")["output_features"]["s3"].clone()
+        for t in (wo, wp, uo, up):
+            t.mul_(1.25)
+        try:
+            ref = ob(img, input_modal="others")["output_features"]
+            out = pb(img, input_modal="others")["output_features"]
+        finally:
+            for t in (wo, wp, uo, up):
+                t.div_(1.25)
+    assert not torch.equal(before, out["s3"])
+    for k in ("s2", "s3", "s4", "s5"):
+        _check("inplace-update/" + k, out[k], ref[k])
+
+
 def test_head_argmax_agreement(pair, cuda_device):
     """North-star gate: argmax segmentation from the UNCHANGED head (oracle restatement of DAFormerHead) fed with the product's
     features is >= 99.5 % pixel-identical to the one fed with the fp32 oracle's features, after the meta-arch's bilinear

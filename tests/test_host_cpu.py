@@ -136,3 +136,45 @@ def test_batch_sharding_world_size_2_gloo():
     assert sorted(m0 + m1) == list(range(21))
     assert t0 == t1 == 11.0
     assert all0 == all1 == [m0, m1]
+
+
+# ---------------------------------------------------------------------------------------------- DAFormer head mirror
+_HEAD_KW = dict(in_channels=[512] * 4, in_keys=["s2", "s3", "s4", "s5"], channels=256, num_classes=19, in_index=[0, 1, 2, 3],
+                norm_cfg=dict(type="BN", requires_grad=True), align_corners=False,
+                decoder_params=dict(embed_dims=256, embed_cfg=dict(type="mlp", act_cfg=None, norm_cfg=None),
+                                    embed_neck_cfg=dict(type="mlp", act_cfg=None, norm_cfg=None),
+                                    fusion_cfg=dict(type="aspp", sep=True, dilations=(1, 6, 12, 18), pool=False, act_cfg=dict(type="ReLU"),
+                                                    norm_cfg=dict(type="BN", requires_grad=True))))
+
+
+def test_head_state_dict_keys_match_reference_layout():
+    """Key names / shapes of the shipped DAFormerHead configuration (mmcv ConvModule = .conv/.bn, DepthwiseSeparableConvModule =
+    .depthwise_conv/.pointwise_conv; daformer_head.py:341-479, 536-640) — checked against the oracle restatement."""
+    from madm_b200.head import DAFormerHead
+    from oracle.daformer_head import build_head
+    ph, oh = DAFormerHead(**_HEAD_KW), build_head()
+    so, sp = oh.state_dict(), ph.state_dict()
+    assert set(so) == set(sp)
+    assert all(tuple(so[k].shape) == tuple(sp[k].shape) for k in so)
+    assert "fuse_layer.aspp_modules.2.depthwise_conv.conv.weight" in sp and sp["fuse_layer.aspp_modules.2.depthwise_conv.conv.weight"].shape == (1024, 1, 3, 3)
+    ph.load_state_dict(so)
+
+
+def test_head_rejects_unsupported_variants_and_has_no_cpu_path():
+    import copy
+    import pytest
+    from madm_b200 import _lib
+    from madm_b200.head import DAFormerHead
+    for patch in (dict(final_fuse_vae_decoder_feat=True), dict(concat_attention_to_conv_seg=True), dict(align_corners=True)):
+        with pytest.raises(NotImplementedError):
+            DAFormerHead(**{**_HEAD_KW, **patch})
+    kw = copy.deepcopy(_HEAD_KW)
+    kw["decoder_params"]["fusion_cfg"]["dilations"] = (1, 2, 3, 4)
+    with pytest.raises(NotImplementedError):
+        DAFormerHead(**kw)
+    head = DAFormerHead(**_HEAD_KW).eval()
+    feats = {k: torch.zeros(1, 512, s, s) for k, s in zip(("s2", "s3", "s4", "s5"), (128, 64, 32, 16))}
+    with pytest.raises(_lib.MadmError):  # CPU tensors: the product refuses instead of computing in PyTorch
+        head({"output_features": feats})
+    with pytest.raises(NotImplementedError):
+        head.train()({"output_features": feats})
