@@ -10,24 +10,29 @@
 
 namespace madm {
 
-// ------------------------------------------------------------------ fp32 NCHW -> 16-bit NHWC (32x32 smem transpose)
+// ------------------------------------------------------------------ fp32 NCHW -> 16-bit NHWC (64 ch x 32 px smem transpose)
+// reads: 32 consecutive pixels of one channel (128 B); writes: 64 consecutive channels of one pixel as 32 packed pairs (128 B)
 __global__ void nchw_to_nhwc16_kernel(const float* __restrict__ x, int C, int HW, int fp16, uint16_t* __restrict__ out) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  __shared__ float tile[64][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;
-  for (int r = ty; r < 32; r += 8) {
+  for (int r = ty; r < 64; r += 8) {
     const int c = c0 + r, p = p0 + tx;
     tile[r][tx] = (c < C && p < HW) ? __ldg(x + (size_t(b) * C + c) * HW + p) : 0.f;
   }
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {
-    const int p = p0 + r, c = c0 + tx;
-    if (p < HW && c < C) out[(size_t(b) * HW + p) * C + c] = cvt_16(tile[tx][r], fp16);
+    const int p = p0 + r, c = c0 + 2 * tx;
+    if (p >= HW) continue;
+    uint16_t* dst = out + (size_t(b) * HW + p) * C + c;
+    if (c + 1 < C) *reinterpret_cast<uint32_t*>(dst) = pack2_16(tile[2 * tx][r], tile[2 * tx + 1][r], fp16);
+    else if (c < C) *dst = cvt_16(tile[2 * tx][r], fp16);
   }
 }
 
 const char* nchw_to_nhwc16(const float* x, int B, int C, int HW, void* out, int fp16, cudaStream_t st) {
-  dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
+  if (C % 2) return "nchw_to_nhwc16: C must be even";
+  dim3 grid((HW + 31) / 32, (C + 63) / 64, B);
   nchw_to_nhwc16_kernel<<<grid, dim3(32, 8), 0, st>>>(x, C, HW, fp16, reinterpret_cast<uint16_t*>(out));
   return cudaGetLastError() == cudaSuccess ? nullptr : "nchw_to_nhwc16 launch failed";
 }
@@ -84,52 +89,82 @@ const char* bilinear_resize_nhwc16(const void* src, int B, int Hs, int Ws, int C
 }
 
 // ------------------------------------------------------------------ depthwise 3x3 (dilated, zero padding = dilation) + BN shift + ReLU
-// One thread = 8 channels of one output pixel; the 9 taps re-read neighbours through L1/L2 (the tensor is read once from HBM).
 // w9: fp32 [9][C] with the BatchNorm scale folded in (tap index = ky*3 + kx); shift: fp32 [C].
-__global__ void depthwise3x3_nhwc_kernel(const uint16_t* __restrict__ src, int H, int W, int C, int dil, const float* __restrict__ w9,
-                                         const float* __restrict__ shift, uint16_t* __restrict__ dst, long total, int fp16) {
+// One thread = 8 channels of one image column x, for the rows of one residue class y = r (mod dil): walking y in steps of the
+// dilation, output row y needs input rows y-dil, y, y+dil, two of which were already loaded for the previous output.  So each
+// output costs 3 (not 9) 16-byte loads (issued one row ahead), and the 72 weights + 8 shifts of the thread's channels stay in registers for the walk.
+__global__ void __launch_bounds__(128) depthwise3x3_nhwc_kernel(const uint16_t* __restrict__ src, int H, int W, int C, int dil,
+                                                                const float* __restrict__ w9, const float* __restrict__ shift,
+                                                                uint16_t* __restrict__ dst, long total, int classes, int fp16) {
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int Q = C >> 3;
   const int c = int(i % Q) * 8;
-  const long pix = i / Q;
-  const int x = int(pix % W), y = int((pix / W) % H), b = int(pix / (long(W) * H));
-  float acc[8];
+  long rest = i / Q;
+  const int x = int(rest % W); rest /= W;
+  const int r = int(rest % classes);  // residue class of y (mod dil); classes = min(dil, H)
+  const int b = int(rest / classes);
+  float w[9][8], sh[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w9 + size_t(t) * C + c)), w1 = __ldg(reinterpret_cast<const float4*>(w9 + size_t(t) * C + c + 4));
+    w[t][0] = w0.x; w[t][1] = w0.y; w[t][2] = w0.z; w[t][3] = w0.w; w[t][4] = w1.x; w[t][5] = w1.y; w[t][6] = w1.z; w[t][7] = w1.w;
+  }
   {
     const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + c)), s1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
-    acc[0] = s0.x; acc[1] = s0.y; acc[2] = s0.z; acc[3] = s0.w; acc[4] = s1.x; acc[5] = s1.y; acc[6] = s1.z; acc[7] = s1.w;
+    sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
   }
   const uint16_t* base = src + size_t(b) * H * W * C + c;
+  const bool xl = x - dil >= 0, xr = x + dil < W;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  auto load_row = [&](int yy, uint4 (&row)[3]) {  // the three x taps of input row yy (zero outside the image)
+    if (yy < 0 || yy >= H) { row[0] = zero; row[1] = zero; row[2] = zero; return; }
+    const uint16_t* p = base + (size_t(yy) * W + x) * C;
+    row[0] = xl ? __ldg(reinterpret_cast<const uint4*>(p - size_t(dil) * C)) : zero;
+    row[1] = __ldg(reinterpret_cast<const uint4*>(p));
+    row[2] = xr ? __ldg(reinterpret_cast<const uint4*>(p + size_t(dil) * C)) : zero;
+  };
+  uint4 up[3], mid[3], dn[3], nx[3];
+  load_row(r - dil, up);
+  load_row(r, mid);
+  load_row(r + dil, dn);
+  for (int y = r; y < H; y += dil) {
+    load_row(y + 2 * dil, nx);  // one row ahead of the one this output needs: its latency hides behind the 72 FMAs below
+    float acc[8];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int yy = y + (ky - 1) * dil;
-    if (yy < 0 || yy >= H) continue;
+    for (int t = 0; t < 8; ++t) acc[t] = sh[t];
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
-      const int xx = x + (kx - 1) * dil;
-      if (xx < 0 || xx >= W) continue;
       float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(base + (size_t(yy) * W + xx) * C)), fp16, v);
-      const float* wt = w9 + size_t(ky * 3 + kx) * C + c;
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt)), w1 = __ldg(reinterpret_cast<const float4*>(wt + 4));
-      acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]); acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
-      acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]); acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+      unpack8(up[kx], fp16, v);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] = fmaf(v[t], w[kx][t], acc[t]);
+      unpack8(mid[kx], fp16, v);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] = fmaf(v[t], w[3 + kx][t], acc[t]);
+      unpack8(dn[kx], fp16, v);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] = fmaf(v[t], w[6 + kx][t], acc[t]);
     }
+    uint4 pk;
+    pk.x = pack2_16(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fp16); pk.y = pack2_16(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f), fp16);
+    pk.z = pack2_16(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fp16); pk.w = pack2_16(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f), fp16);
+    *reinterpret_cast<uint4*>(dst + (size_t(b) * H * W + size_t(y) * W + x) * C + c) = pk;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) { up[kx] = mid[kx]; mid[kx] = dn[kx]; dn[kx] = nx[kx]; }
   }
-  uint4 pk;
-  pk.x = pack2_16(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f), fp16); pk.y = pack2_16(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f), fp16);
-  pk.z = pack2_16(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fp16); pk.w = pack2_16(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f), fp16);
-  *reinterpret_cast<uint4*>(dst + (size_t(b) * H * W + size_t(y) * W + x) * C + c) = pk;
 }
 
 const char* depthwise3x3_nhwc16(const void* src, int B, int H, int W, int C, int dil, const float* w9, const float* shift, void* dst, int fp16,
                                 cudaStream_t st) {
   if (C % 8) return "depthwise3x3: C must be a multiple of 8";
+  if (dil < 1) return "depthwise3x3: dilation must be >= 1";
   if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(w9) | reinterpret_cast<uintptr_t>(shift)) & 15)
     return "depthwise3x3: pointers must be 16B aligned";
-  const long total = long(B) * H * W * (C / 8);
-  depthwise3x3_nhwc_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), H, W, C, dil, w9, shift,
-                                                                         reinterpret_cast<uint16_t*>(dst), total, fp16);
+  const int classes = dil < H ? dil : H;  // residue classes of y that contain at least one row
+  const long total = long(B) * classes * W * (C / 8);
+  depthwise3x3_nhwc_kernel<<<unsigned((total + 127) / 128), 128, 0, st>>>(reinterpret_cast<const uint16_t*>(src), H, W, C, dil, w9, shift,
+                                                                         reinterpret_cast<uint16_t*>(dst), total, classes, fp16);
   return cudaGetLastError() == cudaSuccess ? nullptr : "depthwise3x3 launch failed";
 }
 
