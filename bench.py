@@ -166,6 +166,13 @@ def run_product(args, rank, local_rank, world):
             h.copy_(d, non_blocking=True)
         return res
 
+    # the same end-to-end work, with the copies of neighbouring steps overlapped with compute on a second stream
+    from madm_b200.pipeline import HostPipeline
+    pipe = HostPipeline(lambda x: bb._extract(x, "others", False, None), dev)
+
+    def run_e2e_pipelined(steps):
+        return pipe.run([img_host] * steps)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -194,7 +201,19 @@ def run_product(args, rank, local_rank, world):
         ms, clocks = timed(step_resident, args.steps, ClockSampler(local_rank) if rank == 0 else None)
         for _ in range(2):
             step_e2e()
-        ms_e2e, _ = timed(step_e2e, args.steps)
+        ms_e2e_serial, _ = timed(step_e2e, args.steps)
+        run_e2e_pipelined(2)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run_e2e_pipelined(args.steps)  # K steps: every step's H2D, compute and D2H inside the timed region
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        ms_e2e = t.item()
         # roofline inputs: per-kernel-family CUDA-event timing of instrumented steps on the launch stream
         eng = ldm.engine()
         prof = None
@@ -227,11 +246,18 @@ def run_product(args, rank, local_rank, world):
     gemm_tflops = gemm["flops"] / (gemm["ms"] / 1e3) / 1e12
     total_ms = sum(v["ms"] for v in prof.values())
     gn = prof["groupnorm"]
+    gemm_traffic = None
+    try:  # measured once under ncu for this build; null if the summary is not in the tree
+        with open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")) as f:
+            gemm_traffic = json.load(f)["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {
         "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM: all convs / linears)", "bound": "tensor",
         "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": gemm_tflops / peaks["tflops_sustained"],
         "peak_source": peaks["source"] + ", sustained cuBLAS bf16 figure (kernel timed inside a long step)",
-        "traffic": None,
+        "traffic": gemm_traffic, "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01_gemm_dram_traffic.json)",
+        "algorithmic_bytes_per_launch": gemm["bytes"] / max(1, gemm["launches"]),
         "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
         "algorithmic_gflop_per_launch": gemm["flops"] / max(1, gemm["launches"]) / 1e9,
         "share_of_step": gemm["ms"] / total_ms,
@@ -255,7 +281,9 @@ def run_product(args, rank, local_rank, world):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": sum(t.numel() * 4 for t in outs_host),
-                "api": "AttentionFeatureExtractorBackbone._extract -> madm_extract (C ABI), pinned host buffers",
+                "api": "madm_b200.pipeline.HostPipeline around AttentionFeatureExtractorBackbone._extract -> madm_extract (C ABI): pinned "
+                       "host buffers, H2D / D2H of neighbouring steps overlapped with compute on a copy stream",
+                "serial_value": imgs / (ms_e2e_serial / 1e3), "serial_ms_per_step": ms_e2e_serial / args.steps,
                 "cuda_graph": bool(graphed)},
         "gpu_launches": launches * args.steps,
         "roofline": roofline,

@@ -377,6 +377,18 @@ struct Builder {
     return s < 2 ? 1 : s;
   }
 
+  // algorithmic HBM bytes of one GEMM: every operand / result element crosses HBM once (A is read once, not once per filter tap)
+  static double gemm_algo_bytes(const GemmDesc& d) {
+    double by = 0;
+    for (int sgi = 0; sgi < d.nseg; ++sgi) by += double(d.M) * d.seg[sgi].C * 2 + double(d.N) * d.seg[sgi].ntaps * d.seg[sgi].C * 2;
+    const double mn = double(d.M) * ((d.act == ACT_GEGLU) ? d.N : d.N);
+    if (d.act == ACT_GEGLU) by += double(d.N) * (d.seg[0].ntaps * d.seg[0].C) * 2;  // the gate half of the weight
+    if (d.out_f32) by += mn * 4;
+    if (d.out_bf16) by += mn * 2;
+    if (d.residual) by += mn * 4;
+    if (d.colstats) by += mn / 32 * 8;
+    return by;
+  }
   void gemm(const GemmDesc& d0, double algo_flops = -1.0) {
     const int splits = getenv("MADM_NO_SPLITK") ? 1 : choose_splits(d0);
     if (splits > 1) {  // identical allocation sequence in every builder mode
@@ -395,7 +407,7 @@ struct Builder {
           fprintf(stderr, "MADM_PLAN gemm M=%d N=%d K=%d bn=%d tiles=%d taps=%d nseg=%d act=%d res=%d f32=%d h16=%d gflop=%.3f splits=%d\n", d.M, d.N,
                   int(K), L.bn, L.num_tiles, d.seg[0].ntaps, d.nseg, d0.act, d0.residual ? 1 : 0, d0.out_f32 ? 1 : 0, d0.out_bf16 ? 1 : 0,
                   algo_flops / 1e9, splits);
-        emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, 0.0);
+        emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, gemm_algo_bytes(d));
         const GemmDesc e0 = d0; const float* pp = part.p; const int f16 = ctx->fp16; const long ss = d.split_stride;
         if (e0.alpha != 1.0f) fail(MADM_EINVAL, "split-K with alpha != 1 is not supported");
         emit([=](cudaStream_t st) {
@@ -425,7 +437,7 @@ struct Builder {
       fprintf(stderr, "MADM_PLAN gemm M=%d N=%d K=%d bn=%d tiles=%d taps=%d nseg=%d act=%d res=%d f32=%d h16=%d gflop=%.3f\n", d.M, d.N, K, L.bn,
               L.num_tiles, d.seg[0].ntaps, d.nseg, d.act, d.residual ? 1 : 0, d.out_f32 ? 1 : 0, d.out_bf16 ? 1 : 0, algo_flops / 1e9);
     }
-    emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, 0.0);
+    emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, gemm_algo_bytes(d));
   }
 
   // fused attention: tcgen05/TMEM kernel (tensor maps encoded at plan time); MADM_ATTN_LEGACY=1 selects the mma.sync kernel

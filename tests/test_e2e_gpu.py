@@ -209,6 +209,24 @@ def test_inplace_parameter_update_repacks(pair, cuda_device):
         _check("inplace-update/" + k, out[k], ref[k])
 
 
+def test_host_pipeline_matches_direct_calls(pair, cuda_device):
+    """madm_b200.pipeline.HostPipeline (uploads / downloads of neighbouring steps overlapped with compute on a copy stream) returns
+    exactly what direct calls return, step by step."""
+    from oracle import synthetic
+    from madm_b200.pipeline import HostPipeline
+    _, pb = pair
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    batches = [synthetic.synthetic_images(2, seed=60 + i).pin_memory() for i in range(4)]
+    with torch.no_grad():
+        direct = [[t.cpu() for t in pb._extract(b.to(cuda_device), "others", False, None)["features"]] for b in batches]
+        pipe = HostPipeline(lambda x: pb._extract(x, "others", False, None), cuda_device, depth=len(batches))
+        piped = pipe.run(batches)
+        torch.cuda.synchronize()
+    for d, p in zip(direct, piped):
+        for a, b in zip(d, p):
+            assert torch.equal(a, b)
+
+
 def test_head_argmax_agreement(pair, cuda_device):
     """North-star gate: argmax segmentation from the UNCHANGED head (oracle restatement of DAFormerHead) fed with the product's
     features is >= 99.5 % pixel-identical to the one fed with the fp32 oracle's features, after the meta-arch's bilinear
