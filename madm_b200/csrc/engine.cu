@@ -45,7 +45,8 @@ struct ParamRef {
 enum PackKind { PK_CONV, PK_LINEAR, PK_GEGLU, PK_VAE_HEAD, PK_F32_COPY, PK_F32_SUM2, PK_F32_GEGLU_BIAS,
                 PK_BN_FOLD,   // eval-mode BatchNorm -> fp32 [scale | shift] (bias_off = N floats each)
                 PK_CONV_BN,   // conv weight with the BatchNorm scale (at bias_off) folded into its rows
-                PK_DW_BN };   // depthwise 3x3 weight * BatchNorm scale -> fp32 [9][C]
+                PK_DW_BN,     // depthwise 3x3 weight * BatchNorm scale -> fp32 [9][C]
+                PK_IDENTITY }; // N x N identity block (16-bit) inside a wider packed row: the residual add as an extra K segment
 struct PackEntry {
   PackKind kind;
   std::string src, src2, src3, src4;  // parameter names
@@ -299,6 +300,22 @@ struct Builder {
       return e;
     }).off;
     return Fused{w_off, b_off};
+  }
+  // conv3x3 (C -> C) with the residual add folded in as a second K segment with identity weights: [C, 9*C + C].  The residual
+  // operand then is the 16-bit stream itself, read by TMA like any A tile (exact: 1.0 * x accumulated in fp32), so the epilogue
+  // needs no fp32 residual tensor.
+  size_t conv_plus_identity(const std::string& conv, int C) {
+    const int K0 = 9 * C, K = K0 + C;
+    const size_t w_off = entry("convid:" + conv, [&] {
+      PackEntry e; e.kind = PK_CONV; e.src = conv + ".weight"; e.N = C; e.C = C; e.taps = 9; e.Cpad = C; e.Kpad = K0; e.ldo = K;
+      e.off = pack_reserve(size_t(C) * K * 2);
+      return e;
+    }).off;
+    entry("convid_i:" + conv, [&] {
+      PackEntry e; e.kind = PK_IDENTITY; e.N = C; e.ldo = K; e.off = w_off + size_t(K0) * 2;
+      return e;
+    });
+    return w_off;
   }
   // a region holding several linears stacked along N (fused QKV, all cross-attn K/V, all time_emb_proj)
   size_t region(const std::string& key, size_t bytes) {
@@ -557,14 +574,20 @@ struct Model {
   }
 
   // ---- ResnetBlock2D.  x = channel concat of x0 (and x1).  Returns fp32 (+bf16 copy if want_b16) output.
-  Act resblock(const std::string& p, const Act& x0, const Act* x1, int Cout, float eps, bool has_temb, bool want_b16, bool want_s2d = false) {
+  // A 16-bit-only input (x0.f null: the VAE's high-resolution stages with fp16 operands, where the reference itself runs the
+  // whole VAE in fp16) is read as is by norm1 and enters conv2 as a second K segment (conv_shortcut weights, or identity weights
+  // for the plain residual); out16_only then also drops the fp32 copy of the output.
+  Act resblock(const std::string& p, const Act& x0, const Act* x1, int Cout, float eps, bool has_temb, bool want_b16, bool want_s2d = false,
+               bool out16_only = false) {
     if (getenv("MADM_NO_S2D_FUSE")) want_s2d = false;
     const int Bn = x0.B, H = x0.H, W = x0.W, Cin = x0.C + (x1 ? x1->C : 0);
     const bool shortcut = Cin != Cout;
+    const bool in16 = x0.f.bytes == 0 && x0.h.bytes != 0;  // (valid in every builder mode: sizes, not pointers)
     if (x1 && !shortcut) b.fail(MADM_EINVAL, "resblock: concat input without shortcut");
+    if (in16 && (x1 || x0.h_s2d)) b.fail(MADM_EINVAL, "resblock: a 16-bit stream input must be a single linear tensor");
     B16T n1 = b.b16(size_t(x0.M()) * Cin);
-    B16T raw; if (shortcut) raw = b.b16(size_t(x0.M()) * Cin);
-    b.groupnorm(x0, x1, p + ".norm1", eps, ACT_SILU, n1.p, shortcut ? raw.p : nullptr);
+    B16T raw; if (shortcut && !in16) raw = b.b16(size_t(x0.M()) * Cin);
+    b.groupnorm(x0, x1, p + ".norm1", eps, ACT_SILU, n1.p, (shortcut && !in16) ? raw.p : nullptr, in16);
     // conv1 (+ bias + time embedding row bias) -> 16-bit intermediate (it only feeds norm2)
     Act h1 = b.act(Bn, H, W, Cout, false, true);
     {
@@ -581,15 +604,18 @@ struct Model {
     B16T n2 = b.b16(size_t(x0.M()) * Cout);
     b.groupnorm(h1, nullptr, p + ".norm2", eps, ACT_SILU, n2.p, nullptr, /*in16=*/true);
     b.free(h1);
-    Act out = b.act(Bn, H, W, Cout, true, want_b16 || want_s2d);
+    Act out = b.act(Bn, H, W, Cout, !out16_only, want_b16 || want_s2d || out16_only);
     out.h_s2d = want_s2d;
     {
       GemmDesc d; d.seg[0] = Builder::seg_3x3(n2.p, Bn, H, W, Cout); d.M = int(x0.M()); d.N = Cout; d.Nw = Cout;
       if (want_s2d) { d.s2d_H = H; d.s2d_W = W; }
       if (shortcut) {  // out = conv2(n2) + conv_shortcut(x): one GEMM, K = 9*Cout + Cin
         Builder::Fused f = b.conv_plus_shortcut(p + ".conv2", p + ".conv_shortcut", Cout, Cin);
-        d.nseg = 2; d.seg[1] = Builder::seg_1x1(raw.p, Bn, H, W, Cin);
+        d.nseg = 2; d.seg[1] = Builder::seg_1x1(in16 ? x0.h.p : raw.p, Bn, H, W, Cin);
         d.w = b.pw(f.w_off); d.bias = b.pf(f.b_off);
+      } else if (in16) {  // out = conv2(n2) + I x: the residual is the 16-bit stream, added on the tensor core
+        d.nseg = 2; d.seg[1] = Builder::seg_1x1(x0.h.p, Bn, H, W, Cout);
+        d.w = b.pw(b.conv_plus_identity(p + ".conv2", Cout)); d.bias = P(p + ".conv2.bias", Cout);
       } else {
         d.w = b.pw(b.conv_w(p + ".conv2", Cout, Cout, 9)); d.bias = P(p + ".conv2.bias", Cout);
         d.residual = x0.f.p; d.ldr = Cout;
@@ -599,7 +625,7 @@ struct Model {
       b.gemm(d);
     }
     b.free(n2);
-    if (shortcut) b.free(raw);
+    if (shortcut && !in16) b.free(raw);
     return out;
   }
 
@@ -693,7 +719,7 @@ struct Model {
     return b.param(module + ".bias", n);
   }
 
-  Act downsample(const std::string& p, const Act& x, bool pad1) {
+  Act downsample(const std::string& p, const Act& x, bool pad1, bool out16_only = false) {
     const int Bn = x.B, H = x.H, W = x.W, C = x.C;
     B16T s2d;
     const bf16* s2dp;
@@ -707,9 +733,10 @@ struct Model {
       b.emit([=](cudaStream_t st) { return space_to_depth(src, Bn, H, W, C, dst, h16, st); }, false, MADM_KIND_ELEMENTWISE, 0.0,
              double(x.M()) * C * 6);
     }
-    Act out = b.act(Bn, H / 2, W / 2, C, true, false);
+    Act out = b.act(Bn, H / 2, W / 2, C, !out16_only, out16_only);
     { GemmDesc d; d.seg[0] = Builder::seg_s2(s2dp, Bn, H / 2, W / 2, C, pad1); d.M = int(out.M()); d.N = C; d.Nw = C;
-      d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C;
+      d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C);
+      if (out16_only) { d.out_bf16 = out.h.p; d.ldo16 = C; } else { d.out_f32 = out.f.p; d.ldo32 = C; }
       b.attach_colstats(out, d); b.gemm(d); }
     if (!x.h_s2d) b.free(s2d);
     return out;
@@ -797,9 +824,13 @@ struct Model {
     if (dry()) b.emit(nullptr);
     else { bf16* dst = col.p; const int h16 = f16();
       b.emit([=](cudaStream_t st) { return image_im2col(io->a.img, Bn, R, R, dst, io->a.range_flag, h16, st); }); }
-    Act x = b.act(Bn, R, R, 128, true, false);
+    // fp16 operands: the residual stream of the 512^2 and 256^2 stages (3/4 of the VAE's bytes) is kept in fp16 like the
+    // reference's VAE (AutoencoderKL loaded with torch_dtype=float16, ldm_diffusers.py:246-249); bf16 keeps the fp32 stream.
+    const bool s16 = f16() && !getenv("MADM_VAE_STREAM32");
+    Act x = b.act(Bn, R, R, 128, !s16, s16);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(col.p, long(Bn) * R * R, 64); d.M = Bn * R * R; d.N = 128; d.Nw = 128;
-      d.w = b.pw(b.conv_w(e + "conv_in", 128, 3, 9, /*Cpad=*/3)); d.bias = P(e + "conv_in.bias", 128); d.out_f32 = x.f.p; d.ldo32 = 128;
+      d.w = b.pw(b.conv_w(e + "conv_in", 128, 3, 9, /*Cpad=*/3)); d.bias = P(e + "conv_in.bias", 128);
+      if (s16) { d.out_bf16 = x.h.p; d.ldo16 = 128; } else { d.out_f32 = x.f.p; d.ldo32 = 128; }
       b.attach_colstats(x, d);
       b.gemm(d, 2.0 * double(d.M) * 128 * 27); }
     b.free(col);
@@ -811,7 +842,8 @@ struct Model {
         ++index;
         const bool is_tap = index == 5;  // encoder_block_indices=[5] (counter increments before the check, :289-293)
         const bool feeds_down = (j == 1 && i < 3);  // its output is the input of this stage's stride-2 conv
-        Act y = resblock(p, x, nullptr, ch[i], 1e-6f, false, is_tap, feeds_down && !is_tap);
+        const bool o16 = s16 && i < 2;  // this block's output stays on the 16-bit stream
+        Act y = resblock(p, x, nullptr, ch[i], 1e-6f, false, is_tap, feeds_down && !is_tap, o16);
         b.free(x);
         x = y;
         if (is_tap) {  // keep the tap alive for the projection stage
@@ -821,7 +853,7 @@ struct Model {
         }
       }
       if (i < 3) {
-        Act y = downsample(e + "down_blocks." + std::to_string(i) + ".downsamplers.0", x, /*pad1=*/false);
+        Act y = downsample(e + "down_blocks." + std::to_string(i) + ".downsamplers.0", x, /*pad1=*/false, /*out16_only=*/s16 && i < 2);
         b.free(x);
         x = y;
       }
@@ -1163,6 +1195,11 @@ const char* Model::nchw_to_nhwc4(const float* src, int Bn, int HW, float* dst, c
   return cudaGetLastError() == cudaSuccess ? nullptr : "nchw_to_nhwc4 launch failed";
 }
 
+__global__ void identity16_kernel(uint16_t* out, int N, int ldo, uint16_t one) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N * N) out[size_t(i / N) * ldo + (i % N)] = (i / N == i % N) ? one : uint16_t(0);
+}
+
 __global__ void f32_sum2_kernel(const float* a, const float* b2, int n, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + b2[i];
@@ -1268,6 +1305,8 @@ int madm_set_compute_dtype(madm_ctx* ctx, int32_t dtype) {
     ctx->fp16 = f;
     ctx->plans.clear();
     ctx->last_plan = nullptr;
+    ctx->layout_done = false;       // the packed layout depends on the operand dtype (16-bit VAE stream: identity segments)
+    ctx->ws_bytes_cache.clear();
   }
   return MADM_OK;
 }
@@ -1382,6 +1421,12 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float sc
         if (!w) return set_err(ctx, MADM_ENOTFOUND, "parameter not registered: " + e.src);
         if (w->numel() != int64_t(e.C) * 9) return set_err(ctx, MADM_EINVAL, "unexpected shape: " + e.src);
         err = pack_depthwise(w->p, reinterpret_cast<const float*>(base + e.bias_off), e.C, reinterpret_cast<float*>(base + e.off), st);
+        break;
+      }
+      case PK_IDENTITY: {
+        identity16_kernel<<<(e.N * e.N + 255) / 256, 256, 0, st>>>(reinterpret_cast<uint16_t*>(base + e.off), e.N, e.ldo,
+                                                                  ctx->fp16 ? uint16_t(0x3C00) : uint16_t(0x3F80));
+        if (cudaGetLastError() != cudaSuccess) err = "identity16 launch failed";
         break;
       }
       case PK_F32_SUM2: {

@@ -476,7 +476,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const int s2d_W = p.s2d_W, s2d_H = p.s2d_H, s2d_B = p.s2d_B;
               uint16_t* o16p = out16 + n;
               if (residual) epi_block<true, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
-              else epi_block<false, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
+              else if (out32) epi_block<false, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
+              else epi_block<false, false, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
             } else {
               uint16_t* o16p = out16 ? out16 + size_t(row0) * ldo16 + n : nullptr;
               switch (mode) {
@@ -633,7 +634,7 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   if (d.act == ACT_GEGLU && d.N % 64 != 0) return "gemm: GEGLU needs N % 64 == 0";
   if (d.rowbias && d.rows_per_img % 32 != 0) return "gemm: rows_per_img must be a multiple of 32 when a row bias is given";
   if (d.s2d_W > 0) {
-    if (!d.out_f32) return "gemm: the space-to-depth 16-bit output is a secondary output (out_f32 required)";
+    if (!d.out_f32 && d.residual) return "gemm: a space-to-depth-only output cannot take an fp32 residual";
     if (!d.out_bf16 || (d.s2d_W & 1) || (d.s2d_H & 1) || d.M % (d.s2d_H * d.s2d_W) != 0 || d.N % 32 != 0 || d.act == ACT_GEGLU)
       return "gemm: space-to-depth output needs a 16-bit output, even H/W, M = B*H*W and N % 32 == 0";
   }
