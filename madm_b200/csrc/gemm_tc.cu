@@ -118,18 +118,10 @@ __device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, fl
 // bias (+ the per-image time-embedding row bias).  Compile-time flags keep the loop free of uniform branches.
 template <bool RES, bool O32, int O16>
 __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int M, float alpha, float4 bb, int act, int fp16,
-                                          const float* __restrict__ res, int ldr, float* o32, int ldo32, uint16_t* o16, int ldo16,
+                                          const float4 (&resv)[8], float* o32, int ldo32, uint16_t* o16, int ldo16,
                                           bool do_stats, float (&cs)[8], int s2d_H = 0, int s2d_W = 0, int s2d_B = 0, int N = 0) {
   const int rsub = lane >> 3;
   const int cc = (lane & 7) * 4;
-  float4 resv[8];
-  if constexpr (RES) {
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + rsub;
-      resv[it] = (row0 + r < M) ? *reinterpret_cast<const float4*>(res + size_t(r) * ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + rsub;
@@ -172,6 +164,8 @@ __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int 
 //   warps 2..5  epilogue: tcgen05.ld (thread = row) -> per-warp smem transpose -> coalesced fused epilogue
 //               (bias / time-embedding row bias / fp32 residual / SiLU / ReLU / GEGLU) -> fp32 and/or 16-bit stores
 template <int BN, int MT, int EPI, bool PAIR>
+// Registers: 10 warps are allocated as 12 (granularity of 4 warps), so 65536 / 384 -> 168 registers per thread is the ceiling
+// for this block size (measured: a 186-register build reports maxThreadsPerBlock = 256 and fails to launch).
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, MT, PAIR>;
   extern __shared__ uint8_t smem_raw[];
@@ -372,6 +366,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t r[32];
+#ifdef GEMM_INSTR
+    long long e_wait = 0, e_work = 0, e_tiles = 0;
+    const long long e_t0 = clock64();
+#endif
     float* const out32_base = p.out_f32;
     const int splits = p.splits;
     const long split_stride = p.split_stride;
@@ -381,8 +379,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       const int m0 = ((mn / n_tiles) * (PAIR ? 2 : 1) + rank) * (BM * MT);
       const int n0 = tile_n * BN;
       float* const out32 = out32_base ? out32_base + long(t - mn * splits) * split_stride : nullptr;
+#ifdef GEMM_INSTR
+      const long long ei0 = clock64();
+#endif
       mbar_wait(tmem_full_bar(acc), acc_phase);
       tc_fence_after();
+#ifdef GEMM_INSTR
+      const long long ei1 = clock64();
+      e_wait += ei1 - ei0;
+#endif
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub) {  // M sub-tiles of this CTA tile
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t((acc * MT + sub) * C::ACC_STRIDE);
@@ -441,7 +446,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           __syncwarp();
           const int cc = (lane & 7) * 4;
           float nostats[8];
-          epi_block<false, false, 1>(stg, lane, row0, M, 1.0f, make_float4(0.f, 0.f, 0.f, 0.f), ACT_NONE, fp16, nullptr, 0, nullptr, 0,
+          const float4 nores[8] = {};
+          epi_block<false, false, 1>(stg, lane, row0, M, 1.0f, make_float4(0.f, 0.f, 0.f, 0.f), ACT_NONE, fp16, nores, nullptr, 0,
                                      out16 + size_t(row0) * ldo16 + on0 + half * 32 + cc, ldo16, false, nostats);
         }
       } else {
@@ -451,6 +457,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           if constexpr (STATS) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) cs1[i] = 0.f;
+          }
+          // fp32 residual of this chunk: issued before the TMEM load / transpose so its HBM / L2 latency overlaps them
+          // (in-place residual == out_f32 stays safe: these are this chunk's own elements, loaded before its stores)
+          float4 resv[8];
+          if (residual && vec_ok && n0 + c + 32 <= N) {
+            const float* resp = residual + size_t(row0) * ldr + n0 + c + (lane & 7) * 4;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3);
+              resv[it] = (row0 + rr < M) ? *reinterpret_cast<const float4*>(resp + size_t(rr) * ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
           __syncwarp();  // previous chunk's smem reads are done; warp converged for the aligned tcgen05.ld
           tmem_ld32(taddr + c, r);
@@ -470,23 +487,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               const float4 t4 = __ldg(reinterpret_cast<const float4*>(rowbias + size_t(img) * ld_rowbias + n));
               bb.x += t4.x; bb.y += t4.y; bb.z += t4.z; bb.w += t4.w;
             }
-            const float* resp = residual ? residual + size_t(row0) * ldr + n : nullptr;
             float* o32p = out32 ? out32 + size_t(row0) * ldo32 + n : nullptr;
             if constexpr (S2D) {  // 16-bit output in space-to-depth layout (row offsets computed per row inside)
               const int s2d_W = p.s2d_W, s2d_H = p.s2d_H, s2d_B = p.s2d_B;
               uint16_t* o16p = out16 + n;
-              if (residual) epi_block<true, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
-              else if (out32) epi_block<false, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
-              else epi_block<false, false, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
+              if (residual) epi_block<true, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
+              else if (out32) epi_block<false, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
+              else epi_block<false, false, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
             } else {
               uint16_t* o16p = out16 ? out16 + size_t(row0) * ldo16 + n : nullptr;
               switch (mode) {
-                case 1: epi_block<false, false, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-                case 2: epi_block<false, true, 0>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-                case 3: epi_block<false, true, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-                case 5: epi_block<true, false, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-                case 6: epi_block<true, true, 0>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-                default: epi_block<true, true, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resp, ldr, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 1: epi_block<false, false, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 2: epi_block<false, true, 0>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 3: epi_block<false, true, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 5: epi_block<true, false, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 6: epi_block<true, true, 0>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                default: epi_block<true, true, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
               }
             }
             if (do_stats && lane < 8 && row0 < M) {
@@ -523,6 +539,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
       }
       }  // sub-tiles
+#ifdef GEMM_INSTR
+      e_work += clock64() - ei1;
+      ++e_tiles;
+#endif
       // release this accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -535,6 +555,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         acc_phase ^= 1u;
       }
     }
+#ifdef GEMM_INSTR
+    if (blockIdx.x == 4 && lane == 0 && (warp == 2 || warp == 6))
+      printf("epilogue warp %d: total %lld clk, %lld tiles | waiting for the accumulator %lld, draining it %lld\n", warp, clock64() - e_t0, e_tiles,
+             e_wait, e_work);
+#endif
   }
 
   tc_fence_before();
@@ -758,11 +783,21 @@ static const char* launch_bn_s(const GemmLaunch& L, const GemmParams& p, cudaStr
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MT, EPI, PAIR>, p) != cudaSuccess) return "gemm: cluster launch failed";
-    return nullptr;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MT, EPI, PAIR>, p);
+    if (e == cudaSuccess) return nullptr;
+    static thread_local char buf[160];
+    snprintf(buf, sizeof(buf), "gemm: cluster launch failed (%s)", cudaGetErrorString(e));
+    return buf;
   } else {
     gemm_tc_kernel<BN, MT, EPI, PAIR><<<L.grid, kThreads, Cfg<BN, MT, PAIR>::SMEM, stream>>>(p);
-    return cudaGetLastError() == cudaSuccess ? nullptr : "gemm: kernel launch failed";
+    const cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return nullptr;
+    static thread_local char buf[160];
+    cudaFuncAttributes fa{};
+    cudaFuncGetAttributes(&fa, gemm_tc_kernel<BN, MT, EPI, PAIR>);
+    snprintf(buf, sizeof(buf), "gemm: kernel launch failed (%s; %d regs, max %d threads, %d B smem)", cudaGetErrorString(e), fa.numRegs,
+             fa.maxThreadsPerBlock, int(Cfg<BN, MT, PAIR>::SMEM));
+    return buf;
   }
 }
 template <int BN, int MT, bool PAIR>
