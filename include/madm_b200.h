@@ -162,7 +162,7 @@ typedef struct madm_gemm_args {
   const float* bias;      /* [N] or NULL */
   const float* rowbias;   /* [nimg, ld_rowbias] or NULL */
   int32_t rows_per_img, ld_rowbias;
-  const float* residual;  /* fp32 [M, ldr] or NULL */
+  const float* residual;  /* fp32 [M, ldr] or NULL (16-bit if res16) */
   int32_t ldr;
   float* out_f32; int32_t ldo32;
   void* out_bf16; int32_t ldo16;
@@ -176,6 +176,7 @@ typedef struct madm_gemm_args {
   int32_t mt;             /* M sub-tiles per CTA tile when bn = 128: 0 auto, 1 (128-row tiles), 2 (256-row tiles) */
   int32_t s2d_H, s2d_W;   /* > 0: out_bf16 is written in space-to-depth layout [4][B][H/2][W/2][N] (operand of a stride-2 conv) */
   int32_t pair;           /* CTA pairs (tcgen05 cta_group::2, 256-row MMAs): 0 auto, 1 force, -1 never */
+  int32_t res16;          /* residual points to a 16-bit [M, ldr] tensor of `dtype` (may alias out_bf16) instead of fp32 */
 } madm_gemm_args;
 
 int madm_op_gemm(const madm_gemm_args* a, madm_stream stream);
@@ -188,8 +189,8 @@ int madm_op_groupnorm_from_colstats(const void* x, int32_t C, int32_t B, int32_t
                                     int32_t stat_rows, const float* gamma, const float* beta, float eps, int32_t act,
                                     float* scratch /*[B,32,32,2]*/, void* y_bf16, int32_t dtype, madm_stream stream);
 int madm_op_groupnorm_scratch_floats(int32_t B, int32_t HW, int32_t C); /* scratch size (floats) for the two GN ops */
-int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y_bf16,
-                      int32_t dtype, madm_stream stream);
+int madm_op_layernorm(const void* x, int32_t in16 /* x is 16-bit (dtype) instead of fp32 */, int32_t M, int32_t C, const float* gamma,
+                      const float* beta, float eps, void* y_bf16, int32_t dtype, madm_stream stream);
 int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p_bf16, int32_t dtype, madm_stream stream);
 int madm_op_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o, int32_t ldo,
                       int32_t B, int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bstride, int64_t kv_bstride,

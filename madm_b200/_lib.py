@@ -57,7 +57,7 @@ class MadmGemmArgs(C.Structure):
         ("w", c_void_p), ("bias", c_void_p), ("rowbias", c_void_p), ("rows_per_img", c_int32), ("ld_rowbias", c_int32),
         ("residual", c_void_p), ("ldr", c_int32), ("out_f32", c_void_p), ("ldo32", c_int32),
         ("out_bf16", c_void_p), ("ldo16", c_int32), ("act", c_int32), ("alpha", c_float), ("bn", c_int32), ("dtype", c_int32),
-        ("colstats", c_void_p), ("stat_rows", c_int32), ("mt", c_int32), ("s2d_H", c_int32), ("s2d_W", c_int32), ("pair", c_int32),
+        ("colstats", c_void_p), ("stat_rows", c_int32), ("mt", c_int32), ("s2d_H", c_int32), ("s2d_W", c_int32), ("pair", c_int32), ("res16", c_int32),
     ]
 
 
@@ -83,7 +83,7 @@ SYMBOLS = {
     "madm_op_groupnorm_scratch_floats": (c_int, [c_int32, c_int32, c_int32]),
     "madm_op_groupnorm_from_colstats": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
                                                 c_float, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
-    "madm_op_layernorm": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
+    "madm_op_layernorm": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_void_p]),
     "madm_op_softmax_rows": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_attention": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int32,
                                   c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64, c_float, c_int32, c_int32, c_void_p]),

@@ -45,7 +45,7 @@ int madm_op_gemm(const madm_gemm_args* a, madm_stream stream) {
   d.residual = a->residual; d.ldr = a->ldr;
   d.out_f32 = a->out_f32; d.ldo32 = a->ldo32; d.out_bf16 = a->out_bf16; d.ldo16 = a->ldo16;
   d.act = a->act; d.alpha = a->alpha; d.bn = a->bn; d.fp16 = a->dtype == MADM_DTYPE_FP16;
-  d.colstats = a->colstats; d.stat_rows = a->stat_rows ? a->stat_rows : 32; d.mt = a->mt; d.s2d_H = a->s2d_H; d.s2d_W = a->s2d_W; d.pair = a->pair;
+  d.colstats = a->colstats; d.stat_rows = a->stat_rows ? a->stat_rows : 32; d.mt = a->mt; d.s2d_H = a->s2d_H; d.s2d_W = a->s2d_W; d.pair = a->pair; d.res16 = a->res16;
   GemmLaunch L;
   if (const char* e = gemm_prepare(d, &L)) return fail(e);
   RUN(gemm_launch(L, static_cast<cudaStream_t>(stream)));
@@ -59,9 +59,9 @@ int madm_op_groupnorm(const void* x0, int32_t C0, const void* x1, int32_t C1, in
   RUN(groupnorm_apply(x0, C0, x1, C1, B, HW, in16, stats, 0, gamma, beta, eps, act, y, raw, f16, st));
 }
 
-int madm_op_layernorm(const float* x, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y,
+int madm_op_layernorm(const void* x, int32_t in16, int32_t M, int32_t C, const float* gamma, const float* beta, float eps, void* y,
                       int32_t dtype, madm_stream stream) {
-  RUN(layernorm(x, M, C, gamma, beta, eps, y, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+  RUN(layernorm(x, in16, M, C, gamma, beta, eps, y, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
 int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p, int32_t dtype, madm_stream stream) {

@@ -206,7 +206,7 @@ const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void*
 // out = act( sum_s partial[s] (fixed order) + bias + rowbias[img] + residual ) -> fp32 and/or 16-bit; one float4 per thread
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long split_stride, int M, int N, const float* __restrict__ bias,
                                      const float* __restrict__ rowbias, int rows_per_img, int ld_rowbias, const float* residual, int ldr,
-                                     float* out32, int ldo32, uint16_t* __restrict__ out16, int ldo16, int act, int fp16) {
+                                     float* out32, int ldo32, uint16_t* out16, int ldo16, int act, int fp16, int res16) {
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const int Q = N >> 2;
   if (i >= long(M) * Q) return;
@@ -221,7 +221,13 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
     const float4 t = __ldg(reinterpret_cast<const float4*>(rowbias + size_t(m / rows_per_img) * ld_rowbias + n));
     v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
   }
-  if (residual) { const float4 t = *reinterpret_cast<const float4*>(residual + size_t(m) * ldr + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
+  if (residual && res16) {  // 16-bit residual stream (may alias out16: read before the store below)
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(residual) + size_t(m) * ldr + n);
+    float2 lo, hi;
+    if (fp16) { lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x)); hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y)); }
+    else { lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)); hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y)); }
+    v.x += lo.x; v.y += lo.y; v.z += hi.x; v.w += hi.y;
+  } else if (residual) { const float4 t = *reinterpret_cast<const float4*>(residual + size_t(m) * ldr + n); v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w; }
   if (act == ACT_SILU) { v.x = v.x / (1.f + __expf(-v.x)); v.y = v.y / (1.f + __expf(-v.y)); v.z = v.z / (1.f + __expf(-v.z)); v.w = v.w / (1.f + __expf(-v.w)); }
   else if (act == ACT_RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
   if (out32) *reinterpret_cast<float4*>(out32 + size_t(m) * ldo32 + n) = v;
@@ -230,12 +236,12 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
 
 const char* splitk_reduce(const float* part, int splits, long split_stride, int M, int N, const float* bias, const float* rowbias,
                           int rows_per_img, int ld_rowbias, const float* residual, int ldr, float* out32, int ldo32, void* out16, int ldo16,
-                          int act, int fp16, cudaStream_t st) {
+                          int act, int fp16, cudaStream_t st, int res16) {
   if (N % 4) return "splitk_reduce: N % 4 != 0";
   const long total = long(M) * (N / 4);
   splitk_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(part, splits, split_stride, M, N, bias, rowbias, rows_per_img > 0 ? rows_per_img : 1,
                                                                       ld_rowbias ? ld_rowbias : N, residual, ldr, out32, ldo32,
-                                                                      reinterpret_cast<uint16_t*>(out16), ldo16, act, fp16);
+                                                                      reinterpret_cast<uint16_t*>(out16), ldo16, act, fp16, res16);
   return cudaGetLastError() == cudaSuccess ? nullptr : "splitk_reduce launch failed";
 }
 

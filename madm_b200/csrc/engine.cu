@@ -402,7 +402,7 @@ struct Builder {
     if (d.act == ACT_GEGLU) by += double(d.N) * (d.seg[0].ntaps * d.seg[0].C) * 2;  // the gate half of the weight
     if (d.out_f32) by += mn * 4;
     if (d.out_bf16) by += mn * 2;
-    if (d.residual) by += mn * 4;
+    if (d.residual) by += mn * (d.res16 ? 2 : 4);
     if (d.colstats) by += mn / 32 * 8;
     return by;
   }
@@ -413,7 +413,7 @@ struct Builder {
       if (mode == PLAN) {
         GemmDesc d = d0;
         d.fp16 = ctx->fp16;
-        d.bias = nullptr; d.rowbias = nullptr; d.residual = nullptr; d.out_bf16 = nullptr; d.act = ACT_NONE; d.colstats = nullptr; d.alpha = 1.0f;
+        d.bias = nullptr; d.rowbias = nullptr; d.residual = nullptr; d.res16 = 0; d.out_bf16 = nullptr; d.act = ACT_NONE; d.colstats = nullptr; d.alpha = 1.0f;
         d.out_f32 = part.p; d.ldo32 = d0.N; d.splits = splits; d.split_stride = long(d0.M) * d0.N; d.bn = 128;
         GemmLaunch L;
         if (const char* e = gemm_prepare(d, &L)) fail(MADM_EINVAL, std::string(e));
@@ -429,7 +429,7 @@ struct Builder {
         if (e0.alpha != 1.0f) fail(MADM_EINVAL, "split-K with alpha != 1 is not supported");
         emit([=](cudaStream_t st) {
           return splitk_reduce(pp, splits, ss, e0.M, e0.N, e0.bias, e0.rowbias, e0.rows_per_img, e0.ld_rowbias, e0.residual, e0.ldr, e0.out_f32,
-                               e0.ldo32, e0.out_bf16, e0.ldo16, e0.act, f16, st);
+                               e0.ldo32, e0.out_bf16, e0.ldo16, e0.act, f16, st, e0.res16);
         }, false, MADM_KIND_ELEMENTWISE, 0.0, double(splits + 2) * e0.M * e0.N * 4);
       } else {
         n_ops += 2;
@@ -638,16 +638,31 @@ struct Model {
     const std::string tb = p + ".transformer_blocks.0";
     B16T n = b.b16(size_t(M) * C);
     b.groupnorm(x, nullptr, p + ".norm", 1e-6f, ACT_NONE, n.p, nullptr);
-    F32T hs = b.f32(size_t(M) * C);
+    // The block's internal hidden-state stream (proj_in output, updated in place by the two attention out-projections, consumed by
+    // the feed-forward) is kept in fp16 with fp16 operands, as under the reference's fp16 autocast: its three residual GEMMs are
+    // bound by that stream's HBM traffic.  It is re-based on the fp32 UNet stream by proj_out, so rounding does not accumulate
+    // across blocks.
+    // Measured: NOT a win at these sizes -- the 42 MB stream of a 64x64 block lives in the 126 MB L2, so the residual GEMMs are
+    // bound by epilogue latency rather than HBM bytes, and the conversions cost more than the bytes save (step 23.7 -> 24.5 ms,
+    // LayerNorm 0.71 -> 0.81 ms).  Off by default; MADM_TF_STREAM16=1 enables it (tested at op level and end to end).
+    const bool hs16 = f16() && getenv("MADM_TF_STREAM16");
+    F32T hs; B16T hsh;
+    if (hs16) hsh = b.b16(size_t(M) * C); else hs = b.f32(size_t(M) * C);
+    auto residual_inplace = [&](GemmDesc& d) {  // hs += GEMM
+      if (hs16) { d.residual = reinterpret_cast<const float*>(hsh.p); d.res16 = 1; d.ldr = C; d.out_bf16 = hsh.p; d.ldo16 = C; }
+      else { d.residual = hs.p; d.ldr = C; d.out_f32 = hs.p; d.ldo32 = C; }
+    };
     { GemmDesc d; d.seg[0] = Builder::seg_1x1(n.p, Bn, H, W, C); d.M = int(M); d.N = C; d.Nw = C;
-      d.w = b.pw(b.conv_w(p + ".proj_in", C, C, 1)); d.bias = P(p + ".proj_in.bias", C); d.out_f32 = hs.p; d.ldo32 = C; b.gemm(d); }
+      d.w = b.pw(b.conv_w(p + ".proj_in", C, C, 1)); d.bias = P(p + ".proj_in.bias", C);
+      if (hs16) { d.out_bf16 = hsh.p; d.ldo16 = C; } else { d.out_f32 = hs.p; d.ldo32 = C; }
+      b.gemm(d); }
     b.free(n);
     auto ln = [&](const std::string& name, bf16* y) {
       const float* g = P(name + ".weight", C); const float* be = P(name + ".bias", C);
-      const float* src = hs.p; const int Mi = int(M);
-      const int h16 = f16();
-      b.emit([=](cudaStream_t st) { return layernorm(src, Mi, C, g, be, 1e-5f, y, h16, st); }, false, MADM_KIND_LAYERNORM, 0.0,
-             double(Mi) * C * 6);
+      const void* src = hs16 ? static_cast<const void*>(hsh.p) : static_cast<const void*>(hs.p); const int Mi = int(M);
+      const int h16 = f16(), i16 = hs16 ? 1 : 0;
+      b.emit([=](cudaStream_t st) { return layernorm(src, i16, Mi, C, g, be, 1e-5f, y, h16, st); }, false, MADM_KIND_LAYERNORM, 0.0,
+             double(Mi) * C * (hs16 ? 4 : 6));
     };
     // --- self attention
     B16T l1 = b.b16(size_t(M) * C);
@@ -667,7 +682,7 @@ struct Model {
     b.free(qkv);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(att.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
       d.w = b.pw(b.linear_w(tb + ".attn1.to_out.0", C, C, true)); d.bias = lora_bias(tb + ".attn1.to_out.0", C);
-      d.residual = hs.p; d.ldr = C; d.out_f32 = hs.p; d.ldo32 = C; b.gemm(d); }
+      residual_inplace(d); b.gemm(d); }
     // --- cross attention (K/V precomputed for all layers in kv_all)
     B16T l2 = b.b16(size_t(M) * C);
     ln(tb + ".norm2", l2.p);
@@ -682,7 +697,7 @@ struct Model {
     b.free(q2);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(att.p, M, C); d.M = int(M); d.N = C; d.Nw = C;
       d.w = b.pw(b.linear_w(tb + ".attn2.to_out.0", C, C, true)); d.bias = lora_bias(tb + ".attn2.to_out.0", C);
-      d.residual = hs.p; d.ldr = C; d.out_f32 = hs.p; d.ldo32 = C; b.gemm(d); }
+      residual_inplace(d); b.gemm(d); }
     b.free(att);
     // --- feed-forward (GEGLU fused in the first GEMM's epilogue)
     B16T l3 = b.b16(size_t(M) * C);
@@ -698,9 +713,10 @@ struct Model {
     B16T hsb = b.b16(size_t(M) * C);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(ff.p, M, 4 * C); d.M = int(M); d.N = C; d.Nw = C;
       d.w = b.pw(b.linear_w(tb + ".ff.net.2", C, 4 * C, false)); d.bias = P(tb + ".ff.net.2.bias", C);
-      d.residual = hs.p; d.ldr = C; d.out_bf16 = hsb.p; d.ldo16 = C; b.gemm(d); }
+      if (hs16) { d.residual = reinterpret_cast<const float*>(hsh.p); d.res16 = 1; } else d.residual = hs.p;
+      d.ldr = C; d.out_bf16 = hsb.p; d.ldo16 = C; b.gemm(d); }
     b.free(ff);
-    b.free(hs);
+    if (hs16) b.free(hsh); else b.free(hs);
     Act out = b.act(Bn, H, W, C, true, want_b16 || want_s2d);
     out.h_s2d = want_s2d;
     { GemmDesc d; d.seg[0] = Builder::seg_1x1(hsb.p, Bn, H, W, C); d.M = int(M); d.N = C; d.Nw = C;

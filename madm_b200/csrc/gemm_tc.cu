@@ -46,6 +46,7 @@ struct GemmParams {
   int ld_rowbias;
   const float* residual;
   int ldr;
+  int res16;  // the residual is a 16-bit tensor (operand dtype) instead of fp32
   float* out_f32;
   int ldo32;
   __nv_bfloat16* out_bf16;
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     uint32_t acc_phase = 0;
     uint32_t r[32];
 #ifdef GEMM_INSTR
-    long long e_wait = 0, e_work = 0, e_tiles = 0;
+    long long e_wait = 0, e_work = 0, e_tiles = 0, e_ldtm = 0, e_tr = 0, e_blk = 0, e_chunks = 0;
     const long long e_t0 = clock64();
 #endif
     float* const out32_base = p.out_f32;
@@ -462,21 +463,50 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           // (in-place residual == out_f32 stays safe: these are this chunk's own elements, loaded before its stores)
           float4 resv[8];
           if (residual && vec_ok && n0 + c + 32 <= N) {
-            const float* resp = residual + size_t(row0) * ldr + n0 + c + (lane & 7) * 4;
+            if (p.res16) {  // 16-bit residual stream (8 bytes per lane and row)
+              const uint16_t* resp = reinterpret_cast<const uint16_t*>(residual) + size_t(row0) * ldr + n0 + c + (lane & 7) * 4;
+              uint2 raw16[8];
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int rr = it * 4 + (lane >> 3);
-              resv[it] = (row0 + rr < M) ? *reinterpret_cast<const float4*>(resp + size_t(rr) * ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3);
+                raw16[it] = (row0 + rr < M) ? *reinterpret_cast<const uint2*>(resp + size_t(rr) * ldr) : make_uint2(0u, 0u);
+              }
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                float2 lo, hi;
+                if (fp16) { lo = __half22float2(*reinterpret_cast<const __half2*>(&raw16[it].x)); hi = __half22float2(*reinterpret_cast<const __half2*>(&raw16[it].y)); }
+                else { lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw16[it].x)); hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw16[it].y)); }
+                resv[it] = make_float4(lo.x, lo.y, hi.x, hi.y);
+              }
+            } else {
+              const float* resp = residual + size_t(row0) * ldr + n0 + c + (lane & 7) * 4;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + (lane >> 3);
+                resv[it] = (row0 + rr < M) ? *reinterpret_cast<const float4*>(resp + size_t(rr) * ldr) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
             }
           }
           __syncwarp();  // previous chunk's smem reads are done; warp converged for the aligned tcgen05.ld
+#ifdef GEMM_INSTR
+          const long long ec0 = clock64();
+#endif
           tmem_ld32(taddr + c, r);
           tmem_ld_wait();
+#ifdef GEMM_INSTR
+          const long long ec1 = clock64();
+          e_ldtm += ec1 - ec0;
+#endif
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             st_shared_f4(stg + uint32_t(lane * STG_LD + j) * 4, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
           __syncwarp();
+#ifdef GEMM_INSTR
+          const long long ec2 = clock64();
+          e_tr += ec2 - ec1;
+          ++e_chunks;
+#endif
           const int cc = (lane & 7) * 4;
           const int n = n0 + c + cc;
           if (vec_ok && n0 + c + 32 <= N) {
@@ -505,6 +535,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 default: epi_block<true, true, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
               }
             }
+#ifdef GEMM_INSTR
+            e_blk += clock64() - ec2;
+#endif
             if (do_stats && lane < 8 && row0 < M) {
               // one (sum, sumsq) pair per column for this warp's 32-row block: 8 lanes x 32 B = 256 contiguous bytes, written by
               // exactly one warp -> no atomics, no cross-warp synchronisation, bit-reproducible
@@ -557,8 +590,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
 #ifdef GEMM_INSTR
     if (blockIdx.x == 4 && lane == 0 && (warp == 2 || warp == 6))
-      printf("epilogue warp %d: total %lld clk, %lld tiles | waiting for the accumulator %lld, draining it %lld\n", warp, clock64() - e_t0, e_tiles,
-             e_wait, e_work);
+      printf("epilogue warp %d: total %lld clk, %lld tiles %lld chunks | waiting for the accumulator %lld, draining it %lld (tcgen05.ld %lld, transpose %lld, "
+             "bias + epi_block %lld)\n", warp, clock64() - e_t0, e_tiles, e_chunks, e_wait, e_work, e_ldtm, e_tr, e_blk);
 #endif
   }
 
@@ -662,6 +695,11 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
     if (!d.out_f32 && d.residual) return "gemm: a space-to-depth-only output cannot take an fp32 residual";
     if (!d.out_bf16 || (d.s2d_W & 1) || (d.s2d_H & 1) || d.M % (d.s2d_H * d.s2d_W) != 0 || d.N % 32 != 0 || d.act == ACT_GEGLU)
       return "gemm: space-to-depth output needs a 16-bit output, even H/W, M = B*H*W and N % 32 == 0";
+  }
+  if (d.res16) {
+    if (!d.residual) return "gemm: res16 without a residual";
+    if (d.N % 32 != 0 || d.ldr % 4 != 0 || (reinterpret_cast<uintptr_t>(d.residual) & 7) != 0)
+      return "gemm: a 16-bit residual needs N % 32 == 0, ldr % 4 == 0 and an 8B-aligned pointer (vector epilogue only)";
   }
   if (d.colstats) {
     if (d.stat_rows != 32) return "gemm: stat_rows must be 32";
@@ -846,7 +884,7 @@ const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   p.rowbias = d.rowbias;
   p.rows_per_img = d.rows_per_img > 0 ? d.rows_per_img : 1;
   p.ld_rowbias = d.ld_rowbias ? d.ld_rowbias : d.N;
-  p.residual = d.residual; p.ldr = d.ldr;
+  p.residual = d.residual; p.ldr = d.ldr; p.res16 = d.res16;
   p.out_f32 = d.out_f32; p.ldo32 = d.ldo32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(d.out_bf16); p.ldo16 = d.ldo16;
   p.act = d.act;
@@ -855,6 +893,7 @@ const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   p.vec_ok = (d.N % 8 == 0) && (!d.bias || al16(d.bias)) && (!d.rowbias || (al16(d.rowbias) && p.ld_rowbias % 4 == 0)) &&
              (!d.residual || (al16(d.residual) && d.ldr % 4 == 0)) && (!d.out_f32 || (al16(d.out_f32) && d.ldo32 % 4 == 0)) &&
              (!d.out_bf16 || (al16(d.out_bf16) && d.ldo16 % 8 == 0));
+  if (d.res16 && !p.vec_ok) return "gemm: a 16-bit residual needs the vector epilogue (16B-aligned operands)";
   if (d.act == ACT_GEGLU && !p.vec_ok) return "gemm: GEGLU epilogue needs 16B-aligned outputs";
   if (d.s2d_W > 0 && !p.vec_ok) return "gemm: space-to-depth output needs 16B-aligned operands";
   p.n_tiles = (p.N + L.bn - 1) / L.bn;

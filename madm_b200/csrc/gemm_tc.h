@@ -32,8 +32,9 @@ struct GemmDesc {
   const float* rowbias = nullptr;   // [nimg, N] added per image (time-embedding projection) or null
   int rows_per_img = 1;             // H*W of the output grid (for rowbias)
   int ld_rowbias = 0;               // row pitch of rowbias (0 -> N)
-  const float* residual = nullptr;  // fp32 [M, ldr] or null (may alias out_f32)
+  const float* residual = nullptr;  // fp32 [M, ldr] or null (may alias out_f32); with res16 a 16-bit [M, ldr] tensor (may alias out_bf16)
   int ldr = 0;
+  int res16 = 0;
   float* out_f32 = nullptr;         // fp32 [M, ldo32] or null
   int ldo32 = 0;
   void* out_bf16 = nullptr;         // bf16 [M, ldo16] or null

@@ -27,8 +27,8 @@ const char* groupnorm_colstats_reduce(const float* cs0, int C0, const float* cs1
 const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, const float* partial, int stats_slabs,
                             const float* gamma, const float* beta, float eps, int act, void* y_bf16, void* raw_bf16,
                             int fp16, cudaStream_t st);
-const char* layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y_bf16,
-                      int fp16, cudaStream_t st);
+const char* layernorm(const void* x, int in16 /* x is 16-bit (operand dtype) instead of fp32 */, int M, int C, const float* gamma, const float* beta,
+                      float eps, void* y_bf16, int fp16, cudaStream_t st);
 const char* softmax_rows(const float* s, int R, int L, void* p_bf16, int fp16, cudaStream_t st);
 const char* gn_add_relu_nchw(const float* a, const float* stats_a, const float* ga, const float* ba, const float* s,
                              const float* stats_s, const float* gs, const float* bs, float eps, int B, int HW, int C,
@@ -71,7 +71,7 @@ const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void*
 // split-K: out = act(sum_s partial[s] + bias + rowbias + residual), partial[s] = part + s*split_stride, each [M,N] fp32
 const char* splitk_reduce(const float* part, int splits, long split_stride, int M, int N, const float* bias, const float* rowbias,
                           int rows_per_img, int ld_rowbias, const float* residual, int ldr, float* out32, int ldo32, void* out16, int ldo16,
-                          int act, int fp16, cudaStream_t st);
+                          int act, int fp16, cudaStream_t st, int res16 = 0);
 // fp32 NHWC [B,HW,C] -> NCHW fp32 [B,C,HW]
 const char* nhwc_to_nchw(const float* x, int B, int HW, int C, float* out, cudaStream_t st);
 const char* nhwc_to_nchw_strided(const float* x, int B, int HW, int C, int ld, float* out, cudaStream_t st);

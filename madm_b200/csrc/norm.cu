@@ -364,20 +364,28 @@ const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int 
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm (warp per row)
-__global__ void layernorm_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma,
+template <bool IN16>
+__global__ void layernorm_kernel(const void* __restrict__ x, int M, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, int fp16, uint16_t* __restrict__ y) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const int Q = C >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(x + size_t(row) * C);
   float4 v[10];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
     const int q = i * 32 + lane;
     if (q < Q) {
-      v[i] = __ldg(xr + q);
+      if constexpr (IN16) {  // 16-bit stream: 4 values = 8 bytes
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + size_t(row) * C) + q);
+        float2 lo, hi;
+        if (fp16) { lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x)); hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y)); }
+        else { lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)); hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y)); }
+        v[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        v[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + size_t(row) * C) + q);
+      }
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
   }
@@ -410,11 +418,12 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int M, int C, cons
   }
 }
 
-const char* layernorm(const float* x, int M, int C, const float* gamma, const float* beta, float eps, void* y, int fp16, cudaStream_t st) {
+const char* layernorm(const void* x, int in16, int M, int C, const float* gamma, const float* beta, float eps, void* y, int fp16, cudaStream_t st) {
   if (C % 4 != 0 || C > 1280) return "layernorm: C must be a multiple of 4 and <= 1280";
   const int rows_per_cta = 8;
-  layernorm_kernel<<<(M + rows_per_cta - 1) / rows_per_cta, rows_per_cta * 32, 0, st>>>(x, M, C, gamma, beta, eps, fp16,
-                                                                                      reinterpret_cast<uint16_t*>(y));
+  const unsigned grid = (M + rows_per_cta - 1) / rows_per_cta;
+  if (in16) layernorm_kernel<true><<<grid, rows_per_cta * 32, 0, st>>>(x, M, C, gamma, beta, eps, fp16, reinterpret_cast<uint16_t*>(y));
+  else layernorm_kernel<false><<<grid, rows_per_cta * 32, 0, st>>>(x, M, C, gamma, beta, eps, fp16, reinterpret_cast<uint16_t*>(y));
   return cudaGetLastError() == cudaSuccess ? nullptr : "layernorm launch failed";
 }
 

@@ -74,6 +74,7 @@ def gemm(segs: Sequence[MadmGemmSeg], M: int, N: int, w: torch.Tensor, *, Nw: in
     a.rows_per_img, a.ld_rowbias = rows_per_img, ld_rowbias
     a.residual = residual.data_ptr() if residual is not None else None
     a.ldr = ldr
+    a.res16 = 1 if (residual is not None and residual.dtype != torch.float32) else 0
     a.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
     a.ldo32 = ldo32
     a.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
@@ -113,7 +114,8 @@ def groupnorm_from_colstats(x, B, HW, colstats, stat_rows, gamma, beta, eps, act
 def layernorm(x, gamma, beta, eps, y):
     lib = _lib.load()
     M, Cc = x.shape
-    _lib.check(lib.madm_op_layernorm(_ptr(x), M, Cc, _ptr(gamma), _ptr(beta), eps, _ptr(y), _dt(y.dtype), _stream()), None, "madm_op_layernorm")
+    in16 = 0 if x.dtype == torch.float32 else 1
+    _lib.check(lib.madm_op_layernorm(_ptr(x), in16, M, Cc, _ptr(gamma), _ptr(beta), eps, _ptr(y), _dt(y.dtype), _stream()), None, "madm_op_layernorm")
 
 
 def softmax_rows(s, p):

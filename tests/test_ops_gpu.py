@@ -320,6 +320,24 @@ def test_layernorm(ops, cuda_device, M, Cc):
     y = torch.empty(M, Cc, dtype=DT, device=cuda_device)
     ops.layernorm(x, gamma, beta, 1e-5, y)
     assert relerr(y, F.layer_norm(x, (Cc,), gamma, beta, 1e-5)) < 1e-2
+    x16 = x.to(DT)  # 16-bit input stream (the transformer blocks' hidden states with fp16 operands)
+    y16 = torch.empty(M, Cc, dtype=DT, device=cuda_device)
+    ops.layernorm(x16, gamma, beta, 1e-5, y16)
+    assert relerr(y16, F.layer_norm(x16.float(), (Cc,), gamma, beta, 1e-5)) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K,pair", [(4096, 320, 320, 0), (1000, 640, 2560, -1), (8192, 320, 1280, 1)])
+def test_gemm_16bit_residual_in_place(ops, cuda_device, M, N, K, pair):
+    """hs += A W^T + bias on a 16-bit stream, in place (residual and output are the same 16-bit tensor): the update the
+    transformer blocks' attention out-projections perform with fp16 operands."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = bf(torch.randn(M, K, device=cuda_device, generator=g))
+    w = bf(torch.randn(N, K, device=cuda_device, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=cuda_device, generator=g)
+    hs = bf(torch.randn(M, N, device=cuda_device, generator=g))
+    ref = hs.float() + a.float() @ w.float().t() + bias
+    ops.gemm([ops.make_seg(a, 1, 1, M, K)], M, N, w, bias=bias, residual=hs, ldr=N, out_bf16=hs, ldo16=N, pair=pair)
+    assert relerr(hs, ref) < 1e-2
 
 
 def test_softmax_rows(ops, cuda_device):
