@@ -277,7 +277,7 @@ def run_product(args, rank, local_rank, world):
                                "(VAE-enc + q-sample t=0 + UNet taps + s2..s5 projections); sem_seg_head is SURVEY §8 f-2 (next), not timed",
                    "per_gpu_batch": B, "global_batch": B * world, "input_modal": "others", "adapter": "Depth_r16_a16 (folded)",
                    "l2": f"working set (packed weights 1.8 GB + workspace {ws_gb:.1f} GB) >> 126 MB L2; no explicit flush",
-                   "accumulate": "fp32", "residual_stream": "fp32", "gflop_per_image": GF_PER_IMG},
+                   "accumulate": "fp32", "residual_stream": "fp32 (UNet, projections); fp16 in the VAE 512^2 / 256^2 stages with fp16 operands, like the reference's fp16 VAE", "gflop_per_image": GF_PER_IMG},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": sum(t.numel() * 4 for t in outs_host),

@@ -8,9 +8,11 @@
 // NHWC bf16 activation tensor, shifted by (dx,dy); out-of-bounds rows/columns are zero-filled by TMA, which is exactly
 // the convolution's zero padding.  W tiles are 2-D TMA boxes over the packed K-major weight matrix.  Both land in
 // 128B-swizzled shared memory and are consumed directly by tcgen05.mma (UMMA 128xBNx16, fp32 accumulators in TMEM).
-// Warp roles: warp0 = TMA producer, warp1 = TMEM allocator + single-thread MMA issuer, warps2-5 = epilogue
-// (tcgen05.ld -> registers -> fused bias / time-embedding row bias / fp32 residual / SiLU / GEGLU -> fp32 and/or bf16 stores).
-// Two CTAs are resident per SM (<=113 KB smem, <=256 TMEM columns each) so one CTA's epilogue overlaps the other's mainloop.
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (behind elect.sync), warps 2-9 = epilogue
+// (tcgen05.ld -> per-warp smem transpose -> fused bias / time-embedding row bias / fp32 or 16-bit residual / SiLU / ReLU / GEGLU ->
+// fp32 and/or 16-bit stores, optionally in space-to-depth layout, optionally with the consumer GroupNorm's column statistics).
+// One CTA per SM (~200 KB of smem stages, two TMEM accumulator stages so the MMAs of tile i+1 overlap the epilogue of tile i);
+// tiles >= 128 wide run as cta_group::2 pairs (256-row MMAs, each CTA stages half of W).  See DESIGN.md section 5.
 #include "gemm_tc.h"
 #include "cvt.cuh"
 #include "ptx.cuh"

@@ -88,6 +88,21 @@ def test_head_parity_on_random_features(heads, cuda_device, B):
         assert torch.equal(out, ph({"output_features": feats}))  # no atomics anywhere: bit-identical reruns
 
 
+def test_head_bf16_operands(cuda_device):
+    """The head follows the context's operand dtype: bf16 operands within the looser bf16 gate (cosine >= 0.999, 3e-2)."""
+    from madm_b200.head import DAFormerHead
+    from oracle.daformer_head import build_head
+    oh = build_head().to(cuda_device)
+    ph = DAFormerHead(**HEAD_KW, device=cuda_device, compute_dtype="bf16").eval()
+    ph.load_state_dict(oh.state_dict())
+    feats = _feats(cuda_device, 2, 77)
+    with torch.no_grad():
+        ref = oh({"output_features": feats})
+        out = ph({"output_features": feats})
+    assert cosine(out, ref) >= 0.999 and max_rel(out, ref) <= 3e-2
+    assert (out.argmax(1) == ref.argmax(1)).float().mean().item() >= 0.97
+
+
 def test_head_refolds_after_parameter_update(heads, cuda_device):
     """BatchNorm statistics / weights are folded at pack time: an in-place update must trigger a repack (version tracking)."""
     oh, ph = heads

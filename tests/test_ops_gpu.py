@@ -326,6 +326,41 @@ def test_layernorm(ops, cuda_device, M, Cc):
     assert relerr(y16, F.layer_norm(x16.float(), (Cc,), gamma, beta, 1e-5)) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,taps,bn,mt", [
+    (1, 1, 640, 320, 320, 1, 160, 0),     # 5 row tiles: the last pair has an empty second CTA
+    (1, 1, 1000, 256, 416, 1, 0, 0),      # ragged M and an N that is not a multiple of the tile (W rows past N are TMA zero fill)
+    (2, 64, 64, 320, 320, 9, 0, 0),       # 3x3 conv, 160-wide pair tiles
+    (2, 128, 128, 128, 128, 9, 128, 2),   # 512-row pair tiles (two M sub-tiles per CTA)
+    (3, 32, 32, 640, 1280, 1, 0, 0),
+])
+def test_gemm_cta_pairs_match_single_cta(ops, cuda_device, B, H, W, Cin, Cout, taps, bn, mt):
+    """tcgen05 cta_group::2 pairs (256-row MMAs, each CTA staging half of the W tile) must reproduce the single-CTA kernel bit for
+    bit: same MMA k-order, same epilogue; also against a torch reference."""
+    g = torch.Generator(device="cuda").manual_seed(B * H + Cout)
+    M = B * H * W
+    x = bf(torch.randn(B, H, W, Cin, device=cuda_device, generator=g) * 0.5)
+    w = bf(torch.randn(Cout, taps * Cin, device=cuda_device, generator=g) / math.sqrt(taps * Cin))
+    bias = torch.randn(Cout, device=cuda_device, generator=g)
+    res = torch.randn(M, Cout, device=cuda_device, generator=g)
+    seg = ops.make_seg(x, B, H, W, Cin, taps=ops.taps_3x3()) if taps == 9 else ops.make_seg(x.reshape(M, Cin), 1, 1, M, Cin)
+    outs = {}
+    for pair in (-1, 1):
+        o32 = torch.empty(M, Cout, device=cuda_device)
+        o16 = torch.empty(M, Cout, device=cuda_device, dtype=DT) if Cout % 8 == 0 else None
+        kw = dict(out_bf16=o16, ldo16=Cout) if o16 is not None else {}
+        ops.gemm([seg], M, Cout, w, bias=bias, residual=res, ldr=Cout, out_f32=o32, ldo32=Cout, bn=bn, mt=mt, pair=pair, **kw)
+        outs[pair] = (o32, o16)
+    assert torch.equal(outs[-1][0], outs[1][0])
+    if outs[1][1] is not None:
+        assert torch.equal(outs[-1][1], outs[1][1])
+    if taps == 1:
+        ref = x.reshape(M, Cin).float() @ w.float().t() + bias + res
+    else:
+        wc = w.float().reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wc, padding=1).permute(0, 2, 3, 1).reshape(M, Cout) + bias + res
+    assert relerr(outs[1][0], ref) < 2e-3
+
+
 @pytest.mark.parametrize("M,N,K,pair", [(4096, 320, 320, 0), (1000, 640, 2560, -1), (8192, 320, 1280, 1)])
 def test_gemm_16bit_residual_in_place(ops, cuda_device, M, N, K, pair):
     """hs += A W^T + bias on a 16-bit stream, in place (residual and output are the same 16-bit tensor): the update the
