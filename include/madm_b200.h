@@ -210,6 +210,13 @@ int madm_op_bilinear_resize(const void* src16, int32_t B, int32_t Hs, int32_t Ws
                             int32_t dst_pitch, int32_t dtype, madm_stream stream); /* F.interpolate(bilinear, align_corners=False), NHWC */
 int madm_op_depthwise3x3(const void* src16, int32_t B, int32_t H, int32_t W, int32_t C, int32_t dilation, const float* w9 /*[9][C]*/,
                          const float* shift /*[C]*/, void* dst16, int32_t dtype, madm_stream stream); /* + shift + ReLU */
+/* teacher post-processing + DACS mixing (reference mtmadise.py:337-352, utils/dacs_transforms.py:87-112) */
+int madm_op_pseudo_labels(const float* logits /*[B,C,h,w]*/, int32_t B, int32_t C, int32_t h, int32_t w, int32_t H, int32_t W, float threshold,
+                          int32_t ignore_top, int64_t* label /*[B,H,W]*/, float* prob /*[B,H,W]*/, float* weight /*[B,H,W] or NULL*/,
+                          int32_t* count /*device scalar: pixels with prob >= threshold*/, madm_stream stream);
+int madm_op_class_mask(const int64_t* label, int64_t n, const int64_t* classes, int32_t k, int64_t* mask, madm_stream stream);
+int madm_op_one_mix(const int64_t* mask, int64_t n, const int64_t* label_a, const int64_t* label_b, int64_t* label_out /*or NULL*/,
+                    const float* weight_a, const float* weight_b, float* weight_out /*or NULL*/, madm_stream stream);
 int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, int32_t dtype,
                        madm_stream stream);
 int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out_bf16, int32_t* range_flag,

@@ -95,6 +95,10 @@ SYMBOLS = {
     "madm_op_nchw_to_nhwc16": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_bilinear_resize": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "madm_op_depthwise3x3": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    "madm_op_pseudo_labels": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    "madm_op_class_mask": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
+    "madm_op_one_mix": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "madm_op_upsample2x": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_image_im2col": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
     "madm_op_gn_add_relu_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,

@@ -119,6 +119,20 @@ int madm_op_depthwise3x3(const void* src, int32_t B, int32_t H, int32_t W, int32
   RUN(depthwise3x3_nhwc16(src, B, H, W, C, dilation, w9, shift, dst, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
+int madm_op_pseudo_labels(const float* logits, int32_t B, int32_t C, int32_t h, int32_t w, int32_t H, int32_t W, float threshold,
+                          int32_t ignore_top, int64_t* label, float* prob, float* weight, int32_t* count, madm_stream stream) {
+  RUN(pseudo_labels(logits, B, C, h, w, H, W, threshold, ignore_top, label, prob, weight, count, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_class_mask(const int64_t* label, int64_t n, const int64_t* classes, int32_t k, int64_t* mask, madm_stream stream) {
+  RUN(class_mask(label, long(n), classes, k, mask, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_one_mix(const int64_t* mask, int64_t n, const int64_t* label_a, const int64_t* label_b, int64_t* label_out, const float* weight_a,
+                    const float* weight_b, float* weight_out, madm_stream stream) {
+  RUN(one_mix(mask, long(n), label_a, label_b, label_out, weight_a, weight_b, weight_out, static_cast<cudaStream_t>(stream)));
+}
+
 int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out, int32_t* range_flag, int32_t dtype,
                          madm_stream stream) {
   RUN(image_im2col(img, B, H, W, out, range_flag, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));

@@ -90,6 +90,15 @@ const char* bn_fold(const float* gamma, const float* beta, const float* mean, co
 // depthwise weight [C,1,3,3] * scale[c] -> fp32 [9][C]
 const char* pack_depthwise(const float* w, const float* scale, int C, float* out, cudaStream_t st);
 
+// ---- teacher.cu (teacher post-processing + DACS mixing)
+// logits [B,C,h,w] fp32 NCHW -> bilinear (align_corners=False) to HxW -> softmax max / argmax -> label int64, prob fp32 [B,H,W];
+// count (device int scratch) = #pixels with prob >= threshold; weight (optional) = count/pixels, 0 in the top ignore_top rows
+const char* pseudo_labels(const float* logits, int B, int C, int h, int w, int H, int W, float threshold, int ignore_top, int64_t* label,
+                          float* prob, float* weight, int* count, cudaStream_t st);
+const char* class_mask(const int64_t* label, long n, const int64_t* classes, int k, int64_t* mask, cudaStream_t st);
+const char* one_mix(const int64_t* mask, long n, const int64_t* la, const int64_t* lb, int64_t* lout, const float* wa, const float* wb,
+                    float* wout, cudaStream_t st);
+
 // ---- pack.cu (weight packing; fp32 PyTorch layouts -> bf16 K-major GEMM operands)
 // conv weight [N, C, kh, kw] fp32 -> [N, kh*kw*Cpad] bf16 with K index = tap*Cpad + c (zero fill for c >= C)
 const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out_bf16, int fp16,

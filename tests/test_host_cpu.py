@@ -178,3 +178,20 @@ def test_head_rejects_unsupported_variants_and_has_no_cpu_path():
         head({"output_features": feats})
     with pytest.raises(NotImplementedError):
         head.train()({"output_features": feats})
+
+
+def test_teacher_ops_have_no_cpu_path():
+    """SURVEY §8 f-4 helpers refuse CPU tensors instead of falling back to PyTorch; the oracle restatement runs on CPU."""
+    import pytest
+    from madm_b200 import _lib, teacher
+    from oracle import teacher as ot
+    logits = torch.randn(1, 19, 8, 8)
+    with pytest.raises(_lib.MadmError):
+        teacher.pseudo_labels(logits, (32, 32), 0.9)
+    with pytest.raises(_lib.MadmError):
+        teacher.generate_class_mask(torch.zeros(4, 4, dtype=torch.int64), torch.tensor([0]))
+    lab, prob, w, val = ot.pseudo_labels(logits, (32, 32), 0.2, psweight_ignore_top=3)
+    assert lab.shape == (1, 32, 32) and lab.dtype == torch.int64 and 0.0 <= val <= 1.0
+    assert torch.count_nonzero(w[:, :3]) == 0 and torch.all(w[:, 3:] == val)
+    m = ot.generate_class_mask(lab[0], torch.tensor([int(lab[0, 0, 0])]))
+    assert m.shape == (1, 32, 32) and m[0, 0, 0] == 1
