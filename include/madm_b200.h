@@ -217,6 +217,10 @@ int madm_op_pseudo_labels(const float* logits /*[B,C,h,w]*/, int32_t B, int32_t 
 int madm_op_class_mask(const int64_t* label, int64_t n, const int64_t* classes, int32_t k, int64_t* mask, madm_stream stream);
 int madm_op_one_mix(const int64_t* mask, int64_t n, const int64_t* label_a, const int64_t* label_b, int64_t* label_out /*or NULL*/,
                     const float* weight_a, const float* weight_b, float* weight_out /*or NULL*/, madm_stream stream);
+/* sliding-window merge of per-crop feature maps (reference feature_extractor.py:254-275: accumulate, divide by the count matrix):
+ * feats [nwin*n, C, hf, wf] window-major, wins [nwin][2] = window origin (y1, x1) in feature pixels -> out [n, C, Hf, Wf] */
+int madm_op_slide_merge(const float* feats, int32_t nwin, int32_t n, int32_t C, int32_t hf, int32_t wf, const int32_t* wins, int32_t Hf,
+                        int32_t Wf, float* out, madm_stream stream);
 int madm_op_upsample2x(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, int32_t dtype,
                        madm_stream stream);
 int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out_bf16, int32_t* range_flag,

@@ -167,23 +167,17 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
     def slide_forward(self, img, input_modal="rgb", ema_forward=False, timestep=None, **kwargs):  # :199-278
         b, _, h_img, w_img = img.shape
         wins = self.slide_windows(h_img, w_img)
-        outs = {k: torch.zeros((b, self._out_feature_channels[k], h_img // s, w_img // s), dtype=torch.float32, device=img.device)
-                for k, s in self._out_feature_strides.items()}
-        cnt = {k: torch.zeros((1, 1, h_img // s, w_img // s), dtype=torch.float32, device=img.device)
-               for k, s in self._out_feature_strides.items()}
-        # crops are the batch dimension of the engine: all windows of `crop_batch // len(wins)` images per call
+        from . import ops
+        # crops are the batch dimension of the engine: all windows of `crop_batch // len(wins)` images per call; the accumulate /
+        # divide-by-count of feature_extractor.py:254-275 is one gather kernel per feature map (window order = the reference's += order)
         per_call = max(1, self.crop_batch // len(wins))
+        parts = {k: [] for k in self._out_features}
         for i0 in range(0, b, per_call):
             i1 = min(b, i0 + per_call)
             crops = torch.cat([img[i0:i1, :, y1:y2, x1:x2] for (y1, y2, x1, x2) in wins], dim=0)
             feats = self._extract(crops, input_modal, ema_forward, timestep, **kwargs)["features"]
-            n = i1 - i0
-            for wi, (y1, y2, x1, x2) in enumerate(wins):
-                for k, f in zip(self._out_features, feats):
-                    s = self._out_feature_strides[k]
-                    outs[k][i0:i1, :, y1 // s:y2 // s, x1 // s:x2 // s] += f[wi * n:(wi + 1) * n]
-                    if i0 == 0:
-                        cnt[k][..., y1 // s:y2 // s, x1 // s:x2 // s] += 1
-        for k in outs:
-            outs[k] /= cnt[k]
+            for k, f in zip(self._out_features, feats):
+                s = self._out_feature_strides[k]
+                parts[k].append(ops.slide_merge(f, len(wins), [(y1 // s, x1 // s) for (y1, _, x1, _) in wins], h_img // s, w_img // s))
+        outs = {k: (v[0] if len(v) == 1 else torch.cat(v, dim=0)) for k, v in parts.items()}
         return {"output_features": outs}

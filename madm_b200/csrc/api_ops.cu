@@ -133,6 +133,11 @@ int madm_op_one_mix(const int64_t* mask, int64_t n, const int64_t* label_a, cons
   RUN(one_mix(mask, long(n), label_a, label_b, label_out, weight_a, weight_b, weight_out, static_cast<cudaStream_t>(stream)));
 }
 
+int madm_op_slide_merge(const float* feats, int32_t nwin, int32_t n, int32_t C, int32_t hf, int32_t wf, const int32_t* wins, int32_t Hf, int32_t Wf,
+                        float* out, madm_stream stream) {
+  RUN(slide_merge(feats, nwin, n, C, hf, wf, wins, Hf, Wf, out, static_cast<cudaStream_t>(stream)));
+}
+
 int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void* out, int32_t* range_flag, int32_t dtype,
                          madm_stream stream) {
   RUN(image_im2col(img, B, H, W, out, range_flag, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));

@@ -99,6 +99,9 @@ const char* class_mask(const int64_t* label, long n, const int64_t* classes, int
 const char* one_mix(const int64_t* mask, long n, const int64_t* la, const int64_t* lb, int64_t* lout, const float* wa, const float* wb,
                     float* wout, cudaStream_t st);
 
+// sliding-window merge: feats [nwin*n,C,hf,wf] (window-major), wins [nwin][2] = (y1,x1) in feature pixels -> out [n,C,Hf,Wf] = mean over covering windows
+const char* slide_merge(const float* feats, int nwin, int n, int C, int hf, int wf, const int* wins, int Hf, int Wf, float* out, cudaStream_t st);
+
 // ---- pack.cu (weight packing; fp32 PyTorch layouts -> bf16 K-major GEMM operands)
 // conv weight [N, C, kh, kw] fp32 -> [N, kh*kw*Cpad] bf16 with K index = tap*Cpad + c (zero fill for c >= C)
 const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out_bf16, int fp16,

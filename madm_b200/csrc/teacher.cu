@@ -108,4 +108,33 @@ const char* one_mix(const int64_t* mask, long n, const int64_t* la, const int64_
   return cudaGetLastError() == cudaSuccess ? nullptr : "one_mix launch failed";
 }
 
+// ------------------------------------------------------------------ sliding-window merge (feature_extractor.py:254-275)
+// feats [nwin*n, C, hf, wf] (window-major: crop wi of image b at row wi*n + b) -> out [n, C, Hf, Wf] = sum over the windows that
+// cover a pixel / their count.  Gather form: each output pixel adds its windows in window order (the reference's `+=` order) and
+// divides by the count, so there are no atomics and the result is bit-identical to the sequential accumulate.
+__global__ void slide_merge_kernel(const float* __restrict__ feats, int nwin, int n, int C, int hf, int wf, const int* __restrict__ wins,
+                                   int Hf, int Wf, long total, float* __restrict__ out) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = int(i % Wf), y = int((i / Wf) % Hf);
+  const long bc = i / (long(Wf) * Hf);
+  const int c = int(bc % C), b = int(bc / C);
+  float acc = 0.f;
+  int cnt = 0;
+  for (int wi = 0; wi < nwin; ++wi) {
+    const int yy = y - wins[2 * wi], xx = x - wins[2 * wi + 1];
+    if (yy >= 0 && yy < hf && xx >= 0 && xx < wf) {
+      acc += feats[((size_t(wi) * n + b) * C + c) * hf * wf + size_t(yy) * wf + xx];
+      ++cnt;
+    }
+  }
+  out[i] = acc / float(cnt);  // cnt == 0 cannot happen for the reference's window grids (inf/nan like the reference's 0/0 otherwise)
+}
+const char* slide_merge(const float* feats, int nwin, int n, int C, int hf, int wf, const int* wins, int Hf, int Wf, float* out, cudaStream_t st) {
+  if (nwin < 1 || n < 1 || C < 1 || hf < 1 || wf < 1 || Hf < hf || Wf < wf) return "slide_merge: bad geometry";
+  const long total = long(n) * C * Hf * Wf;
+  slide_merge_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(feats, nwin, n, C, hf, wf, wins, Hf, Wf, total, out);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "slide_merge launch failed";
+}
+
 }  // namespace madm

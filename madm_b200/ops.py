@@ -206,6 +206,18 @@ def depthwise3x3(x, w9, shift, dilation):
     return out
 
 
+def slide_merge(feats, nwin, wins_yx, Hf, Wf):
+    """feats [nwin*n,C,hf,wf] fp32 (window-major), wins_yx [(y1,x1)] in feature pixels -> [n,C,Hf,Wf] mean over covering windows."""
+    lib = _lib.load()
+    NB, Cc, hf, wf = feats.shape
+    n = NB // nwin
+    wins = torch.tensor(list(wins_yx), dtype=torch.int32, device=feats.device).reshape(-1).contiguous()
+    out = torch.empty(n, Cc, Hf, Wf, dtype=torch.float32, device=feats.device)
+    _lib.check(lib.madm_op_slide_merge(_ptr(feats.contiguous()), nwin, n, Cc, hf, wf, _ptr(wins), Hf, Wf, _ptr(out), _stream()), None,
+               "madm_op_slide_merge")
+    return out
+
+
 def image_im2col(img, range_flag=None, dtype=torch.float16):
     lib = _lib.load()
     B, _, H, W = img.shape

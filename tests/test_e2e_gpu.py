@@ -181,6 +181,63 @@ def test_slide_forward_512x1024(pair, cuda_device):
         _check("slide/" + k, out[k], ref[k])
 
 
+def test_slide_forward_1024x1024_config3(pair, cuda_device):
+    """1024x1024 -> 3x3 = 9 crops of 512^2 at stride 256 (crops are the engine's batch dimension)."""
+    from oracle import synthetic
+    from oracle.lora import set_adapter
+    ob, pb = pair
+    if _MODE != "fp16":
+        pytest.skip("one dtype is enough for the 9-crop configuration")
+    set_adapter(ob.feature_extractor.ldm_extractor.unet, ["Depth"])
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    img = synthetic.synthetic_images(1, h=1024, w=1024, seed=33).to(cuda_device)
+    assert len(pb.slide_windows(1024, 1024)) == 9
+    with torch.no_grad():
+        ref = ob.slide_forward(img, "others")["output_features"]
+        out = pb.slide_forward(img, "others")["output_features"]
+    for k in ref:
+        assert out[k].shape == ref[k].shape
+        _check("slide1024/" + k, out[k], ref[k])
+
+
+def test_teacher_chain_1024x2048_config4(pair, cuda_device):
+    """1024x2048, input_modal='others', ema_forward=True -> 3x7 = 21 crops -> EMA-projected features -> head ->
+    softmax / max (pseudo-label) as mtmadise.py:335-349, product chain (backbone, head and post-processing on the device) against
+    the oracle chain."""
+    import torch.nn.functional as F
+    from oracle import synthetic, teacher as ot
+    from oracle.daformer_head import build_head
+    from oracle.lora import set_adapter
+    from madm_b200 import teacher
+    from madm_b200.head import DAFormerHead
+    from test_head_gpu import HEAD_KW
+    ob, pb = pair
+    if _MODE != "fp16":
+        pytest.skip("one dtype is enough for the 21-crop configuration")
+    set_adapter(ob.feature_extractor.ldm_extractor.unet, ["Depth"])
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    img = synthetic.synthetic_images(1, h=1024, w=2048, seed=35).to(cuda_device)
+    assert len(pb.slide_windows(1024, 2048)) == 21
+    with torch.no_grad():
+        ref = ob.slide_forward(img, "others", ema_forward=True)
+        out = pb.slide_forward(img, "others", ema_forward=True)
+        for k in ref["output_features"]:
+            _check("config4/" + k, out["output_features"][k], ref["output_features"][k])
+        # the head consumes 128x128 s2 maps: evaluate it on the 512x512 window at the image centre of the merged feature maps
+        def centre(fd):
+            return {"output_features": {k: v[:, :, v.shape[2] // 2 - v.shape[2] // 4:v.shape[2] // 2 + v.shape[2] // 4,
+                                             v.shape[3] // 2 - v.shape[3] // 8:v.shape[3] // 2 + v.shape[3] // 8].contiguous()
+                                        for k, v in fd["output_features"].items()}}
+        oh = build_head().to(cuda_device)
+        ph = DAFormerHead(**HEAD_KW, device=cuda_device).eval()
+        ph.load_state_dict(oh.state_dict())
+        lab_r, prob_r, w_r, val_r = ot.pseudo_labels(oh(centre(ref)), (512, 512), 0.3)
+        lab, prob, wgt, count = teacher.pseudo_labels(ph(centre(out)), (512, 512), 0.3)
+    agree = (lab == lab_r).float().mean().item()
+    print(f"config 4 pseudo-label agreement {100 * agree:.3f} %")
+    assert agree >= 0.995
+
+
 def test_inplace_parameter_update_repacks(pair, cuda_device):
     """The engine keeps 16-bit packed copies of the weights; an in-place update of a parameter after the first forward (optimizer
     step, load_state_dict -> copy_) must be seen through the shared version counter and trigger a repack."""

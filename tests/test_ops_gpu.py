@@ -443,3 +443,23 @@ def test_pack_linear_lora_fold(ops, cuda_device):
     assert (diff > 0).float().mean().item() < 1e-3
     assert relerr(out, ref) < 1e-2
     assert torch.equal(ops.pack_linear(w, dtype=DT), bf(w))
+
+
+# ---------------------------------------------------------------------------------------------- sliding-window merge
+@pytest.mark.parametrize("H,W", [(512, 1024), (1024, 1024), (768, 1280)])
+def test_slide_merge_matches_sequential_accumulate(ops, cuda_device, H, W):
+    """feature_extractor.py:254-275: out[window] += crop; cnt[window] += 1; out /= cnt -- reproduced bit for bit by the gather kernel
+    (same addition order per pixel)."""
+    g = torch.Generator(device="cuda").manual_seed(H + W)
+    s, n, Cc, crop, stride = 8, 2, 24, 512, 256
+    wins = [(y, x) for y in range(0, H - crop + 1, stride) for x in range(0, W - crop + 1, stride)]
+    hf = crop // s
+    feats = torch.randn(len(wins) * n, Cc, hf, hf, device=cuda_device, generator=g)
+    out = ops.slide_merge(feats, len(wins), [(y // s, x // s) for y, x in wins], H // s, W // s)
+    ref = torch.zeros(n, Cc, H // s, W // s, device=cuda_device)
+    cnt = torch.zeros(1, 1, H // s, W // s, device=cuda_device)
+    for wi, (y, x) in enumerate(wins):
+        ref[:, :, y // s:y // s + hf, x // s:x // s + hf] += feats[wi * n:(wi + 1) * n]
+        cnt[..., y // s:y // s + hf, x // s:x // s + hf] += 1
+    ref /= cnt
+    assert torch.equal(out, ref)
