@@ -288,6 +288,23 @@ class BasePromptTimeGenerator(nn.Module):
         """ldm_base.py:832-917: fills cond_inputs / cond_emb / timestep into ``batched_inputs``."""
         assert input_modal in {"rgb", "others", "mixed", "masked_prompt", "prompt_perturbation", "rand_prompt"}
         image = batched_inputs["img"]
+        # The deterministic modes depend on a handful of small parameters only (batch-invariant): the batched tensors are cached
+        # per (mode, ema, batch) and re-derived when a parameter's version counter moves, so steady-state inference launches no
+        # PyTorch kernels for the conditioning at all.
+        cache_key = None
+        if not torch.is_grad_enabled() and (input_modal in ("rgb", "others") or (input_modal == "mixed" and self.mix_source_target_prompt)):
+            mods = [self.clip_project_rgb] if input_modal == "rgb" else (
+                [self.clip_project_rgb, self.clip_project_others] if input_modal == "mixed"
+                else [self.ema_clip_project_others if ema_forward else self.clip_project_others])
+            vers = tuple((id(t), t._version, t.data_ptr()) for m in mods for t in m.parameters()) + (
+                (id(self.uncond_inputs), self.uncond_inputs._version),)
+            cache_key = (input_modal, bool(ema_forward), int(image.shape[0]), str(image.device))
+            hit = getattr(self, "_cond_cache", {}).get(cache_key)
+            if hit is not None and hit[0] == vers:
+                if timestep is not None:
+                    batched_inputs["timestep"] = timestep
+                batched_inputs["cond_inputs"], batched_inputs["cond_emb"] = hit[1], hit[2]
+                return batched_inputs
         if input_modal == "rgb":
             assert ema_forward is False
             ci, ce = self.clip_project_rgb(self.uncond_inputs, None)
@@ -312,6 +329,10 @@ class BasePromptTimeGenerator(nn.Module):
             ci = torch.repeat_interleave(ci, repeats=image.shape[0], dim=0)
             ce = torch.repeat_interleave(ce, repeats=image.shape[0], dim=0)
         batched_inputs["cond_inputs"], batched_inputs["cond_emb"] = ci, ce
+        if cache_key is not None:
+            if not hasattr(self, "_cond_cache"):
+                object.__setattr__(self, "_cond_cache", {})
+            self._cond_cache[cache_key] = (vers, ci.detach(), ce.detach())
         return batched_inputs
 
     def forward(self, batched_inputs, input_modal, ema_forward=False, timestep=None, return_unet_feats=False, **kwargs):

@@ -251,15 +251,17 @@ def test_inplace_parameter_update_repacks(pair, cuda_device):
     wp = pb.feature_projections[1][0].conv1.weight
     uo = ob.feature_extractor.ldm_extractor.unet.conv_in.weight
     up = pb.feature_extractor.ldm_extractor.unet.conv_in.weight
+    po = ob.feature_extractor.clip_project_others.prompt_embed  # the cached conditioning tensors must follow their parameters too
+    pp = pb.feature_extractor.clip_project_others.prompt_embed
     with torch.no_grad():
         before = pb(img, input_modal="others")["output_features"]["s3"].clone()
-        for t in (wo, wp, uo, up):
+        for t in (wo, wp, uo, up, po, pp):
             t.mul_(1.25)
         try:
             ref = ob(img, input_modal="others")["output_features"]
             out = pb(img, input_modal="others")["output_features"]
         finally:
-            for t in (wo, wp, uo, up):
+            for t in (wo, wp, uo, up, po, pp):
                 t.div_(1.25)
     assert not torch.equal(before, out["s3"])
     for k in ("s2", "s3", "s4", "s5"):
