@@ -71,6 +71,20 @@ int madm_destroy(madm_ctx* ctx);
 int madm_set_compute_dtype(madm_ctx* ctx, int32_t dtype);
 int madm_get_compute_dtype(const madm_ctx* ctx);
 
+/* Path variant (a property of the backbone's constructor config).
+ * MADM_VARIANT_BASE: config_files/common/models/mtmadise_multi_lora.py:14-41 — encoder tap (encoder_block_indices=[5]) -> 's2'.
+ * MADM_VARIANT_S0:   the configuration all shipped experiment files select
+ *   (config_files/SemSeg/MTMADISE/mtmadise_cityscapes_rgb_to_depth_11.py:47-55: vae_decoder_loss=True, encoder_block_indices=[],
+ *   feature_dims[0]=3, projection_dim[0]=128, out_features[0]='s0'): the UNet runs to its final output (conv_norm_out / conv_out,
+ *   ldm_diffusers.py:608-611), the VAE decoder decodes it (vae_decoder, ldm_diffusers.py:314-346) and the decoded 3 x 512 x 512 image
+ *   is the first feature, projected by Bottleneck(3 -> 128 -> 128) into 's0' [B,128,512,512].
+ * Needs the vae.decoder.* / vae.post_quant_conv.* / unet.conv_norm_out.* / unet.conv_out.* parameters registered.
+ * Invalidates packed weights and plans: call before madm_pack_weights. */
+#define MADM_VARIANT_BASE 0
+#define MADM_VARIANT_S0 1
+int madm_set_variant(madm_ctx* ctx, int32_t variant);
+int madm_get_variant(const madm_ctx* ctx);
+
 /* Register / refresh parameter pointers.  Replaces nn.Module parameter ownership: the library never copies or
  * owns model weights, it reads biases and norm affines in place and packs GEMM weights into the arena below. */
 int madm_set_tensors(madm_ctx* ctx, const madm_tensor* named, int32_t n);
@@ -94,6 +108,10 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float lo
  * dict: reads args.out[0..3] (s2..s5, produced by MADM_STAGE_PROJ in the same call or supplied by the caller) and writes
  * args.logits.  Needs the head's parameters registered under "sem_seg_head." (a context may hold only those). */
 #define MADM_STAGE_HEAD 8
+/* MADM_VARIANT_S0 only: UNet conv_norm_out / conv_out (ldm_diffusers.py:608-611) + vae_decoder(output_final=True)
+ * (ldm_diffusers.py:192, :314-346).  Runs between MADM_STAGE_UNET and MADM_STAGE_PROJ; MADM_STAGE_ALL_S0 is the whole variant path. */
+#define MADM_STAGE_DEC 16
+#define MADM_STAGE_ALL_S0 23
 
 /* Workspace bytes needed by madm_extract for batch B (all stages). */
 size_t madm_workspace_bytes(madm_ctx* ctx, int32_t B);
@@ -109,7 +127,7 @@ typedef struct madm_extract_args {
   const int64_t* timesteps;    /* [B] int64 device: torch.randint(lo,hi,(B,)) (ldm_diffusers.py:160) */
   const float* shared_noise;   /* [1,4,64,64] fp32: buffer shared_noise (ldm_diffusers.py:73-75) */
   const float* noisy_latents_in; /* optional [B,4,64,64] NCHW: overrides VAE+q-sample output for the UNet stage */
-  float* out[4];               /* s2 [B,512,128,128], s3 [B,512,64,64], s4 [B,512,32,32], s5 [B,512,16,16] fp32 NCHW */
+  float* out[4];               /* s2 [B,512,128,128] (MADM_VARIANT_S0: s0 [B,128,512,512]), s3 [B,512,64,64], s4 [B,512,32,32], s5 [B,512,16,16] fp32 NCHW */
   /* optional debug / parity taps (NULL to skip), fp32 NCHW */
   float* latents;              /* [B,4,64,64]  vae mean * 0.18215 */
   float* noisy_latents;        /* [B,4,64,64] */
@@ -120,6 +138,11 @@ typedef struct madm_extract_args {
   int32_t* range_flag;         /* optional device int: set to 1 if the normalised image leaves [-1,1]
                                   (the reference asserts this with a host sync, ldm_diffusers.py:147) */
   float* logits;               /* MADM_STAGE_HEAD: [B,num_classes,128,128] fp32 NCHW (DAFormerHead output, before any resize) */
+  /* MADM_VARIANT_S0 (MADM_STAGE_DEC); out[0] then is s0 [B,128,512,512].  Both optional (NULL to skip), fp32 NCHW: the dict
+   * LdmDiffusers.forward returns under return_unet_final_output (ldm_diffusers.py:211-215) */
+  float* unet_sample;          /* [B,4,64,64]   'before_vae.decoder': unet_final_output.sample */
+  float* decoded;              /* [B,3,512,512] 'after_vae.decoder': clip(decoder_output, -1, 1) */
+  float* decoded_raw;          /* [B,3,512,512] decoder_output itself: the first entry of the feature list (ldm_diffusers.py:199) */
 } madm_extract_args;
 
 /* The whole path a-1..a-9 of SURVEY §8: VAE encode -> q-sample -> UNet forward with taps -> GN-bottleneck projections. */

@@ -15,6 +15,8 @@ LIB_PATH = os.environ.get("MADM_B200_LIB") or os.path.join(_HERE, "libmadm_b200.
 MADM_OK = 0
 STAGE_VAE, STAGE_UNET, STAGE_PROJ, STAGE_ALL = 1, 2, 4, 7
 STAGE_HEAD = 8
+STAGE_DEC, STAGE_ALL_S0 = 16, 23
+VARIANT_BASE, VARIANT_S0 = 0, 1
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU = 0, 1, 2, 3
 DTYPE_BF16, DTYPE_FP16 = 0, 1
 
@@ -35,6 +37,7 @@ class MadmExtractArgs(C.Structure):
         ("latents", c_void_p), ("noisy_latents", c_void_p), ("taps", c_void_p * 4),
         ("packed", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("range_flag", c_void_p), ("logits", c_void_p),
+        ("unet_sample", c_void_p), ("decoded", c_void_p), ("decoded_raw", c_void_p),
     ]
 
 
@@ -69,6 +72,8 @@ SYMBOLS = {
     "madm_destroy": (c_int, [c_void_p]),
     "madm_set_compute_dtype": (c_int, [c_void_p, c_int32]),
     "madm_get_compute_dtype": (c_int, [c_void_p]),
+    "madm_set_variant": (c_int, [c_void_p, c_int32]),
+    "madm_get_variant": (c_int, [c_void_p]),
     "madm_set_tensors": (c_int, [c_void_p, C.POINTER(MadmTensor), c_int32]),
     "madm_packed_bytes": (c_size_t, [c_void_p]),
     "madm_pack_weights": (c_int, [c_void_p, c_void_p, c_char_p, c_float, c_int32, c_void_p]),

@@ -112,10 +112,16 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
         self.target_attention_loss = target_attention_loss
         self.attention_select_index = attention_select_index
         self.crop_batch = crop_batch
-        if list(out_features) != ["s2", "s3", "s4", "s5"] or self.feature_dims != [512, 320, 640, 1280] or \
-                list(projection_dim) != [512] * 4 or bottleneck_channels != 128:
-            raise NotImplementedError("madm_b200 implements the shipped projection config: out_features s2..s5, "
-                                      "feature_dims [512,320,640,1280], projection_dim [512]*4, bottleneck 128")
+        variant = getattr(feature_extractor.ldm_extractor, "variant", "base")
+        want = dict(base=(["s2", "s3", "s4", "s5"], [512, 320, 640, 1280], [512] * 4),
+                    s0=(["s0", "s3", "s4", "s5"], [3, 320, 640, 1280], [128, 512, 512, 512]))[variant]
+        if (list(out_features), self.feature_dims, list(projection_dim)) != want or bottleneck_channels != 128:
+            raise NotImplementedError(
+                "madm_b200 implements the shipped projection configs: out_features s2..s5 / feature_dims [512,320,640,1280] / "
+                "projection_dim [512]*4 (mtmadise_multi_lora.py:14-41), or with ldm_extractor.vae_decoder_loss=True out_features "
+                "s0,s3,s4,s5 / feature_dims [3,320,640,1280] / projection_dim [128,512,512,512] "
+                "(mtmadise_cityscapes_rgb_to_depth_11.py:47-55); bottleneck 128")
+        self.variant = variant
         device = feature_extractor.ldm_extractor.device
         self.feature_projections = nn.ModuleList(
             [make_projection(fd, projection_dim[i], bottleneck_channels, num_res_blocks, device) for i, fd in enumerate(self.feature_dims)])
@@ -148,7 +154,10 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
         if tuple(img.shape[-2:]) != (512, 512):
             raise ValueError(f"single_forward expects 512x512 after preprocessing, got {tuple(img.shape[-2:])}")
         res = self._extract(img, input_modal, ema_forward, timestep, **kwargs)
-        return {"output_features": dict(zip(self._out_features, res["features"]))}
+        feats = {"output_features": dict(zip(self._out_features, res["features"]))}
+        if "return_unet_final_output" in kwargs:  # :164-166
+            return feats, {"before_vae.decoder": res["unet_sample"], "after_vae.decoder": res["decoded"]}
+        return feats
 
     def forward_features(self, features, input_image_size=None, ema_forward=False):  # :367-396
         """Projection stage on taps produced by ``self.feature_extractor(...)`` (the reference's two-step use)."""
@@ -165,6 +174,8 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
         return {"output_features": dict(zip(self._out_features, res["features"]))}
 
     def slide_forward(self, img, input_modal="rgb", ema_forward=False, timestep=None, **kwargs):  # :199-278
+        if "return_unet_final_output" in kwargs:
+            raise NotImplementedError("return_unet_final_output with slide inference (the reference's slide_forward drops it too)")
         b, _, h_img, w_img = img.shape
         wins = self.slide_windows(h_img, w_img)
         from . import ops

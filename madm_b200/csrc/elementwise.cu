@@ -202,6 +202,86 @@ const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void*
   return cudaGetLastError() == cudaSuccess ? nullptr : "upsample_nearest2x launch failed";
 }
 
+// ------------------------------------------------------------------ nearest 2x upsample of a 16-bit tensor (8 channels per thread)
+__global__ void upsample2x_16_kernel(const uint4* __restrict__ x, int B, int H, int W, int C8, uint4* __restrict__ out) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = long(B) * H * W * C8;
+  if (i >= total) return;
+  const int c = int(i % C8);
+  const long pix = i / C8;
+  const int xx = int(pix % W);
+  const int yy = int((pix / W) % H);
+  const int b = int(pix / (long(W) * H));
+  const uint4 v = __ldg(x + i);
+  const int W2 = W * 2;
+  const size_t row0 = ((size_t(b) * H * 2 + yy * 2) * W2 + xx * 2) * C8 + c;
+  out[row0] = v;
+  out[row0 + C8] = v;
+  out[row0 + size_t(W2) * C8] = v;
+  out[row0 + size_t(W2) * C8 + C8] = v;
+}
+
+const char* upsample_nearest2x_16(const void* x16, int B, int H, int W, int C, void* out16, cudaStream_t st) {
+  if (C % 8) return "upsample_nearest2x_16: C % 8 != 0";
+  const long total = long(B) * H * W * (C / 8);
+  upsample2x_16_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x16), B, H, W, C / 8,
+                                                                      reinterpret_cast<uint4*>(out16));
+  return cudaGetLastError() == cudaSuccess ? nullptr : "upsample_nearest2x_16 launch failed";
+}
+
+// ------------------------------------------------------------------ VAE decoder entry / exit
+__global__ void post_quant_conv_kernel(const float4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float inv_scale,
+                                       long M, float4* __restrict__ z) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float4 v = __ldg(x + i);
+  v.x *= inv_scale; v.y *= inv_scale; v.z *= inv_scale; v.w *= inv_scale;
+  float o[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) o[n] = __ldg(bias + n) + __ldg(w + n * 4) * v.x + __ldg(w + n * 4 + 1) * v.y + __ldg(w + n * 4 + 2) * v.z + __ldg(w + n * 4 + 3) * v.w;
+  z[i] = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+const char* post_quant_conv(const float* sample, const float* w, const float* bias, float inv_scale, long M, float* z, cudaStream_t st) {
+  post_quant_conv_kernel<<<unsigned((M + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(sample), w, bias, inv_scale, M,
+                                                                    reinterpret_cast<float4*>(z));
+  return cudaGetLastError() == cudaSuccess ? nullptr : "post_quant_conv launch failed";
+}
+
+// 8 threads per pixel: each writes one 16-byte piece of the pixel's 128-byte operand row (piece 0 carries the 3 channels)
+__global__ void decoder_image_pack_kernel(const float4* __restrict__ img4, int HW, long M, int fp16, uint4* __restrict__ rows, float* __restrict__ clipped,
+                                          float* __restrict__ raw) {
+  const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long pix = t >> 3;
+  const int piece = int(t & 7);
+  if (pix >= M) return;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (piece == 0) {
+    const float4 v = __ldg(img4 + pix);
+    const uint2 pk = pack4_16(v.x, v.y, v.z, 0.f, fp16);
+    o.x = pk.x; o.y = pk.y;
+    const long b = pix / HW, p = pix % HW;
+    if (clipped) {
+      float* dst = clipped + size_t(b) * 3 * HW + p;
+      dst[0] = fminf(fmaxf(v.x, -1.f), 1.f);
+      dst[HW] = fminf(fmaxf(v.y, -1.f), 1.f);
+      dst[2 * size_t(HW)] = fminf(fmaxf(v.z, -1.f), 1.f);
+    }
+    if (raw) {
+      float* dst = raw + size_t(b) * 3 * HW + p;
+      dst[0] = v.x; dst[HW] = v.y; dst[2 * size_t(HW)] = v.z;
+    }
+  }
+  rows[t] = o;
+}
+
+const char* decoder_image_pack(const float* img4, int B, int HW, void* rows16, float* clipped, float* raw, int fp16, cudaStream_t st) {
+  const long M = long(B) * HW;
+  decoder_image_pack_kernel<<<unsigned((M * 8 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(img4), HW, M, fp16,
+                                                                           reinterpret_cast<uint4*>(rows16), clipped, raw);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "decoder_image_pack launch failed";
+}
+
 // ------------------------------------------------------------------ split-K reduction + fused epilogue
 // out = act( sum_s partial[s] (fixed order) + bias + rowbias[img] + residual ) -> fp32 and/or 16-bit; one float4 per thread
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long split_stride, int M, int N, const float* __restrict__ bias,

@@ -98,6 +98,7 @@ struct Plan {
 struct madm_ctx {
   int device = 0;
   int fp16 = 1;  // compute dtype of GEMM operands (MADM_DTYPE_FP16 default)
+  int variant = MADM_VARIANT_BASE;
   std::string err;
   std::unordered_map<std::string, ParamRef> params;
   std::vector<PackEntry> pack;
@@ -758,15 +759,22 @@ struct Model {
     return out;
   }
 
-  Act upsample(const std::string& p, const Act& x) {
+  // Upsample2D: nearest 2x (materialised as a 16-bit operand) + conv3x3.  A 16-bit-only input (x.f empty: the VAE decoder's
+  // high-resolution stream) is replicated as is; out16_only keeps the result on the 16-bit stream.
+  Act upsample(const std::string& p, const Act& x, bool out16_only = false) {
     const int Bn = x.B, H = x.H, W = x.W, C = x.C;
+    const bool in16 = x.f.bytes == 0 && x.h.bytes != 0;
     B16T up = b.b16(size_t(x.M()) * 4 * C);
-    { const float* src = x.f.p; bf16* dst = up.p;
+    { const float* src = x.f.p; const bf16* src16 = x.h.p; bf16* dst = up.p;
       const int h16 = f16();
-      b.emit([=](cudaStream_t st) { return upsample_nearest2x(src, Bn, H, W, C, dst, h16, st); }); }
-    Act out = b.act(Bn, 2 * H, 2 * W, C, true, false);
+      if (in16) b.emit([=](cudaStream_t st) { return upsample_nearest2x_16(src16, Bn, H, W, C, dst, st); }, false, MADM_KIND_ELEMENTWISE, 0.0,
+                       double(x.M()) * C * 10);
+      else b.emit([=](cudaStream_t st) { return upsample_nearest2x(src, Bn, H, W, C, dst, h16, st); }, false, MADM_KIND_ELEMENTWISE, 0.0,
+                  double(x.M()) * C * 12); }
+    Act out = b.act(Bn, 2 * H, 2 * W, C, !out16_only, out16_only);
     { GemmDesc d; d.seg[0] = Builder::seg_3x3(up.p, Bn, 2 * H, 2 * W, C); d.M = int(out.M()); d.N = C; d.Nw = C;
-      d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C); d.out_f32 = out.f.p; d.ldo32 = C;
+      d.w = b.pw(b.conv_w(p + ".conv", C, C, 9)); d.bias = P(p + ".conv.bias", C);
+      if (out16_only) { d.out_bf16 = out.h.p; d.ldo16 = C; } else { d.out_f32 = out.f.p; d.ldo32 = C; }
       b.attach_colstats(out, d); b.gemm(d); }
     b.free(up);
     return out;
@@ -779,10 +787,10 @@ struct Model {
     B16T n = b.b16(size_t(M) * C);
     b.groupnorm(x, nullptr, p + ".group_norm", 1e-6f, ACT_NONE, n.p, nullptr);
     B16T qk = b.b16(size_t(M) * 2 * C);
-    { const size_t reg = b.region("vae_qk", size_t(2) * C * C * 2);
+    { const size_t reg = b.region("vae_qk:" + p, size_t(2) * C * C * 2);
       b.linear_part(p + ".to_q", reg, 0, C, C, false);
       b.linear_part(p + ".to_k", reg, C, C, C, false);
-      const size_t breg = b.region("vae_qk_bias", size_t(2) * C * 4);
+      const size_t breg = b.region("vae_qk_bias:" + p, size_t(2) * C * 4);
       b.f32_part(p + ".to_q.bias", breg, 0, C);
       b.f32_part(p + ".to_k.bias", breg, C, C);
       GemmDesc d; d.seg[0] = Builder::seg_plain(n.p, M, C); d.M = int(M); d.N = 2 * C; d.Nw = 2 * C; d.w = b.pw(reg); d.bias = b.pf(breg);
@@ -816,7 +824,9 @@ struct Model {
   }
 
   // persistent cross-stage buffers
-  Act enc_tap;           // [B,128,128,512] fp32 + bf16
+  bool s0() const { return b.ctx->variant == MADM_VARIANT_S0; }
+  Act enc_tap;           // [B,128,128,512] fp32 + bf16; MADM_VARIANT_S0: the decoded image, C = 3, `h` = zero-padded rows [B*512*512, 64]
+  F32T unet_sample;      // MADM_VARIANT_S0: [B*4096, 4] UNet final output (NHWC)
   F32T latents;          // [B*4096, 4]
   Act unet_tap[3];       // 64x64x320, 32x32x640, 16x16x1280 (fp32 + bf16)
 
@@ -856,7 +866,7 @@ struct Model {
       for (int j = 0; j < 2; ++j) {
         const std::string p = e + "down_blocks." + std::to_string(i) + ".resnets." + std::to_string(j);
         ++index;
-        const bool is_tap = index == 5;  // encoder_block_indices=[5] (counter increments before the check, :289-293)
+        const bool is_tap = index == 5 && !s0();  // encoder_block_indices=[5] (counter increments before the check, :289-293); [] in the s0 variant
         const bool feeds_down = (j == 1 && i < 3);  // its output is the input of this stage's stride-2 conv
         const bool o16 = s16 && i < 2;  // this block's output stays on the 16-bit stream
         Act y = resblock(p, x, nullptr, ch[i], 1e-6f, false, is_tap, feeds_down && !is_tap, o16);
@@ -1013,6 +1023,86 @@ struct Model {
     b.free(kv_all);
   }
 
+  // =========================================================================== UNet tail + VAE decoder (MADM_VARIANT_S0)
+  // unet.conv_norm_out / conv_act / conv_out (reference ldm_diffusers.py:608-611) -> sample [B,4,64,64] ('before_vae.decoder'), then
+  // vae_decoder(latents=sample, output_final=True) (ldm_diffusers.py:192, :314-346): 1/0.18215 scale, post_quant_conv, conv_in,
+  // mid block, 4 up blocks x 3 ResBlocks (512, 512, 256, 128 channels) with nearest-2x + conv between, GN + SiLU + conv 128 -> 3.
+  // The decoded image (not clipped, ldm_diffusers.py:199) becomes the first feature of forward_features.
+  void build_dec() {
+    b.cur_stage = MADM_STAGE_DEC;
+    const int Bn = b.B;
+    std::shared_ptr<IoBind> io = dry() ? nullptr : b.plan->io;
+    const int h16 = f16();
+    {
+      const Act& x = unet_tap[0];  // output of up layer 11 (64x64x320), the UNet's last hidden state
+      B16T n = b.b16(size_t(x.M()) * 320);
+      b.groupnorm(x, nullptr, kUnet + "conv_norm_out", 1e-5f, ACT_SILU, n.p, nullptr);
+      unet_sample = b.f32(size_t(x.M()) * 4);
+      GemmDesc d; d.seg[0] = Builder::seg_3x3(n.p, Bn, 64, 64, 320); d.M = int(x.M()); d.N = 4; d.Nw = 4; d.bn = 16;
+      d.w = b.pw(b.conv_w(kUnet + "conv_out", 4, 320, 9)); d.bias = P(kUnet + "conv_out.bias", 4); d.out_f32 = unet_sample.p; d.ldo32 = 4;
+      b.gemm(d);
+      b.free(n);
+      if (dry()) b.emit(nullptr, true);
+      else { const float* src = unet_sample.p;
+        b.emit([=](cudaStream_t st) -> const char* {
+          return io->a.unet_sample ? nhwc_to_nchw(src, Bn, 64 * 64, 4, io->a.unet_sample, st) : nullptr; }, true); }
+    }
+    const std::string dc = kVae + "decoder.";
+    const long M0 = long(Bn) * 4096;
+    F32T z = b.f32(size_t(M0) * 4);
+    { const float* src = unet_sample.p; float* dst = z.p;
+      const float* w = P(kVae + "post_quant_conv.weight", 16); const float* bi = P(kVae + "post_quant_conv.bias", 4);
+      b.emit([=](cudaStream_t st) { return post_quant_conv(src, w, bi, 1.0f / 0.18215f, M0, dst, st); }); }
+    b.free(unet_sample);
+    B16T col = b.b16(size_t(M0) * 64);
+    { const float* src = z.p; bf16* dst = col.p;
+      b.emit([=](cudaStream_t st) { return latent_im2col(src, Bn, 64, 64, dst, h16, st); }); }
+    Act x = b.act(Bn, 64, 64, 512, true, false);
+    { GemmDesc d; d.seg[0] = Builder::seg_plain(col.p, M0, 64); d.M = int(M0); d.N = 512; d.Nw = 512;
+      d.w = b.pw(b.conv_w(dc + "conv_in", 512, 4, 9, /*Cpad=*/4)); d.bias = P(dc + "conv_in.bias", 512); d.out_f32 = x.f.p; d.ldo32 = 512;
+      b.attach_colstats(x, d);
+      b.gemm(d, 2.0 * double(d.M) * 512 * 36 + 2.0 * double(d.M) * 16); }  // + post_quant_conv
+    b.free(col); b.free(z);
+    {
+      Act y = resblock(dc + "mid_block.resnets.0", x, nullptr, 512, 1e-6f, false, false); b.free(x); x = y;
+      y = vae_attention(dc + "mid_block.attentions.0", x); b.free(x); x = y;
+      y = resblock(dc + "mid_block.resnets.1", x, nullptr, 512, 1e-6f, false, false); b.free(x); x = y;
+    }
+    // fp16 operands: the 256^2 and 512^2 stages keep their residual stream in fp16, like the encoder's (and the reference's fp16 VAE)
+    const bool s16 = f16() && !getenv("MADM_VAE_STREAM32");
+    const int ch[4] = {512, 512, 256, 128};
+    for (int i = 0; i < 4; ++i) {
+      const bool o16 = s16 && i >= 2;
+      for (int j = 0; j < 3; ++j) {
+        Act y = resblock(dc + "up_blocks." + std::to_string(i) + ".resnets." + std::to_string(j), x, nullptr, ch[i], 1e-6f, false, false, false, o16);
+        b.free(x);
+        x = y;
+      }
+      if (i < 3) {
+        Act y = upsample(dc + "up_blocks." + std::to_string(i) + ".upsamplers.0", x, /*out16_only=*/s16 && i + 1 >= 2);
+        b.free(x);
+        x = y;
+      }
+    }
+    const long M = x.M();
+    B16T n = b.b16(size_t(M) * 128);
+    b.groupnorm(x, nullptr, dc + "conv_norm_out", 1e-6f, ACT_SILU, n.p, nullptr, /*in16=*/x.f.bytes == 0);
+    b.free(x);
+    F32T img = b.f32(size_t(M) * 4);
+    { GemmDesc d; d.seg[0] = Builder::seg_3x3(n.p, Bn, 512, 512, 128); d.M = int(M); d.N = 3; d.Nw = 3; d.bn = 16;
+      d.w = b.pw(b.conv_w(dc + "conv_out", 3, 128, 9)); d.bias = P(dc + "conv_out.bias", 3); d.out_f32 = img.p; d.ldo32 = 4;
+      b.gemm(d); }
+    b.free(n);
+    enc_tap = Act(); enc_tap.B = Bn; enc_tap.H = 512; enc_tap.W = 512; enc_tap.C = 3;
+    enc_tap.h = b.b16(size_t(M) * 64);
+    if (dry()) b.emit(nullptr);
+    else { const float* src = img.p; bf16* dst = enc_tap.h.p;
+      b.emit([=](cudaStream_t st) { return decoder_image_pack(src, Bn, 512 * 512, dst, io->a.decoded, io->a.decoded_raw, h16, st); }, false, MADM_KIND_ELEMENTWISE,
+             0.0, double(M) * (16 + 128)); }
+    b.free(img);
+    b.pin(enc_tap);
+  }
+
   static const char* nchw_to_nhwc4(const float* src, int Bn, int HW, float* dst, cudaStream_t st);
 
   // =========================================================================== feature projections
@@ -1024,13 +1114,19 @@ struct Model {
     for (int i = 0; i < 4; ++i) {
       const Act& x = *taps[i];
       const std::string p = root + std::to_string(i) + ".0.";
-      const int Bn = x.B, H = x.H, W = x.W, Cin = x.C, Cb = 128, Cout = 512;
+      const ParamRef* w1 = b.find(p + "conv1.weight"); const ParamRef* w3 = b.find(p + "conv3.weight");
+      if (!w1 || !w3) b.fail(MADM_ENOTFOUND, "parameter not registered: " + p + "conv1.weight / conv3.weight");
+      const int Bn = x.B, H = x.H, W = x.W, Cin = x.C, Cb = int(w1->shape[0]), Cout = int(w3->shape[0]);
+      if (int(w1->shape[1]) != Cin || Cb % 64 != 0 || Cout % 64 != 0) b.fail(MADM_EINVAL, "feature projection " + std::to_string(i) + ": unsupported channels");
+      // a narrow input (the 3-channel decoded image of the s0 variant) is a zero-padded 64-wide operand row; weights padded alike
+      const int Cop = Cin < 64 ? 64 : Cin, Cpad = Cin < 64 ? Cin : 0;
       const long M = x.M();
       const bool shortcut = Cin != Cout;
       // every GroupNorm of the bottleneck takes its statistics from the producing GEMM's epilogue
       Act c1 = b.act(Bn, H, W, Cb, false, true);
-      { GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cin); d.M = int(M); d.N = Cb; d.Nw = Cb;
-        d.w = b.pw(b.conv_w(p + "conv1", Cb, Cin, 1)); d.out_bf16 = c1.h.p; d.ldo16 = Cb; b.attach_colstats(c1, d); b.gemm(d); }
+      { GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cop); d.M = int(M); d.N = Cb; d.Nw = Cb;
+        d.w = b.pw(b.conv_w(p + "conv1", Cb, Cin, 1, Cpad)); d.out_bf16 = c1.h.p; d.ldo16 = Cb; b.attach_colstats(c1, d);
+        b.gemm(d, 2.0 * double(M) * Cb * Cin); }
       B16T a1 = b.b16(size_t(M) * Cb);
       b.groupnorm(c1, nullptr, p + "conv1.norm", 1e-5f, ACT_RELU, a1.p, nullptr, /*in16=*/true);
       b.free(c1);
@@ -1048,8 +1144,9 @@ struct Model {
       Act sc;
       if (shortcut) {
         sc = b.act(Bn, H, W, Cout, true, false);
-        GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cin); d.M = int(M); d.N = Cout; d.Nw = Cout;
-        d.w = b.pw(b.conv_w(p + "shortcut", Cout, Cin, 1)); d.out_f32 = sc.f.p; d.ldo32 = Cout; b.attach_colstats(sc, d); b.gemm(d);
+        GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cop); d.M = int(M); d.N = Cout; d.Nw = Cout;
+        d.w = b.pw(b.conv_w(p + "shortcut", Cout, Cin, 1, Cpad)); d.out_f32 = sc.f.p; d.ldo32 = Cout; b.attach_colstats(sc, d);
+        b.gemm(d, 2.0 * double(M) * Cout * Cin);
       }
       const int HW = H * W;
       float* st3 = b.new_stats(1);
@@ -1192,6 +1289,7 @@ struct Model {
       enumerate_unet();
       build_vae();
       build_unet();
+      if (s0()) build_dec();
       build_proj();
     }
     if (has_head()) build_head();
@@ -1254,6 +1352,7 @@ int ensure_layout(madm_ctx* ctx) {
       m.enumerate_unet();
       // projections need tap shapes only
       m.enc_tap.B = 1; m.enc_tap.H = 128; m.enc_tap.W = 128; m.enc_tap.C = 512;
+      if (m.s0()) { m.enc_tap.H = 512; m.enc_tap.W = 512; m.enc_tap.C = 3; }
       const int hw[3] = {64, 32, 16}, cc[3] = {320, 640, 1280};
       for (int i = 0; i < 3; ++i) { m.unet_tap[i].B = 1; m.unet_tap[i].H = hw[i]; m.unet_tap[i].W = hw[i]; m.unet_tap[i].C = cc[i]; }
       m.build_proj();
@@ -1328,6 +1427,20 @@ int madm_set_compute_dtype(madm_ctx* ctx, int32_t dtype) {
 }
 
 int madm_get_compute_dtype(const madm_ctx* ctx) { return ctx && !ctx->fp16 ? MADM_DTYPE_BF16 : MADM_DTYPE_FP16; }
+
+int madm_set_variant(madm_ctx* ctx, int32_t variant) {
+  if (!ctx || (variant != MADM_VARIANT_BASE && variant != MADM_VARIANT_S0)) return set_err(ctx, MADM_EINVAL, "madm_set_variant: bad argument");
+  if (variant != ctx->variant) {
+    ctx->variant = variant;
+    ctx->plans.clear();
+    ctx->last_plan = nullptr;
+    ctx->layout_done = false;
+    ctx->ws_bytes_cache.clear();
+  }
+  return MADM_OK;
+}
+
+int madm_get_variant(const madm_ctx* ctx) { return ctx ? ctx->variant : MADM_VARIANT_BASE; }
 
 int madm_set_tensors(madm_ctx* ctx, const madm_tensor* named, int32_t n) {
   if (!ctx || (!named && n > 0)) return set_err(ctx, MADM_EINVAL, "madm_set_tensors: null argument");

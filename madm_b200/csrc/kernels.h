@@ -68,6 +68,15 @@ const char* f32_to_bf16(const float* x, const float* add_or_null, long n, int ac
 const char* space_to_depth(const float* x, int B, int H, int W, int C, void* out_bf16, int fp16, cudaStream_t st);
 // fp32 NHWC [B,H,W,C] -> nearest 2x bf16 [B,2H,2W,C]
 const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void* out_bf16, int fp16, cudaStream_t st);
+// 16-bit NHWC [B,H,W,C] -> nearest 2x 16-bit [B,2H,2W,C] (the VAE decoder's 16-bit stream)
+const char* upsample_nearest2x_16(const void* x16, int B, int H, int W, int C, void* out16, cudaStream_t st);
+// VAE decoder entry: z = post_quant_conv(sample * inv_scale), a 1x1 conv 4 -> 4 in fp32 (ldm_diffusers.py:319-320); NHWC [M,4]
+const char* post_quant_conv(const float* sample, const float* w /*[4,4]*/, const float* bias /*[4]*/, float inv_scale, long M, float* z,
+                            cudaStream_t st);
+// decoder image fp32 NHWC [B*HW, 4] (3 real channels) -> 16-bit operand rows [B*HW, 64] (zero padded) for the s0 projection's 1x1
+// convs, and optionally clip(x, -1, 1) ('after_vae.decoder') and x itself as fp32 NCHW [B,3,HW]
+const char* decoder_image_pack(const float* img4, int B, int HW, void* rows16, float* clipped_nchw_or_null, float* raw_nchw_or_null, int fp16,
+                               cudaStream_t st);
 // split-K: out = act(sum_s partial[s] + bias + rowbias + residual), partial[s] = part + s*split_stride, each [M,N] fp32
 const char* splitk_reduce(const float* part, int splits, long split_stride, int M, int N, const float* bias, const float* rowbias,
                           int rows_per_img, int ld_rowbias, const float* residual, int ldr, float* out32, int ldo32, void* out16, int ldo16,

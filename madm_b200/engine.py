@@ -8,14 +8,16 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import MadmExtractArgs, MadmTensor, STAGE_ALL, STAGE_HEAD, STAGE_PROJ, STAGE_UNET, STAGE_VAE
+from ._lib import MadmExtractArgs, MadmTensor, STAGE_ALL, STAGE_ALL_S0, STAGE_DEC, STAGE_HEAD, STAGE_PROJ, STAGE_UNET, STAGE_VAE
 
 TAP_SHAPES = ((512, 128), (320, 64), (640, 32), (1280, 16))  # enc tap, unet taps (C, HW side)
 OUT_SIDES = (128, 64, 32, 16)                                  # s2..s5
+# variant -> per-output (C, side) and the first "tap" (base: encoder tap; s0: the decoded image)
+OUT_SHAPES = {"base": ((512, 128), (512, 64), (512, 32), (512, 16)), "s0": ((128, 512), (512, 64), (512, 32), (512, 16))}
 
 
 class Engine:
-    def __init__(self, device: torch.device, compute_dtype: str = "fp16"):
+    def __init__(self, device: torch.device, compute_dtype: str = "fp16", variant: str = "base"):
         if device.type != "cuda":
             raise _lib.MadmError("madm_b200 runs on sm_100a CUDA devices only (no CPU fallback)")
         self.lib = _lib.load()
@@ -29,6 +31,11 @@ class Engine:
         self.compute_dtype = compute_dtype
         _lib.check(self.lib.madm_set_compute_dtype(self.ctx, _lib.DTYPE_FP16 if compute_dtype == "fp16" else _lib.DTYPE_BF16),
                    self.ctx, "madm_set_compute_dtype")
+        if variant not in OUT_SHAPES:
+            raise _lib.MadmError(f"variant must be 'base' or 's0', got {variant!r}")
+        self.variant = variant
+        _lib.check(self.lib.madm_set_variant(self.ctx, _lib.VARIANT_S0 if variant == "s0" else _lib.VARIANT_BASE), self.ctx, "madm_set_variant")
+        self.stage_all = STAGE_ALL_S0 if variant == "s0" else STAGE_ALL
         self._named: List[Tuple[str, torch.Tensor]] = []
         self._sig = None
         self._versions = None
@@ -107,17 +114,17 @@ class Engine:
         return self._ws
 
     def extract_graphed(self, img, cond_inputs, cond_emb, timesteps, shared_noise, *, ema=False, stages=STAGE_ALL, want_taps=False,
-                        want_latents=False):
+                        want_latents=False, want_final=False):
         """`extract` through a captured CUDA graph (static input / output buffers, one graph per call signature)."""
         B = img.shape[0]
-        key = (B, bool(ema), stages, bool(want_taps), bool(want_latents), self._packed.data_ptr(), shared_noise.data_ptr())
+        key = (B, bool(ema), stages, bool(want_taps), bool(want_latents), bool(want_final), self._packed.data_ptr(), shared_noise.data_ptr())
         g = self._graphs.get(key)
         if g is None:
             st = dict(img=torch.empty_like(img, dtype=torch.float32), cond_inputs=torch.empty(B, 77, 768, device=self.device),
                       cond_emb=torch.empty(B, 1280, device=self.device), timesteps=torch.zeros(B, dtype=torch.int64, device=self.device))
             for k, v in (("img", img), ("cond_inputs", cond_inputs), ("cond_emb", cond_emb), ("timesteps", timesteps)):
                 st[k].copy_(v)
-            kw = dict(ema=ema, stages=stages, want_taps=want_taps, want_latents=want_latents)
+            kw = dict(ema=ema, stages=stages, want_taps=want_taps, want_latents=want_latents, want_final=want_final)
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):  # warm-up outside capture: plan build, cudaFuncSetAttribute, allocations
@@ -170,7 +177,7 @@ class Engine:
     def extract(self, img: Optional[torch.Tensor], cond_inputs: torch.Tensor, cond_emb: torch.Tensor, timesteps: torch.Tensor,
                 shared_noise: torch.Tensor, *, ema: bool = False, stages: int = STAGE_ALL, want_taps: bool = False,
                 want_latents: bool = False, noisy_latents_in: Optional[torch.Tensor] = None, B: Optional[int] = None,
-                out: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, object]:
+                out: Optional[Sequence[torch.Tensor]] = None, want_final: bool = False) -> Dict[str, object]:
         if self._packed is None:
             raise _lib.MadmError("Engine.extract called before ensure_packed()")
         B = B if B is not None else (img.shape[0] if img is not None else noisy_latents_in.shape[0])
@@ -202,20 +209,32 @@ class Engine:
         res: Dict[str, object] = {}
         outs = []
         if stages & STAGE_PROJ:
-            for i, side in enumerate(OUT_SIDES):
-                t = out[i] if out is not None else torch.empty(B, 512, side, side, dtype=torch.float32, device=dev)
+            for i, (ch, side) in enumerate(OUT_SHAPES[self.variant]):
+                t = out[i] if out is not None else torch.empty(B, ch, side, side, dtype=torch.float32, device=dev)
+                if tuple(t.shape) != (B, ch, side, side) or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _lib.MadmError(f"out[{i}] must be a contiguous fp32 [{B},{ch},{side},{side}] tensor")
                 outs.append(t)
                 a.out[i] = t.data_ptr()
             res["features"] = outs
         if want_taps:
-            taps = [torch.empty(B, c, s, s, dtype=torch.float32, device=dev) for c, s in TAP_SHAPES]
+            shapes = TAP_SHAPES if self.variant == "base" else ((3, 512),) + TAP_SHAPES[1:]
+            taps = [torch.empty(B, c, s, s, dtype=torch.float32, device=dev) for c, s in shapes]
             for i, t in enumerate(taps):
                 a.taps[i] = t.data_ptr()
+            if self.variant == "s0":  # first feature = decoder_output (ldm_diffusers.py:199), written by the decoder stage
+                a.taps[0] = None
+                a.decoded_raw = taps[0].data_ptr()
             res["taps"] = taps
         if want_latents:
             res["latents"] = torch.empty(B, 4, 64, 64, dtype=torch.float32, device=dev)
             res["noisy_latents"] = torch.empty(B, 4, 64, 64, dtype=torch.float32, device=dev)
             a.latents, a.noisy_latents = res["latents"].data_ptr(), res["noisy_latents"].data_ptr()
+        if want_final:  # return_unet_final_output (ldm_diffusers.py:211-215)
+            if self.variant != "s0" or not (stages & STAGE_DEC):
+                raise _lib.MadmError("want_final needs the s0 variant and MADM_STAGE_DEC")
+            res["unet_sample"] = torch.empty(B, 4, 64, 64, dtype=torch.float32, device=dev)
+            res["decoded"] = torch.empty(B, 3, 512, 512, dtype=torch.float32, device=dev)
+            a.unet_sample, a.decoded = res["unet_sample"].data_ptr(), res["decoded"].data_ptr()
         a.packed = self._packed.data_ptr()
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         a.range_flag = self.range_flag.data_ptr()

@@ -76,18 +76,24 @@ class LdmDiffusers(nn.Module):
         self.final_fuse_vae_decoder_feat = final_fuse_vae_decoder_feat
         # rows of SURVEY §8 that are "next" / out of scope fail loudly instead of silently computing something else
         unsupported = []
-        if self.encoder_block_indices != [5]: unsupported.append("encoder_block_indices != [5]")
+        # two supported configurations: the base one (encoder tap -> s2) and the shipped experiments' s0 variant
+        # (vae_decoder_loss=True, encoder_block_indices=[]: decoded image -> s0)
+        self.variant = "s0" if vae_decoder_loss else "base"
+        if self.encoder_block_indices != ([] if vae_decoder_loss else [5]):
+            unsupported.append("encoder_block_indices must be [5] (base) or [] with vae_decoder_loss=True (ldm_diffusers.py:198)")
         if self.unet_block_indices != [5, 8, 11] or unet_block_indices_type != "after": unsupported.append("unet taps != [5,8,11]/'after'")
         if self.decoder_block_indices: unsupported.append("decoder_block_indices")
         if input_range != "-1+1": unsupported.append("input_range='01'")
         if concat_pixel_shuffle or input_channel_plus or norm_latent_noise or add_latent_noise != -1:
             unsupported.append("concat_pixel_shuffle / input_channel_plus / latent-noise variants")
-        if vae_decoder_loss or final_fuse_vae_decoder_feat: unsupported.append("vae_decoder_loss / s0 variant (SURVEY §8 f-1)")
+        if final_fuse_vae_decoder_feat: unsupported.append("final_fuse_vae_decoder_feat")
         if unsupported:
             raise NotImplementedError("madm_b200 implements the base hot-path configuration "
-                                      "(config_files/common/models/mtmadise_multi_lora.py:14-41); unsupported: " + ", ".join(unsupported))
+                                      "(config_files/common/models/mtmadise_multi_lora.py:14-41) and its vae_decoder_loss / s0 variant "
+                                      "(config_files/SemSeg/MTMADISE/mtmadise_cityscapes_rgb_to_depth_11.py:47-55); unsupported: "
+                                      + ", ".join(unsupported))
         device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.vae = VAEParams(device=device)
+        self.vae = VAEParams(device=device, with_decoder=bool(vae_decoder_loss))
         self.unet = UNetParams(device=device)
         loaded = False
         if self.stable_diffusion_name_or_path and os.path.isdir(self.stable_diffusion_name_or_path):
@@ -138,7 +144,7 @@ class LdmDiffusers(nn.Module):
     # ---------------------------------------------------------------------------- engine plumbing
     def engine(self) -> Engine:
         if self._engine is None:
-            self._engine = Engine(self.device, self.compute_dtype)
+            self._engine = Engine(self.device, self.compute_dtype, self.variant)
         return self._engine
 
     def named_engine_tensors(self) -> List[Tuple[str, torch.Tensor]]:
@@ -163,8 +169,11 @@ class LdmDiffusers(nn.Module):
             timesteps: Optional[torch.Tensor] = None, out=None, **kwargs):
         if kwargs.get("ema_forward") and hasattr(self, "ema_unet"):
             raise NotImplementedError("ema_unet (ema_w_unet) is not part of the base hot path")
-        if "modality_mask" in kwargs or kwargs.get("return_unet_final_output"):
-            raise NotImplementedError("modality_mask / return_unet_final_output belong to the s0 / vae_decoder variant (SURVEY §8 f-1)")
+        if "modality_mask" in kwargs:
+            raise NotImplementedError("modality_mask needs input_channel_plus != 0, which is outside the shipped configs")
+        want_final = bool(kwargs.get("return_unet_final_output"))
+        if want_final and self.variant != "s0":
+            raise NotImplementedError("return_unet_final_output needs vae_decoder_loss=True (the reference raises on decoder_output too)")
         images = batched_inputs["img"]
         bsz = images.shape[0]
         eng = self.prepare(extra)
@@ -179,19 +188,23 @@ class LdmDiffusers(nn.Module):
         if cond_emb.shape[0] == 1 and bsz > 1:
             cond_emb = cond_emb.expand(bsz, -1)
         self._serial += 1
-        if out is None and 0 < bsz <= eng.graph_max_batch and stages == _lib.STAGE_ALL and tuple(images.shape[1:]) == (3, 512, 512):
+        if self.variant == "s0" and (stages & _lib.STAGE_UNET):  # the decoded image is the first feature: the decoder stage belongs to the UNet's
+            stages |= _lib.STAGE_DEC
+        if out is None and 0 < bsz <= eng.graph_max_batch and stages == eng.stage_all and tuple(images.shape[1:]) == (3, 512, 512):
             return eng.extract_graphed(images.float(), cond_inputs, cond_emb, timesteps, self.shared_noise, ema=ema_projections,
-                                       stages=stages, want_taps=want_taps, want_latents=want_latents)
+                                       stages=stages, want_taps=want_taps, want_latents=want_latents, want_final=want_final)
         return eng.extract(images, cond_inputs, cond_emb, timesteps, self.shared_noise, ema=ema_projections, stages=stages,
-                           want_taps=want_taps, want_latents=want_latents, out=out)
+                           want_taps=want_taps, want_latents=want_latents, out=out, want_final=want_final)
 
     def forward(self, batched_inputs, input_modal, **kwargs):
         """Reference semantics: returns ``[enc_tap, unet_tap16, unet_tap32, unet_tap64]`` as NCHW fp32 tensors
         (order of ldm_diffusers.py:217: encoder features, then unet features in up-path order 16, 32, 64)."""
         res = self.run(batched_inputs, input_modal, stages=_lib.STAGE_VAE | _lib.STAGE_UNET, want_taps=True, **kwargs)
-        enc, t64, t32, t16 = res["taps"]
+        enc, t64, t32, t16 = res["taps"]  # s0 variant: `enc` is decoder_output (ldm_diffusers.py:199)
         taps = FeatureTaps([enc, t16, t32, t64])
         taps.token = (id(self), self._serial)
+        if kwargs.get("return_unet_final_output"):  # ldm_diffusers.py:211-215
+            return taps, {"before_vae.decoder": res["unet_sample"], "after_vae.decoder": res["decoded"]}
         return taps
 
 

@@ -99,6 +99,27 @@ def unet_spec(in_channels: int = 4, out_channels: int = 4, cross: int = 768) -> 
     return s
 
 
+def vae_decoder_spec() -> Spec:
+    """Decoder half of SD-1.4 ``vae/config.json`` (49,490,179 parameters): conv_in 4->512, mid block, four up blocks of three
+    ResBlocks with output channels (512, 512, 256, 128) and nearest-2x + conv between, GN + conv 128->3."""
+    s: Spec = [("decoder.conv_in.weight", (512, 4, 3, 3)), ("decoder.conv_in.bias", (512,))]
+    s += _res("decoder.mid_block.resnets.0", 512, 512, None)
+    a = "decoder.mid_block.attentions.0"
+    s += [(f"{a}.group_norm.weight", (512,)), (f"{a}.group_norm.bias", (512,))] + _attn(a, 512, 512, True)
+    s += _res("decoder.mid_block.resnets.1", 512, 512, None)
+    cout = 512
+    for i, c in enumerate((512, 512, 256, 128)):
+        cin, cout = cout, c
+        for j in range(3):
+            s += _res(f"decoder.up_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout, None)
+        if i < 3:
+            s += [(f"decoder.up_blocks.{i}.upsamplers.0.conv.weight", (cout, cout, 3, 3)),
+                  (f"decoder.up_blocks.{i}.upsamplers.0.conv.bias", (cout,))]
+    s += [("decoder.conv_norm_out.weight", (128,)), ("decoder.conv_norm_out.bias", (128,)),
+          ("decoder.conv_out.weight", (3, 128, 3, 3)), ("decoder.conv_out.bias", (3,))]
+    return s
+
+
 def vae_spec() -> Spec:
     """SD-1.4 ``vae/config.json`` encoder half + quant / post_quant convs."""
     bo = (128, 256, 512, 512)
@@ -277,9 +298,9 @@ class VAEParams(ParamNode):
     scaling_factor = 0.18215
     latent_channels = 4
 
-    def __init__(self, device=None, seed: Optional[int] = None):
+    def __init__(self, device=None, seed: Optional[int] = None, with_decoder: bool = False):
         super().__init__()
-        tree = build_tree(vae_spec(), device=device, seed=seed)
+        tree = build_tree(vae_spec() + (vae_decoder_spec() if with_decoder else []), device=device, seed=seed)
         for k, m in tree._modules.items():
             self.add_module(k, m)
 

@@ -137,6 +137,8 @@ class LdmDiffusers(nn.Module):
         self.final_fuse_vae_decoder_feat = final_fuse_vae_decoder_feat
         self.vae = sd14.AutoencoderKL()
         self.unet = sd14.UNet2DConditionModel()
+        if vae_decoder_loss or self.decoder_block_indices:  # built after the base modules: the base random-init stream is unchanged
+            self.vae.decoder = sd14.Decoder()
         self.register_buffer("alphas_cumprod", sd14.ddpm_alphas_cumprod(), persistent=False)
         rng = torch.Generator().manual_seed(42)                                       # :73-75
         self.register_buffer("shared_noise", torch.randn(1, 4, *self.latent_image_size, generator=rng))
@@ -161,11 +163,24 @@ class LdmDiffusers(nn.Module):
         forward_unet = self.unet
         if kwargs.get("ema_forward") and hasattr(self, "ema_unet"):                                  # :182-185
             forward_unet = self.ema_unet
-        _, unet_features = sd14.diffusion_unet(forward_unet, noisy, timesteps, text_prompt, res_time_embedding,
-                                               self.unet_block_indices, self.unet_block_indices_type,
-                                               need_sample=False)                                    # :186
+        sample, unet_features = sd14.diffusion_unet(forward_unet, noisy, timesteps, text_prompt, res_time_embedding,
+                                                    self.unet_block_indices, self.unet_block_indices_type,
+                                                    need_sample=self.vae_decoder_loss)               # :186
         self.last_intermediates = dict(latents=latents, noisy_latents=noisy, timesteps=timesteps)
-        return [*encoder_features, *unet_features]                                                   # :217
+        decoder_features = []
+        if self.vae_decoder_loss:                                                                    # :191-201
+            decoder_output, _ = sd14.vae_decoder(self.vae, sample, [], output_final=True)
+            if self.final_fuse_vae_decoder_feat:
+                decoder_features = [decoder_output.detach()]
+            else:
+                assert len(self.encoder_block_indices) == 0
+                encoder_features = [decoder_output.detach()]
+        elif self.decoder_block_indices:                                                             # :203-205
+            _, decoder_features = sd14.vae_decoder(self.vae, latents, self.decoder_block_indices)
+        feats = [*encoder_features, *unet_features, *decoder_features]
+        if kwargs.get("return_unet_final_output"):                                                   # :211-215
+            return feats, {"before_vae.decoder": sample, "after_vae.decoder": torch.clip(decoder_output, min=-1.0, max=1.0)}
+        return feats                                                                                 # :217
 
 
 class BasePromptTimeGenerator(nn.Module):
@@ -269,6 +284,8 @@ class AttentionFeatureExtractorBackbone(nn.Module):
         size = img.shape[-2:]
         img = self.preprocess_image(img)
         feats = self.feature_extractor(dict(img=img), input_modal, ema_forward, timestep, **kwargs)
+        if "return_unet_final_output" in kwargs:                                       # :164-166
+            return self.forward_features(feats[0], size, ema_forward), feats[1]
         return self.forward_features(feats, size, ema_forward)
 
     def slide_windows(self, h_img, w_img, crop=512, stride=256):

@@ -371,17 +371,47 @@ class Encoder(nn.Module):
         self.conv_out = nn.Conv2d(block_out[-1], 2 * latent, 3, padding=1)
 
 
+class _DecUpBlock(nn.Module):
+    """diffusers UpDecoderBlock2D: 3 ResnetBlock2D (layers_per_block + 1, no time embedding) + nearest-2x Upsample2D."""
+
+    def __init__(self, cin, cout, with_up):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, None, 1e-6) for i in range(3)])
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if with_up else None
+
+
+class Decoder(nn.Module):
+    """diffusers ``Decoder`` of SD-1.4 ``vae/config.json``: conv_in 4->512, mid block, four up blocks with output
+    channels (512, 512, 256, 128), GN32(eps 1e-6) + SiLU + conv 128->3."""
+
+    def __init__(self, out_channels=3, latent=4, block_out=(128, 256, 512, 512)):
+        super().__init__()
+        rev = block_out[::-1]
+        self.conv_in = nn.Conv2d(latent, rev[0], 3, padding=1)
+        self.mid_block = _VaeMidBlock(rev[0])
+        self.up_blocks = nn.ModuleList()
+        cout = rev[0]
+        for i, c in enumerate(rev):
+            cin, cout = cout, c
+            self.up_blocks.append(_DecUpBlock(cin, cout, with_up=i < len(rev) - 1))
+        self.conv_norm_out = nn.GroupNorm(32, block_out[0], eps=1e-6)
+        self.conv_out = nn.Conv2d(block_out[0], out_channels, 3, padding=1)
+
+
 class AutoencoderKL(nn.Module):
-    """Encoder half only (+quant_conv / post_quant_conv parameters); the decoder is the
-    'next' row f-1 of SURVEY §8 and is not part of the base hot path."""
+    """Encoder half (+quant_conv / post_quant_conv parameters) by default; ``with_decoder=True`` adds the decoder half
+    used by the ``vae_decoder_loss`` / ``s0`` variant.  The decoder is constructed last so the
+    random-init stream of the base configuration does not change."""
     scaling_factor = 0.18215
     latent_channels = 4
 
-    def __init__(self):
+    def __init__(self, with_decoder: bool = False):
         super().__init__()
         self.encoder = Encoder()
         self.quant_conv = nn.Conv2d(8, 8, 1)
         self.post_quant_conv = nn.Conv2d(4, 4, 1)
+        if with_decoder:
+            self.decoder = Decoder()
 
 
 @torch.no_grad()
@@ -406,6 +436,30 @@ def vae_encoder(vae: AutoencoderKL, images, encoder_block_indices: Sequence[int]
     latents = mean * vae.scaling_factor                                         # :308
     assert len(encoder_block_indices) == len(features)
     return latents, features
+
+
+@torch.no_grad()
+def vae_decoder(vae: AutoencoderKL, latents, decoder_block_indices: Sequence[int], output_final: bool = False):
+    """Restates reference ``modeling/meta_arch/ldm_diffusers.py:314-346``."""
+    index = 0
+    features = []
+    latents = 1.0 / vae.scaling_factor * latents                                # :319
+    sample = vae.post_quant_conv(latents)                                       # :320
+    sample = qr(vae.decoder.conv_in(q(sample)))                                 # :322
+    sample = vae.decoder.mid_block(sample)                                      # :325
+    for blk in vae.decoder.up_blocks:                                           # :328-336
+        for resnet in blk.resnets:
+            if index in decoder_block_indices:
+                features.append(sample)
+            index += 1
+            sample = resnet(sample)
+        if blk.upsamplers is not None:
+            sample = blk.upsamplers[0](sample)
+    if output_final:                                                            # :339-342
+        sample = vae.decoder.conv_out(q(F.silu(vae.decoder.conv_norm_out(sample))))
+    else:
+        sample = None
+    return sample, features
 
 
 # --------------------------------------------------------------------------------------

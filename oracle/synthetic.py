@@ -21,15 +21,21 @@ CONFIG = dict(  # reference config_files/common/models/mtmadise_multi_lora.py:14
     encoder_block_indices=[5], unet_block_indices=[5, 8, 11], unet_block_indices_type="after",
     decoder_block_indices=(), input_range="-1+1", out_features=["s2", "s3", "s4", "s5"],
 )
+# the variant all three shipped experiment files select (config_files/SemSeg/MTMADISE/mtmadise_cityscapes_rgb_to_depth_11.py:47-55):
+# UNet final output -> VAE decoder -> 3-channel 512^2 "feature" -> Bottleneck(3 -> 128 -> 128) -> 's0'   
+CONFIG_S0 = dict(CONFIG, feature_dims=[3, 320, 640, 1280], projection_dim=[128, 512, 512, 512], encoder_block_indices=[],
+                 out_features=["s0", "s3", "s4", "s5"], vae_decoder_loss=True)
 
 
 def build_backbone(lora_configs: Sequence[str] = ("default_r16_a16", "Depth_r16_a16"), seed: int = 1234,
-                   same_cond_params: bool = False, with_ema: bool = True) -> ob.AttentionFeatureExtractorBackbone:
+                   same_cond_params: bool = False, with_ema: bool = True, variant: str = "base") -> ob.AttentionFeatureExtractorBackbone:
+    CONFIG = globals()["CONFIG"] if variant == "base" else CONFIG_S0
     torch.manual_seed(seed)
     ldm = ob.LdmDiffusers(
         stable_diffusion_name_or_path=None, encoder_block_indices=CONFIG["encoder_block_indices"],
         unet_block_indices=CONFIG["unet_block_indices"], unet_block_indices_type=CONFIG["unet_block_indices_type"],
-        decoder_block_indices=CONFIG["decoder_block_indices"], input_range=CONFIG["input_range"], finetune_unet="all")
+        decoder_block_indices=CONFIG["decoder_block_indices"], input_range=CONFIG["input_range"], finetune_unet="all",
+        vae_decoder_loss=CONFIG.get("vae_decoder_loss", False))
     gen = ob.BasePromptTimeGenerator(learnable_cond_prompt=True, learnable_cond_time=True, clip_state="no",
                                      num_timesteps=1, clip_model_name="ViT-L-14-336", ldm_extractor=ldm,
                                      same_cond_params=same_cond_params)

@@ -6,7 +6,11 @@ The reference (XiaRho/MADM) cannot be imported here (diffusers / peft / detectro
 the oracle restatement, not of the reference: PARITY UNPINNED (see oracle/__init__.py).  They pin the oracle against
 silent drift and let the GPU tests check the product without re-running the oracle.
 
-Run:  python tests/golden/make_golden.py     (about 30 s on 8 cores; deterministic for a given torch build)
+``s0_b1.npz`` is the same for the vae_decoder_loss / 's0' variant all shipped experiment files select
+(config_files/SemSeg/MTMADISE/mtmadise_cityscapes_rgb_to_depth_11.py:47-55): UNet final output, decoded image,
+s0 / s3 / s4 / s5.
+
+Run:  python tests/golden/make_golden.py [base|s0]    (about 30 s each on 8 cores; deterministic for a given torch build)
 """
 import os
 import sys
@@ -19,7 +23,7 @@ sys.path.insert(0, ROOT)
 from oracle import synthetic  # noqa: E402
 from oracle.lora import set_adapter  # noqa: E402
 
-SUB = {"s2": 4, "s3": 2, "s4": 1, "s5": 1, "enc_tap": 4, "unet_tap16": 1, "unet_tap32": 1, "unet_tap64": 2}
+SUB = {"s2": 4, "s3": 2, "s4": 1, "s5": 1, "enc_tap": 4, "unet_tap16": 1, "unet_tap32": 1, "unet_tap64": 2, "s0": 8, "decoded_raw": 2}
 
 
 def subsample(name, t):
@@ -48,5 +52,27 @@ def main():
     print("wrote", path, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 
+def main_s0():
+    torch.set_num_threads(os.cpu_count() or 1)
+    bb = synthetic.build_backbone(variant="s0")
+    set_adapter(bb.feature_extractor.ldm_extractor.unet, ["Depth"])
+    img = synthetic.synthetic_images(1)
+    with torch.no_grad():
+        taps, fin = bb.feature_extractor(dict(img=img), "others", return_unet_final_output=True)
+        feats = bb.forward_features(taps)["output_features"]
+    out = {"unet_sample": fin["before_vae.decoder"].numpy(), "decoded_raw": subsample("decoded_raw", taps[0]).numpy().astype(np.float16),
+           "decoded_raw_absmax": np.float32(taps[0].abs().max().item())}
+    for name, t in feats.items():
+        out[name] = subsample(name, t).numpy().astype(np.float16)
+        out[name + "_absmax"] = np.float32(t.abs().max().item())
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "s0_b1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1] if len(sys.argv) > 1 else "both"
+    if which in ("base", "both"):
+        main()
+    if which in ("s0", "both"):
+        main_s0()

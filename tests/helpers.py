@@ -8,19 +8,20 @@ import torch.nn.functional as F
 LORA_CONFIGS = ("default_r16_a16", "Depth_r16_a16")
 
 
-def build_product_backbone(device, lora_configs=LORA_CONFIGS, with_ema=True, same_cond_params=False, compute_dtype="fp16"):
+def build_product_backbone(device, lora_configs=LORA_CONFIGS, with_ema=True, same_cond_params=False, compute_dtype="fp16", variant="base"):
     """Construct madm_b200's backbone exactly as the reference LazyCall config does
     (config_files/common/models/mtmadise_multi_lora.py:14-41) + MTMADISE.set_multi_lora (mtmadise.py:115-127)."""
     from madm_b200.backbone import AttentionFeatureExtractorBackbone
     from madm_b200.ldm import BasePromptTimeGenerator, LdmDiffusers
-    ldm = LdmDiffusers(stable_diffusion_name_or_path=None, encoder_block_indices=[5], unet_block_indices=[5, 8, 11],
+    s0 = variant == "s0"  # the overrides of config_files/SemSeg/MTMADISE/mtmadise_cityscapes_rgb_to_depth_11.py:47-55
+    ldm = LdmDiffusers(stable_diffusion_name_or_path=None, encoder_block_indices=[] if s0 else [5], unet_block_indices=[5, 8, 11],
                        unet_block_indices_type="after", decoder_block_indices=(), input_range="-1+1", finetune_unet="all",
-                       device=device, compute_dtype=compute_dtype)
+                       vae_decoder_loss=s0, device=device, compute_dtype=compute_dtype)
     gen = BasePromptTimeGenerator(learnable_cond_prompt=True, learnable_cond_time=True, clip_state="no", num_timesteps=1,
                                   clip_model_name="ViT-L-14-336", ldm_extractor=ldm, same_cond_params=same_cond_params)
-    bb = AttentionFeatureExtractorBackbone(attention_features_res=None, feature_dims=[512, 320, 640, 1280],
-                                           projection_dim=[512, 512, 512, 512], attention_features_location=None,
-                                           feature_extractor=gen, num_res_blocks=1, out_features=["s2", "s3", "s4", "s5"],
+    bb = AttentionFeatureExtractorBackbone(attention_features_res=None, feature_dims=[3 if s0 else 512, 320, 640, 1280],
+                                           projection_dim=[128 if s0 else 512, 512, 512, 512], attention_features_location=None,
+                                           feature_extractor=gen, num_res_blocks=1, out_features=["s0" if s0 else "s2", "s3", "s4", "s5"],
                                            use_checkpoint=False, slide_training=False)
     for cfg in lora_configs:
         name, rank, alpha = cfg.split("_")

@@ -76,6 +76,31 @@ def test_state_dict_keys_match_oracle_and_reference_names():
     assert torch.equal(shared.cpu(), torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(42)))
 
 
+def test_s0_variant_state_dict_keys_match_oracle():
+    """vae_decoder_loss / s0 variant (mtmadise_cityscapes_rgb_to_depth_11.py:47-55): the product holders expose exactly the
+    oracle's (= diffusers) keys incl. vae.decoder.*, and the projection for 's0' is Bottleneck(3 -> 128 -> 128)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import build_product_backbone
+    from oracle import synthetic
+    pb = build_product_backbone(torch.device("cpu"), variant="s0")
+    with torch.device("meta"):
+        ob = synthetic.build_backbone(variant="s0", lora_configs=(), with_ema=False)
+    pk = {k: tuple(v.shape) for k, v in pb.state_dict().items()}
+    pre = "feature_extractor.ldm_extractor.vae."
+    for k, v in ob.state_dict().items():
+        if k.startswith(pre) or k.startswith("feature_projections."):
+            assert pk.get(k) == tuple(v.shape), (k, pk.get(k), tuple(v.shape))
+    assert pk[pre + "decoder.up_blocks.2.resnets.0.conv_shortcut.weight"] == (256, 512, 1, 1)
+    assert pk["feature_projections.0.0.conv1.weight"] == (128, 3, 1, 1) and pk["feature_projections.0.0.shortcut.weight"] == (128, 3, 1, 1)
+    assert pk["feature_projections.0.0.conv3.weight"] == (128, 128, 1, 1)
+    assert sum(v.numel() for k, v in pb.state_dict().items() if k.startswith(pre + "decoder.")) == 49_490_179
+    assert pb._out_features == ["s0", "s3", "s4", "s5"] and pb._out_feature_strides["s0"] == 1
+    from madm_b200.backbone import AttentionFeatureExtractorBackbone
+    with pytest.raises(NotImplementedError):  # s2 projection config on an s0 extractor
+        AttentionFeatureExtractorBackbone(None, [512, 320, 640, 1280], None, feature_extractor=pb.feature_extractor,
+                                          out_features=["s2", "s3", "s4", "s5"])
+
+
 def test_adapter_selection_follows_reference_semantics():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import set_lora_adapter

@@ -28,6 +28,48 @@ def test_sd14_parameter_counts():
     assert nparams(vae.post_quant_conv) == 20
 
 
+def test_vae_decoder_parameter_counts():
+    """Decoder half of the SD-1.4 VAE: 49,490,179 parameters; the whole AutoencoderKL has the published
+    83,653,863.  The base model's random-init stream must not change when the decoder exists (it is constructed last)."""
+    with torch.device("meta"):
+        vae = sd14.AutoencoderKL(with_decoder=True)
+    assert nparams(vae.decoder) == 49_490_179
+    assert nparams(vae) == 83_653_863
+    # up blocks: three ResBlocks each, output channels (512, 512, 256, 128), upsamplers on the first three
+    assert [len(b.resnets) for b in vae.decoder.up_blocks] == [3, 3, 3, 3]
+    assert [b.resnets[-1].conv2.out_channels for b in vae.decoder.up_blocks] == [512, 512, 256, 128]
+    assert [b.upsamplers is not None for b in vae.decoder.up_blocks] == [True, True, True, False]
+
+
+def test_vae_decoder_control_flow_small():
+    """vae_decoder (ldm_diffusers.py:314-346): 1/0.18215 scale, post_quant_conv, conv_in, mid, up blocks, taps *before* resnet
+    `index`, final GN/SiLU/conv only with output_final.  Checked on an 8x8 latent against the modules applied by hand."""
+    torch.manual_seed(0)
+    vae = sd14.AutoencoderKL(with_decoder=True).eval()
+    lat = torch.randn(1, 4, 8, 8)
+    with torch.no_grad():
+        out, feats = sd14.vae_decoder(vae, lat, [0, 3, 9], output_final=True)
+        none, _ = sd14.vae_decoder(vae, lat, [], output_final=False)
+        d = vae.decoder
+        x = d.conv_in(vae.post_quant_conv(lat / 0.18215))
+        x = d.mid_block(x)
+        ref_feats = []
+        i = 0
+        for blk in d.up_blocks:
+            for r in blk.resnets:
+                if i in (0, 3, 9):
+                    ref_feats.append(x)
+                i += 1
+                x = r(x)
+            if blk.upsamplers is not None:
+                x = blk.upsamplers[0](x)
+        ref = d.conv_out(torch.nn.functional.silu(d.conv_norm_out(x)))
+    assert none is None and out.shape == (1, 3, 64, 64)
+    assert torch.allclose(out, ref, atol=1e-5)
+    assert [tuple(f.shape) for f in feats] == [(1, 512, 8, 8), (1, 512, 16, 16), (1, 256, 64, 64)]
+    assert all(torch.allclose(a, b, atol=1e-5) for a, b in zip(feats, ref_feats))
+
+
 def test_lora_layer_count_and_params():
     """128 wrapped projections; r * 199,296 parameters per adapter."""
     with torch.device("meta"):
@@ -145,6 +187,28 @@ def test_oracle_tap_shapes_and_golden(oracle_run):
         got = feats[k][:, :, ::s, ::s].numpy()
         ref = g[k].astype(np.float32)
         assert np.abs(got - ref).max() <= 2e-3 * float(g[k + "_absmax"]) + 2e-3, k  # fp16 storage of the fixture + thread-count jitter
+
+
+def test_oracle_s0_variant_shapes_and_golden():
+    """The vae_decoder_loss / s0 variant (mtmadise_cityscapes_rgb_to_depth_11.py:47-55): shapes, the return_unet_final_output
+    dict (ldm_diffusers.py:211-215, clip only on the returned copy) and the committed fixture tests/golden/s0_b1.npz."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    bb = synthetic.build_backbone(variant="s0")
+    lora.set_adapter(bb.feature_extractor.ldm_extractor.unet, ["Depth"])
+    img = synthetic.synthetic_images(1)
+    with torch.no_grad():
+        out, fin = bb(img, input_modal="others", return_unet_final_output=True)
+    feats = out["output_features"]
+    assert {k: tuple(v.shape) for k, v in feats.items()} == {"s0": (1, 128, 512, 512), "s3": (1, 512, 64, 64), "s4": (1, 512, 32, 32),
+                                                             "s5": (1, 512, 16, 16)}
+    assert fin["before_vae.decoder"].shape == (1, 4, 64, 64) and fin["after_vae.decoder"].shape == (1, 3, 512, 512)
+    assert fin["after_vae.decoder"].min() >= -1 and fin["after_vae.decoder"].max() <= 1
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "s0_b1.npz"))
+    assert np.allclose(fin["before_vae.decoder"].numpy(), g["unet_sample"], atol=2e-3)
+    for k, s in {"s0": 8, "s3": 2, "s4": 1, "s5": 1}.items():
+        got = feats[k][:, :, ::s, ::s].numpy()
+        ref = g[k].astype(np.float32)
+        assert np.abs(got - ref).max() <= 2e-3 * float(g[k + "_absmax"]) + 2e-3, k
 
 
 def test_bf16_error_budget(oracle_run):
