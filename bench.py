@@ -27,6 +27,9 @@ UNIT = "images/s"
 PER_GPU_BATCH = 8
 # algorithmic FLOPs per 512^2 image (2*MAC), SURVEY §8d / BASELINE.md §2
 GF_PER_IMG = {"vae_encoder": 1116.66, "unet_taps": 803.18, "projections": 14.35, "total": 1934.2}
+# --variant s0 (not the default bench line): the vae_decoder_loss configuration of the shipped experiment files:
+# + UNet conv_out, VAE decoder 2514.5, Bottleneck(3->128->128) at 512^2 instead of the s2 projection; SURVEY §8d total 4526.0
+GF_PER_IMG_S0 = {"vae_encoder": 1116.66, "unet": 803.27, "vae_decoder": 2514.5, "projections": 91.6, "total": 4526.0}
 
 
 def read_peaks():
@@ -87,13 +90,13 @@ class ClockSampler:
                 "power_w_max": max(pw)}
 
 
-def cpu_oracle_throughput(timed: int = 3, warm: int = 1):
+def cpu_oracle_throughput(timed: int = 3, warm: int = 1, variant: str = "base"):
     """The fp32 oracle (CPU restatement of the reference path) on the host cores: config 1, 1x3x512x512."""
     import torch
     from oracle import synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    ob = synthetic.build_backbone(with_ema=False)
+    ob = synthetic.build_backbone(with_ema=False, variant=variant)
     img = synthetic.synthetic_images(1)
     with torch.no_grad():
         for _ in range(warm):
@@ -104,7 +107,7 @@ def cpu_oracle_throughput(timed: int = 3, warm: int = 1):
         dt = (time.perf_counter() - t0) / timed
     return dict(value=1.0 / dt, unit=UNIT, cores=torch.get_num_threads(), kind="port",
                 sample=f"BASELINE config 1: 1x3x512x512 fp32 oracle forward, {warm} warm-up + {timed} timed, {dt:.2f} s/img, "
-                       f"{GF_PER_IMG['total'] / dt:.0f} GFLOP/s implied"), dt
+                       f"{(GF_PER_IMG if variant == 'base' else GF_PER_IMG_S0)['total'] / dt:.0f} GFLOP/s implied"), dt
 
 
 def run_reference(args, rank, world):
@@ -113,7 +116,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     steps = max(1, min(args.steps, 3))
-    base, dt = cpu_oracle_throughput(timed=steps, warm=1)
+    base, dt = cpu_oracle_throughput(timed=steps, warm=1, variant=args.variant)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -138,7 +141,8 @@ def run_product(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(1234 + rank)
-    bb = build_product_backbone(dev, compute_dtype=args.dtype)  # random-init SD-1.4 weights + 2 LoRA adapters (r16)
+    bb = build_product_backbone(dev, compute_dtype=args.dtype, variant=args.variant)  # random-init SD-1.4 weights + 2 LoRA adapters (r16)
+    gf = GF_PER_IMG if args.variant == "base" else GF_PER_IMG_S0
     ldm = bb.feature_extractor.ldm_extractor
     with torch.no_grad():  # de-degenerate the zero-init pieces like the parity fixtures do
         g = torch.Generator(device=dev).manual_seed(99)
@@ -149,8 +153,9 @@ def run_product(args, rank, local_rank, world):
     gi = torch.Generator().manual_seed(rank)
     img_host = (torch.rand(B, 3, 512, 512, generator=gi)).pin_memory()
     img_dev = img_host.to(dev, non_blocking=True)
-    outs_host = [torch.empty(B, 512, s, s, dtype=torch.float32).pin_memory() for s in (128, 64, 32, 16)]
-    outs_dev = [torch.empty(B, 512, s, s, dtype=torch.float32, device=dev) for s in (128, 64, 32, 16)]
+    from madm_b200.engine import OUT_SHAPES
+    outs_host = [torch.empty(B, c, s, s, dtype=torch.float32).pin_memory() for c, s in OUT_SHAPES[args.variant]]
+    outs_dev = [torch.empty(B, c, s, s, dtype=torch.float32, device=dev) for c, s in OUT_SHAPES[args.variant]]
 
     # B <= engine.graph_max_batch (8): the backbone replays the step's ~555 launches as one CUDA graph (static input buffer,
     # results cloned out of the static output buffers); larger batches launch on the stream into `outs_dev`.
@@ -263,21 +268,25 @@ def run_product(args, rank, local_rank, world):
         "share_of_step": gemm["ms"] / total_ms,
         "families": {k: {"ms_per_step": v["ms"], "launches": v["launches"], "share": v["ms"] / total_ms} for k, v in prof.items()},
         "groupnorm_hbm": {"achieved_gbs": gn["bytes"] / (gn["ms"] / 1e3) / 1e9 if gn["ms"] > 0 else None, "peak_gbs": peaks["hbm_gbs"]},
-        "whole_path_tflops": value / world * GF_PER_IMG["total"] / 1e3,
+        "whole_path_tflops": value / world * gf["total"] / 1e3,
     }
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_base, _ = cpu_oracle_throughput(timed=3, warm=1)
+        cpu_base, _ = cpu_oracle_throughput(timed=3, warm=1, variant=args.variant)
     ws_gb = eng._ws.numel() / 2 ** 30
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic (seeded rand images, random-init SD-1.4 weights + r16 LoRA, SURVEY §8d)",
-        "config": {"workload": f"BASELINE configs[1]: {B}x3x512x512 per GPU, feature extraction a-1..a-9 "
-                               "(VAE-enc + q-sample t=0 + UNet taps + s2..s5 projections); sem_seg_head is SURVEY §8 f-2 (next), not timed",
+        "config": {"workload": (f"BASELINE configs[1]: {B}x3x512x512 per GPU, feature extraction a-1..a-9 "
+                                "(VAE-enc + q-sample t=0 + UNet taps + s2..s5 projections); sem_seg_head is SURVEY §8 f-2 (next), not timed")
+                   if args.variant == "base" else
+                   (f"{B}x3x512x512 per GPU, vae_decoder_loss / s0 variant of the shipped experiment configs (SURVEY §8 a-11): VAE-enc + "
+                    "q-sample t=0 + UNet to its final output + VAE decoder + s0/s3/s4/s5 projections"),
+                   "variant": args.variant,
                    "per_gpu_batch": B, "global_batch": B * world, "input_modal": "others", "adapter": "Depth_r16_a16 (folded)",
                    "l2": f"working set (packed weights 1.8 GB + workspace {ws_gb:.1f} GB) >> 126 MB L2; no explicit flush",
-                   "accumulate": "fp32", "residual_stream": "fp32 (UNet, projections); fp16 in the VAE 512^2 / 256^2 stages with fp16 operands, like the reference's fp16 VAE", "gflop_per_image": GF_PER_IMG},
+                   "accumulate": "fp32", "residual_stream": "fp32 (UNet, projections); fp16 in the VAE 512^2 / 256^2 stages with fp16 operands, like the reference's fp16 VAE", "gflop_per_image": gf},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": sum(t.numel() * 4 for t in outs_host),
@@ -303,6 +312,8 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"], help="GEMM operand dtype (fp32 accumulate)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", default="base", choices=["base", "s0"],
+                    help="base = BASELINE configs[1] (the bench line); s0 = vae_decoder_loss configuration of the shipped experiment files")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -137,7 +137,8 @@ typedef struct madm_extract_args {
   size_t workspace_bytes;
   int32_t* range_flag;         /* optional device int: set to 1 if the normalised image leaves [-1,1]
                                   (the reference asserts this with a host sync, ldm_diffusers.py:147) */
-  float* logits;               /* MADM_STAGE_HEAD: [B,num_classes,128,128] fp32 NCHW (DAFormerHead output, before any resize) */
+  float* logits;               /* MADM_STAGE_HEAD: [B,num_classes,128,128] fp32 NCHW (DAFormerHead output, before any resize);
+                                  MADM_VARIANT_S0: the head fuses on the s0 grid -> [B,num_classes,512,512] */
   /* MADM_VARIANT_S0 (MADM_STAGE_DEC); out[0] then is s0 [B,128,512,512].  Both optional (NULL to skip), fp32 NCHW: the dict
    * LdmDiffusers.forward returns under return_unet_final_output (ldm_diffusers.py:211-215) */
   float* unet_sample;          /* [B,4,64,64]   'before_vae.decoder': unet_final_output.sample */

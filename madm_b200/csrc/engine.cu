@@ -1195,14 +1195,17 @@ struct Model {
     const ParamRef* cs = b.find(h + "conv_seg.weight");
     const ParamRef* e0 = b.find(h + "embed_layers.0.proj.weight");
     if (!cs || !e0) b.fail(MADM_ENOTFOUND, "sem_seg_head parameters are not registered");
-    const int ncls = int(cs->shape[0]), CH = int(cs->shape[1]), E = int(e0->shape[0]), Cin = int(e0->shape[1]);
-    if (Cin != 512 || E % 64 != 0 || CH % 64 != 0 || ncls > 32) b.fail(MADM_EINVAL, "sem_seg_head: unsupported channel configuration");
-    const int Bn = b.B, side[4] = {128, 64, 32, 16}, H = 128, W = 128, CAT = 4 * E;
+    const int ncls = int(cs->shape[0]), CH = int(cs->shape[1]), E = int(e0->shape[0]), Cin0 = int(e0->shape[1]);
+    // base: s2..s5, four 512-channel maps, fused on the 128^2 grid.  s0 variant (in_keys[0]='s0', in_channels[0]=128,
+    // mtmadise_cityscapes_rgb_to_depth_11.py:51-55): the first map is 128 x 512^2, so the head fuses on the 512^2 grid.
+    const int H0 = s0() ? 512 : 128;
+    if (Cin0 != (s0() ? 128 : 512) || E % 64 != 0 || CH % 64 != 0 || ncls > 32) b.fail(MADM_EINVAL, "sem_seg_head: unsupported channel configuration");
+    const int Bn = b.B, side[4] = {H0, 64, 32, 16}, H = H0, W = H0, CAT = 4 * E;
     const long M = long(Bn) * H * W;
     const int f16v = f16();
     B16T cat = b.b16(size_t(M) * CAT);
     for (int i = 0; i < 4; ++i) {
-      const int Hi = side[i], HWi = Hi * Hi;
+      const int Hi = side[i], HWi = Hi * Hi, Cin = i == 0 ? Cin0 : 512;
       const long Mi = long(Bn) * HWi;
       B16T x = b.b16(size_t(Mi) * Cin);
       if (dry()) b.emit(nullptr);

@@ -148,7 +148,8 @@ class Engine:
 
     # ------------------------------------------------------------------ DAFormer head
     def head(self, feats: Sequence[torch.Tensor], num_classes: int) -> torch.Tensor:
-        """``MADM_STAGE_HEAD`` on the feature dict: s2..s5 fp32 NCHW [B,512,side,side] -> logits [B,num_classes,128,128]."""
+        """``MADM_STAGE_HEAD`` on the feature dict: s2..s5 fp32 NCHW [B,512,side,side] -> logits [B,num_classes,128,128]
+        (s0 variant: s0 [B,128,512,512], s3..s5 -> logits [B,num_classes,512,512])."""
         if self._packed is None:
             raise _lib.MadmError("Engine.head called before ensure_packed()")
         dev = self.device
@@ -156,14 +157,15 @@ class Engine:
         a = MadmExtractArgs()
         a.B, a.stages, a.ema = B, STAGE_HEAD, 0
         keep = []
-        for i, side in enumerate(OUT_SIDES):
+        for i, (ch, side) in enumerate(OUT_SHAPES[self.variant]):
             t = feats[i]
-            if t.device != dev or tuple(t.shape) != (B, 512, side, side):
-                raise _lib.MadmError(f"feature map {i} must be [{B},512,{side},{side}] on {dev}, got {tuple(t.shape)} on {t.device}")
+            if t.device != dev or tuple(t.shape) != (B, ch, side, side):
+                raise _lib.MadmError(f"feature map {i} must be [{B},{ch},{side},{side}] on {dev}, got {tuple(t.shape)} on {t.device}")
             t = t.to(torch.float32).contiguous()
             keep.append(t)
             a.out[i] = t.data_ptr()
-        logits = torch.empty(B, num_classes, OUT_SIDES[0], OUT_SIDES[0], dtype=torch.float32, device=dev)
+        side0 = OUT_SHAPES[self.variant][0][1]
+        logits = torch.empty(B, num_classes, side0, side0, dtype=torch.float32, device=dev)
         a.logits = logits.data_ptr()
         ws = self.workspace(B)
         a.packed = self._packed.data_ptr()

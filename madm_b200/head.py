@@ -102,7 +102,9 @@ class DAFormerHead(nn.Module):
             (not final_fuse_vae_decoder_feat, "final_fuse_vae_decoder_feat=False"),
             (not align_corners, "align_corners=False"),
             (input_transform == "multiple_select", "input_transform='multiple_select'"),
-            (in_channels == [512] * 4 and in_keys == ["s2", "s3", "s4", "s5"] and in_index == [0, 1, 2, 3], "the four 512-channel maps s2..s5"),
+            ((in_channels, in_keys) in (([512] * 4, ["s2", "s3", "s4", "s5"]), ([128, 512, 512, 512], ["s0", "s3", "s4", "s5"]))
+             and in_index == [0, 1, 2, 3], "the four 512-channel maps s2..s5, or s0 (128 channels) + s3..s5 "
+             "(mtmadise_cityscapes_rgb_to_depth_11.py:51-55)"),
             (embed.get("type") == "mlp" and neck.get("type") == "mlp", "embed_cfg / embed_neck_cfg type 'mlp'"),
             (fusion.get("type") == "aspp" and bool(fusion.get("sep")) and tuple(fusion.get("dilations", ())) == (1, 6, 12, 18)
              and not fusion.get("pool") and not fusion.get("context_cfg"), "fusion_cfg aspp, sep=True, dilations (1,6,12,18), pool=False"),
@@ -115,6 +117,7 @@ class DAFormerHead(nn.Module):
             if not ok:
                 raise NotImplementedError(_UNSUPPORTED.format(what))
         self.in_channels, self.in_keys, self.in_index = in_channels, in_keys, in_index
+        self.variant = "s0" if in_keys[0] == "s0" else "base"
         self.channels, self.num_classes, self.dropout_ratio = channels, num_classes, dropout_ratio
         self.ignore_index, self.align_corners = ignore_index, align_corners
         E = dp["embed_dims"]
@@ -138,7 +141,7 @@ class DAFormerHead(nn.Module):
     def engine(self) -> Engine:
         dev = self.conv_seg.weight.device
         if self._engine is None or self._engine.device != dev:
-            self._engine = Engine(dev, self.compute_dtype)  # raises without libmadm_b200.so / an sm_100 device
+            self._engine = Engine(dev, self.compute_dtype, self.variant)  # raises without libmadm_b200.so / an sm_100 device
         return self._engine
 
     def transfer_input_dict_to_list(self, inputs_dict: Dict[str, torch.Tensor]) -> List[torch.Tensor]:

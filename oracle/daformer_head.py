@@ -83,10 +83,11 @@ class DAFormerHead(nn.Module):
         return self.conv_seg(x)  # cls_seg :673-699 (dropout is identity in eval)
 
 
-def build_head(seed: int = 4321) -> DAFormerHead:
-    """Random-init head in eval mode with non-trivial BatchNorm running statistics and a classifier whose logits are O(1)."""
+def build_head(seed: int = 4321, variant: str = "base") -> DAFormerHead:
+    """Random-init head in eval mode with non-trivial BatchNorm running statistics and a classifier whose logits are O(1).
+    variant 's0': in_channels[0] = 128, in_keys[0] = 's0' (mtmadise_cityscapes_rgb_to_depth_11.py:51-55): fuses on the 512^2 grid."""
     torch.manual_seed(seed)
-    head = DAFormerHead()
+    head = DAFormerHead() if variant == "base" else DAFormerHead(in_channels=(128, 512, 512, 512), in_keys=("s0", "s3", "s4", "s5"))
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():
         for m in head.modules():

@@ -119,3 +119,31 @@ def test_s0_ema_and_sliding_window(pair, cuda_device):
     assert got["s0"].shape == (1, 128, 512, 1024)
     for k in ref:
         _check("slide-ema/" + k, got[k], ref[k])
+
+
+def test_s0_head_image_to_segmentation(pair, cuda_device):
+    """Row f-2 in the variant: DAFormerHead with in_keys[0]='s0', in_channels[0]=128 fuses on the 512^2 grid
+    (mtmadise_cityscapes_rgb_to_depth_11.py:51-55).  Logits parity on the oracle's features, and image -> product backbone ->
+    product head against image -> oracle backbone -> oracle head: argmax >= 99.5 % pixel-identical (north_star gate)."""
+    from madm_b200.head import DAFormerHead
+    from oracle import synthetic
+    from oracle.daformer_head import build_head
+    from test_head_gpu import HEAD_KW
+    ob, pb = pair
+    oh = build_head(variant="s0").to(cuda_device)
+    kw = dict(HEAD_KW, in_channels=[128, 512, 512, 512], in_keys=["s0", "s3", "s4", "s5"])
+    ph = DAFormerHead(**kw, device=cuda_device).eval()
+    assert set(ph.state_dict().keys()) == set(oh.state_dict().keys())
+    ph.load_state_dict(oh.state_dict())
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    img = synthetic.synthetic_images(1, seed=21).to(cuda_device)
+    with torch.no_grad():
+        rf = ob(img, input_modal="others")
+        ref = oh(rf)
+        same_feats = ph(rf)
+        got = ph(pb(img, input_modal="others"))
+    assert got.shape == ref.shape == (1, 19, 512, 512)
+    _check("head(s0)/logits on oracle features", same_feats, ref)
+    agree = (got.argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"[s0] image -> segmentation argmax agreement {agree * 100:.3f} %")
+    assert agree >= 0.995
