@@ -53,9 +53,13 @@ def test_s0_variant_parity(pair, cuda_device):
         res = pb._extract(img, "others", False, None, want_taps=True, return_unet_final_output=True)
     _check("before_vae.decoder", res["unet_sample"], fin["before_vae.decoder"])
     _check("decoder_output", res["taps"][0], taps[0])
-    _check("after_vae.decoder", res["decoded"], fin["after_vae.decoder"])
+    # 'after_vae.decoder' is clip(decoder_output, -1, 1): the clip itself is bit-exact (asserted), so its error is the decoder
+    # output's, measured on the decoder output's scale (the clipped copy's own max is 1 by construction)
     assert res["decoded"].min() >= -1.0 and res["decoded"].max() <= 1.0
     assert torch.equal(res["decoded"], res["taps"][0].clamp(-1.0, 1.0))
+    err = (res["decoded"] - fin["after_vae.decoder"]).abs().max().item() / taps[0].abs().max().item()
+    print(f"[s0] after_vae.decoder: cos={cosine(res['decoded'], fin['after_vae.decoder']):.6f} max_rel={err:.5f}")
+    assert cosine(res["decoded"], fin["after_vae.decoder"]) >= COS_MIN and err <= REL_MAX
     for k, got in zip(["s0", "s3", "s4", "s5"], res["features"]):
         assert got.shape == feats[k].shape
         _check(k, got, feats[k])
