@@ -241,6 +241,26 @@ int madm_op_pseudo_labels(const float* logits /*[B,C,h,w]*/, int32_t B, int32_t 
 int madm_op_class_mask(const int64_t* label, int64_t n, const int64_t* classes, int32_t k, int64_t* mask, madm_stream stream);
 int madm_op_one_mix(const int64_t* mask, int64_t n, const int64_t* label_a, const int64_t* label_b, int64_t* label_out /*or NULL*/,
                     const float* weight_a, const float* weight_b, float* weight_out /*or NULL*/, madm_stream stream);
+/* image side of the DACS mixing (reference utils/dacs_transforms.py:98-112 one_mix on `data`, :62-84 gaussian_blur =
+ * kornia.filters.GaussianBlur2d(kernel_size, (sigma, sigma)), separable, border 'reflect') */
+int madm_op_image_mix(const int64_t* mask /*[HW] 0/1*/, const float* a /*[C,HW]*/, const float* b, int32_t C, int64_t HW, float* out,
+                      madm_stream stream);
+int madm_op_gaussian_blur(const float* src /*[planes,H,W]*/, int32_t planes, int32_t H, int32_t W, int32_t ky, int32_t kx, float sigma_y,
+                          float sigma_x, float* tmp /*scratch, same size*/, float* dst, madm_stream stream);
+/* optimizer side of the training step.  Pointer tables are HOST arrays of n DEVICE pointers (fp32 tensors of numel[i]
+ * elements); everything is enqueued on `stream`, nothing returns to the host.
+ *   madm_op_ema_update : CMDISE._update_ema (modeling/meta_arch/cmdise.py:337-349): ema = alpha * ema + one_minus_alpha * param
+ *   madm_op_grad_norm  : the global L2 norm torch.nn.utils.clip_grad_norm_ computes (engine/train_loop.py:123-124, :201-210) -> device scalar
+ *   madm_op_adamw_step : one torch.optim.AdamW step (config_files/common/optim.py:9-18), step counted from 1; with grad_norm (device
+ *                        scalar) and max_norm > 0 the gradients are scaled by min(max_norm / (norm + 1e-6), 1) first.
+ *                        Hyper-parameters are doubles: torch derives 1 - beta, lr / (1 - beta1^t), ... in Python floats before casting */
+int madm_op_ema_update(float* const* ema, const float* const* param, const int64_t* numel, int32_t n, float alpha, float one_minus_alpha,
+                       madm_stream stream);
+int madm_op_grad_norm_scratch_floats(int32_t n);
+int madm_op_grad_norm(const float* const* grad, const int64_t* numel, int32_t n, float* scratch, float* out_norm, madm_stream stream);
+int madm_op_adamw_step(float* const* param, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel,
+                       int32_t n, double lr, double beta1, double beta2, double eps, double weight_decay, int32_t step, const float* grad_norm,
+                       float max_norm, madm_stream stream);
 /* sliding-window merge of per-crop feature maps (reference feature_extractor.py:254-275: accumulate, divide by the count matrix):
  * feats [nwin*n, C, hf, wf] window-major, wins [nwin][2] = window origin (y1, x1) in feature pixels -> out [n, C, Hf, Wf] */
 int madm_op_slide_merge(const float* feats, int32_t nwin, int32_t n, int32_t C, int32_t hf, int32_t wf, const int32_t* wins, int32_t Hf,

@@ -104,6 +104,13 @@ SYMBOLS = {
                                       c_void_p, c_void_p, c_void_p]),
     "madm_op_class_mask": (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "madm_op_one_mix": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "madm_op_image_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+    "madm_op_gaussian_blur": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "madm_op_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_void_p]),
+    "madm_op_grad_norm_scratch_floats": (c_int, [c_int32]),
+    "madm_op_grad_norm": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "madm_op_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                   C.c_double, c_int32, c_void_p, c_float, c_void_p]),
     "madm_op_slide_merge": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "madm_op_upsample2x": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_image_im2col": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),

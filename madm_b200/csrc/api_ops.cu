@@ -133,6 +133,38 @@ int madm_op_one_mix(const int64_t* mask, int64_t n, const int64_t* label_a, cons
   RUN(one_mix(mask, long(n), label_a, label_b, label_out, weight_a, weight_b, weight_out, static_cast<cudaStream_t>(stream)));
 }
 
+int madm_op_ema_update(float* const* ema, const float* const* param, const int64_t* numel, int32_t n, float alpha, float one_minus_alpha,
+                       madm_stream stream) {
+  if (!ema || !param || !numel || n < 1) return fail("madm_op_ema_update: null argument");
+  RUN(ema_update(ema, param, reinterpret_cast<const long*>(numel), n, alpha, one_minus_alpha, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_grad_norm_scratch_floats(int32_t n) { return grad_norm_scratch_floats(n); }
+
+int madm_op_grad_norm(const float* const* grad, const int64_t* numel, int32_t n, float* scratch, float* out_norm, madm_stream stream) {
+  if (!grad || !numel || !scratch || !out_norm || n < 1) return fail("madm_op_grad_norm: null argument");
+  RUN(grad_norm(grad, reinterpret_cast<const long*>(numel), n, scratch, out_norm, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_adamw_step(float* const* param, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel,
+                       int32_t n, double lr, double beta1, double beta2, double eps, double weight_decay, int32_t step, const float* grad_norm,
+                       float max_norm, madm_stream stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !numel || n < 1) return fail("madm_op_adamw_step: null argument");
+  RUN(adamw_step(param, grad, exp_avg, exp_avg_sq, reinterpret_cast<const long*>(numel), n, lr, beta1, beta2, eps, weight_decay, step, grad_norm,
+                 max_norm, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_image_mix(const int64_t* mask, const float* a, const float* b, int32_t C, int64_t HW, float* out, madm_stream stream) {
+  if (!mask || !a || !b || !out) return fail("madm_op_image_mix: null argument");
+  RUN(image_mix(mask, a, b, C, long(HW), out, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_gaussian_blur(const float* src, int32_t planes, int32_t H, int32_t W, int32_t ky, int32_t kx, float sigma_y, float sigma_x, float* tmp,
+                          float* dst, madm_stream stream) {
+  if (!src || !tmp || !dst) return fail("madm_op_gaussian_blur: null argument");
+  RUN(gaussian_blur(src, planes, H, W, ky, kx, sigma_y, sigma_x, tmp, dst, static_cast<cudaStream_t>(stream)));
+}
+
 int madm_op_slide_merge(const float* feats, int32_t nwin, int32_t n, int32_t C, int32_t hf, int32_t wf, const int32_t* wins, int32_t Hf, int32_t Wf,
                         float* out, madm_stream stream) {
   RUN(slide_merge(feats, nwin, n, C, hf, wf, wins, Hf, Wf, out, static_cast<cudaStream_t>(stream)));

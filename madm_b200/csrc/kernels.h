@@ -111,6 +111,22 @@ const char* one_mix(const int64_t* mask, long n, const int64_t* la, const int64_
 // sliding-window merge: feats [nwin*n,C,hf,wf] (window-major), wins [nwin][2] = (y1,x1) in feature pixels -> out [n,C,Hf,Wf] = mean over covering windows
 const char* slide_merge(const float* feats, int nwin, int n, int C, int hf, int wf, const int* wins, int Hf, int Wf, float* out, cudaStream_t st);
 
+// ---- optim.cu (optimizer side of the training step; image side of the DACS mixing, f-4)
+// Pointer tables are HOST arrays of n device pointers.  ema = wa * ema + wb * param   (wa = alpha, wb = 1 - alpha)
+const char* ema_update(float* const* ema, const float* const* param, const long* numel, int n, float wa, float wb, cudaStream_t st);
+int grad_norm_scratch_floats(int n);
+// out_norm (device scalar) = sqrt(sum over all tensors of g^2); partial: device scratch of grad_norm_scratch_floats(n) floats
+const char* grad_norm(const float* const* grad, const long* numel, int n, float* partial, float* out_norm, cudaStream_t st);
+// torch.optim.AdamW step `step` (>= 1) on n tensors; grad_norm_dev (device scalar or null) + max_norm > 0: clip_grad_norm_ folded in
+const char* adamw_step(float* const* param, const float* const* grad, float* const* exp_avg, float* const* exp_avg_sq, const long* numel, int n,
+                       double lr, double beta1, double beta2, double eps, double weight_decay, int step, const float* grad_norm_dev, float max_norm,
+                       cudaStream_t st);
+// out[c, i] = mask[i] * a[c, i] + (1 - mask[i]) * b[c, i]
+const char* image_mix(const int64_t* mask, const float* a, const float* b, int C, long HW, float* out, cudaStream_t st);
+// separable Gaussian blur of `planes` HxW fp32 planes, reflect border; tmp: scratch of the same size (may not alias src / dst)
+const char* gaussian_blur(const float* src, int planes, int H, int W, int ky, int kx, float sigma_y, float sigma_x, float* tmp, float* dst,
+                          cudaStream_t st);
+
 // ---- pack.cu (weight packing; fp32 PyTorch layouts -> bf16 K-major GEMM operands)
 // conv weight [N, C, kh, kw] fp32 -> [N, kh*kw*Cpad] bf16 with K index = tap*Cpad + c (zero fill for c >= C)
 const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out_bf16, int fp16,

@@ -78,3 +78,47 @@ def one_mix(mask: torch.Tensor, target: Optional[torch.Tensor] = None, weight: O
         raise _lib.MadmError("one_mix: nothing to mix")
     _lib.check(lib.madm_op_one_mix(_ptr(m), n, _ptr(la), _ptr(lb), _ptr(lo), _ptr(wa), _ptr(wb), _ptr(wo), _stream()), None, "madm_op_one_mix")
     return (lo.unsqueeze(0) if lo is not None else None), (wo.unsqueeze(0) if wo is not None else None)
+
+
+def image_mix(mask: torch.Tensor, data: torch.Tensor) -> torch.Tensor:
+    """``one_mix`` on images (dacs_transforms.py:101-104): ``mask[0] * data[0] + (1 - mask[0]) * data[1]`` with the [1,H,W] class mask
+    broadcast over channels; ``data`` is the stacked pair [2,C,H,W] fp32.  Returns [1,C,H,W]."""
+    _need_cuda(data, "data")
+    lib = _lib.load()
+    d = data.to(torch.float32).contiguous()
+    m = mask[0].to(device=d.device, dtype=torch.int64).contiguous()
+    if d.dim() != 4 or d.shape[0] != 2 or m.numel() != d.shape[2] * d.shape[3]:
+        raise _lib.MadmError("image_mix: data must be [2,C,H,W] and mask [1,H,W]")
+    out = torch.empty_like(d[0])
+    _lib.check(lib.madm_op_image_mix(_ptr(m), _ptr(d[0]), _ptr(d[1]), d.shape[1], m.numel(), _ptr(out), _stream()), None, "madm_op_image_mix")
+    return out.unsqueeze(0)
+
+
+def blur_kernel_size(h: int, w: int) -> Tuple[int, int]:
+    """Kernel size rule of dacs_transforms.gaussian_blur (:66-75): ~10 % of the image side, forced odd."""
+    import math
+
+    def k(n):
+        c = math.ceil(0.1 * n)
+        return int(math.floor(c - 0.5 + c % 2))
+    return k(h), k(w)
+
+
+def gaussian_blur(blur: float, data: torch.Tensor, sigma: Optional[float] = None) -> torch.Tensor:
+    """dacs_transforms.gaussian_blur (:62-84): if ``blur > 0.5`` blur the 3-channel images [B,3,H,W] with
+    ``kornia.filters.GaussianBlur2d(kernel_size, (sigma, sigma))`` (separable, border 'reflect'); ``sigma`` defaults to the reference's
+    ``np.random.uniform(0.15, 1.15)`` draw.  Other inputs pass through unchanged, as in the reference."""
+    if data is None or data.shape[1] != 3 or not blur > 0.5:
+        return data
+    _need_cuda(data, "data")
+    import numpy as np
+    if sigma is None:
+        sigma = float(np.random.uniform(0.15, 1.15))
+    lib = _lib.load()
+    d = data.to(torch.float32).contiguous()
+    B, Cc, H, W = d.shape
+    ky, kx = blur_kernel_size(H, W)
+    tmp, out = torch.empty_like(d), torch.empty_like(d)
+    _lib.check(lib.madm_op_gaussian_blur(_ptr(d), B * Cc, H, W, ky, kx, float(sigma), float(sigma), _ptr(tmp), _ptr(out), _stream()), None,
+               "madm_op_gaussian_blur")
+    return out

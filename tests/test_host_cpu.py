@@ -220,3 +220,64 @@ def test_teacher_ops_have_no_cpu_path():
     assert torch.count_nonzero(w[:, :3]) == 0 and torch.all(w[:, 3:] == val)
     m = ot.generate_class_mask(lab[0], torch.tensor([int(lab[0, 0, 0])]))
     assert m.shape == (1, 32, 32) and m[0, 0, 0] == 1
+
+
+def _gloo_allreduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from madm_b200.optim import allreduce_grads
+    torch.manual_seed(0)
+    # two LoRA adapters' worth of parameters; each rank trained a different adapter this step (mtmadise.py:149-157)
+    params = [torch.nn.Parameter(torch.zeros(16, 320)), torch.nn.Parameter(torch.zeros(320, 16)),     # adapter "default"
+              torch.nn.Parameter(torch.zeros(16, 320)), torch.nn.Parameter(torch.zeros(320, 16)),     # adapter "Depth"
+              torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(3), requires_grad=False)]
+    mine = (0, 1) if rank == 0 else (2, 3)
+    for i in mine:
+        params[i].grad = torch.full_like(params[i], float(rank + 1))
+    params[4].grad = torch.full_like(params[4], 10.0 * (rank + 1))
+    flat = allreduce_grads(params)
+    q.put((rank, [None if p.grad is None else p.grad.clone() for p in params], flat.numel()))
+    dist.destroy_process_group()
+
+
+def test_lora_grad_allreduce_world_size_2_gloo():
+    """Training configuration: ONE all-reduce over the flat buffer of all trainable gradients, zeros
+    materialised for the adapter a rank did not train, averaged over ranks; frozen parameters stay out of the buffer."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    for rank, grads, n in res:
+        assert n == 2 * (16 * 320 + 320 * 16) + 7
+        assert torch.equal(grads[0], torch.full((16, 320), 0.5)) and torch.equal(grads[1], torch.full((320, 16), 0.5))   # (1 + 0) / 2
+        assert torch.equal(grads[2], torch.full((16, 320), 1.0)) and torch.equal(grads[3], torch.full((320, 16), 1.0))   # (0 + 2) / 2
+        assert torch.equal(grads[4], torch.full((7,), 15.0))
+        assert grads[5] is None
+
+
+def test_optimizer_ops_have_no_cpu_path():
+    from madm_b200 import _lib
+    from madm_b200.optim import FusedAdamW, update_ema
+    from madm_b200.teacher import gaussian_blur, image_mix
+    p = torch.nn.Parameter(torch.ones(4))
+    p.grad = torch.ones(4)
+    opt = FusedAdamW([p], lr=1e-3)
+    assert opt.param_groups[0]["weight_decay"] == 1e-2 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    with pytest.raises(_lib.MadmError):
+        opt.step()
+    with pytest.raises(_lib.MadmError):
+        update_ema([torch.nn.Parameter(torch.ones(4))], [p], 3)
+    with pytest.raises(_lib.MadmError):
+        image_mix(torch.ones(1, 4, 4, dtype=torch.long), torch.rand(2, 3, 4, 4))
+    with pytest.raises(_lib.MadmError):
+        gaussian_blur(0.9, torch.rand(1, 3, 64, 64), 0.5)
+    x = torch.rand(1, 3, 64, 64)
+    assert gaussian_blur(0.2, x, 0.5) is x  # not selected: untouched, like the reference
