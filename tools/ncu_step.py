@@ -17,9 +17,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--dtype", default="fp16")
+ap.add_argument("--variant", default="base", choices=["base", "s0"])
 args = ap.parse_args()
 dev = torch.device("cuda:0")
-bb = build_product_backbone(dev, compute_dtype=args.dtype)
+bb = build_product_backbone(dev, compute_dtype=args.dtype, variant=args.variant)
 set_lora_adapter(bb.feature_extractor.ldm_extractor.unet, "Depth")
 bb.feature_extractor.ldm_extractor.engine().graph_max_batch = 0  # profile the stream launches, not a graph replay
 img = torch.rand(args.batch, 3, 512, 512, device=dev)
