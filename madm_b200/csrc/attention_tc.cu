@@ -13,6 +13,7 @@
 // then one softmax / output warpgroup per query tile.
 #include "cvt.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <mutex>
@@ -137,6 +138,8 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_trigger();  // programmatic dependent launch: the prologue above overlapped the previous kernel's tail
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -490,7 +493,8 @@ static const char* fa_launch_t(const FaLaunch& L, cudaStream_t st) {
       return "attention: cudaFuncSetAttribute failed";
     attr = true;
   }
-  fa_tc_kernel<D, NQT, FP16><<<L.grid, C::THREADS, C::SMEM, st>>>(*reinterpret_cast<const FaParams*>(L.params));
+  if (launch_k(fa_tc_kernel<D, NQT, FP16>, L.grid, dim3(C::THREADS), C::SMEM, st, *reinterpret_cast<const FaParams*>(L.params)) != cudaSuccess)
+    return "fa_tc launch failed";
   return cudaGetLastError() == cudaSuccess ? nullptr : "attention: launch failed";
 }
 template <int D, int NQT>

@@ -3,6 +3,7 @@
 // space-to-depth for the stride-2 convs, nearest-2x upsample, and layout conversions.
 #include "cvt.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 
 namespace madm {
 
@@ -151,6 +152,8 @@ const char* f32_to_bf16(const float* x, const float* add, long n, int act, void*
 // ------------------------------------------------------------------ space-to-depth (stride-2 conv input), fp32 -> bf16
 // out[phase][b][y/2][x/2][c], phase = (y&1)*2 + (x&1)
 __global__ void space_to_depth_kernel(const float* __restrict__ x, int B, int H, int W, int C, int fp16, uint16_t* __restrict__ out) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;  // one float4 per thread
   const int Q = C >> 2;
   const long total = long(B) * H * W * Q;
@@ -170,12 +173,14 @@ __global__ void space_to_depth_kernel(const float* __restrict__ x, int B, int H,
 const char* space_to_depth(const float* x, int B, int H, int W, int C, void* out, int fp16, cudaStream_t st) {
   if ((H | W) & 1 || C % 4) return "space_to_depth: H, W must be even and C % 4 == 0";
   const long total = long(B) * H * W * (C / 4);
-  space_to_depth_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(x, B, H, W, C, fp16, reinterpret_cast<uint16_t*>(out));
+  launch_k(space_to_depth_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, x, B, H, W, C, fp16, reinterpret_cast<uint16_t*>(out));
   return cudaGetLastError() == cudaSuccess ? nullptr : "space_to_depth launch failed";
 }
 
 // ------------------------------------------------------------------ nearest 2x upsample, fp32 -> bf16
 __global__ void upsample2x_kernel(const float* __restrict__ x, int B, int H, int W, int C, int fp16, uint16_t* __restrict__ out) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;  // one float4 of the INPUT per thread -> 4 outputs
   const int Q = C >> 2;
   const long total = long(B) * H * W * Q;
@@ -198,12 +203,14 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, int B, int H, int
 const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void* out, int fp16, cudaStream_t st) {
   if (C % 4) return "upsample_nearest2x: C % 4 != 0";
   const long total = long(B) * H * W * (C / 4);
-  upsample2x_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(x, B, H, W, C, fp16, reinterpret_cast<uint16_t*>(out));
+  launch_k(upsample2x_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, x, B, H, W, C, fp16, reinterpret_cast<uint16_t*>(out));
   return cudaGetLastError() == cudaSuccess ? nullptr : "upsample_nearest2x launch failed";
 }
 
 // ------------------------------------------------------------------ nearest 2x upsample of a 16-bit tensor (8 channels per thread)
 __global__ void upsample2x_16_kernel(const uint4* __restrict__ x, int B, int H, int W, int C8, uint4* __restrict__ out) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const long total = long(B) * H * W * C8;
   if (i >= total) return;
@@ -224,8 +231,8 @@ __global__ void upsample2x_16_kernel(const uint4* __restrict__ x, int B, int H, 
 const char* upsample_nearest2x_16(const void* x16, int B, int H, int W, int C, void* out16, cudaStream_t st) {
   if (C % 8) return "upsample_nearest2x_16: C % 8 != 0";
   const long total = long(B) * H * W * (C / 8);
-  upsample2x_16_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x16), B, H, W, C / 8,
-                                                                      reinterpret_cast<uint4*>(out16));
+  launch_k(upsample2x_16_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const uint4*>(x16), B, H, W, C / 8,
+           reinterpret_cast<uint4*>(out16));
   return cudaGetLastError() == cudaSuccess ? nullptr : "upsample_nearest2x_16 launch failed";
 }
 
@@ -287,6 +294,8 @@ const char* decoder_image_pack(const float* img4, int B, int HW, void* rows16, f
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, long split_stride, int M, int N, const float* __restrict__ bias,
                                      const float* __restrict__ rowbias, int rows_per_img, int ld_rowbias, const float* residual, int ldr,
                                      float* out32, int ldo32, uint16_t* out16, int ldo16, int act, int fp16, int res16) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const int Q = N >> 2;
   if (i >= long(M) * Q) return;
@@ -319,9 +328,9 @@ const char* splitk_reduce(const float* part, int splits, long split_stride, int 
                           int act, int fp16, cudaStream_t st, int res16) {
   if (N % 4) return "splitk_reduce: N % 4 != 0";
   const long total = long(M) * (N / 4);
-  splitk_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(part, splits, split_stride, M, N, bias, rowbias, rows_per_img > 0 ? rows_per_img : 1,
-                                                                      ld_rowbias ? ld_rowbias : N, residual, ldr, out32, ldo32,
-                                                                      reinterpret_cast<uint16_t*>(out16), ldo16, act, fp16, res16);
+  launch_k(splitk_reduce_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, part, splits, split_stride, M, N, bias, rowbias,
+           rows_per_img > 0 ? rows_per_img : 1, ld_rowbias ? ld_rowbias : N, residual, ldr, out32, ldo32, reinterpret_cast<uint16_t*>(out16), ldo16,
+           act, fp16, res16);
   return cudaGetLastError() == cudaSuccess ? nullptr : "splitk_reduce launch failed";
 }
 

@@ -15,6 +15,7 @@
 // tiles >= 128 wide run as cta_group::2 pairs (256-row MMAs, each CTA stages half of W).  See DESIGN.md section 5.
 #include "gemm_tc.h"
 #include "cvt.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 #include <mutex>
@@ -216,6 +217,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the tail of the
+  // previous kernel; nothing below may touch global memory before that kernel has completed
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -818,19 +823,23 @@ static const char* launch_bn_s(const GemmLaunch& L, const GemmParams& p, cudaStr
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg<BN, MT, PAIR>::SMEM;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
+    if (pdl_enabled()) {
+      at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.numAttrs = 2;
+    }
     const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, MT, EPI, PAIR>, p);
     if (e == cudaSuccess) return nullptr;
     static thread_local char buf[160];
     snprintf(buf, sizeof(buf), "gemm: cluster launch failed (%s)", cudaGetErrorString(e));
     return buf;
   } else {
-    gemm_tc_kernel<BN, MT, EPI, PAIR><<<L.grid, kThreads, Cfg<BN, MT, PAIR>::SMEM, stream>>>(p);
-    const cudaError_t e = cudaGetLastError();
+    const cudaError_t e = launch_k(gemm_tc_kernel<BN, MT, EPI, PAIR>, L.grid, dim3(kThreads), Cfg<BN, MT, PAIR>::SMEM, stream, p);
     if (e == cudaSuccess) return nullptr;
     static thread_local char buf[160];
     cudaFuncAttributes fa{};

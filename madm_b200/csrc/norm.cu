@@ -4,6 +4,7 @@
 // coalesced along the channel axis; statistics are accumulated in fp32 (sum, sum of squares) per (image, group).
 #include "cvt.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 
 namespace madm {
 
@@ -57,6 +58,8 @@ __device__ __forceinline__ void stv16(uint16_t* dst, const float (&v)[V], int fp
 template <bool IN16>
 __global__ void gn_stats_kernel(const void* __restrict__ x0, int C0, const void* __restrict__ x1, int C1, int HW,
                                 int pix_per_cta, int P, int fp16, float* __restrict__ partial /*[B,slabs,32,2]*/) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   constexpr int V = GnVec<IN16>::V;
   extern __shared__ float sm[];  // [2][P][C]
   const int C = C0 + C1;
@@ -152,6 +155,8 @@ __device__ __forceinline__ void gn_reduce_partials_wide(const float* __restrict_
 // The input may be the channel concat of two producers.
 __global__ void gn_colstats_reduce_kernel(const float* __restrict__ cs0, int C0, const float* __restrict__ cs1, int C1, int nb,
                                           int blocks_per_chunk, float* __restrict__ out /*[B,S,32,2]*/) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   extern __shared__ float sm[];  // [C][2]
   const int chunk = blockIdx.x, S = gridDim.x, b = blockIdx.y;
   const int C = C0 + C1, cpg = C / 32;
@@ -188,6 +193,8 @@ __global__ void gn_colstats_reduce_kernel(const float* __restrict__ cs0, int C0,
 }
 
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int slabs, float* __restrict__ stats /*[B,32,2]*/) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   __shared__ float red[64];
   gn_reduce_partials(partial, blockIdx.x, slabs, red);
   if (threadIdx.x < 64) stats[size_t(blockIdx.x) * 64 + threadIdx.x] = red[threadIdx.x];
@@ -202,6 +209,8 @@ __global__ void gn_apply_kernel(const void* __restrict__ x0, int C0, const void*
                                 int pix_per_cta, int P, const float* __restrict__ partial, int slabs, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int act, int fp16, uint16_t* __restrict__ y,
                                 uint16_t* __restrict__ raw) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   constexpr int V = GnVec<IN16>::V;
   __shared__ float red[64];
   __shared__ float red_tmp[4 * 64];
@@ -304,18 +313,18 @@ const char* groupnorm_stats(const void* x0, int C0, const void* x1, int C1, int 
   int P, threads, ppc, slabs;
   gn_launch_geometry(HW, C, in16, &P, &threads, &ppc, &slabs);
   const size_t smem = size_t(2) * P * C * sizeof(float);
-  if (in16) gn_stats_kernel<true><<<dim3(slabs, B), threads, smem, st>>>(x0, C0, x1, C1, HW, ppc, P, fp16, partial);
-  else gn_stats_kernel<false><<<dim3(slabs, B), threads, smem, st>>>(x0, C0, x1, C1, HW, ppc, P, fp16, partial);
+  if (in16) launch_k(gn_stats_kernel<true>, dim3(slabs, B), dim3(threads), smem, st, x0, C0, x1, C1, HW, ppc, P, fp16, partial);
+  else launch_k(gn_stats_kernel<false>, dim3(slabs, B), dim3(threads), smem, st, x0, C0, x1, C1, HW, ppc, P, fp16, partial);
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_stats launch failed";
 }
 
 const char* groupnorm_finalize_slabs(const float* partial, int B, int slabs, float* stats, cudaStream_t st) {
-  gn_finalize_kernel<<<B, 64, 0, st>>>(partial, slabs, stats);
+  launch_k(gn_finalize_kernel, dim3(B), dim3(64), 0, st, partial, slabs, stats);
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_finalize launch failed";
 }
 
 const char* groupnorm_finalize(const float* partial, int B, int HW, int C, float* stats, cudaStream_t st) {
-  gn_finalize_kernel<<<B, 64, 0, st>>>(partial, groupnorm_slabs(HW, C), stats);
+  launch_k(gn_finalize_kernel, dim3(B), dim3(64), 0, st, partial, groupnorm_slabs(HW, C), stats);
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_finalize launch failed";
 }
 
@@ -331,7 +340,7 @@ const char* groupnorm_colstats_reduce(const float* cs0, int C0, const float* cs1
   if (C % 32 != 0) return "groupnorm: C must be a multiple of 32";
   const int S = groupnorm_colstats_chunks(nblocks);
   const int bpc = (nblocks + S - 1) / S;
-  gn_colstats_reduce_kernel<<<dim3(S, B), 256, size_t(C) * 2 * sizeof(float), st>>>(cs0, C0, cs1, C1, nblocks, bpc, out);
+  launch_k(gn_colstats_reduce_kernel, dim3(S, B), dim3(256), size_t(C) * 2 * sizeof(float), st, cs0, C0, cs1, C1, nblocks, bpc, out);
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_colstats_reduce launch failed";
 }
 
@@ -355,11 +364,11 @@ const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int 
   if (ppc > HW) ppc = HW;
   slabs = (HW + ppc - 1) / ppc;
   if (in16)
-    gn_apply_kernel<true><<<dim3(slabs, B), threads, 0, st>>>(x0, C0, x1, C1, HW, ppc, P, partial, pslabs, gamma, beta, eps, act, fp16,
-                                                              reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
+    launch_k(gn_apply_kernel<true>, dim3(slabs, B), dim3(threads), 0, st, x0, C0, x1, C1, HW, ppc, P, partial, pslabs, gamma, beta, eps, act, fp16,
+             reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
   else
-    gn_apply_kernel<false><<<dim3(slabs, B), threads, 0, st>>>(x0, C0, x1, C1, HW, ppc, P, partial, pslabs, gamma, beta, eps, act, fp16,
-                                                               reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
+    launch_k(gn_apply_kernel<false>, dim3(slabs, B), dim3(threads), 0, st, x0, C0, x1, C1, HW, ppc, P, partial, pslabs, gamma, beta, eps, act, fp16,
+             reinterpret_cast<uint16_t*>(y), reinterpret_cast<uint16_t*>(raw));
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_apply launch failed";
 }
 
@@ -367,6 +376,8 @@ const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int 
 template <bool IN16>
 __global__ void layernorm_kernel(const void* __restrict__ x, int M, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps, int fp16, uint16_t* __restrict__ y) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -422,8 +433,8 @@ const char* layernorm(const void* x, int in16, int M, int C, const float* gamma,
   if (C % 4 != 0 || C > 1280) return "layernorm: C must be a multiple of 4 and <= 1280";
   const int rows_per_cta = 8;
   const unsigned grid = (M + rows_per_cta - 1) / rows_per_cta;
-  if (in16) layernorm_kernel<true><<<grid, rows_per_cta * 32, 0, st>>>(x, M, C, gamma, beta, eps, fp16, reinterpret_cast<uint16_t*>(y));
-  else layernorm_kernel<false><<<grid, rows_per_cta * 32, 0, st>>>(x, M, C, gamma, beta, eps, fp16, reinterpret_cast<uint16_t*>(y));
+  if (in16) launch_k(layernorm_kernel<true>, dim3(grid), dim3(rows_per_cta * 32), 0, st, x, M, C, gamma, beta, eps, fp16, reinterpret_cast<uint16_t*>(y));
+  else launch_k(layernorm_kernel<false>, dim3(grid), dim3(rows_per_cta * 32), 0, st, x, M, C, gamma, beta, eps, fp16, reinterpret_cast<uint16_t*>(y));
   return cudaGetLastError() == cudaSuccess ? nullptr : "layernorm launch failed";
 }
 
