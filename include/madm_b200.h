@@ -241,6 +241,11 @@ int madm_op_pseudo_labels(const float* logits /*[B,C,h,w]*/, int32_t B, int32_t 
 int madm_op_class_mask(const int64_t* label, int64_t n, const int64_t* classes, int32_t k, int64_t* mask, madm_stream stream);
 int madm_op_one_mix(const int64_t* mask, int64_t n, const int64_t* label_a, const int64_t* label_b, int64_t* label_out /*or NULL*/,
                     const float* weight_a, const float* weight_b, float* weight_out /*or NULL*/, madm_stream stream);
+/* FeatureExtractorBackbone.preprocess_image (reference modeling/backbone/feature_extractor.py:140-146, :77-79): T.Resize(backbone_in_size,
+ * BILINEAR) — on tensors with the reference's pinned torchvision 0.16.1 that is F.interpolate(bilinear, align_corners=False) WITHOUT
+ * antialiasing — to Hr x Wr, then the zero padding of ImageList.from_tensors up to Hd x Wd; fp32 planes (B*3 of them). */
+int madm_op_preprocess_image(const float* src /*[planes,Hs,Ws]*/, int32_t planes, int32_t Hs, int32_t Ws, int32_t Hr, int32_t Wr, int32_t Hd,
+                             int32_t Wd, float* dst /*[planes,Hd,Wd]*/, madm_stream stream);
 /* image side of the DACS mixing (reference utils/dacs_transforms.py:98-112 one_mix on `data`, :62-84 gaussian_blur =
  * kornia.filters.GaussianBlur2d(kernel_size, (sigma, sigma)), separable, border 'reflect') */
 int madm_op_image_mix(const int64_t* mask /*[HW] 0/1*/, const float* a /*[C,HW]*/, const float* b, int32_t C, int64_t HW, float* out,

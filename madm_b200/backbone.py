@@ -14,7 +14,6 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib
 from .ldm import BasePromptTimeGenerator, FeatureTaps, LdmDiffusers
@@ -72,13 +71,14 @@ class FeatureExtractorBackbone(_BackboneBase):
         return destination
 
     def preprocess_image(self, img):  # :140-146
-        if not self._slide_inference and tuple(img.shape[-2:]) != self.backbone_in_size:
-            img = F.interpolate(img, size=self.backbone_in_size, mode="bilinear", align_corners=False, antialias=True)
-        h, w = img.shape[-2:]
-        ph, pw = (-h) % self.size_divisibility, (-w) % self.size_divisibility
-        if ph or pw:
-            img = F.pad(img, (0, pw, 0, ph))
-        return img
+        """T.Resize(backbone_in_size, BILINEAR) unless sliding (with the reference's pinned torchvision 0.16.1 a tensor input is NOT
+        antialiased), then ImageList.from_tensors' zero padding to a multiple of 64: one kernel; identity (no launch) at 512 x 512."""
+        resize = not self._slide_inference and tuple(img.shape[-2:]) != self.backbone_in_size
+        h, w = self.backbone_in_size if resize else img.shape[-2:]
+        if not resize and h % self.size_divisibility == 0 and w % self.size_divisibility == 0:
+            return img
+        from . import ops
+        return ops.preprocess_image(img, self.backbone_in_size if resize else None, self.size_divisibility)
 
     def checkpoint_forward_features(self, features, input_image_size, ema_forward=False):  # :148-154
         return self.forward_features(features, input_image_size, ema_forward)

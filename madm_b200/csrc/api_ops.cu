@@ -154,6 +154,12 @@ int madm_op_adamw_step(float* const* param, const float* const* grad, float* con
                  max_norm, static_cast<cudaStream_t>(stream)));
 }
 
+int madm_op_preprocess_image(const float* src, int32_t planes, int32_t Hs, int32_t Ws, int32_t Hr, int32_t Wr, int32_t Hd, int32_t Wd, float* dst,
+                             madm_stream stream) {
+  if (!src || !dst) return fail("madm_op_preprocess_image: null argument");
+  RUN(resize_bilinear_nchw(src, planes, Hs, Ws, Hr, Wr, Hd, Wd, dst, static_cast<cudaStream_t>(stream)));
+}
+
 int madm_op_image_mix(const int64_t* mask, const float* a, const float* b, int32_t C, int64_t HW, float* out, madm_stream stream) {
   if (!mask || !a || !b || !out) return fail("madm_op_image_mix: null argument");
   RUN(image_mix(mask, a, b, C, long(HW), out, static_cast<cudaStream_t>(stream)));

@@ -207,6 +207,39 @@ const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void*
   return cudaGetLastError() == cudaSuccess ? nullptr : "upsample_nearest2x launch failed";
 }
 
+// ------------------------------------------------------------------ image preprocessing: bilinear resize + zero pad (fp32 NCHW)
+// T.Resize(size, BILINEAR) on a tensor with torchvision 0.16.1 (the reference's pinned version: antialias defaults to "warn" = off) is
+// F.interpolate(mode='bilinear', align_corners=False) = ATen upsample_bilinear2d: src = max((dst + 0.5) * in/out - 0.5, 0).  The output
+// may be larger than the resized image: the rest is the zero padding of ImageList.from_tensors(size_divisibility).
+__global__ void resize_bilinear_nchw_kernel(const float* __restrict__ src, int planes, int Hs, int Ws, int Hr, int Wr, int Hd, int Wd, float sy,
+                                            float sx, float* __restrict__ dst) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = long(planes) * Hd * Wd;
+  if (i >= total) return;
+  const int x = int(i % Wd), y = int((i / Wd) % Hd);
+  const long pl = i / (long(Wd) * Hd);
+  float v = 0.f;
+  if (y < Hr && x < Wr) {
+    const float fy = fmaxf((y + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf((x + 0.5f) * sx - 0.5f, 0.f);
+    const int y0 = min(int(fy), Hs - 1), x0 = min(int(fx), Ws - 1);
+    const int y1 = min(y0 + 1, Hs - 1), x1 = min(x0 + 1, Ws - 1);
+    const float ly = fy - float(y0), lx = fx - float(x0), hy = 1.f - ly, hx = 1.f - lx;
+    const float* p = src + pl * long(Hs) * Ws;
+    // same association as ATen: hy * (hx * a + lx * b) + ly * (hx * c + lx * d)
+    v = hy * (hx * __ldg(p + size_t(y0) * Ws + x0) + lx * __ldg(p + size_t(y0) * Ws + x1)) +
+        ly * (hx * __ldg(p + size_t(y1) * Ws + x0) + lx * __ldg(p + size_t(y1) * Ws + x1));
+  }
+  dst[i] = v;
+}
+
+const char* resize_bilinear_nchw(const float* src, int planes, int Hs, int Ws, int Hr, int Wr, int Hd, int Wd, float* dst, cudaStream_t st) {
+  if (Hs < 1 || Ws < 1 || Hr < 1 || Wr < 1 || Hd < Hr || Wd < Wr) return "resize_bilinear: bad geometry";
+  const long total = long(planes) * Hd * Wd;
+  resize_bilinear_nchw_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(src, planes, Hs, Ws, Hr, Wr, Hd, Wd, float(Hs) / float(Hr),
+                                                                            float(Ws) / float(Wr), dst);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "resize_bilinear launch failed";
+}
+
 // ------------------------------------------------------------------ nearest 2x upsample of a 16-bit tensor (8 channels per thread)
 __global__ void upsample2x_16_kernel(const uint4* __restrict__ x, int B, int H, int W, int C8, uint4* __restrict__ out) {
   pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()

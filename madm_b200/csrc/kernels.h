@@ -68,6 +68,9 @@ const char* f32_to_bf16(const float* x, const float* add_or_null, long n, int ac
 const char* space_to_depth(const float* x, int B, int H, int W, int C, void* out_bf16, int fp16, cudaStream_t st);
 // fp32 NHWC [B,H,W,C] -> nearest 2x bf16 [B,2H,2W,C]
 const char* upsample_nearest2x(const float* x, int B, int H, int W, int C, void* out_bf16, int fp16, cudaStream_t st);
+// fp32 planes [planes,Hs,Ws] -> bilinear (align_corners=False, no antialias) to Hr x Wr, written into the top-left corner of zero-filled
+// [planes,Hd,Wd] planes (Hd >= Hr, Wd >= Wr): T.Resize + ImageList.from_tensors padding of FeatureExtractorBackbone.preprocess_image
+const char* resize_bilinear_nchw(const float* src, int planes, int Hs, int Ws, int Hr, int Wr, int Hd, int Wd, float* dst, cudaStream_t st);
 // 16-bit NHWC [B,H,W,C] -> nearest 2x 16-bit [B,2H,2W,C] (the VAE decoder's 16-bit stream)
 const char* upsample_nearest2x_16(const void* x16, int B, int H, int W, int C, void* out16, cudaStream_t st);
 // VAE decoder entry: z = post_quant_conv(sample * inv_scale), a 1x1 conv 4 -> 4 in fp32 (ldm_diffusers.py:319-320); NHWC [M,4]

@@ -206,6 +206,19 @@ def depthwise3x3(x, w9, shift, dilation):
     return out
 
 
+def preprocess_image(img, size, divisibility=64):
+    """T.Resize(size, BILINEAR) (no antialias: torchvision 0.16.1 on tensors) + zero pad to a multiple of `divisibility`
+    (FeatureExtractorBackbone.preprocess_image, feature_extractor.py:140-146).  size=None: pad only."""
+    lib = _lib.load()
+    x = img.to(torch.float32).contiguous()
+    B, Cc, Hs, Ws = x.shape
+    Hr, Wr = (Hs, Ws) if size is None else (int(size[0]), int(size[1]))
+    Hd, Wd = Hr + (-Hr) % divisibility, Wr + (-Wr) % divisibility
+    out = torch.empty(B, Cc, Hd, Wd, dtype=torch.float32, device=x.device)
+    _lib.check(lib.madm_op_preprocess_image(_ptr(x), B * Cc, Hs, Ws, Hr, Wr, Hd, Wd, _ptr(out), _stream()), None, "madm_op_preprocess_image")
+    return out
+
+
 def slide_merge(feats, nwin, wins_yx, Hf, Wf):
     """feats [nwin*n,C,hf,wf] fp32 (window-major), wins_yx [(y1,x1)] in feature pixels -> [n,C,Hf,Wf] mean over covering windows."""
     lib = _lib.load()

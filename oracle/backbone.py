@@ -266,7 +266,8 @@ class AttentionFeatureExtractorBackbone(nn.Module):
 
     def preprocess_image(self, img):                                                  # :140-146
         if not self._slide_inference and tuple(img.shape[-2:]) != self.backbone_in_size:
-            img = F.interpolate(img, size=self.backbone_in_size, mode="bilinear", align_corners=False, antialias=True)
+            # T.Resize(..., BILINEAR) on a tensor: torchvision 0.16.1 (README.md:31) defaults antialias to "warn" = no antialiasing
+            img = F.interpolate(img, size=self.backbone_in_size, mode="bilinear", align_corners=False, antialias=False)
         h, w = img.shape[-2:]
         ph, pw = (-h) % 64, (-w) % 64
         return F.pad(img, (0, pw, 0, ph)) if (ph or pw) else img

@@ -309,3 +309,34 @@ def test_head_argmax_agreement(pair, cuda_device):
     print(f"[{_MODE}] head argmax agreement {100 * agree:.3f} % over {seg_ref.numel()} pixels, {ncls} classes present")
     assert ncls >= 5, "degenerate head: too few classes predicted for the test to be meaningful"
     assert agree >= (0.995 if _MODE == "fp16" else 0.97)
+
+
+@pytest.mark.parametrize("hw", [(384, 640), (600, 800), (512, 512), (250, 1000)])
+def test_preprocess_image_kernel(cuda_device, hw):
+    """Row a-1: T.Resize((512, 512), BILINEAR) without antialiasing (torchvision 0.16.1 on tensors) + zero pad to a multiple of 64,
+    as one CUDA kernel, against F.interpolate / F.pad."""
+    import torch.nn.functional as F
+    from madm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(hw[0])
+    x = torch.rand(2, 3, *hw, device=cuda_device, generator=g)
+    got = ops.preprocess_image(x, (512, 512))
+    ref = F.interpolate(x, size=(512, 512), mode="bilinear", align_corners=False, antialias=False)
+    assert got.shape == ref.shape and (got - ref).abs().max().item() <= 1e-6
+    got = ops.preprocess_image(x, None)  # sliding-window mode: pad only (ImageList.from_tensors(..., 64))
+    ph, pw = (-hw[0]) % 64, (-hw[1]) % 64
+    assert torch.equal(got, F.pad(x, (0, pw, 0, ph)))
+
+
+def test_non_512_input_is_resized(pair, cuda_device):
+    """single_forward on a 384 x 640 image: preprocess (resize kernel) + the path, against the oracle."""
+    from oracle import synthetic
+    from oracle.lora import set_adapter
+    ob, pb = pair
+    img = synthetic.synthetic_images(1, h=384, w=640, seed=17).to(cuda_device)
+    set_adapter(ob.feature_extractor.ldm_extractor.unet, ["Depth"])
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    with torch.no_grad():
+        ref = ob(img, input_modal="others")["output_features"]
+        out = pb(img, input_modal="others")["output_features"]
+    for k in ref:
+        _check("resized/" + k, out[k], ref[k])
