@@ -116,12 +116,15 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float lo
 /* Workspace bytes needed by madm_extract for batch B (all stages). */
 size_t madm_workspace_bytes(madm_ctx* ctx, int32_t B);
 
+#define MADM_FLAG_IMG_NORMALISED 1
 typedef struct madm_extract_args {
   int32_t B;                   /* images (512x512 crops) in this call */
   int32_t stages;              /* MADM_STAGE_* mask; intermediate results live in the workspace between calls */
   int32_t ema;                 /* use ema_feature_projections (ema_forward=True) */
-  int32_t reserved;
-  const float* img;            /* [B,3,512,512] fp32 NCHW in [0,1] (LdmDiffusers.forward input, input_range '-1+1') */
+  int32_t flags;               /* MADM_FLAG_* */
+  const float* img;            /* [B,3,512,512] fp32 NCHW in [0,1] (LdmDiffusers.forward input, input_range '-1+1'); with
+                                  MADM_FLAG_IMG_NORMALISED already in [-1,1]: what the module-level vae_encoder() of the reference
+                                  receives (ldm_diffusers.py:283-311, called from mtmadise.py:254,345,398,463 on colour targets) */
   const float* cond_inputs;    /* [B,77,768] fp32: batched_inputs['cond_inputs'] (ldm_base.py:915-917) */
   const float* cond_emb;       /* [B,1280] fp32: batched_inputs['cond_emb'][:,0] */
   const int64_t* timesteps;    /* [B] int64 device: torch.randint(lo,hi,(B,)) (ldm_diffusers.py:160) */

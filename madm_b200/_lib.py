@@ -17,6 +17,7 @@ STAGE_VAE, STAGE_UNET, STAGE_PROJ, STAGE_ALL = 1, 2, 4, 7
 STAGE_HEAD = 8
 STAGE_DEC, STAGE_ALL_S0 = 16, 23
 VARIANT_BASE, VARIANT_S0 = 0, 1
+FLAG_IMG_NORMALISED = 1
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU = 0, 1, 2, 3
 DTYPE_BF16, DTYPE_FP16 = 0, 1
 
@@ -30,7 +31,7 @@ class MadmTensor(C.Structure):
 
 class MadmExtractArgs(C.Structure):
     _fields_ = [
-        ("B", c_int32), ("stages", c_int32), ("ema", c_int32), ("reserved", c_int32),
+        ("B", c_int32), ("stages", c_int32), ("ema", c_int32), ("flags", c_int32),
         ("img", c_void_p), ("cond_inputs", c_void_p), ("cond_emb", c_void_p), ("timesteps", c_void_p),
         ("shared_noise", c_void_p), ("noisy_latents_in", c_void_p),
         ("out", c_void_p * 4),

@@ -11,7 +11,7 @@ namespace madm {
 // ------------------------------------------------------------------ image -> normalised 3x3 im2col rows (K padded to 64)
 // One thread per output pixel writes its 128-byte row: k = (ky*3+kx)*3 + c for k < 27, zeros after.
 __global__ void image_im2col_kernel(const float* __restrict__ img, int B, int H, int W, int fp16, uint16_t* __restrict__ out,
-                                    int* __restrict__ range_flag) {
+                                    int* __restrict__ range_flag, int normalised) {
   const long idx = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const long total = long(B) * H * W;
   if (idx >= total) return;
@@ -31,7 +31,8 @@ __global__ void image_im2col_kernel(const float* __restrict__ img, int B, int H,
       for (int c = 0; c < 3; ++c) {
         float t = 0.f;
         if (in) {
-          t = (__ldg(base + (size_t(c) * H + yy) * W + xx) - 0.5f) / 0.5f;
+          t = __ldg(base + (size_t(c) * H + yy) * W + xx);
+          if (!normalised) t = (t - 0.5f) / 0.5f;  // input_range '-1+1' (ldm_diffusers.py:145-146); vae_encoder() callers pass [-1,1] already
           if (ky == 1 && kx == 1 && !(t >= -1.0f && t <= 1.0f)) bad = true;
         }
         v[(ky * 3 + kx) * 3 + c] = t;
@@ -53,9 +54,9 @@ __global__ void image_im2col_kernel(const float* __restrict__ img, int B, int H,
   for (int j = 4; j < 8; ++j) o[j] = make_uint4(0u, 0u, 0u, 0u);
 }
 
-const char* image_im2col(const float* img, int B, int H, int W, void* out, int* range_flag, int fp16, cudaStream_t st) {
+const char* image_im2col(const float* img, int B, int H, int W, void* out, int* range_flag, int fp16, cudaStream_t st, int normalised) {
   const long total = long(B) * H * W;
-  image_im2col_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(img, B, H, W, fp16, reinterpret_cast<uint16_t*>(out), range_flag);
+  image_im2col_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(img, B, H, W, fp16, reinterpret_cast<uint16_t*>(out), range_flag, normalised);
   return cudaGetLastError() == cudaSuccess ? nullptr : "image_im2col launch failed";
 }
 

@@ -849,7 +849,7 @@ struct Model {
     B16T col = b.b16(size_t(Bn) * R * R * 64);
     if (dry()) b.emit(nullptr);
     else { bf16* dst = col.p; const int h16 = f16();
-      b.emit([=](cudaStream_t st) { return image_im2col(io->a.img, Bn, R, R, dst, io->a.range_flag, h16, st); }); }
+      b.emit([=](cudaStream_t st) { return image_im2col(io->a.img, Bn, R, R, dst, io->a.range_flag, h16, st, io->a.flags & MADM_FLAG_IMG_NORMALISED); }); }
     // fp16 operands: the residual stream of the 512^2 and 256^2 stages (3/4 of the VAE's bytes) is kept in fp16 like the
     // reference's VAE (AutoencoderKL loaded with torch_dtype=float16, ldm_diffusers.py:246-249); bf16 keeps the fp32 stream.
     const bool s16 = f16() && !getenv("MADM_VAE_STREAM32");

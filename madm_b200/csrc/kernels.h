@@ -53,7 +53,8 @@ const char* flash_attention_tc_launch(const FaLaunch& l, cudaStream_t st);
 
 // ---- elementwise.cu
 // img NCHW fp32 in [0,1] -> (img-0.5)/0.5 -> 3x3 im2col rows [B*H*W, 64] bf16 (27 real columns, tap-major (ky,kx,c))
-const char* image_im2col(const float* img, int B, int H, int W, void* out_bf16, int* range_flag, int fp16, cudaStream_t st);
+// normalised != 0: img already is in [-1,1] (no (img-0.5)/0.5)
+const char* image_im2col(const float* img, int B, int H, int W, void* out_bf16, int* range_flag, int fp16, cudaStream_t st, int normalised = 0);
 // noisy[b,p,:] = sqrt(ac[t_b])*lat[b,p,:] + sqrt(1-ac[t_b])*noise[:,p]  (latents NHWC fp32 [B*HW,4], noise NCHW [4,HW])
 const char* qsample(const float* lat, const float* noise_nchw, const int64_t* t, const float* alphas_cumprod, int B, int HW,
                     float* noisy_nhwc, float* noisy_nchw_or_null, cudaStream_t st);

@@ -179,7 +179,7 @@ class Engine:
     def extract(self, img: Optional[torch.Tensor], cond_inputs: torch.Tensor, cond_emb: torch.Tensor, timesteps: torch.Tensor,
                 shared_noise: torch.Tensor, *, ema: bool = False, stages: int = STAGE_ALL, want_taps: bool = False,
                 want_latents: bool = False, noisy_latents_in: Optional[torch.Tensor] = None, B: Optional[int] = None,
-                out: Optional[Sequence[torch.Tensor]] = None, want_final: bool = False) -> Dict[str, object]:
+                out: Optional[Sequence[torch.Tensor]] = None, want_final: bool = False, img_normalised: bool = False) -> Dict[str, object]:
         if self._packed is None:
             raise _lib.MadmError("Engine.extract called before ensure_packed()")
         B = B if B is not None else (img.shape[0] if img is not None else noisy_latents_in.shape[0])
@@ -204,6 +204,7 @@ class Engine:
         ws = self.workspace(B)
         a = MadmExtractArgs()
         a.B, a.stages, a.ema = B, stages, 1 if ema else 0
+        a.flags = _lib.FLAG_IMG_NORMALISED if img_normalised else 0
         a.img = img.data_ptr() if img is not None else None
         a.cond_inputs, a.cond_emb, a.timesteps = cond_inputs.data_ptr(), cond_emb.data_ptr(), timesteps.data_ptr()
         a.shared_noise = shared_noise.data_ptr() if shared_noise is not None else None

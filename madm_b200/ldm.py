@@ -95,6 +95,8 @@ class LdmDiffusers(nn.Module):
         device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.vae = VAEParams(device=device, with_decoder=bool(vae_decoder_loss))
         self.unet = UNetParams(device=device)
+        import weakref
+        object.__setattr__(self.vae, "_owner", weakref.ref(self))  # lets the module-level vae_encoder(vae, ...) find the engine
         loaded = False
         if self.stable_diffusion_name_or_path and os.path.isdir(self.stable_diffusion_name_or_path):
             for sub, mod in (("vae", self.vae), ("unet", self.unet)):
@@ -156,7 +158,10 @@ class LdmDiffusers(nn.Module):
     def prepare(self, extra: Sequence[Tuple[str, torch.Tensor]] = ()):
         """Bind parameter pointers and (re)pack weights if anything changed (version counters, adapter switch)."""
         eng = self.engine()
-        eng.bind(self.named_engine_tensors() + list(extra))
+        extra = list(extra)
+        if extra:  # remembered, so callers without the projection tensors (forward(), vae_encoder()) do not force a re-bind / repack
+            self._bound_extra = extra
+        eng.bind(self.named_engine_tensors() + self._bound_extra)
         adapter = self.unet.active_adapter()
         eng.ensure_packed(adapter, self.unet.scaling_of(adapter) if adapter else 0.0)
         return eng
@@ -206,6 +211,27 @@ class LdmDiffusers(nn.Module):
         if kwargs.get("return_unet_final_output"):  # ldm_diffusers.py:211-215
             return taps, {"before_vae.decoder": res["unet_sample"], "after_vae.decoder": res["decoded"]}
         return taps
+
+
+def vae_encoder(vae, images, encoder_block_indices=()):
+    """Module-level ``vae_encoder`` of the reference (``ldm_diffusers.py:283-311``), which the meta-arch imports to encode colour
+    targets for the ``vae_decoder_loss`` (``mtmadise.py:15,254,345,398,463``): ``images`` [B,3,512,512] already in [-1,1] ->
+    ``(latents [B,4,64,64] = mean * 0.18215, features)``.  ``vae`` is the ``LdmDiffusers.vae`` holder; the VAE stage of the engine runs."""
+    owner = getattr(vae, "_owner", None)
+    ldm = owner() if owner is not None else None
+    if ldm is None:
+        raise _lib.MadmError("vae_encoder: `vae` must be the .vae of a madm_b200.ldm.LdmDiffusers")
+    idx = list(encoder_block_indices)
+    if idx not in ([], [5]) or (idx == [5] and ldm.variant != "base"):
+        raise NotImplementedError("vae_encoder: encoder_block_indices must be [] (or [5] in the base configuration)")
+    bsz = images.shape[0]
+    eng = ldm.prepare(ldm._bound_extra)
+    dev = ldm.device
+    res = eng.extract(images, torch.zeros(bsz, 77, 768, device=dev), torch.zeros(bsz, 1280, device=dev),
+                      torch.zeros(bsz, dtype=torch.int64, device=dev), ldm.shared_noise, stages=_lib.STAGE_VAE, want_latents=True,
+                      want_taps=bool(idx), img_normalised=True)
+    ldm._serial += 1
+    return res["latents"], ([res["taps"][0]] if idx else [])
 
 
 class ClipFeatureProject(nn.Module):

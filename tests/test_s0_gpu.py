@@ -151,3 +151,21 @@ def test_s0_head_image_to_segmentation(pair, cuda_device):
     agree = (got.argmax(1) == ref.argmax(1)).float().mean().item()
     print(f"[s0] image -> segmentation argmax agreement {agree * 100:.3f} %")
     assert agree >= 0.995
+
+
+def test_module_level_vae_encoder(pair, cuda_device):
+    """`from modeling.meta_arch.ldm_diffusers import vae_encoder` (mtmadise.py:15): the meta-arch encodes colour targets in [-1,1] with
+    the backbone's VAE for the vae_decoder_loss (mtmadise.py:254,345,398,463).  Drop-in: madm_b200.ldm.vae_encoder."""
+    from madm_b200.ldm import vae_encoder
+    from oracle import sd14, synthetic
+    ob, pb = pair
+    x = synthetic.synthetic_images(2, seed=31).to(cuda_device) * 2.0 - 1.0
+    with torch.no_grad():
+        ref, ref_feats = sd14.vae_encoder(ob.feature_extractor.ldm_extractor.vae, x, [])
+        v0 = pb.feature_extractor.ldm_extractor.engine()._versions
+        lat, feats = vae_encoder(pb.feature_extractor.ldm_extractor.vae, x, encoder_block_indices=[])
+    assert feats == [] and ref_feats == [] and lat.shape == (2, 4, 64, 64)
+    assert pb.feature_extractor.ldm_extractor.engine()._versions is v0  # no re-bind / repack between backbone calls and vae_encoder
+    _check("vae_encoder/latents", lat, ref)
+    with pytest.raises(NotImplementedError):
+        vae_encoder(pb.feature_extractor.ldm_extractor.vae, x, encoder_block_indices=[5])  # no encoder tap in the s0 configuration
