@@ -167,7 +167,7 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
         if features.token != (id(ldm), ldm._serial):
             raise RuntimeError("stale FeatureTaps: another forward ran since these taps were produced")
         b = features[0].shape[0]
-        eng = ldm.prepare(self._projection_tensors())
+        eng = ldm.prepare(self._projection_tensors(), ema_unet=ldm._last_ema_unet)  # the context whose workspace holds these taps
         dummy = torch.zeros(b, dtype=torch.int64, device=ldm.device)
         res = eng.extract(None, torch.zeros(b, 77, 768, device=ldm.device), torch.zeros(b, 1280, device=ldm.device), dummy,
                           ldm.shared_noise, ema=bool(ema_forward), stages=_lib.STAGE_PROJ, B=b)

@@ -117,6 +117,8 @@ class LdmDiffusers(nn.Module):
         self.register_buffer("uncond_inputs", uncond_inputs.detach().to(device))
         self.compute_dtype = compute_dtype  # 'fp16' (reference AMP dtype, default) or 'bf16'; see DESIGN.md Numerics
         self._engine: Optional[Engine] = None
+        self._ema_engine: Optional[Engine] = None  # second context for `ema_unet` (CMDISE ema_w_unet, cmdise.py:318-321)
+        self._last_ema_unet = False
         self._bound_extra: List[Tuple[str, torch.Tensor]] = []
         self._serial = 0
         self._freeze()
@@ -144,26 +146,32 @@ class LdmDiffusers(nn.Module):
         return self.shared_noise.device
 
     # ---------------------------------------------------------------------------- engine plumbing
-    def engine(self) -> Engine:
+    def engine(self, ema_unet: bool = False) -> Engine:
+        if ema_unet:
+            if self._ema_engine is None:
+                self._ema_engine = Engine(self.device, self.compute_dtype, self.variant)
+            return self._ema_engine
         if self._engine is None:
             self._engine = Engine(self.device, self.compute_dtype, self.variant)
         return self._engine
 
-    def named_engine_tensors(self) -> List[Tuple[str, torch.Tensor]]:
+    def named_engine_tensors(self, ema_unet: bool = False) -> List[Tuple[str, torch.Tensor]]:
         pre = "feature_extractor.ldm_extractor."
-        out = [(pre + "unet." + n, p.detach()) for n, p in self.unet.named_parameters()]
+        unet = self.ema_unet if ema_unet else self.unet  # the EMA teacher's UNet is bound under the same names in its own context
+        out = [(pre + "unet." + n, p.detach()) for n, p in unet.named_parameters()]
         out += [(pre + "vae." + n, p.detach()) for n, p in self.vae.named_parameters()]
         return out
 
-    def prepare(self, extra: Sequence[Tuple[str, torch.Tensor]] = ()):
+    def prepare(self, extra: Sequence[Tuple[str, torch.Tensor]] = (), ema_unet: bool = False):
         """Bind parameter pointers and (re)pack weights if anything changed (version counters, adapter switch)."""
-        eng = self.engine()
+        eng = self.engine(ema_unet)
         extra = list(extra)
         if extra:  # remembered, so callers without the projection tensors (forward(), vae_encoder()) do not force a re-bind / repack
             self._bound_extra = extra
-        eng.bind(self.named_engine_tensors() + self._bound_extra)
-        adapter = self.unet.active_adapter()
-        eng.ensure_packed(adapter, self.unet.scaling_of(adapter) if adapter else 0.0)
+        eng.bind(self.named_engine_tensors(ema_unet) + self._bound_extra)
+        unet = self.ema_unet if ema_unet else self.unet
+        adapter = unet.active_adapter()
+        eng.ensure_packed(adapter, unet.scaling_of(adapter) if adapter else 0.0)
         return eng
 
     def sample_timesteps(self, batched_inputs, bsz: int) -> torch.Tensor:
@@ -172,8 +180,7 @@ class LdmDiffusers(nn.Module):
 
     def run(self, batched_inputs, input_modal, *, stages, ema_projections=False, extra=(), want_taps=False, want_latents=False,
             timesteps: Optional[torch.Tensor] = None, out=None, **kwargs):
-        if kwargs.get("ema_forward") and hasattr(self, "ema_unet"):
-            raise NotImplementedError("ema_unet (ema_w_unet) is not part of the base hot path")
+        use_ema_unet = bool(kwargs.get("ema_forward")) and hasattr(self, "ema_unet")  # ldm_diffusers.py:182-185
         if "modality_mask" in kwargs:
             raise NotImplementedError("modality_mask needs input_channel_plus != 0, which is outside the shipped configs")
         want_final = bool(kwargs.get("return_unet_final_output"))
@@ -181,7 +188,8 @@ class LdmDiffusers(nn.Module):
             raise NotImplementedError("return_unet_final_output needs vae_decoder_loss=True (the reference raises on decoder_output too)")
         images = batched_inputs["img"]
         bsz = images.shape[0]
-        eng = self.prepare(extra)
+        eng = self.prepare(extra, ema_unet=use_ema_unet)
+        self._last_ema_unet = use_ema_unet
         if timesteps is None:
             timesteps = self.sample_timesteps(batched_inputs, bsz)
         cond_inputs = batched_inputs["cond_inputs"]

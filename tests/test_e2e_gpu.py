@@ -340,3 +340,40 @@ def test_non_512_input_is_resized(pair, cuda_device):
         out = pb(img, input_modal="others")["output_features"]
     for k in ref:
         _check("resized/" + k, out[k], ref[k])
+
+
+def test_ema_unet_teacher(cuda_device):
+    """CMDISE ema_w_unet (cmdise.py:318-321): `ldm_extractor.ema_unet = deepcopy(unet)` is the UNet of `ema_forward=True` calls
+    (ldm_diffusers.py:182-185).  The product keeps a second engine context for it; the student path is unaffected."""
+    import copy
+    from oracle import synthetic
+    from oracle.lora import set_adapter
+    ob = synthetic.build_backbone().to(cuda_device)
+    pb = build_product_backbone(cuda_device)
+    pb.load_state_dict(ob.state_dict(), strict=True)
+    for bb in (ob, pb):  # the same deep copy + the same perturbation on both sides
+        ldm = bb.feature_extractor.ldm_extractor
+        ldm.ema_unet = copy.deepcopy(ldm.unet)
+        g = torch.Generator(device="cuda").manual_seed(77)
+        with torch.no_grad():
+            for n, p in sorted(ldm.ema_unet.named_parameters()):
+                if p.dim() >= 2:
+                    p.mul_(1.0 + 0.05 * torch.randn(p.shape, device=p.device, generator=g))
+    set_adapter(ob.feature_extractor.ldm_extractor.unet, ["Depth"])
+    set_adapter(ob.feature_extractor.ldm_extractor.ema_unet, ["Depth"])
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.ema_unet, "Depth")
+    img = synthetic.synthetic_images(1, seed=41).to(cuda_device)
+    with torch.no_grad():
+        ref_t = ob(img, input_modal="others", ema_forward=True)["output_features"]
+        ref_s = ob(img, input_modal="others")["output_features"]
+        out_t = pb(img, input_modal="others", ema_forward=True)["output_features"]
+        out_s = pb(img, input_modal="others")["output_features"]
+    global _MODE
+    _MODE = "fp16"
+    for k in ref_t:
+        _check("ema_unet/teacher/" + k, out_t[k], ref_t[k])
+        _check("ema_unet/student/" + k, out_s[k], ref_s[k])
+    assert max_rel(out_t["s3"], out_s["s3"]) > 5e-2  # the two UNets really differ
+    del pb, ob
+    torch.cuda.empty_cache()
