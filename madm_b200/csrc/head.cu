@@ -124,12 +124,15 @@ __global__ void __launch_bounds__(128) depthwise3x3_nhwc_kernel(const uint16_t* 
     row[1] = __ldg(reinterpret_cast<const uint4*>(p));
     row[2] = xr ? __ldg(reinterpret_cast<const uint4*>(p + size_t(dil) * C)) : zero;
   };
-  uint4 up[3], mid[3], dn[3], nx[3];
+  // Two rows are in flight beyond the three an output needs (6 x 16 B per thread): at ~150 registers only 12 warps are resident per SM, so
+  // memory-level parallelism has to come from each thread (one row ahead: 2.0 TB/s on the 512^2 grid of the s0 head).
+  uint4 up[3], mid[3], dn[3], n1[3], nx[3];
   load_row(r - dil, up);
   load_row(r, mid);
   load_row(r + dil, dn);
+  load_row(r + 2 * dil, n1);
   for (int y = r; y < H; y += dil) {
-    load_row(y + 2 * dil, nx);  // one row ahead of the one this output needs: its latency hides behind the 72 FMAs below
+    load_row(y + 3 * dil, nx);  // two rows ahead of the one this output needs: the latency hides behind two iterations of 72 FMAs
     float acc[8];
 #pragma unroll
     for (int t = 0; t < 8; ++t) acc[t] = sh[t];
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(128) depthwise3x3_nhwc_kernel(const uint16_t* 
     pk.z = pack2_16(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f), fp16); pk.w = pack2_16(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f), fp16);
     *reinterpret_cast<uint4*>(dst + (size_t(b) * H * W + size_t(y) * W + x) * C + c) = pk;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) { up[kx] = mid[kx]; mid[kx] = dn[kx]; dn[kx] = nx[kx]; }
+    for (int kx = 0; kx < 3; ++kx) { up[kx] = mid[kx]; mid[kx] = dn[kx]; dn[kx] = n1[kx]; n1[kx] = nx[kx]; }
   }
 }
 
