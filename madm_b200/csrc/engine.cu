@@ -1628,6 +1628,10 @@ int madm_extract(madm_ctx* ctx, const madm_extract_args* a, madm_stream stream) 
   if (a->B < 1) return set_err(ctx, MADM_EINVAL, "madm_extract: B must be >= 1");
   if (!a->packed || !a->workspace) return set_err(ctx, MADM_ESTATE, "madm_extract: packed arena and workspace are required");
   if ((a->stages & MADM_STAGE_VAE) && !a->img) return set_err(ctx, MADM_EINVAL, "madm_extract: img is null");
+  if ((a->stages & MADM_STAGE_DEC) && ctx->variant != MADM_VARIANT_S0)
+    return set_err(ctx, MADM_EINVAL, "madm_extract: MADM_STAGE_DEC needs madm_set_variant(MADM_VARIANT_S0)");
+  if ((a->unet_sample || a->decoded || a->decoded_raw) && !(a->stages & MADM_STAGE_DEC))
+    return set_err(ctx, MADM_EINVAL, "madm_extract: unet_sample / decoded / decoded_raw are outputs of MADM_STAGE_DEC");
   if ((a->stages & MADM_STAGE_UNET) && (!a->cond_inputs || !a->cond_emb || !a->timesteps || (!a->shared_noise && !a->noisy_latents_in)))
     return set_err(ctx, MADM_EINVAL, "madm_extract: conditioning / timesteps / shared_noise are required for the UNet stage");
   int rc = ensure_layout(ctx);

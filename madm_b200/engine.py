@@ -226,7 +226,8 @@ class Engine:
                 a.taps[i] = t.data_ptr()
             if self.variant == "s0":  # first feature = decoder_output (ldm_diffusers.py:199), written by the decoder stage
                 a.taps[0] = None
-                a.decoded_raw = taps[0].data_ptr()
+                if stages & STAGE_DEC:
+                    a.decoded_raw = taps[0].data_ptr()
             res["taps"] = taps
         if want_latents:
             res["latents"] = torch.empty(B, 4, 64, 64, dtype=torch.float32, device=dev)

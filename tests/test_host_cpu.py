@@ -34,6 +34,31 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(_lib.MadmProfile) == 5 * (32 + 8 + 3 * 8)
 
 
+def test_ctypes_structs_match_the_compiled_header(tmp_path):
+    """sizeof / offsetof of the POD structs as gcc lays them out from include/madm_b200.h == the ctypes mirrors in madm_b200/_lib.py."""
+    import ctypes as C
+    import subprocess
+    from madm_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "madm_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(madm_tensor), sizeof(madm_extract_args), sizeof(madm_gemm_seg), sizeof(madm_gemm_args),
+         sizeof(madm_profile), offsetof(madm_extract_args, out), offsetof(madm_extract_args, packed), offsetof(madm_extract_args, logits),
+         offsetof(madm_extract_args, decoded_raw));
+  return 0;
+}
+''')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    A = _lib.MadmExtractArgs
+    want = [C.sizeof(_lib.MadmTensor), C.sizeof(A), C.sizeof(_lib.MadmGemmSeg), C.sizeof(_lib.MadmGemmArgs), C.sizeof(_lib.MadmProfile),
+            A.out.offset, A.packed.offset, A.logits.offset, A.decoded_raw.offset]
+    assert got == want, (got, want)
+
+
 def test_create_without_gpu_fails_loudly():
     """No CPU fallback: without a CUDA device madm_create must fail with a message, and the Engine must raise."""
     if torch.cuda.is_available():
