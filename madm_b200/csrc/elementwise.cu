@@ -313,7 +313,7 @@ __global__ void decoder_image_pack_kernel(const float4* __restrict__ img4, int H
       dst[0] = v.x; dst[HW] = v.y; dst[2 * size_t(HW)] = v.z;
     }
   }
-  rows[t] = o;
+  if (rows) rows[t] = o;
 }
 
 const char* decoder_image_pack(const float* img4, int B, int HW, void* rows16, float* clipped, float* raw, int fp16, cudaStream_t st) {

@@ -1093,13 +1093,14 @@ struct Model {
       d.w = b.pw(b.conv_w(dc + "conv_out", 3, 128, 9)); d.bias = P(dc + "conv_out.bias", 3); d.out_f32 = img.p; d.ldo32 = 4;
       b.gemm(d); }
     b.free(n);
+    // the decoded image stays as fp32 [B*512*512][4] (3 used): the s0 projection consumes it directly (build_proj, 3-channel input)
     enc_tap = Act(); enc_tap.B = Bn; enc_tap.H = 512; enc_tap.W = 512; enc_tap.C = 3;
-    enc_tap.h = b.b16(size_t(M) * 64);
-    if (dry()) b.emit(nullptr);
-    else { const float* src = img.p; bf16* dst = enc_tap.h.p;
-      b.emit([=](cudaStream_t st) { return decoder_image_pack(src, Bn, 512 * 512, dst, io->a.decoded, io->a.decoded_raw, h16, st); }, false, MADM_KIND_ELEMENTWISE,
-             0.0, double(M) * (16 + 128)); }
-    b.free(img);
+    enc_tap.f = img;
+    if (dry()) b.emit(nullptr, true);
+    else { const float* src = img.p;
+      b.emit([=](cudaStream_t st) -> const char* {
+        if (!io->a.decoded && !io->a.decoded_raw) return nullptr;
+        return decoder_image_pack(src, Bn, 512 * 512, nullptr, io->a.decoded, io->a.decoded_raw, h16, st); }, true); }
     b.pin(enc_tap);
   }
 
@@ -1118,18 +1119,40 @@ struct Model {
       if (!w1 || !w3) b.fail(MADM_ENOTFOUND, "parameter not registered: " + p + "conv1.weight / conv3.weight");
       const int Bn = x.B, H = x.H, W = x.W, Cin = x.C, Cb = int(w1->shape[0]), Cout = int(w3->shape[0]);
       if (int(w1->shape[1]) != Cin || Cb % 64 != 0 || Cout % 64 != 0) b.fail(MADM_EINVAL, "feature projection " + std::to_string(i) + ": unsupported channels");
-      // a narrow input (the 3-channel decoded image of the s0 variant) is a zero-padded 64-wide operand row; weights padded alike
-      const int Cop = Cin < 64 ? 64 : Cin, Cpad = Cin < 64 ? Cin : 0;
       const long M = x.M();
       const bool shortcut = Cin != Cout;
+      // The 3-channel decoded image of the s0 variant: its K = 3 1x1 convs are not GEMMs.  conv1 -> GN -> ReLU is one elementwise pass with
+      // GroupNorm statistics derived from the image's moments, and the shortcut branch is recomputed inside the final pass (norm.cu).
+      const bool rgb3 = Cin == 3;
+      if (Cin < 64 && !rgb3) b.fail(MADM_EINVAL, "feature projection " + std::to_string(i) + ": input channels must be 3 or a multiple of 64");
+      F32T mom, coef1, coefs;
+      const float* img4 = x.f.p;
+      if (rgb3) {
+        if (!shortcut) b.fail(MADM_EINVAL, "feature projection: a 3-channel input needs a shortcut conv");
+        mom = b.f32(size_t(image_moments_floats(Bn)));
+        coef1 = b.f32(size_t(Bn) * Cb * 4);
+        coefs = b.f32(size_t(Bn) * Cout * 4);
+        const int HWi = H * W;
+        float* mp = mom.p; float* c1p = coef1.p; float* csp = coefs.p;
+        const float* w1p = P(p + "conv1.weight", int64_t(Cb) * 3); const float* g1 = P(p + "conv1.norm.weight", Cb); const float* b1 = P(p + "conv1.norm.bias", Cb);
+        const float* wsp = P(p + "shortcut.weight", int64_t(Cout) * 3); const float* gsp = P(p + "shortcut.norm.weight", Cout);
+        const float* bsp = P(p + "shortcut.norm.bias", Cout);
+        b.emit([=](cudaStream_t st) { return image_moments(img4, Bn, HWi, mp, st); }, false, MADM_KIND_GROUPNORM, 0.0, double(M) * 16);
+        b.emit([=](cudaStream_t st) { return c3_gn_coeffs(mp, w1p, g1, b1, 1e-5f, Bn, HWi, Cb, c1p, st); }, false, MADM_KIND_GROUPNORM, 0.0, 0.0);
+        b.emit([=](cudaStream_t st) { return c3_gn_coeffs(mp, wsp, gsp, bsp, 1e-5f, Bn, HWi, Cout, csp, st); }, false, MADM_KIND_GROUPNORM, 0.0, 0.0);
+      }
       // every GroupNorm of the bottleneck takes its statistics from the producing GEMM's epilogue
-      Act c1 = b.act(Bn, H, W, Cb, false, true);
-      { GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cop); d.M = int(M); d.N = Cb; d.Nw = Cb;
-        d.w = b.pw(b.conv_w(p + "conv1", Cb, Cin, 1, Cpad)); d.out_bf16 = c1.h.p; d.ldo16 = Cb; b.attach_colstats(c1, d);
-        b.gemm(d, 2.0 * double(M) * Cb * Cin); }
       B16T a1 = b.b16(size_t(M) * Cb);
-      b.groupnorm(c1, nullptr, p + "conv1.norm", 1e-5f, ACT_RELU, a1.p, nullptr, /*in16=*/true);
-      b.free(c1);
+      if (rgb3) {
+        bf16* a1p = a1.p; const float* c1p = coef1.p; const int HWi = H * W; const int h16 = f16();
+        b.emit([=](cudaStream_t st) { return c3_conv_gn_relu(img4, c1p, Bn, HWi, Cb, a1p, h16, st); }, false, MADM_KIND_GROUPNORM, 0.0, double(M) * (16 + 2.0 * Cb));
+      } else {
+        Act c1 = b.act(Bn, H, W, Cb, false, true);
+        { GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cin); d.M = int(M); d.N = Cb; d.Nw = Cb;
+          d.w = b.pw(b.conv_w(p + "conv1", Cb, Cin, 1)); d.out_bf16 = c1.h.p; d.ldo16 = Cb; b.attach_colstats(c1, d); b.gemm(d); }
+        b.groupnorm(c1, nullptr, p + "conv1.norm", 1e-5f, ACT_RELU, a1.p, nullptr, /*in16=*/true);
+        b.free(c1);
+      }
       Act c2 = b.act(Bn, H, W, Cb, false, true);
       { GemmDesc d; d.seg[0] = Builder::seg_3x3(a1.p, Bn, H, W, Cb); d.M = int(M); d.N = Cb; d.Nw = Cb;
         d.w = b.pw(b.conv_w(p + "conv2", Cb, Cb, 9)); d.out_bf16 = c2.h.p; d.ldo16 = Cb; b.attach_colstats(c2, d); b.gemm(d); }
@@ -1142,16 +1165,15 @@ struct Model {
         d.w = b.pw(b.conv_w(p + "conv3", Cout, Cb, 1)); d.out_f32 = c3.f.p; d.ldo32 = Cout; b.attach_colstats(c3, d); b.gemm(d); }
       b.free(a2);
       Act sc;
-      if (shortcut) {
+      if (shortcut && !rgb3) {
         sc = b.act(Bn, H, W, Cout, true, false);
-        GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cop); d.M = int(M); d.N = Cout; d.Nw = Cout;
-        d.w = b.pw(b.conv_w(p + "shortcut", Cout, Cin, 1, Cpad)); d.out_f32 = sc.f.p; d.ldo32 = Cout; b.attach_colstats(sc, d);
-        b.gemm(d, 2.0 * double(M) * Cout * Cin);
+        GemmDesc d; d.seg[0] = Builder::seg_1x1(x.h.p, Bn, H, W, Cin); d.M = int(M); d.N = Cout; d.Nw = Cout;
+        d.w = b.pw(b.conv_w(p + "shortcut", Cout, Cin, 1)); d.out_f32 = sc.f.p; d.ldo32 = Cout; b.attach_colstats(sc, d); b.gemm(d);
       }
       const int HW = H * W;
       float* st3 = b.new_stats(1);
-      float* sts = shortcut ? b.new_stats(1) : nullptr;
-      const float* c3p = c3.f.p; const float* scp = shortcut ? sc.f.p : x.f.p;
+      float* sts = (shortcut && !rgb3) ? b.new_stats(1) : nullptr;
+      const float* c3p = c3.f.p; const float* scp = rgb3 ? nullptr : (shortcut ? sc.f.p : x.f.p);
       const double pel = double(Bn) * HW * Cout;
       auto tail_stats = [&](const Act& t, const float* src, float* dst) {  // [B,32,2] group sums of a fp32 [M,Cout] tensor
         if (t.has_cs) {
@@ -1168,18 +1190,26 @@ struct Model {
         }
       };
       tail_stats(c3, c3p, st3);
-      if (shortcut) tail_stats(sc, scp, sts);
+      if (shortcut && !rgb3) tail_stats(sc, scp, sts);
       const float* g3 = P(p + "conv3.norm.weight", Cout); const float* b3 = P(p + "conv3.norm.bias", Cout);
       const float* gs = shortcut ? P(p + "shortcut.norm.weight", Cout) : nullptr;
       const float* bs = shortcut ? P(p + "shortcut.norm.bias", Cout) : nullptr;
       if (dry()) b.emit(nullptr);
-      else b.emit([=](cudaStream_t st) -> const char* {
+      else if (rgb3) {
+        const float* csp = coefs.p;
+        b.emit([=](cudaStream_t st) -> const char* {
+          float* dst = io->a.out[i];
+          if (!dst) return "madm_extract: output pointer is null";
+          return gn_add_relu_nchw_c3(c3p, st3, g3, b3, img4, csp, 1e-5f, Bn, HW, Cout, dst, st);
+        }, false, MADM_KIND_GROUPNORM, 0.0, pel * 8);
+      } else b.emit([=](cudaStream_t st) -> const char* {
         float* dst = io->a.out[i];
         if (!dst) return "madm_extract: output pointer is null";
         return gn_add_relu_nchw(c3p, st3, g3, b3, scp, sts, gs, bs, 1e-5f, Bn, HW, Cout, dst, st);
       }, false, MADM_KIND_GROUPNORM, 0.0, pel * 12);
       b.free(c3);
-      if (shortcut) b.free(sc);
+      if (shortcut && !rgb3) b.free(sc);
+      if (rgb3) { b.free(mom); b.free(coef1); b.free(coefs); }
     }
   }
 

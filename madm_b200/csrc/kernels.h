@@ -34,6 +34,18 @@ const char* gn_add_relu_nchw(const float* a, const float* stats_a, const float* 
                              const float* stats_s, const float* gs, const float* bs, float eps, int B, int HW, int C,
                              float* out_nchw, cudaStream_t st);
 
+// 3-channel input of the s0 projection: image moments -> analytic GroupNorm statistics of its K = 3 1x1 convs
+int image_moments_floats(int B);
+const char* image_moments(const float* img4 /*[B*HW][4]*/, int B, int HW, float* partial /*image_moments_floats(B)*/, cudaStream_t st);
+// coef[B][C][4] = (a0, a1, a2, d) with GN32(conv1x1(x; w [C][3]))_c = a . x + d
+const char* c3_gn_coeffs(const float* mom, const float* w, const float* gamma, const float* beta, float eps, int B, int HW, int C, float* coef,
+                         cudaStream_t st);
+// out16[B*HW, C] = relu(a_c . x + d_c) in one pass
+const char* c3_conv_gn_relu(const float* img4, const float* coef, int B, int HW, int C, void* out16, int fp16, cudaStream_t st);
+// out NCHW = relu(GN(a; stats_a) + as_c . x + ds_c): the shortcut branch recomputed from the image
+const char* gn_add_relu_nchw_c3(const float* a, const float* stats_a, const float* ga, const float* ba, const float* img4, const float* coef_s, float eps,
+                                int B, int HW, int C, float* out_nchw, cudaStream_t st);
+
 // ---- attention.cu : O[b, i, h*d:(h+1)*d] = softmax(Q K^T * scale) V per (image, head); bf16 in/out, fp32 softmax
 const char* flash_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
                             int B, int heads, int d, int Nq, int Nk, long q_bstride, long kv_bstride, long o_bstride,

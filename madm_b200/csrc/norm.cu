@@ -545,4 +545,155 @@ const char* gn_add_relu_nchw(const float* a, const float* stats_a, const float* 
   return cudaGetLastError() == cudaSuccess ? nullptr : "gn_add_relu_nchw launch failed";
 }
 
+// ---------------------------------------------------------------------------------------------- 3-channel input of the s0 projection
+// Bottleneck(3 -> Cb -> Cout) on the decoded image: its two 1x1 convs have K = 3.  They are not GEMMs: a 1x1 conv of a
+// 3-channel image is 3 FMAs per output, and the GroupNorm statistics of y_c = w_c . x follow from the image's first and second moments,
+//     sum_p y_c = w_c . (sum_p x),     sum_p y_c^2 = w_c^T (sum_p x x^T) w_c,
+// so `conv1 -> GN -> ReLU` is ONE elementwise pass writing the 16-bit operand of conv2 (no conv output, no statistics pass), and the
+// shortcut branch `conv -> GN` is recomputed from the image inside the block's final pass instead of being stored as a 1 GB fp32 tensor.
+static constexpr int kMomSlabs = 64;  // partial moment sums per image: [B][64][12] (9 used), reduced in fixed order by the consumers
+
+__global__ void __launch_bounds__(256) image_moments_kernel(const float4* __restrict__ img4, int HW, float* __restrict__ partial) {
+  const int b = blockIdx.y, slab = blockIdx.x;
+  const int per = (HW + kMomSlabs - 1) / kMomSlabs;
+  const int p0 = slab * per, p1 = min(HW, p0 + per);
+  float m[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // x y z xx xy xz yy yz zz
+  for (int p = p0 + threadIdx.x; p < p1; p += 256) {
+    const float4 v = __ldg(img4 + size_t(b) * HW + p);
+    m[0] += v.x; m[1] += v.y; m[2] += v.z;
+    m[3] = fmaf(v.x, v.x, m[3]); m[4] = fmaf(v.x, v.y, m[4]); m[5] = fmaf(v.x, v.z, m[5]);
+    m[6] = fmaf(v.y, v.y, m[6]); m[7] = fmaf(v.y, v.z, m[7]); m[8] = fmaf(v.z, v.z, m[8]);
+  }
+  __shared__ float red[9][256];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) red[k][threadIdx.x] = m[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {  // fixed-order tree
+    if (threadIdx.x < s) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 9) partial[(size_t(b) * kMomSlabs + slab) * 12 + threadIdx.x] = red[threadIdx.x][0];
+}
+
+// Per image and channel: GroupNorm(32) of y = W x (W fp32 [C][3]) folded into y_norm_c = a . x + d  ->  coef[b][c] = (a0, a1, a2, d).
+// grid = B, block = C threads.  The moments are reduced in fixed order, the statistics evaluated in double.
+__global__ void c3_gn_coeffs_kernel(const float* __restrict__ partial, const float* __restrict__ w, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, float eps, int HW, int C, float4* __restrict__ coef) {
+  __shared__ double mom[9];
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c < 9) {
+    double acc = 0.0;
+    for (int sl = 0; sl < kMomSlabs; ++sl) acc += double(partial[(size_t(b) * kMomSlabs + sl) * 12 + c]);
+    mom[c] = acc / double(HW);
+  }
+  __syncthreads();
+  if (c >= C) return;
+  const double* mu = mom;       // E[x]
+  const double* S = mom + 3;    // E[x x^T]: xx xy xz yy yz zz
+  const int cpg = C / 32, g0 = (c / cpg) * cpg;
+  double m1 = 0.0, m2 = 0.0;
+  for (int k = g0; k < g0 + cpg; ++k) {
+    const double wx = w[k * 3], wy = w[k * 3 + 1], wz = w[k * 3 + 2];
+    m1 += wx * mu[0] + wy * mu[1] + wz * mu[2];
+    m2 += wx * wx * S[0] + 2.0 * wx * wy * S[1] + 2.0 * wx * wz * S[2] + wy * wy * S[3] + 2.0 * wy * wz * S[4] + wz * wz * S[5];
+  }
+  const double mean = m1 / cpg;
+  const double var = fmax(m2 / cpg - mean * mean, 0.0);
+  const double sc = double(gamma[c]) / sqrt(var + double(eps));
+  coef[size_t(b) * C + c] = make_float4(float(sc * w[c * 3]), float(sc * w[c * 3 + 1]), float(sc * w[c * 3 + 2]), float(double(beta[c]) - mean * sc));
+}
+
+// out16[b, p, c] = relu(a_c . x + d_c)  = relu(GN(conv1x1(x)))  for the 3-channel image x (img4: fp32 [B*HW][4], 3 used)
+__global__ void __launch_bounds__(256) c3_conv_gn_relu_kernel(const float4* __restrict__ img4, const float4* __restrict__ coef, int HW, int C,
+                                                              int pix_per_cta, int fp16, uint16_t* __restrict__ out16) {
+  const int b = blockIdx.y;
+  const int Q = C >> 3, q = threadIdx.x % Q, pl = threadIdx.x / Q, P = 256 / Q;
+  float4 cf[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) cf[t] = __ldg(coef + size_t(b) * C + q * 8 + t);
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  for (int p = p0 + pl; p < p1; p += P) {
+    const float4 x = __ldg(img4 + size_t(b) * HW + p);
+    float o[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) o[t] = fmaxf(fmaf(cf[t].x, x.x, fmaf(cf[t].y, x.y, fmaf(cf[t].z, x.z, cf[t].w))), 0.f);
+    uint4 pk;
+    pk.x = pack2_16(o[0], o[1], fp16); pk.y = pack2_16(o[2], o[3], fp16); pk.z = pack2_16(o[4], o[5], fp16); pk.w = pack2_16(o[6], o[7], fp16);
+    *reinterpret_cast<uint4*>(out16 + (size_t(b) * HW + p) * C + q * 8) = pk;
+  }
+}
+
+const char* image_moments(const float* img4, int B, int HW, float* partial, cudaStream_t st) {
+  image_moments_kernel<<<dim3(kMomSlabs, B), 256, 0, st>>>(reinterpret_cast<const float4*>(img4), HW, partial);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "image_moments launch failed";
+}
+int image_moments_floats(int B) { return B * kMomSlabs * 12; }
+
+const char* c3_gn_coeffs(const float* mom, const float* w, const float* gamma, const float* beta, float eps, int B, int HW, int C, float* coef,
+                         cudaStream_t st) {
+  if (C % 32 != 0 || C > 1024) return "c3_gn_coeffs: C must be a multiple of 32, at most 1024";
+  c3_gn_coeffs_kernel<<<B, C < 32 ? 32 : C, 0, st>>>(mom, w, gamma, beta, eps, HW, C, reinterpret_cast<float4*>(coef));
+  return cudaGetLastError() == cudaSuccess ? nullptr : "c3_gn_coeffs launch failed";
+}
+
+const char* c3_conv_gn_relu(const float* img4, const float* coef, int B, int HW, int C, void* out16, int fp16, cudaStream_t st) {
+  if (C % 32 != 0 || C > 1024 || 256 % (C / 8) != 0) return "c3_conv_gn_relu: C must be a multiple of 32 with C/8 dividing 256";
+  const int ppc = 1024;
+  c3_conv_gn_relu_kernel<<<dim3((HW + ppc - 1) / ppc, B), 256, 0, st>>>(reinterpret_cast<const float4*>(img4), reinterpret_cast<const float4*>(coef),
+                                                                       HW, C, ppc, fp16, reinterpret_cast<uint16_t*>(out16));
+  return cudaGetLastError() == cudaSuccess ? nullptr : "c3_conv_gn_relu launch failed";
+}
+
+// Final pass of the bottleneck with the shortcut branch recomputed from the 3-channel image:
+// out[b, c, p] = relu(GN(a)[b, p, c] + (as_c . x[b, p] + ds_c))  ->  fp32 NCHW   (coef_s = the shortcut's folded conv + GroupNorm)
+__global__ void gn_add_relu_nchw_c3_kernel(const float* __restrict__ a, const float* __restrict__ stats_a, const float* __restrict__ ga,
+                                           const float* __restrict__ ba, const float4* __restrict__ img4, const float4* __restrict__ coef_s, float eps,
+                                           int HW, int C, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const int p0 = blockIdx.x * 32;
+  const int cpg = C / 32;
+  const float inv_n = 1.0f / (float(HW) * float(cpg));
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = c0 + tx;
+  const int g = c / cpg;
+  float sca, sha;
+  {
+    const float mean = stats_a[(size_t(b) * 32 + g) * 2] * inv_n;
+    const float var = fmaxf(stats_a[(size_t(b) * 32 + g) * 2 + 1] * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    sca = rstd * ga[c];
+    sha = ba[c] - mean * sca;
+  }
+  const float4 cs = __ldg(coef_s + size_t(b) * C + c);
+  const float sh = sha + cs.w;
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r;
+    float v = 0.f;
+    if (p < HW) {
+      const float4 x = __ldg(img4 + size_t(b) * HW + p);
+      v = fmaxf(fmaf(a[(size_t(b) * HW + p) * C + c], sca, fmaf(cs.x, x.x, fmaf(cs.y, x.y, fmaf(cs.z, x.z, sh)))), 0.f);
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + tx;
+    if (p < HW) out[(size_t(b) * C + c0 + r) * HW + p] = tile[tx][r];
+  }
+}
+
+const char* gn_add_relu_nchw_c3(const float* a, const float* stats_a, const float* ga, const float* ba, const float* img4, const float* coef_s, float eps,
+                                int B, int HW, int C, float* out, cudaStream_t st) {
+  if (C % 32 != 0) return "gn_add_relu_nchw_c3: C must be a multiple of 32";
+  dim3 grid((HW + 31) / 32, C / 32, B);
+  gn_add_relu_nchw_c3_kernel<<<grid, dim3(32, 8), 0, st>>>(a, stats_a, ga, ba, reinterpret_cast<const float4*>(img4),
+                                                          reinterpret_cast<const float4*>(coef_s), eps, HW, C, out);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "gn_add_relu_nchw_c3 launch failed";
+}
+
 }  // namespace madm
