@@ -580,7 +580,7 @@ struct Model {
   // for the plain residual); out16_only then also drops the fp32 copy of the output.
   Act resblock(const std::string& p, const Act& x0, const Act* x1, int Cout, float eps, bool has_temb, bool want_b16, bool want_s2d = false,
                bool out16_only = false) {
-    if (getenv("MADM_NO_S2D_FUSE")) want_s2d = false;
+    if (getenv("MADM_NO_S2D_FUSE") && !out16_only) want_s2d = false;  // (debug switch; a 16-bit-only output has no fp32 copy to convert later)
     const int Bn = x0.B, H = x0.H, W = x0.W, Cin = x0.C + (x1 ? x1->C : 0);
     const bool shortcut = Cin != Cout;
     const bool in16 = x0.f.bytes == 0 && x0.h.bytes != 0;  // (valid in every builder mode: sizes, not pointers)
@@ -743,6 +743,7 @@ struct Model {
     if (x.h_s2d) {  // the producer's epilogue already wrote the space-to-depth operand
       s2dp = x.h.p;
     } else {
+      if (x.f.bytes == 0) b.fail(MADM_EINVAL, "downsample: the input has neither a space-to-depth operand nor an fp32 copy");
       s2d = b.b16(size_t(x.M()) * C);
       s2dp = s2d.p;
       const float* src = x.f.p; bf16* dst = s2d.p;
