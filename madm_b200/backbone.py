@@ -8,9 +8,8 @@ The forward pass is one ``madm_extract`` call: VAE encode -> q-sample -> UNet wi
 projections, all in the CUDA engine.  There is no PyTorch/eager fallback.
 """
 import logging
-import math
 from collections import OrderedDict
-from typing import Dict, List, Optional, Sequence, Tuple, Union
+from typing import List, Tuple, Union
 
 import torch
 import torch.nn as nn

@@ -5,10 +5,9 @@ import ctypes as C
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
-import torch.nn as nn
 
 from . import _lib
-from ._lib import MadmExtractArgs, MadmTensor, STAGE_ALL, STAGE_ALL_S0, STAGE_DEC, STAGE_HEAD, STAGE_PROJ, STAGE_UNET, STAGE_VAE
+from ._lib import MadmExtractArgs, MadmTensor, STAGE_ALL, STAGE_ALL_S0, STAGE_DEC, STAGE_HEAD, STAGE_PROJ
 
 TAP_SHAPES = ((512, 128), (320, 64), (640, 32), (1280, 16))  # enc tap, unet taps (C, HW side)
 OUT_SIDES = (128, 64, 32, 16)                                  # s2..s5

@@ -8,14 +8,12 @@ Same constructor keywords, ``forward(input_dict)`` contract and ``state_dict`` k
 ``madm_extract``: tcgen05 GEMMs with the eval-mode BatchNorm folded into the packed weights, bilinear / depthwise kernels).
 Inference only (BatchNorm in eval mode, dropout = identity); there is no eager fallback.
 """
-import ctypes as C
 import math
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn as nn
 
-from . import _lib
 from .engine import Engine
 
 _UNSUPPORTED = "madm_b200.head.DAFormerHead supports the shipped decoder configuration only ({}); SURVEY §8 f-1/f-2 variants are next"

@@ -11,7 +11,6 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from . import _lib
 from .engine import Engine

@@ -12,15 +12,13 @@ TEST INFRASTRUCTURE; PARITY UNPINNED (see oracle/__init__.py).  Follows:
 Device-agnostic (the reference hard-codes ``.cuda()``); no CLIP text tower: ``uncond_inputs`` is a
 seeded stand-in for CLIP('') (reference ``ldm_diffusers.py:76,219-243``), as SURVEY §8d specifies.
 """
-import math
-from typing import List, Optional, Sequence
+from typing import Optional
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from . import sd14
-from .lora import add_adapter, set_adapter
 from .sd14 import q
 
 

@@ -18,7 +18,7 @@ bf16 round-trip to budget the error of a bf16-storage pipeline against the fp32 
 default identity hooks they do not change the oracle's results.
 """
 import math
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn

@@ -2,7 +2,6 @@
 import copy
 from types import SimpleNamespace
 
-import torch
 import torch.nn.functional as F
 
 LORA_CONFIGS = ("default_r16_a16", "Depth_r16_a16")

@@ -7,8 +7,6 @@
 * image_mix against dacs_transforms.one_mix (bit-exact), gaussian_blur against a plain-torch restatement of
   kornia.filters.GaussianBlur2d (separable Gaussian, border 'reflect'; kornia itself is not installed: parity unpinned).
 """
-import math
-
 import pytest
 import torch
 import torch.nn.functional as F
