@@ -253,6 +253,12 @@ int madm_op_preprocess_image(const float* src /*[planes,Hs,Ws]*/, int32_t planes
  * kornia.filters.GaussianBlur2d(kernel_size, (sigma, sigma)), separable, border 'reflect') */
 int madm_op_image_mix(const int64_t* mask /*[HW] 0/1*/, const float* a /*[C,HW]*/, const float* b, int32_t C, int64_t HW, float* out,
                       madm_stream stream);
+/* dacs_transforms.color_jitter (:41-59) = kornia.augmentation.ColorJitter.apply_transform (classic 0.6.x - 0.7.0 arithmetic: additive
+ * brightness, multiplicative contrast, saturation / hue through HSV; the reference does not pin a kornia release) between denorm_ / renorm_.
+ * in / out [B,3,HW] fp32; order [B][4] device int32 = permutation of (0 brightness, 1 contrast, 2 saturation, 3 hue); factors [B][4] device =
+ * (brightness_factor - 1, contrast_factor, saturation_factor, hue_factor * 2 pi); mean / std: device [3] or both NULL. */
+int madm_op_color_jitter(const float* in, int32_t B, int64_t HW, const int32_t* order, const float* factors, const float* mean, const float* stdv,
+                         float* out, madm_stream stream);
 int madm_op_gaussian_blur(const float* src /*[planes,H,W]*/, int32_t planes, int32_t H, int32_t W, int32_t ky, int32_t kx, float sigma_y,
                           float sigma_x, float* tmp /*scratch, same size*/, float* dst, madm_stream stream);
 /* optimizer side of the training step.  Pointer tables are HOST arrays of n DEVICE pointers (fp32 tensors of numel[i]

@@ -107,6 +107,7 @@ SYMBOLS = {
     "madm_op_one_mix": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "madm_op_preprocess_image": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "madm_op_image_mix": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p, c_void_p]),
+    "madm_op_color_jitter": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "madm_op_gaussian_blur": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "madm_op_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_void_p]),
     "madm_op_grad_norm_scratch_floats": (c_int, [c_int32]),

@@ -165,6 +165,12 @@ int madm_op_image_mix(const int64_t* mask, const float* a, const float* b, int32
   RUN(image_mix(mask, a, b, C, long(HW), out, static_cast<cudaStream_t>(stream)));
 }
 
+int madm_op_color_jitter(const float* in, int32_t B, int64_t HW, const int32_t* order, const float* factors, const float* mean, const float* stdv,
+                         float* out, madm_stream stream) {
+  if (!in || !order || !factors || !out) return fail("madm_op_color_jitter: null argument");
+  RUN(color_jitter(in, B, long(HW), order, factors, mean, stdv, out, static_cast<cudaStream_t>(stream)));
+}
+
 int madm_op_gaussian_blur(const float* src, int32_t planes, int32_t H, int32_t W, int32_t ky, int32_t kx, float sigma_y, float sigma_x, float* tmp,
                           float* dst, madm_stream stream) {
   if (!src || !tmp || !dst) return fail("madm_op_gaussian_blur: null argument");

@@ -139,6 +139,10 @@ const char* adamw_step(float* const* param, const float* const* grad, float* con
                        cudaStream_t st);
 // out[c, i] = mask[i] * a[c, i] + (1 - mask[i]) * b[c, i]
 const char* image_mix(const int64_t* mask, const float* a, const float* b, int C, long HW, float* out, cudaStream_t st);
+// kornia ColorJitter.apply_transform on [B,3,HW] fp32: order [B][4] = permutation of (0 brightness, 1 contrast, 2 saturation, 3 hue),
+// factors [B][4] = (brightness_factor - 1, contrast_factor, saturation_factor, hue_factor * 2 pi); mean / std [3] or null (denorm_ / renorm_)
+const char* color_jitter(const float* in, int B, long HW, const int* order, const float* factors, const float* mean, const float* stdv, float* out,
+                         cudaStream_t st);
 // separable Gaussian blur of `planes` HxW fp32 planes, reflect border; tmp: scratch of the same size (may not alias src / dst)
 const char* gaussian_blur(const float* src, int planes, int H, int W, int ky, int kx, float sigma_y, float sigma_x, float* tmp, float* dst,
                           cudaStream_t st);

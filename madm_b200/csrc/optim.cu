@@ -177,6 +177,85 @@ const char* image_mix(const int64_t* mask, const float* a, const float* b, int C
   return cudaGetLastError() == cudaSuccess ? nullptr : "image_mix launch failed";
 }
 
+// ------------------------------------------------------------------ colour jitter (kornia.augmentation.ColorJitter.apply_transform)
+// dacs_transforms.color_jitter (reference utils/dacs_transforms.py:41-59): the four adjustments of kornia's classic ColorJitter (0.6.x - 0.7.0:
+// additive brightness, multiplicative contrast, saturation and hue through HSV), applied per image in the sampled order with the sampled
+// factors, between the reference's denorm_ / renorm_ (x * std + mean ... (x - mean) / std).  One thread = one pixel; all arithmetic in fp32.
+// torch semantics kept: clamp(0, 1) after brightness / contrast / saturation scaling, torch.fmod for the hue shift, torch.remainder ("%")
+// in the RGB <-> HSV conversions (kornia.color.rgb_to_hsv with eps 1e-8, hue in [0, 2 pi]).
+__device__ __forceinline__ float torch_remainder(float a, float b) {
+  float m = fmodf(a, b);
+  if (m != 0.f && ((b < 0.f) != (m < 0.f))) m += b;
+  return m;
+}
+__device__ __forceinline__ void rgb_to_hsv(float r, float g, float b, float& h, float& s, float& v) {
+  const float mx = fmaxf(r, fmaxf(g, b)), mn = fminf(r, fminf(g, b));
+  const int arg = (r >= g && r >= b) ? 0 : (g >= b ? 1 : 2);  // first maximum, like torch.max
+  v = mx;
+  float d = mx - mn;
+  s = d / (mx + 1e-8f);
+  if (d == 0.f) d = 1.f;
+  const float rc = mx - r, gc = mx - g, bc = mx - b;
+  const float hh = arg == 0 ? (bc - gc) : (arg == 1 ? (rc - bc) + 2.0f * d : (gc - rc) + 4.0f * d);
+  h = 6.283185307179586f * torch_remainder((hh / d) / 6.0f, 1.0f);
+}
+__device__ __forceinline__ void hsv_to_rgb(float h, float s, float v, float& r, float& g, float& b) {
+  const float h6 = (h / 6.283185307179586f) * 6.0f;
+  const float hi_f = torch_remainder(floorf(h6), 6.0f);
+  const float f = torch_remainder(h6, 6.0f) - hi_f;
+  const float p = v * (1.0f - s), q = v * (1.0f - f * s), t = v * (1.0f - (1.0f - f) * s);
+  switch (int(hi_f)) {
+    case 0: r = v; g = t; b = p; break;
+    case 1: r = q; g = v; b = p; break;
+    case 2: r = p; g = v; b = t; break;
+    case 3: r = p; g = q; b = v; break;
+    case 4: r = t; g = p; b = v; break;
+    default: r = v; g = p; b = q; break;
+  }
+}
+
+__global__ void __launch_bounds__(256) color_jitter_kernel(const float* __restrict__ in, long HW, const int* __restrict__ order /*[B][4]*/,
+                                                           const float* __restrict__ factors /*[B][4]*/, const float* __restrict__ mean,
+                                                           const float* __restrict__ stdv, float* __restrict__ out) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= HW) return;
+  const int bi = blockIdx.y;
+  const float* p = in + size_t(bi) * 3 * HW + i;
+  float c[3] = {p[0], p[HW], p[2 * HW]};
+  if (mean) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = __fadd_rn(__fmul_rn(c[k], stdv[k]), mean[k]);  // denorm_: img.mul_(std).add_(mean)
+  }
+  for (int k = 0; k < 4; ++k) {
+    const int op = order[bi * 4 + k];
+    const float fac = factors[bi * 4 + op];
+    if (op == 0) {         // adjust_brightness(img, brightness_factor - 1): additive
+      for (int j = 0; j < 3; ++j) c[j] = fminf(fmaxf(c[j] + fac, 0.f), 1.f);
+    } else if (op == 1) {  // adjust_contrast(img, contrast_factor): multiplicative
+      for (int j = 0; j < 3; ++j) c[j] = fminf(fmaxf(c[j] * fac, 0.f), 1.f);
+    } else {
+      float h, s, v;
+      rgb_to_hsv(c[0], c[1], c[2], h, s, v);
+      if (op == 2) s = fminf(fmaxf(s * fac, 0.f), 1.f);  // adjust_saturation
+      else h = fmodf(h + fac, 6.283185307179586f);       // adjust_hue(img, hue_factor * 2 pi): torch.fmod
+      hsv_to_rgb(h, s, v, c[0], c[1], c[2]);
+    }
+  }
+  if (mean) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = __fdiv_rn(__fsub_rn(c[k], mean[k]), stdv[k]);  // renorm_: img.sub_(mean).div_(std)
+  }
+  float* o = out + size_t(bi) * 3 * HW + i;
+  o[0] = c[0]; o[HW] = c[1]; o[2 * HW] = c[2];
+}
+
+const char* color_jitter(const float* in, int B, long HW, const int* order, const float* factors, const float* mean, const float* stdv, float* out,
+                         cudaStream_t st) {
+  if ((mean == nullptr) != (stdv == nullptr)) return "color_jitter: mean and std come together";
+  color_jitter_kernel<<<dim3(unsigned((HW + 255) / 256), B), 256, 0, st>>>(in, HW, order, factors, mean, stdv, out);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "color_jitter launch failed";
+}
+
 // ------------------------------------------------------------------ separable Gaussian blur, reflect border (no edge repeat)
 static constexpr int kBlurMaxK = 129;
 struct BlurTaps { float w[kBlurMaxK]; };

@@ -122,3 +122,46 @@ def gaussian_blur(blur: float, data: torch.Tensor, sigma: Optional[float] = None
     _lib.check(lib.madm_op_gaussian_blur(_ptr(d), B * Cc, H, W, ky, kx, float(sigma), float(sigma), _ptr(tmp), _ptr(out), _stream()), None,
                "madm_op_gaussian_blur")
     return out
+
+
+def color_jitter_params(batch: int, s=0.25, generator: Optional[torch.Generator] = None):
+    """What kornia's ColorJitterGenerator samples for ``ColorJitter(brightness=s, contrast=s, saturation=s, hue=s)`` (or the dict form the
+    reference also accepts): per image a random order of the four adjustments, brightness / contrast / saturation factors uniform in
+    ``[max(0, 1 - s), 1 + s]`` and a hue factor uniform in ``[-s, s]`` (bounded by 0.5).  Host-side: a handful of scalars per image."""
+    cfg = dict(brightness=s, contrast=s, saturation=s, hue=s) if not isinstance(s, dict) else dict(brightness=0.0, contrast=0.0, saturation=0.0, hue=0.0, **s)
+
+    def uni(lo, hi):
+        return lo + (hi - lo) * torch.rand(batch, generator=generator)
+    b, c, sa, h = (float(cfg[k]) for k in ("brightness", "contrast", "saturation", "hue"))
+    return dict(order=torch.stack([torch.randperm(4, generator=generator) for _ in range(batch)]),
+                brightness_factor=uni(max(0.0, 1 - b), 1 + b), contrast_factor=uni(max(0.0, 1 - c), 1 + c),
+                saturation_factor=uni(max(0.0, 1 - sa), 1 + sa), hue_factor=uni(-min(h, 0.5), min(h, 0.5)))
+
+
+def color_jitter(color_jitter: float, mean=None, std=None, data: Optional[torch.Tensor] = None, target=None, s=0.25, p=0.2, params=None):
+    """dacs_transforms.color_jitter (:41-59): if ``color_jitter > p`` apply kornia's ColorJitter to the 3-channel images ``data`` [B,3,H,W]
+    (between ``denorm_`` / ``renorm_`` when ``mean`` / ``std`` are given), in one kernel.  ``params`` (``color_jitter_params``) can be passed to
+    make the draw reproducible.  Returns ``(data, target)`` like the reference; other inputs pass through unchanged."""
+    if data is None or data.shape[1] != 3 or not color_jitter > p:
+        return data, target
+    _need_cuda(data, "data")
+    import math
+    lib = _lib.load()
+    d = data.to(torch.float32).contiguous()
+    B, _, H, W = d.shape
+    if params is None:
+        params = color_jitter_params(B, s)
+    dev = d.device
+    order = params["order"].to(device=dev, dtype=torch.int32).contiguous()
+    fac = torch.stack([params["brightness_factor"].float() - 1.0, params["contrast_factor"].float(), params["saturation_factor"].float(),
+                       params["hue_factor"].float() * (2 * math.pi)], dim=1).to(dev).contiguous()
+    m = sd = None
+    if mean is not None and std is not None:
+        m = torch.as_tensor(mean, dtype=torch.float32, device=dev).reshape(-1).expand(3).contiguous() if torch.as_tensor(mean).numel() in (1, 3) else None
+        sd = torch.as_tensor(std, dtype=torch.float32, device=dev).reshape(-1).expand(3).contiguous() if torch.as_tensor(std).numel() in (1, 3) else None
+        if m is None or sd is None:
+            raise _lib.MadmError("color_jitter: mean / std must be scalars or per-channel 3-vectors")
+    out = torch.empty_like(d)
+    _lib.check(lib.madm_op_color_jitter(_ptr(d), B, H * W, _ptr(order), _ptr(fac), _ptr(m), _ptr(sd), _ptr(out), _stream()), None,
+               "madm_op_color_jitter")
+    return out, target

@@ -306,3 +306,10 @@ def test_optimizer_ops_have_no_cpu_path():
         gaussian_blur(0.9, torch.rand(1, 3, 64, 64), 0.5)
     x = torch.rand(1, 3, 64, 64)
     assert gaussian_blur(0.2, x, 0.5) is x  # not selected: untouched, like the reference
+    from madm_b200.teacher import color_jitter, color_jitter_params
+    with pytest.raises(_lib.MadmError):
+        color_jitter(0.9, data=x)
+    assert color_jitter(0.1, data=x, target=None)[0] is x
+    prm = color_jitter_params(5, 0.25, torch.Generator().manual_seed(1))
+    assert prm["order"].shape == (5, 4) and all(sorted(r) == [0, 1, 2, 3] for r in prm["order"].tolist())
+    assert (prm["brightness_factor"] >= 0.75).all() and (prm["brightness_factor"] <= 1.25).all() and (prm["hue_factor"].abs() <= 0.25).all()

@@ -103,3 +103,35 @@ def test_gaussian_blur(cuda_device, hw, sigma):
     ref = _kornia_gaussian_blur(x, ky, kx, sigma)
     assert out.shape == ref.shape
     assert (out - ref).abs().max().item() <= 2e-6
+
+
+def test_color_jitter(cuda_device):
+    """dacs_transforms.color_jitter = kornia ColorJitter (classic arithmetic) between denorm_ / renorm_, against the torch restatement of
+    kornia's published formulas (oracle/teacher.py; kornia is not installed: parity unpinned).  Piecewise functions (argmax of RGB, floor of
+    the hue sextant) may flip for pixels that sit on a boundary to within fp32 rounding, hence the tiny tolerated fraction of outliers."""
+    from madm_b200.teacher import color_jitter, color_jitter_params
+    from oracle import teacher as ot
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.rand(6, 3, 96, 128, device=cuda_device, generator=g)
+    x[0, :, :8, :8] = 0.5          # grey patch: zero saturation, delta == 0 branch
+    x[1, 0] = x[1, 1]              # r == g ties in the arg-max
+    params = color_jitter_params(6, 0.25, generator=torch.Generator().manual_seed(3))
+    params["order"][0] = torch.tensor([3, 2, 1, 0])
+    params["hue_factor"][1] = -0.25
+    assert color_jitter(0.1, data=x, p=0.2)[0] is x  # not selected: untouched
+    got, tgt = color_jitter(0.9, data=x, target="lbl", s=0.25, p=0.2, params=params)
+    ref = ot.color_jitter_apply(x, params["order"].tolist(), params["brightness_factor"], params["contrast_factor"],
+                                params["saturation_factor"], params["hue_factor"])
+    assert tgt == "lbl" and got.shape == ref.shape
+    err = (got - ref).abs()
+    assert (err > 1e-5).float().mean().item() < 1e-4, ((err > 1e-5).float().mean().item(), err.max().item())
+    assert got.min() >= 0 and got.max() <= 1
+    # with normalisation constants: denorm_ -> jitter -> renorm_
+    mean, std = torch.tensor([0.2, 0.1, 0.3]), torch.tensor([0.5, 0.6, 0.4])
+    xn = (x - mean.view(1, 3, 1, 1).to(cuda_device)) / std.view(1, 3, 1, 1).to(cuda_device)
+    got2, _ = color_jitter(0.9, mean=mean, std=std, data=xn, params=params)
+    den = xn * std.view(1, 3, 1, 1).to(cuda_device) + mean.view(1, 3, 1, 1).to(cuda_device)
+    ref2 = (ot.color_jitter_apply(den.clamp(0, 1), params["order"].tolist(), params["brightness_factor"], params["contrast_factor"],
+                                  params["saturation_factor"], params["hue_factor"]) - mean.view(1, 3, 1, 1).to(cuda_device)) / std.view(1, 3, 1, 1).to(cuda_device)
+    err2 = (got2 - ref2).abs()
+    assert (err2 > 1e-4).float().mean().item() < 1e-3, ((err2 > 1e-4).float().mean().item(), err2.max().item())
