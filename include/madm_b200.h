@@ -227,6 +227,13 @@ int madm_op_pack_linear(const float* w, int32_t N, int32_t K, const float* lora_
                         void* out_bf16, int32_t ldo, int32_t dtype, madm_stream stream);
 int madm_op_pack_conv(const float* w, int32_t N, int32_t C, int32_t taps, int32_t Cpad, void* out_bf16, int32_t ldo,
                       int32_t dtype, madm_stream stream);
+/* dgrad operands (first building block of SURVEY §8 row f-3, the backward pass): the input gradient of a stride-1 conv / a linear is
+ * madm_op_gemm on the output gradient with these packed weights — conv [Cout,Cin,kh,kw] -> [Cin, taps*CoPad] with mirrored taps (the
+ * forward tap offsets apply as is), linear [N,K] (+ LoRA: W + s B A) -> its transpose [K, ldo >= N]. */
+int madm_op_pack_conv_dgrad(const float* w, int32_t Cout, int32_t Cin, int32_t taps, int32_t CoPad, void* out_bf16, int32_t ldo, int32_t dtype,
+                            madm_stream stream);
+int madm_op_pack_linear_dgrad(const float* w, int32_t N, int32_t K, const float* lora_a, const float* lora_b, int32_t r, float scale,
+                              void* out_bf16, int32_t ldo, int32_t dtype, madm_stream stream);
 int madm_op_pack_geglu(const float* w, const float* bias, int32_t C4, int32_t K, void* out_bf16, float* out_bias,
                        int32_t dtype, madm_stream stream);
 int madm_op_space_to_depth(const float* x, int32_t B, int32_t H, int32_t W, int32_t C, void* out_bf16, int32_t dtype,

@@ -96,6 +96,8 @@ SYMBOLS = {
     "madm_op_pack_linear": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_int32,
                                     c_int32, c_void_p]),
     "madm_op_pack_conv": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    "madm_op_pack_conv_dgrad": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    "madm_op_pack_linear_dgrad": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_float, c_void_p, c_int32, c_int32, c_void_p]),
     "madm_op_pack_geglu": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
     "madm_op_space_to_depth": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_nchw_to_nhwc16": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),

@@ -92,6 +92,17 @@ int madm_op_pack_conv(const float* w, int32_t N, int32_t C, int32_t taps, int32_
   RUN(pack_conv_weight(w, N, C, taps, Cpad, Kpad, ldo ? ldo : Kpad, out, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
 
+int madm_op_pack_conv_dgrad(const float* w, int32_t Cout, int32_t Cin, int32_t taps, int32_t CoPad, void* out, int32_t ldo, int32_t dtype,
+                            madm_stream stream) {
+  const int Kpad = taps * CoPad;
+  RUN(pack_conv_dgrad_weight(w, Cout, Cin, taps, CoPad, Kpad, ldo ? ldo : Kpad, out, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+}
+
+int madm_op_pack_linear_dgrad(const float* w, int32_t N, int32_t K, const float* lora_a, const float* lora_b, int32_t r, float scale, void* out,
+                              int32_t ldo, int32_t dtype, madm_stream stream) {
+  RUN(pack_linear_dgrad_weight(w, N, K, lora_a, lora_b, r, scale, ldo ? ldo : N, out, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+}
+
 int madm_op_pack_geglu(const float* w, const float* bias, int32_t C4, int32_t K, void* out, float* out_bias, int32_t dtype,
                        madm_stream stream) {
   RUN(pack_geglu_weight(w, bias, C4, K, out, out_bias, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));

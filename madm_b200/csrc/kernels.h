@@ -154,6 +154,11 @@ const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, i
 // linear weight [N, K] (+ LoRA: + scale * B[N,r] @ A[r,K]) -> bf16 [N, K] written at row offset / interleave
 const char* pack_linear_weight(const float* w, int N, int K, const float* lora_a, const float* lora_b, int r, float scale,
                                int ldo, void* out_bf16, int fp16, cudaStream_t st);
+// dgrad operands: conv weight [Cout, Cin, kh, kw] -> [Cin, taps*CoPad] with mirrored taps; linear (+ LoRA) -> its transpose [K, N]
+const char* pack_conv_dgrad_weight(const float* w, int Cout, int Cin, int taps, int CoPad, int Kpad, int ldo, void* out_bf16, int fp16,
+                                   cudaStream_t st);
+const char* pack_linear_dgrad_weight(const float* w, int N, int K, const float* lora_a, const float* lora_b, int r, float scale, int ldo,
+                                     void* out_bf16, int fp16, cudaStream_t st);
 // GEGLU: rows of W[8C, C] reordered so each 128-row tile holds 64 value rows then their 64 gate rows (bias likewise)
 const char* pack_geglu_weight(const float* w, const float* bias, int C4 /* = 4C */, int K, void* out_bf16, float* out_bias,
                               int fp16, cudaStream_t st);

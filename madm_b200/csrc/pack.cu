@@ -32,6 +32,56 @@ const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, i
   return cudaGetLastError() == cudaSuccess ? nullptr : "pack_conv_weight launch failed";
 }
 
+// ---- dgrad operands (first building block of SURVEY §8 row f-3): the input gradient of a stride-1 conv / a linear is the same implicit
+// GEMM run on the output gradient with the weight's in / out roles swapped (and the filter taps mirrored):
+//   conv:   dX[b,y,x,ci] = sum_{ky,kx,co} dY[b, y-(ky-1), x-(kx-1), co] * W[co,ci,ky,kx]
+//           -> out[ci, tap'*CoPad + co] = W[co, ci, taps-1-tap']     (tap' = the forward kernel's tap order, so seg_3x3 offsets apply as is)
+//   linear: dX = dY (W + s B A)   -> out[k, n] = W'[n, k]
+__global__ void pack_conv_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int CoPad, int Kpad, int ldo, int fp16,
+                                       uint16_t* __restrict__ out) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = long(Cin) * Kpad;
+  if (i >= total) return;
+  const int k = int(i % Kpad);
+  const int ci = int(i / Kpad);
+  float v = 0.f;
+  if (k < taps * CoPad) {
+    const int tap = k / CoPad, co = k % CoPad;
+    if (co < Cout) v = w[(size_t(co) * Cin + ci) * taps + (taps - 1 - tap)];
+  }
+  out[size_t(ci) * ldo + k] = cvt_16(v, fp16);
+}
+
+const char* pack_conv_dgrad_weight(const float* w, int Cout, int Cin, int taps, int CoPad, int Kpad, int ldo, void* out, int fp16, cudaStream_t st) {
+  if (taps != 1 && taps != 9) return "pack_conv_dgrad: 1x1 or 3x3 (stride 1) filters only";
+  const long total = long(Cin) * Kpad;
+  pack_conv_dgrad_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w, Cout, Cin, taps, CoPad, Kpad, ldo, fp16, reinterpret_cast<uint16_t*>(out));
+  return cudaGetLastError() == cudaSuccess ? nullptr : "pack_conv_dgrad_weight launch failed";
+}
+
+// out[k, n] = 16-bit( w[n,k] + scale * sum_j lb[n,j] * la[j,k] )   (the transpose of pack_linear_kernel's result)
+__global__ void pack_linear_dgrad_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ la, const float* __restrict__ lb,
+                                         int r, float scale, int ldo, int fp16, uint16_t* __restrict__ out) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= long(N) * K) return;
+  const int n = int(i % N);  // n fastest: coalesced writes of the transposed matrix
+  const int k = int(i / N);
+  float v = w[size_t(n) * K + k];
+  if (la != nullptr) {
+    float acc = 0.f;
+    for (int j = 0; j < r; ++j) acc += lb[size_t(n) * r + j] * la[size_t(j) * K + k];
+    v += scale * acc;
+  }
+  out[size_t(k) * ldo + n] = cvt_16(v, fp16);
+}
+
+const char* pack_linear_dgrad_weight(const float* w, int N, int K, const float* la, const float* lb, int r, float scale, int ldo, void* out,
+                                     int fp16, cudaStream_t st) {
+  const long total = long(N) * K;
+  pack_linear_dgrad_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(w, N, K, la, lb, r, scale, ldo, fp16, reinterpret_cast<uint16_t*>(out));
+  return cudaGetLastError() == cudaSuccess ? nullptr : "pack_linear_dgrad_weight launch failed";
+}
+
 // out[n, k] = bf16( w[n,k] + scale * sum_j lb[n,j] * la[j,k] )
 __global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ la,
                                    const float* __restrict__ lb, int r, float scale, int ldo, int fp16, uint16_t* __restrict__ out) {

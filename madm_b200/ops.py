@@ -152,6 +152,28 @@ def pack_conv(w, Cpad=0, out=None, ldo=0, dtype=torch.float16):
     return out
 
 
+def pack_conv_dgrad(w, CoPad=0, dtype=torch.float16):
+    """[Cout,Cin,kh,kw] -> [Cin, taps*CoPad] with mirrored taps: the B operand of the conv's input-gradient GEMM."""
+    lib = _lib.load()
+    Cout, Cin, kh, kw = w.shape
+    taps = kh * kw
+    CoPad = CoPad or (Cout + 63) // 64 * 64
+    out = torch.empty(Cin, taps * CoPad, dtype=dtype, device=w.device)
+    _lib.check(lib.madm_op_pack_conv_dgrad(_ptr(w), Cout, Cin, taps, CoPad, _ptr(out), 0, _dt(dtype), _stream()), None, "madm_op_pack_conv_dgrad")
+    return out
+
+
+def pack_linear_dgrad(w, lora_a=None, lora_b=None, scale=0.0, dtype=torch.float16):
+    """[N,K] (+ scale * B @ A) -> its transpose [K,N]: the B operand of the linear's input-gradient GEMM."""
+    lib = _lib.load()
+    N, K = w.shape
+    out = torch.empty(K, N, dtype=dtype, device=w.device)
+    r = lora_a.shape[0] if lora_a is not None else 0
+    _lib.check(lib.madm_op_pack_linear_dgrad(_ptr(w), N, K, _ptr(lora_a), _ptr(lora_b), r, float(scale), _ptr(out), 0, _dt(dtype), _stream()),
+               None, "madm_op_pack_linear_dgrad")
+    return out
+
+
 def pack_geglu(w, bias, dtype=torch.float16):
     lib = _lib.load()
     N2, K = w.shape

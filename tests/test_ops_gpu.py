@@ -463,3 +463,39 @@ def test_slide_merge_matches_sequential_accumulate(ops, cuda_device, H, W):
         cnt[..., y // s:y // s + hf, x // s:x // s + hf] += 1
     ref /= cnt
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(2, 32, 32, 128, 192, 3), (1, 64, 64, 320, 320, 3), (2, 16, 16, 640, 1280, 1), (1, 8, 128, 64, 128, 3), (3, 8, 8, 128, 320, 3)])
+def test_conv_dgrad_is_the_same_implicit_gemm(ops, cuda_device, B, H, W, Cin, Cout, k):
+    """First building block of SURVEY §8 row f-3: dX of a stride-1 conv = the forward implicit-GEMM kernel on dY with the weight's in / out
+    roles swapped and the taps mirrored (madm_op_pack_conv_dgrad), against torch.autograd."""
+    g = torch.Generator(device="cuda").manual_seed(Cin + H)
+    x = torch.randn(B, Cin, H, W, device=cuda_device, generator=g, requires_grad=True)
+    w = torch.randn(Cout, Cin, k, k, device=cuda_device, generator=g) / math.sqrt(k * k * Cin)
+    dy = bf(torch.randn(B, Cout, H, W, device=cuda_device, generator=g))
+    y = F.conv2d(x, bf(w).float(), padding=k // 2)
+    (ref,) = torch.autograd.grad(y, x, dy.float())
+    wp = ops.pack_conv_dgrad(w, dtype=DT)
+    a = nhwc(dy)
+    M = B * H * W
+    out = torch.empty(M, Cin, device=cuda_device)
+    seg = ops.make_seg(a, B, H, W, Cout, taps=ops.taps_3x3() if k == 3 else None)
+    ops.gemm([seg], M, Cin, wp, out_f32=out, ldo32=Cin)
+    assert relerr(out, nhwc(ref).reshape(M, Cin)) < 2e-3
+
+
+def test_linear_dgrad_with_folded_lora(ops, cuda_device):
+    """dX = dY (W + s B A): the transposed, LoRA-folded weight as the GEMM's B operand (madm_op_pack_linear_dgrad), against torch.autograd."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    M, K, N, r, sc = 4096, 320, 960, 16, 2.0
+    x = torch.randn(M, K, device=cuda_device, generator=g, requires_grad=True)
+    w = torch.randn(N, K, device=cuda_device, generator=g) / math.sqrt(K)
+    la = torch.randn(r, K, device=cuda_device, generator=g) / math.sqrt(r)
+    lb = torch.randn(N, r, device=cuda_device, generator=g) * 0.02
+    dy = bf(torch.randn(M, N, device=cuda_device, generator=g))
+    wp = ops.pack_linear_dgrad(w, la, lb, sc, dtype=DT)
+    assert torch.equal(wp, ops.pack_linear(w, la, lb, sc, dtype=DT).t().contiguous())  # exactly the transpose of the forward operand
+    (ref,) = torch.autograd.grad(F.linear(x, wp.float().t()), x, dy.float())
+    out = torch.empty(M, K, device=cuda_device)
+    ops.gemm([ops.make_seg(dy, 1, 1, M, N)], M, K, wp, out_f32=out, ldo32=K)
+    assert relerr(out, ref) < 2e-3
