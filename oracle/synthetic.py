@@ -71,6 +71,32 @@ def build_backbone(lora_configs: Sequence[str] = ("default_r16_a16", "Depth_r16_
     return bb
 
 
+def training_gradients(bb, img: torch.Tensor, adapter: str = "Depth", input_modal: str = "others", seed: int = 99):
+    """Reference gradients for SURVEY §8 row f-3 / BASELINE config 5 (the target of the backward pass that is still to be built): the
+    trainable set of the LoRA training step — the active adapter's A / B factors, the feature projections and the learned prompt / time
+    parameters — receives the gradient of a fixed linear functional of the feature dict, L = sum_k <feat_k, R_k> / 1000 with seeded
+    Gaussian R_k.  As in the reference the VAE encoder runs under no_grad (ldm_diffusers.py:282), so gradients flow through the UNet and
+    the projections only.  Returns (loss, {name: grad}) with None for parameters the path does not reach."""
+    from .lora import set_adapter
+    set_adapter(bb.feature_extractor.ldm_extractor.unet, [adapter])
+    train = [(n, p) for n, p in bb.named_parameters()
+             if ("lora_" in n and f".{adapter}." in n) or n.startswith("feature_projections.") or "clip_project_others" in n]
+    for p in bb.parameters():
+        p.requires_grad_(False)
+        p.grad = None
+    for _, p in train:
+        p.requires_grad_(True)
+    out = bb(img, input_modal=input_modal)["output_features"]
+    g = torch.Generator().manual_seed(seed)
+    loss = sum((v * torch.randn(v.shape, generator=g)).sum() for v in out.values()) / 1e3
+    loss.backward()
+    grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in train}
+    for _, p in train:
+        p.requires_grad_(False)
+        p.grad = None
+    return float(loss.detach()), grads
+
+
 def synthetic_images(batch: int, h: int = 512, w: int = 512, seed: int = 0) -> torch.Tensor:
     """``img255 = rand*255`` as the dataloader would give; the meta-arch divides by pixel_std=255."""
     g = torch.Generator().manual_seed(seed)

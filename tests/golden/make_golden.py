@@ -10,7 +10,10 @@ silent drift and let the GPU tests check the product without re-running the orac
 (config_files/SemSeg/MTMADISE/mtmadise_cityscapes_rgb_to_depth_11.py:47-55): UNet final output, decoded image,
 s0 / s3 / s4 / s5.
 
-Run:  python tests/golden/make_golden.py [base|s0]    (about 30 s each on 8 cores; deterministic for a given torch build)
+``config5_lora_grads_b1.npz`` (``grads``) holds the oracle's gradients of the LoRA training step's trainable set: the parity target of
+the backward pass that SURVEY §8 row f-3 still asks for.
+
+Run:  python tests/golden/make_golden.py [base|s0|grads]    (about 30 s each on 8 cores; deterministic for a given torch build)
 """
 import os
 import sys
@@ -70,9 +73,29 @@ def main_s0():
     print("wrote", path, {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
 
 
+def main_grads():
+    """config5_lora_grads_b1.npz: oracle gradients of the LoRA training step's trainable set (oracle.synthetic.training_gradients) at
+    1x3x512x512 — per tensor the L2 norm and the first 8 values.  The parity target of the backward pass, not yet consumed
+    by a product test."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    bb = synthetic.build_backbone()
+    loss, grads = synthetic.training_gradients(bb, synthetic.synthetic_images(1))
+    names = sorted(grads)
+    out = {"loss": np.float32(loss), "names": np.array(names),
+           "norm": np.array([0.0 if grads[n] is None else float(grads[n].double().norm()) for n in names], dtype=np.float32),
+           "reached": np.array([grads[n] is not None for n in names]),
+           "head8": np.stack([np.zeros(8, np.float32) if grads[n] is None else
+                              np.pad(grads[n].flatten()[:8].numpy(), (0, max(0, 8 - grads[n].numel()))) for n in names]).astype(np.float32)}
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "config5_lora_grads_b1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, len(names), "tensors, total norm", float(np.sqrt((out["norm"].astype(np.float64) ** 2).sum())), "loss", loss)
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "both"
     if which in ("base", "both"):
         main()
     if which in ("s0", "both"):
         main_s0()
+    if which == "grads":
+        main_grads()

@@ -211,6 +211,48 @@ def test_oracle_s0_variant_shapes_and_golden():
         assert np.abs(got - ref).max() <= 2e-3 * float(g[k + "_absmax"]) + 2e-3, k
 
 
+def test_oracle_training_gradients_fixture_and_directional_derivative():
+    """SURVEY §8 row f-3 / BASELINE config 5: the oracle's gradients of the LoRA training step's trainable set (the parity target of the
+    backward pass still to be built).  Pinned two ways: against the committed fixture tests/golden/config5_lora_grads_b1.npz, and against a
+    central finite difference of the loss along the gradient direction of the LoRA B factors (L is exactly linear in the features, the
+    features smooth in the parameters): <g, d> must equal (L(theta + h d) - L(theta - h d)) / 2h."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    bb = synthetic.build_backbone()
+    img = synthetic.synthetic_images(1)
+    loss, grads = synthetic.training_gradients(bb, img)
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "config5_lora_grads_b1.npz"))
+    names = [str(n) for n in g["names"]]
+    assert names == sorted(grads) and abs(loss - float(g["loss"])) <= 1e-4 * max(1.0, abs(loss))
+    n_lora = sum(1 for n in names if "lora_" in n)
+    assert n_lora == 256  # 128 LoRA-wrapped projections x (A, B) of the active adapter
+    for i, n in enumerate(names):
+        assert (grads[n] is not None) == bool(g["reached"][i]), n
+        if grads[n] is not None:
+            assert abs(float(grads[n].double().norm()) - float(g["norm"][i])) <= 2e-3 * float(g["norm"][i]) + 1e-7, n
+    # every LoRA factor and every projection is reached; what is not reached are conditioning parameters the 'others' path does not use
+    assert all(bool(r) for n, r in zip(names, g["reached"]) if "lora_" in n or n.startswith("feature_projections."))
+    # directional derivative along the (normalised) gradient of all lora_B factors
+    params = dict(bb.named_parameters())
+    sel = [n for n in names if "lora_B" in n]
+    gn = float(torch.sqrt(sum((grads[n].double() ** 2).sum() for n in sel)))
+    analytic = gn  # <g, g / |g|>
+
+    def loss_at(h):
+        with torch.no_grad():
+            for n in sel:
+                params[n].add_(grads[n] * (h / gn))
+            out = bb(img, input_modal="others")["output_features"]
+            gen = torch.Generator().manual_seed(99)
+            val = float(sum((v.double() * torch.randn(v.shape, generator=gen).double()).sum() for v in out.values()) / 1e3)
+            for n in sel:
+                params[n].sub_(grads[n] * (h / gn))
+        return val
+    h = 5e-3
+    numeric = (loss_at(h) - loss_at(-h)) / (2 * h)
+    print(f"directional derivative along grad(lora_B): analytic {analytic:.5f} numeric {numeric:.5f}")
+    assert abs(numeric - analytic) <= 1e-2 * abs(analytic), (numeric, analytic)
+
+
 def test_bf16_error_budget(oracle_run):
     """Error budget of an IDEAL 16-bit-operand pipeline, emulated by rounding every GEMM operand (weights + activations) in
     the oracle while keeping accumulation, norms and the residual stream in fp32 — exactly the product's storage plan.
