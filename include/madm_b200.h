@@ -162,10 +162,14 @@ int madm_extract(madm_ctx* ctx, const madm_extract_args* args, madm_stream strea
 #define MADM_KIND_ELEMENTWISE 4 /* im2col, q-sample, space-to-depth, upsample, softmax rows, casts */
 #define MADM_NUM_KINDS 5
 typedef struct madm_profile {
-  struct { char name[32]; int32_t launches; double ms; double flops; double bytes; } kind[MADM_NUM_KINDS];
+  /* flops: ALGORITHMIC (2*MAC of the reference's convs / linears / attention products: no K padding, no identity-weight residual
+   * segments) -- the numerator of the roofline line; exec_flops: what the launches execute (>= flops). */
+  struct { char name[32]; int32_t launches; double ms; double flops; double bytes; double exec_flops; } kind[MADM_NUM_KINDS];
 } madm_profile;
 int madm_set_profiling(madm_ctx* ctx, int32_t on);
 int madm_get_profile(madm_ctx* ctx, madm_profile* out);
+/* the same, restricted to the launches of the stages in stage_mask (MADM_STAGE_*): e.g. MADM_STAGE_UNET for the UNet contractions */
+int madm_get_profile_stages(madm_ctx* ctx, int32_t stage_mask, madm_profile* out);
 
 /* Number of kernels one madm_extract call launches for batch B with the given stage mask (for bench accounting). */
 int madm_launch_count(madm_ctx* ctx, int32_t B, int32_t stages);
@@ -221,7 +225,7 @@ int madm_op_layernorm(const void* x, int32_t in16 /* x is 16-bit (dtype) instead
 int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p_bf16, int32_t dtype, madm_stream stream);
 int madm_op_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o, int32_t ldo,
                       int32_t B, int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bstride, int64_t kv_bstride,
-                      int64_t o_bstride, float scale, int32_t dtype, int32_t impl /* 0 = tcgen05/TMEM kernel, 1 = mma.sync kernel */,
+                      int64_t o_bstride, float scale, int32_t dtype, int32_t impl /* must be 0: the tcgen05/TMEM kernel */,
                       madm_stream stream);
 int madm_op_pack_linear(const float* w, int32_t N, int32_t K, const float* lora_a, const float* lora_b, int32_t r, float scale,
                         void* out_bf16, int32_t ldo, int32_t dtype, madm_stream stream);

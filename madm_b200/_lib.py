@@ -43,7 +43,8 @@ class MadmExtractArgs(C.Structure):
 
 
 class _MadmProfileKind(C.Structure):
-    _fields_ = [("name", C.c_char * 32), ("launches", c_int32), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double)]
+    _fields_ = [("name", C.c_char * 32), ("launches", c_int32), ("ms", C.c_double), ("flops", C.c_double), ("bytes", C.c_double),
+                ("exec_flops", C.c_double)]
 
 
 class MadmProfile(C.Structure):
@@ -83,6 +84,7 @@ SYMBOLS = {
     "madm_launch_count": (c_int, [c_void_p, c_int32, c_int32]),
     "madm_set_profiling": (c_int, [c_void_p, c_int32]),
     "madm_get_profile": (c_int, [c_void_p, C.POINTER(MadmProfile)]),
+    "madm_get_profile_stages": (c_int, [c_void_p, c_int32, C.POINTER(MadmProfile)]),
     "madm_op_gemm": (c_int, [C.POINTER(MadmGemmArgs), c_void_p]),
     "madm_op_groupnorm": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_float,
                                   c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),

@@ -136,8 +136,37 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
             out += [("ema_feature_projections." + n, p.detach()) for n, p in ema.named_parameters()]
         return out
 
+    def _grad_inputs(self, input_modal, ema_forward) -> List[Tuple[str, torch.Tensor]]:
+        """Parameters this call's result depends on that currently require grad (empty under no_grad)."""
+        if not torch.is_grad_enabled():
+            return []
+        gen: BasePromptTimeGenerator = self.feature_extractor
+        ldm: LdmDiffusers = gen.ldm_extractor
+        unet = ldm.ema_unet if (ema_forward and hasattr(ldm, "ema_unet")) else ldm.unet
+        proj = self.ema_feature_projections if ema_forward else self.feature_projections
+        mods = [("feature_extractor.ldm_extractor.unet.", unet), ("feature_projections.", proj)]
+        if input_modal in ("rgb", "mixed"):
+            mods.append(("feature_extractor.clip_project_rgb.", gen.clip_project_rgb))
+        if input_modal != "rgb":
+            mods.append(("feature_extractor.clip_project_others.", gen.ema_clip_project_others if ema_forward else gen.clip_project_others))
+        seen, out = set(), []
+        for pre, m in mods:
+            for n, p in m.named_parameters():
+                if p.requires_grad and id(p) not in seen:
+                    seen.add(id(p))
+                    out.append((pre + n, p))
+        return out
+
     def _extract(self, img, input_modal, ema_forward, timestep, want_taps=False, timesteps=None, **kwargs):
         gen: BasePromptTimeGenerator = self.feature_extractor
+        grad_inputs = self._grad_inputs(input_modal, ema_forward)
+        if grad_inputs:
+            # Called under grad with trainable parameters (MTMADISE.forward's student passes, mtmadise.py:240-302): the result must carry
+            # a grad_fn.  The training path (madm_b200/train.py: autograd.Function around madm_extract / madm_backward) provides it for
+            # the LoRA training step's trainable set and raises for anything else -- never a silent grad-free tensor.
+            from . import train
+            return train.extract_with_grad(self, img, input_modal, ema_forward, timestep, grad_inputs, want_taps=want_taps,
+                                           timesteps=timesteps, **kwargs)
         batched = dict(img=img)
         with torch.no_grad():
             gen.conditioning(batched, input_modal, ema_forward, timestep)
@@ -162,6 +191,9 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
         """Projection stage on taps produced by ``self.feature_extractor(...)`` (the reference's two-step use)."""
         if not isinstance(features, FeatureTaps) or features.token is None:
             raise NotImplementedError("forward_features needs the FeatureTaps returned by this backbone's feature_extractor")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in (self.ema_feature_projections if ema_forward else self.feature_projections).parameters()):
+            raise NotImplementedError("forward_features under torch.enable_grad() with trainable projections: the two-step use has no "
+                                      "backward path; call the backbone's forward (training path) or wrap inference in torch.no_grad()")
         ldm: LdmDiffusers = self.feature_extractor.ldm_extractor
         if features.token != (id(ldm), ldm._serial):
             raise RuntimeError("stale FeatureTaps: another forward ran since these taps were produced")

@@ -71,9 +71,7 @@ int madm_op_softmax_rows(const float* s, int32_t R, int32_t L, void* p, int32_t 
 int madm_op_attention(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, void* o, int32_t ldo,
                       int32_t B, int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bs, int64_t kv_bs, int64_t o_bs,
                       float scale, int32_t dtype, int32_t impl, madm_stream stream) {
-  if (impl == 1)
-    RUN(flash_attention(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, dtype == MADM_DTYPE_FP16,
-                        static_cast<cudaStream_t>(stream)));
+  if (impl != 0) return fail("madm_op_attention: impl must be 0 (the mma.sync kernel of round 1 was removed from the library)");
   FaLaunch L;
   if (const char* e = flash_attention_tc_prepare(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale,
                                                  dtype == MADM_DTYPE_FP16, &L))

@@ -85,7 +85,8 @@ struct Plan {
   std::vector<int> stage_of;  // stage bit per op
   std::vector<char> optional; // debug/taps ops that launch only when the caller asks for the extra output
   std::vector<int> kind;      // MADM_KIND_* per op
-  std::vector<double> flops;  // algorithmic FLOPs per op (2*MAC)
+  std::vector<double> flops;  // algorithmic FLOPs per op (2*MAC of the reference's convs / linears: no K padding, no identity segments)
+  std::vector<double> exec_flops;  // FLOPs the launch executes (padded K, identity-weight residual segments, GEGLU both halves)
   std::vector<double> bytes;  // algorithmic HBM bytes per op (HBM-bound kernels)
   std::vector<cudaEvent_t> ev;  // 2 per op, created on demand when profiling
   ~Plan() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
@@ -368,7 +369,7 @@ struct Builder {
   }
 
   // ---- op emission
-  void emit(Op op, bool optional = false, int kind = MADM_KIND_ELEMENTWISE, double flops = 0.0, double bytes = 0.0) {
+  void emit(Op op, bool optional = false, int kind = MADM_KIND_ELEMENTWISE, double flops = 0.0, double bytes = 0.0, double exec_flops = -1.0) {
     ++n_ops;
     if (mode == PLAN) {
       plan->ops.push_back(std::move(op));
@@ -376,6 +377,7 @@ struct Builder {
       plan->optional.push_back(optional ? 1 : 0);
       plan->kind.push_back(kind);
       plan->flops.push_back(flops);
+      plan->exec_flops.push_back(exec_flops < 0 ? flops : exec_flops);
       plan->bytes.push_back(bytes);
     }
   }
@@ -420,12 +422,13 @@ struct Builder {
         if (const char* e = gemm_prepare(d, &L)) fail(MADM_EINVAL, std::string(e));
         double K = 0;
         for (int sgi = 0; sgi < d.nseg; ++sgi) K += double(d.seg[sgi].ntaps) * d.seg[sgi].C;
-        if (algo_flops < 0) algo_flops = 2.0 * double(d.M) * d.N * K;
+        const double exec = 2.0 * double(d.M) * d.N * K;
+        if (algo_flops < 0) algo_flops = exec;
         if (getenv("MADM_DUMP_PLAN"))
           fprintf(stderr, "MADM_PLAN gemm M=%d N=%d K=%d bn=%d tiles=%d taps=%d nseg=%d act=%d res=%d f32=%d h16=%d gflop=%.3f splits=%d\n", d.M, d.N,
                   int(K), L.bn, L.num_tiles, d.seg[0].ntaps, d.nseg, d0.act, d0.residual ? 1 : 0, d0.out_f32 ? 1 : 0, d0.out_bf16 ? 1 : 0,
                   algo_flops / 1e9, splits);
-        emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, gemm_algo_bytes(d));
+        emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, gemm_algo_bytes(d), exec);
         const GemmDesc e0 = d0; const float* pp = part.p; const int f16 = ctx->fp16; const long ss = d.split_stride;
         if (e0.alpha != 1.0f) fail(MADM_EINVAL, "split-K with alpha != 1 is not supported");
         emit([=](cudaStream_t st) {
@@ -443,32 +446,29 @@ struct Builder {
     d.fp16 = ctx->fp16;
     GemmLaunch L;
     if (const char* e = gemm_prepare(d, &L)) fail(MADM_EINVAL, std::string(e));
-    if (algo_flops < 0) {
+    double exec;
+    {
       double K = 0;
       for (int sgi = 0; sgi < d.nseg; ++sgi) K += double(d.seg[sgi].ntaps) * d.seg[sgi].C;
       const double N = (d.act == ACT_GEGLU) ? 2.0 * d.N : double(d.N);
-      algo_flops = 2.0 * double(d.M) * N * K;
+      exec = 2.0 * double(d.M) * N * K;
     }
+    if (algo_flops < 0) algo_flops = exec;
     if (getenv("MADM_DUMP_PLAN")) {
       int K = 0;
       for (int sgi = 0; sgi < d.nseg; ++sgi) K += d.seg[sgi].ntaps * d.seg[sgi].C;
       fprintf(stderr, "MADM_PLAN gemm M=%d N=%d K=%d bn=%d tiles=%d taps=%d nseg=%d act=%d res=%d f32=%d h16=%d gflop=%.3f\n", d.M, d.N, K, L.bn,
               L.num_tiles, d.seg[0].ntaps, d.nseg, d.act, d.residual ? 1 : 0, d.out_f32 ? 1 : 0, d.out_bf16 ? 1 : 0, algo_flops / 1e9);
     }
-    emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, gemm_algo_bytes(d));
+    emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, gemm_algo_bytes(d), exec);
   }
 
-  // fused attention: tcgen05/TMEM kernel (tensor maps encoded at plan time); MADM_ATTN_LEGACY=1 selects the mma.sync kernel
+  // fused attention: tcgen05/TMEM kernel (tensor maps encoded at plan time)
   void attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, int Bn, int heads, int d, int Nq,
                  int Nk, long q_bs, long kv_bs, long o_bs, float scale) {
     const double flops = 4.0 * double(Bn) * Nq * Nk * heads * d;
     if (mode != PLAN) { ++n_ops; return; }
     const int h16 = ctx->fp16;
-    if (getenv("MADM_ATTN_LEGACY")) {
-      emit([=](cudaStream_t st) { return flash_attention(q, ldq, k, ldk, v, ldv, o, ldo, Bn, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, h16, st); },
-           false, MADM_KIND_ATTENTION, flops, 0.0);
-      return;
-    }
     FaLaunch L;
     if (const char* e = flash_attention_tc_prepare(q, ldq, k, ldk, v, ldv, o, ldo, Bn, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, h16, &L))
       fail(MADM_EINVAL, std::string(e));
@@ -623,7 +623,8 @@ struct Model {
       }
       d.out_f32 = out.f.p; d.ldo32 = Cout; d.out_bf16 = out.h.p; d.ldo16 = Cout;
       b.attach_colstats(out, d);  // statistics for whichever GroupNorm consumes this block's output
-      b.gemm(d);
+      // the identity-weight segment is the reference's residual ADD: executed on the tensor core, but not algorithmic work
+      b.gemm(d, (!shortcut && in16) ? 2.0 * double(d.M) * Cout * (9.0 * Cout) : -1.0);
     }
     b.free(n2);
     if (shortcut && !in16) b.free(raw);
@@ -1623,22 +1624,25 @@ int madm_set_profiling(madm_ctx* ctx, int32_t on) {
   return MADM_OK;
 }
 
-int madm_get_profile(madm_ctx* ctx, madm_profile* out) {
+int madm_get_profile(madm_ctx* ctx, madm_profile* out) { return madm_get_profile_stages(ctx, ~0, out); }
+
+int madm_get_profile_stages(madm_ctx* ctx, int32_t stage_mask, madm_profile* out) {
   if (!ctx || !out) return set_err(ctx, MADM_EINVAL, "madm_get_profile: null argument");
   Plan* plan = ctx->last_plan;
   if (!plan || plan->ev.size() != 2 * plan->ops.size()) return set_err(ctx, MADM_ESTATE, "madm_get_profile: no profiled madm_extract call");
   static const char* names[MADM_NUM_KINDS] = {"gemm_tc", "flash_attention", "groupnorm", "layernorm", "elementwise"};
   for (int k = 0; k < MADM_NUM_KINDS; ++k) {
     snprintf(out->kind[k].name, sizeof(out->kind[k].name), "%s", names[k]);
-    out->kind[k].launches = 0; out->kind[k].ms = 0; out->kind[k].flops = 0; out->kind[k].bytes = 0;
+    out->kind[k].launches = 0; out->kind[k].ms = 0; out->kind[k].flops = 0; out->kind[k].bytes = 0; out->kind[k].exec_flops = 0;
   }
   if (cudaDeviceSynchronize() != cudaSuccess) return set_err(ctx, MADM_ECUDA, "cudaDeviceSynchronize failed");
   for (size_t i = 0; i < plan->ops.size(); ++i) {
-    if (!(plan->stage_of[i] & ctx->last_stages) || !plan->ops[i] || plan->optional[i]) continue;
+    if (!(plan->stage_of[i] & ctx->last_stages) || !(plan->stage_of[i] & stage_mask) || !plan->ops[i] || plan->optional[i]) continue;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, plan->ev[2 * i], plan->ev[2 * i + 1]) != cudaSuccess) continue;
     const int k = plan->kind[i];
     out->kind[k].launches += 1; out->kind[k].ms += ms; out->kind[k].flops += plan->flops[i]; out->kind[k].bytes += plan->bytes[i];
+    out->kind[k].exec_flops += plan->exec_flops[i];
   }
   return MADM_OK;
 }

@@ -46,12 +46,8 @@ const char* c3_conv_gn_relu(const float* img4, const float* coef, int B, int HW,
 const char* gn_add_relu_nchw_c3(const float* a, const float* stats_a, const float* ga, const float* ba, const float* img4, const float* coef_s, float eps,
                                 int B, int HW, int C, float* out_nchw, cudaStream_t st);
 
-// ---- attention.cu : O[b, i, h*d:(h+1)*d] = softmax(Q K^T * scale) V per (image, head); bf16 in/out, fp32 softmax
-const char* flash_attention(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo,
-                            int B, int heads, int d, int Nq, int Nk, long q_bstride, long kv_bstride, long o_bstride,
-                            float scale, int fp16, cudaStream_t st);
-
-// ---- attention_tc.cu : the same contract on tcgen05 / TMEM (prepared launch: TMA tensor maps encoded once)
+// ---- attention_tc.cu : O[b, i, h*d:(h+1)*d] = softmax(Q K^T * scale) V per (image, head); 16-bit in/out, fp32 softmax, on tcgen05 / TMEM
+// (prepared launch: TMA tensor maps encoded once)
 struct FaLaunch {
   alignas(64) unsigned char params[512];
   int d = 0;

@@ -76,7 +76,13 @@ __global__ void __launch_bounds__(256) adamw_kernel(MtTable t, AdamArgs a, const
   float* __restrict__ v = static_cast<float*>(t.p[3][k]);
   const long n = t.numel[k];
   float coef = 1.0f;
-  if (grad_norm && a.max_norm > 0.f) coef = fminf(a.max_norm / (*grad_norm + 1e-6f), 1.0f);  // clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max=1)
+  if (grad_norm) {
+    const float gn = *grad_norm;
+    // a non-finite gradient norm skips the whole step, parameters and moments untouched: what GradScaler.step does under the reference's
+    // AMP trainer (engine/train_loop.py:277-302) when unscale_ finds an inf / NaN; fminf(NaN, 1) would otherwise apply it unclipped
+    if (!isfinite(gn)) return;
+    if (a.max_norm > 0.f) coef = fminf(a.max_norm / (gn + 1e-6f), 1.0f);  // clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max=1)
+  }
   for (long i = long(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += long(gridDim.x) * blockDim.x) {
     const float gi = __fmul_rn(g[i], coef);
     float pi = __fmul_rn(p[i], a.decay);

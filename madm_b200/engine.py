@@ -42,7 +42,12 @@ class Engine:
         self._packed_adapter: Optional[str] = "\0unset"
         self._ws: Optional[torch.Tensor] = None
         self._keep = []
+        # image_im2col raises this device flag when a normalised image leaves [-1, 1] (the reference asserts that with a host sync,
+        # ldm_diffusers.py:147).  It is copied to pinned host memory asynchronously after every call and looked at on the NEXT call
+        # (or by check_input_range()), so steady-state inference keeps running without a synchronisation.
         self.range_flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self._range_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._range_event: Optional[torch.cuda.Event] = None
         # CUDA graphs: at small batch the ~550 launches of one forward are CPU-launch-bound, and even at B = 8 the graph saves the
         # inter-kernel launch gaps (24.9 -> 24.1 ms per step); one graph per call signature
         # replays them.  graph_max_batch: largest B that is graphed (0 disables).
@@ -76,6 +81,7 @@ class Engine:
             for k, s in enumerate(t.shape):
                 arr[i].shape[k] = s
         _lib.check(self.lib.madm_set_tensors(self.ctx, arr, len(named)), self.ctx, "madm_set_tensors")
+        self._graphs.clear()  # captured graphs hold the old parameter pointers (biases / norm affines are read in place)
         self._named, self._sig = named, sig
         self._versions = None  # force a full repack
         return True
@@ -112,10 +118,37 @@ class Engine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    # ------------------------------------------------------------------ input range guard (ldm_diffusers.py:147)
+    def _range_poll(self, wait: bool = False):
+        ev = self._range_event
+        if ev is None:
+            return
+        if wait:
+            ev.synchronize()
+        elif not ev.query():
+            return
+        self._range_event = None
+        if int(self._range_host[0]) != 0:
+            self._range_host.zero_()
+            self.range_flag.zero_()
+            raise _lib.MadmError("input image outside [0, 1] (normalised: outside [-1, 1]) in an earlier madm_extract call: the reference "
+                                 "asserts `batched_inputs['img'].min() >= -1.0 and .max() <= 1.0` (ldm_diffusers.py:147)")
+
+    def _range_publish(self):
+        self._range_host.copy_(self.range_flag, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._range_event = ev
+
+    def check_input_range(self):
+        """Wait for the last call's range flag and raise if any image since the last check left the reference's input range."""
+        self._range_poll(wait=True)
+
     def extract_graphed(self, img, cond_inputs, cond_emb, timesteps, shared_noise, *, ema=False, stages=STAGE_ALL, want_taps=False,
                         want_latents=False, want_final=False):
         """`extract` through a captured CUDA graph (static input / output buffers, one graph per call signature)."""
         B = img.shape[0]
+        self._range_poll()
         key = (B, bool(ema), stages, bool(want_taps), bool(want_latents), bool(want_final), self._packed.data_ptr(), shared_noise.data_ptr())
         g = self._graphs.get(key)
         if g is None:
@@ -140,6 +173,8 @@ class Engine:
         st["cond_emb"].copy_(cond_emb)
         st["timesteps"].copy_(timesteps)
         g["graph"].replay()
+        if stages & _lib.STAGE_VAE:
+            self._range_publish()
         out = {}
         for k, v in g["res"].items():  # fresh tensors, like the eager path: the static buffers are overwritten by the next replay
             out[k] = [t.clone() for t in v] if isinstance(v, list) else v.clone()
@@ -183,6 +218,9 @@ class Engine:
             raise _lib.MadmError("Engine.extract called before ensure_packed()")
         B = B if B is not None else (img.shape[0] if img is not None else noisy_latents_in.shape[0])
         dev = self.device
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self._range_poll()
 
         def f32c(t, shape, name):
             if t is None:
@@ -243,6 +281,8 @@ class Engine:
         a.range_flag = self.range_flag.data_ptr()
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(self.lib.madm_extract(self.ctx, C.byref(a), st), self.ctx, "madm_extract")
+        if (stages & _lib.STAGE_VAE) and not capturing:
+            self._range_publish()
         # inputs must outlive the asynchronous launches: park references until the next call
         self._keep = [img, cond_inputs, cond_emb, timesteps, shared_noise, noisy_latents_in]
         return res
@@ -250,11 +290,12 @@ class Engine:
     def set_profiling(self, on: bool):
         _lib.check(self.lib.madm_set_profiling(self.ctx, 1 if on else 0), self.ctx, "madm_set_profiling")
 
-    def profile(self) -> Dict[str, Dict[str, float]]:
-        """Per kernel family: launches, device ms (CUDA events on the launch stream), algorithmic FLOPs / bytes."""
+    def profile(self, stages: int = -1) -> Dict[str, Dict[str, float]]:
+        """Per kernel family (optionally restricted to a MADM_STAGE_* mask): launches, device ms (CUDA events on the launch stream),
+        algorithmic FLOPs / bytes and executed FLOPs."""
         p = _lib.MadmProfile()
-        _lib.check(self.lib.madm_get_profile(self.ctx, C.byref(p)), self.ctx, "madm_get_profile")
-        return {k.name.decode(): dict(launches=k.launches, ms=k.ms, flops=k.flops, bytes=k.bytes) for k in p.kind}
+        _lib.check(self.lib.madm_get_profile_stages(self.ctx, stages, C.byref(p)), self.ctx, "madm_get_profile_stages")
+        return {k.name.decode(): dict(launches=k.launches, ms=k.ms, flops=k.flops, bytes=k.bytes, exec_flops=k.exec_flops) for k in p.kind}
 
     def launch_count(self, B: int, stages: int = STAGE_ALL) -> int:
         return int(self.lib.madm_launch_count(self.ctx, B, stages))

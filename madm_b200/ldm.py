@@ -175,11 +175,18 @@ class LdmDiffusers(nn.Module):
 
     def sample_timesteps(self, batched_inputs, bsz: int) -> torch.Tensor:
         lo, hi = batched_inputs["timestep"] if "timestep" in batched_inputs else (0, 1)  # ldm_diffusers.py:156-161
+        if not 0 <= int(lo) < int(hi) <= 1000:  # q-sample indexes the 1000-entry alpha-bar table of DDPMScheduler with these
+            raise ValueError(f"timestep range must satisfy 0 <= lo < hi <= 1000 (num_train_timesteps), got {(lo, hi)}")
         return torch.randint(low=int(lo), high=int(hi), size=(bsz,), device=self.device).long()
 
     def run(self, batched_inputs, input_modal, *, stages, ema_projections=False, extra=(), want_taps=False, want_latents=False,
             timesteps: Optional[torch.Tensor] = None, out=None, **kwargs):
         use_ema_unet = bool(kwargs.get("ema_forward")) and hasattr(self, "ema_unet")  # ldm_diffusers.py:182-185
+        if torch.is_grad_enabled() and any(p.requires_grad for p in (self.ema_unet if use_ema_unet else self.unet).parameters()):
+            raise NotImplementedError(
+                "LdmDiffusers called under torch.enable_grad() with trainable UNet parameters: the engine's taps carry no grad_fn. "
+                "Call the backbone (AttentionFeatureExtractorBackbone.forward), whose training path back-propagates through the engine, "
+                "or wrap inference in torch.no_grad()")
         if "modality_mask" in kwargs:
             raise NotImplementedError("modality_mask needs input_channel_plus != 0, which is outside the shipped configs")
         want_final = bool(kwargs.get("return_unet_final_output"))
@@ -251,6 +258,12 @@ class ClipFeatureProject(nn.Module):
         super().__init__()
         if input_prefix or multi_layer_prompt or init_uncond_prompt:
             raise NotImplementedError("clip prefix / multi-layer / uncond-initialised prompts are outside the shipped config")
+        if not learnable_cond_time:
+            raise NotImplementedError("learnable_cond_time=False (no cond_emb; the reference then passes res_time_embedding=None) is "
+                                      "outside the shipped config (mtmadise_multi_lora.py:14-41 sets it True)")
+        if learnable_cond_prompt and prompt_seq_len != 77:
+            raise NotImplementedError("prompt_seq_len != 77 (the reference interpolates uncond_prompt, ldm_base.py:700-706) is outside "
+                                      "the shipped config")
         self.learnable_cond_prompt = learnable_cond_prompt
         self.learnable_cond_time = learnable_cond_time
         self.input_prefix = input_prefix

@@ -11,7 +11,7 @@ Mirrors, with the same names and argument meaning:
 * DDP's gradient averaging (``main.py:290``) as ONE all-reduce over a flat buffer, with zero gradients materialised for the
   parameters that did not take part in the step — the reference's ``add_zero_gead_on_unused_lora`` trick (``mtmadise.py:149-157``).
 
-The backward pass itself (dgrad / wgrad of the UNet) is not built yet: gradients come from whatever produced ``p.grad``.
+The backward pass itself lives in ``madm_b200/train.py`` (``madm_backward`` behind an ``autograd.Function``); these consume ``p.grad``.
 torch tensors are device memory only; there is no CPU path for the kernels (the all-reduce helper is plain torch.distributed).
 """
 import ctypes as C
@@ -76,41 +76,29 @@ def update_ema(ema_params: Iterable[torch.Tensor], params: Iterable[torch.Tensor
     return alpha
 
 
-class FusedAdamW:
+class FusedAdamW(torch.optim.Optimizer):
     """``torch.optim.AdamW`` (amsgrad=False, maximize=False) with ``clip_grad_norm_`` folded into the step.
 
-    ``FusedAdamW(params, lr, weight_decay, betas, eps)`` takes parameters or param-group dicts like torch's optimizer;
-    ``step(clip_grad=None)`` does norm -> clip -> AdamW with two multi-tensor launches per group and no host synchronisation, and
-    returns the total gradient norm as a device scalar (what the reference logs as ``grad_norm``)."""
+    A ``torch.optim.Optimizer`` subclass: parameters or param-group dicts, ``add_param_group``, ``state_dict`` / ``load_state_dict``
+    (state keys ``step`` / ``exp_avg`` / ``exp_avg_sq`` like torch's AdamW, so the reference's checkpointer saves and resumes it) and
+    LR schedulers (``LambdaLR`` of ``config_files/common/optim.py``) work unchanged.  ``step(clip_grad=None)`` does
+    norm -> clip -> AdamW with two multi-tensor launches per group and no host synchronisation, and returns the total gradient norm
+    as a device scalar (what the reference logs as ``grad_norm``).  A non-finite gradient norm skips the update on the device
+    (parameters and moments untouched), as ``GradScaler.step`` does under the reference's AMP trainer; the host-side ``step``
+    counters still advance, since nothing is read back."""
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
-        params = list(params)
-        if not params:
-            raise ValueError("optimizer got an empty parameter list")
-        groups = params if isinstance(params[0], dict) else [{"params": params}]
-        self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
-        self.param_groups: List[dict] = []
-        for g in groups:
-            g = dict(g)
-            g["params"] = list(g["params"])
-            for k, v in self.defaults.items():
-                g.setdefault(k, v)
-            self.param_groups.append(g)
-        self.state = {}
+        if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
+            raise ValueError("FusedAdamW: invalid hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._norm = None
         self._scratch = None
 
-    def zero_grad(self, set_to_none: bool = True):
-        for g in self.param_groups:
-            for p in g["params"]:
-                if p.grad is not None:
-                    if set_to_none:
-                        p.grad = None
-                    else:
-                        p.grad.zero_()
-
     @torch.no_grad()
-    def step(self, clip_grad: Optional[float] = None) -> Optional[torch.Tensor]:
+    def step(self, closure=None, clip_grad: Optional[float] = None) -> Optional[torch.Tensor]:
+        if closure is not None:
+            with torch.enable_grad():
+                closure()
         lib = _lib.load()
         active = [[p for p in g["params"] if p.grad is not None] for g in self.param_groups]
         allp = [p for ps in active for p in ps]
@@ -130,20 +118,21 @@ class FusedAdamW:
             if not ps:
                 continue
             for p in ps:
-                st = self.state.setdefault(p, {})
-                if not st:
+                st = self.state[p]
+                if len(st) == 0:
                     st["step"] = 0
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
+                st["step"] = int(st["step"]) + 1  # (a state_dict written by torch.optim.AdamW carries a tensor here)
             steps = {self.state[p]["step"] for p in ps}
             for s in sorted(steps):  # parameters that joined later have their own step count (bias correction)
                 sel = [p for p in ps if self.state[p]["step"] == s]
+                _check_tensors([self.state[p]["exp_avg"] for p in sel] + [self.state[p]["exp_avg_sq"] for p in sel], "FusedAdamW.step (state)")
                 _lib.check(lib.madm_op_adamw_step(
                     _table([p.data for p in sel]), _table([p.grad for p in sel]), _table([self.state[p]["exp_avg"] for p in sel]),
                     _table([self.state[p]["exp_avg_sq"] for p in sel]), _numel(sel), len(sel), float(g["lr"]), float(g["betas"][0]),
                     float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]), int(s),
-                    C.c_void_p(self._norm.data_ptr()) if clip_grad is not None else None, float(clip_grad) if clip_grad is not None else 0.0,
+                    C.c_void_p(self._norm.data_ptr()), float(clip_grad) if clip_grad is not None else 0.0,
                     _stream()), None, "madm_op_adamw_step")
             _bump_versions(ps)
         return self._norm

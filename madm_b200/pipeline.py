@@ -10,25 +10,40 @@ import torch
 
 
 class HostPipeline:
-    """``run(batches)`` feeds pinned host image batches through ``fn(device_images) -> {key: [device tensors]}`` and returns
-    pinned host copies of every step's ``features``; uploads / downloads overlap the compute of neighbouring steps."""
+    """``run(batches)`` feeds pinned host image batches through ``fn(device_images) -> {key: [device tensors]}``; uploads and
+    downloads overlap the compute of neighbouring steps.
 
-    def __init__(self, fn: Callable[[torch.Tensor], Dict[str, object]], device: torch.device, depth: int = 2):
+    Two ways to receive the results:
+
+    * ``run(batches)`` returns one list of pinned host tensors PER STEP.  Every step owns its buffers (the pool grows to
+      ``len(batches)`` sets and is reused by later calls), so no result is overwritten by a later step.
+    * ``run(batches, consume=f)`` streams: ``f(step_index, host_tensors)`` is called once that step's download has completed, and
+      its buffers are recycled afterwards — ``depth`` buffer sets in total, the steady-state mode of a long evaluation loop.
+      ``run`` then returns the number of steps.  The tensors passed to ``f`` are only valid during the call.
+
+    ``select`` picks the device tensors to download from ``fn``'s result (default: ``res['features']``)."""
+
+    def __init__(self, fn: Callable[[torch.Tensor], Dict[str, object]], device: torch.device, depth: int = 2,
+                 select: Optional[Callable[[Dict[str, object]], Sequence[torch.Tensor]]] = None):
         self.fn, self.device, self.depth = fn, device, max(2, depth)
+        self.select = select or (lambda res: res["features"])
         self.copy_stream = torch.cuda.Stream(device=device)
-        self._host_out: List[Optional[List[torch.Tensor]]] = [None] * self.depth
+        self._pool: List[List[torch.Tensor]] = []
 
     def _host_buffers(self, slot: int, like: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-        bufs = self._host_out[slot]
-        if bufs is None or any(b.shape != t.shape or b.dtype != t.dtype for b, t in zip(bufs, like)):
+        while len(self._pool) <= slot:
+            self._pool.append([])
+        bufs = self._pool[slot]
+        if len(bufs) != len(like) or any(b.shape != t.shape or b.dtype != t.dtype for b, t in zip(bufs, like)):
             bufs = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in like]
-            self._host_out[slot] = bufs
+            self._pool[slot] = bufs
         return bufs
 
-    def run(self, batches: Sequence[torch.Tensor]) -> List[List[torch.Tensor]]:
+    def run(self, batches: Sequence[torch.Tensor], consume: Optional[Callable[[int, List[torch.Tensor]], None]] = None):
         main = torch.cuda.current_stream(self.device)
         cs = self.copy_stream
         results: List[List[torch.Tensor]] = []
+        pending: List[tuple] = []  # (step, slot, host buffers, download-complete event) not yet handed to `consume`
         uploaded = None
         if len(batches):
             cs.wait_stream(main)
@@ -42,17 +57,31 @@ class HostPipeline:
             x.record_stream(main)
             res = self.fn(x)
             done = torch.cuda.Event(); done.record(main)
-            feats = res["features"]
+            feats = list(self.select(res))
+            if consume is not None and len(pending) == self.depth:  # recycle the oldest slot: its consumer runs first
+                j, _, host_j, ev_j = pending.pop(0)
+                ev_j.synchronize()
+                consume(j, host_j)
+            slot = i % self.depth if consume is not None else i
             with torch.cuda.stream(cs):
                 if i + 1 < len(batches):  # next step's upload first: it is on the critical path of the next compute
                     xn = batches[i + 1].to(self.device, non_blocking=True)
                     evn = torch.cuda.Event(); evn.record(cs)
                     uploaded = (xn, evn)
                 cs.wait_event(done)
-                host = self._host_buffers(i % self.depth, feats)
+                host = self._host_buffers(slot, feats)
                 for h, d in zip(host, feats):
                     d.record_stream(cs)
                     h.copy_(d, non_blocking=True)
-            results.append(host)
+                dl = torch.cuda.Event(); dl.record(cs)
+            if consume is not None:
+                pending.append((i, slot, host, dl))
+            else:
+                results.append(host)
         main.wait_stream(cs)
+        if consume is not None:
+            for j, _, host_j, ev_j in pending:
+                ev_j.synchronize()
+                consume(j, host_j)
+            return len(batches)
         return results

@@ -26,6 +26,23 @@ except Exception:  # peft absent (this image): standalone marker class
 LORA_TARGETS = ("to_k", "to_q", "to_v", "to_out.0")
 Spec = List[Tuple[str, Tuple[int, ...]]]
 
+_EMPTY_INIT = False
+
+
+class empty_init:
+    """``with empty_init(): ...`` builds holders with uninitialised storage (``torch.empty``: no random-init kernels, no host work)
+    for callers that fill every parameter right afterwards with ``load_state_dict`` — the normal MADM workflow (checkpoint load)."""
+
+    def __enter__(self):
+        global _EMPTY_INIT
+        self._prev, _EMPTY_INIT = _EMPTY_INIT, True
+        return self
+
+    def __exit__(self, *exc):
+        global _EMPTY_INIT
+        _EMPTY_INIT = self._prev
+        return False
+
 
 # ----------------------------------------------------------------------------------------- specs
 def _res(p: str, cin: int, cout: int, temb: Optional[int]) -> Spec:
@@ -192,7 +209,7 @@ def build_tree(spec: Spec, kind: str = "torch", device=None, seed: Optional[int]
             if p not in node._modules:
                 node.add_module(p, ParamNode())
             node = node._modules[p]
-        t = _default_init(name, shape, kind, gen, device)
+        t = torch.empty(shape, device=device) if _EMPTY_INIT else _default_init(name, shape, kind, gen, device)
         if t is None:
             bound = 1.0 / math.sqrt(fan_in.get(name.rsplit(".", 1)[0], max(1, shape[0])))
             t = (torch.rand(shape, generator=gen, device=device) * 2.0 - 1.0) * bound
@@ -219,12 +236,14 @@ class LoraLinearParams(ParamNode, _TunerBase):
         out_f, in_f = self.base_layer.weight.shape
         dev = self.base_layer.weight.device
         a, b = ParamNode(), ParamNode()
-        if init == "gaussian":
+        if _EMPTY_INIT:
+            wa = torch.empty(r, in_f, device=dev)
+        elif init == "gaussian":
             wa = torch.randn(r, in_f, device=dev) / r
         else:
             wa = (torch.rand(r, in_f, device=dev) * 2 - 1) / math.sqrt(in_f)
         a.register_parameter("weight", nn.Parameter(wa))
-        b.register_parameter("weight", nn.Parameter(torch.zeros(out_f, r, device=dev)))
+        b.register_parameter("weight", nn.Parameter(torch.empty(out_f, r, device=dev) if _EMPTY_INIT else torch.zeros(out_f, r, device=dev)))
         self.lora_A[name] = a
         self.lora_B[name] = b
         self.r[name], self.lora_alpha[name], self.scaling[name] = r, alpha, alpha / r

@@ -69,7 +69,8 @@ def test_full_path_parity_others(pair, cuda_device):
     _check("unet_tap64", t64, taps[3])
     for k, got in zip(["s2", "s3", "s4", "s5"], res["features"]):
         _check(k, got, feats[k])
-    out = pb(img, input_modal="others")["output_features"]
+    with torch.no_grad():
+        out = pb(img, input_modal="others")["output_features"]
     assert list(out.keys()) == ["s2", "s3", "s4", "s5"]
     assert out["s2"].shape == (2, 512, 128, 128) and out["s5"].shape == (2, 512, 16, 16)
 
@@ -83,7 +84,8 @@ def test_adapter_switch_and_rgb(pair, cuda_device):
     set_adapter(ob.feature_extractor.ldm_extractor.unet, ["default"])
     set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "default")
     _, feats = _oracle_taps(ob, img, "rgb")
-    out = pb(img, input_modal="rgb")["output_features"]
+    with torch.no_grad():
+        out = pb(img, input_modal="rgb")["output_features"]
     for k in out:
         _check("rgb/" + k, out[k], feats[k])
 
@@ -96,7 +98,8 @@ def test_ema_forward(pair, cuda_device):
     set_adapter(ob.feature_extractor.ldm_extractor.unet, ["Depth"])
     set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
     _, feats = _oracle_taps(ob, img, "others", ema=True)
-    out = pb(img, input_modal="others", ema_forward=True)["output_features"]
+    with torch.no_grad():
+        out = pb(img, input_modal="others", ema_forward=True)["output_features"]
     for k in out:
         _check("ema/" + k, out[k], feats[k])
 
@@ -270,19 +273,29 @@ def test_inplace_parameter_update_repacks(pair, cuda_device):
 
 def test_host_pipeline_matches_direct_calls(pair, cuda_device):
     """madm_b200.pipeline.HostPipeline (uploads / downloads of neighbouring steps overlapped with compute on a copy stream) returns
-    exactly what direct calls return, step by step."""
+    exactly what direct calls return, step by step — with the DEFAULT depth (2) and more batches than that, in both modes: every
+    returned step owns its pinned buffers (no aliasing between results[i] and results[i + depth]), and the streaming `consume`
+    callback sees every step before its buffers are recycled."""
     from oracle import synthetic
     from madm_b200.pipeline import HostPipeline
     _, pb = pair
     set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
-    batches = [synthetic.synthetic_images(2, seed=60 + i).pin_memory() for i in range(4)]
+    batches = [synthetic.synthetic_images(2, seed=60 + i).pin_memory() for i in range(5)]
     with torch.no_grad():
         direct = [[t.cpu() for t in pb._extract(b.to(cuda_device), "others", False, None)["features"]] for b in batches]
-        pipe = HostPipeline(lambda x: pb._extract(x, "others", False, None), cuda_device, depth=len(batches))
+        pipe = HostPipeline(lambda x: pb._extract(x, "others", False, None), cuda_device)
+        assert pipe.depth == 2 < len(batches)
         piped = pipe.run(batches)
         torch.cuda.synchronize()
-    for d, p in zip(direct, piped):
-        for a, b in zip(d, p):
+        assert len({t.data_ptr() for step in piped for t in step}) == sum(len(step) for step in piped)
+        for d, p in zip(direct, piped):
+            for a, b in zip(d, p):
+                assert torch.equal(a, b)
+        seen = {}
+        n = pipe.run(batches, consume=lambda i, host: seen.__setitem__(i, [t.clone() for t in host]))
+    assert n == len(batches) and sorted(seen) == list(range(len(batches)))
+    for i, d in enumerate(direct):
+        for a, b in zip(d, seen[i]):
             assert torch.equal(a, b)
 
 
@@ -377,3 +390,145 @@ def test_ema_unet_teacher(cuda_device):
     assert max_rel(out_t["s3"], out_s["s3"]) > 5e-2  # the two UNets really differ
     del pb, ob
     torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------------- shipped-configuration parity holes (round 2)
+def test_zero_adapter_configuration(cuda_device):
+    """`model.lora_configs = []` — what all three shipped experiment files set (mtmadise_cityscapes_rgb_to_depth_11.py:10; SURVEY §8
+    a-8 "must support both"): no peft wrapping, so the attention projections keep their plain diffusers keys (`to_q.weight`, not
+    `to_q.base_layer.weight`), set_lora_adapter is a no-op (mtmadise.py:131-132) and the pack pass takes its no-adapter branch.
+    A checkpoint-style strict load_state_dict with the un-wrapped keys, then 'others' and 'rgb' against the oracle."""
+    from oracle import synthetic
+    global _MODE
+    _MODE = "fp16"
+    ob = synthetic.build_backbone(lora_configs=()).to(cuda_device)
+    pb = build_product_backbone(cuda_device, lora_configs=())
+    sd = ob.state_dict()
+    assert any(k.endswith("attn1.to_q.weight") for k in sd) and not any("base_layer" in k or "lora_" in k for k in sd)
+    pb.load_state_dict(sd, strict=True)
+    unet = pb.feature_extractor.ldm_extractor.unet
+    assert unet.active_adapter() is None and not list(unet.lora_layers())
+    set_lora_adapter(unet, "Depth")  # no-op without adapters, like the reference
+    img = synthetic.synthetic_images(2, seed=71).to(cuda_device)
+    for modal in ("others", "rgb"):
+        taps, feats = _oracle_taps(ob, img, modal)
+        with torch.no_grad():
+            res = pb._extract(img, modal, False, None, want_taps=True)
+        for name, got, ref in zip(("enc_tap", "unet_tap64", "unet_tap32", "unet_tap16"), res["taps"], (taps[0], taps[3], taps[2], taps[1])):
+            _check(f"no-lora/{modal}/{name}", got, ref)
+        for k, got in zip(["s2", "s3", "s4", "s5"], res["features"]):
+            _check(f"no-lora/{modal}/{k}", got, feats[k])
+    del pb, ob
+    torch.cuda.empty_cache()
+
+
+def test_full_batch_against_oracle_config2(pair, cuda_device):
+    """BASELINE configs[1] compared DIRECTLY: the product's batch-8 call (the bench shape, CUDA-graph replay) against the fp32 oracle
+    run on the same 8 images, every tap and every projected map."""
+    from oracle import synthetic
+    from oracle.lora import set_adapter
+    ob, pb = pair
+    if _MODE != "fp16":
+        pytest.skip("one dtype is enough at the full batch")
+    set_adapter(ob.feature_extractor.ldm_extractor.unet, ["Depth"])
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    img = synthetic.synthetic_images(8, seed=81).to(cuda_device)
+    taps, feats = _oracle_taps(ob, img, "others")
+    with torch.no_grad():
+        res = pb._extract(img, "others", False, None, want_taps=True)
+    for name, got, ref in zip(("enc_tap", "unet_tap64", "unet_tap32", "unet_tap16"), res["taps"], (taps[0], taps[3], taps[2], taps[1])):
+        _check("b8/" + name, got, ref)
+    for k, got in zip(["s2", "s3", "s4", "s5"], res["features"]):
+        _check("b8/" + k, got, feats[k])
+        for i in range(8):  # per image too: one bad image cannot hide in the batch statistics
+            assert max_rel(got[i], feats[k][i]) <= REL_MAX[_MODE], (k, i)
+
+
+@pytest.mark.parametrize("same_cond_params,mix", [(True, False), (False, True), (True, True), (False, False)])
+def test_mixed_modal_conditioning(cuda_device, same_cond_params, mix):
+    """input_modal='mixed' (the student's pass on DACS-mixed images, mtmadise.py:286-302) with `same_cond_params=True` — every shipped
+    experiment sets it, so clip_project_others IS clip_project_rgb (ldm_base.py:811-812) — and with `mix_source_target_prompt`, which
+    averages the two parameter sets (ldm_base.py:880-884); end to end against the oracle, plus the random conditioning modes
+    ('masked_prompt', 'prompt_perturbation', 'rand_prompt', ldm_base.py:892-903) at the conditioning level under the same seed."""
+    from oracle import synthetic
+    from oracle import backbone as obk
+    from oracle.lora import set_adapter
+    from madm_b200.ldm import BasePromptTimeGenerator
+    global _MODE
+    _MODE = "fp16"
+    ob = synthetic.build_backbone(same_cond_params=same_cond_params).to(cuda_device)
+    pb = build_product_backbone(cuda_device, same_cond_params=same_cond_params)
+    og, pg = ob.feature_extractor, pb.feature_extractor
+    assert (pg.clip_project_others is pg.clip_project_rgb) == same_cond_params
+    pb.load_state_dict(ob.state_dict(), strict=True)
+    for g in (og, pg):
+        g.mix_source_target_prompt = mix
+        g.mask_prompt_ratio, g.prompt_perturbation, g.rand_prompt_scale = 0.3, 0.05, 2.0
+    set_adapter(og.ldm_extractor.unet, ["Depth"])
+    set_lora_adapter(pg.ldm_extractor.unet, "Depth")
+    img = synthetic.synthetic_images(2, seed=91).to(cuda_device)
+    with torch.no_grad():
+        ref = ob(img, input_modal="mixed")["output_features"]
+        out = pb(img, input_modal="mixed")["output_features"]
+        out2 = pb(img, input_modal="mixed")["output_features"]  # second call: served from the conditioning cache where eligible
+    for k in ref:
+        _check(f"mixed(same={same_cond_params},mix={mix})/{k}", out[k], ref[k])
+        assert torch.equal(out[k], out2[k])
+    if same_cond_params and mix:  # conditioning only, bit-exact under the same seed
+        captured = {}
+        og.ldm_extractor.forward = lambda bi, modal, **kw: captured.update(bi)
+        for modal in ("masked_prompt", "prompt_perturbation", "rand_prompt", "mixed", "others", "rgb"):
+            torch.manual_seed(5)
+            with torch.no_grad():
+                og(dict(img=img), modal)
+                o_ci, o_ce = captured["cond_inputs"].clone(), captured["cond_emb"].clone()
+                torch.manual_seed(5)
+                bi = pg.conditioning(dict(img=img), modal)
+            assert torch.equal(bi["cond_inputs"], o_ci) and torch.equal(bi["cond_emb"], o_ce), modal
+            assert bi["cond_inputs"].shape == (2, 77, 768) and bi["cond_emb"].shape == (2, 1, 1280)
+    del pb, ob
+    torch.cuda.empty_cache()
+
+
+def test_input_range_guard_and_timestep_validation(pair, cuda_device):
+    """The reference asserts the normalised image stays in [-1, 1] with a host sync (ldm_diffusers.py:147); here the kernel raises a
+    device flag that is checked on the NEXT call (or by check_input_range()), so steady-state inference never synchronises.  Timestep
+    ranges outside the 1000-entry alpha-bar table are rejected on the host."""
+    from oracle import synthetic
+    from madm_b200._lib import MadmError
+    _, pb = pair
+    eng = pb.feature_extractor.ldm_extractor.engine()
+    img = synthetic.synthetic_images(1, seed=3).to(cuda_device)
+    with torch.no_grad():
+        pb(img, input_modal="others")
+        eng.check_input_range()  # in range: no error
+        pb(img * 1.5, input_modal="others")  # leaves [0, 1]
+        with pytest.raises(MadmError, match="outside"):
+            eng.check_input_range()
+        pb(img * 1.5, input_modal="others")
+        torch.cuda.synchronize()
+        with pytest.raises(MadmError, match="outside"):
+            pb(img, input_modal="others")  # lazily, on the next call
+        pb(img, input_modal="others")  # the flag was reset by the raise
+        eng.check_input_range()
+        for bad in ((0, 1001), (-1, 5), (10, 10), (1000, 1001)):
+            with pytest.raises(ValueError, match="timestep"):
+                pb(img, input_modal="others", timestep=bad)
+
+
+def test_call_under_grad_raises_or_trains(pair, cuda_device):
+    """A call under torch.enable_grad() with trainable parameters must never hand back grad-free tensors silently (the reference's
+    student passes run under grad, mtmadise.py:240-256): parameter sets the training path does not cover raise."""
+    from oracle import synthetic
+    _, pb = pair
+    ldm = pb.feature_extractor.ldm_extractor
+    img = synthetic.synthetic_images(1, seed=3).to(cuda_device)
+    assert any(p.requires_grad for p in ldm.unet.parameters())  # finetune_unet='all' (mtmadise_multi_lora.py:34)
+    with torch.enable_grad():
+        with pytest.raises(NotImplementedError):
+            pb(img, input_modal="others")  # whole-UNet fine-tuning: outside the LoRA training step the engine back-propagates
+        with pytest.raises(NotImplementedError):
+            pb.feature_extractor(dict(img=img), "others")
+    with torch.no_grad():
+        out = pb(img, input_modal="others")["output_features"]
+    assert all(not v.requires_grad for v in out.values())

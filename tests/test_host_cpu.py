@@ -31,7 +31,7 @@ def test_struct_layouts_match_header_sizes():
     from madm_b200 import _lib
     assert C.sizeof(_lib.MadmTensor) == 8 + 8 + 8 + 32  # name, data, ndim(+pad), shape[4]
     assert C.sizeof(_lib.MadmGemmSeg) == 8 + 6 * 4 + 9 + 9 + 2 + 9 * 4  # a, 6 ints, dx, dy, pad, b_off
-    assert C.sizeof(_lib.MadmProfile) == 5 * (32 + 8 + 3 * 8)
+    assert C.sizeof(_lib.MadmProfile) == 5 * (32 + 8 + 4 * 8)
 
 
 def test_ctypes_structs_match_the_compiled_header(tmp_path):

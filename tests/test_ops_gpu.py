@@ -398,7 +398,7 @@ def test_gn_add_relu_nchw(ops, cuda_device):
 
 
 # ---------------------------------------------------------------------------------------------- attention
-@pytest.mark.parametrize("impl", [0, 1])  # 0 = tcgen05/TMEM kernel (product path), 1 = mma.sync kernel
+@pytest.mark.parametrize("impl", [0])  # the tcgen05/TMEM kernel (the round-1 mma.sync kernel is gone from the library)
 @pytest.mark.parametrize("B,heads,d,Nq,Nk", [(2, 8, 40, 4096, 4096), (1, 8, 80, 1024, 1024), (2, 8, 160, 256, 256), (1, 8, 160, 64, 64),
                                              (2, 8, 40, 4096, 77), (2, 8, 160, 64, 77), (1, 8, 80, 1024, 77)])
 def test_attention(ops, cuda_device, B, heads, d, Nq, Nk, impl):

@@ -135,3 +135,53 @@ def test_color_jitter(cuda_device):
                                   params["saturation_factor"], params["hue_factor"]) - mean.view(1, 3, 1, 1).to(cuda_device)) / std.view(1, 3, 1, 1).to(cuda_device)
     err2 = (got2 - ref2).abs()
     assert (err2 > 1e-4).float().mean().item() < 1e-3, ((err2 > 1e-4).float().mean().item(), err2.max().item())
+
+
+def test_fused_adamw_is_a_torch_optimizer(cuda_device):
+    """The reference's training loop drives the optimizer through torch.optim machinery (LambdaLR scheduler,
+    config_files/common/optim.py; checkpointer state_dict / load_state_dict): FusedAdamW must behave as one, resume bit-exactly
+    from a saved state — also from one written by torch.optim.AdamW (tensor `step`) — and skip the step on a non-finite norm."""
+    from madm_b200.optim import FusedAdamW
+    assert issubclass(FusedAdamW, torch.optim.Optimizer)
+    kw = dict(lr=5e-3, weight_decay=0.05)
+    p1 = [torch.nn.Parameter(t.clone()) for t in _make(cuda_device, 1)[:6]]
+    o1 = FusedAdamW(p1, **kw)
+    sched = torch.optim.lr_scheduler.LambdaLR(o1, lambda it: 1.0 / (1 + it))
+    for it in range(3):
+        for p, g in zip(p1, _make(cuda_device, 200 + it)):
+            p.grad = g.clone()
+        o1.step(clip_grad=1.0)
+        sched.step()
+    assert abs(o1.param_groups[0]["lr"] - 5e-3 / 4) < 1e-12
+    sd = o1.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    # resume into a fresh optimizer over copies of the parameters, and into torch.optim.AdamW: one more identical step each
+    p2 = [torch.nn.Parameter(p.detach().clone()) for p in p1]
+    p3 = [torch.nn.Parameter(p.detach().clone()) for p in p1]
+    o2 = FusedAdamW(p2, **kw)
+    o2.load_state_dict(sd)
+    o3 = torch.optim.AdamW(p3, **kw)
+    sd3 = {"state": {k: dict(v, step=torch.tensor(float(v["step"]))) for k, v in sd["state"].items()}, "param_groups": sd["param_groups"]}
+    o3.load_state_dict(sd3)
+    grads = _make(cuda_device, 300)
+    for ps in (p1, p2, p3):
+        for p, g in zip(ps, grads):
+            p.grad = g.clone()
+    o1.step(); o2.step(); o3.step()
+    for a, b, c in zip(p1, p2, p3):
+        assert torch.equal(a, b)
+        assert torch.allclose(a, c, rtol=2e-6, atol=1e-7)
+    # and back: a state written by torch's AdamW (tensor step) resumes in FusedAdamW
+    o4 = FusedAdamW([torch.nn.Parameter(p.detach().clone()) for p in p3], **kw)
+    o4.load_state_dict(o3.state_dict())
+    assert all(int(s["step"]) == 4 for s in o4.state.values())
+    # non-finite gradient: the update is skipped on the device (GradScaler semantics), nothing becomes NaN
+    before = [p.detach().clone() for p in p1]
+    m_before = [o1.state[p]["exp_avg"].clone() for p in p1]
+    for p, g in zip(p1, grads):
+        p.grad = g.clone()
+    p1[2].grad.view(-1)[0] = float("inf")
+    norm = o1.step(clip_grad=1.0)
+    assert not torch.isfinite(norm).item()
+    for p, b, m in zip(p1, before, m_before):
+        assert torch.equal(p, b) and torch.equal(o1.state[p]["exp_avg"], m)

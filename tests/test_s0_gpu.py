@@ -65,6 +65,7 @@ def test_s0_variant_parity(pair, cuda_device):
         _check(k, got, feats[k])
 
 
+@torch.no_grad()
 def test_s0_public_forward_and_final_output_dict(pair, cuda_device):
     """backbone(img, return_unet_final_output=True) returns (feature dict, {'before_vae.decoder', 'after_vae.decoder'}) as
     feature_extractor.py:164-166 / ldm_diffusers.py:211-215; without the kwarg just the dict; graph replay == eager launch."""
@@ -169,3 +170,24 @@ def test_module_level_vae_encoder(pair, cuda_device):
     _check("vae_encoder/latents", lat, ref)
     with pytest.raises(NotImplementedError):
         vae_encoder(pb.feature_extractor.ldm_extractor.vae, x, encoder_block_indices=[5])  # no encoder tap in the s0 configuration
+
+
+def test_s0_zero_adapter_shipped_configuration(cuda_device):
+    """The configuration the three shipped experiment files actually run: the s0 variant with `model.lora_configs = []`
+    (mtmadise_cityscapes_rgb_to_depth_11.py:10, :47-55) and `same_cond_params=True` (:41) — un-wrapped `to_q.weight` keys, no adapter
+    fold, one shared prompt / time parameter set — against the oracle built the same way."""
+    from oracle import synthetic
+    ob = synthetic.build_backbone(lora_configs=(), variant="s0", same_cond_params=True).to(cuda_device)
+    pb = build_product_backbone(cuda_device, lora_configs=(), variant="s0", same_cond_params=True)
+    sd = ob.state_dict()
+    assert not any("base_layer" in k or "lora_" in k for k in sd)
+    pb.load_state_dict(sd, strict=True)
+    img = synthetic.synthetic_images(1, seed=73).to(cuda_device)
+    with torch.no_grad():
+        ref, rfin = ob(img, input_modal="others", return_unet_final_output=True)
+        out, fin = pb(img, input_modal="others", return_unet_final_output=True)
+    _check("no-lora/before_vae.decoder", fin["before_vae.decoder"], rfin["before_vae.decoder"])
+    for k in ("s0", "s3", "s4", "s5"):
+        _check("no-lora/" + k, out["output_features"][k], ref["output_features"][k])
+    del pb, ob
+    torch.cuda.empty_cache()
