@@ -9,6 +9,12 @@ rows a-1..a-9) over one batch of 8 synthetic 512x512 images per GPU (BASELINE.js
 seeded as SURVEY §8d).  For N > 1 the driver launches this file with torchrun: one rank per GPU, images batch-sharded,
 no collective on the data path (weak scaling); timing = max over ranks of the CUDA-event time of exactly K steps,
 bracketed by barrier + synchronize.  Rank 0 prints ONE JSON line.
+
+--config selects the measured workload (default `base` = BASELINE.json configs[1], the contract's bench line):
+  base         8 x 3 x 512^2 per GPU, feature extraction a-1..a-9                                   (BASELINE configs[1])
+  slide1024    1024^2 sliding-window inference, 9 crops per image, images sharded over the ranks    (BASELINE configs[2])
+  teacher2048  1024 x 2048 EMA-teacher pass: 21 crops per image -> EMA projections -> head -> pseudo-labels (BASELINE configs[3])
+  train        LoRA training step, 2 images per GPU: forward + backward + gradient all-reduce + AdamW + EMA   (BASELINE configs[4])
 """
 import argparse
 import json
@@ -137,7 +143,10 @@ def run_product(args, rank, local_rank, world):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    numa = None
     if world > 1:
+        from madm_b200.sharding import bind_to_gpu_numa
+        numa = bind_to_gpu_numa(local_rank)  # before any pinned allocation: first touch places the host buffers next to the GPU
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     torch.manual_seed(1234 + rank)
@@ -175,8 +184,26 @@ def run_product(args, rank, local_rank, world):
     from madm_b200.pipeline import HostPipeline
     pipe = HostPipeline(lambda x: bb._extract(x, "others", False, None), dev)
 
-    def run_e2e_pipelined(steps):
-        return pipe.run([img_host] * steps)
+    def run_e2e_pipelined(steps):  # streaming mode: `depth` pinned buffer sets, each step's result is handed over once downloaded
+        return pipe.run([img_host] * steps, consume=lambda i, host: None)
+
+    # The faithful end of MADM's eval loop: the feature dict never leaves the device -- the head consumes it (mtmadise.py:685-688)
+    # and only the arg-max labels go to the host (evaluation/d2_evaluator.py:106).  Backbone + head stage + fused
+    # upsample / softmax / arg-max on the device, 8 x 512 x 512 int64 labels downloaded per step.
+    from madm_b200 import teacher as mteacher
+    from madm_b200.head import DAFormerHead
+    from test_head_gpu import HEAD_KW
+    head = None
+    if args.variant == "base":
+        head = DAFormerHead(**HEAD_KW, device=dev, compute_dtype=args.dtype).eval()
+
+    def seg_step(x):
+        res = bb._extract(x, "others", False, None)
+        logits = head({"output_features": dict(zip(("s2", "s3", "s4", "s5"), res["features"]))})
+        label, _, _, _ = mteacher.pseudo_labels(logits, (512, 512), 0.0)
+        return {"label": [label]}
+
+    pipe_head = HostPipeline(seg_step, dev, select=lambda res: res["label"]) if head is not None else None
 
     def barrier():
         if world > 1:
@@ -219,24 +246,44 @@ def run_product(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         barrier()
         ms_e2e = t.item()
+        ms_e2e_head = None
+        if pipe_head is not None:
+            pipe_head.run([img_host] * 2, consume=lambda i, host: None)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pipe_head.run([img_host] * args.steps, consume=lambda i, host: None)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            barrier()
+            ms_e2e_head = t.item()
         # roofline inputs: per-kernel-family CUDA-event timing of instrumented steps on the launch stream
         eng = ldm.engine()
         prof = None
         if rank == 0:
             eng.set_profiling(True)
-            acc = None
+            acc, acc_unet = None, None
             psteps = 2
+            from madm_b200 import _lib as mlib
+
+            def add(dst, p):
+                if dst is None:
+                    return p
+                for k in p:
+                    for f in p[k]:
+                        dst[k][f] += p[k][f]
+                return dst
+
             for _ in range(psteps):
                 bb._extract(img_dev, "others", False, None, out=outs_dev)  # stream launches: the per-launch events live there
-                p = eng.profile()
-                if acc is None:
-                    acc = p
-                else:
-                    for k in p:
-                        for f in ("launches", "ms", "flops", "bytes"):
-                            acc[k][f] += p[k][f]
+                acc = add(acc, eng.profile())
+                acc_unet = add(acc_unet, eng.profile(mlib.STAGE_UNET))
             eng.set_profiling(False)
             prof = {k: {f: v[f] / psteps for f in v} for k, v in acc.items()}
+            prof_unet = {k: {f: v[f] / psteps for f in v} for k, v in acc_unet.items()}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -257,9 +304,25 @@ def run_product(args, rank, local_rank, world):
             gemm_traffic = json.load(f)["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass
+    # the north_star's target: the UNet's contractions (convs / linears AND the attention products) against the sustained tensor peak
+    u_ms = prof_unet["gemm_tc"]["ms"] + prof_unet["flash_attention"]["ms"]
+    u_fl = prof_unet["gemm_tc"]["flops"] + prof_unet["flash_attention"]["flops"]
+    roofline_unet = {
+        "kernels": "UNet stage: gemm_tc_kernel + fa_tc_kernel launches", "bound": "tensor", "unit": "TFLOP/s",
+        "achieved": u_fl / (u_ms / 1e3) / 1e12, "peak": peaks["tflops_sustained"], "frac": u_fl / (u_ms / 1e3) / 1e12 / peaks["tflops_sustained"],
+        "algorithmic_gflop_per_step": u_fl / 1e9, "ms_per_step": u_ms,
+        "gemm": {"tflops": prof_unet["gemm_tc"]["flops"] / (prof_unet["gemm_tc"]["ms"] / 1e3) / 1e12, "ms": prof_unet["gemm_tc"]["ms"],
+                 "launches": prof_unet["gemm_tc"]["launches"]},
+        "attention": {"tflops": prof_unet["flash_attention"]["flops"] / (prof_unet["flash_attention"]["ms"] / 1e3) / 1e12,
+                      "ms": prof_unet["flash_attention"]["ms"], "launches": prof_unet["flash_attention"]["launches"]},
+        "stage_ms_by_family": {k: v["ms"] for k, v in prof_unet.items()},
+    }
     roofline = {
         "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM: all convs / linears)", "bound": "tensor",
         "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": gemm_tflops / peaks["tflops_sustained"],
+        "flops": "algorithmic (2*MAC of the reference's convs / linears; K padding and the identity-weight residual segments of the 16-bit "
+                 "VAE stream are excluded)",
+        "executed_tflops": gemm["exec_flops"] / (gemm["ms"] / 1e3) / 1e12,
         "peak_source": peaks["source"] + ", sustained cuBLAS bf16 figure (kernel timed inside a long step)",
         "traffic": gemm_traffic, "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01_gemm_dram_traffic.json)",
         "algorithmic_bytes_per_launch": gemm["bytes"] / max(1, gemm["launches"]),
@@ -296,8 +359,141 @@ def run_product(args, rank, local_rank, world):
                 "cuda_graph": bool(graphed)},
         "gpu_launches": launches * args.steps,
         "roofline": roofline,
+        "roofline_unet": roofline_unet,
         "cpu_baseline": cpu_base,
     }
+    if ms_e2e_head is not None:
+        line["e2e_head"] = {"value": imgs / (ms_e2e_head / 1e3), "unit": UNIT, "ms_per_step": ms_e2e_head / args.steps,
+                            "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": B * 512 * 512 * 8,
+                            "api": "HostPipeline around backbone -> madm_b200.head.DAFormerHead (MADM_STAGE_HEAD) -> teacher.pseudo_labels "
+                                   "(fused upsample / softmax / arg-max): the feature dict stays on the device as in MADM's eval loop "
+                                   "(mtmadise.py:685-688), only the int64 label map is downloaded (d2_evaluator.py:106)"}
+    if numa:
+        line["config"]["numa"] = numa
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_slide(args, rank, local_rank, world):
+    """BASELINE configs[2] / configs[3]: sliding-window inference over full-resolution images, crops as the engine's batch dimension
+    (feature_extractor.py:199-278), images sharded over the ranks with no collective (weak scaling: --images per GPU).
+      slide1024   : 1024 x 1024, 9 crops / image, input_modal 'others' -> merged feature dict (what slide_forward returns)
+      teacher2048 : 1024 x 2048, 21 crops / image, 'others' + ema_forward -> EMA-projected merged features -> DAFormer head on the
+                    256 x 512 grid -> fused upsample / softmax / max -> pseudo-labels + weights (mtmadise.py:335-349)"""
+    import torch
+    import torch.distributed as dist
+    from helpers import build_product_backbone, set_lora_adapter
+    from madm_b200 import teacher as mteacher
+    from madm_b200.head import DAFormerHead
+    from test_head_gpu import HEAD_KW
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    numa = None
+    if world > 1:
+        from madm_b200.sharding import bind_to_gpu_numa
+        numa = bind_to_gpu_numa(local_rank)
+        dist.init_process_group("nccl", device_id=dev)
+    teacher = args.config == "teacher2048"
+    H, W = (1024, 2048) if teacher else (1024, 1024)
+    n_img = args.images
+    torch.manual_seed(1234 + rank)
+    bb = build_product_backbone(dev, compute_dtype=args.dtype)
+    ldm = bb.feature_extractor.ldm_extractor
+    with torch.no_grad():
+        g = torch.Generator(device=dev).manual_seed(99)
+        for _, m in ldm.unet.lora_layers():
+            for a in m.lora_B:
+                m.lora_B[a].weight.copy_(torch.randn(m.lora_B[a].weight.shape, device=dev, generator=g) * 0.02)
+    set_lora_adapter(ldm.unet, "Depth")
+    bb._slide_inference = True
+    crops = len(bb.slide_windows(H, W))
+    bb.crop_batch = 18 if not teacher else 21  # whole images per engine call: 2 x 9 or 1 x 21 crops (CUDA-graph replay per call)
+    head = DAFormerHead(**HEAD_KW, device=dev, compute_dtype=args.dtype).eval() if teacher else None
+    gi = torch.Generator().manual_seed(rank)
+    img_host = torch.rand(n_img, 3, H, W, generator=gi).pin_memory()
+    img_dev = img_host.to(dev)
+
+    def step(x):
+        out = bb.slide_forward(x, "others", ema_forward=teacher)
+        if not teacher:
+            return list(out["output_features"].values())
+        logits = head(out)                                       # [n, 19, 256, 512]
+        label, prob, weight, count = mteacher.pseudo_labels(logits, (H, W), 0.968)
+        return [label, weight]
+
+    host_out = None
+
+    def step_e2e():
+        nonlocal host_out
+        x = img_host.to(dev, non_blocking=True)
+        res = step(x)
+        if host_out is None:
+            host_out = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in res]
+        for h, d in zip(host_out, res):
+            h.copy_(d, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return ms.item(), clocks
+
+    with torch.no_grad():
+        for _ in range(max(3, args.warmup)):
+            step(img_dev)
+        ms, clocks = timed(lambda: step(img_dev), args.steps, ClockSampler(local_rank) if rank == 0 else None)
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, _ = timed(step_e2e, args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    eng = ldm.engine()
+    imgs = n_img * world * args.steps
+    calls = (n_img + max(1, bb.crop_batch // crops) - 1) // max(1, bb.crop_batch // crops)
+    per_call = crops * max(1, bb.crop_batch // crops)
+    line = {
+        "metric": METRIC, "value": imgs / (ms / 1e3), "unit": "full-resolution images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic (seeded rand images, random-init SD-1.4 weights + r16 LoRA, SURVEY §8d)",
+        "crops_per_s": imgs * crops / (ms / 1e3),
+        "config": {"workload": (f"BASELINE configs[3]: {n_img} x 3 x 1024 x 2048 per GPU, EMA-teacher pseudo-label pass: 21 crops / image -> "
+                                "feature extraction with ema_feature_projections -> merged maps -> DAFormer head (256 x 512 grid) -> "
+                                "pseudo-labels + weights (mtmadise.py:335-349)") if teacher else
+                               (f"BASELINE configs[2]: {n_img} x 3 x 1024 x 1024 per GPU, sliding-window inference: 9 crops / image at stride 256 "
+                                "-> merged s2..s5 maps (feature_extractor.py:199-278)"),
+                   "config": args.config, "images_per_gpu": n_img, "crops_per_image": crops, "crops_per_engine_call": per_call,
+                   "engine_calls_per_step": calls, "input_modal": "others", "adapter": "Depth_r16_a16 (folded)",
+                   "l2": "working set >> 126 MB L2; no explicit flush", "cuda_graph": per_call <= eng.graph_max_batch},
+        "clocks": clocks,
+        "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "full-resolution images/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": sum(t.numel() * t.element_size() for t in host_out),
+                "api": "backbone.slide_forward" + (" -> DAFormerHead -> teacher.pseudo_labels; labels + weights downloaded" if teacher else
+                                                   "; merged feature dict downloaded") + " (pinned host buffers, serial copies)"},
+        "gpu_launches": eng.launch_count(per_call) * calls * args.steps,
+        "whole_path_tflops_per_gpu": imgs / world * crops / (ms / 1e3) * GF_PER_IMG["total"] / 1e3,
+    }
+    if numa:
+        line["config"]["numa"] = numa
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -312,6 +508,9 @@ def main():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"], help="GEMM operand dtype (fp32 accumulate)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="base", choices=["base", "slide1024", "teacher2048", "train"],
+                    help="base = BASELINE configs[1] (the bench line); slide1024 / teacher2048 / train = BASELINE configs[2..4]")
+    ap.add_argument("--images", type=int, default=8, help="full-resolution images per GPU per step (slide1024 / teacher2048)")
     ap.add_argument("--variant", default="base", choices=["base", "s0"],
                     help="base = BASELINE configs[1] (the bench line); s0 = vae_decoder_loss configuration of the shipped experiment files")
     args = ap.parse_args()
@@ -325,6 +524,10 @@ def main():
         sys.exit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.config in ("slide1024", "teacher2048"):
+        run_slide(args, rank, local_rank, world)
+    elif args.config == "train":
+        run_train(args, rank, local_rank, world)
     else:
         run_product(args, rank, local_rank, world)
 

@@ -115,6 +115,8 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float lo
 
 /* Workspace bytes needed by madm_extract for batch B (all stages). */
 size_t madm_workspace_bytes(madm_ctx* ctx, int32_t B);
+/* the same when the head stage runs on a head_h x head_w grid (madm_extract_args.head_h / head_w) */
+size_t madm_workspace_bytes_head(madm_ctx* ctx, int32_t B, int32_t head_h, int32_t head_w);
 
 #define MADM_FLAG_IMG_NORMALISED 1
 typedef struct madm_extract_args {
@@ -147,6 +149,11 @@ typedef struct madm_extract_args {
   float* unet_sample;          /* [B,4,64,64]   'before_vae.decoder': unet_final_output.sample */
   float* decoded;              /* [B,3,512,512] 'after_vae.decoder': clip(decoder_output, -1, 1) */
   float* decoded_raw;          /* [B,3,512,512] decoder_output itself: the first entry of the feature list (ldm_diffusers.py:199) */
+  /* MADM_STAGE_HEAD alone: grid of the first feature map in out[0] (0, 0 = that of a 512 x 512 crop: 128 x 128, s0 variant 512 x 512).
+   * Sliding-window inference merges the crops' features into full-image maps before the head runs (feature_extractor.py:270-275), e.g.
+   * 256 x 512 for a 1024 x 2048 image; the other three maps are 1/2, 1/4, 1/8 of it (s0 variant: 1/8, 1/16, 1/32) and the logits
+   * come out on this grid. */
+  int32_t head_h, head_w;
 } madm_extract_args;
 
 /* The whole path a-1..a-9 of SURVEY §8: VAE encode -> q-sample -> UNet forward with taps -> GN-bottleneck projections. */

@@ -39,6 +39,7 @@ class MadmExtractArgs(C.Structure):
         ("packed", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("range_flag", c_void_p), ("logits", c_void_p),
         ("unet_sample", c_void_p), ("decoded", c_void_p), ("decoded_raw", c_void_p),
+        ("head_h", c_int32), ("head_w", c_int32),
     ]
 
 
@@ -80,6 +81,7 @@ SYMBOLS = {
     "madm_packed_bytes": (c_size_t, [c_void_p]),
     "madm_pack_weights": (c_int, [c_void_p, c_void_p, c_char_p, c_float, c_int32, c_void_p]),
     "madm_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
+    "madm_workspace_bytes_head": (c_size_t, [c_void_p, c_int32, c_int32, c_int32]),
     "madm_extract": (c_int, [c_void_p, C.POINTER(MadmExtractArgs), c_void_p]),
     "madm_launch_count": (c_int, [c_void_p, c_int32, c_int32]),
     "madm_set_profiling": (c_int, [c_void_p, c_int32]),

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <memory>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -110,8 +111,8 @@ struct madm_ctx {
   bool profiling = false;
   Plan* last_plan = nullptr;
   int last_stages = 0;
-  std::map<std::pair<int, int>, std::unique_ptr<Plan>> plans;  // (B, ema)
-  std::map<int, size_t> ws_bytes_cache;
+  std::map<std::tuple<int, int, int, int>, std::unique_ptr<Plan>> plans;  // (B, ema, head_h, head_w)
+  std::map<std::tuple<int, int, int>, size_t> ws_bytes_cache;             // (B, head_h, head_w)
 };
 
 namespace {
@@ -140,6 +141,7 @@ struct Builder {
   const uint8_t* packed = nullptr;
   int cur_stage = MADM_STAGE_VAE;
   int n_ops = 0;
+  int head_h = 0, head_w = 0;  // grid of the head's first feature map (0 = the 512 x 512 crop's: 128 x 128, s0 variant 512 x 512)
 
   // ---- workspace allocator (first-fit free list, 1 KB granularity); identical sequence in SIZE and PLAN modes
   struct Blk { size_t off, bytes; };
@@ -1230,14 +1232,18 @@ struct Model {
     const int ncls = int(cs->shape[0]), CH = int(cs->shape[1]), E = int(e0->shape[0]), Cin0 = int(e0->shape[1]);
     // base: s2..s5, four 512-channel maps, fused on the 128^2 grid.  s0 variant (in_keys[0]='s0', in_channels[0]=128,
     // mtmadise_cityscapes_rgb_to_depth_11.py:51-55): the first map is 128 x 512^2, so the head fuses on the 512^2 grid.
-    const int H0 = s0() ? 512 : 128;
+    // grid of the first map: the 512^2 crop's by default; sliding-window inference hands the head full-image maps (feature_extractor.py:
+    // 270-275 merges the crops before the head runs), so the grid is a call argument (madm_extract_args.head_h / head_w)
+    const int H = b.head_h > 0 ? b.head_h : (s0() ? 512 : 128), W = b.head_w > 0 ? b.head_w : (s0() ? 512 : 128);
     if (Cin0 != (s0() ? 128 : 512) || E % 64 != 0 || CH % 64 != 0 || ncls > 32) b.fail(MADM_EINVAL, "sem_seg_head: unsupported channel configuration");
-    const int Bn = b.B, side[4] = {H0, 64, 32, 16}, H = H0, W = H0, CAT = 4 * E;
+    const int ratio[4] = {1, s0() ? 8 : 2, s0() ? 16 : 4, s0() ? 32 : 8};
+    if (H % ratio[3] != 0 || W % ratio[3] != 0 || !(W % 128 == 0 || 128 % W == 0)) b.fail(MADM_EINVAL, "sem_seg_head: unsupported feature grid");
+    const int Bn = b.B, CAT = 4 * E;
     const long M = long(Bn) * H * W;
     const int f16v = f16();
     B16T cat = b.b16(size_t(M) * CAT);
     for (int i = 0; i < 4; ++i) {
-      const int Hi = side[i], HWi = Hi * Hi, Cin = i == 0 ? Cin0 : 512;
+      const int Hi = H / ratio[i], Wi = W / ratio[i], HWi = Hi * Wi, Cin = i == 0 ? Cin0 : 512;
       const long Mi = long(Bn) * HWi;
       B16T x = b.b16(size_t(Mi) * Cin);
       if (dry()) b.emit(nullptr);
@@ -1260,7 +1266,7 @@ struct Model {
         d.out_bf16 = e.p; d.ldo16 = E;
         b.gemm(d);
         bf16* ep = e.p; bf16* dst = cat.p + size_t(i) * E;
-        b.emit([=](cudaStream_t st) { return bilinear_resize_nhwc16(ep, Bn, Hi, Hi, E, dst, H, W, CAT, f16v, st); }, false, MADM_KIND_ELEMENTWISE,
+        b.emit([=](cudaStream_t st) { return bilinear_resize_nhwc16(ep, Bn, Hi, Wi, E, dst, H, W, CAT, f16v, st); }, false, MADM_KIND_ELEMENTWISE,
                0.0, double(M) * E * 2 + double(Mi) * E * 2);
         b.free(e);
       }
@@ -1361,8 +1367,9 @@ int set_err(madm_ctx* ctx, int code, const std::string& m) {
 }
 
 // Runs the traversal in a dry mode; returns workspace bytes (peak + stats region) and op count.
-int dry_run(madm_ctx* ctx, Mode mode, int B, size_t* ws_bytes, int* n_ops) {
+int dry_run(madm_ctx* ctx, Mode mode, int B, size_t* ws_bytes, int* n_ops, int head_h = 0, int head_w = 0) {
   Builder bld{ctx, mode, B, false};
+  bld.head_h = head_h; bld.head_w = head_w;
   Model m(bld);
   try {
     m.build_all();
@@ -1607,14 +1614,17 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float sc
   return MADM_OK;
 }
 
-size_t madm_workspace_bytes(madm_ctx* ctx, int32_t B) {
-  if (!ctx || B < 1) return 0;
+size_t madm_workspace_bytes(madm_ctx* ctx, int32_t B) { return madm_workspace_bytes_head(ctx, B, 0, 0); }
+
+size_t madm_workspace_bytes_head(madm_ctx* ctx, int32_t B, int32_t head_h, int32_t head_w) {
+  if (!ctx || B < 1 || head_h < 0 || head_w < 0) return 0;
   if (ensure_layout(ctx) != MADM_OK) return 0;
-  auto it = ctx->ws_bytes_cache.find(B);
+  const std::tuple<int, int, int> key{B, head_h, head_w};
+  auto it = ctx->ws_bytes_cache.find(key);
   if (it != ctx->ws_bytes_cache.end()) return it->second;
   size_t bytes = 0;
-  if (dry_run(ctx, SIZE, B, &bytes, nullptr) != MADM_OK) return 0;
-  ctx->ws_bytes_cache[B] = bytes;
+  if (dry_run(ctx, SIZE, B, &bytes, nullptr, head_h, head_w) != MADM_OK) return 0;
+  ctx->ws_bytes_cache[key] = bytes;
   return bytes;
 }
 
@@ -1649,8 +1659,9 @@ int madm_get_profile_stages(madm_ctx* ctx, int32_t stage_mask, madm_profile* out
 
 int madm_launch_count(madm_ctx* ctx, int32_t B, int32_t stages) {
   if (!ctx || B < 1) return -1;
-  auto it = ctx->plans.find({B, 0});
-  if (it == ctx->plans.end()) it = ctx->plans.find({B, 1});
+  auto it = ctx->plans.end();
+  for (auto p = ctx->plans.begin(); p != ctx->plans.end(); ++p)
+    if (std::get<0>(p->first) == B) { it = p; break; }
   if (it == ctx->plans.end()) return -1;
   int n = 0;
   for (size_t i = 0; i < it->second->ops.size(); ++i)
@@ -1671,12 +1682,13 @@ int madm_extract(madm_ctx* ctx, const madm_extract_args* a, madm_stream stream) 
     return set_err(ctx, MADM_EINVAL, "madm_extract: conditioning / timesteps / shared_noise are required for the UNet stage");
   int rc = ensure_layout(ctx);
   if (rc != MADM_OK) return rc;
-  const size_t need = madm_workspace_bytes(ctx, a->B);
+  if (a->head_h < 0 || a->head_w < 0 || ((a->head_h > 0) != (a->head_w > 0))) return set_err(ctx, MADM_EINVAL, "madm_extract: bad head_h / head_w");
+  const size_t need = madm_workspace_bytes_head(ctx, a->B, a->head_h, a->head_w);
   if (need == 0) return MADM_EINVAL;
   if (a->workspace_bytes < need) return set_err(ctx, MADM_ENOMEM, "madm_extract: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-  const std::pair<int, int> key{a->B, a->ema ? 1 : 0};
+  const std::tuple<int, int, int, int> key{a->B, a->ema ? 1 : 0, a->head_h, a->head_w};
   Plan* plan = nullptr;
   auto it = ctx->plans.find(key);
   if (it != ctx->plans.end() && it->second->packed == a->packed && it->second->ws == a->workspace) plan = it->second.get();
@@ -1684,12 +1696,14 @@ int madm_extract(madm_ctx* ctx, const madm_extract_args* a, madm_stream stream) 
     std::unique_ptr<Plan> np(new Plan());
     np->B = a->B; np->ema = a->ema != 0; np->packed = a->packed; np->ws = a->workspace; np->ws_bytes = a->workspace_bytes;
     Builder bld{ctx, PLAN, a->B, a->ema != 0};
+    bld.head_h = a->head_h; bld.head_w = a->head_w;
     bld.plan = np.get();
     bld.packed = static_cast<const uint8_t*>(a->packed);
     // statistics slots live at the start of the workspace; activations after them
     size_t total = 0; int nops = 0;
     {
       Builder probe{ctx, SIZE, a->B, a->ema != 0};
+      probe.head_h = a->head_h; probe.head_w = a->head_w;
       Model pm(probe);
       try { pm.build_all(); } catch (const BuildError& e) { return set_err(ctx, e.code, e.msg); }
       total = probe.stats_used; nops = probe.n_ops;

@@ -51,7 +51,7 @@ class Engine:
         # CUDA graphs: at small batch the ~550 launches of one forward are CPU-launch-bound, and even at B = 8 the graph saves the
         # inter-kernel launch gaps (24.9 -> 24.1 ms per step); one graph per call signature
         # replays them.  graph_max_batch: largest B that is graphed (0 disables).
-        self.graph_max_batch = 8
+        self.graph_max_batch = 32  # covers the sliding-window crop batches (9, 18, 21 crops per call)
         self._graphs: Dict[Tuple, Dict[str, object]] = {}
 
     def __del__(self):
@@ -108,8 +108,8 @@ class Engine:
                        "madm_pack_weights(lora_only)")
             self._packed_adapter = adapter
 
-    def workspace(self, B: int) -> torch.Tensor:
-        need = self.lib.madm_workspace_bytes(self.ctx, B)
+    def workspace(self, B: int, head_hw: Tuple[int, int] = (0, 0)) -> torch.Tensor:
+        need = self.lib.madm_workspace_bytes_head(self.ctx, B, head_hw[0], head_hw[1])
         if need == 0:
             _lib.check(-1, self.ctx, "madm_workspace_bytes")
         if self._ws is None or self._ws.numel() < need:
@@ -182,8 +182,9 @@ class Engine:
 
     # ------------------------------------------------------------------ DAFormer head
     def head(self, feats: Sequence[torch.Tensor], num_classes: int) -> torch.Tensor:
-        """``MADM_STAGE_HEAD`` on the feature dict: s2..s5 fp32 NCHW [B,512,side,side] -> logits [B,num_classes,128,128]
-        (s0 variant: s0 [B,128,512,512], s3..s5 -> logits [B,num_classes,512,512])."""
+        """``MADM_STAGE_HEAD`` on the feature dict: s2..s5 fp32 NCHW [B,512,h/r,w/r] (r = 1, 2, 4, 8) -> logits [B,num_classes,h,w];
+        h = w = 128 for a 512^2 crop, larger for the merged maps of sliding-window inference (s0 variant: s0 [B,128,h,w] with
+        h = w = 512 for a crop, s3..s5 at 1/8, 1/16, 1/32 -> logits on the s0 grid)."""
         if self._packed is None:
             raise _lib.MadmError("Engine.head called before ensure_packed()")
         dev = self.device
@@ -191,17 +192,22 @@ class Engine:
         a = MadmExtractArgs()
         a.B, a.stages, a.ema = B, STAGE_HEAD, 0
         keep = []
-        for i, (ch, side) in enumerate(OUT_SHAPES[self.variant]):
+        h0, w0 = int(feats[0].shape[2]), int(feats[0].shape[3])
+        ratios = (1, 8, 16, 32) if self.variant == "s0" else (1, 2, 4, 8)
+        for i, (ch, _) in enumerate(OUT_SHAPES[self.variant]):
             t = feats[i]
-            if t.device != dev or tuple(t.shape) != (B, ch, side, side):
-                raise _lib.MadmError(f"feature map {i} must be [{B},{ch},{side},{side}] on {dev}, got {tuple(t.shape)} on {t.device}")
+            want = (B, ch, h0 // ratios[i], w0 // ratios[i])
+            if t.device != dev or tuple(t.shape) != want or h0 % ratios[3] or w0 % ratios[3]:
+                raise _lib.MadmError(f"feature map {i} must be {list(want)} on {dev}, got {tuple(t.shape)} on {t.device}")
             t = t.to(torch.float32).contiguous()
             keep.append(t)
             a.out[i] = t.data_ptr()
         side0 = OUT_SHAPES[self.variant][0][1]
-        logits = torch.empty(B, num_classes, side0, side0, dtype=torch.float32, device=dev)
+        head_hw = (0, 0) if (h0, w0) == (side0, side0) else (h0, w0)
+        a.head_h, a.head_w = head_hw
+        logits = torch.empty(B, num_classes, h0, w0, dtype=torch.float32, device=dev)
         a.logits = logits.data_ptr()
-        ws = self.workspace(B)
+        ws = self.workspace(B, head_hw)
         a.packed = self._packed.data_ptr()
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)

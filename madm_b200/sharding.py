@@ -25,3 +25,37 @@ def gather_max(value: float) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def bind_to_gpu_numa(local_rank: int) -> str:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs ``local_cpulist`` of the GPU's PCI function), before any
+    pinned host buffer is allocated: first-touch then places those buffers on that node, so the feature-dict downloads of the 8
+    ranks of one box do not all land in one socket's memory.  Returns a short description; never raises (best effort)."""
+    import os
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return f"gpu {bdf}: local cpus {spec} not in this process's cpuset; unchanged"
+        os.sched_setaffinity(0, use)
+        node = "?"
+        try:
+            with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+                node = f.read().strip()
+        except OSError:
+            pass
+        return f"gpu {bdf}: numa node {node}, {len(use)} cpus"
+    except Exception as e:  # noqa: BLE001 - sysfs layout / permissions differ between boxes
+        return f"not bound ({type(e).__name__}: {e})"

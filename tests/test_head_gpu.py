@@ -88,6 +88,24 @@ def test_head_parity_on_random_features(heads, cuda_device, B):
         assert torch.equal(out, ph({"output_features": feats}))  # no atomics anywhere: bit-identical reruns
 
 
+@pytest.mark.parametrize("hw", [(256, 512), (256, 256), (64, 128)])
+def test_head_on_full_image_grids(heads, cuda_device, hw):
+    """Sliding-window inference merges the crops' features into full-image maps before the head runs (feature_extractor.py:270-275):
+    the head stage takes the grid as a call argument (madm_extract_args.head_h / head_w), e.g. 256 x 512 for a 1024 x 2048 image
+    (BASELINE config 4) and 256 x 256 for 1024 x 1024 (config 3)."""
+    oh, ph = heads
+    g = torch.Generator(device="cuda").manual_seed(hw[0] + hw[1])
+    feats = {k: F.relu(torch.randn(1, 512, hw[0] // r, hw[1] // r, device=cuda_device, generator=g)) for k, r in zip(("s2", "s3", "s4", "s5"), (1, 2, 4, 8))}
+    with torch.no_grad():
+        ref = oh({"output_features": feats})
+        out = ph({"output_features": feats})
+    assert out.shape == ref.shape == (1, 19, hw[0], hw[1])
+    c, r = cosine(out, ref), max_rel(out, ref)
+    agree = (out.argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"head logits on {hw}: cosine {c:.6f} max-rel {r:.2e} argmax agreement {100 * agree:.3f} %")
+    assert c >= 0.999 and r <= 2e-2 and agree >= 0.995
+
+
 def test_head_bf16_operands(cuda_device):
     """The head follows the context's operand dtype: bf16 operands within the looser bf16 gate (cosine >= 0.999, 3e-2)."""
     from madm_b200.head import DAFormerHead

@@ -153,13 +153,14 @@ def test_fused_adamw_is_a_torch_optimizer(cuda_device):
         o1.step(clip_grad=1.0)
         sched.step()
     assert abs(o1.param_groups[0]["lr"] - 5e-3 / 4) < 1e-12
-    sd = o1.state_dict()
+    import copy
+    sd = copy.deepcopy(o1.state_dict())  # a checkpoint round trip (state_dict() itself hands out references to the live moments)
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
     # resume into a fresh optimizer over copies of the parameters, and into torch.optim.AdamW: one more identical step each
     p2 = [torch.nn.Parameter(p.detach().clone()) for p in p1]
     p3 = [torch.nn.Parameter(p.detach().clone()) for p in p1]
     o2 = FusedAdamW(p2, **kw)
-    o2.load_state_dict(sd)
+    o2.load_state_dict(copy.deepcopy(sd))
     o3 = torch.optim.AdamW(p3, **kw)
     sd3 = {"state": {k: dict(v, step=torch.tensor(float(v["step"]))) for k, v in sd["state"].items()}, "param_groups": sd["param_groups"]}
     o3.load_state_dict(sd3)
@@ -173,7 +174,7 @@ def test_fused_adamw_is_a_torch_optimizer(cuda_device):
         assert torch.allclose(a, c, rtol=2e-6, atol=1e-7)
     # and back: a state written by torch's AdamW (tensor step) resumes in FusedAdamW
     o4 = FusedAdamW([torch.nn.Parameter(p.detach().clone()) for p in p3], **kw)
-    o4.load_state_dict(o3.state_dict())
+    o4.load_state_dict(copy.deepcopy(o3.state_dict()))
     assert all(int(s["step"]) == 4 for s in o4.state.values())
     # non-finite gradient: the update is skipped on the device (GradScaler semantics), nothing becomes NaN
     before = [p.detach().clone() for p in p1]
