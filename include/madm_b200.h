@@ -154,6 +154,8 @@ typedef struct madm_extract_args {
    * 256 x 512 for a 1024 x 2048 image; the other three maps are 1/2, 1/4, 1/8 of it (s0 variant: 1/8, 1/16, 1/32) and the logits
    * come out on this grid. */
   int32_t head_h, head_w;
+  const void* packed_dgrad;    /* MADM_FLAG_TRAIN: the arena filled by madm_pack_dgrad_weights (holds the natural-order feed-forward weights
+                                  of the training forward next to the input-gradient operands) */
 } madm_extract_args;
 
 /* The whole path a-1..a-9 of SURVEY §8: VAE encode -> q-sample -> UNet forward with taps -> GN-bottleneck projections. */
@@ -304,6 +306,76 @@ int madm_op_image_im2col(const float* img, int32_t B, int32_t H, int32_t W, void
 int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, const float* s, const float* gs, const float* bs,
                              int32_t has_shortcut_norm, float eps, int32_t B, int32_t HW, int32_t C, float* stats_scratch,
                              float* out_nchw, madm_stream stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training path (SURVEY §8 row f-3 / BASELINE config 5): the backward pass of madm_extract for the LoRA training step's trainable set
+ *   - the active adapter's lora_A / lora_B factors on to_q / to_k / to_v / to_out.0 of all 32 attentions (mtmadise.py:115-147),
+ *   - feature_projections.* (conv weights and GroupNorm affines of the four GN bottlenecks, feature_extractor.py:347-359),
+ *   - the learned prompt / time conditioning, through d(cond_inputs) and d(cond_emb) (ldm_base.py:632-717: tiny tanh(alpha) * embed
+ *     arithmetic that stays with the caller),
+ * i.e. what `loss.backward()` produces in the reference's AMPTrainer.run_step (engine/train_loop.py:277-302) once the base UNet weights
+ * are frozen, as BASELINE.json narrows config 5.  The VAE encoder runs without gradient (ldm_diffusers.py:282); base variant only.
+ *
+ * Protocol: madm_pack_dgrad_weights (after every parameter update / adapter switch, next to madm_pack_weights) -> madm_extract with
+ * MADM_FLAG_TRAIN (keeps every activation the backward needs in the training workspace; B <= 8) -> madm_backward with the gradients of
+ * the four feature maps.  Gradients are WRITTEN (not accumulated) into the buffers registered with madm_set_grad_tensors under the
+ * parameters' names; parameters without a registered buffer get no gradient.  16-bit gradient tensors have the context's operand dtype;
+ * with fp16 operands pass a loss_scale (the incoming gradients are multiplied by it, every output is divided by it again), with bf16 1.0.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define MADM_FLAG_TRAIN 2
+int madm_set_grad_tensors(madm_ctx* ctx, const madm_tensor* named, int32_t n); /* fp32 device buffers shaped like the parameters */
+size_t madm_dgrad_packed_bytes(madm_ctx* ctx);
+int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed_dgrad, const char* adapter, float lora_alpha_over_r, madm_stream stream);
+size_t madm_train_workspace_bytes(madm_ctx* ctx, int32_t B);
+typedef struct madm_backward_args {
+  int32_t B;
+  int32_t reserved;
+  const float* dout[4];        /* gradients of out[0..3] (s2..s5), fp32 NCHW */
+  const float* out[4];         /* the forward's outputs themselves (ReLU mask of the projections' last pass) */
+  const float* cond_emb;       /* [B,1280]: the forward's cond_emb (time path SiLU backward) */
+  float* d_cond_inputs;        /* [B,77,768] or NULL */
+  float* d_cond_emb;           /* [B,1280] or NULL */
+  const char* adapter;         /* active LoRA adapter of the forward ("" / NULL: none, no LoRA gradients) */
+  float lora_alpha_over_r;
+  float loss_scale;            /* > 0; 1.0 for bf16 operands */
+  const void* packed;          /* forward arena (madm_pack_weights) */
+  const void* packed_dgrad;    /* madm_pack_dgrad_weights arena */
+  void* workspace;             /* the training workspace the MADM_FLAG_TRAIN forward ran in */
+  size_t workspace_bytes;
+} madm_backward_args;
+int madm_backward(madm_ctx* ctx, const madm_backward_args* args, madm_stream stream);
+/* number of kernels one madm_backward call launches (after a MADM_FLAG_TRAIN forward at this B) */
+int madm_backward_launch_count(madm_ctx* ctx, int32_t B);
+
+/* ---- backward pass of the LoRA training step, operator level.  "16" tensors have the operand dtype `dtype`. ---- */
+/* GroupNorm(32)(+act) backward.  x = channel concat of x0 / x1 (fp32, or 16-bit if in16); stats = group sums [B,32,2] (sum, sum of squares)
+ * of x; dy16 [B,HW,C] = gradient of act(GN(x)); scratch = madm_op_groupnorm_bwd_scratch_floats(B,HW,C) floats.  Any subset of outputs:
+ * out16 [B,HW,C]; fp32 dx0 [B,HW,C0] / dx1 [B,HW,C1] (acc != 0: accumulated); `extra` fp32 [B,HW,C] is added to dx; dgamma / dbeta [C]. */
+int madm_op_groupnorm_bwd_scratch_floats(int32_t B, int32_t HW, int32_t C);
+int madm_op_groupnorm_bwd(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW, int32_t in16, const float* stats,
+                          const float* gamma, const float* beta, float eps, int32_t act, const void* dy16, const float* extra, float* scratch,
+                          void* out16, float* dx0, int32_t acc0, float* dx1, int32_t acc1, float* dgamma, float* dbeta, int32_t dtype,
+                          madm_stream stream);
+int madm_op_layernorm_bwd(const float* x, int32_t M, int32_t C, const float* gamma, float eps, const void* dy16, float* dx, int32_t accumulate,
+                          int32_t dtype, madm_stream stream);
+/* GEGLU, natural column order: raw16 [M,2H] = (hidden | gate) -> out16 [M,H]; backward: draw16 [M,2H] */
+int madm_op_geglu_fwd(const void* raw16, int64_t M, int32_t H, void* out16, int32_t dtype, madm_stream stream);
+int madm_op_geglu_bwd(const void* raw16, const void* dout16, int64_t M, int32_t H, void* draw16, int32_t dtype, madm_stream stream);
+/* softmax(Q K^T scale) V backward per (image, head): same addressing as madm_op_attention; scratch = 2*B*heads*Nq floats */
+int madm_op_attention_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, const void* o, int32_t ldo,
+                          const void* dout, int32_t lddo, void* dq, int32_t lddq, void* dk, int32_t lddk, void* dv, int32_t lddv, int32_t B,
+                          int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bs, int64_t kv_bs, int64_t o_bs, int64_t do_bs, int64_t dq_bs,
+                          int64_t dkv_bs, float scale, float* scratch, int32_t dtype, madm_stream stream);
+/* weight gradient dW[n,k] = alpha * sum_m dY[m,n] X[m,k]; taps = 9: implicit im2col of X [Bimg,H,W,K] -> PyTorch conv layout [N,K,3,3];
+ * transpose_out != 0 (taps = 1): out[k,n].  scratch = madm_op_wgrad_scratch_floats(M,N,K,taps) floats */
+int64_t madm_op_wgrad_scratch_floats(int32_t M, int32_t N, int32_t K, int32_t taps);
+int madm_op_wgrad(const void* dy16, int32_t lda, const void* x16, int32_t ldb, int32_t M, int32_t N, int32_t K, int32_t taps, int32_t Bimg, int32_t H,
+                  int32_t W, float alpha, float* out, int32_t transpose_out, float* scratch, int32_t dtype, madm_stream stream);
+int madm_op_colsum_per_image(const void* x16, int32_t B, int32_t HW, int32_t C, float* out, int32_t ldo, int32_t dtype, madm_stream stream);
+int madm_op_zero_stuff2x(const void* x16, int32_t B, int32_t h, int32_t w, int32_t C, void* out16, madm_stream stream);
+int madm_op_sum2x2(const float* x, int32_t B, int32_t h, int32_t w, int32_t C, float* out, int32_t accumulate, madm_stream stream);
+int madm_op_relu_bwd_nchw(const float* dout, const float* out, int32_t B, int32_t C, int32_t HW, float scale, void* dz16, int32_t dtype,
+                          madm_stream stream);
 
 #ifdef __cplusplus
 }

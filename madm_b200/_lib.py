@@ -123,6 +123,22 @@ SYMBOLS = {
     "madm_op_slide_merge": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "madm_op_upsample2x": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_image_im2col": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
+    "madm_op_groupnorm_bwd_scratch_floats": (c_int, [c_int32, c_int32, c_int32]),
+    "madm_op_groupnorm_bwd": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_int32,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
+    "madm_op_layernorm_bwd": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_float, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    "madm_op_geglu_fwd": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_geglu_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_attention_bwd": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32,
+                                      c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64,
+                                      c_int64, c_int64, c_int64, c_float, c_void_p, c_int32, c_void_p]),
+    "madm_op_wgrad_scratch_floats": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
+    "madm_op_wgrad": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p,
+                              c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_colsum_per_image": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    "madm_op_zero_stuff2x": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "madm_op_sum2x2": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_relu_bwd_nchw": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_int32, c_void_p]),
     "madm_op_gn_add_relu_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_float,
                                          c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }

@@ -230,4 +230,60 @@ int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, c
   RUN(gn_add_relu_nchw(a, st_a, ga, ba, s, has_shortcut_norm ? st_s : nullptr, gs, bs, eps, B, HW, C, out, st));
 }
 
+// ---- backward pass
+int madm_op_groupnorm_bwd_scratch_floats(int32_t B, int32_t HW, int32_t C) {
+  return int(size_t(B) * groupnorm_bwd_slabs(HW) * C * 2 + size_t(B) * 64 + size_t(B) * C * 2);
+}
+int madm_op_groupnorm_bwd(const void* x0, int32_t C0, const void* x1, int32_t C1, int32_t B, int32_t HW, int32_t in16, const float* stats,
+                          const float* gamma, const float* beta, float eps, int32_t act, const void* dy16, const float* extra, float* scratch,
+                          void* out16, float* dx0, int32_t acc0, float* dx1, int32_t acc1, float* dgamma, float* dbeta, int32_t dtype,
+                          madm_stream stream) {
+  const int C = C0 + C1;
+  float* partial = scratch;
+  float* coef = partial + size_t(B) * groupnorm_bwd_slabs(HW) * C * 2;
+  float* chan = coef + size_t(B) * 64;
+  RUN(groupnorm_bwd(x0, C0, x1, C1, B, HW, in16, stats, gamma, beta, eps, act, dy16, dtype == MADM_DTYPE_FP16, partial, coef, chan, extra, out16, dx0,
+                    acc0, dx1, acc1, dgamma, dbeta, 1.0f, static_cast<cudaStream_t>(stream)));
+}
+int madm_op_layernorm_bwd(const float* x, int32_t M, int32_t C, const float* gamma, float eps, const void* dy16, float* dx, int32_t accumulate,
+                          int32_t dtype, madm_stream stream) {
+  RUN(layernorm_bwd(x, M, C, gamma, eps, dy16, dtype == MADM_DTYPE_FP16, dx, accumulate, static_cast<cudaStream_t>(stream)));
+}
+int madm_op_geglu_fwd(const void* raw16, int64_t M, int32_t H, void* out16, int32_t dtype, madm_stream stream) {
+  RUN(geglu_fwd(raw16, long(M), H, out16, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+}
+int madm_op_geglu_bwd(const void* raw16, const void* dout16, int64_t M, int32_t H, void* draw16, int32_t dtype, madm_stream stream) {
+  RUN(geglu_bwd(raw16, dout16, long(M), H, draw16, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+}
+int madm_op_attention_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, const void* o, int32_t ldo,
+                          const void* dout, int32_t lddo, void* dq, int32_t lddq, void* dk, int32_t lddk, void* dv, int32_t lddv, int32_t B,
+                          int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bs, int64_t kv_bs, int64_t o_bs, int64_t do_bs, int64_t dq_bs,
+                          int64_t dkv_bs, float scale, float* scratch, int32_t dtype, madm_stream stream) {
+  RUN(attention_bwd(q, ldq, k, ldk, v, ldv, o, ldo, dout, lddo, dq, lddq, dk, lddk, dv, lddv, B, heads, d, Nq, Nk, long(q_bs), long(kv_bs), long(kv_bs),
+                    long(o_bs), long(do_bs), long(dq_bs), long(dkv_bs), long(dkv_bs), scale, scratch, dtype == MADM_DTYPE_FP16,
+                    static_cast<cudaStream_t>(stream)));
+}
+int64_t madm_op_wgrad_scratch_floats(int32_t M, int32_t N, int32_t K, int32_t taps) { return int64_t(wgrad_scratch_floats(M, N, K, taps)); }
+int madm_op_wgrad(const void* dy16, int32_t lda, const void* x16, int32_t ldb, int32_t M, int32_t N, int32_t K, int32_t taps, int32_t Bimg, int32_t H,
+                  int32_t W, float alpha, float* out, int32_t transpose_out, float* scratch, int32_t dtype, madm_stream stream) {
+  long so_n = K, so_k = 1, so_tap = 0;
+  if (taps == 9) { so_n = long(K) * 9; so_k = 9; so_tap = 1; }
+  else if (transpose_out) { so_n = 1; so_k = N; }
+  RUN(wgrad(dy16, lda, x16, ldb, M, N, K, taps, Bimg, H, W, alpha, out, so_n, so_k, so_tap, scratch, dtype == MADM_DTYPE_FP16,
+            static_cast<cudaStream_t>(stream)));
+}
+int madm_op_colsum_per_image(const void* x16, int32_t B, int32_t HW, int32_t C, float* out, int32_t ldo, int32_t dtype, madm_stream stream) {
+  RUN(colsum_per_image(x16, B, HW, C, dtype == MADM_DTYPE_FP16, out, ldo, static_cast<cudaStream_t>(stream)));
+}
+int madm_op_zero_stuff2x(const void* x16, int32_t B, int32_t h, int32_t w, int32_t C, void* out16, madm_stream stream) {
+  RUN(zero_stuff2x(x16, B, h, w, C, out16, static_cast<cudaStream_t>(stream)));
+}
+int madm_op_sum2x2(const float* x, int32_t B, int32_t h, int32_t w, int32_t C, float* out, int32_t accumulate, madm_stream stream) {
+  RUN(sum2x2(x, B, h, w, C, out, accumulate, static_cast<cudaStream_t>(stream)));
+}
+int madm_op_relu_bwd_nchw(const float* dout, const float* out, int32_t B, int32_t C, int32_t HW, float scale, void* dz16, int32_t dtype,
+                          madm_stream stream) {
+  RUN(relu_bwd_nchw_to_nhwc16(dout, out, B, C, HW, scale, dz16, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+}
+
 }  // extern "C"

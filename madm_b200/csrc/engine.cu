@@ -59,14 +59,39 @@ struct PackEntry {
 
 struct IoBind {  // per-call pointers read by the plan's first/last ops
   madm_extract_args a;
+  madm_backward_args b;  // training plans: the arguments of the madm_backward call being replayed
+};
+
+// ---- input-gradient ("dgrad") arena of the training path: transposed / tap-mirrored 16-bit copies of the frozen weights (LoRA folded),
+// the skinny LoRA factor operands, and the natural-order feed-forward weight of the training forward
+enum DPackKind { DG_CONV,        // conv [Cout,Cin,k,k] -> [Cin, taps*CoPad], mirrored taps
+                 DG_LINEAR,      // linear [N,K] (+ LoRA) -> its transpose, written at a column offset of a [K, ldo] region
+                 DG_LINEAR_FWD,  // linear [N,K] -> [N,K] (forward operand in natural row order: ff.net.0.proj of the training forward)
+                 DG_LORA_A,      // lora_A [r,in] -> [r,in]       (operand of U = X A^T)
+                 DG_LORA_BT,     // lora_B [out,r] -> [r,out]     (operand of V = dY B)
+                 DG_REGION };
+struct DPackEntry {
+  DPackKind kind;
+  std::string src;   // parameter name (conv: "<m>.weight"; linear / LoRA: module path)
+  size_t off = 0;
+  int N = 0, C = 0, taps = 1, CoPad = 0, ldo = 0;
+  bool lora = false;
 };
 
 struct F32T { float* p = nullptr; size_t off = 0; size_t bytes = 0; };
 struct B16T { bf16* p = nullptr; size_t off = 0; size_t bytes = 0; };
 
+// gradient of an fp32-stream activation in a training plan: allocated by its first contributor; later contributors accumulate
+struct GradBuf {
+  F32T f;
+  bool written = false;  // at least one contribution has been emitted
+  bool stop = false;     // nothing trainable lies upstream: contributions are skipped
+};
+
 // fp32 residual-stream activation, NHWC, optionally with a bf16 copy for consumers that take it as a GEMM operand
 struct Act {
   F32T f; B16T h;
+  std::shared_ptr<struct GradBuf> gr;  // training plans: gradient of this activation (fp32 [M,C]), shared by all copies of the handle
   float* cs = nullptr;  // per-column statistics written by the producing GEMM's epilogue ([M/sr][C][2]), if any
   int sr = 0;           // rows per statistics block (64 or 128)
   bool has_cs = false;  // valid in every builder mode (cs itself is null outside PLAN mode)
@@ -83,6 +108,11 @@ struct Plan {
   void* ws = nullptr;
   size_t ws_bytes = 0;
   std::vector<Op> ops;
+  std::vector<Op> bops;       // training plans: the backward pass (replayed by madm_backward)
+  bool train = false;
+  const void* dpacked = nullptr;
+  float loss_scale = 1.0f;
+  std::string adapter;
   std::vector<int> stage_of;  // stage bit per op
   std::vector<char> optional; // debug/taps ops that launch only when the caller asks for the extra output
   std::vector<int> kind;      // MADM_KIND_* per op
@@ -113,6 +143,14 @@ struct madm_ctx {
   int last_stages = 0;
   std::map<std::tuple<int, int, int, int>, std::unique_ptr<Plan>> plans;  // (B, ema, head_h, head_w)
   std::map<std::tuple<int, int, int>, size_t> ws_bytes_cache;             // (B, head_h, head_w)
+  // training path
+  std::unordered_map<std::string, float*> grads;     // gradient output buffers by parameter name (madm_set_grad_tensors)
+  std::vector<DPackEntry> dpack;
+  std::map<std::string, size_t> dpack_index;
+  size_t dpacked_bytes = 0;
+  bool dlayout_done = false;
+  std::map<int, std::unique_ptr<Plan>> train_plans;  // B -> forward (activations kept) + backward
+  std::map<int, size_t> train_ws_cache;
 };
 
 namespace {

@@ -143,6 +143,44 @@ const char* color_jitter(const float* in, int B, long HW, const int* order, cons
 const char* gaussian_blur(const float* src, int planes, int H, int W, int ky, int kx, float sigma_y, float sigma_x, float* tmp, float* dst,
                           cudaStream_t st);
 
+// ---- backward.cu (backward of the HBM-bound layers; 16-bit gradients have the context's operand dtype)
+// GroupNorm(32)(+act) backward.  x = channel concat of x0 / x1 (fp32, or 16-bit if in16); stats = the forward's finalised group sums
+// [B,32,2] (sum, sum of squares); dy16 [B,HW,C] = gradient of act(GN(x)).  Scratch: partial [B][groupnorm_bwd_slabs(HW)][C][2], coef
+// [B][32][2], chan [B][C][2] (only for affine gradients).  Outputs (any subset): out16 [B,HW,C]; fp32 dx0 [B,HW,C0] / dx1 [B,HW,C1], each
+// stored or accumulated; `extra` (fp32 [B,HW,C]) is added to dx; dgamma / dbeta [C] = affine_scale * sums over (B, HW).
+int groupnorm_bwd_slabs(int HW);
+const char* groupnorm_bwd(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, const float* stats, const float* gamma,
+                          const float* beta, float eps, int act, const void* dy16, int fp16, float* partial, float* coef, float* chan,
+                          const float* extra, void* out16, float* dx0, int acc0, float* dx1, int acc1, float* dgamma, float* dbeta,
+                          float affine_scale, cudaStream_t st);
+// LayerNorm backward over rows of x fp32 [M,C] (statistics recomputed): dx stored or accumulated (fp32)
+const char* layernorm_bwd(const float* x, int M, int C, const float* gamma, float eps, const void* dy16, int fp16, float* dx, int accumulate,
+                          cudaStream_t st);
+// GEGLU in natural column order: raw16 [M, 2H] = (hidden | gate) -> out16 [M,H] = hidden * gelu(gate); backward -> draw16 [M, 2H]
+const char* geglu_fwd(const void* raw16, long M, int H, void* out16, int fp16, cudaStream_t st);
+const char* geglu_bwd(const void* raw16, const void* dout16, long M, int H, void* draw16, int fp16, cudaStream_t st);
+// out[b * ldo + c] = sum over the pixels of image b of x16[b, :, c]   (gradient of a per-image row bias: time_emb_proj)
+const char* colsum_per_image(const void* x16, int B, int HW, int C, int fp16, float* out, int ldo, cudaStream_t st);
+// 16-bit [B,h,w,C] -> [B,2h,2w,C], values at even positions, zeros elsewhere (operand of a stride-2 conv's input gradient)
+const char* zero_stuff2x(const void* x16, int B, int h, int w, int C, void* out16, cudaStream_t st);
+// fp32 [B,2h,2w,C] -> [B,h,w,C]: 2x2 block sums (backward of nearest-2x upsampling), stored or accumulated
+const char* sum2x2(const float* x, int B, int h, int w, int C, float* out, int accumulate, cudaStream_t st);
+// dz16 [B,HW,C] = scale * dout[b,c,p] * (out[b,c,p] > 0): ReLU backward of the projections' last pass + NCHW -> NHWC
+const char* relu_bwd_nchw_to_nhwc16(const float* dout, const float* out, int B, int C, int HW, float scale, void* dz16, int fp16, cudaStream_t st);
+const char* temb_silu_bwd(const float* d_act, const float* emb, const float* cond_emb, long n, float scale, float* d_cond_emb, cudaStream_t st);
+
+// ---- attention_bwd.cu: gradients of softmax(Q K^T scale) V per (image, head); scratch = attention_bwd_scratch_floats(B, heads, Nq) floats
+size_t attention_bwd_scratch_floats(int B, int heads, int Nq);
+const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, int ldo, const void* dout, int lddo,
+                          void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B, int heads, int d, int Nq, int Nk, long q_bs, long k_bs,
+                          long v_bs, long o_bs, long do_bs, long dq_bs, long dk_bs, long dv_bs, float scale, float* scratch, int fp16, cudaStream_t st);
+
+// ---- wgrad.cu: dW[n,k] = alpha * sum_m dY[m,n] X[m,k] (taps = 9: implicit im2col of X [Bimg,H,W,K]) -> out[n*so_n + k*so_k + tap*so_tap]
+int wgrad_splits(int M, int N, int K, int taps);
+size_t wgrad_scratch_floats(int M, int N, int K, int taps);
+const char* wgrad(const void* dy16, int lda, const void* x16, int ldb, int M, int N, int K, int taps, int Bimg, int H, int W, float alpha,
+                  float* out, long so_n, long so_k, long so_tap, float* scratch, int fp16, cudaStream_t st);
+
 // ---- pack.cu (weight packing; fp32 PyTorch layouts -> bf16 K-major GEMM operands)
 // conv weight [N, C, kh, kw] fp32 -> [N, kh*kw*Cpad] bf16 with K index = tap*Cpad + c (zero fill for c >= C)
 const char* pack_conv_weight(const float* w, int N, int C, int taps, int Cpad, int Kpad, int ldo, void* out_bf16, int fp16,

@@ -268,3 +268,113 @@ def gn_add_relu_nchw(a, ga, ba, s, gs, bs, eps, B, HW, Cc):
     _lib.check(lib.madm_op_gn_add_relu_nchw(_ptr(a), _ptr(ga), _ptr(ba), _ptr(s), _ptr(gs), _ptr(bs), 1 if gs is not None else 0,
                                             eps, B, HW, Cc, _ptr(stats), _ptr(out), _stream()), None, "madm_op_gn_add_relu_nchw")
     return out
+
+
+# ---------------------------------------------------------------------------------------------- backward pass
+def groupnorm_bwd(x0, x1, stats, gamma, beta, eps, act, dy, *, extra=None, want16=True, want32=False, acc=(False, False),
+                  dx0=None, dx1=None, want_affine=False):
+    """GroupNorm(32)(+act) backward on NHWC inputs ([B,HW,C0] (+[B,HW,C1]) fp32 or 16-bit); stats [B,32,2] group sums of x.
+    Returns dict(out16, dx0, dx1, dgamma, dbeta)."""
+    lib = _lib.load()
+    B, HW, C0 = x0.shape
+    C1 = x1.shape[2] if x1 is not None else 0
+    Cc = C0 + C1
+    dev = x0.device
+    in16 = 1 if x0.dtype in (torch.float16, torch.bfloat16) else 0
+    scratch = torch.empty(lib.madm_op_groupnorm_bwd_scratch_floats(B, HW, Cc), dtype=torch.float32, device=dev)
+    out16 = torch.empty(B, HW, Cc, dtype=dy.dtype, device=dev) if want16 else None
+    if want32:
+        dx0 = dx0 if dx0 is not None else torch.empty(B, HW, C0, dtype=torch.float32, device=dev)
+        if C1:
+            dx1 = dx1 if dx1 is not None else torch.empty(B, HW, C1, dtype=torch.float32, device=dev)
+    dg = torch.empty(Cc, dtype=torch.float32, device=dev) if want_affine else None
+    db = torch.empty(Cc, dtype=torch.float32, device=dev) if want_affine else None
+    _lib.check(lib.madm_op_groupnorm_bwd(_ptr(x0), C0, _ptr(x1), C1, B, HW, in16, _ptr(stats), _ptr(gamma), _ptr(beta), float(eps), int(act), _ptr(dy),
+                                         _ptr(extra), _ptr(scratch), _ptr(out16), _ptr(dx0), int(acc[0]), _ptr(dx1), int(acc[1]), _ptr(dg), _ptr(db),
+                                         _dt(dy.dtype), _stream()), None, "madm_op_groupnorm_bwd")
+    return dict(out16=out16, dx0=dx0, dx1=dx1, dgamma=dg, dbeta=db)
+
+
+def layernorm_bwd(x, gamma, eps, dy, dx=None, accumulate=False):
+    lib = _lib.load()
+    M, Cc = x.shape
+    if dx is None:
+        dx = torch.empty(M, Cc, dtype=torch.float32, device=x.device)
+    _lib.check(lib.madm_op_layernorm_bwd(_ptr(x), M, Cc, _ptr(gamma), float(eps), _ptr(dy), _ptr(dx), int(accumulate), _dt(dy.dtype), _stream()), None,
+               "madm_op_layernorm_bwd")
+    return dx
+
+
+def geglu_fwd(raw):
+    lib = _lib.load()
+    M, H2 = raw.shape
+    out = torch.empty(M, H2 // 2, dtype=raw.dtype, device=raw.device)
+    _lib.check(lib.madm_op_geglu_fwd(_ptr(raw), M, H2 // 2, _ptr(out), _dt(raw.dtype), _stream()), None, "madm_op_geglu_fwd")
+    return out
+
+
+def geglu_bwd(raw, dout):
+    lib = _lib.load()
+    M, H2 = raw.shape
+    draw = torch.empty_like(raw)
+    _lib.check(lib.madm_op_geglu_bwd(_ptr(raw), _ptr(dout), M, H2 // 2, _ptr(draw), _dt(raw.dtype), _stream()), None, "madm_op_geglu_bwd")
+    return draw
+
+
+def attention_bwd(q, ldq, k, ldk, v, ldv, o, ldo, dout, lddo, dq, lddq, dk, lddk, dv, lddv, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, do_bs, dq_bs,
+                  dkv_bs, scale):
+    lib = _lib.load()
+    scratch = torch.empty(2 * B * heads * Nq, dtype=torch.float32, device=o.device)
+    _lib.check(lib.madm_op_attention_bwd(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(o), ldo, _ptr(dout), lddo, _ptr(dq), lddq, _ptr(dk), lddk,
+                                         _ptr(dv), lddv, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, do_bs, dq_bs, dkv_bs, float(scale), _ptr(scratch),
+                                         _dt(o.dtype), _stream()), None, "madm_op_attention_bwd")
+
+
+def wgrad(dy, x, N, K, *, taps=1, geom=(0, 0, 0), alpha=1.0, transpose_out=False, lda=None, ldb=None, M=None):
+    """dW[n,k] = alpha * sum_m dY[m,n] X[m,k] (taps=9: X is NHWC [B,H,W,K], result in conv layout [N,K,3,3])."""
+    lib = _lib.load()
+    M = M if M is not None else dy.shape[0]
+    lda = lda if lda is not None else dy.stride(0)
+    ldb = ldb if ldb is not None else (x.stride(0) if x.dim() == 2 else x.shape[-1])
+    shape = (N, K, 3, 3) if taps == 9 else ((K, N) if transpose_out else (N, K))
+    out = torch.empty(shape, dtype=torch.float32, device=dy.device)
+    scratch = torch.empty(lib.madm_op_wgrad_scratch_floats(M, N, K, taps), dtype=torch.float32, device=dy.device)
+    _lib.check(lib.madm_op_wgrad(_ptr(dy), lda, _ptr(x), ldb, M, N, K, taps, geom[0], geom[1], geom[2], float(alpha), _ptr(out), int(transpose_out),
+                                 _ptr(scratch), _dt(dy.dtype), _stream()), None, "madm_op_wgrad")
+    return out
+
+
+def colsum_per_image(x, out=None, col_off=0):
+    lib = _lib.load()
+    B, HW, Cc = x.shape
+    if out is None:
+        out = torch.empty(B, Cc, dtype=torch.float32, device=x.device)
+    _lib.check(lib.madm_op_colsum_per_image(_ptr(x), B, HW, Cc, C.c_void_p(out.data_ptr() + 4 * col_off), out.stride(0), _dt(x.dtype), _stream()), None,
+               "madm_op_colsum_per_image")
+    return out
+
+
+def zero_stuff2x(x):
+    lib = _lib.load()
+    B, h, w, Cc = x.shape
+    out = torch.empty(B, 2 * h, 2 * w, Cc, dtype=x.dtype, device=x.device)
+    _lib.check(lib.madm_op_zero_stuff2x(_ptr(x), B, h, w, Cc, _ptr(out), _stream()), None, "madm_op_zero_stuff2x")
+    return out
+
+
+def sum2x2(x, out=None, accumulate=False):
+    lib = _lib.load()
+    B, H2, W2, Cc = x.shape
+    if out is None:
+        out = torch.empty(B, H2 // 2, W2 // 2, Cc, dtype=torch.float32, device=x.device)
+    _lib.check(lib.madm_op_sum2x2(_ptr(x), B, H2 // 2, W2 // 2, Cc, _ptr(out), int(accumulate), _stream()), None, "madm_op_sum2x2")
+    return out
+
+
+def relu_bwd_nchw(dout, out, scale=1.0, dtype=torch.bfloat16):
+    lib = _lib.load()
+    B, Cc, H, W = out.shape
+    dz = torch.empty(B, H * W, Cc, dtype=dtype, device=out.device)
+    _lib.check(lib.madm_op_relu_bwd_nchw(_ptr(dout), _ptr(out), B, Cc, H * W, float(scale), _ptr(dz), _dt(dtype), _stream()), None,
+               "madm_op_relu_bwd_nchw")
+    return dz
