@@ -156,6 +156,9 @@ typedef struct madm_extract_args {
   int32_t head_h, head_w;
   const void* packed_dgrad;    /* MADM_FLAG_TRAIN: the arena filled by madm_pack_dgrad_weights (holds the natural-order feed-forward weights
                                   of the training forward next to the input-gradient operands) */
+  const char* train_adapter;   /* MADM_FLAG_TRAIN: the active LoRA adapter (names the lora_A / lora_B gradients); NULL / "" = none */
+  float train_lora_scale;      /* its alpha / r */
+  float train_loss_scale;      /* loss scale of the backward that will follow (> 0; 1.0 with bf16 operands) */
 } madm_extract_args;
 
 /* The whole path a-1..a-9 of SURVEY §8: VAE encode -> q-sample -> UNet forward with taps -> GN-bottleneck projections. */
@@ -326,7 +329,8 @@ int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, c
 int madm_set_grad_tensors(madm_ctx* ctx, const madm_tensor* named, int32_t n); /* fp32 device buffers shaped like the parameters */
 size_t madm_dgrad_packed_bytes(madm_ctx* ctx);
 int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed_dgrad, const char* adapter, float lora_alpha_over_r, madm_stream stream);
-size_t madm_train_workspace_bytes(madm_ctx* ctx, int32_t B);
+/* workspace of a MADM_FLAG_TRAIN forward + madm_backward at batch B with this adapter active (call after madm_set_grad_tensors) */
+size_t madm_train_workspace_bytes(madm_ctx* ctx, int32_t B, const char* adapter);
 typedef struct madm_backward_args {
   int32_t B;
   int32_t reserved;

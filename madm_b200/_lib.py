@@ -18,6 +18,7 @@ STAGE_HEAD = 8
 STAGE_DEC, STAGE_ALL_S0 = 16, 23
 VARIANT_BASE, VARIANT_S0 = 0, 1
 FLAG_IMG_NORMALISED = 1
+FLAG_TRAIN = 2
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU = 0, 1, 2, 3
 DTYPE_BF16, DTYPE_FP16 = 0, 1
 
@@ -40,6 +41,17 @@ class MadmExtractArgs(C.Structure):
         ("range_flag", c_void_p), ("logits", c_void_p),
         ("unet_sample", c_void_p), ("decoded", c_void_p), ("decoded_raw", c_void_p),
         ("head_h", c_int32), ("head_w", c_int32),
+        ("packed_dgrad", c_void_p), ("train_adapter", c_char_p), ("train_lora_scale", c_float), ("train_loss_scale", c_float),
+    ]
+
+
+class MadmBackwardArgs(C.Structure):
+    _fields_ = [
+        ("B", c_int32), ("reserved", c_int32),
+        ("dout", c_void_p * 4), ("out", c_void_p * 4), ("cond_emb", c_void_p),
+        ("d_cond_inputs", c_void_p), ("d_cond_emb", c_void_p),
+        ("adapter", c_char_p), ("lora_alpha_over_r", c_float), ("loss_scale", c_float),
+        ("packed", c_void_p), ("packed_dgrad", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
     ]
 
 
@@ -83,6 +95,12 @@ SYMBOLS = {
     "madm_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
     "madm_workspace_bytes_head": (c_size_t, [c_void_p, c_int32, c_int32, c_int32]),
     "madm_extract": (c_int, [c_void_p, C.POINTER(MadmExtractArgs), c_void_p]),
+    "madm_set_grad_tensors": (c_int, [c_void_p, C.POINTER(MadmTensor), c_int32]),
+    "madm_dgrad_packed_bytes": (c_size_t, [c_void_p]),
+    "madm_pack_dgrad_weights": (c_int, [c_void_p, c_void_p, c_char_p, c_float, c_void_p]),
+    "madm_train_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_char_p]),
+    "madm_backward": (c_int, [c_void_p, C.POINTER(MadmBackwardArgs), c_void_p]),
+    "madm_backward_launch_count": (c_int, [c_void_p, c_int32]),
     "madm_launch_count": (c_int, [c_void_p, c_int32, c_int32]),
     "madm_set_profiling": (c_int, [c_void_p, c_int32]),
     "madm_get_profile": (c_int, [c_void_p, C.POINTER(MadmProfile)]),

@@ -24,6 +24,11 @@ constexpr int AB = 64;        // block of queries / keys
 constexpr int AB_THREADS = 256;
 constexpr int SLD = AB + 4;   // fp32 score tile pitch
 constexpr int PLD = AB + 8;   // 16-bit probability tile pitch
+// The probability and dS tiles are rounded to 16 bits for the second set of products.  With thousands of keys P ~ 1/n and
+// dS = P * (dP - D) * scale sits around 1e-8 .. 1e-5: in fp16 that is the subnormal range (or below it).  Both tiles are therefore
+// stored pre-multiplied by a power of two and the fp32 accumulators are divided by it when the results are written (exact exponent shifts).
+constexpr float kPScale = 256.0f;     // P <= 1
+constexpr float kDsScale = 16384.0f;
 
 struct AttnBwdParams {
   const uint16_t *q, *k, *v, *o, *dout;
@@ -79,12 +84,12 @@ __device__ __forceinline__ void tile_abt(const T* A, const T* Bm, float* out) {
 
 // fp32 staging [64][DP + 4] -> 16-bit global rows [row0, row0+64) x [0, d)
 template <typename T, int DP>
-__device__ __forceinline__ void write_tile(const float* stage, uint16_t* dst, int ld, int row0, int nrows, int d) {
+__device__ __forceinline__ void write_tile(const float* stage, uint16_t* dst, int ld, int row0, int nrows, int d, float mul) {
   constexpr int FLD = DP + 4;
   for (int i = threadIdx.x; i < AB * (d / 2); i += AB_THREADS) {
     const int r = i / (d / 2), c = (i % (d / 2)) * 2;
     if (row0 + r < nrows) {
-      T a = from_float<T>(stage[r * FLD + c]), b = from_float<T>(stage[r * FLD + c + 1]);
+      T a = from_float<T>(stage[r * FLD + c] * mul), b = from_float<T>(stage[r * FLD + c + 1] * mul);
       uint32_t w = uint32_t(*reinterpret_cast<uint16_t*>(&a)) | (uint32_t(*reinterpret_cast<uint16_t*>(&b)) << 16);
       *reinterpret_cast<uint32_t*>(dst + size_t(row0 + r) * ld + c) = w;
     }
@@ -159,8 +164,8 @@ __device__ __forceinline__ void softmax_grad_tile(const float* Sf, const float* 
       pv = __expf(Sf[r * SLD + c] * scale - Ls[r]);
       ds = pv * (dPf[r * SLD + c] - Ds[r]) * scale;
     }
-    if (Ps) Ps[r * PLD + c] = from_float<T>(pv);
-    dSs[r * PLD + c] = from_float<T>(ds);
+    if (Ps) Ps[r * PLD + c] = from_float<T>(pv * kPScale);
+    dSs[r * PLD + c] = from_float<T>(ds * kDsScale);
   }
 }
 
@@ -244,12 +249,12 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const AttnBwdP
 #pragma unroll
   for (int i = 0; i < NTH; ++i) { const int t = tc + 2 * i; if (t < NT) wmma::store_matrix_sync(stage + (r * 16) * FLD + t * 16, accK[i], FLD, wmma::mem_row_major); }
   __syncthreads();
-  write_tile<T, DP>(stage, dk, p.lddk, j0, p.Nk, p.d);
+  write_tile<T, DP>(stage, dk, p.lddk, j0, p.Nk, p.d, 1.0f / kDsScale);
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < NTH; ++i) { const int t = tc + 2 * i; if (t < NT) wmma::store_matrix_sync(stage + (r * 16) * FLD + t * 16, accV[i], FLD, wmma::mem_row_major); }
   __syncthreads();
-  write_tile<T, DP>(stage, dv, p.lddv, j0, p.Nk, p.d);
+  write_tile<T, DP>(stage, dv, p.lddv, j0, p.Nk, p.d, 1.0f / kPScale);
 }
 
 // ------------------------------------------------------------------------------------------------ dQ
@@ -314,7 +319,7 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dq_kernel(const AttnBwdPa
 #pragma unroll
   for (int i = 0; i < NTH; ++i) { const int t = tc + 2 * i; if (t < NT) wmma::store_matrix_sync(stage + (r * 16) * FLD + t * 16, accQ[i], FLD, wmma::mem_row_major); }
   __syncthreads();
-  write_tile<T, DP>(stage, p.dq + size_t(b) * p.dq_bs + h * p.d, p.lddq, i0, p.Nq, p.d);
+  write_tile<T, DP>(stage, p.dq + size_t(b) * p.dq_bs + h * p.d, p.lddq, i0, p.Nq, p.d, 1.0f / kDsScale);
 }
 
 template <typename T, int DP>

@@ -412,7 +412,17 @@ __global__ void temb_silu_bwd_kernel(const float* __restrict__ d_act, const floa
   d_cond_emb[i] = scale * d_act[i] * act_grad(emb[i] + cond_emb[i], ACT_SILU);
 }
 
+__global__ void scale_copy_kernel(const float* __restrict__ src, long n, float scale, float* __restrict__ dst) {
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * scale;
+}
+
 }  // namespace
+
+const char* scale_copy_f32(const float* src, long n, float scale, float* dst, cudaStream_t st) {
+  scale_copy_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(src, n, scale, dst);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "scale_copy_f32 launch failed";
+}
 
 // ------------------------------------------------------------------------------------------------ launchers
 static inline int gn_bwd_slab_pix(int HW) { return HW >= 4096 ? 64 : 16; }

@@ -167,6 +167,7 @@ const char* zero_stuff2x(const void* x16, int B, int h, int w, int C, void* out1
 const char* sum2x2(const float* x, int B, int h, int w, int C, float* out, int accumulate, cudaStream_t st);
 // dz16 [B,HW,C] = scale * dout[b,c,p] * (out[b,c,p] > 0): ReLU backward of the projections' last pass + NCHW -> NHWC
 const char* relu_bwd_nchw_to_nhwc16(const float* dout, const float* out, int B, int C, int HW, float scale, void* dz16, int fp16, cudaStream_t st);
+const char* scale_copy_f32(const float* src, long n, float scale, float* dst, cudaStream_t st);
 const char* temb_silu_bwd(const float* d_act, const float* emb, const float* cond_emb, long n, float scale, float* d_cond_emb, cudaStream_t st);
 
 // ---- attention_bwd.cu: gradients of softmax(Q K^T scale) V per (image, head); scratch = attention_bwd_scratch_floats(B, heads, Nq) floats

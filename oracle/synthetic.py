@@ -88,7 +88,7 @@ def training_gradients(bb, img: torch.Tensor, adapter: str = "Depth", input_moda
         p.requires_grad_(True)
     out = bb(img, input_modal=input_modal)["output_features"]
     g = torch.Generator().manual_seed(seed)
-    loss = sum((v * torch.randn(v.shape, generator=g)).sum() for v in out.values()) / 1e3
+    loss = sum((v * torch.randn(v.shape, generator=g).to(v.device)).sum() for v in out.values()) / 1e3
     loss.backward()
     grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in train}
     for _, p in train:
