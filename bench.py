@@ -499,6 +499,186 @@ def run_slide(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_train(args, rank, local_rank, world):
+    """BASELINE configs[4]: the LoRA training step, 2 images per GPU (reference MTMADISE.forward
+    mtmadise.py:177-656 under AMPTrainer.run_step, engine/train_loop.py:257-311).  One step =
+      source pass  : backbone(source, 'rgb', adapter default) under grad
+      teacher pass : backbone(target, 'others', ema_forward=True, adapter Depth) under no_grad -> DAFormer head -> pseudo-labels / weights
+      DACS mix     : class mask from the source labels, image_mix, one_mix of labels / weights (device kernels, no host sync)
+      mixed pass   : backbone(mixed, 'mixed', adapter Depth) under grad
+      backward     : ONE backward of the summed losses through both student passes (madm_backward x 2)
+      all-reduce   : ONE NCCL all-reduce over the flat gradient buffer of the trainable set (zeros for what took no part)
+      update       : FusedAdamW with folded clip_grad_norm_, EMA update of the teacher's projections
+    The segmentation head + criterion of the student passes are outside SURVEY §8's path (they stay the reference's own PyTorch code in a
+    real run): the bench closes the loop with a fixed linear functional of the feature dict weighted by the mixed pixel weights, so
+    every gradient the engine produces is consumed.  value = source images per second over all ranks (2 per GPU per step)."""
+    import torch
+    import torch.distributed as dist
+    from helpers import build_product_backbone, set_lora_adapter
+    from madm_b200 import teacher as mteacher
+    from madm_b200.head import DAFormerHead
+    from madm_b200.optim import FusedAdamW, allreduce_grads, update_ema
+    from test_head_gpu import HEAD_KW
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = 2
+    dtype = args.train_dtype
+    torch.manual_seed(1234)  # identical replicas on every rank (DDP broadcasts the weights; here the seed does)
+    bb = build_product_backbone(dev, compute_dtype=dtype)
+    ldm = bb.feature_extractor.ldm_extractor
+    with torch.no_grad():
+        g = torch.Generator(device=dev).manual_seed(99)
+        for _, m in ldm.unet.lora_layers():
+            for a in m.lora_B:
+                m.lora_B[a].weight.copy_(torch.randn(m.lora_B[a].weight.shape, device=dev, generator=g) * 0.02)
+    for n, p in bb.named_parameters():  # the LoRA training step's trainable set (BASELINE.json narrows config 5 to it)
+        p.requires_grad_(("lora_" in n) or n.startswith("feature_projections.") or (n.startswith("feature_extractor.clip_project_")))
+    trainable = [p for p in bb.parameters() if p.requires_grad]
+    n_train = sum(p.numel() for p in trainable)
+    opt = FusedAdamW(trainable, lr=1e-5, weight_decay=0.01)
+    head = DAFormerHead(**HEAD_KW, device=dev, compute_dtype=dtype).eval()
+    gi = torch.Generator().manual_seed(100 + rank)
+    src_host = torch.rand(B, 3, 512, 512, generator=gi).pin_memory()
+    tgt_host = torch.rand(B, 3, 512, 512, generator=gi).pin_memory()
+    lab_host = torch.randint(0, 19, (B, 512, 512), generator=gi).pin_memory()
+    src_dev, tgt_dev, lab_dev = src_host.to(dev), tgt_host.to(dev), lab_host.to(dev)
+    gr = torch.Generator().manual_seed(7)
+    R = [torch.randn(B, 512, s, s, generator=gr).to(dev) / 1e3 for s in (128, 64, 32, 16)]
+    classes = torch.arange(0, 19, 2, device=dev)
+    ev = {k: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for k in ("fwd", "bwd", "allreduce", "update")}
+    acc_ms = {k: 0.0 for k in ev}
+    it = [0]
+
+    def functional(feats, w=None):
+        tot = 0.0
+        for f, r in zip(feats.values(), R):
+            t = f * r
+            if w is not None:
+                t = t * w
+            tot = tot + t.sum()
+        return tot
+
+    def step(src, tgt, lab, timed=False):
+        if timed:
+            ev["fwd"][0].record()
+        set_lora_adapter(ldm.unet, "default")
+        f_src = bb(src, input_modal="rgb")["output_features"]
+        loss = functional(f_src)
+        with torch.no_grad():
+            set_lora_adapter(ldm.unet, "Depth")
+            f_t = bb(tgt, input_modal="others", ema_forward=True)
+            label, prob, weight, count = mteacher.pseudo_labels(head(f_t), (512, 512), 0.968)
+            mixed, wmix = [], []
+            for i in range(B):
+                mask = mteacher.generate_class_mask(lab[i], classes)
+                mixed.append(mteacher.image_mix(mask, torch.stack((src[i], tgt[i]))))
+                _, wm = mteacher.one_mix(mask, target=torch.stack((lab[i], label[i])),
+                                         weight=torch.stack((torch.ones_like(weight[i]), weight[i])))
+                wmix.append(wm)
+            mixed = torch.cat(mixed)
+            wscalar = torch.cat(wmix).mean()
+        f_mix = bb(mixed, input_modal="mixed")["output_features"]
+        loss = loss + functional(f_mix) * wscalar
+        if timed:
+            ev["fwd"][1].record(); ev["bwd"][0].record()
+        loss.backward()
+        if timed:
+            ev["bwd"][1].record(); ev["allreduce"][0].record()
+        allreduce_grads(trainable)
+        if timed:
+            ev["allreduce"][1].record(); ev["update"][0].record()
+        opt.step(clip_grad=1.0)
+        it[0] += 1
+        update_ema(list(bb.ema_feature_projections.parameters()), list(bb.feature_projections.parameters()), it[0])
+        opt.zero_grad(set_to_none=True)
+        if timed:
+            ev["update"][1].record()
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step(src_dev, tgt_dev, lab_dev)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(src_dev, tgt_dev, lab_dev, timed=True)
+        torch.cuda.current_stream().synchronize() if False else None
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    for k in ev:  # (events of the LAST step: a per-phase picture, not the timed total)
+        acc_ms[k] = ev[k][0].elapsed_time(ev[k][1])
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    barrier()
+    # end to end: the step's inputs come from pinned host memory, its loss is read back
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_e2e():
+        l = step(src_host.to(dev, non_blocking=True), tgt_host.to(dev, non_blocking=True), lab_host.to(dev, non_blocking=True))
+        loss_host.copy_(l.reshape(1), non_blocking=True)
+    step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    torch.cuda.synchronize()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    eng = ldm.engine()
+    imgs = B * world * args.steps
+    fwd_l = eng.launch_count(B)
+    bwd_l = int(eng.lib.madm_backward_launch_count(eng.ctx, B))
+    # algorithmic FLOPs of one step per GPU: 3 forwards of the base path on 2 images + 2 backward passes through UNet + projections
+    # (input gradients ~ 1x the forward contractions of the UNet, attention backward 2.5x its forward; LoRA / projection weight
+    # gradients are small) -- reported as an estimate, the bench's figure of merit is images/s
+    gf_fwd = 3 * B * GF_PER_IMG["total"]
+    gf_bwd = 2 * B * (GF_PER_IMG["unet_taps"] * 1.25 + GF_PER_IMG["projections"] * 2)
+    line = {
+        "metric": METRIC, "value": imgs / (ms.item() / 1e3), "unit": "training images/s (2 source images per GPU per step)", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms.item() / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic (seeded rand images / labels, random-init SD-1.4 weights + r16 LoRA, SURVEY §8d)",
+        "config": {"workload": "BASELINE configs[4]: LoRA training step, 2 images per GPU: source pass (rgb / default) + EMA-teacher pass + DACS "
+                               "mix + mixed pass (mixed / Depth) under grad, one backward, one gradient all-reduce, AdamW + clip, EMA update",
+                   "config": "train", "per_gpu_batch": B, "trainable_parameters": n_train, "allreduce_bytes": n_train * 4,
+                   "loss": "fixed linear functional of the feature dict (the head + criterion of the student passes are outside SURVEY §8)",
+                   "loss_scale": float(getattr(ldm, "train_loss_scale", None) or (1.0 if dtype == "bf16" else 4096.0)),
+                   "l2": "working set >> 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": imgs / (ms2.item() / 1e3), "unit": "training images/s", "ms_per_step": ms2.item() / args.steps,
+                "h2d_bytes_per_step": 2 * src_host.numel() * 4 + lab_host.numel() * 8, "d2h_bytes_per_step": 4,
+                "api": "backbone(...) under grad x 2 + teacher pass + loss.backward() + allreduce_grads + FusedAdamW.step + update_ema; images "
+                       "and labels uploaded from pinned memory, the loss read back"},
+        "phases_last_step_ms": acc_ms,
+        "allreduce_exposed_ms": acc_ms["allreduce"],
+        "gpu_launches": (3 * fwd_l + 2 * bwd_l) * args.steps,
+        "launches_per_step": {"forward_per_pass": fwd_l, "backward_per_pass": bwd_l},
+        "estimated_tflops_per_gpu": (gf_fwd + gf_bwd) / (ms.item() / args.steps),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -510,6 +690,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="base", choices=["base", "slide1024", "teacher2048", "train"],
                     help="base = BASELINE configs[1] (the bench line); slide1024 / teacher2048 / train = BASELINE configs[2..4]")
+    ap.add_argument("--train-dtype", default="fp16", choices=["fp16", "bf16"],
+                    help="operand dtype of the training step: fp16 + loss scale (the reference's AMP regime, default) or bf16")
     ap.add_argument("--images", type=int, default=8, help="full-resolution images per GPU per step (slide1024 / teacher2048)")
     ap.add_argument("--variant", default="base", choices=["base", "s0"],
                     help="base = BASELINE configs[1] (the bench line); s0 = vae_decoder_loss configuration of the shipped experiment files")

@@ -95,8 +95,9 @@ size_t madm_packed_bytes(madm_ctx* ctx);
 /* fp32 -> bf16 K-major packing of every GEMM weight into `packed` (caller-allocated, madm_packed_bytes()).
  * `adapter` names the active LoRA adapter to fold (W' = W + alpha/r * B@A; replaces peft's LoRA Linear.forward and
  * MTMADISE.set_lora_adapter, reference modeling/meta_arch/mtmadise.py:115-147); NULL or "" = base weights.
- * lora_alpha_over_r: scaling for that adapter.  lora_only != 0 repacks just the 128 LoRA-targeted projections
- * (adapter switch); 0 repacks everything (after load_state_dict / optimizer step / EMA update). */
+ * lora_alpha_over_r: scaling for that adapter.  lora_only = 1 repacks just the 128 LoRA-targeted projections (adapter switch),
+ * 2 those plus the feature_projections / ema_feature_projections convs (what a LoRA training step's optimizer / EMA update touches);
+ * 0 repacks everything (after load_state_dict). */
 int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float lora_alpha_over_r, int32_t lora_only,
                       madm_stream stream);
 
@@ -328,7 +329,10 @@ int madm_op_gn_add_relu_nchw(const float* a, const float* ga, const float* ba, c
 #define MADM_FLAG_TRAIN 2
 int madm_set_grad_tensors(madm_ctx* ctx, const madm_tensor* named, int32_t n); /* fp32 device buffers shaped like the parameters */
 size_t madm_dgrad_packed_bytes(madm_ctx* ctx);
-int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed_dgrad, const char* adapter, float lora_alpha_over_r, madm_stream stream);
+/* trainable_only != 0 repacks just what an optimizer step or an adapter switch can change (LoRA-folded linears, LoRA factors,
+ * feature_projections convs) in an arena that was fully packed before */
+int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed_dgrad, const char* adapter, float lora_alpha_over_r, int32_t trainable_only,
+                            madm_stream stream);
 /* workspace of a MADM_FLAG_TRAIN forward + madm_backward at batch B with this adapter active (call after madm_set_grad_tensors) */
 size_t madm_train_workspace_bytes(madm_ctx* ctx, int32_t B, const char* adapter);
 typedef struct madm_backward_args {

@@ -97,7 +97,7 @@ SYMBOLS = {
     "madm_extract": (c_int, [c_void_p, C.POINTER(MadmExtractArgs), c_void_p]),
     "madm_set_grad_tensors": (c_int, [c_void_p, C.POINTER(MadmTensor), c_int32]),
     "madm_dgrad_packed_bytes": (c_size_t, [c_void_p]),
-    "madm_pack_dgrad_weights": (c_int, [c_void_p, c_void_p, c_char_p, c_float, c_void_p]),
+    "madm_pack_dgrad_weights": (c_int, [c_void_p, c_void_p, c_char_p, c_float, c_int32, c_void_p]),
     "madm_train_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_char_p]),
     "madm_backward": (c_int, [c_void_p, C.POINTER(MadmBackwardArgs), c_void_p]),
     "madm_backward_launch_count": (c_int, [c_void_p, c_int32]),

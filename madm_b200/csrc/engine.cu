@@ -2314,9 +2314,11 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float sc
     auto it = ctx->params.find(name);
     return it == ctx->params.end() ? nullptr : &it->second;
   };
+  auto is_proj = [](const std::string& s) { return s.rfind("feature_projections.", 0) == 0 || s.rfind("ema_feature_projections.", 0) == 0; };
   for (const PackEntry& e : ctx->pack) {
     const char* err = nullptr;
-    if (lora_only && !(e.kind == PK_LINEAR && e.lora)) continue;
+    if (lora_only == 1 && !(e.kind == PK_LINEAR && e.lora)) continue;
+    if (lora_only == 2 && !((e.kind == PK_LINEAR && e.lora) || is_proj(e.src))) continue;  // the training step's trainable set
     switch (e.kind) {
       case PK_CONV: {
         const ParamRef* w = get(e.src);
@@ -2638,7 +2640,7 @@ size_t madm_dgrad_packed_bytes(madm_ctx* ctx) {
   return ctx->dpacked_bytes;
 }
 
-int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed, const char* adapter, float scale, madm_stream stream) {
+int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed, const char* adapter, float scale, int32_t trainable_only, madm_stream stream) {
   if (!ctx || !packed) return set_err(ctx, MADM_EINVAL, "madm_pack_dgrad_weights: null argument");
   if (ctx->device < 0) return set_err(ctx, MADM_ECUDA, "madm_pack_dgrad_weights: this context was created without a device (MADM_PLAN_ONLY)");
   int rc = ensure_dlayout(ctx);
@@ -2652,6 +2654,11 @@ int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed, const char* adapter, fl
   };
   for (const DPackEntry& e : ctx->dpack) {
     const char* err = nullptr;
+    if (trainable_only) {  // only what an optimizer step / adapter switch can change: LoRA-folded linears, LoRA factors, projection convs
+      const bool hit = (e.kind == DG_LINEAR && e.lora) || e.kind == DG_LORA_A || e.kind == DG_LORA_BT ||
+                       (e.kind == DG_CONV && e.src.rfind("feature_projections.", 0) == 0);
+      if (!hit) continue;
+    }
     switch (e.kind) {
       case DG_CONV: {
         const ParamRef* w = get(e.src);

@@ -89,6 +89,16 @@ class Engine:
     def _version_vector(self):
         return tuple(t._version for _, t in self._named)
 
+    def only_trainables_changed(self, old, new) -> bool:
+        """True if every tensor whose version moved between two version vectors belongs to the LoRA training step's trainable set
+        (LoRA factors, feature_projections / ema_feature_projections) and nothing else did — then a partial repack suffices."""
+        if old is None or len(old) != len(new):
+            return False
+        for (n, _), a, b in zip(self._named, old, new):
+            if a != b and not (".lora_A." in n or ".lora_B." in n or n.startswith("feature_projections.") or n.startswith("ema_feature_projections.")):
+                return False
+        return True
+
     def ensure_packed(self, adapter: Optional[str], scaling: float):
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         need = self.lib.madm_packed_bytes(self.ctx)
@@ -100,7 +110,9 @@ class Engine:
         vers = self._version_vector()
         ad = (adapter or "").encode()
         if vers != self._versions:
-            _lib.check(self.lib.madm_pack_weights(self.ctx, C.c_void_p(self._packed.data_ptr()), ad, scaling, 0, st), self.ctx,
+            # a LoRA training step moves only LoRA factors and projection weights (optimizer step, EMA update): repack just those
+            mode = 2 if self.only_trainables_changed(self._versions, vers) else 0
+            _lib.check(self.lib.madm_pack_weights(self.ctx, C.c_void_p(self._packed.data_ptr()), ad, scaling, mode, st), self.ctx,
                        "madm_pack_weights")
             self._versions, self._packed_adapter = vers, adapter
         elif adapter != self._packed_adapter:  # adapter switch: re-fold only the 128 LoRA-targeted projections

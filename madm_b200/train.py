@@ -127,12 +127,14 @@ class _ExtractFn(torch.autograd.Function):
         need = lib.madm_dgrad_packed_bytes(eng.ctx)
         if need == 0:
             _lib.check(-1, eng.ctx, "madm_dgrad_packed_bytes")
-        sig = (eng._version_vector(), adapter)
+        sig = (eng._version_vector(), adapter, id(eng._named))
         if slot.dgrad is None or slot.dgrad.numel() != need:
             slot.dgrad, slot.dgrad_sig = torch.empty(need, dtype=torch.uint8, device=dev), None
         if slot.dgrad_sig != sig:
-            _lib.check(lib.madm_pack_dgrad_weights(eng.ctx, C.c_void_p(slot.dgrad.data_ptr()), ad, float(scaling), st), eng.ctx,
-                       "madm_pack_dgrad_weights")
+            old = slot.dgrad_sig
+            partial = old is not None and old[2] == sig[2] and eng.only_trainables_changed(old[0], sig[0])
+            _lib.check(lib.madm_pack_dgrad_weights(eng.ctx, C.c_void_p(slot.dgrad.data_ptr()), ad, float(scaling), 1 if partial else 0, st),
+                       eng.ctx, "madm_pack_dgrad_weights")
             slot.dgrad_sig = sig
         wneed = lib.madm_train_workspace_bytes(eng.ctx, B, ad)
         if wneed == 0:

@@ -185,7 +185,7 @@ def test_golden_gradient_fixture(pair, cuda_device):
         got = params[n].grad
         assert got is not None, n
         ref_norm = float(g["norm"][i])
-        if abs(float(got.double().norm()) - ref_norm) > (5e-2 if mode == "fp16" else 1e-1) * ref_norm + 1e-9:
+        if abs(float(got.double().norm()) - ref_norm) > (5e-2 if mode == "fp16" else 2e-1) * ref_norm + 1e-9:
             bad.append((n, float(got.norm()), ref_norm))
         head = got.flatten()[:8].double().cpu().numpy()
         scale = ref_norm / np.sqrt(got.numel())  # leading values of every tensor, in units of its RMS
