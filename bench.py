@@ -246,6 +246,24 @@ def run_product(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         barrier()
         ms_e2e = t.item()
+        # opt-in fp16 feature maps (backbone.feature_dtype = torch.float16, MADM_FLAG_OUT_FP16): the same pipelined end-to-end run with
+        # half the download -- what a host-bound consumer of the feature dict would choose; `e2e` above stays on the reference's fp32 maps
+        ms_e2e_f16 = None
+        if args.variant == "base":
+            bb.feature_dtype = torch.float16
+            run_e2e_pipelined(2)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            run_e2e_pipelined(args.steps)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            barrier()
+            ms_e2e_f16 = t.item()
+            bb.feature_dtype = torch.float32
         ms_e2e_head = None
         if pipe_head is not None:
             pipe_head.run([img_host] * 2, consume=lambda i, host: None)
@@ -368,6 +386,10 @@ def run_product(args, rank, local_rank, world):
                             "api": "HostPipeline around backbone -> madm_b200.head.DAFormerHead (MADM_STAGE_HEAD) -> teacher.pseudo_labels "
                                    "(fused upsample / softmax / arg-max): the feature dict stays on the device as in MADM's eval loop "
                                    "(mtmadise.py:685-688), only the int64 label map is downloaded (d2_evaluator.py:106)"}
+    if ms_e2e_f16 is not None:
+        line["e2e_fp16_features"] = {"value": imgs / (ms_e2e_f16 / 1e3), "unit": UNIT, "ms_per_step": ms_e2e_f16 / args.steps,
+                                     "h2d_bytes_per_step": img_host.numel() * 4, "d2h_bytes_per_step": sum(t.numel() * 2 for t in outs_host),
+                                     "api": "as `e2e`, with backbone.feature_dtype = torch.float16 (opt-in extension: fp16 feature maps)"}
     if numa:
         line["config"]["numa"] = numa
     print(json.dumps(line), flush=True)

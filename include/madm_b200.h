@@ -120,6 +120,10 @@ size_t madm_workspace_bytes(madm_ctx* ctx, int32_t B);
 size_t madm_workspace_bytes_head(madm_ctx* ctx, int32_t B, int32_t head_h, int32_t head_w);
 
 #define MADM_FLAG_IMG_NORMALISED 1
+/* out[0..3] are fp16 [B,C,H,W] tensors instead of fp32 (base variant, MADM_STAGE_PROJ): an opt-in for host-bound consumers -- the
+ * reference returns fp32 maps (GroupNorm runs in fp32 under autocast), so fp32 stays the default.  Halves the 357 MB per 8 images that
+ * a caller who downloads the feature dict moves over PCIe. */
+#define MADM_FLAG_OUT_FP16 4
 typedef struct madm_extract_args {
   int32_t B;                   /* images (512x512 crops) in this call */
   int32_t stages;              /* MADM_STAGE_* mask; intermediate results live in the workspace between calls */
@@ -369,7 +373,8 @@ int madm_op_layernorm_bwd(const float* x, int32_t M, int32_t C, const float* gam
 /* GEGLU, natural column order: raw16 [M,2H] = (hidden | gate) -> out16 [M,H]; backward: draw16 [M,2H] */
 int madm_op_geglu_fwd(const void* raw16, int64_t M, int32_t H, void* out16, int32_t dtype, madm_stream stream);
 int madm_op_geglu_bwd(const void* raw16, const void* dout16, int64_t M, int32_t H, void* draw16, int32_t dtype, madm_stream stream);
-/* softmax(Q K^T scale) V backward per (image, head): same addressing as madm_op_attention; scratch = 2*B*heads*Nq floats */
+/* softmax(Q K^T scale) V backward per (image, head): same addressing as madm_op_attention; scratch = madm_op_attention_bwd_scratch_floats(..) floats */
+int64_t madm_op_attention_bwd_scratch_floats(int32_t B, int32_t heads, int32_t d, int32_t Nq, int32_t Nk);
 int madm_op_attention_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, const void* o, int32_t ldo,
                           const void* dout, int32_t lddo, void* dq, int32_t lddq, void* dk, int32_t lddk, void* dv, int32_t lddv, int32_t B,
                           int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bs, int64_t kv_bs, int64_t o_bs, int64_t do_bs, int64_t dq_bs,

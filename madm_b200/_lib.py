@@ -19,6 +19,7 @@ STAGE_DEC, STAGE_ALL_S0 = 16, 23
 VARIANT_BASE, VARIANT_S0 = 0, 1
 FLAG_IMG_NORMALISED = 1
 FLAG_TRAIN = 2
+FLAG_OUT_FP16 = 4
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_RELU = 0, 1, 2, 3
 DTYPE_BF16, DTYPE_FP16 = 0, 1
 
@@ -147,6 +148,7 @@ SYMBOLS = {
     "madm_op_layernorm_bwd": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_float, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "madm_op_geglu_fwd": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p]),
     "madm_op_geglu_bwd": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_attention_bwd_scratch_floats": (c_int64, [c_int32, c_int32, c_int32, c_int32, c_int32]),
     "madm_op_attention_bwd": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32,
                                       c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int64, c_int64, c_int64,
                                       c_int64, c_int64, c_int64, c_float, c_void_p, c_int32, c_void_p]),

@@ -102,9 +102,13 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
                  attention_select_index=None, feature_extractor=None, out_features: List[str] = None,
                  backbone_in_size: Union[int, Tuple[int]] = (512, 512), min_stride: int = 4, max_stride: int = 32,
                  projection_dim: List[int] = [512, 512, 512, 512], bottleneck_channels: int = 512 // 4, num_res_blocks: int = 1,
-                 use_checkpoint: bool = False, slide_training: bool = False, slide_inference: bool = False, crop_batch: int = 16):
+                 use_checkpoint: bool = False, slide_training: bool = False, slide_inference: bool = False, crop_batch: int = 16,
+                 feature_dtype=torch.float32):
         super().__init__(feature_extractor, out_features, backbone_in_size, min_stride, max_stride, projection_dim, num_res_blocks,
                          use_checkpoint, slide_training, slide_inference)
+        # extension (not a reference kwarg): torch.float16 makes inference return fp16 feature maps (base variant) -- half the bytes for
+        # callers that download the feature dict; the reference's maps are fp32, which stays the default
+        self.feature_dtype = feature_dtype
         self.attention_features_res = attention_features_res
         self.feature_dims = list(feature_dims)
         self.attention_features_location = attention_features_location
@@ -174,7 +178,7 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
             raise AttributeError("ema_forward=True needs backbone.ema_feature_projections (CMDISE._inti_ema_weights)")
         return gen.ldm_extractor.run(batched, input_modal, stages=_lib.STAGE_ALL, ema_projections=bool(ema_forward),
                                      extra=self._projection_tensors(), want_taps=want_taps, timesteps=timesteps,
-                                     ema_forward=ema_forward, **kwargs)
+                                     ema_forward=ema_forward, out_dtype=getattr(self, "feature_dtype", torch.float32), **kwargs)
 
     # ------------------------------------------------------------------ reference surface
     def single_forward(self, img, input_modal="rgb", ema_forward=False, timestep=None, **kwargs):  # :156-170
@@ -220,6 +224,7 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
             feats = self._extract(crops, input_modal, ema_forward, timestep, **kwargs)["features"]
             for k, f in zip(self._out_features, feats):
                 s = self._out_feature_strides[k]
+                f = f if f.dtype == torch.float32 else f.float()  # (feature_dtype=float16: the merge accumulates in fp32)
                 parts[k].append(ops.slide_merge(f, len(wins), [(y1 // s, x1 // s) for (y1, _, x1, _) in wins], h_img // s, w_img // s))
         outs = {k: (v[0] if len(v) == 1 else torch.cat(v, dim=0)) for k, v in parts.items()}
         return {"output_features": outs}

@@ -255,6 +255,9 @@ int madm_op_geglu_fwd(const void* raw16, int64_t M, int32_t H, void* out16, int3
 int madm_op_geglu_bwd(const void* raw16, const void* dout16, int64_t M, int32_t H, void* draw16, int32_t dtype, madm_stream stream) {
   RUN(geglu_bwd(raw16, dout16, long(M), H, draw16, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
 }
+int64_t madm_op_attention_bwd_scratch_floats(int32_t B, int32_t heads, int32_t d, int32_t Nq, int32_t Nk) {
+  return int64_t(attention_bwd_scratch_floats(B, heads, d, Nq, Nk));
+}
 int madm_op_attention_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk, const void* v, int32_t ldv, const void* o, int32_t ldo,
                           const void* dout, int32_t lddo, void* dq, int32_t lddq, void* dk, int32_t lddk, void* dv, int32_t lddv, int32_t B,
                           int32_t heads, int32_t d, int32_t Nq, int32_t Nk, int64_t q_bs, int64_t kv_bs, int64_t o_bs, int64_t do_bs, int64_t dq_bs,

@@ -38,6 +38,10 @@ struct AttnBwdParams {
   int heads, d, Nq, Nk;
   float scale;
   float *L, *D;  // [B, heads, Nq]
+  // few keys (cross-attention, 77): the query loop of the dK / dV kernel is split over qsplit CTAs per key block, each writing an fp32
+  // partial [qsplit][B][heads][kv blocks * 64][DP] that attn_bwd_kv_reduce sums in fixed order
+  int qsplit;
+  float *part_k, *part_v;
 };
 
 template <typename T> __device__ __forceinline__ T from_float(float v);
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const AttnBwdP
   T* dSs = Ps + AB * PLD;
   float* Ls = reinterpret_cast<float*>(dSs + AB * PLD);
   float* Ds = Ls + AB;
-  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int jb = blockIdx.x / p.qsplit, qs = blockIdx.x % p.qsplit, h = blockIdx.y, b = blockIdx.z;
   const int j0 = jb * AB;
   const int warp = threadIdx.x >> 5, r = warp >> 1, tc = warp & 1;
   const uint16_t* q = p.q + size_t(b) * p.q_bs + h * p.d;
@@ -207,7 +211,9 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const AttnBwdP
   wmma::fragment<wmma::accumulator, 16, 16, 16, float> accK[NTH], accV[NTH];
 #pragma unroll
   for (int i = 0; i < NTH; ++i) { wmma::fill_fragment(accK[i], 0.0f); wmma::fill_fragment(accV[i], 0.0f); }
-  for (int i0 = 0; i0 < p.Nq; i0 += AB) {
+  const int qblocks = (p.Nq + AB - 1) / AB, per = (qblocks + p.qsplit - 1) / p.qsplit;
+  const int i_begin = qs * per * AB, i_end = min(p.Nq, (qs + 1) * per * AB);
+  for (int i0 = i_begin; i0 < i_end; i0 += AB) {
     __syncthreads();  // the previous iteration's readers of Qs / dOs / Ps / dSs are done
     load_tile<T, DP>(Qs, q, p.ldq, i0, p.Nq, p.d);
     load_tile<T, DP>(dOs, dout, p.lddo, i0, p.Nq, p.d);
@@ -240,6 +246,19 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const AttnBwdP
         }
       }
     }
+  }
+  if (p.qsplit > 1) {  // fp32 partials straight from the accumulators; attn_bwd_kv_reduce finishes
+    const int kvrows = ((p.Nk + AB - 1) / AB) * AB;
+    const size_t base = (((size_t(qs) * gridDim.z + b) * p.heads + h) * kvrows + j0) * DP;
+#pragma unroll
+    for (int i = 0; i < NTH; ++i) {
+      const int t = tc + 2 * i;
+      if (t < NT) {
+        wmma::store_matrix_sync(p.part_k + base + size_t(r * 16) * DP + t * 16, accK[i], DP, wmma::mem_row_major);
+        wmma::store_matrix_sync(p.part_v + base + size_t(r * 16) * DP + t * 16, accV[i], DP, wmma::mem_row_major);
+      }
+    }
+    return;
   }
   // ---- results: fp32 staging over the (now idle) K / V tiles, then 16-bit rows
   float* stage = reinterpret_cast<float*>(smem_raw);
@@ -322,6 +341,30 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dq_kernel(const AttnBwdPa
   write_tile<T, DP>(stage, p.dq + size_t(b) * p.dq_bs + h * p.d, p.lddq, i0, p.Nq, p.d, 1.0f / kDsScale);
 }
 
+// dk / dv = sum over the query splits of the fp32 partials (fixed order), unscaled, rounded to 16 bits
+template <typename T, int DP>
+__global__ void attn_bwd_kv_reduce_kernel(const AttnBwdParams p, int B) {
+  const int kvrows = ((p.Nk + AB - 1) / AB) * AB;
+  const long total = long(B) * p.heads * p.Nk * (p.d / 2);
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = int(i % (p.d / 2)) * 2;
+  long rest = i / (p.d / 2);
+  const int j = int(rest % p.Nk); rest /= p.Nk;
+  const int h = int(rest % p.heads), b = int(rest / p.heads);
+  float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+  for (int s = 0; s < p.qsplit; ++s) {
+    const size_t o = (((size_t(s) * B + b) * p.heads + h) * kvrows + j) * DP + c;
+    k0 += p.part_k[o]; k1 += p.part_k[o + 1]; v0 += p.part_v[o]; v1 += p.part_v[o + 1];
+  }
+  auto put = [&](uint16_t* dst, float a, float bb) {
+    T x = from_float<T>(a), y = from_float<T>(bb);
+    *reinterpret_cast<uint32_t*>(dst) = uint32_t(*reinterpret_cast<uint16_t*>(&x)) | (uint32_t(*reinterpret_cast<uint16_t*>(&y)) << 16);
+  };
+  put(p.dk + size_t(b) * p.dk_bs + size_t(j) * p.lddk + h * p.d + c, k0 * (1.0f / kDsScale), k1 * (1.0f / kDsScale));
+  put(p.dv + size_t(b) * p.dv_bs + size_t(j) * p.lddv + h * p.d + c, v0 * (1.0f / kPScale), v1 * (1.0f / kPScale));
+}
+
 template <typename T, int DP>
 const char* launch_all(const AttnBwdParams& p, int B, cudaStream_t st) {
   static bool attr = false;
@@ -332,16 +375,36 @@ const char* launch_all(const AttnBwdParams& p, int B, cudaStream_t st) {
       return "attention_bwd: cudaFuncSetAttribute failed";
     attr = true;
   }
-  const dim3 gq((p.Nq + AB - 1) / AB, p.heads, B), gk((p.Nk + AB - 1) / AB, p.heads, B);
+  const dim3 gq((p.Nq + AB - 1) / AB, p.heads, B), gk(((p.Nk + AB - 1) / AB) * p.qsplit, p.heads, B);
   attn_bwd_prep_kernel<T, DP><<<gq, AB_THREADS, AttnSmem<DP>::PREP, st>>>(p);
   attn_bwd_dkv_kernel<T, DP><<<gk, AB_THREADS, AttnSmem<DP>::DKV, st>>>(p);
+  if (p.qsplit > 1) {
+    const long total = long(B) * p.heads * p.Nk * (p.d / 2);
+    attn_bwd_kv_reduce_kernel<T, DP><<<unsigned((total + 255) / 256), 256, 0, st>>>(p, B);
+  }
   attn_bwd_dq_kernel<T, DP><<<gq, AB_THREADS, AttnSmem<DP>::DQ, st>>>(p);
   return cudaGetLastError() == cudaSuccess ? nullptr : "attention_bwd launch failed";
 }
 
 }  // namespace
 
-size_t attention_bwd_scratch_floats(int B, int heads, int Nq) { return size_t(2) * B * heads * Nq; }
+// query splits of the dK / dV kernel: only when there are too few key blocks to fill the GPU (cross-attention: 77 keys = 2 blocks)
+static int attn_qsplit(int B, int heads, int Nq, int Nk) {
+  const int kvb = (Nk + AB - 1) / AB, qb = (Nq + AB - 1) / AB;
+  if (kvb * heads * B >= 148 || qb < 4) return 1;
+  int s = (296 + kvb * heads * B - 1) / (kvb * heads * B);
+  if (s > 16) s = 16;
+  if (s > qb) s = qb;
+  return s < 1 ? 1 : s;
+}
+static int attn_dp(int d) { return d == 40 ? 48 : d; }
+
+size_t attention_bwd_scratch_floats(int B, int heads, int d, int Nq, int Nk) {
+  size_t n = size_t(2) * B * heads * Nq;
+  const int qs = attn_qsplit(B, heads, Nq, Nk);
+  if (qs > 1) n += size_t(2) * qs * B * heads * (((Nk + AB - 1) / AB) * AB) * attn_dp(d) + 16;
+  return n;
+}
 
 const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, int ldo, const void* dout, int lddo,
                           void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B, int heads, int d, int Nq, int Nk, long q_bs, long k_bs,
@@ -359,6 +422,14 @@ const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const 
   p.q_bs = q_bs; p.k_bs = k_bs; p.v_bs = v_bs; p.o_bs = o_bs; p.do_bs = do_bs; p.dq_bs = dq_bs; p.dk_bs = dk_bs; p.dv_bs = dv_bs;
   p.heads = heads; p.d = d; p.Nq = Nq; p.Nk = Nk; p.scale = scale;
   p.L = scratch; p.D = scratch + size_t(B) * heads * Nq;
+  p.qsplit = attn_qsplit(B, heads, Nq, Nk);
+  p.part_k = p.part_v = nullptr;
+  if (p.qsplit > 1) {
+    float* base = scratch + size_t(2) * B * heads * Nq;
+    base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(base) + 31) & ~uintptr_t(31));  // wmma stores need 32-byte alignment
+    const size_t one = size_t(p.qsplit) * B * heads * (((Nk + AB - 1) / AB) * AB) * attn_dp(d);
+    p.part_k = base; p.part_v = base + one;
+  }
   if (fp16) {
     if (d == 40) return launch_all<__half, 48>(p, B, st);
     if (d == 80) return launch_all<__half, 80>(p, B, st);

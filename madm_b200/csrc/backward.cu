@@ -38,18 +38,22 @@ __device__ __forceinline__ float act_grad(float z, int act) {
 // Thread layout shared by the reduce and the apply pass: a CTA owns a slab of pixels of one image; thread (lane v, pixel lane pl)
 // owns the channel pairs v, v + TX, ... (KMAX of them) and walks pixels pl, pl + P, ...
 constexpr int kGnKMax = 5;       // channel pairs per thread: C <= 2 * 256 * 5 = 2560 (the widest concat input of the UNet)
-constexpr int kGnThreads = 256;
+constexpr int kGnThreads = 512;  // CTA size limit: TX * P <= 512
 
 struct GnBwdGeo {
-  int TX;  // threads along the channel-pair axis
-  int P;   // pixel lanes
+  int TX;  // threads along the channel-pair axis (<= 256)
+  int P;   // pixel lanes (1..4)
   int K;   // channel pairs per thread
 };
 __host__ __device__ inline GnBwdGeo gn_bwd_geo(int C) {
   GnBwdGeo g;
   const int cv = C / 2;
-  if (cv <= kGnThreads) { g.TX = cv; g.P = kGnThreads / cv; g.K = 1; }
-  else { g.K = (cv + kGnThreads - 1) / kGnThreads; g.TX = (cv + g.K - 1) / g.K; g.P = 1; }
+  g.K = (cv + 255) / 256;
+  while (g.K < kGnKMax && cv % g.K != 0) ++g.K;  // an exact split where one exists (C = 1280: 640 pairs = 4 x 160)
+  g.TX = (cv + g.K - 1) / g.K;
+  g.P = kGnThreads / g.TX;
+  if (g.P > 4) g.P = 4;
+  if (g.P < 1) g.P = 1;
   return g;
 }
 
@@ -101,19 +105,32 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_reduce_kernel(const void* _
   }
   const int p0 = slab * slab_pix, p1 = min(HW, p0 + slab_pix);
   if (active) {
-    for (int p = p0 + pl; p < p1; p += geo.P) {
-      const size_t pix = size_t(b) * HW + p;
+    for (int p = p0 + pl; p < p1; p += 2 * geo.P) {  // two pixels per trip: their loads are independent and stay in flight together
+      const size_t pixa = size_t(b) * HW + p;
+      const bool two = p + geo.P < p1;
+      const size_t pixb = two ? pixa + geo.P : pixa;
 #pragma unroll
       for (int k = 0; k < kGnKMax; ++k) {
         const int v = tx + k * geo.TX;
         if (k < geo.K && v < cv) {
-          const float2 xv = gn_load_x<IN16>(x0, C0, x1, C1, pix, 2 * v, fp16);
-          const float2 dv = ld2_16(dy + pix * C + 2 * v, fp16);
-          const float xh0 = (xv.x - ch[k].mean[0]) * ch[k].rstd[0], xh1 = (xv.y - ch[k].mean[1]) * ch[k].rstd[1];
-          const float g0 = dv.x * act_grad(fmaf(xh0, ch[k].ga[0], ch[k].be[0]), act);
-          const float g1 = dv.y * act_grad(fmaf(xh1, ch[k].ga[1], ch[k].be[1]), act);
-          acc[k][0] += g0; acc[k][1] = fmaf(g0, xh0, acc[k][1]);
-          acc[k][2] += g1; acc[k][3] = fmaf(g1, xh1, acc[k][3]);
+          const float2 xa = gn_load_x<IN16>(x0, C0, x1, C1, pixa, 2 * v, fp16);
+          const float2 da = ld2_16(dy + pixa * C + 2 * v, fp16);
+          const float2 xb = gn_load_x<IN16>(x0, C0, x1, C1, pixb, 2 * v, fp16);
+          const float2 db = ld2_16(dy + pixb * C + 2 * v, fp16);
+          {
+            const float xh0 = (xa.x - ch[k].mean[0]) * ch[k].rstd[0], xh1 = (xa.y - ch[k].mean[1]) * ch[k].rstd[1];
+            const float g0 = da.x * act_grad(fmaf(xh0, ch[k].ga[0], ch[k].be[0]), act);
+            const float g1 = da.y * act_grad(fmaf(xh1, ch[k].ga[1], ch[k].be[1]), act);
+            acc[k][0] += g0; acc[k][1] = fmaf(g0, xh0, acc[k][1]);
+            acc[k][2] += g1; acc[k][3] = fmaf(g1, xh1, acc[k][3]);
+          }
+          if (two) {
+            const float xh0 = (xb.x - ch[k].mean[0]) * ch[k].rstd[0], xh1 = (xb.y - ch[k].mean[1]) * ch[k].rstd[1];
+            const float g0 = db.x * act_grad(fmaf(xh0, ch[k].ga[0], ch[k].be[0]), act);
+            const float g1 = db.y * act_grad(fmaf(xh1, ch[k].ga[1], ch[k].be[1]), act);
+            acc[k][0] += g0; acc[k][1] = fmaf(g0, xh0, acc[k][1]);
+            acc[k][2] += g1; acc[k][3] = fmaf(g1, xh1, acc[k][3]);
+          }
         }
       }
     }
@@ -140,36 +157,33 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_reduce_kernel(const void* _
   }
 }
 
-// pass 2: one CTA per (group, image): chan[b][c] = (A_c, B_c) summed over the slabs, coef[b][g] = (sum_c gamma_c A_c, sum_c gamma_c B_c) / n
+// pass 2: one CTA (4 warps) per (group, image): chan[b][c] = (A_c, B_c) summed over the slabs in a fixed order (lane-strided partial sums,
+// butterfly reduction), coef[b][g] = (sum_c gamma_c A_c, sum_c gamma_c B_c) / n.  Warp w owns the group's channels w, w + 4, ...
 __global__ void __launch_bounds__(128) gn_bwd_finalize_kernel(const float* __restrict__ partial, int slabs, int C, int HW,
                                                               const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ chan) {
   const int g = blockIdx.x, b = blockIdx.y, cpg = C / 32;
-  __shared__ float sA[128], sB[128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float sw[4][2];
   float s1 = 0.f, s2 = 0.f;
-  for (int k = 0; k < cpg; ++k) {
+  for (int k = warp; k < cpg; k += 4) {
     const int c = g * cpg + k;
     float a = 0.f, bb = 0.f;
-    for (int s = threadIdx.x; s < slabs; s += 128) {
+    for (int s = lane; s < slabs; s += 32) {
       const float2 v = *reinterpret_cast<const float2*>(partial + ((size_t(b) * slabs + s) * C + c) * 2);
       a += v.x; bb += v.y;
     }
-    __syncthreads();
-    sA[threadIdx.x] = a; sB[threadIdx.x] = bb;
-    __syncthreads();
-    for (int off = 64; off > 0; off >>= 1) {
-      if (threadIdx.x < off) { sA[threadIdx.x] += sA[threadIdx.x + off]; sB[threadIdx.x] += sB[threadIdx.x + off]; }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      const float ga = gamma ? gamma[c] : 1.0f;
-      s1 = fmaf(ga, sA[0], s1); s2 = fmaf(ga, sB[0], s2);
-      if (chan) { chan[(size_t(b) * C + c) * 2] = sA[0]; chan[(size_t(b) * C + c) * 2 + 1] = sB[0]; }
-    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); bb += __shfl_xor_sync(0xffffffffu, bb, o); }
+    const float ga = gamma ? gamma[c] : 1.0f;
+    s1 = fmaf(ga, a, s1); s2 = fmaf(ga, bb, s2);
+    if (lane == 0 && chan) { chan[(size_t(b) * C + c) * 2] = a; chan[(size_t(b) * C + c) * 2 + 1] = bb; }
   }
+  if (lane == 0) { sw[warp][0] = s1; sw[warp][1] = s2; }
+  __syncthreads();
   if (threadIdx.x == 0) {
     const float inv_n = 1.0f / (float(HW) * float(cpg));
-    coef[(size_t(b) * 32 + g) * 2] = s1 * inv_n;
-    coef[(size_t(b) * 32 + g) * 2 + 1] = s2 * inv_n;
+    coef[(size_t(b) * 32 + g) * 2] = ((sw[0][0] + sw[1][0]) + (sw[2][0] + sw[3][0])) * inv_n;
+    coef[(size_t(b) * 32 + g) * 2 + 1] = ((sw[0][1] + sw[1][1]) + (sw[2][1] + sw[3][1])) * inv_n;
   }
 }
 
@@ -425,7 +439,7 @@ const char* scale_copy_f32(const float* src, long n, float scale, float* dst, cu
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
-static inline int gn_bwd_slab_pix(int HW) { return HW >= 4096 ? 64 : 16; }
+static inline int gn_bwd_slab_pix(int HW) { return HW >= 16384 ? 64 : 16; }  // >= 256 CTAs per image batch at every UNet level
 int groupnorm_bwd_slabs(int HW) { const int sp = gn_bwd_slab_pix(HW); return (HW + sp - 1) / sp; }
 
 const char* groupnorm_bwd(const void* x0, int C0, const void* x1, int C1, int B, int HW, int in16, const float* stats, const float* gamma,
@@ -437,15 +451,17 @@ const char* groupnorm_bwd(const void* x0, int C0, const void* x1, int C1, int B,
   if ((dgamma || dbeta) && !chan) return "groupnorm_bwd: affine gradients need the per-channel scratch";
   const int sp = gn_bwd_slab_pix(HW), slabs = (HW + sp - 1) / sp;
   const dim3 grid(slabs, B);
+  const GnBwdGeo geo = gn_bwd_geo(C);
+  const int threads = geo.TX * geo.P;
   const uint16_t* dy = static_cast<const uint16_t*>(dy16);
-  if (in16) gn_bwd_reduce_kernel<true><<<grid, kGnThreads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, fp16, partial);
-  else gn_bwd_reduce_kernel<false><<<grid, kGnThreads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, fp16, partial);
+  if (in16) gn_bwd_reduce_kernel<true><<<grid, threads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, fp16, partial);
+  else gn_bwd_reduce_kernel<false><<<grid, threads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, fp16, partial);
   gn_bwd_finalize_kernel<<<dim3(32, B), 128, 0, st>>>(partial, slabs, C, HW, gamma, coef, chan);
   if (dgamma || dbeta) gn_bwd_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(chan, B, C, affine_scale, dgamma, dbeta);
   if (out16 || dx0 || dx1) {
     uint16_t* o16 = static_cast<uint16_t*>(out16);
-    if (in16) gn_bwd_apply_kernel<true><<<grid, kGnThreads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, coef, extra, o16, dx0, acc0, dx1, acc1, fp16);
-    else gn_bwd_apply_kernel<false><<<grid, kGnThreads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, coef, extra, o16, dx0, acc0, dx1, acc1, fp16);
+    if (in16) gn_bwd_apply_kernel<true><<<grid, threads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, coef, extra, o16, dx0, acc0, dx1, acc1, fp16);
+    else gn_bwd_apply_kernel<false><<<grid, threads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, coef, extra, o16, dx0, acc0, dx1, acc1, fp16);
   }
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_bwd launch failed";
 }

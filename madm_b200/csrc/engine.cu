@@ -1231,7 +1231,7 @@ struct Model {
         });
       };
       ln_bwd(tb + ".norm3", hs2.p);
-      F32T ascr = b.f32(attention_bwd_scratch_floats(Bn, heads, n_tok));
+      F32T ascr = b.f32(attention_bwd_scratch_floats(Bn, heads, d_head, n_tok, n_tok > 77 ? n_tok : 77) + attention_bwd_scratch_floats(Bn, heads, d_head, n_tok, 77));
       // --- cross attention
       B16T datt = b.b16(size_t(M) * C);
       { GemmDesc d; d.seg[0] = Builder::seg_plain(dh16.p, M, C); d.M = Mi; d.N = C; d.Nw = C; d.w = b.dpw(w_o2); d.out_bf16 = datt.p; d.ldo16 = C; b.gemm(d); }
@@ -1965,7 +1965,7 @@ struct Model {
       } else b.emit([=](cudaStream_t st) -> const char* {
         float* dst = io->a.out[i];
         if (!dst) return "madm_extract: output pointer is null";
-        return gn_add_relu_nchw(c3p, st3, g3, b3, scp, sts, gs, bs, 1e-5f, Bn, HW, Cout, dst, st);
+        return gn_add_relu_nchw(c3p, st3, g3, b3, scp, sts, gs, bs, 1e-5f, Bn, HW, Cout, dst, st, (io->a.flags & MADM_FLAG_OUT_FP16) ? 1 : 0);
       }, false, MADM_KIND_GROUPNORM, 0.0, pel * 12);
       b.free(c3);
       if (shortcut && !rgb3) b.free(sc);
@@ -2480,6 +2480,8 @@ int madm_extract(madm_ctx* ctx, const madm_extract_args* a, madm_stream stream) 
   if (rc != MADM_OK) return rc;
   if (a->flags & MADM_FLAG_TRAIN) return extract_train(ctx, a, static_cast<cudaStream_t>(stream));
   if (a->head_h < 0 || a->head_w < 0 || ((a->head_h > 0) != (a->head_w > 0))) return set_err(ctx, MADM_EINVAL, "madm_extract: bad head_h / head_w");
+  if ((a->flags & MADM_FLAG_OUT_FP16) && (ctx->variant != MADM_VARIANT_BASE || (a->stages & MADM_STAGE_HEAD)))
+    return set_err(ctx, MADM_EINVAL, "madm_extract: MADM_FLAG_OUT_FP16 is for the base variant's feature maps (not with MADM_STAGE_HEAD in the same call)");
   const size_t need = madm_workspace_bytes_head(ctx, a->B, a->head_h, a->head_w);
   if (need == 0) return MADM_EINVAL;
   if (a->workspace_bytes < need) return set_err(ctx, MADM_ENOMEM, "madm_extract: workspace too small");

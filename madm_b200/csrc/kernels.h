@@ -30,9 +30,10 @@ const char* groupnorm_apply(const void* x0, int C0, const void* x1, int C1, int 
 const char* layernorm(const void* x, int in16 /* x is 16-bit (operand dtype) instead of fp32 */, int M, int C, const float* gamma, const float* beta,
                       float eps, void* y_bf16, int fp16, cudaStream_t st);
 const char* softmax_rows(const float* s, int R, int L, void* p_bf16, int fp16, cudaStream_t st);
+// out_fp16 != 0: out_nchw is an fp16 [B,C,HW] tensor (MADM_FLAG_OUT_FP16: halves the feature dict's bytes for host-bound consumers)
 const char* gn_add_relu_nchw(const float* a, const float* stats_a, const float* ga, const float* ba, const float* s,
                              const float* stats_s, const float* gs, const float* bs, float eps, int B, int HW, int C,
-                             float* out_nchw, cudaStream_t st);
+                             float* out_nchw, cudaStream_t st, int out_fp16 = 0);
 
 // 3-channel input of the s0 projection: image moments -> analytic GroupNorm statistics of its K = 3 1x1 convs
 int image_moments_floats(int B);
@@ -170,8 +171,8 @@ const char* relu_bwd_nchw_to_nhwc16(const float* dout, const float* out, int B, 
 const char* scale_copy_f32(const float* src, long n, float scale, float* dst, cudaStream_t st);
 const char* temb_silu_bwd(const float* d_act, const float* emb, const float* cond_emb, long n, float scale, float* d_cond_emb, cudaStream_t st);
 
-// ---- attention_bwd.cu: gradients of softmax(Q K^T scale) V per (image, head); scratch = attention_bwd_scratch_floats(B, heads, Nq) floats
-size_t attention_bwd_scratch_floats(int B, int heads, int Nq);
+// ---- attention_bwd.cu: gradients of softmax(Q K^T scale) V per (image, head); scratch = attention_bwd_scratch_floats(B, heads, d, Nq, Nk) floats
+size_t attention_bwd_scratch_floats(int B, int heads, int d, int Nq, int Nk);
 const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, int ldo, const void* dout, int lddo,
                           void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B, int heads, int d, int Nq, int Nk, long q_bs, long k_bs,
                           long v_bs, long o_bs, long do_bs, long dq_bs, long dk_bs, long dv_bs, float scale, float* scratch, int fp16, cudaStream_t st);

@@ -493,7 +493,7 @@ __global__ void gn_add_relu_nchw_kernel(const float* __restrict__ a, const float
                                         const float* __restrict__ ga, const float* __restrict__ ba,
                                         const float* __restrict__ s, const float* __restrict__ stats_s,
                                         const float* __restrict__ gs, const float* __restrict__ bs, float eps, int HW, int C,
-                                        float* __restrict__ out) {
+                                        float* __restrict__ out, int out_fp16) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 32;
@@ -532,16 +532,20 @@ __global__ void gn_add_relu_nchw_kernel(const float* __restrict__ a, const float
   __syncthreads();
   for (int r = ty; r < 32; r += 8) {  // r = channel within tile, tx = pixel
     const int p = p0 + tx;
-    if (p < HW) out[(size_t(b) * C + c0 + r) * HW + p] = tile[tx][r];
+    if (p < HW) {
+      const size_t o = (size_t(b) * C + c0 + r) * HW + p;
+      if (out_fp16) reinterpret_cast<__half*>(out)[o] = __float2half_rn(tile[tx][r]);
+      else out[o] = tile[tx][r];
+    }
   }
 }
 
 const char* gn_add_relu_nchw(const float* a, const float* stats_a, const float* ga, const float* ba, const float* s,
                              const float* stats_s, const float* gs, const float* bs, float eps, int B, int HW, int C,
-                             float* out, cudaStream_t st) {
+                             float* out, cudaStream_t st, int out_fp16) {
   if (C % 32 != 0) return "gn_add_relu_nchw: C must be a multiple of 32";
   dim3 grid((HW + 31) / 32, C / 32, B);
-  gn_add_relu_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(a, stats_a, ga, ba, s, stats_s, gs, bs, eps, HW, C, out);
+  gn_add_relu_nchw_kernel<<<grid, dim3(32, 8), 0, st>>>(a, stats_a, ga, ba, s, stats_s, gs, bs, eps, HW, C, out, out_fp16);
   return cudaGetLastError() == cudaSuccess ? nullptr : "gn_add_relu_nchw launch failed";
 }
 

@@ -157,18 +157,19 @@ class Engine:
         self._range_poll(wait=True)
 
     def extract_graphed(self, img, cond_inputs, cond_emb, timesteps, shared_noise, *, ema=False, stages=STAGE_ALL, want_taps=False,
-                        want_latents=False, want_final=False):
+                        want_latents=False, want_final=False, out_dtype=torch.float32):
         """`extract` through a captured CUDA graph (static input / output buffers, one graph per call signature)."""
         B = img.shape[0]
         self._range_poll()
-        key = (B, bool(ema), stages, bool(want_taps), bool(want_latents), bool(want_final), self._packed.data_ptr(), shared_noise.data_ptr())
+        key = (B, bool(ema), stages, bool(want_taps), bool(want_latents), bool(want_final), self._packed.data_ptr(), shared_noise.data_ptr(),
+               out_dtype)
         g = self._graphs.get(key)
         if g is None:
             st = dict(img=torch.empty_like(img, dtype=torch.float32), cond_inputs=torch.empty(B, 77, 768, device=self.device),
                       cond_emb=torch.empty(B, 1280, device=self.device), timesteps=torch.zeros(B, dtype=torch.int64, device=self.device))
             for k, v in (("img", img), ("cond_inputs", cond_inputs), ("cond_emb", cond_emb), ("timesteps", timesteps)):
                 st[k].copy_(v)
-            kw = dict(ema=ema, stages=stages, want_taps=want_taps, want_latents=want_latents, want_final=want_final)
+            kw = dict(ema=ema, stages=stages, want_taps=want_taps, want_latents=want_latents, want_final=want_final, out_dtype=out_dtype)
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):  # warm-up outside capture: plan build, cudaFuncSetAttribute, allocations
@@ -231,7 +232,8 @@ class Engine:
     def extract(self, img: Optional[torch.Tensor], cond_inputs: torch.Tensor, cond_emb: torch.Tensor, timesteps: torch.Tensor,
                 shared_noise: torch.Tensor, *, ema: bool = False, stages: int = STAGE_ALL, want_taps: bool = False,
                 want_latents: bool = False, noisy_latents_in: Optional[torch.Tensor] = None, B: Optional[int] = None,
-                out: Optional[Sequence[torch.Tensor]] = None, want_final: bool = False, img_normalised: bool = False) -> Dict[str, object]:
+                out: Optional[Sequence[torch.Tensor]] = None, want_final: bool = False, img_normalised: bool = False,
+                out_dtype=torch.float32) -> Dict[str, object]:
         if self._packed is None:
             raise _lib.MadmError("Engine.extract called before ensure_packed()")
         B = B if B is not None else (img.shape[0] if img is not None else noisy_latents_in.shape[0])
@@ -259,7 +261,9 @@ class Engine:
         ws = self.workspace(B)
         a = MadmExtractArgs()
         a.B, a.stages, a.ema = B, stages, 1 if ema else 0
-        a.flags = _lib.FLAG_IMG_NORMALISED if img_normalised else 0
+        if out_dtype not in (torch.float32, torch.float16) or (out_dtype == torch.float16 and self.variant != "base"):
+            raise _lib.MadmError("out_dtype must be torch.float32, or torch.float16 with the base variant")
+        a.flags = (_lib.FLAG_IMG_NORMALISED if img_normalised else 0) | (_lib.FLAG_OUT_FP16 if out_dtype == torch.float16 else 0)
         a.img = img.data_ptr() if img is not None else None
         a.cond_inputs, a.cond_emb, a.timesteps = cond_inputs.data_ptr(), cond_emb.data_ptr(), timesteps.data_ptr()
         a.shared_noise = shared_noise.data_ptr() if shared_noise is not None else None
@@ -268,9 +272,9 @@ class Engine:
         outs = []
         if stages & STAGE_PROJ:
             for i, (ch, side) in enumerate(OUT_SHAPES[self.variant]):
-                t = out[i] if out is not None else torch.empty(B, ch, side, side, dtype=torch.float32, device=dev)
-                if tuple(t.shape) != (B, ch, side, side) or t.dtype != torch.float32 or not t.is_contiguous():
-                    raise _lib.MadmError(f"out[{i}] must be a contiguous fp32 [{B},{ch},{side},{side}] tensor")
+                t = out[i] if out is not None else torch.empty(B, ch, side, side, dtype=out_dtype, device=dev)
+                if tuple(t.shape) != (B, ch, side, side) or t.dtype != out_dtype or not t.is_contiguous():
+                    raise _lib.MadmError(f"out[{i}] must be a contiguous {out_dtype} [{B},{ch},{side},{side}] tensor")
                 outs.append(t)
                 a.out[i] = t.data_ptr()
             res["features"] = outs

@@ -180,7 +180,7 @@ class LdmDiffusers(nn.Module):
         return torch.randint(low=int(lo), high=int(hi), size=(bsz,), device=self.device).long()
 
     def run(self, batched_inputs, input_modal, *, stages, ema_projections=False, extra=(), want_taps=False, want_latents=False,
-            timesteps: Optional[torch.Tensor] = None, out=None, **kwargs):
+            timesteps: Optional[torch.Tensor] = None, out=None, out_dtype=torch.float32, **kwargs):
         use_ema_unet = bool(kwargs.get("ema_forward")) and hasattr(self, "ema_unet")  # ldm_diffusers.py:182-185
         if torch.is_grad_enabled() and any(p.requires_grad for p in (self.ema_unet if use_ema_unet else self.unet).parameters()):
             raise NotImplementedError(
@@ -211,9 +211,10 @@ class LdmDiffusers(nn.Module):
             stages |= _lib.STAGE_DEC
         if out is None and 0 < bsz <= eng.graph_max_batch and stages == eng.stage_all and tuple(images.shape[1:]) == (3, 512, 512):
             return eng.extract_graphed(images.float(), cond_inputs, cond_emb, timesteps, self.shared_noise, ema=ema_projections,
-                                       stages=stages, want_taps=want_taps, want_latents=want_latents, want_final=want_final)
+                                       stages=stages, want_taps=want_taps, want_latents=want_latents, want_final=want_final,
+                                       out_dtype=out_dtype)
         return eng.extract(images, cond_inputs, cond_emb, timesteps, self.shared_noise, ema=ema_projections, stages=stages,
-                           want_taps=want_taps, want_latents=want_latents, out=out, want_final=want_final)
+                           want_taps=want_taps, want_latents=want_latents, out=out, want_final=want_final, out_dtype=out_dtype)
 
     def forward(self, batched_inputs, input_modal, **kwargs):
         """Reference semantics: returns ``[enc_tap, unet_tap16, unet_tap32, unet_tap64]`` as NCHW fp32 tensors

@@ -324,7 +324,7 @@ def geglu_bwd(raw, dout):
 def attention_bwd(q, ldq, k, ldk, v, ldv, o, ldo, dout, lddo, dq, lddq, dk, lddk, dv, lddv, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, do_bs, dq_bs,
                   dkv_bs, scale):
     lib = _lib.load()
-    scratch = torch.empty(2 * B * heads * Nq, dtype=torch.float32, device=o.device)
+    scratch = torch.empty(lib.madm_op_attention_bwd_scratch_floats(B, heads, d, Nq, Nk), dtype=torch.float32, device=o.device)
     _lib.check(lib.madm_op_attention_bwd(_ptr(q), ldq, _ptr(k), ldk, _ptr(v), ldv, _ptr(o), ldo, _ptr(dout), lddo, _ptr(dq), lddq, _ptr(dk), lddk,
                                          _ptr(dv), lddv, B, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, do_bs, dq_bs, dkv_bs, float(scale), _ptr(scratch),
                                          _dt(o.dtype), _stream()), None, "madm_op_attention_bwd")

@@ -532,3 +532,25 @@ def test_call_under_grad_raises_or_trains(pair, cuda_device):
     with torch.no_grad():
         out = pb(img, input_modal="others")["output_features"]
     assert all(not v.requires_grad for v in out.values())
+
+
+def test_fp16_feature_outputs(pair, cuda_device):
+    """Opt-in extension `feature_dtype=torch.float16` (MADM_FLAG_OUT_FP16): the feature maps come back as fp16, equal to the fp32 maps
+    rounded once; sliding-window merging still accumulates in fp32."""
+    from oracle import synthetic
+    _, pb = pair
+    set_lora_adapter(pb.feature_extractor.ldm_extractor.unet, "Depth")
+    img = synthetic.synthetic_images(2, seed=13).to(cuda_device)
+    with torch.no_grad():
+        ref = pb(img, input_modal="others")["output_features"]
+        pb.feature_dtype = torch.float16
+        try:
+            out = pb(img, input_modal="others")["output_features"]
+            wide = synthetic.synthetic_images(1, h=512, w=1024, seed=31).to(cuda_device)
+            merged16 = pb.slide_forward(wide, "others")["output_features"]
+        finally:
+            pb.feature_dtype = torch.float32
+        merged32 = pb.slide_forward(wide, "others")["output_features"]
+    for k in ref:
+        assert out[k].dtype == torch.float16 and torch.equal(out[k], ref[k].half()), k
+        assert merged16[k].dtype == torch.float32 and max_rel(merged16[k], merged32[k]) < 1e-3, k
