@@ -128,16 +128,22 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
         device = feature_extractor.ldm_extractor.device
         self.feature_projections = nn.ModuleList(
             [make_projection(fd, projection_dim[i], bottleneck_channels, num_res_blocks, device) for i, fd in enumerate(self.feature_dims)])
+        self.register_load_state_dict_post_hook(lambda module, incompatible: object.__setattr__(module, "_proj_cache", None))
         self._out_feature_strides = {s: 2 ** int(s[1]) for s in out_features}  # :361-364
         self._out_feature_channels = {s: projection_dim[i] for i, s in enumerate(out_features)}
         self._out_features = list(self._out_feature_strides.keys())
 
     # ------------------------------------------------------------------ engine plumbing
     def _projection_tensors(self) -> List[Tuple[str, torch.Tensor]]:
-        out = [("feature_projections." + n, p.detach()) for n, p in self.feature_projections.named_parameters()]
         ema = getattr(self, "ema_feature_projections", None)  # set by CMDISE._inti_ema_weights (cmdise.py:308)
+        key = (id(self.feature_projections), id(ema))
+        hit = getattr(self, "_proj_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        out = [("feature_projections." + n, p) for n, p in self.feature_projections.named_parameters()]
         if ema is not None:
-            out += [("ema_feature_projections." + n, p.detach()) for n, p in ema.named_parameters()]
+            out += [("ema_feature_projections." + n, p) for n, p in ema.named_parameters()]
+        object.__setattr__(self, "_proj_cache", (key, out))
         return out
 
     def _grad_inputs(self, input_modal, ema_forward) -> List[Tuple[str, torch.Tensor]]:
@@ -146,19 +152,21 @@ class AttentionFeatureExtractorBackbone(FeatureExtractorBackbone):
             return []
         gen: BasePromptTimeGenerator = self.feature_extractor
         ldm: LdmDiffusers = gen.ldm_extractor
-        unet = ldm.ema_unet if (ema_forward and hasattr(ldm, "ema_unet")) else ldm.unet
-        proj = self.ema_feature_projections if ema_forward else self.feature_projections
-        mods = [("feature_extractor.ldm_extractor.unet.", unet), ("feature_projections.", proj)]
+        use_ema_unet = bool(ema_forward and hasattr(ldm, "ema_unet"))
+        # the big lists (UNet, projections) come from the caches the engine binding uses; names already carry their prefixes
+        cands = [(n, p) for n, p in ldm.named_engine_tensors(use_ema_unet) if ".unet." in n]
+        cands += [(("feature_projections." + n[len("ema_feature_projections."):]) if n.startswith("ema_") else n, p)
+                  for n, p in self._projection_tensors() if n.startswith("ema_feature_projections.") == bool(ema_forward)]
         if input_modal in ("rgb", "mixed"):
-            mods.append(("feature_extractor.clip_project_rgb.", gen.clip_project_rgb))
+            cands += [("feature_extractor.clip_project_rgb." + n, p) for n, p in gen.clip_project_rgb.named_parameters()]
         if input_modal != "rgb":
-            mods.append(("feature_extractor.clip_project_others.", gen.ema_clip_project_others if ema_forward else gen.clip_project_others))
+            others = gen.ema_clip_project_others if ema_forward else gen.clip_project_others
+            cands += [("feature_extractor.clip_project_others." + n, p) for n, p in others.named_parameters()]
         seen, out = set(), []
-        for pre, m in mods:
-            for n, p in m.named_parameters():
-                if p.requires_grad and id(p) not in seen:
-                    seen.add(id(p))
-                    out.append((pre + n, p))
+        for n, p in cands:
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                out.append((n, p))
         return out
 
     def _extract(self, img, input_modal, ema_forward, timestep, want_taps=False, timesteps=None, **kwargs):

@@ -63,6 +63,30 @@ __device__ __forceinline__ void load_tile(T* dst, const uint16_t* src, int ld, i
   }
 }
 
+// the same through cp.async (16-byte copies, zero fill where load_tile writes zeros): the tile of the NEXT loop iteration is in flight
+// while the current one is consumed
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const unsigned s = unsigned(__cvta_generic_to_shared(smem));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, bool valid) {
+  const unsigned s = unsigned(__cvta_generic_to_shared(smem));
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <typename T, int DP>
+__device__ __forceinline__ void load_tile_async(T* dst, const uint16_t* src, int ld, int row0, int nrows, int d) {
+  constexpr int LD = DP + 8;
+  for (int i = threadIdx.x; i < AB * (DP / 8); i += AB_THREADS) {
+    const int r = i / (DP / 8), c8 = (i % (DP / 8)) * 8;
+    const bool ok = row0 + r < nrows && c8 < d;
+    cp_async16(dst + r * LD + c8, ok ? src + size_t(row0 + r) * ld + c8 : src, ok);
+  }
+}
+
 // S = A B^T for two 64 x DP tiles: warp w computes the 16-row band w/2 and two 16-column tiles; results -> out[64][SLD] (fp32)
 template <typename T, int DP>
 __device__ __forceinline__ void tile_abt(const T* A, const T* Bm, float* out) {
@@ -176,8 +200,8 @@ __device__ __forceinline__ void softmax_grad_tile(const float* Sf, const float* 
 template <int DP> struct AttnSmem {
   static constexpr int LD = DP + 8;
   static constexpr size_t TILE = size_t(AB) * LD * 2;                                  // one 16-bit 64 x DP tile
-  static constexpr size_t DKV = 4 * TILE + 2 * AB * SLD * 4 + 2 * AB * PLD * 2 + 2 * AB * 4;
-  static constexpr size_t DQ = 4 * TILE + 2 * AB * SLD * 4 + 1 * AB * PLD * 2 + 2 * AB * 4;
+  static constexpr size_t DKV = 6 * TILE + 2 * AB * SLD * 4 + 2 * AB * PLD * 2 + 4 * AB * 4;  // K, V, 2 x (Q, dO), S, dP, P, dS, 2 x (L, D)
+  static constexpr size_t DQ = 6 * TILE + 2 * AB * SLD * 4 + 1 * AB * PLD * 2 + 2 * AB * 4;   // Q, dO, 2 x (K, V), S, dP, dS, L, D
   static constexpr size_t PREP = 2 * TILE + AB * SLD * 4;
   static_assert(2 * TILE >= size_t(AB) * (DP + 4) * 4, "fp32 output staging must fit in two operand tiles");
 };
@@ -189,14 +213,14 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const AttnBwdP
   constexpr int LD = DP + 8, NT = DP / 16, NTH = (NT + 1) / 2, FLD = DP + 4;
   T* Ks = reinterpret_cast<T*>(smem_raw);
   T* Vs = Ks + AB * LD;
-  T* Qs = Vs + AB * LD;
-  T* dOs = Qs + AB * LD;
-  float* Sf = reinterpret_cast<float*>(dOs + AB * LD);
+  T* Qb = Vs + AB * LD;            // [2][64][LD]
+  T* dOb = Qb + 2 * AB * LD;       // [2][64][LD]
+  float* Sf = reinterpret_cast<float*>(dOb + 2 * AB * LD);
   float* dPf = Sf + AB * SLD;
   T* Ps = reinterpret_cast<T*>(dPf + AB * SLD);
   T* dSs = Ps + AB * PLD;
-  float* Ls = reinterpret_cast<float*>(dSs + AB * PLD);
-  float* Ds = Ls + AB;
+  float* Lb = reinterpret_cast<float*>(dSs + AB * PLD);  // [2][64]
+  float* Db = Lb + 2 * AB;                                // [2][64]
   const int jb = blockIdx.x / p.qsplit, qs = blockIdx.x % p.qsplit, h = blockIdx.y, b = blockIdx.z;
   const int j0 = jb * AB;
   const int warp = threadIdx.x >> 5, r = warp >> 1, tc = warp & 1;
@@ -213,16 +237,26 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const AttnBwdP
   for (int i = 0; i < NTH; ++i) { wmma::fill_fragment(accK[i], 0.0f); wmma::fill_fragment(accV[i], 0.0f); }
   const int qblocks = (p.Nq + AB - 1) / AB, per = (qblocks + p.qsplit - 1) / p.qsplit;
   const int i_begin = qs * per * AB, i_end = min(p.Nq, (qs + 1) * per * AB);
-  for (int i0 = i_begin; i0 < i_end; i0 += AB) {
-    __syncthreads();  // the previous iteration's readers of Qs / dOs / Ps / dSs are done
-    load_tile<T, DP>(Qs, q, p.ldq, i0, p.Nq, p.d);
-    load_tile<T, DP>(dOs, dout, p.lddo, i0, p.Nq, p.d);
+  auto prefetch = [&](int i0, int buf) {  // Q / dO tiles and L / D of the query block starting at i0 -> buffer `buf`
+    load_tile_async<T, DP>(Qb + buf * AB * LD, q, p.ldq, i0, p.Nq, p.d);
+    load_tile_async<T, DP>(dOb + buf * AB * LD, dout, p.lddo, i0, p.Nq, p.d);
     if (threadIdx.x < AB) {
       const bool ok = i0 + threadIdx.x < p.Nq;
-      Ls[threadIdx.x] = ok ? Lg[i0 + threadIdx.x] : 0.f;
-      Ds[threadIdx.x] = ok ? Dg[i0 + threadIdx.x] : 0.f;
+      cp_async4(Lb + buf * AB + threadIdx.x, ok ? Lg + i0 + threadIdx.x : Lg, ok);
+      cp_async4(Db + buf * AB + threadIdx.x, ok ? Dg + i0 + threadIdx.x : Dg, ok);
     }
-    __syncthreads();
+    cp_async_commit();
+  };
+  int buf = 0;
+  if (i_begin < i_end) prefetch(i_begin, 0);
+  for (int i0 = i_begin; i0 < i_end; i0 += AB, buf ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();  // this block's tiles have landed; every reader of the other buffer / of P, dS (previous iteration) is done
+    if (i0 + AB < i_end) prefetch(i0 + AB, buf ^ 1);
+    const T* Qs = Qb + buf * AB * LD;
+    const T* dOs = dOb + buf * AB * LD;
+    const float* Ls = Lb + buf * AB;
+    const float* Ds = Db + buf * AB;
     tile_abt<T, DP>(Qs, Ks, Sf);     // S  = Q K^T
     tile_abt<T, DP>(dOs, Vs, dPf);   // dP = dO V^T
     __syncthreads();
@@ -281,9 +315,9 @@ template <typename T, int DP>
 __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dq_kernel(const AttnBwdParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int LD = DP + 8, NT = DP / 16, NTH = (NT + 1) / 2, FLD = DP + 4;
-  T* Ks = reinterpret_cast<T*>(smem_raw);
-  T* Vs = Ks + AB * LD;
-  T* Qs = Vs + AB * LD;
+  T* Kb = reinterpret_cast<T*>(smem_raw);  // [2][64][LD]
+  T* Vb = Kb + 2 * AB * LD;                 // [2][64][LD]
+  T* Qs = Vb + 2 * AB * LD;
   T* dOs = Qs + AB * LD;
   float* Sf = reinterpret_cast<float*>(dOs + AB * LD);
   float* dPf = Sf + AB * SLD;
@@ -308,11 +342,20 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dq_kernel(const AttnBwdPa
   wmma::fragment<wmma::accumulator, 16, 16, 16, float> accQ[NTH];
 #pragma unroll
   for (int i = 0; i < NTH; ++i) wmma::fill_fragment(accQ[i], 0.0f);
-  for (int j0 = 0; j0 < p.Nk; j0 += AB) {
-    __syncthreads();
-    load_tile<T, DP>(Ks, k, p.ldk, j0, p.Nk, p.d);
-    load_tile<T, DP>(Vs, v, p.ldv, j0, p.Nk, p.d);
-    __syncthreads();
+  auto prefetch = [&](int j0, int buf) {
+    load_tile_async<T, DP>(Kb + buf * AB * LD, k, p.ldk, j0, p.Nk, p.d);
+    load_tile_async<T, DP>(Vb + buf * AB * LD, v, p.ldv, j0, p.Nk, p.d);
+    cp_async_commit();
+  };
+  int buf = 0;
+  prefetch(0, 0);
+  const T* Ks = Kb;
+  for (int j0 = 0; j0 < p.Nk; j0 += AB, buf ^= 1) {
+    cp_async_wait_all();
+    __syncthreads();  // K / V of this block landed (and Q, dO, L, D on the first pass); the other buffer's readers are done
+    if (j0 + AB < p.Nk) prefetch(j0 + AB, buf ^ 1);
+    Ks = Kb + buf * AB * LD;
+    const T* Vs = Vb + buf * AB * LD;
     tile_abt<T, DP>(Qs, Ks, Sf);
     tile_abt<T, DP>(dOs, Vs, dPf);
     __syncthreads();

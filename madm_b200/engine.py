@@ -36,6 +36,8 @@ class Engine:
         _lib.check(self.lib.madm_set_variant(self.ctx, _lib.VARIANT_S0 if variant == "s0" else _lib.VARIANT_BASE), self.ctx, "madm_set_variant")
         self.stage_all = STAGE_ALL_S0 if variant == "s0" else STAGE_ALL
         self._named: List[Tuple[str, torch.Tensor]] = []
+        self._named_src = None  # the caller's list object behind the last bind (fast path: compare data pointers only)
+        self._ptrs = None
         self._sig = None
         self._versions = None
         self._packed: Optional[torch.Tensor] = None
@@ -65,9 +67,15 @@ class Engine:
     # ------------------------------------------------------------------ parameters
     def bind(self, named: Sequence[Tuple[str, torch.Tensor]]):
         """(Re)register fp32 CUDA parameter tensors under their reference state_dict names."""
+        if named is self._named_src:  # the caller's cached list: only the storage pointers can have moved
+            ptrs = tuple(t.data_ptr() for _, t in named)
+            if ptrs == self._ptrs:
+                return False
+        src = named
         named = [(n, t) for n, t in named]
         sig = tuple((n, t.data_ptr(), tuple(t.shape)) for n, t in named)
         if sig == self._sig:
+            self._named_src, self._ptrs = src, tuple(p for _, p, _ in sig)
             return False
         for n, t in named:
             if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
@@ -83,6 +91,7 @@ class Engine:
         _lib.check(self.lib.madm_set_tensors(self.ctx, arr, len(named)), self.ctx, "madm_set_tensors")
         self._graphs.clear()  # captured graphs hold the old parameter pointers (biases / norm affines are read in place)
         self._named, self._sig = named, sig
+        self._named_src, self._ptrs = src, tuple(p for _, p, _ in sig)
         self._versions = None  # force a full repack
         return True
 

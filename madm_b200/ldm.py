@@ -116,6 +116,9 @@ class LdmDiffusers(nn.Module):
         self.register_buffer("uncond_inputs", uncond_inputs.detach().to(device))
         self.compute_dtype = compute_dtype  # 'fp16' (reference AMP dtype, default) or 'bf16'; see DESIGN.md Numerics
         self._engine: Optional[Engine] = None
+        self._named_cache: Dict = {}
+        self._bind_cache = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate_parameter_cache())
         self._ema_engine: Optional[Engine] = None  # second context for `ema_unet` (CMDISE ema_w_unet, cmdise.py:318-321)
         self._last_ema_unet = False
         self._bound_extra: List[Tuple[str, torch.Tensor]] = []
@@ -155,19 +158,36 @@ class LdmDiffusers(nn.Module):
         return self._engine
 
     def named_engine_tensors(self, ema_unet: bool = False) -> List[Tuple[str, torch.Tensor]]:
-        pre = "feature_extractor.ldm_extractor."
+        """(state_dict key, Parameter) of every UNet / VAE parameter.  Walking the ~1500-parameter module tree costs milliseconds, so the
+        list is cached per (UNet object, its structure version); the Parameters themselves are stored, so moved storage (`.to()`,
+        `load_state_dict`) is seen by the engine's data_ptr check.  `invalidate_parameter_cache()` drops it (done automatically after
+        `load_state_dict`, which may replace Parameter objects with assign=True)."""
         unet = self.ema_unet if ema_unet else self.unet  # the EMA teacher's UNet is bound under the same names in its own context
-        out = [(pre + "unet." + n, p.detach()) for n, p in unet.named_parameters()]
-        out += [(pre + "vae." + n, p.detach()) for n, p in self.vae.named_parameters()]
+        key = (bool(ema_unet), id(unet), getattr(unet, "_struct_version", 0))
+        hit = self._named_cache.get(bool(ema_unet))
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        pre = "feature_extractor.ldm_extractor."
+        out = [(pre + "unet." + n, p) for n, p in unet.named_parameters()]
+        out += [(pre + "vae." + n, p) for n, p in self.vae.named_parameters()]
+        self._named_cache[bool(ema_unet)] = (key, out)
         return out
+
+    def invalidate_parameter_cache(self):
+        self._named_cache.clear()
+        self._bind_cache = None
 
     def prepare(self, extra: Sequence[Tuple[str, torch.Tensor]] = (), ema_unet: bool = False):
         """Bind parameter pointers and (re)pack weights if anything changed (version counters, adapter switch)."""
         eng = self.engine(ema_unet)
-        extra = list(extra)
         if extra:  # remembered, so callers without the projection tensors (forward(), vae_encoder()) do not force a re-bind / repack
-            self._bound_extra = extra
-        eng.bind(self.named_engine_tensors(ema_unet) + self._bound_extra)
+            self._bound_extra = extra if isinstance(extra, list) else list(extra)
+        base = self.named_engine_tensors(ema_unet)
+        bc = self._bind_cache
+        if bc is None or bc[0] is not base or bc[1] is not self._bound_extra:  # the concatenation is cached with its parts
+            bc = (base, self._bound_extra, base + list(self._bound_extra))
+            self._bind_cache = bc
+        eng.bind(bc[2])
         unet = self.ema_unet if ema_unet else self.unet
         adapter = unet.active_adapter()
         eng.ensure_packed(adapter, unet.scaling_of(adapter) if adapter else 0.0)

@@ -263,6 +263,7 @@ class UNetParams(ParamNode):
         for k, m in tree._modules.items():
             self.add_module(k, m)
         self.adapter_names: List[str] = []
+        self._struct_version = 0  # bumped whenever the parameter SET changes (add_adapter): name / tensor lists are cached per version
 
     def lora_layers(self) -> Iterable[Tuple[str, LoraLinearParams]]:
         for n, m in self.named_modules():
@@ -287,6 +288,7 @@ class UNetParams(ParamNode):
             cur.update_layer(adapter_name, r, alpha, init if isinstance(init, str) else "kaiming")
         if adapter_name not in self.adapter_names:
             self.adapter_names.append(adapter_name)
+        object.__setattr__(self, "_struct_version", getattr(self, "_struct_version", 0) + 1)
         self.set_adapter(adapter_name)
 
     def set_adapter(self, adapter_name):

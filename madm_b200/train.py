@@ -46,13 +46,17 @@ class TrainContext:
         self.backbone = backbone
         self.slots: List[_Slot] = []
         self.grad_sig = None
+        self.grad_src = None
         self.grad_flat: Optional[torch.Tensor] = None
         self.grad_views: Dict[str, torch.Tensor] = {}
 
     # ------------------------------------------------------------------ gradient buffers (one flat fp32 buffer, views per parameter)
     def ensure_grads(self, eng, named: Sequence[Tuple[str, torch.Tensor]]):
+        if named is self.grad_src:  # the cached list object: nothing can have changed
+            return
         sig = tuple((n, tuple(t.shape)) for n, t in named)
         if sig == self.grad_sig:
+            self.grad_src = named
             return
         total = sum(t.numel() for _, t in named)
         self.grad_flat = torch.zeros(total, dtype=torch.float32, device=eng.device)
@@ -68,7 +72,7 @@ class TrainContext:
             for k, s in enumerate(t.shape):
                 arr[i].shape[k] = s
         _lib.check(eng.lib.madm_set_grad_tensors(eng.ctx, arr, len(named)), eng.ctx, "madm_set_grad_tensors")
-        self.grad_sig = sig
+        self.grad_sig, self.grad_src = sig, named
         for s in self.slots:  # plans were dropped; sizes may have changed
             s.ws = None
 
@@ -226,8 +230,7 @@ def extract_with_grad(backbone, img, input_modal, ema_forward, timestep, grad_in
     eng = ldm.prepare(backbone._projection_tensors())
     tc = _context(backbone)
     # gradient buffers for EVERY engine-side trainable (all adapters' factors + projections), so one registration serves all passes
-    all_named = [(n, p) for n, p in _all_engine_trainables(backbone)]
-    tc.ensure_grads(eng, all_named)
+    tc.ensure_grads(eng, _all_engine_trainables(backbone))
     slot = tc.acquire()
     scaling = ldm.unet.scaling_of(adapter) if adapter else 0.0
     loss_scale = float(getattr(ldm, "train_loss_scale", None) or (1.0 if ldm.compute_dtype == "bf16" else 4096.0))
@@ -244,9 +247,14 @@ def extract_with_grad(backbone, img, input_modal, ema_forward, timestep, grad_in
 
 
 def _all_engine_trainables(backbone):
+    """Every parameter the engine can produce a gradient for (all adapters' factors + the projections), from the cached name lists."""
     ldm = backbone.feature_extractor.ldm_extractor
-    for n, p in ldm.unet.named_parameters():
-        if ".lora_A." in n or ".lora_B." in n:
-            yield "feature_extractor.ldm_extractor.unet." + n, p
-    for n, p in backbone.feature_projections.named_parameters():
-        yield "feature_projections." + n, p
+    base = ldm.named_engine_tensors(False)
+    proj = backbone._projection_tensors()
+    hit = getattr(backbone, "_trainables_cache", None)
+    if hit is not None and hit[0] is base and hit[1] is proj:
+        return hit[2]
+    out = [(n, p) for n, p in base if ".lora_A." in n or ".lora_B." in n]
+    out += [(n, p) for n, p in proj if n.startswith("feature_projections.")]
+    object.__setattr__(backbone, "_trainables_cache", (base, proj, out))
+    return out

@@ -13,7 +13,10 @@ KEYS = [
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
     ("lts__t_bytes.sum", "L2 bytes"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+    ("sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe (hmma) cycles active % of peak"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe cycles active % of peak"),
     ("sm__inst_executed_pipe_tensor_op_hmma.avg.pct_of_peak_sustained_active", "tensor(hmma) inst %"),
+    ("sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active", "uniform pipe (UTCHMMA issue) %"),
     ("sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "tensor hmma cycles active (avg/SM)"),
     ("sm__cycles_active.avg", "SM cycles active (avg)"),
     ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe %"),
