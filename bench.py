@@ -631,13 +631,17 @@ def run_train(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    prof = bool(os.environ.get("MADM_BENCH_CUDA_PROFILE"))  # bracket the timed steps for `ncu --profile-from-start off`
+    if prof:
+        torch.cuda.cudart().cudaProfilerStart()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step(src_dev, tgt_dev, lab_dev, timed=True)
-        torch.cuda.current_stream().synchronize() if False else None
     e1.record()
     torch.cuda.synchronize()
+    if prof:
+        torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop() if sampler else None
     for k in ev:  # (events of the LAST step: a per-phase picture, not the timed total)
         acc_ms[k] = ev[k][0].elapsed_time(ev[k][1])

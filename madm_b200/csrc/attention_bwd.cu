@@ -181,6 +181,28 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_prep_kernel(const AttnBwd
   }
 }
 
+// D only (the forward kernel supplied L): one warp-quarter per row as above, no Q K^T pass
+__global__ void __launch_bounds__(AB_THREADS) attn_bwd_d_kernel(const AttnBwdParams p, int fp16) {
+  const int ib = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int row = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const int i = ib * AB + row;
+  float dsum = 0.f;
+  if (i < p.Nq) {
+    const uint16_t* orow = p.o + size_t(b) * p.o_bs + size_t(i) * p.ldo + h * p.d;
+    const uint16_t* drow = p.dout + size_t(b) * p.do_bs + size_t(i) * p.lddo + h * p.d;
+    for (int c = part * 2; c < p.d; c += 8) {
+      const uint32_t a = *reinterpret_cast<const uint32_t*>(orow + c), g = *reinterpret_cast<const uint32_t*>(drow + c);
+      float2 fa, fg;
+      if (fp16) { fa = __half22float2(*reinterpret_cast<const __half2*>(&a)); fg = __half22float2(*reinterpret_cast<const __half2*>(&g)); }
+      else { fa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a)); fg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g)); }
+      dsum = fmaf(fa.x, fg.x, dsum); dsum = fmaf(fa.y, fg.y, dsum);
+    }
+  }
+  dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+  dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+  if (part == 0 && i < p.Nq) p.D[(size_t(b) * p.heads + h) * p.Nq + i] = dsum;
+}
+
 // shared by the two main kernels: P (optional) and dS tiles from the fp32 S / dP tiles
 template <typename T>
 __device__ __forceinline__ void softmax_grad_tile(const float* Sf, const float* dPf, const float* Ls, const float* Ds, int i0, int j0, int Nq, int Nk,
@@ -409,7 +431,7 @@ __global__ void attn_bwd_kv_reduce_kernel(const AttnBwdParams p, int B) {
 }
 
 template <typename T, int DP>
-const char* launch_all(const AttnBwdParams& p, int B, cudaStream_t st) {
+const char* launch_all(const AttnBwdParams& p, int B, cudaStream_t st, bool have_lse, int fp16) {
   static bool attr = false;
   if (!attr) {
     if (cudaFuncSetAttribute(attn_bwd_dkv_kernel<T, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(AttnSmem<DP>::DKV)) != cudaSuccess ||
@@ -419,7 +441,8 @@ const char* launch_all(const AttnBwdParams& p, int B, cudaStream_t st) {
     attr = true;
   }
   const dim3 gq((p.Nq + AB - 1) / AB, p.heads, B), gk(((p.Nk + AB - 1) / AB) * p.qsplit, p.heads, B);
-  attn_bwd_prep_kernel<T, DP><<<gq, AB_THREADS, AttnSmem<DP>::PREP, st>>>(p);
+  if (have_lse) attn_bwd_d_kernel<<<gq, AB_THREADS, 0, st>>>(p, fp16);
+  else attn_bwd_prep_kernel<T, DP><<<gq, AB_THREADS, AttnSmem<DP>::PREP, st>>>(p);
   attn_bwd_dkv_kernel<T, DP><<<gk, AB_THREADS, AttnSmem<DP>::DKV, st>>>(p);
   if (p.qsplit > 1) {
     const long total = long(B) * p.heads * p.Nk * (p.d / 2);
@@ -451,7 +474,8 @@ size_t attention_bwd_scratch_floats(int B, int heads, int d, int Nq, int Nk) {
 
 const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, int ldo, const void* dout, int lddo,
                           void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B, int heads, int d, int Nq, int Nk, long q_bs, long k_bs,
-                          long v_bs, long o_bs, long do_bs, long dq_bs, long dk_bs, long dv_bs, float scale, float* scratch, int fp16, cudaStream_t st) {
+                          long v_bs, long o_bs, long do_bs, long dq_bs, long dk_bs, long dv_bs, float scale, float* scratch, int fp16, cudaStream_t st,
+                          const float* lse) {
   if (d != 40 && d != 80 && d != 160) return "attention_bwd: head dim must be 40, 80 or 160";
   const int lds[8] = {ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv};
   for (int i = 0; i < 8; ++i) if (lds[i] % 8 != 0) return "attention_bwd: row pitches must be multiples of 8 elements";
@@ -464,7 +488,7 @@ const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const 
   p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo; p.lddo = lddo; p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.q_bs = q_bs; p.k_bs = k_bs; p.v_bs = v_bs; p.o_bs = o_bs; p.do_bs = do_bs; p.dq_bs = dq_bs; p.dk_bs = dk_bs; p.dv_bs = dv_bs;
   p.heads = heads; p.d = d; p.Nq = Nq; p.Nk = Nk; p.scale = scale;
-  p.L = scratch; p.D = scratch + size_t(B) * heads * Nq;
+  p.L = lse ? const_cast<float*>(lse) : scratch; p.D = scratch + size_t(B) * heads * Nq;
   p.qsplit = attn_qsplit(B, heads, Nq, Nk);
   p.part_k = p.part_v = nullptr;
   if (p.qsplit > 1) {
@@ -473,14 +497,15 @@ const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const 
     const size_t one = size_t(p.qsplit) * B * heads * (((Nk + AB - 1) / AB) * AB) * attn_dp(d);
     p.part_k = base; p.part_v = base + one;
   }
+  const bool hl = lse != nullptr;
   if (fp16) {
-    if (d == 40) return launch_all<__half, 48>(p, B, st);
-    if (d == 80) return launch_all<__half, 80>(p, B, st);
-    return launch_all<__half, 160>(p, B, st);
+    if (d == 40) return launch_all<__half, 48>(p, B, st, hl, fp16);
+    if (d == 80) return launch_all<__half, 80>(p, B, st, hl, fp16);
+    return launch_all<__half, 160>(p, B, st, hl, fp16);
   }
-  if (d == 40) return launch_all<__nv_bfloat16, 48>(p, B, st);
-  if (d == 80) return launch_all<__nv_bfloat16, 80>(p, B, st);
-  return launch_all<__nv_bfloat16, 160>(p, B, st);
+  if (d == 40) return launch_all<__nv_bfloat16, 48>(p, B, st, hl, fp16);
+  if (d == 80) return launch_all<__nv_bfloat16, 80>(p, B, st, hl, fp16);
+  return launch_all<__nv_bfloat16, 160>(p, B, st, hl, fp16);
 }
 
 }  // namespace madm

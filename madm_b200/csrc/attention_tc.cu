@@ -66,6 +66,7 @@ struct FaParams {
   int Nq, Nk;
   float scale_log2;
   int fp16;
+  float* lse;  // optional [B, heads, Nq]: natural-log log-sum-exp of the scaled scores of every query row (consumed by the backward pass)
 };
 
 __device__ __forceinline__ float fa_ex2(float x) {
@@ -404,7 +405,9 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
     // normalise and store this row
     const int m = q0 + g * FA_BM + row;
     if (m < p.Nq) {
-      const float inv = 1.0f / (C::ONES ? o_acc[C::ONES ? D : 0] : l_run);
+      const float den = C::ONES ? o_acc[C::ONES ? D : 0] : l_run;
+      const float inv = 1.0f / den;
+      if (p.lse) p.lse[(size_t(b) * gridDim.y + h) * p.Nq + m] = (m_run * p.scale_log2 + log2f(den)) * 0.6931471805599453f;
       uint16_t* op = p.O + size_t(b) * p.o_bs + size_t(m) * p.ldo + h * D;
 #pragma unroll
       for (int c = 0; c < D; c += 8) {
@@ -463,7 +466,7 @@ static const char* fa_map(CUtensorMap* tm, const void* ptr, int d, int heads, in
 
 const char* flash_attention_tc_prepare(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
                                        int heads, int d, int Nq, int Nk, long q_bs, long kv_bs, long o_bs, float scale, int fp16,
-                                       FaLaunch* L) {
+                                       FaLaunch* L, float* lse) {
   if (d != 40 && d != 80 && d != 160) return "attention: unsupported head dim (40, 80, 160)";
   if (ldq % 8 || ldk % 8 || ldv % 8 || ldo % 8 || q_bs % 8 || kv_bs % 8) return "attention: pitches must be multiples of 8 elements";
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15)
@@ -478,6 +481,7 @@ const char* flash_attention_tc_prepare(const void* q, int ldq, const void* k, in
   p->ldo = ldo; p->o_bs = o_bs; p->Nq = Nq; p->Nk = Nk;
   p->scale_log2 = scale * 1.4426950408889634f;
   p->fp16 = fp16;
+  p->lse = lse;
   L->d = d;
   L->nqt = (d <= 80 && Nq >= 2 * FA_BM) ? 2 : 1;  // two query tiles per CTA when there are enough rows (d=160: TMEM/regs allow one)
   L->grid = dim3((Nq + FA_BM * L->nqt - 1) / (FA_BM * L->nqt), heads, B);

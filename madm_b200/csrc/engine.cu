@@ -535,12 +535,12 @@ struct Builder {
 
   // fused attention: tcgen05/TMEM kernel (tensor maps encoded at plan time)
   void attention(const bf16* q, int ldq, const bf16* k, int ldk, const bf16* v, int ldv, bf16* o, int ldo, int Bn, int heads, int d, int Nq,
-                 int Nk, long q_bs, long kv_bs, long o_bs, float scale) {
+                 int Nk, long q_bs, long kv_bs, long o_bs, float scale, float* lse = nullptr) {
     const double flops = 4.0 * double(Bn) * Nq * Nk * heads * d;
     if (mode != PLAN) { ++(bwd ? n_bops : n_ops); return; }
     const int h16 = ctx->fp16;
     FaLaunch L;
-    if (const char* e = flash_attention_tc_prepare(q, ldq, k, ldk, v, ldv, o, ldo, Bn, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, h16, &L))
+    if (const char* e = flash_attention_tc_prepare(q, ldq, k, ldk, v, ldv, o, ldo, Bn, heads, d, Nq, Nk, q_bs, kv_bs, o_bs, scale, h16, &L, lse))
       fail(MADM_EINVAL, std::string(e));
     emit([L](cudaStream_t st) { return flash_attention_tc_launch(L, st); }, false, MADM_KIND_ATTENTION, flops, 0.0);
   }
@@ -1148,8 +1148,9 @@ struct Model {
       GemmDesc d; d.seg[0] = Builder::seg_plain(l1.p, M, C); d.M = Mi; d.N = 3 * C; d.Nw = 3 * C; d.w = b.pw(reg);
       d.out_bf16 = qkv.p; d.ldo16 = 3 * C; b.gemm(d); }
     B16T att1 = b.b16(size_t(M) * C);
+    F32T lse1 = b.f32(size_t(Bn) * heads * n_tok), lse2 = b.f32(size_t(Bn) * heads * n_tok);  // log-sum-exp rows of both attentions (for the backward)
     b.attention(qkv.p, 3 * C, qkv.p ? qkv.p + C : nullptr, 3 * C, qkv.p ? qkv.p + 2 * C : nullptr, 3 * C, att1.p, C, Bn, heads, d_head, n_tok, n_tok,
-                long(n_tok) * 3 * C, long(n_tok) * 3 * C, long(n_tok) * C, sc);
+                long(n_tok) * 3 * C, long(n_tok) * 3 * C, long(n_tok) * C, sc, lse1.p);
     { GemmDesc d; d.seg[0] = Builder::seg_plain(att1.p, M, C); d.M = Mi; d.N = C; d.Nw = C;
       d.w = b.pw(b.linear_w(tb + ".attn1.to_out.0", C, C, true)); d.bias = lora_bias(tb + ".attn1.to_out.0", C);
       d.residual = hs0.p; d.ldr = C; d.out_f32 = hs1.p; d.ldo32 = C; b.gemm(d); }
@@ -1163,7 +1164,7 @@ struct Model {
     const int kvo = kv_off[tb + ".attn2"], ldkv = kv_total;
     { const bf16* kv = kv_all.p;
       b.attention(q2.p, C, kv ? kv + kvo : nullptr, ldkv, kv ? kv + kvo + C : nullptr, ldkv, att2.p, C, Bn, heads, d_head, n_tok, 77, long(n_tok) * C,
-                  long(77) * ldkv, long(n_tok) * C, sc); }
+                  long(77) * ldkv, long(n_tok) * C, sc, lse2.p); }
     { GemmDesc d; d.seg[0] = Builder::seg_plain(att2.p, M, C); d.M = Mi; d.N = C; d.Nw = C;
       d.w = b.pw(b.linear_w(tb + ".attn2.to_out.0", C, C, true)); d.bias = lora_bias(tb + ".attn2.to_out.0", C);
       d.residual = hs1.p; d.ldr = C; d.out_f32 = hs2.p; d.ldo32 = C; b.gemm(d); }
@@ -1238,10 +1239,11 @@ struct Model {
       lora_wgrad(tb + ".attn2.to_out.0", att2.p, C, dh16.p, C, M, C, C);
       B16T dq2 = b.b16(size_t(M) * C);
       { const bf16* q = q2.p; const bf16* kv = kv_all.p; const bf16* o = att2.p; const bf16* dop = datt.p; bf16* dqp = dq2.p; bf16* dkv = dkv_all.p; float* sp = ascr.p;
+        const float* lse = lse2.p;
         b.emit([=](cudaStream_t st) {
           return attention_bwd(q, C, kv + kvo, ldkv, kv + kvo + C, ldkv, o, C, dop, C, dqp, C, dkv + kvo, ldkv, dkv + kvo + C, ldkv, Bn, heads, d_head, n_tok, 77,
                                long(n_tok) * C, long(77) * ldkv, long(77) * ldkv, long(n_tok) * C, long(n_tok) * C, long(n_tok) * C, long(77) * ldkv,
-                               long(77) * ldkv, sc, sp, h16, st); }); }
+                               long(77) * ldkv, sc, sp, h16, st, lse); }); }
       lora_wgrad(tb + ".attn2.to_q", l2.p, C, dq2.p, C, M, C, C);
       lora_wgrad(tb + ".attn2.to_k", ctx16_saved.p, 768, dkv_all.p ? dkv_all.p + kvo : nullptr, ldkv, long(Bn) * 77, C, 768);
       lora_wgrad(tb + ".attn2.to_v", ctx16_saved.p, 768, dkv_all.p ? dkv_all.p + kvo + C : nullptr, ldkv, long(Bn) * 77, C, 768);
@@ -1253,10 +1255,11 @@ struct Model {
       lora_wgrad(tb + ".attn1.to_out.0", att1.p, C, dh16.p, C, M, C, C);
       B16T dqkv = b.b16(size_t(M) * 3 * C);
       { const bf16* q = qkv.p; const bf16* o = att1.p; const bf16* dop = datt.p; bf16* dq = dqkv.p; float* sp = ascr.p;
+        const float* lse = lse1.p;
         b.emit([=](cudaStream_t st) {
           return attention_bwd(q, 3 * C, q + C, 3 * C, q + 2 * C, 3 * C, o, C, dop, C, dq, 3 * C, dq + C, 3 * C, dq + 2 * C, 3 * C, Bn, heads, d_head, n_tok, n_tok,
                                long(n_tok) * 3 * C, long(n_tok) * 3 * C, long(n_tok) * 3 * C, long(n_tok) * C, long(n_tok) * C, long(n_tok) * 3 * C,
-                               long(n_tok) * 3 * C, long(n_tok) * 3 * C, sc, sp, h16, st); }); }
+                               long(n_tok) * 3 * C, long(n_tok) * 3 * C, sc, sp, h16, st, lse); }); }
       b.free(datt);
       lora_wgrad(tb + ".attn1.to_q", l1.p, C, dqkv.p, 3 * C, M, C, C);
       lora_wgrad(tb + ".attn1.to_k", l1.p, C, dqkv.p ? dqkv.p + C : nullptr, 3 * C, M, C, C);
@@ -2315,6 +2318,7 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float sc
     return it == ctx->params.end() ? nullptr : &it->second;
   };
   auto is_proj = [](const std::string& s) { return s.rfind("feature_projections.", 0) == 0 || s.rfind("ema_feature_projections.", 0) == 0; };
+  std::vector<LoraPackEntry> multi;
   for (const PackEntry& e : ctx->pack) {
     const char* err = nullptr;
     if (lora_only == 1 && !(e.kind == PK_LINEAR && e.lora)) continue;
@@ -2342,6 +2346,11 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float sc
           r = int(A->shape[0]);
           if (A->shape[1] != e.C || Bm->shape[0] != e.N || Bm->shape[1] != r) return set_err(ctx, MADM_EINVAL, "LoRA shape mismatch: " + e.src);
           la = A->p; lb = Bm->p;
+        }
+        if (e.lora && r <= 16) {  // the 128 LoRA-targeted projections: folded by the multi-tensor kernel after the loop
+          LoraPackEntry le; le.w = w->p; le.la = la; le.lb = lb; le.out = base + e.off; le.N = e.N; le.K = e.C; le.r = r; le.ldo = e.ldo;
+          multi.push_back(le);
+          break;
         }
         err = pack_linear_weight(w->p, e.N, e.C, la, lb, r, scale, e.ldo, base + e.off, ctx->fp16, st);
         break;
@@ -2406,6 +2415,8 @@ int madm_pack_weights(madm_ctx* ctx, void* packed, const char* adapter, float sc
     }
     if (err) return set_err(ctx, MADM_ECUDA, err);
   }
+  if (!multi.empty())
+    if (const char* err = pack_lora_multi(multi.data(), int(multi.size()), scale, 0, ctx->fp16, st)) return set_err(ctx, MADM_ECUDA, err);
   return MADM_OK;
 }
 
@@ -2654,6 +2665,7 @@ int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed, const char* adapter, fl
     auto it = ctx->params.find(name);
     return it == ctx->params.end() ? nullptr : &it->second;
   };
+  std::vector<LoraPackEntry> multi_t, multi_n;  // transposed / natural outputs of the multi-tensor pack kernel
   for (const DPackEntry& e : ctx->dpack) {
     const char* err = nullptr;
     if (trainable_only) {  // only what an optimizer step / adapter switch can change: LoRA-folded linears, LoRA factors, projection convs
@@ -2684,6 +2696,11 @@ int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed, const char* adapter, fl
           r = int(A->shape[0]);
           la = A->p; lb = Bm->p;
         }
+        if (e.kind == DG_LINEAR && e.lora && r <= 16) {
+          LoraPackEntry le; le.w = w->p; le.la = la; le.lb = lb; le.out = base + e.off; le.N = e.N; le.K = e.C; le.r = r; le.ldo = e.ldo;
+          multi_t.push_back(le);
+          break;
+        }
         if (e.kind == DG_LINEAR) err = pack_linear_dgrad_weight(w->p, e.N, e.C, la, lb, r, scale, e.ldo, base + e.off, ctx->fp16, st);
         else err = pack_linear_weight(w->p, e.N, e.C, nullptr, nullptr, 0, 0.f, e.ldo, base + e.off, ctx->fp16, st);
         break;
@@ -2692,12 +2709,15 @@ int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed, const char* adapter, fl
         if (ad.empty()) break;
         const ParamRef* f = get(e.src + (e.kind == DG_LORA_A ? ".lora_A." : ".lora_B.") + ad + ".weight");
         if (!f) break;  // module not wrapped (zero-adapter configuration)
+        LoraPackEntry le; le.w = f->p; le.la = nullptr; le.lb = nullptr; le.out = base + e.off; le.r = 0; le.ldo = e.ldo;
         if (e.kind == DG_LORA_A) {
           if (f->shape[0] != 16 || f->shape[1] != e.C) return set_err(ctx, MADM_EINVAL, "training path: lora_A must be [16, in]: " + e.src);
-          err = pack_linear_weight(f->p, 16, e.C, nullptr, nullptr, 0, 0.f, e.ldo, base + e.off, ctx->fp16, st);
+          le.N = 16; le.K = e.C;
+          multi_n.push_back(le);  // [16, in] as is
         } else {
           if (f->shape[0] != e.N || f->shape[1] != 16) return set_err(ctx, MADM_EINVAL, "training path: lora_B must be [out, 16]: " + e.src);
-          err = pack_linear_dgrad_weight(f->p, e.N, 16, nullptr, nullptr, 0, 0.f, e.ldo, base + e.off, ctx->fp16, st);
+          le.N = e.N; le.K = 16;
+          multi_t.push_back(le);  // [out, 16] -> [16, out]
         }
         break;
       }
@@ -2705,6 +2725,10 @@ int madm_pack_dgrad_weights(madm_ctx* ctx, void* packed, const char* adapter, fl
     }
     if (err) return set_err(ctx, MADM_ECUDA, err);
   }
+  if (!multi_t.empty())
+    if (const char* err = pack_lora_multi(multi_t.data(), int(multi_t.size()), scale, 1, ctx->fp16, st)) return set_err(ctx, MADM_ECUDA, err);
+  if (!multi_n.empty())
+    if (const char* err = pack_lora_multi(multi_n.data(), int(multi_n.size()), scale, 0, ctx->fp16, st)) return set_err(ctx, MADM_ECUDA, err);
   return MADM_OK;
 }
 

@@ -30,6 +30,9 @@ static constexpr int kThreads = 64 + 32 * kEpiWarps;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 static constexpr int STG_LD = 36;                   // floats per staging row (32 + 4 pad: conflict-free 128-bit access)
 static constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
+#ifndef EPI_BATCH
+#define EPI_BATCH 4
+#endif
 
 struct GemmParams {
   CUtensorMap tmA[2];
@@ -120,16 +123,30 @@ __device__ __forceinline__ void st_shared_f4(uint32_t addr, float a, float b, fl
 // Fused epilogue of one 32x32 fp32 block that sits transposed in this warp's staging buffer: lane = (row sub-index, 4
 // columns), 8 iterations of 4 rows -> every global access is a full 128-byte row segment.  `bb` already holds
 // bias (+ the per-image time-embedding row bias).  Compile-time flags keep the loop free of uniform branches.
-template <bool RES, bool O32, int O16>
+template <bool RES, bool O32, int O16, bool ST = false>
 __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int M, float alpha, float4 bb, int act, int fp16,
                                           const float4 (&resv)[8], float* o32, int ldo32, uint16_t* o16, int ldo16,
                                           bool do_stats, float (&cs)[8], int s2d_H = 0, int s2d_W = 0, int s2d_B = 0, int N = 0) {
   const int rsub = lane >> 3;
   const int cc = (lane & 7) * 4;
+  // All eight shared-memory reads first, then the arithmetic and the stores: ld_shared_f4 is an `asm volatile` with a memory clobber, so
+  // in a single loop the compiler must keep every global store between two of them and the in-order issue serialises
+  // {ld.shared -> ~12 dependent ALU ops -> st.global} eight times per chunk (measured ~250 clk per iteration, profiles/r01_epilogue_store_bound.txt).
+  // Hoisted, the eight loads pipeline and the eight rows' arithmetic overlaps; the registers are those of the (now dead) TMEM fragment.
+  // Batches of EB rows.  Measured (tools/bench_epilogue.py, B200): with 16-bit / fp32 outputs and no residual, hoisting takes 15-18 % off
+  // output-bound launches (QKV 48.8 -> 41.3 us, 32768x320x320 26.0 -> 21.4 us); with a residual the eight prefetched residual rows already fill the
+  // register budget and the hoisted variant was 20 % SLOWER (30.0 -> 35.9 us), so those keep one row at a time.
+  constexpr int EB = (RES || ST) ? 1 : EPI_BATCH;  // (the statistics variant carries 8 more live accumulators: hoisting spills there)
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
+  for (int it0 = 0; it0 < 8; it0 += EB) {
+  float4 vv[EB];
+#pragma unroll
+  for (int u = 0; u < EB; ++u) vv[u] = ld_shared_f4(stg + uint32_t(((it0 + u) * 4 + rsub) * STG_LD + cc) * 4);
+#pragma unroll
+  for (int u = 0; u < EB; ++u) {
+    const int it = it0 + u;
     const int r = it * 4 + rsub;
-    float4 v = ld_shared_f4(stg + uint32_t(r * STG_LD + cc) * 4);
+    float4 v = vv[u];
     v.x = fmaf(v.x, alpha, bb.x); v.y = fmaf(v.y, alpha, bb.y); v.z = fmaf(v.z, alpha, bb.z); v.w = fmaf(v.w, alpha, bb.w);
     if constexpr (RES) { v.x += resv[it].x; v.y += resv[it].y; v.z += resv[it].z; v.w += resv[it].w; }
     if (act == ACT_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
@@ -152,6 +169,7 @@ __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int 
       }
     }
   }
+  }  // batches
   if (do_stats) {  // fold the 4 row sub-groups of this warp: lanes 0..7 end up with the totals of their 4 columns over 32 rows
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -528,18 +546,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if constexpr (S2D) {  // 16-bit output in space-to-depth layout (row offsets computed per row inside)
               const int s2d_W = p.s2d_W, s2d_H = p.s2d_H, s2d_B = p.s2d_B;
               uint16_t* o16p = out16 + n;
-              if (residual) epi_block<true, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
-              else if (out32) epi_block<false, true, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
-              else epi_block<false, false, 2>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
+              if (residual) epi_block<true, true, 2, STATS>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
+              else if (out32) epi_block<false, true, 2, STATS>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
+              else epi_block<false, false, 2, STATS>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1, s2d_H, s2d_W, s2d_B, N);
             } else {
               uint16_t* o16p = out16 ? out16 + size_t(row0) * ldo16 + n : nullptr;
               switch (mode) {
-                case 1: epi_block<false, false, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-                case 2: epi_block<false, true, 0>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-                case 3: epi_block<false, true, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-                case 5: epi_block<true, false, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-                case 6: epi_block<true, true, 0>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
-                default: epi_block<true, true, 1>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 1: epi_block<false, false, 1, STATS>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 2: epi_block<false, true, 0, STATS>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 3: epi_block<false, true, 1, STATS>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 5: epi_block<true, false, 1, STATS>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                case 6: epi_block<true, true, 0, STATS>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
+                default: epi_block<true, true, 1, STATS>(stg, lane, row0, M, alpha, bb, act, fp16, resv, o32p, ldo32, o16p, ldo16, do_stats, cs1); break;
               }
             }
 #ifdef GEMM_INSTR

@@ -57,7 +57,7 @@ struct FaLaunch {
 };
 const char* flash_attention_tc_prepare(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, void* o, int ldo, int B,
                                        int heads, int d, int Nq, int Nk, long q_bstride, long kv_bstride, long o_bstride, float scale,
-                                       int fp16, FaLaunch* out);
+                                       int fp16, FaLaunch* out, float* lse = nullptr /* optional [B,heads,Nq] log-sum-exp output */);
 const char* flash_attention_tc_launch(const FaLaunch& l, cudaStream_t st);
 
 // ---- elementwise.cu
@@ -175,7 +175,8 @@ const char* temb_silu_bwd(const float* d_act, const float* emb, const float* con
 size_t attention_bwd_scratch_floats(int B, int heads, int d, int Nq, int Nk);
 const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* o, int ldo, const void* dout, int lddo,
                           void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, int B, int heads, int d, int Nq, int Nk, long q_bs, long k_bs,
-                          long v_bs, long o_bs, long do_bs, long dq_bs, long dk_bs, long dv_bs, float scale, float* scratch, int fp16, cudaStream_t st);
+                          long v_bs, long o_bs, long do_bs, long dq_bs, long dk_bs, long dv_bs, float scale, float* scratch, int fp16, cudaStream_t st,
+                          const float* lse = nullptr /* [B,heads,Nq] from the forward kernel: skips the backward's own Q K^T pass */);
 
 // ---- wgrad.cu: dW[n,k] = alpha * sum_m dY[m,n] X[m,k] (taps = 9: implicit im2col of X [Bimg,H,W,K]) -> out[n*so_n + k*so_k + tap*so_tap]
 int wgrad_splits(int M, int N, int K, int taps);
@@ -195,6 +196,12 @@ const char* pack_conv_dgrad_weight(const float* w, int Cout, int Cin, int taps, 
                                    cudaStream_t st);
 const char* pack_linear_dgrad_weight(const float* w, int N, int K, const float* lora_a, const float* lora_b, int r, float scale, int ldo,
                                      void* out_bf16, int fp16, cudaStream_t st);
+// many linears in one launch: out = 16-bit(w + scale * lb la) as [N, ldo] rows (transpose = 0) or transposed [K, ldo] rows (transpose = 1);
+// la = null: plain conversion.  r <= 16.
+struct LoraPackEntry { const float* w; const float* la; const float* lb; void* out; int N, K, r, ldo; };
+constexpr int kLoraPackMax = 48;
+struct LoraPackTable { LoraPackEntry e[kLoraPackMax]; int n; float scale; int transpose; int fp16; };
+const char* pack_lora_multi(const LoraPackEntry* entries, int n, float scale, int transpose, int fp16, cudaStream_t st);
 // GEGLU: rows of W[8C, C] reordered so each 128-row tile holds 64 value rows then their 64 gate rows (bias likewise)
 const char* pack_geglu_weight(const float* w, const float* bias, int C4 /* = 4C */, int K, void* out_bf16, float* out_bias,
                               int fp16, cudaStream_t st);

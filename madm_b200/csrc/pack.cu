@@ -82,6 +82,65 @@ const char* pack_linear_dgrad_weight(const float* w, int N, int K, const float* 
   return cudaGetLastError() == cudaSuccess ? nullptr : "pack_linear_dgrad_weight launch failed";
 }
 
+// Many linears in one launch (the 128 LoRA-wrapped projections are re-folded after every optimizer step and adapter switch of a training
+// step: one launch per 48 of them instead of one each).  32 x 32 tiles: w is read along k, the LoRA factors of the tile go through shared
+// memory, the result is written along k (forward operand) or, transposed through the tile, along n (input-gradient operand).
+__global__ void __launch_bounds__(256) pack_lora_multi_kernel(const __grid_constant__ LoraPackTable t) {
+  const LoraPackEntry e = t.e[blockIdx.z];
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  if (n0 >= e.N || k0 >= e.K) return;
+  __shared__ float sw[32][33];
+  __shared__ float sb[32][17];
+  __shared__ float sa[16][33];
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+  for (int i = ty; i < 32; i += 8) sw[i][tx] = (n0 + i < e.N && k0 + tx < e.K) ? e.w[size_t(n0 + i) * e.K + k0 + tx] : 0.f;
+  const bool lora = e.la != nullptr;
+  if (lora) {
+    for (int i = tid; i < 32 * 16; i += 256) {
+      const int r = i >> 4, j = i & 15;
+      sb[r][j] = (n0 + r < e.N && j < e.r) ? e.lb[size_t(n0 + r) * e.r + j] : 0.f;
+      const int jj = i >> 5, c = i & 31;
+      sa[jj][c] = (jj < e.r && k0 + c < e.K) ? e.la[size_t(jj) * e.K + k0 + c] : 0.f;
+    }
+  }
+  __syncthreads();
+  if (lora) {
+    for (int i = ty; i < 32; i += 8) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc = fmaf(sb[i][j], sa[j][tx], acc);
+      sw[i][tx] = fmaf(t.scale, acc, sw[i][tx]);
+    }
+    __syncthreads();
+  }
+  uint16_t* out = reinterpret_cast<uint16_t*>(e.out);
+  if (!t.transpose) {
+    for (int i = ty; i < 32; i += 8)
+      if (n0 + i < e.N && k0 + tx < e.K) out[size_t(n0 + i) * e.ldo + k0 + tx] = cvt_16(sw[i][tx], t.fp16);
+  } else {
+    for (int i = ty; i < 32; i += 8)
+      if (k0 + i < e.K && n0 + tx < e.N) out[size_t(k0 + i) * e.ldo + n0 + tx] = cvt_16(sw[tx][i], t.fp16);
+  }
+}
+
+const char* pack_lora_multi(const LoraPackEntry* entries, int n, float scale, int transpose, int fp16, cudaStream_t st) {
+  for (int first = 0; first < n; first += kLoraPackMax) {
+    LoraPackTable t;
+    t.n = n - first < kLoraPackMax ? n - first : kLoraPackMax;
+    t.scale = scale; t.transpose = transpose; t.fp16 = fp16;
+    int maxN = 0, maxK = 0;
+    for (int i = 0; i < t.n; ++i) {
+      t.e[i] = entries[first + i];
+      if (t.e[i].la && t.e[i].r > 16) return "pack_lora_multi: LoRA rank must be <= 16";
+      if (t.e[i].N > maxN) maxN = t.e[i].N;
+      if (t.e[i].K > maxK) maxK = t.e[i].K;
+    }
+    pack_lora_multi_kernel<<<dim3((maxK + 31) / 32, (maxN + 31) / 32, t.n), dim3(32, 8), 0, st>>>(t);
+    if (cudaGetLastError() != cudaSuccess) return "pack_lora_multi launch failed";
+  }
+  return nullptr;
+}
+
 // out[n, k] = bf16( w[n,k] + scale * sum_j lb[n,j] * la[j,k] )
 __global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, const float* __restrict__ la,
                                    const float* __restrict__ lb, int r, float scale, int ldo, int fp16, uint16_t* __restrict__ out) {
