@@ -29,7 +29,15 @@ static constexpr int kEpiWarps = 8;                 // two warps per TMEM lane q
 static constexpr int kThreads = 64 + 32 * kEpiWarps;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 static constexpr int STG_LD = 36;                   // floats per staging row (32 + 4 pad: conflict-free 128-bit access)
-static constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
+// Per-epilogue-warp staging: the transpose buffer of the coalesced epilogue (32 x 36 floats) or, on the TMA-store path, EPI_NBUF
+// swizzled 32 x 32 tiles (4 KB each, 1024-byte aligned: the TMA swizzle pattern is a function of the shared-memory address bits).
+#ifndef EPI_NBUF
+#define EPI_NBUF 2
+#endif
+static constexpr int TMA_TILE_BYTES = 4096;
+static constexpr int STG_WARP_BYTES = EPI_NBUF * TMA_TILE_BYTES > 5120 ? EPI_NBUF * TMA_TILE_BYTES : 5120;
+static_assert(STG_WARP_BYTES >= 32 * STG_LD * 4 && STG_WARP_BYTES % 1024 == 0, "staging");
+enum { TMA_EPI_NONE = 0, TMA_EPI_F32 = 1, TMA_EPI_RED = 2, TMA_EPI_H16 = 3 };
 #ifndef EPI_BATCH
 #define EPI_BATCH 4
 #endif
@@ -37,6 +45,8 @@ static constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
 struct GemmParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
+  CUtensorMap tmO;   // output tensor map of the TMA-store epilogue (box 32 columns x 32 rows; fp32 with 128B swizzle or 16-bit with 64B swizzle)
+  int tma_epi;       // TMA_EPI_*: 0 = coalesced-store epilogue, else the epilogue hands 32x32 tiles to cp(.reduce).async.bulk.tensor
   int nseg;
   int kchunks[2];
   int cpt[2];
@@ -74,7 +84,7 @@ struct GemmParams {
 // MT = M sub-tiles (128 rows each) per CTA tile.  MT = 2 loads one W box per K chunk for two A boxes (tile 256 x BN): the
 // L2->SM operand traffic per FLOP drops from (128+BN) to (256+BN)/2 bytes-equivalents, which is what bounds the BN = 128
 // layers (measured 12.7 TB/s of L2->SM reads at 42 % tensor-pipe activity on the VAE 512^2 convs).
-enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_S2D = 2 };  // epilogue variants (bit mask) compiled as separate kernels
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_S2D = 2, EPI_TMA = 4 };  // epilogue variants (bit mask; EPI_TMA only alone) compiled as separate kernels
 
 // PAIR: the CTA is one half of a cta_group::2 pair (cluster of 2): the pair's tile is 2*MT*128 rows x BN, each CTA stages its own
 // A rows and HALF of the W tile (BN/2 rows), and the leader's tcgen05.mma.cta_group::2 (M = 256) reads both halves.  Per CTA the
@@ -179,6 +189,43 @@ __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int 
   }
 }
 
+// TMA-store epilogue of one 32x32 block, in the row-per-thread layout tcgen05.ld delivers (thread = row, v[j] = column j, bias and
+// activation already applied): the tile is written to a swizzled staging buffer (conflict-free: the 8 lanes of a quarter-warp cover all
+// 32 banks) and leaves the SM as ONE bulk tensor store -- or, for `hs += GEMM` (in-place fp32 residual), one bulk reduce-add executed at
+// the L2, so the residual never enters the SM.  No ld.shared, no per-thread global loads / stores: the serial chain per chunk is
+// tcgen05.ld -> FMAs -> st.shared -> fence -> issue, and the next chunk starts while the TMA engine drains this one.
+// `buf` toggles between the EPI_NBUF staging tiles; the elected lane (elect.sync is deterministic for a full mask) owns the bulk groups.
+template <bool H16>
+__device__ __forceinline__ void tma_epi_tile(const float (&v)[32], uint32_t stg, int& buf, int lane, const CUtensorMap* tm, int mode, int col, int row,
+                                             int fp16) {
+  const uint32_t sb = stg + uint32_t(buf) * TMA_TILE_BYTES;
+  if (elect_one()) bulk_wait_read<EPI_NBUF - 1>();  // the store that last used this buffer has read it
+  __syncwarp();
+  if constexpr (H16) {  // 32 rows x 64 B, SWIZZLE_64B: 16-byte unit index ^= address bits [7,9) = (row >> 1) & 3
+    const uint32_t rowp = sb + uint32_t(lane) * 64u;
+    const uint32_t sw = uint32_t(lane >> 1) & 3u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t a = pack2_16(v[8 * u + 0], v[8 * u + 1], fp16), b = pack2_16(v[8 * u + 2], v[8 * u + 3], fp16);
+      const uint32_t c = pack2_16(v[8 * u + 4], v[8 * u + 5], fp16), d = pack2_16(v[8 * u + 6], v[8 * u + 7], fp16);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(rowp + ((uint32_t(u) ^ sw) << 4)), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+    }
+  } else {  // 32 rows x 128 B, SWIZZLE_128B: 16-byte unit index ^= address bits [7,10) = row & 7
+    const uint32_t rowp = sb + uint32_t(lane) * 128u;
+    const uint32_t sw = uint32_t(lane) & 7u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) st_shared_f4(rowp + ((uint32_t(u) ^ sw) << 4), v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+  }
+  fence_proxy_async();  // this thread's generic-proxy writes -> visible to the async proxy (TMA)
+  __syncwarp();
+  if (elect_one()) {
+    if (mode == TMA_EPI_RED) tma_reduce_add_2d(tm, sb, col, row);
+    else tma_store_2d(tm, sb, col, row);
+    bulk_commit();
+  }
+  buf = (buf + 1 == EPI_NBUF) ? 0 : buf + 1;
+}
+
 // Persistent, warp-specialised kernel: one CTA per SM walks the tile list (tile = blockIdx.x + i*gridDim.x, N fastest).
 //   warp 0      TMA producer: fills the STAGES-deep smem ring (A box + W box per 64-wide K chunk)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; two accumulator stages in TMEM so the MMAs of tile
@@ -216,6 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     prefetch_tmap(&p.tmA[0]);
     if (p.nseg > 1) prefetch_tmap(&p.tmA[1]);
     prefetch_tmap(&p.tmB);
+    if (p.tma_epi) prefetch_tmap(&p.tmO);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -389,6 +437,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     constexpr bool STATS = (EPI & EPI_STATS) != 0;
     constexpr bool S2D = (EPI & EPI_S2D) != 0;  // separate instantiation: its extra live values would otherwise spill in every variant
     constexpr bool do_stats = STATS;  // compile-time: the statistics-free variant keeps the tighter rolled chunk loop
+    // TMA-store epilogue (plain variant only: statistics / space-to-depth outputs keep the coalesced path)
+    constexpr bool TMA = (EPI & EPI_TMA) != 0;  // separate instantiation: neither path pays for the other's live registers
+    const int tma_epi = TMA ? p.tma_epi : 0;
+    int tbuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t r[32];
@@ -453,6 +505,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           tmem_ld32(taddr + half * 32, r);
           tmem_ld32(taddr + 64 + half * 32, g);
           tmem_ld_wait();
+          if constexpr (TMA) {  // value * gelu(gate) in the row-per-thread layout -> one 16-bit tile store
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 bh = make_float4(0.f, 0.f, 0.f, 0.f), bg = bh;
+              if (bias) {
+                bh = __ldg(reinterpret_cast<const float4*>(bias + n0 + half * 32 + j));
+                bg = __ldg(reinterpret_cast<const float4*>(bias + n0 + 64 + half * 32 + j));
+              }
+              v[j + 0] = fmaf(__uint_as_float(r[j + 0]), alpha, bh.x) * gelu_erf_f(fmaf(__uint_as_float(g[j + 0]), alpha, bg.x));
+              v[j + 1] = fmaf(__uint_as_float(r[j + 1]), alpha, bh.y) * gelu_erf_f(fmaf(__uint_as_float(g[j + 1]), alpha, bg.y));
+              v[j + 2] = fmaf(__uint_as_float(r[j + 2]), alpha, bh.z) * gelu_erf_f(fmaf(__uint_as_float(g[j + 2]), alpha, bg.z));
+              v[j + 3] = fmaf(__uint_as_float(r[j + 3]), alpha, bh.w) * gelu_erf_f(fmaf(__uint_as_float(g[j + 3]), alpha, bg.w));
+            }
+            if (row0 < M) tma_epi_tile<true>(v, stg, tbuf, lane, &p.tmO, TMA_EPI_H16, on0 + half * 32, row0, fp16);
+          } else {
           // value * gelu(gate) in the row-per-thread layout, then transpose through smem for coalesced 16-bit stores
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -475,11 +543,42 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           const float4 nores[8] = {};
           epi_block<false, false, 1>(stg, lane, row0, M, 1.0f, make_float4(0.f, 0.f, 0.f, 0.f), ACT_NONE, fp16, nores, nullptr, 0,
                                      out16 + size_t(row0) * ldo16 + on0 + half * 32 + cc, ldo16, false, nostats);
+          }  // !TMA
         }
       } else {
         float cs1[8];  // column statistics of the current chunk (STATS variant only)
 #pragma unroll 1
         for (int c = par * 32; c < BN; c += 64) {
+          if constexpr (TMA) {  // (N % 32 == 0 on this path: a chunk is either inside the matrix or entirely outside)
+            if (n0 + c >= N) break;
+            __syncwarp();
+            tmem_ld32(taddr + c, r);
+            const int n = n0 + c;
+            const float* rb = rowbias ? rowbias + size_t(min(row0, M - 1) / rows_per_img) * ld_rowbias + n : nullptr;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {  // bias (+ time-embedding row bias): uniform addresses, issued under the TMEM load
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n + j));
+              if (rb) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(rb + j));
+                b4.x += t4.x; b4.y += t4.y; b4.z += t4.z; b4.w += t4.w;
+              }
+              v[j] = b4.x; v[j + 1] = b4.y; v[j + 2] = b4.z; v[j + 3] = b4.w;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = fmaf(__uint_as_float(r[j]), alpha, v[j]);
+              if (act == ACT_SILU) x = silu_f(x);
+              else if (act == ACT_RELU) x = fmaxf(x, 0.f);
+              v[j] = x;
+            }
+            if (row0 < M) {
+              if (tma_epi == TMA_EPI_H16) tma_epi_tile<true>(v, stg, tbuf, lane, &p.tmO, tma_epi, n, row0, fp16);
+              else tma_epi_tile<false>(v, stg, tbuf, lane, &p.tmO, tma_epi, n, row0, fp16);
+            }
+          } else {
           if constexpr (STATS) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) cs1[i] = 0.f;
@@ -594,6 +693,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               }
             }
           }
+          }  // !TMA
         }
       }
       }  // sub-tiles
@@ -612,6 +712,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         acc = 0;
         acc_phase ^= 1u;
       }
+    }
+    if (tma_epi) {  // all bulk stores of this warp are complete (smem read and global writes) before the CTA may exit
+      if (elect_one()) bulk_wait_all();
+      __syncwarp();
     }
 #ifdef GEMM_INSTR
     if (blockIdx.x == 4 && lane == 0 && (warp == 2 || warp == 6))
@@ -649,13 +753,13 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static const char* encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                              const cuuint32_t* box) {
+                              const cuuint32_t* box, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_UINT16,
+                              CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return "cuTensorMapEncodeTiled unavailable (no CUDA driver)";
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, dt, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     static thread_local char buf[160];
     snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu/%llu)", int(r), rank,
@@ -807,6 +911,35 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
     L.split_stride = d.split_stride;
   }
   L.num_tiles = n_tiles * m_tiles * L.splits;
+  // TMA-store epilogue: single-output launches whose 32-column chunks tile N exactly.  fp32 output -> bulk tensor store; in-place fp32
+  // residual (hs += GEMM, no activation) -> bulk reduce-add at the L2; 16-bit output (also GEGLU) -> 16-bit tile store.  Statistics,
+  // space-to-depth, split-K, two outputs and out-of-place / 16-bit residuals keep the coalesced epilogue.  MADM_GEMM_TMA_EPI=0 disables.
+  L.tma_epi = TMA_EPI_NONE;
+  {
+    const char* env = getenv("MADM_GEMM_TMA_EPI");
+    const bool on = !env || atoi(env) != 0;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool plain = on && L.bn >= 32 && L.splits == 1 && !d.colstats && d.s2d_W == 0 && d.N % 32 == 0 && (!d.bias || al16(d.bias)) &&
+                       (!d.rowbias || (al16(d.rowbias) && (d.ld_rowbias ? d.ld_rowbias : d.N) % 4 == 0));
+    if (plain && d.act == ACT_GEGLU) {
+      if (al16(d.out_bf16) && d.ldo16 % 8 == 0) L.tma_epi = TMA_EPI_H16;
+    } else if (plain && d.out_f32 && !d.out_bf16 && al16(d.out_f32) && d.ldo32 % 4 == 0) {
+      if (!d.residual) L.tma_epi = TMA_EPI_F32;
+      else if (!d.res16 && d.residual == d.out_f32 && d.ldr == d.ldo32 && d.act == ACT_NONE) L.tma_epi = TMA_EPI_RED;
+    } else if (plain && d.out_bf16 && !d.out_f32 && !d.residual && al16(d.out_bf16) && d.ldo16 % 8 == 0) {
+      L.tma_epi = TMA_EPI_H16;
+    }
+    if (L.tma_epi) {
+      const bool h16 = L.tma_epi == TMA_EPI_H16;
+      cuuint64_t dims[2] = {cuuint64_t(d.N), cuuint64_t(d.M)};
+      cuuint64_t strides[1] = {h16 ? cuuint64_t(d.ldo16) * 2 : cuuint64_t(d.ldo32) * 4};
+      cuuint32_t box[2] = {32, 32};
+      const void* base = h16 ? static_cast<const void*>(d.out_bf16) : static_cast<const void*>(d.out_f32);
+      if (const char* e = encode_map(&L.tmO, base, 2, dims, strides, box, h16 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                                     h16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B))
+        return e;
+    }
+  }
   if (L.pair) {
     const int pairs = L.num_tiles < num_sms() / 2 ? L.num_tiles : num_sms() / 2;
     L.grid = dim3(unsigned(2 * pairs));
@@ -870,6 +1003,9 @@ static const char* launch_bn_s(const GemmLaunch& L, const GemmParams& p, cudaStr
 template <int BN, int MT, bool PAIR>
 static const char* launch_epi(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
   const int epi = (p.s2d_W > 0 ? EPI_S2D : 0) | (p.colstats ? EPI_STATS : 0);
+  if constexpr (BN >= 32) {
+    if (p.tma_epi) return launch_bn_s<BN, MT, EPI_TMA, PAIR>(L, p, stream);  // (only chosen for plain launches, see gemm_prepare)
+  }
   switch (epi) {
     case 0: return launch_bn_s<BN, MT, 0, PAIR>(L, p, stream);
     case 1: return launch_bn_s<BN, MT, 1, PAIR>(L, p, stream);
@@ -894,6 +1030,8 @@ const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   p.tmA[0] = L.tmA[0];
   p.tmA[1] = L.tmA[d.nseg > 1 ? 1 : 0];
   p.tmB = L.tmB;
+  p.tma_epi = L.tma_epi;
+  if (L.tma_epi) p.tmO = L.tmO; else p.tmO = L.tmB;
   p.nseg = d.nseg;
   for (int s = 0; s < 2; ++s) {
     p.kchunks[s] = s < d.nseg ? L.kchunks[s] : 0;

@@ -55,6 +55,8 @@ struct GemmDesc {
 struct GemmLaunch {  // prepared launch: tensor maps encoded once, replayed per forward
   alignas(64) CUtensorMap tmA[2];
   alignas(64) CUtensorMap tmB;
+  alignas(64) CUtensorMap tmO;  // output map of the TMA-store epilogue (valid when tma_epi != 0)
+  int tma_epi = 0;           // 0 coalesced-store epilogue, 1 fp32 bulk store, 2 fp32 bulk reduce-add (in-place residual), 3 16-bit bulk store
   GemmDesc d;
   int bn = 128;
   int kchunks[2] = {0, 0};   // 64-wide K chunks per segment

@@ -137,6 +137,64 @@ def test_gemm_geglu(ops, cuda_device):
     assert relerr(out, h * F.gelu(gate)) < 1e-2
 
 
+@pytest.mark.parametrize("M,K,N,bn,pair", [(300, 320, 320, 0, 0), (1000, 320, 960, 192, -1), (4096, 1280, 320, 0, 1), (32768, 320, 320, 0, 0), (520, 640, 640, 64, 0),
+                                           (2048, 128, 96, 32, 0), (8192, 640, 1280, 128, 0), (8192, 512, 512, 256, 1)])
+def test_gemm_tma_store_epilogue_matches_coalesced(ops, cuda_device, monkeypatch, M, K, N, bn, pair):
+    """The TMA-store epilogue (bulk tensor stores of swizzled 32x32 tiles; bulk reduce-add for `hs += GEMM`) against the coalesced-store
+    epilogue (MADM_GEMM_TMA_EPI=0) on the same launch: bit-identical for every mode it takes over, incl. ragged M (clipped by the
+    tensor map), row bias, activation and untouched neighbours in a wider output buffer."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + bn)
+    a = bf(torch.randn(M, K, device=cuda_device, generator=g))
+    w = bf(torch.randn(N, K, device=cuda_device, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=cuda_device, generator=g)
+    HW = 8 if M % 32 else 32
+    nimg = (M + HW - 1) // HW
+    rowbias = torch.randn(nimg, N, device=cuda_device, generator=g) if M % 32 == 0 else None
+    res = torch.randn(M, N + 32, device=cuda_device, generator=g)
+    seg = ops.make_seg(a, 1, 1, M, K)
+
+    def run_all():
+        outs = []
+        o32 = torch.full((M, N + 32), 7.0, device=cuda_device)  # wider buffer: the last 32 columns must stay untouched
+        ops.gemm([seg], M, N, w, bias=bias, rowbias=rowbias, rows_per_img=HW, out_f32=o32, ldo32=N + 32, bn=bn, pair=pair, act=1)
+        outs.append(o32)
+        hs = res.clone()
+        ops.gemm([seg], M, N, w, bias=bias, residual=hs, ldr=N + 32, out_f32=hs, ldo32=N + 32, bn=bn, pair=pair, alpha=0.5)
+        outs.append(hs)
+        o16 = torch.full((M, N + 32), 3.0, device=cuda_device, dtype=DT)
+        ops.gemm([seg], M, N, w, bias=bias, out_bf16=o16, ldo16=N + 32, bn=bn, pair=pair)
+        outs.append(o16)
+        torch.cuda.synchronize()
+        return outs
+
+    monkeypatch.setenv("MADM_GEMM_TMA_EPI", "0")
+    ref = run_all()
+    monkeypatch.setenv("MADM_GEMM_TMA_EPI", "1")
+    got = run_all()
+    for r_, g_ in zip(ref, got):
+        assert torch.equal(r_, g_)
+    assert relerr(got[0][:, :N], F.silu(a.float() @ w.float().t() + bias + (rowbias.repeat_interleave(HW, 0)[:M] if rowbias is not None else 0))) < 2e-3
+    assert relerr(got[1][:, :N], 0.5 * (a.float() @ w.float().t()) + bias + res[:, :N]) < 2e-3
+    assert torch.equal(got[1][:, N:], res[:, N:]) and bool((got[0][:, N:] == 7.0).all()) and bool((got[2][:, N:] == 3.0).all())
+
+
+def test_gemm_geglu_tma_store_matches_coalesced(ops, cuda_device, monkeypatch):
+    g = torch.Generator(device="cuda").manual_seed(12)
+    M, Cc = 1000, 320
+    x = bf(torch.randn(M, Cc, device=cuda_device, generator=g))
+    w = torch.randn(8 * Cc, Cc, device=cuda_device, generator=g) / math.sqrt(Cc)
+    b = torch.randn(8 * Cc, device=cuda_device, generator=g)
+    wp, bp = ops.pack_geglu(w, b, dtype=DT)
+    outs = []
+    for sw in ("0", "1"):
+        monkeypatch.setenv("MADM_GEMM_TMA_EPI", sw)
+        out = torch.zeros(M, 4 * Cc, dtype=DT, device=cuda_device)
+        ops.gemm([ops.make_seg(x, 1, 1, M, Cc)], M, 4 * Cc, wp, Nw=8 * Cc, bias=bp, out_bf16=out, ldo16=4 * Cc, act=2)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+
+
 # ---------------------------------------------------------------------------------------------- implicit-GEMM convs
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 128, 192), (1, 8, 128, 64, 128), (3, 8, 8, 128, 320), (1, 64, 64, 320, 320),
                                             (2, 32, 32, 192, 640), (1, 4, 256, 64, 128)])

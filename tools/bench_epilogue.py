@@ -13,10 +13,14 @@ from madm_b200 import ops  # noqa: E402
 dev = torch.device("cuda:0")
 DT = torch.float16
 only = sys.argv[1] if len(sys.argv) > 1 else ""
+print("MADM_GEMM_TMA_EPI =", os.environ.get("MADM_GEMM_TMA_EPI", "(default: on)"), flush=True)
 for name, M, K, N, mode, stats in [("conv_in 2.1Mx128x64 h16", 2097152, 64, 128, "h16", False), ("conv_in 2.1Mx128x64 h16+stats", 2097152, 64, 128, "h16", True),
                                    ("2.1Mx128x128 f32+stats", 2097152, 128, 128, "f32", True), ("32768x320x320 res", 32768, 320, 320, "res", True),
                                    ("32768x320x320 h16", 32768, 320, 320, "h16", False), ("8192x640x640 res", 8192, 640, 640, "res", True),
-                                   ("32768x960x320 h16 (qkv)", 32768, 320, 960, "h16", False)]:
+                                   ("32768x960x320 h16 (qkv)", 32768, 320, 960, "h16", False), ("32768x320x320 res plain", 32768, 320, 320, "res", False),
+                                   ("8192x640x640 res plain", 8192, 640, 640, "res", False), ("2048x1280x1280 res plain", 2048, 1280, 1280, "res", False),
+                                   ("32768x320x320 f32", 32768, 320, 320, "f32", False), ("8192x1920x640 h16 (qkv)", 8192, 640, 1920, "h16", False),
+                                   ("2.1Mx128x128 f32 plain", 2097152, 128, 128, "f32", False)]:
     if only and only not in name:
         continue
     x = torch.randn(M, K, device=dev).to(DT)
