@@ -495,9 +495,9 @@ struct Builder {
         const double exec = 2.0 * double(d.M) * d.N * K;
         if (algo_flops < 0) algo_flops = exec;
         if (getenv("MADM_DUMP_PLAN"))
-          fprintf(stderr, "MADM_PLAN gemm M=%d N=%d K=%d bn=%d tiles=%d taps=%d nseg=%d act=%d res=%d f32=%d h16=%d gflop=%.3f splits=%d\n", d.M, d.N,
+          fprintf(stderr, "MADM_PLAN gemm M=%d N=%d K=%d bn=%d tiles=%d taps=%d nseg=%d act=%d res=%d f32=%d h16=%d gflop=%.3f splits=%d tma=%d stats=0\n", d.M, d.N,
                   int(K), L.bn, L.num_tiles, d.seg[0].ntaps, d.nseg, d0.act, d0.residual ? 1 : 0, d0.out_f32 ? 1 : 0, d0.out_bf16 ? 1 : 0,
-                  algo_flops / 1e9, splits);
+                  algo_flops / 1e9, splits, L.tma_epi);
         emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, gemm_algo_bytes(d), exec);
         const GemmDesc e0 = d0; const float* pp = part.p; const int f16 = ctx->fp16; const long ss = d.split_stride;
         if (e0.alpha != 1.0f) fail(MADM_EINVAL, "split-K with alpha != 1 is not supported");
@@ -527,8 +527,9 @@ struct Builder {
     if (getenv("MADM_DUMP_PLAN")) {
       int K = 0;
       for (int sgi = 0; sgi < d.nseg; ++sgi) K += d.seg[sgi].ntaps * d.seg[sgi].C;
-      fprintf(stderr, "MADM_PLAN gemm M=%d N=%d K=%d bn=%d tiles=%d taps=%d nseg=%d act=%d res=%d f32=%d h16=%d gflop=%.3f\n", d.M, d.N, K, L.bn,
-              L.num_tiles, d.seg[0].ntaps, d.nseg, d.act, d.residual ? 1 : 0, d.out_f32 ? 1 : 0, d.out_bf16 ? 1 : 0, algo_flops / 1e9);
+      fprintf(stderr, "MADM_PLAN gemm M=%d N=%d K=%d bn=%d tiles=%d taps=%d nseg=%d act=%d res=%d f32=%d h16=%d gflop=%.3f tma=%d stats=%d\n", d.M, d.N, K, L.bn,
+              L.num_tiles, d.seg[0].ntaps, d.nseg, d.act, d.residual ? 1 : 0, d.out_f32 ? 1 : 0, d.out_bf16 ? 1 : 0, algo_flops / 1e9, L.tma_epi,
+              (d.colstats ? 1 : 0) | (d.s2d_W > 0 ? 2 : 0));
     }
     emit([L](cudaStream_t st) { return gemm_launch(L, st); }, false, MADM_KIND_GEMM, algo_flops, gemm_algo_bytes(d), exec);
   }

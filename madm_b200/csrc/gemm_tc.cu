@@ -84,7 +84,7 @@ struct GemmParams {
 // MT = M sub-tiles (128 rows each) per CTA tile.  MT = 2 loads one W box per K chunk for two A boxes (tile 256 x BN): the
 // L2->SM operand traffic per FLOP drops from (128+BN) to (256+BN)/2 bytes-equivalents, which is what bounds the BN = 128
 // layers (measured 12.7 TB/s of L2->SM reads at 42 % tensor-pipe activity on the VAE 512^2 convs).
-enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_S2D = 2, EPI_TMA = 4 };  // epilogue variants (bit mask; EPI_TMA only alone) compiled as separate kernels
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_S2D = 2, EPI_TMA = 4 };  // epilogue variants (bit mask; EPI_TMA never with EPI_S2D) compiled as separate kernels
 
 // PAIR: the CTA is one half of a cta_group::2 pair (cluster of 2): the pair's tile is 2*MT*128 rows x BN, each CTA stages its own
 // A rows and HALF of the W tile (BN/2 rows), and the leader's tcgen05.mma.cta_group::2 (M = 256) reads both halves.  Per CTA the
@@ -187,6 +187,36 @@ __device__ __forceinline__ void epi_block(uint32_t stg, int lane, int row0, int 
       cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
     }
   }
+}
+
+// Column (sum, sum of squares) of a 32x32 block held one row per lane: recursive halving -- at step `off` a lane keeps the half of its
+// columns selected by its own bit and receives the partner's partial sums of that half -- leaves lane l with the totals of column l
+// after 31 shuffles per quantity (fixed order: bit-reproducible, no atomics).
+__device__ __forceinline__ void colstats_rows32(const float (&v)[32], int lane, float& sum, float& sumsq) {
+  float a[16], q[16];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float keep = up ? v[k + 16] : v[k], send = up ? v[k] : v[k + 16];
+      const float r = __shfl_xor_sync(0xffffffffu, send, 16);
+      a[k] = keep + r;
+      q[k] = fmaf(keep, keep, r * r);
+    }
+  }
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float keep = up ? a[k + off] : a[k], send = up ? a[k] : a[k + off];
+      a[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      const float keepq = up ? q[k + off] : q[k], sendq = up ? q[k] : q[k + off];
+      q[k] = keepq + __shfl_xor_sync(0xffffffffu, sendq, off);
+    }
+  }
+  sum = a[0];
+  sumsq = q[0];
 }
 
 // TMA-store epilogue of one 32x32 block, in the row-per-thread layout tcgen05.ld delivers (thread = row, v[j] = column j, bias and
@@ -577,6 +607,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (row0 < M) {
               if (tma_epi == TMA_EPI_H16) tma_epi_tile<true>(v, stg, tbuf, lane, &p.tmO, tma_epi, n, row0, fp16);
               else tma_epi_tile<false>(v, stg, tbuf, lane, &p.tmO, tma_epi, n, row0, fp16);
+              if constexpr (STATS) {  // GroupNorm statistics of the consumer: (sum, sumsq) of the fp32 values per column over this warp's 32 rows
+                if (row0 + lane >= M) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
+                float cs, cq;
+                colstats_rows32(v, lane, cs, cq);
+                *reinterpret_cast<float2*>(p.colstats + (size_t(row0 >> 5) * N + n + lane) * 2) = make_float2(cs, cq);
+              }
             }
           } else {
           if constexpr (STATS) {
@@ -912,20 +951,21 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   }
   L.num_tiles = n_tiles * m_tiles * L.splits;
   // TMA-store epilogue: single-output launches whose 32-column chunks tile N exactly.  fp32 output -> bulk tensor store; in-place fp32
-  // residual (hs += GEMM, no activation) -> bulk reduce-add at the L2; 16-bit output (also GEGLU) -> 16-bit tile store.  Statistics,
-  // space-to-depth, split-K, two outputs and out-of-place / 16-bit residuals keep the coalesced epilogue.  MADM_GEMM_TMA_EPI=0 disables.
+  // residual (hs += GEMM, no activation) -> bulk reduce-add at the L2; 16-bit output (also GEGLU) -> 16-bit tile store; fused GroupNorm
+  // column statistics ride along (EPI_TMA | EPI_STATS), except with the reduce-add, whose sums never enter the SM.  Space-to-depth,
+  // split-K, two outputs and out-of-place / 16-bit residuals keep the coalesced epilogue.  MADM_GEMM_TMA_EPI=0 disables.
   L.tma_epi = TMA_EPI_NONE;
   {
     const char* env = getenv("MADM_GEMM_TMA_EPI");
     const bool on = !env || atoi(env) != 0;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    const bool plain = on && L.bn >= 32 && L.splits == 1 && !d.colstats && d.s2d_W == 0 && d.N % 32 == 0 && (!d.bias || al16(d.bias)) &&
+    const bool plain = on && L.bn >= 32 && L.splits == 1 && d.s2d_W == 0 && d.N % 32 == 0 && (!d.bias || al16(d.bias)) &&
                        (!d.rowbias || (al16(d.rowbias) && (d.ld_rowbias ? d.ld_rowbias : d.N) % 4 == 0));
     if (plain && d.act == ACT_GEGLU) {
       if (al16(d.out_bf16) && d.ldo16 % 8 == 0) L.tma_epi = TMA_EPI_H16;
     } else if (plain && d.out_f32 && !d.out_bf16 && al16(d.out_f32) && d.ldo32 % 4 == 0) {
       if (!d.residual) L.tma_epi = TMA_EPI_F32;
-      else if (!d.res16 && d.residual == d.out_f32 && d.ldr == d.ldo32 && d.act == ACT_NONE) L.tma_epi = TMA_EPI_RED;
+      else if (!d.res16 && d.residual == d.out_f32 && d.ldr == d.ldo32 && d.act == ACT_NONE && !d.colstats) L.tma_epi = TMA_EPI_RED;
     } else if (plain && d.out_bf16 && !d.out_f32 && !d.residual && al16(d.out_bf16) && d.ldo16 % 8 == 0) {
       L.tma_epi = TMA_EPI_H16;
     }
@@ -1003,8 +1043,8 @@ static const char* launch_bn_s(const GemmLaunch& L, const GemmParams& p, cudaStr
 template <int BN, int MT, bool PAIR>
 static const char* launch_epi(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
   const int epi = (p.s2d_W > 0 ? EPI_S2D : 0) | (p.colstats ? EPI_STATS : 0);
-  if constexpr (BN >= 32) {
-    if (p.tma_epi) return launch_bn_s<BN, MT, EPI_TMA, PAIR>(L, p, stream);  // (only chosen for plain launches, see gemm_prepare)
+  if constexpr (BN >= 32) {  // (tma_epi is only chosen for launches without a space-to-depth output, see gemm_prepare)
+    if (p.tma_epi) return p.colstats ? launch_bn_s<BN, MT, EPI_TMA | EPI_STATS, PAIR>(L, p, stream) : launch_bn_s<BN, MT, EPI_TMA, PAIR>(L, p, stream);
   }
   switch (epi) {
     case 0: return launch_bn_s<BN, MT, 0, PAIR>(L, p, stream);

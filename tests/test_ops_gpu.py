@@ -164,6 +164,13 @@ def test_gemm_tma_store_epilogue_matches_coalesced(ops, cuda_device, monkeypatch
         o16 = torch.full((M, N + 32), 3.0, device=cuda_device, dtype=DT)
         ops.gemm([seg], M, N, w, bias=bias, out_bf16=o16, ldo16=N + 32, bn=bn, pair=pair)
         outs.append(o16)
+        if M % 32 == 0:  # fused GroupNorm column statistics next to either output kind
+            for kind in ("f32", "h16"):
+                cs = torch.full((M // 32, N, 2), float("nan"), device=cuda_device)
+                o = torch.empty(M, N, device=cuda_device, dtype=torch.float32 if kind == "f32" else DT)
+                kw = dict(out_f32=o, ldo32=N) if kind == "f32" else dict(out_bf16=o, ldo16=N)
+                ops.gemm([seg], M, N, w, bias=bias, colstats=cs, stat_rows=32, bn=bn, pair=pair, **kw)
+                outs += [o, cs]
         torch.cuda.synchronize()
         return outs
 
@@ -171,8 +178,14 @@ def test_gemm_tma_store_epilogue_matches_coalesced(ops, cuda_device, monkeypatch
     ref = run_all()
     monkeypatch.setenv("MADM_GEMM_TMA_EPI", "1")
     got = run_all()
-    for r_, g_ in zip(ref, got):
-        assert torch.equal(r_, g_)
+    for i, (r_, g_) in enumerate(zip(ref, got)):
+        if i >= 3 and i % 2 == 0:  # statistics: another (fixed) summation order
+            assert relerr(g_, r_) < 1e-5
+            o = got[i - 1].float() if got[i - 1].dtype == torch.float32 else None
+            if o is not None:
+                assert relerr(g_[..., 0], o.reshape(M // 32, 32, N).sum(1)) < 1e-4 and relerr(g_[..., 1], (o * o).reshape(M // 32, 32, N).sum(1)) < 1e-4
+        else:
+            assert torch.equal(r_, g_)
     assert relerr(got[0][:, :N], F.silu(a.float() @ w.float().t() + bias + (rowbias.repeat_interleave(HW, 0)[:M] if rowbias is not None else 0))) < 2e-3
     assert relerr(got[1][:, :N], 0.5 * (a.float() @ w.float().t()) + bias + res[:, :N]) < 2e-3
     assert torch.equal(got[1][:, N:], res[:, N:]) and bool((got[0][:, N:] == 7.0).all()) and bool((got[2][:, N:] == 3.0).all())
