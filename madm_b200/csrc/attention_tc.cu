@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
       const int kvalid = p.Nk - j * FA_BN;  // keys >= kvalid are masked (only the last tile can be ragged)
       const bool ragged = kvalid < FA_BN;
       float corr, rs = 0.f;
-      if constexpr (C::REG_S) {
+      if constexpr (C::REG_S && C::P_TMEM) {
         // whole score row -> registers (4 loads in flight, one wait), then hand the S buffer back to the MMA warp
         uint32_t sc[4][32];
         __syncwarp();
@@ -337,6 +337,89 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
           }
         }
         if constexpr (C::P_TMEM) { tmem_st_wait(); tc_fence_before(); }
+        rs += rs1;
+      } else if constexpr (C::REG_S) {
+        // d = 80 (P through shared memory): two TMEM passes.  Pass 1: row maximum, two quarters (64 columns) per round trip.  Pass 2
+        // re-reads the scores quarter by quarter (TMEM reads are cheap) instead of keeping all 128 next to the 80-column O accumulator:
+        // that spilled at the 168-register cap (measured: 74 -> 64 us per launch at n = 1024, B = 8).  For d = 40 the single-pass
+        // variant above stays faster (445 vs 480 us): it releases the only S buffer right after the load, so the next Q K^T overlaps.
+        uint32_t sa[32], sb2[32];
+        float mx0 = m_run, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          __syncwarp();
+          tmem_ld32(ts + hlf * 64, sa);
+          tmem_ld32(ts + hlf * 64 + 32, sb2);
+          tmem_ld_wait();
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (hlf * 64 + i >= kvalid) sa[i] = 0xff800000u;  // -inf
+              if (hlf * 64 + 32 + i >= kvalid) sb2[i] = 0xff800000u;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(sa[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(sa[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(sb2[i]));
+            mx3 = fmaxf(mx3, __uint_as_float(sb2[i + 1]));
+          }
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        corr = fa_ex2((m_run - mx) * sl);
+        m_run = mx;
+        const float ms = -mx * sl;
+        {  // every softmax thread observes V(j) before P(j) is posted, so the issuer needs no wait of its own on v_full
+          const int stage = j % C::STAGES;
+          mbar_wait(v_full(stage), (j / C::STAGES) & 1);
+          if constexpr (C::ONES) {  // (d = 40 with one query tile per CTA) V(j)[key = row][column D] = 1: the P V MMA accumulates the denominator
+            const uint32_t addr = sV + stage * C::KV_BYTES + uint32_t(D >> 6) * FA_TILE + uint32_t(row) * 128 +
+                                  uint32_t((((D & 63) >> 3) ^ (row & 7)) << 4) + uint32_t((D & 7) * 2);
+            const uint16_t one = FP16 ? 0x3C00 : 0x3F80;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(one) : "memory");
+          }
+        }
+        float rs1 = 0.f;
+        // Pass 2: p = 2^(s*c - m*c), quarter by quarter; the next quarter's scores are in flight while this one's exponentials run.
+        __syncwarp();
+        tmem_ld32(ts, sa);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t (&cur)[32] = (c & 1) ? sb2 : sa;
+          uint32_t (&nxt)[32] = (c & 1) ? sa : sb2;
+          tmem_ld_wait();
+          if (c < 3) {
+            __syncwarp();
+            tmem_ld32(ts + (c + 1) * 32, nxt);
+          } else {  // all of S(j) has been read: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty(g, sb));
+          }
+          if (ragged) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= kvalid) cur[i] = 0xff800000u;  // -inf -> p = 0
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fa_ex2(fmaf(__uint_as_float(cur[i]), sl, ms));
+            const float p1 = fa_ex2(fmaf(__uint_as_float(cur[i + 1]), sl, ms));
+            pk[i >> 1] = pack2_16(p0, p1, fp16);
+            if constexpr (!C::ONES) { rs += p0; rs1 += p1; }
+          }
+          if (c == 0 && j > 0) mbar_wait(pv_done(g), (j - 1) & 1);  // the first quarter is computed before the P buffer has to be free
+          const uint32_t chunk_base = sPg + uint32_t(c >> 1) * FA_TILE + uint32_t(row) * 128;
+          const int u0 = (c & 1) * 4;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t addr = chunk_base + uint32_t(((u0 + u) ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * u]), "r"(pk[4 * u + 1]), "r"(pk[4 * u + 2]),
+                         "r"(pk[4 * u + 3]) : "memory");
+          }
+        }
         rs += rs1;
       } else {
         // pass 1: row max
