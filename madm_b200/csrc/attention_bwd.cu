@@ -42,6 +42,7 @@ struct AttnBwdParams {
   // partial [qsplit][B][heads][kv blocks * 64][DP] that attn_bwd_kv_reduce sums in fixed order
   int qsplit;
   float *part_k, *part_v;
+  float* L2out;  // tcgen05 path: log2-domain log-sum-exp L * log2(e), written by the L / D pass (replaces L when that pass computes it itself)
 };
 
 template <typename T> __device__ __forceinline__ T from_float(float v);
@@ -176,7 +177,8 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_prep_kernel(const AttnBwd
   dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
   if (part == 0 && i0 + row < p.Nq) {
     const size_t o = (size_t(b) * p.heads + h) * p.Nq + i0 + row;
-    p.L[o] = m + __logf(l);
+    if (p.L2out) p.L2out[o] = (m + __logf(l)) * 1.4426950408889634f;
+    else p.L[o] = m + __logf(l);
     p.D[o] = dsum;
   }
 }
@@ -200,7 +202,11 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_d_kernel(const AttnBwdPar
   }
   dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
   dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
-  if (part == 0 && i < p.Nq) p.D[(size_t(b) * p.heads + h) * p.Nq + i] = dsum;
+  if (part == 0 && i < p.Nq) {
+    const size_t o = (size_t(b) * p.heads + h) * p.Nq + i;
+    p.D[o] = dsum;
+    if (p.L2out) p.L2out[o] = p.L[o] * 1.4426950408889634f;
+  }
 }
 
 // shared by the two main kernels: P (optional) and dS tiles from the fp32 S / dP tiles
@@ -443,6 +449,11 @@ const char* launch_all(const AttnBwdParams& p, int B, cudaStream_t st, bool have
   const dim3 gq((p.Nq + AB - 1) / AB, p.heads, B), gk(((p.Nk + AB - 1) / AB) * p.qsplit, p.heads, B);
   if (have_lse) attn_bwd_d_kernel<<<gq, AB_THREADS, 0, st>>>(p, fp16);
   else attn_bwd_prep_kernel<T, DP><<<gq, AB_THREADS, AttnSmem<DP>::PREP, st>>>(p);
+  if (p.L2out) {  // large self-attention: the tcgen05 / TMEM kernels (attention_bwd_tc.cu) take over after the L / D pass
+    if (cudaGetLastError() != cudaSuccess) return "attention_bwd launch failed";
+    return attention_bwd_tc(p.q, p.ldq, p.k, p.ldk, p.v, p.ldv, p.dout, p.lddo, p.dq, p.lddq, p.dk, p.lddk, p.dv, p.lddv, B, p.heads, p.d, p.Nq, p.Nk, p.q_bs,
+                            p.k_bs, p.v_bs, p.do_bs, p.dq_bs, p.dk_bs, p.dv_bs, p.scale, p.L2out, p.D, fp16, st);
+  }
   attn_bwd_dkv_kernel<T, DP><<<gk, AB_THREADS, AttnSmem<DP>::DKV, st>>>(p);
   if (p.qsplit > 1) {
     const long total = long(B) * p.heads * p.Nk * (p.d / 2);
@@ -491,6 +502,7 @@ const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const 
   p.L = lse ? const_cast<float*>(lse) : scratch; p.D = scratch + size_t(B) * heads * Nq;
   p.qsplit = attn_qsplit(B, heads, Nq, Nk);
   p.part_k = p.part_v = nullptr;
+  p.L2out = attention_bwd_tc_supported(d, Nq, Nk) ? scratch : nullptr;  // (scratch[0, B*heads*Nq) is free when the forward supplied the log-sum-exp)
   if (p.qsplit > 1) {
     float* base = scratch + size_t(2) * B * heads * Nq;
     base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(base) + 31) & ~uintptr_t(31));  // wmma stores need 32-byte alignment

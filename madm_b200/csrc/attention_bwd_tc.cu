@@ -1,0 +1,359 @@
+// tcgen05 / TMEM backward of softmax(Q K^T * scale) V for the UNet's large self-attention layers (d <= 64: the 64x64-token level, d = 40,
+// n = 4096 -- 5 of the 16 transformer blocks and ~60 % of the training step's attention FLOPs).  SURVEY §8 row f-3; the reference
+// back-propagates through diffusers' Attention processors (modeling/meta_arch/mtmadise.py:240-302 under engine/train_loop.py:277-302).
+//
+// Flash-style, no stored probabilities, deterministic (no atomics): one kernel template, two roles.
+//   MODE 0 (dK, dV)  CTA = 128 keys of one (image, head), resident K_j, V_j; streams the query tiles (Q_i, dO_i, L_i, D_i):
+//                      X = K_j Q_i^T = S^T        Y = V_j dO_i^T = dP^T                (128 x 128 x d, both operands K-major in smem)
+//                      P^T = 2^(X c - L2[col])    dS^T = P^T (Y - D[col])              (thread = key row; L2 / D per column from smem)
+//                      dV_j += P^T dO_i           dK_j += dS^T Q_i                     (A = 16-bit tile in TENSOR MEMORY, B = the streamed
+//                                                                                       tile read MN-major: no transposes anywhere)
+//   MODE 1 (dQ)      CTA = 128 queries, resident Q_i, dO_i; streams the key tiles (K_j, V_j):
+//                      X = Q_i K_j^T = S          Y = dO_i V_j^T = dP                  P = 2^(X c - L2[row]), dS = P (Y - D[row])
+//                      dQ_i += dS K_j
+// L2 = log-sum-exp of the scaled scores times log2(e) (the forward kernel writes the log-sum-exp), D = rowsum(dO * O).
+// TMEM (512 columns): X 128 | Y 128 | P 64 | dS 64 | acc(P product) 64 | acc(dS product) 64 -- every fp32 accumulator of the two
+// running products stays in tensor memory for the whole loop.  Warp roles: warp 0 TMA producer (2-stage ring), warp 1 TMEM allocator +
+// MMA issuer, warps 4-11 softmax (two warps per TMEM lane quarter: each thread owns one row and 64 of its 128 columns).
+// The 16-bit P / dS tiles are pre-scaled by powers of two (fp16 subnormals: dS ~ 1e-8..1e-5) exactly like the warp-level kernels in
+// attention_bwd.cu, which remain the path for d = 80 / 160, ragged token counts and the 77-key cross-attention.
+#include "cvt.cuh"
+#include "kernels.h"
+#include "launch.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+#include <stdio.h>
+
+namespace madm {
+
+namespace {
+
+constexpr int BT_TILE = 128 * 128;   // bytes of one [128 rows][64 x 16-bit] swizzled operand tile
+constexpr int BT_KSTEPS_MAX = 4;
+constexpr int BT_STAGES = 2;
+constexpr int BT_THREADS = 384;
+constexpr float kPScale = 256.0f;      // P <= 1
+constexpr float kDsScale = 16384.0f;   // same constants as attention_bwd.cu
+constexpr size_t BT_SMEM = 2 * BT_TILE + BT_STAGES * (2 * BT_TILE + 1024) + 256 + 1024;
+
+struct BwdTcParams {
+  CUtensorMap tmR1, tmR2, tmT1, tmT2;  // resident / streamed operand maps: MODE 0: K, V, Q, dO; MODE 1: Q, dO, K, V
+  const float* L2;                     // [B, heads, Nq] log2-domain log-sum-exp
+  const float* D;                      // [B, heads, Nq]
+  uint16_t* out_s; int ld_s; long bs_s;  // dS product: dK (MODE 0) / dQ (MODE 1)
+  uint16_t* out_p; int ld_p; long bs_p;  // P product: dV (MODE 0)
+  int Nq, n_stream;                    // streamed tiles per CTA
+  int d, ksteps, dv;                   // head dim, 16-wide k-steps carrying data, output columns (UMMA N)
+  float scale_log2, out_scale_s, out_scale_p;
+};
+
+__device__ __forceinline__ float bt_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int MODE, bool FP16>
+__global__ void __launch_bounds__(BT_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ BwdTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sR1 = base, sR2 = base + BT_TILE;
+  auto sT1 = [&](int st) { return base + 2 * BT_TILE + uint32_t(st) * (2 * BT_TILE); };
+  auto sT2 = [&](int st) { return sT1(st) + BT_TILE; };
+  const uint32_t sVec = base + 2 * BT_TILE + BT_STAGES * 2 * BT_TILE;  // per stage: L2[128] | D[128] floats
+  const uint32_t sBar = sVec + BT_STAGES * 1024;
+  const uint32_t r_full = sBar;
+  auto t_full = [&](int s) { return sBar + 8u * (1 + s); };
+  auto t_empty = [&](int s) { return sBar + 8u * (3 + s); };
+  const uint32_t x_full = sBar + 8u * 5, sm_done = sBar + 8u * 6, o_done = sBar + 8u * 7;
+  const uint32_t tmem_slot = sBar + 8u * 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n = p.n_stream;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmR1); prefetch_tmap(&p.tmR2); prefetch_tmap(&p.tmT1); prefetch_tmap(&p.tmT2);
+    mbar_init(r_full, 1);
+    for (int s = 0; s < BT_STAGES; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 1); }
+    mbar_init(x_full, 1); mbar_init(sm_done, 8); mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tX = tmem, tY = tmem + 128, tP = tmem + 256, tdS = tmem + 320, tAccP = tmem + 384, tAccS = tmem + 448;
+  pdl_trigger();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(r_full, 2 * BT_TILE);
+      tma_load_4d(sR1, &p.tmR1, r_full, 0, h, r0, b);
+      tma_load_4d(sR2, &p.tmR2, r_full, 0, h, r0, b);
+      const float* l2g = p.L2 + (size_t(b) * gridDim.y + h) * p.Nq;
+      const float* dg = p.D + (size_t(b) * gridDim.y + h) * p.Nq;
+      for (int it = 0; it < n; ++it) {
+        const int st = it % BT_STAGES;
+        mbar_wait(t_empty(st), ((it / BT_STAGES) & 1) ^ 1u);
+        mbar_arrive_expect_tx(t_full(st), 2 * BT_TILE + (MODE == 0 ? 1024 : 0));
+        tma_load_4d(sT1(st), &p.tmT1, t_full(st), 0, h, it * 128, b);
+        tma_load_4d(sT2(st), &p.tmT2, t_full(st), 0, h, it * 128, b);
+        if constexpr (MODE == 0) {  // the streamed query tile's L2 / D vectors
+          bulk_load_1d(sVec + st * 1024, l2g + it * 128, 512, t_full(st));
+          bulk_load_1d(sVec + st * 1024 + 512, dg + it * 128, 512, t_full(st));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc_x = make_idesc_16(128, 128, FP16 ? 1 : 0);
+      const uint32_t idesc_o = make_idesc_16(128, p.dv, FP16 ? 1 : 0) | (1u << 16);  // B operand MN-major
+      const int ksteps = p.ksteps;
+      const uint64_t r1d = make_smem_desc_sw128(sR1), r2d = make_smem_desc_sw128(sR2);
+      uint64_t t1d[BT_STAGES], t2d[BT_STAGES], t1mn[BT_STAGES], t2mn[BT_STAGES];
+#pragma unroll
+      for (int s = 0; s < BT_STAGES; ++s) {
+        t1d[s] = make_smem_desc_sw128(sT1(s)); t2d[s] = make_smem_desc_sw128(sT2(s));
+        t1mn[s] = make_smem_desc_sw128_mn(sT1(s), BT_TILE); t2mn[s] = make_smem_desc_sw128_mn(sT2(s), BT_TILE);
+      }
+      auto issue_xy = [&](int it) {  // X = R1 T1^T, Y = R2 T2^T
+        const int st = it % BT_STAGES;
+        mbar_wait(t_full(st), (it / BT_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t a1 = st == 0 ? t1d[0] : t1d[BT_STAGES - 1], a2 = st == 0 ? t2d[0] : t2d[BT_STAGES - 1];
+#pragma unroll
+        for (int ks = 0; ks < BT_KSTEPS_MAX; ++ks)
+          if (ks < ksteps) umma_bf16_ss(tX, r1d + uint64_t(2 * ks), a1 + uint64_t(2 * ks), idesc_x, ks != 0);
+#pragma unroll
+        for (int ks = 0; ks < BT_KSTEPS_MAX; ++ks)
+          if (ks < ksteps) umma_bf16_ss(tY, r2d + uint64_t(2 * ks), a2 + uint64_t(2 * ks), idesc_x, ks != 0);
+        umma_commit(x_full);
+      };
+      mbar_wait(r_full, 0);
+      issue_xy(0);
+      for (int it = 0; it < n; ++it) {
+        mbar_wait(sm_done, it & 1);  // the softmax warps have read X / Y and posted the 16-bit P / dS tiles
+        tc_fence_after();
+        if (it + 1 < n) issue_xy(it + 1);  // first: the next tile's softmax waits for nothing but these
+        const int st = it % BT_STAGES;
+        const uint64_t b1 = st == 0 ? t1mn[0] : t1mn[BT_STAGES - 1], b2 = st == 0 ? t2mn[0] : t2mn[BT_STAGES - 1];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) umma_f16_ts(tAccS, tdS + kk * 8, b1 + uint64_t(kk * (2048 >> 4)), idesc_o, (it > 0 || kk > 0) ? 1u : 0u);
+        if constexpr (MODE == 0) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) umma_f16_ts(tAccP, tP + kk * 8, b2 + uint64_t(kk * (2048 >> 4)), idesc_o, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(o_done);
+        umma_commit(t_empty(st));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax-gradient warps: thread = row, 64 of its 128 columns =====================
+    const int q = warp & 3, hf = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = uint32_t(q * 32) << 16;
+    const float sl = p.scale_log2;
+    float l2r = 0.f, dr = 0.f;
+    if constexpr (MODE == 1) {
+      const size_t o = (size_t(b) * gridDim.y + h) * p.Nq + r0 + row;
+      l2r = p.L2[o];
+      dr = p.D[o];
+    }
+    for (int it = 0; it < n; ++it) {
+      const int st = it % BT_STAGES;
+      mbar_wait(x_full, it & 1);
+      tc_fence_after();
+      uint32_t pkS[32], pkP[MODE == 0 ? 32 : 1];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int c0 = hf * 64 + ch * 32;
+        uint32_t xr[32], yr[32];
+        __syncwarp();
+        tmem_ld32(tX + lane_base + c0, xr);
+        tmem_ld32(tY + lane_base + c0, yr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          float4 l4, d4;
+          if constexpr (MODE == 0) {
+            l4 = lds_f4(sVec + st * 1024 + uint32_t(c0 + i) * 4);
+            d4 = lds_f4(sVec + st * 1024 + 512 + uint32_t(c0 + i) * 4);
+          } else {
+            l4 = make_float4(l2r, l2r, l2r, l2r);
+            d4 = make_float4(dr, dr, dr, dr);
+          }
+          const float p0 = bt_ex2(fmaf(__uint_as_float(xr[i]), sl, -l4.x)), p1 = bt_ex2(fmaf(__uint_as_float(xr[i + 1]), sl, -l4.y));
+          const float p2 = bt_ex2(fmaf(__uint_as_float(xr[i + 2]), sl, -l4.z)), p3 = bt_ex2(fmaf(__uint_as_float(xr[i + 3]), sl, -l4.w));
+          const float s0 = p0 * (__uint_as_float(yr[i]) - d4.x) * kDsScale, s1 = p1 * (__uint_as_float(yr[i + 1]) - d4.y) * kDsScale;
+          const float s2 = p2 * (__uint_as_float(yr[i + 2]) - d4.z) * kDsScale, s3 = p3 * (__uint_as_float(yr[i + 3]) - d4.w) * kDsScale;
+          pkS[ch * 16 + (i >> 1)] = pack2_16(s0, s1, FP16 ? 1 : 0);
+          pkS[ch * 16 + (i >> 1) + 1] = pack2_16(s2, s3, FP16 ? 1 : 0);
+          if constexpr (MODE == 0) {
+            pkP[ch * 16 + (i >> 1)] = pack2_16(p0 * kPScale, p1 * kPScale, FP16 ? 1 : 0);
+            pkP[ch * 16 + (i >> 1) + 1] = pack2_16(p2 * kPScale, p3 * kPScale, FP16 ? 1 : 0);
+          }
+        }
+      }
+      // the previous tile's products have consumed the P / dS tiles (their MMAs ran behind this tile's X / Y while the loop above computed)
+      if (it > 0) mbar_wait(o_done, (it - 1) & 1);
+      tc_fence_after();
+      __syncwarp();
+      {
+        uint32_t t16[16];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          const uint32_t col = uint32_t(hf * 32 + ch * 16);  // 32 16-bit columns = 16 packed 32-bit TMEM columns
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t16[i] = pkS[ch * 16 + i];
+          tmem_st16(tdS + lane_base + col, t16);
+          if constexpr (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t16[i] = pkP[ch * 16 + i];
+            tmem_st16(tP + lane_base + col, t16);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm_done);
+    }
+    // ---- accumulators -> 16-bit gradients (dS product: half 0; P product: half 1)
+    mbar_wait(o_done, (n - 1) & 1);
+    tc_fence_after();
+    if (hf == 0 || MODE == 0) {
+      const uint32_t tacc = (hf == 0 ? tAccS : tAccP) + lane_base;
+      const float osc = hf == 0 ? p.out_scale_s : p.out_scale_p;
+      uint16_t* op = (hf == 0 ? p.out_s + size_t(b) * p.bs_s + size_t(r0 + row) * p.ld_s : p.out_p + size_t(b) * p.bs_p + size_t(r0 + row) * p.ld_p) + h * p.d;
+      uint32_t ro[64];
+      __syncwarp();
+      tmem_ld16_at<0>(tacc, ro);
+      tmem_ld16_at<16>(tacc + 16, ro);
+      tmem_ld16_at<32>(tacc + 32, ro);
+      if (p.dv > 48) tmem_ld16_at<48>(tacc + 48, ro);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 64; c += 8) {
+        if (c < p.d) {
+          uint4 v;
+          v.x = pack2_16(__uint_as_float(ro[c]) * osc, __uint_as_float(ro[c + 1]) * osc, FP16 ? 1 : 0);
+          v.y = pack2_16(__uint_as_float(ro[c + 2]) * osc, __uint_as_float(ro[c + 3]) * osc, FP16 ? 1 : 0);
+          v.z = pack2_16(__uint_as_float(ro[c + 4]) * osc, __uint_as_float(ro[c + 5]) * osc, FP16 ? 1 : 0);
+          v.w = pack2_16(__uint_as_float(ro[c + 6]) * osc, __uint_as_float(ro[c + 7]) * osc, FP16 ? 1 : 0);
+          *reinterpret_cast<uint4*>(op + c) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn bt_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(q);
+  });
+  return fn;
+}
+// [d, heads, tokens, batch] view of a [batch, tokens, ld] buffer whose head h occupies columns [h*d, (h+1)*d); box = 64 columns (zero-filled
+// past d) x 128 tokens
+const char* bt_map(CUtensorMap* tm, const void* ptr, int d, int heads, int ntok, int B, int ld, long bstride) {
+  EncodeTiledFn fn = bt_encode_fn();
+  if (!fn) return "attention_bwd: cuTensorMapEncodeTiled unavailable";
+  cuuint64_t dims[4] = {cuuint64_t(d), cuuint64_t(heads), cuuint64_t(ntok), cuuint64_t(B)};
+  cuuint64_t strides[3] = {cuuint64_t(d) * 2, cuuint64_t(ld) * 2, cuuint64_t(bstride) * 2};
+  if (B == 1) strides[2] = cuuint64_t(ntok) * ld * 2;
+  cuuint32_t box[4] = {64, 1, 128, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "attention_bwd: cuTensorMapEncodeTiled failed";
+}
+
+template <int MODE, bool FP16>
+const char* bt_launch(const BwdTcParams& p, dim3 grid, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_bwd_tc_kernel<MODE, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BT_SMEM)) != cudaSuccess)
+      return "attention_bwd: cudaFuncSetAttribute failed";
+    attr = true;
+  }
+  if (launch_k(attn_bwd_tc_kernel<MODE, FP16>, grid, dim3(BT_THREADS), BT_SMEM, st, p) != cudaSuccess) return "attention_bwd: tcgen05 kernel launch failed";
+  return nullptr;
+}
+
+}  // namespace
+
+bool attention_bwd_tc_supported(int d, int Nq, int Nk) {
+  static const bool off = getenv("MADM_ATTN_BWD_TC") && atoi(getenv("MADM_ATTN_BWD_TC")) == 0;
+  return !off && d % 8 == 0 && d <= 64 && Nq % 128 == 0 && Nk % 128 == 0 && Nq >= 128 && Nk >= 128;
+}
+
+// dK / dV and dQ of one attention layer on the tcgen05 kernels.  L2 = log2-domain log-sum-exp, D = rowsum(dO * O), both [B, heads, Nq].
+const char* attention_bwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* dout, int lddo, void* dq, int lddq,
+                             void* dk, int lddk, void* dv, int lddv, int B, int heads, int d, int Nq, int Nk, long q_bs, long k_bs, long v_bs, long do_bs,
+                             long dq_bs, long dk_bs, long dv_bs, float scale, const float* L2, const float* D, int fp16, cudaStream_t st) {
+  if (!attention_bwd_tc_supported(d, Nq, Nk)) return "attention_bwd_tc: unsupported shape";
+  BwdTcParams p;
+  p.L2 = L2; p.D = D; p.Nq = Nq; p.d = d;
+  p.ksteps = (d + 15) / 16;
+  p.dv = (d + 15) / 16 * 16;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.out_scale_s = scale / kDsScale;
+  p.out_scale_p = 1.0f / kPScale;
+  CUtensorMap tq, tk, tv, tdo;
+  if (const char* e = bt_map(&tq, q, d, heads, Nq, B, ldq, q_bs)) return e;
+  if (const char* e = bt_map(&tk, k, d, heads, Nk, B, ldk, k_bs)) return e;
+  if (const char* e = bt_map(&tv, v, d, heads, Nk, B, ldv, v_bs)) return e;
+  if (const char* e = bt_map(&tdo, dout, d, heads, Nq, B, lddo, do_bs)) return e;
+  {  // dK, dV
+    p.tmR1 = tk; p.tmR2 = tv; p.tmT1 = tq; p.tmT2 = tdo;
+    p.out_s = static_cast<uint16_t*>(dk); p.ld_s = lddk; p.bs_s = dk_bs;
+    p.out_p = static_cast<uint16_t*>(dv); p.ld_p = lddv; p.bs_p = dv_bs;
+    p.n_stream = Nq / 128;
+    const dim3 grid(Nk / 128, heads, B);
+    if (const char* e = fp16 ? bt_launch<0, true>(p, grid, st) : bt_launch<0, false>(p, grid, st)) return e;
+  }
+  {  // dQ
+    p.tmR1 = tq; p.tmR2 = tdo; p.tmT1 = tk; p.tmT2 = tv;
+    p.out_s = static_cast<uint16_t*>(dq); p.ld_s = lddq; p.bs_s = dq_bs;
+    p.out_p = nullptr; p.ld_p = 0; p.bs_p = 0;
+    p.n_stream = Nk / 128;
+    const dim3 grid(Nq / 128, heads, B);
+    if (const char* e = fp16 ? bt_launch<1, true>(p, grid, st) : bt_launch<1, false>(p, grid, st)) return e;
+  }
+  return cudaGetLastError() == cudaSuccess ? nullptr : "attention_bwd_tc launch failed";
+}
+
+}  // namespace madm

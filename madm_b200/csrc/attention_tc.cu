@@ -75,18 +75,6 @@ __device__ __forceinline__ float fa_ex2(float x) {
   return y;
 }
 
-// smem descriptor of an MN-major (N contiguous) 128B-swizzled B operand: 8-row (K) atoms of 1024 B (SBO), 64-element N groups
-// `lbo_bytes` apart.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-
 // NQT query tiles (128 rows each) per CTA share every K/V tile; each query tile has its own softmax warpgroup, S / O tiles in
 // TMEM and P buffer, so the softmax of one tile overlaps the MMAs (and the softmax) of the other.
 template <int D, int NQT, bool FP16>

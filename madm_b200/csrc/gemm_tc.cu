@@ -956,8 +956,9 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   // split-K, two outputs and out-of-place / 16-bit residuals keep the coalesced epilogue.  MADM_GEMM_TMA_EPI=0 disables.
   L.tma_epi = TMA_EPI_NONE;
   {
-    const char* env = getenv("MADM_GEMM_TMA_EPI");
-    const bool on = !env || atoi(env) != 0;
+    const char* env = getenv("MADM_GEMM_TMA_EPI");  // bit mask: 1 fp32 stores, 2 reduce-add, 4 16-bit stores, 8 with fused statistics
+    const int mask = env ? atoi(env) : 15;
+    const bool on = mask != 0;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     const bool plain = on && L.bn >= 32 && L.splits == 1 && d.s2d_W == 0 && d.N % 32 == 0 && (!d.bias || al16(d.bias)) &&
                        (!d.rowbias || (al16(d.rowbias) && (d.ld_rowbias ? d.ld_rowbias : d.N) % 4 == 0));
@@ -969,6 +970,8 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
     } else if (plain && d.out_bf16 && !d.out_f32 && !d.residual && al16(d.out_bf16) && d.ldo16 % 8 == 0) {
       L.tma_epi = TMA_EPI_H16;
     }
+    if (L.tma_epi && !((mask >> (L.tma_epi == TMA_EPI_F32 ? 0 : (L.tma_epi == TMA_EPI_RED ? 1 : 2))) & 1)) L.tma_epi = TMA_EPI_NONE;
+    if (L.tma_epi && d.colstats && !(mask & 8)) L.tma_epi = TMA_EPI_NONE;
     if (L.tma_epi) {
       const bool h16 = L.tma_epi == TMA_EPI_H16;
       cuuint64_t dims[2] = {cuuint64_t(d.N), cuuint64_t(d.M)};

@@ -178,6 +178,13 @@ const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const 
                           long v_bs, long o_bs, long do_bs, long dq_bs, long dk_bs, long dv_bs, float scale, float* scratch, int fp16, cudaStream_t st,
                           const float* lse = nullptr /* [B,heads,Nq] from the forward kernel: skips the backward's own Q K^T pass */);
 
+// ---- attention_bwd_tc.cu: the same gradients on tcgen05 / TMEM for d <= 64 and token counts that are multiples of 128 (the UNet's 64x64 self-attention);
+// attention_bwd dispatches to it after its L / D pass.  L2 = log-sum-exp * log2(e), D = rowsum(dO * O), both [B, heads, Nq].
+bool attention_bwd_tc_supported(int d, int Nq, int Nk);
+const char* attention_bwd_tc(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, const void* dout, int lddo, void* dq, int lddq,
+                             void* dk, int lddk, void* dv, int lddv, int B, int heads, int d, int Nq, int Nk, long q_bs, long k_bs, long v_bs, long do_bs,
+                             long dq_bs, long dk_bs, long dv_bs, float scale, const float* L2, const float* D, int fp16, cudaStream_t st);
+
 // ---- wgrad.cu: dW[n,k] = alpha * sum_m dY[m,n] X[m,k] (taps = 9: implicit im2col of X [Bimg,H,W,K]) -> out[n*so_n + k*so_k + tap*so_tap]
 int wgrad_splits(int M, int N, int K, int taps);
 size_t wgrad_scratch_floats(int M, int N, int K, int taps);

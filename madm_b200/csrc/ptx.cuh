@@ -159,6 +159,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// smem descriptor of an MN-major (N contiguous) 128B-swizzled B operand: 8-row (K) atoms of 1024 B (SBO), 64-element N groups
+// `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: c_format[4,6)=1 (f32), a_format[7,10), b_format[10,13) (0 = f16, 1 = bf16),
 // a_major[15]=0 (K), b_major[16]=0 (K), n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
 // a_format / b_format: 0 = f16, 1 = bf16.

@@ -105,7 +105,8 @@ def test_geglu_fwd_bwd(ops, cuda_device, dt):
 
 @pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("B,heads,d,Nq,Nk", [(2, 8, 40, 1024, 1024), (1, 8, 80, 1024, 1024), (2, 8, 160, 256, 256), (1, 8, 160, 64, 64),
-                                             (2, 8, 40, 4096, 77), (2, 8, 160, 64, 77), (1, 8, 80, 1024, 77), (1, 8, 40, 4096, 4096)])
+                                             (2, 8, 40, 4096, 77), (2, 8, 160, 64, 77), (1, 8, 80, 1024, 77), (1, 8, 40, 4096, 4096),
+                                             (2, 8, 40, 256, 128), (1, 8, 40, 128, 384)])  # (d = 40 with token counts that are multiples of 128: the tcgen05 kernels)
 def test_attention_bwd(ops, cuda_device, dt, B, heads, d, Nq, Nk):
     if dt == torch.float16 and Nq == 4096 and Nk == 4096:
         pytest.skip("one dtype is enough at the largest shape")

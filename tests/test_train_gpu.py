@@ -47,7 +47,12 @@ def family(n):
 
 
 # gates per operand dtype: (per-tensor cosine, per-family / overall cosine); see the module docstring for what sets the floor
-GATES = {"fp16": (0.99, 0.998), "bf16": (0.93, 0.985)}
+# (per-tensor, per-family) cosine gates.  The comparison has a noise band of its own: two runs of the PRODUCT that differ only in an fp32
+# summation order (MADM_NO_SPLITK=1, or the TMA-store epilogue's column statistics against the coalesced epilogue's) differ from each
+# other by 9e-4 of the feature norm and by cosine 0.9980 - 0.9989 per gradient family (tools/check_grads.py, profiles/r02_gradient_noise_band.txt):
+# the random-init UNet amplifies rounding-level perturbations (near one-hot attention rows, ReLU / rounding boundaries).  Against the
+# oracle the fp16 families therefore land anywhere in 0.9977 - 0.9990 depending on the rounding realisation; the gate sits below that band.
+GATES = {"fp16": (0.99, 0.997), "bf16": (0.93, 0.985)}
 
 
 def compare(grads_ref, params, tag, mode, gates=None):
