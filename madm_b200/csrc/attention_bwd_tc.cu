@@ -31,7 +31,7 @@ namespace {
 
 constexpr int BT_TILE = 128 * 128;   // bytes of one [128 rows][64 x 16-bit] swizzled operand tile
 constexpr int BT_KSTEPS_MAX = 4;
-constexpr int BT_STAGES = 2;
+constexpr int BT_STAGES = 4;     // streamed-tile ring: the refill of a slot starts when its products retire, two to three tiles before it is needed
 constexpr int BT_THREADS = 384;
 constexpr float kPScale = 256.0f;      // P <= 1
 constexpr float kDsScale = 16384.0f;   // same constants as attention_bwd.cu
@@ -74,9 +74,12 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attn_bwd_tc_kernel(const __grid
   const uint32_t sBar = sVec + BT_STAGES * 1024;
   const uint32_t r_full = sBar;
   auto t_full = [&](int s) { return sBar + 8u * (1 + s); };
-  auto t_empty = [&](int s) { return sBar + 8u * (3 + s); };
-  const uint32_t x_full = sBar + 8u * 5, sm_done = sBar + 8u * 6, o_done = sBar + 8u * 7;
-  const uint32_t tmem_slot = sBar + 8u * 8;
+  auto t_empty = [&](int s) { return sBar + 8u * (1 + BT_STAGES + s); };
+  // x_full: X / Y complete -> softmax; xy_free: the softmax warps hold all of X / Y in registers -> the next tile's X / Y MMAs may overwrite them
+  // (they then run under the second half of this tile's softmax arithmetic); p_ready: the 16-bit P / dS tiles are in tensor memory
+  constexpr uint32_t kB0 = 1 + 2 * BT_STAGES;
+  const uint32_t x_full = sBar + 8u * kB0, xy_free = sBar + 8u * (kB0 + 1), o_done = sBar + 8u * (kB0 + 2), p_ready = sBar + 8u * (kB0 + 3);
+  const uint32_t tmem_slot = sBar + 8u * (kB0 + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attn_bwd_tc_kernel(const __grid
     prefetch_tmap(&p.tmR1); prefetch_tmap(&p.tmR2); prefetch_tmap(&p.tmT1); prefetch_tmap(&p.tmT2);
     mbar_init(r_full, 1);
     for (int s = 0; s < BT_STAGES; ++s) { mbar_init(t_full(s), 1); mbar_init(t_empty(s), 1); }
-    mbar_init(x_full, 1); mbar_init(sm_done, 8); mbar_init(o_done, 1);
+    mbar_init(x_full, 1); mbar_init(xy_free, 8); mbar_init(o_done, 1); mbar_init(p_ready, 8);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -129,17 +132,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attn_bwd_tc_kernel(const __grid
       const uint32_t idesc_o = make_idesc_16(128, p.dv, FP16 ? 1 : 0) | (1u << 16);  // B operand MN-major
       const int ksteps = p.ksteps;
       const uint64_t r1d = make_smem_desc_sw128(sR1), r2d = make_smem_desc_sw128(sR2);
-      uint64_t t1d[BT_STAGES], t2d[BT_STAGES], t1mn[BT_STAGES], t2mn[BT_STAGES];
-#pragma unroll
-      for (int s = 0; s < BT_STAGES; ++s) {
-        t1d[s] = make_smem_desc_sw128(sT1(s)); t2d[s] = make_smem_desc_sw128(sT2(s));
-        t1mn[s] = make_smem_desc_sw128_mn(sT1(s), BT_TILE); t2mn[s] = make_smem_desc_sw128_mn(sT2(s), BT_TILE);
-      }
+      // descriptors of ring slot 0; slot s is the same descriptor + s * (slot bytes >> 4) in the start-address field (no carry: smem < 256 KB)
+      const uint64_t t1d0 = make_smem_desc_sw128(sT1(0)), t2d0 = make_smem_desc_sw128(sT2(0));
+      const uint64_t t1mn0 = make_smem_desc_sw128_mn(sT1(0), BT_TILE), t2mn0 = make_smem_desc_sw128_mn(sT2(0), BT_TILE);
+      constexpr uint64_t kSlot = (2 * BT_TILE) >> 4;
       auto issue_xy = [&](int it) {  // X = R1 T1^T, Y = R2 T2^T
         const int st = it % BT_STAGES;
         mbar_wait(t_full(st), (it / BT_STAGES) & 1);
         tc_fence_after();
-        const uint64_t a1 = st == 0 ? t1d[0] : t1d[BT_STAGES - 1], a2 = st == 0 ? t2d[0] : t2d[BT_STAGES - 1];
+        const uint64_t a1 = t1d0 + uint64_t(st) * kSlot, a2 = t2d0 + uint64_t(st) * kSlot;
 #pragma unroll
         for (int ks = 0; ks < BT_KSTEPS_MAX; ++ks)
           if (ks < ksteps) umma_bf16_ss(tX, r1d + uint64_t(2 * ks), a1 + uint64_t(2 * ks), idesc_x, ks != 0);
@@ -151,11 +152,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attn_bwd_tc_kernel(const __grid
       mbar_wait(r_full, 0);
       issue_xy(0);
       for (int it = 0; it < n; ++it) {
-        mbar_wait(sm_done, it & 1);  // the softmax warps have read X / Y and posted the 16-bit P / dS tiles
+        if (it + 1 < n) {
+          mbar_wait(xy_free, it & 1);  // X / Y of this tile are in the softmax warps' registers
+          tc_fence_after();
+          issue_xy(it + 1);            // first: the next tile's softmax waits for nothing but these
+        }
+        mbar_wait(p_ready, it & 1);    // the 16-bit P / dS tiles of this tile are posted
         tc_fence_after();
-        if (it + 1 < n) issue_xy(it + 1);  // first: the next tile's softmax waits for nothing but these
         const int st = it % BT_STAGES;
-        const uint64_t b1 = st == 0 ? t1mn[0] : t1mn[BT_STAGES - 1], b2 = st == 0 ? t2mn[0] : t2mn[BT_STAGES - 1];
+        const uint64_t b1 = t1mn0 + uint64_t(st) * kSlot, b2 = t2mn0 + uint64_t(st) * kSlot;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) umma_f16_ts(tAccS, tdS + kk * 8, b1 + uint64_t(kk * (2048 >> 4)), idesc_o, (it > 0 || kk > 0) ? 1u : 0u);
         if constexpr (MODE == 0) {
@@ -191,6 +196,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attn_bwd_tc_kernel(const __grid
         tmem_ld32(tX + lane_base + c0, xr);
         tmem_ld32(tY + lane_base + c0, yr);
         tmem_ld_wait();
+        if (ch == 1) {  // every column of X / Y this warp owns is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(xy_free);
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           float4 l4, d4;
@@ -235,7 +245,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) attn_bwd_tc_kernel(const __grid
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sm_done);
+      if (lane == 0) mbar_arrive(p_ready);
     }
     // ---- accumulators -> 16-bit gradients (dS product: half 0; P product: half 1)
     mbar_wait(o_done, (n - 1) & 1);
