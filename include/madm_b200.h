@@ -384,6 +384,12 @@ int madm_op_attention_bwd(const void* q, int32_t ldq, const void* k, int32_t ldk
 int64_t madm_op_wgrad_scratch_floats(int32_t M, int32_t N, int32_t K, int32_t taps);
 int madm_op_wgrad(const void* dy16, int32_t lda, const void* x16, int32_t ldb, int32_t M, int32_t N, int32_t K, int32_t taps, int32_t Bimg, int32_t H,
                   int32_t W, float alpha, float* out, int32_t transpose_out, float* scratch, int32_t dtype, madm_stream stream);
+/* fused LoRA factor gradients of one rank-16 wrapped linear y = (W + s B A) x (the reference trains them through peft's Linear under autograd,
+ * modeling/meta_arch/mtmadise.py:115-147): gB [N,16] = alpha dY^T (X A^T), gA [16,K] = alpha (dY B)^T X; a16 = A [16,K], bt16 = B^T [16,N] in the
+ * operand dtype; N in {320,640,1280}, K in {320,640,768,1280}; scratch = madm_op_lora_grads_scratch_floats(M,N,K) floats; gA / gB may be null */
+int64_t madm_op_lora_grads_scratch_floats(int32_t M, int32_t N, int32_t K);
+int madm_op_lora_grads(const void* x16, int32_t ldx, const void* dy16, int32_t ldy, const void* a16, const void* bt16, int32_t M, int32_t N, int32_t K,
+                       float alpha, float* gA, float* gB, float* scratch, int32_t dtype, madm_stream stream);
 int madm_op_colsum_per_image(const void* x16, int32_t B, int32_t HW, int32_t C, float* out, int32_t ldo, int32_t dtype, madm_stream stream);
 int madm_op_zero_stuff2x(const void* x16, int32_t B, int32_t h, int32_t w, int32_t C, void* out16, madm_stream stream);
 int madm_op_sum2x2(const float* x, int32_t B, int32_t h, int32_t w, int32_t C, float* out, int32_t accumulate, madm_stream stream);

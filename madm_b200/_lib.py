@@ -155,6 +155,9 @@ SYMBOLS = {
     "madm_op_wgrad_scratch_floats": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "madm_op_wgrad": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, c_void_p,
                               c_int32, c_void_p, c_int32, c_void_p]),
+    "madm_op_lora_grads_scratch_floats": (c_int64, [c_int32, c_int32, c_int32]),
+    "madm_op_lora_grads": (c_int, [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p,
+                                   c_void_p, c_int32, c_void_p]),
     "madm_op_colsum_per_image": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
     "madm_op_zero_stuff2x": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "madm_op_sum2x2": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),

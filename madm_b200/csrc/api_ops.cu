@@ -275,6 +275,11 @@ int madm_op_wgrad(const void* dy16, int32_t lda, const void* x16, int32_t ldb, i
   RUN(wgrad(dy16, lda, x16, ldb, M, N, K, taps, Bimg, H, W, alpha, out, so_n, so_k, so_tap, scratch, dtype == MADM_DTYPE_FP16,
             static_cast<cudaStream_t>(stream)));
 }
+int64_t madm_op_lora_grads_scratch_floats(int32_t M, int32_t N, int32_t K) { return lora_grads_supported(N, K) ? int64_t(lora_grads_scratch_floats(M, N, K)) : -1; }
+int madm_op_lora_grads(const void* x16, int32_t ldx, const void* dy16, int32_t ldy, const void* a16, const void* bt16, int32_t M, int32_t N, int32_t K,
+                       float alpha, float* gA, float* gB, float* scratch, int32_t dtype, madm_stream stream) {
+  RUN(lora_grads(x16, ldx, dy16, ldy, a16, bt16, M, N, K, alpha, gA, gB, scratch, dtype == MADM_DTYPE_FP16, static_cast<cudaStream_t>(stream)));
+}
 int madm_op_colsum_per_image(const void* x16, int32_t B, int32_t HW, int32_t C, float* out, int32_t ldo, int32_t dtype, madm_stream stream) {
   RUN(colsum_per_image(x16, B, HW, C, dtype == MADM_DTYPE_FP16, out, ldo, static_cast<cudaStream_t>(stream)));
 }

@@ -1031,6 +1031,14 @@ struct Model {
     check_lora_rank(module);
     const float alpha = b.lora_scale / b.loss_scale;
     const int h16 = f16(), Mi = int(M);
+    static const bool fused_off = getenv("MADM_LORA_GRADS_FUSED") && atoi(getenv("MADM_LORA_GRADS_FUSED")) == 0;
+    if (!fused_off && lora_grads_supported(N, K)) {  // both factor gradients in one kernel + one reduce (wgrad.cu)
+      F32T scr = b.f32(lora_grads_scratch_floats(Mi, N, K));
+      const bf16* a16 = b.dpw(oa); const bf16* bt16 = b.dpw(ob); float* sp = scr.p;
+      b.emit([=](cudaStream_t st) { return lora_grads(X, ldx, dY, ldy, a16, bt16, Mi, N, K, alpha, gA, gB, sp, h16, st); });
+      b.free(scr);
+      return;
+    }
     if (gB) {
       B16T U = b.b16(size_t(M) * 16);
       { GemmDesc d; d.seg[0] = Builder::seg_plain(X, M, K, ldx); d.M = Mi; d.N = 16; d.Nw = 16; d.w = b.dpw(oa); d.out_bf16 = U.p; d.ldo16 = 16; d.bn = 16; b.gemm(d); }

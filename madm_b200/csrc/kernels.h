@@ -178,6 +178,13 @@ const char* attention_bwd(const void* q, int ldq, const void* k, int ldk, const 
                           long v_bs, long o_bs, long do_bs, long dq_bs, long dk_bs, long dv_bs, float scale, float* scratch, int fp16, cudaStream_t st,
                           const float* lse = nullptr /* [B,heads,Nq] from the forward kernel: skips the backward's own Q K^T pass */);
 
+// fused LoRA factor gradients of one rank-16 wrapped linear (wgrad.cu): gB [N,16] = alpha dY^T (X A^T), gA [16,K] = alpha (dY B)^T X;
+// a16 = lora_A [16,K], bt16 = lora_B^T [16,N] in the operand dtype; scratch = lora_grads_scratch_floats(M, N, K) floats
+bool lora_grads_supported(int N, int K);
+size_t lora_grads_scratch_floats(int M, int N, int K);
+const char* lora_grads(const void* x16, int ldx, const void* dy16, int ldy, const void* a16, const void* bt16, int M, int N, int K, float alpha, float* gA,
+                       float* gB, float* scratch, int fp16, cudaStream_t st);
+
 // ---- attention_bwd_tc.cu: the same gradients on tcgen05 / TMEM for d <= 64 and token counts that are multiples of 128 (the UNet's 64x64 self-attention);
 // attention_bwd dispatches to it after its L / D pass.  L2 = log-sum-exp * log2(e), D = rowsum(dO * O), both [B, heads, Nq].
 bool attention_bwd_tc_supported(int d, int Nq, int Nk);

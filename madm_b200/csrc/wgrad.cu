@@ -17,6 +17,10 @@ namespace {
 
 using namespace nvcuda;
 
+template <typename T> __device__ __forceinline__ T from_float_t(float v);
+template <> __device__ __forceinline__ __half from_float_t<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float_t<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
 constexpr int WG_TN = 64;   // output rows (columns of dY) per CTA
 constexpr int WG_MC = 64;   // pixels per smem chunk
 constexpr int WG_PAD = 8;
@@ -113,6 +117,165 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, 
   out[n * so_n + k * so_k + tap * so_tap] = alpha * s;
 }
 
+
+// ------------------------------------------------------------------------------------------------ LoRA factor gradients, fused
+// Both factor gradients of one LoRA-wrapped linear y = (W + s B A) x in ONE kernel (+ one reduce):
+//   U = X A^T  [M,16]     dB = s dY^T U  [N,16]            V = dY B  [M,16]     dA = s V^T X  [16,K]
+// The path used to be two skinny tcgen05 GEMMs, two weight-gradient kernels and two reduces per linear: 768 launches of 5-10 us per
+// training pass, 6.2 of its 32 ms.  Here a CTA owns a range of 64-row chunks of the pixel axis: per chunk it streams 64-column pieces
+// of X and dY through shared memory twice -- first for the two skinny products (warps 0-3: U, warps 4-7: V, 16-bit results kept in
+// shared memory), then for the two outer products, whose [N,16] / [K,16] fp32 accumulators live in registers across all chunks
+// (KP / NP pieces per warp, compile-time; four pieces = 256 columns are staged per round so a 1280-wide layer needs 5 + 5 rounds).
+// Every CTA writes its partial sums; lora_grad_reduce_kernel adds them in fixed order.
+struct LoraGradParams {
+  const uint16_t* x; int ldx;     // [M, K]
+  const uint16_t* dy; int ldy;    // [M, N]
+  const uint16_t* a16;            // [16, K] (lora_A, 16-bit)
+  const uint16_t* bt16;           // [16, N] (lora_B^T, 16-bit)
+  int M, chunks_per_cta;
+  float* part_b;                  // [ctas][N][16]
+  float* part_a;                  // [ctas][K][16]
+};
+
+constexpr int LG_W = 256;          // columns of X / dY staged per round (four 64-column pieces)
+constexpr int LG_LD = LG_W + 8;
+constexpr size_t LG_SMEM = size_t(2) * 64 * LG_LD * 2 + size_t(2) * 64 * 24 * 2 + size_t(8) * 16 * 20 * 4;
+
+template <typename T, int KP, int NP>
+__global__ void __launch_bounds__(256, 1) lora_grad_kernel(const LoraGradParams p) {
+  constexpr int K = 64 * KP, N = 64 * NP, PMAX = KP > NP ? KP : NP, ROUNDS = (PMAX + 3) / 4;
+  extern __shared__ __align__(128) unsigned char lg_smem[];
+  T (*Xs)[LG_LD] = reinterpret_cast<T (*)[LG_LD]>(lg_smem);
+  T (*Ys)[LG_LD] = reinterpret_cast<T (*)[LG_LD]>(lg_smem + size_t(64) * LG_LD * 2);
+  T (*UVs)[64][24] = reinterpret_cast<T (*)[64][24]>(lg_smem + size_t(2) * 64 * LG_LD * 2);       // [0] = U, [1] = V (16-bit)
+  float (*Fs)[16][20] = reinterpret_cast<float (*)[16][20]>(lg_smem + size_t(2) * 64 * LG_LD * 2 + size_t(2) * 64 * 24 * 2);  // per-warp fp32 staging
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int role = warp >> 2, t = warp & 3;  // role 0: U / dB (outer product with dY), role 1: V / dA (outer product with X)
+  constexpr int PO = 4 * ROUNDS;             // outer-product pieces a warp owns (N or K up to 1280: 20)
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[PO];
+#pragma unroll
+  for (int i = 0; i < PO; ++i) wmma::fill_fragment(acc[i], 0.0f);
+  const int c_begin = blockIdx.x * p.chunks_per_cta;
+  const int n_chunks = (p.M + 63) / 64;
+  const int c_end = min(n_chunks, c_begin + p.chunks_per_cta);
+
+  auto stage = [&](int m0, int rd) {  // columns [256 rd, 256 rd + 256) of X and dY (64 rows); rows past M / columns past K, N are zero
+    for (int i = threadIdx.x; i < 64 * (LG_W / 8); i += 256) {
+      const int r = i / (LG_W / 8), c8 = (i % (LG_W / 8)) * 8;
+      const int m = m0 + r, col = rd * LG_W + c8;
+      uint4 vx = make_uint4(0u, 0u, 0u, 0u), vy = vx;
+      if (m < p.M) {
+        if (col < K) vx = *reinterpret_cast<const uint4*>(p.x + size_t(m) * p.ldx + col);
+        if (col < N) vy = *reinterpret_cast<const uint4*>(p.dy + size_t(m) * p.ldy + col);
+      }
+      *reinterpret_cast<uint4*>(&Xs[r][c8]) = vx;
+      *reinterpret_cast<uint4*>(&Ys[r][c8]) = vy;
+    }
+  };
+
+  for (int ch = c_begin; ch < c_end; ++ch) {
+    const int m0 = ch * 64;
+    // ---- phase 1: U = X A^T (warps 0-3), V = dY B (warps 4-7); warp t owns rows [16t, 16t+16)
+    wmma::fragment<wmma::accumulator, 16, 16, 16, float> sk;
+    wmma::fill_fragment(sk, 0.0f);
+#pragma unroll 1
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      __syncthreads();
+      stage(m0, rd);
+      __syncthreads();
+      const T* src = role == 0 ? &Xs[16 * t][0] : &Ys[16 * t][0];
+      const int ldf = role == 0 ? K : N;
+      const T* fac = reinterpret_cast<const T*>(role == 0 ? p.a16 : p.bt16) + rd * LG_W;  // [16][K or N]: element (k, r) at fac[r * ld + k]
+      const int kend = min(LG_W, ldf - rd * LG_W);
+      for (int kk = 0; kk < kend; kk += 16) {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, T, wmma::row_major> fa;
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, T, wmma::col_major> fb;
+        wmma::load_matrix_sync(fa, src + kk, LG_LD);
+        wmma::load_matrix_sync(fb, fac + kk, ldf);
+        wmma::mma_sync(sk, fa, fb, sk);
+      }
+    }
+    wmma::store_matrix_sync(&Fs[warp][0][0], sk, 20, wmma::mem_row_major);
+    __syncwarp();
+    for (int i = lane; i < 256; i += 32) UVs[role][16 * t + (i >> 4)][i & 15] = from_float_t<T>(Fs[warp][i >> 4][i & 15]);
+    // ---- phase 2: dB += dY^T U (warps 0-3), dA^T += X^T V (warps 4-7); warp t owns output rows [64 pc + 16 t, +16) of every piece pc
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      __syncthreads();  // (also publishes U / V on the first pass)
+      stage(m0, rd);
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int pc = 4 * rd + j;
+        if (pc < (role == 0 ? NP : KP)) {
+          const T* src = role == 0 ? &Ys[0][64 * j + 16 * t] : &Xs[0][64 * j + 16 * t];  // transposed operand: element (n, m) at src[m * LG_LD + n]
+#pragma unroll
+          for (int kk = 0; kk < 64; kk += 16) {
+            wmma::fragment<wmma::matrix_a, 16, 16, 16, T, wmma::col_major> fa;
+            wmma::fragment<wmma::matrix_b, 16, 16, 16, T, wmma::row_major> fb;
+            wmma::load_matrix_sync(fa, src + kk * LG_LD, LG_LD);
+            wmma::load_matrix_sync(fb, &UVs[role][kk][0], 24);
+            wmma::mma_sync(acc[pc], fa, fb, acc[pc]);
+          }
+        }
+      }
+    }
+  }
+  float* dst = (role == 0 ? p.part_b + size_t(blockIdx.x) * N * 16 : p.part_a + size_t(blockIdx.x) * K * 16) + size_t(16 * t) * 16;
+#pragma unroll
+  for (int pc = 0; pc < PO; ++pc)
+    if (pc < (role == 0 ? NP : KP)) wmma::store_matrix_sync(dst + size_t(pc) * 64 * 16, acc[pc], 16, wmma::mem_row_major);
+}
+
+// gB[n*16 + r] = alpha * sum_c part_b[c][n][r]   ;   gA[r*K + k] = alpha * sum_c part_a[c][k][r]
+__global__ void lora_grad_reduce_kernel(const float* __restrict__ part_b, const float* __restrict__ part_a, int ctas, int N, int K, float alpha,
+                                        float* __restrict__ gB, float* __restrict__ gA) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N * 16) {
+    if (!gB) return;
+    float s = 0.f;
+    for (int c = 0; c < ctas; ++c) s += part_b[size_t(c) * N * 16 + i];
+    gB[i] = alpha * s;
+  } else if (i < (N + K) * 16) {
+    if (!gA) return;
+    const int j = i - N * 16, k = j >> 4, r = j & 15;
+    float s = 0.f;
+    for (int c = 0; c < ctas; ++c) s += part_a[size_t(c) * K * 16 + j];
+    gA[size_t(r) * K + k] = alpha * s;
+  }
+}
+
+template <typename T, int KP, int NP>
+const char* lora_grad_launch_kn(const LoraGradParams& p, int ctas, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(lora_grad_kernel<T, KP, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(LG_SMEM)) != cudaSuccess)
+      return "lora_grads: cudaFuncSetAttribute failed";
+    attr = true;
+  }
+  lora_grad_kernel<T, KP, NP><<<ctas, 256, LG_SMEM, st>>>(p);
+  return nullptr;
+}
+template <typename T, int KP>
+const char* lora_grad_launch_n(const LoraGradParams& p, int NPn, int ctas, cudaStream_t st) {
+  switch (NPn) {
+    case 5: return lora_grad_launch_kn<T, KP, 5>(p, ctas, st);
+    case 10: return lora_grad_launch_kn<T, KP, 10>(p, ctas, st);
+    case 20: return lora_grad_launch_kn<T, KP, 20>(p, ctas, st);
+  }
+  return "lora_grads: N must be 320, 640 or 1280";
+}
+template <typename T>
+const char* lora_grad_launch(const LoraGradParams& p, int KPn, int NPn, int ctas, cudaStream_t st) {
+  switch (KPn) {
+    case 5: return lora_grad_launch_n<T, 5>(p, NPn, ctas, st);
+    case 10: return lora_grad_launch_n<T, 10>(p, NPn, ctas, st);
+    case 12: return lora_grad_launch_n<T, 12>(p, NPn, ctas, st);
+    case 20: return lora_grad_launch_n<T, 20>(p, NPn, ctas, st);
+  }
+  return "lora_grads: K must be 320, 640, 768 or 1280";
+}
+
 }  // namespace
 
 int wgrad_splits(int M, int N, int K, int taps) {
@@ -149,6 +312,33 @@ const char* wgrad(const void* dy16, int lda, const void* x16, int ldb, int M, in
   const long per = long(taps) * N * K;
   wgrad_reduce_kernel<<<unsigned((per + 255) / 256), 256, 0, st>>>(scratch, splits, taps, N, K, alpha, out, so_n, so_k, so_tap);
   return cudaGetLastError() == cudaSuccess ? nullptr : "wgrad launch failed";
+}
+
+
+// ---- fused LoRA factor gradients (rank 16): gB [N,16] = alpha dY^T (X A^T), gA [16,K] = alpha (dY B)^T X; either output may be null
+static int lora_grad_ctas(int M) {
+  const int chunks = (M + 63) / 64;
+  return chunks < 148 ? chunks : 148;
+}
+bool lora_grads_supported(int N, int K) { return (N == 320 || N == 640 || N == 1280) && (K == 320 || K == 640 || K == 768 || K == 1280); }
+size_t lora_grads_scratch_floats(int M, int N, int K) { return size_t(lora_grad_ctas(M)) * 16 * (size_t(N) + K); }
+const char* lora_grads(const void* x16, int ldx, const void* dy16, int ldy, const void* a16, const void* bt16, int M, int N, int K, float alpha, float* gA,
+                       float* gB, float* scratch, int fp16, cudaStream_t st) {
+  if (!lora_grads_supported(N, K)) return "lora_grads: unsupported N / K";
+  if (ldx % 8 != 0 || ldy % 8 != 0 || ((reinterpret_cast<uintptr_t>(x16) | reinterpret_cast<uintptr_t>(dy16) | reinterpret_cast<uintptr_t>(a16) |
+                                         reinterpret_cast<uintptr_t>(bt16)) & 31))
+    return "lora_grads: operands must be 32-byte aligned with pitches that are multiples of 8";
+  LoraGradParams p;
+  p.x = static_cast<const uint16_t*>(x16); p.ldx = ldx; p.dy = static_cast<const uint16_t*>(dy16); p.ldy = ldy;
+  p.a16 = static_cast<const uint16_t*>(a16); p.bt16 = static_cast<const uint16_t*>(bt16);
+  p.M = M;
+  const int ctas = lora_grad_ctas(M), chunks = (M + 63) / 64;
+  p.chunks_per_cta = (chunks + ctas - 1) / ctas;
+  p.part_b = scratch; p.part_a = scratch + size_t(ctas) * N * 16;
+  const int used = (chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;  // CTAs that own at least one chunk (the others would write zeros)
+  if (const char* e = fp16 ? lora_grad_launch<__half>(p, K / 64, N / 64, used, st) : lora_grad_launch<__nv_bfloat16>(p, K / 64, N / 64, used, st)) return e;
+  lora_grad_reduce_kernel<<<((N + K) * 16 + 255) / 256, 256, 0, st>>>(p.part_b, p.part_a, used, N, K, alpha, gB, gA);
+  return cudaGetLastError() == cudaSuccess ? nullptr : "lora_grads launch failed";
 }
 
 }  // namespace madm

@@ -344,6 +344,26 @@ def wgrad(dy, x, N, K, *, taps=1, geom=(0, 0, 0), alpha=1.0, transpose_out=False
     return out
 
 
+def lora_grads(x, dy, A, B, alpha=1.0, M=None, ldx=None, ldy=None):
+    """Fused LoRA factor gradients of y = (W + s B A) x: returns (gA [16,K], gB [N,16]) = alpha * ((dY B)^T X, dY^T (X A^T)).
+    x [M,K], dy [M,N] 16-bit (row pitches ldx / ldy); A [16,K], B [N,16] fp32 or 16-bit (converted to the operand dtype here)."""
+    lib = _lib.load()
+    M = M if M is not None else x.shape[0]
+    K, N = A.shape[1], B.shape[0]
+    a16 = A.to(x.dtype).contiguous()
+    bt16 = B.t().to(x.dtype).contiguous()
+    gA = torch.empty(16, K, dtype=torch.float32, device=x.device)
+    gB = torch.empty(N, 16, dtype=torch.float32, device=x.device)
+    n = lib.madm_op_lora_grads_scratch_floats(M, N, K)
+    if n < 0:
+        raise ValueError(f"lora_grads: unsupported N / K ({N}, {K})")
+    scratch = torch.empty(n, dtype=torch.float32, device=x.device)
+    _lib.check(lib.madm_op_lora_grads(_ptr(x), ldx if ldx is not None else x.stride(0), _ptr(dy), ldy if ldy is not None else dy.stride(0), _ptr(a16),
+                                      _ptr(bt16), M, N, K, float(alpha), _ptr(gA), _ptr(gB), _ptr(scratch), _dt(x.dtype), _stream()), None,
+               "madm_op_lora_grads")
+    return gA, gB
+
+
 def colsum_per_image(x, out=None, col_off=0):
     lib = _lib.load()
     B, HW, Cc = x.shape

@@ -148,6 +148,28 @@ def test_attention_bwd(ops, cuda_device, dt, B, heads, d, Nq, Nk):
 
 
 @pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("M,N,K", [(8192, 320, 320), (154, 640, 768), (2048, 640, 640), (512, 1280, 1280), (154, 1280, 768), (1000, 320, 768), (16384, 320, 320)])
+def test_lora_grads_fused(ops, cuda_device, dt, M, N, K):
+    """Both LoRA factor gradients of one wrapped linear in one kernel (+ reduce): dB = s dY^T (X A^T), dA = s (dY B)^T X against fp32 matmuls of the
+    same 16-bit operands (the skinny products are rounded to 16 bits in between, as on the unfused path); dY / X are column slices of wider
+    buffers, M is ragged against the 64-row chunks, and more chunks than CTAs (M = 16384) exercise the per-CTA chunk loop."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    wide_y = torch.randn(M, N + 64, device=cuda_device, generator=g).to(dt)
+    wide_x = torch.randn(M, K + 128, device=cuda_device, generator=g).to(dt)
+    dy, x = wide_y[:, 64:], wide_x[:, 128:]
+    A = torch.randn(16, K, device=cuda_device, generator=g) / math.sqrt(K)
+    B = torch.randn(N, 16, device=cuda_device, generator=g) * 0.05
+    gA, gB = ops.lora_grads(x, dy, A, B, alpha=0.25)
+    a16, b16 = A.to(dt).float(), B.to(dt).float()
+    U = (x.float() @ a16.t()).to(dt).float()
+    V = (dy.float() @ b16).to(dt).float()
+    assert relerr(gB, 0.25 * dy.float().t() @ U) < 2e-3
+    assert relerr(gA, 0.25 * V.t() @ x.float()) < 2e-3
+    gA2, gB2 = ops.lora_grads(x, dy, A, B, alpha=0.25)
+    assert torch.equal(gA, gA2) and torch.equal(gB, gB2)  # deterministic
+
+
+@pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("M,N,K", [(8192, 320, 16), (154, 1280, 16), (2048, 640, 64), (32768, 512, 128), (8192, 128, 512), (100, 64, 64)])
 def test_wgrad_linear(ops, cuda_device, dt, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
