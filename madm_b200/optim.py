@@ -142,20 +142,18 @@ class FusedAdamW(torch.optim.Optimizer):
 def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None, average: bool = True) -> torch.Tensor:
     """The one collective of the training configuration: every rank contributes the gradients of ALL trainable
     parameters — zeros where a parameter took no part in this rank's step, e.g. the LoRA adapters that were not active
-    (``mtmadise.py:149-157``) — through ONE all-reduce (SUM, then / world) over a flat fp32 buffer.  Writes the averaged
-    gradients back into ``p.grad`` (allocating the zero ones) and returns the flat buffer.  NCCL on the GPU box, gloo in the tests."""
+    (``mtmadise.py:149-157``) — through ONE all-reduce (SUM, then / world) over a flat fp32 buffer.  Afterwards every
+    ``p.grad`` is a view into that buffer (zeros for the parameters that had no gradient); the flat buffer is returned.  NCCL on the GPU box, gloo in the tests."""
     import torch.distributed as dist
     params = [p for p in params if p.requires_grad]
     if not params:
         raise ValueError("allreduce_grads: no trainable parameters")
-    dev, total = params[0].device, sum(p.numel() for p in params)
-    flat = torch.zeros(total, dtype=torch.float32, device=dev)
-    off = 0
-    for p in params:
-        n = p.numel()
-        if p.grad is not None:
-            flat[off:off + n].copy_(p.grad.reshape(-1))
-        off += n
+    dev, sizes = params[0].device, [p.numel() for p in params]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+    views = [v.view_as(p) for v, p in zip(flat.split(sizes), params)]
+    have = [(v, p.grad) for v, p in zip(views, params) if p.grad is not None]
+    if have:  # one multi-tensor copy instead of one small kernel per parameter (567 tensors: 4 ms of launches per step)
+        torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
     world = 1
     if dist.is_available() and dist.is_initialized():
         world = dist.get_world_size(group)
@@ -163,13 +161,6 @@ def allreduce_grads(params: Iterable[torch.nn.Parameter], group=None, average: b
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average and world > 1:
         flat.div_(world)
-    off = 0
-    for p in params:
-        n = p.numel()
-        g = flat[off:off + n].view_as(p)
-        if p.grad is None:
-            p.grad = g.clone()
-        else:
-            p.grad.copy_(g)
-        off += n
+    for p, v in zip(params, views):  # the averaged gradients ARE the flat buffer: p.grad becomes a view of it (no copy back)
+        p.grad = v
     return flat
