@@ -318,7 +318,7 @@ def run_product(args, rank, local_rank, world):
     gn = prof["groupnorm"]
     gemm_traffic = None
     try:  # measured once under ncu for this build; null if the summary is not in the tree
-        with open(os.path.join(ROOT, "profiles", "r01_gemm_dram_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_gemm_dram_traffic.json")) as f:
             gemm_traffic = json.load(f)["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass
@@ -342,7 +342,7 @@ def run_product(args, rank, local_rank, world):
                  "VAE stream are excluded)",
         "executed_tflops": gemm["exec_flops"] / (gemm["ms"] / 1e3) / 1e12,
         "peak_source": peaks["source"] + ", sustained cuBLAS bf16 figure (kernel timed inside a long step)",
-        "traffic": gemm_traffic, "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r01_gemm_dram_traffic.json)",
+        "traffic": gemm_traffic, "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r02_gemm_dram_traffic.json)",
         "algorithmic_bytes_per_launch": gemm["bytes"] / max(1, gemm["launches"]),
         "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
         "algorithmic_gflop_per_launch": gemm["flops"] / max(1, gemm["launches"]) / 1e9,
