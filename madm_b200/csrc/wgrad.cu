@@ -133,13 +133,14 @@ struct LoraGradParams {
   const uint16_t* a16;            // [16, K] (lora_A, 16-bit)
   const uint16_t* bt16;           // [16, N] (lora_B^T, 16-bit)
   int M, chunks_per_cta;
+  int groups;                     // gridDim.y: the outer-product rounds are dealt round-robin to `groups` CTAs per chunk range (small M: few chunk ranges)
   float* part_b;                  // [ctas][N][16]
   float* part_a;                  // [ctas][K][16]
 };
 
 constexpr int LG_W = 256;          // columns of X / dY staged per round (four 64-column pieces)
 constexpr int LG_LD = LG_W + 8;
-constexpr size_t LG_SMEM = size_t(2) * 64 * LG_LD * 2 + size_t(2) * 64 * 24 * 2 + size_t(8) * 16 * 20 * 4;
+constexpr size_t LG_SMEM = size_t(2) * 64 * LG_LD * 2 + size_t(2) * 64 * 24 * 2 + size_t(8) * 16 * 20 * 4 + size_t(2) * 16 * LG_LD * 2;
 
 template <typename T, int KP, int NP>
 __global__ void __launch_bounds__(256, 1) lora_grad_kernel(const LoraGradParams p) {
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(256, 1) lora_grad_kernel(const LoraGradParams 
   T (*Ys)[LG_LD] = reinterpret_cast<T (*)[LG_LD]>(lg_smem + size_t(64) * LG_LD * 2);
   T (*UVs)[64][24] = reinterpret_cast<T (*)[64][24]>(lg_smem + size_t(2) * 64 * LG_LD * 2);       // [0] = U, [1] = V (16-bit)
   float (*Fs)[16][20] = reinterpret_cast<float (*)[16][20]>(lg_smem + size_t(2) * 64 * LG_LD * 2 + size_t(2) * 64 * 24 * 2);  // per-warp fp32 staging
+  T (*Fac)[16][LG_LD] = reinterpret_cast<T (*)[16][LG_LD]>(lg_smem + size_t(2) * 64 * LG_LD * 2 + size_t(2) * 64 * 24 * 2 + size_t(8) * 16 * 20 * 4);  // [0] = A, [1] = B^T: 256 columns
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int role = warp >> 2, t = warp & 3;  // role 0: U / dB (outer product with dY), role 1: V / dA (outer product with X)
   constexpr int PO = 4 * ROUNDS;             // outer-product pieces a warp owns (N or K up to 1280: 20)
@@ -159,7 +161,17 @@ __global__ void __launch_bounds__(256, 1) lora_grad_kernel(const LoraGradParams 
   const int n_chunks = (p.M + 63) / 64;
   const int c_end = min(n_chunks, c_begin + p.chunks_per_cta);
 
-  auto stage = [&](int m0, int rd) {  // columns [256 rd, 256 rd + 256) of X and dY (64 rows); rows past M / columns past K, N are zero
+  auto stage = [&](int m0, int rd, bool with_factors) {  // columns [256 rd, 256 rd + 256) of X and dY (64 rows); rows past M / columns past K, N are zero
+    if (with_factors) {  // the same columns of A [16,K] and B^T [16,N] (fragment loads from global memory are scattered 2-byte accesses)
+      for (int i = threadIdx.x; i < 2 * 16 * (LG_W / 8); i += 256) {
+        const int which = i / (16 * (LG_W / 8)), j = i % (16 * (LG_W / 8));
+        const int r = j / (LG_W / 8), c8 = (j % (LG_W / 8)) * 8, col = rd * LG_W + c8;
+        const int ld = which == 0 ? K : N;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (col < ld) v = *reinterpret_cast<const uint4*>((which == 0 ? p.a16 : p.bt16) + size_t(r) * ld + col);
+        *reinterpret_cast<uint4*>(&Fac[which][r][c8]) = v;
+      }
+    }
     for (int i = threadIdx.x; i < 64 * (LG_W / 8); i += 256) {
       const int r = i / (LG_W / 8), c8 = (i % (LG_W / 8)) * 8;
       const int m = m0 + r, col = rd * LG_W + c8;
@@ -181,17 +193,17 @@ __global__ void __launch_bounds__(256, 1) lora_grad_kernel(const LoraGradParams 
 #pragma unroll 1
     for (int rd = 0; rd < ROUNDS; ++rd) {
       __syncthreads();
-      stage(m0, rd);
+      stage(m0, rd, true);
       __syncthreads();
       const T* src = role == 0 ? &Xs[16 * t][0] : &Ys[16 * t][0];
       const int ldf = role == 0 ? K : N;
-      const T* fac = reinterpret_cast<const T*>(role == 0 ? p.a16 : p.bt16) + rd * LG_W;  // [16][K or N]: element (k, r) at fac[r * ld + k]
+      const T* fac = &Fac[role][0][0];  // [16][256 columns of K or N]: element (k, r) at fac[r * LG_LD + k]
       const int kend = min(LG_W, ldf - rd * LG_W);
       for (int kk = 0; kk < kend; kk += 16) {
         wmma::fragment<wmma::matrix_a, 16, 16, 16, T, wmma::row_major> fa;
         wmma::fragment<wmma::matrix_b, 16, 16, 16, T, wmma::col_major> fb;
         wmma::load_matrix_sync(fa, src + kk, LG_LD);
-        wmma::load_matrix_sync(fb, fac + kk, ldf);
+        wmma::load_matrix_sync(fb, fac + kk, LG_LD);
         wmma::mma_sync(sk, fa, fb, sk);
       }
     }
@@ -201,8 +213,9 @@ __global__ void __launch_bounds__(256, 1) lora_grad_kernel(const LoraGradParams 
     // ---- phase 2: dB += dY^T U (warps 0-3), dA^T += X^T V (warps 4-7); warp t owns output rows [64 pc + 16 t, +16) of every piece pc
 #pragma unroll
     for (int rd = 0; rd < ROUNDS; ++rd) {
+      if (rd % p.groups != int(blockIdx.y)) continue;  // (uniform per CTA) another CTA of this chunk range owns this round's output pieces
       __syncthreads();  // (also publishes U / V on the first pass)
-      stage(m0, rd);
+      stage(m0, rd, false);
       __syncthreads();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -224,7 +237,7 @@ __global__ void __launch_bounds__(256, 1) lora_grad_kernel(const LoraGradParams 
   float* dst = (role == 0 ? p.part_b + size_t(blockIdx.x) * N * 16 : p.part_a + size_t(blockIdx.x) * K * 16) + size_t(16 * t) * 16;
 #pragma unroll
   for (int pc = 0; pc < PO; ++pc)
-    if (pc < (role == 0 ? NP : KP)) wmma::store_matrix_sync(dst + size_t(pc) * 64 * 16, acc[pc], 16, wmma::mem_row_major);
+    if (pc < (role == 0 ? NP : KP) && (pc / 4) % p.groups == int(blockIdx.y)) wmma::store_matrix_sync(dst + size_t(pc) * 64 * 16, acc[pc], 16, wmma::mem_row_major);
 }
 
 // gB[n*16 + r] = alpha * sum_c part_b[c][n][r]   ;   gA[r*K + k] = alpha * sum_c part_a[c][k][r]
@@ -253,7 +266,7 @@ const char* lora_grad_launch_kn(const LoraGradParams& p, int ctas, cudaStream_t 
       return "lora_grads: cudaFuncSetAttribute failed";
     attr = true;
   }
-  lora_grad_kernel<T, KP, NP><<<ctas, 256, LG_SMEM, st>>>(p);
+  lora_grad_kernel<T, KP, NP><<<dim3(ctas, p.groups), 256, LG_SMEM, st>>>(p);
   return nullptr;
 }
 template <typename T, int KP>
@@ -336,6 +349,12 @@ const char* lora_grads(const void* x16, int ldx, const void* dy16, int ldy, cons
   p.chunks_per_cta = (chunks + ctas - 1) / ctas;
   p.part_b = scratch; p.part_a = scratch + size_t(ctas) * N * 16;
   const int used = (chunks + p.chunks_per_cta - 1) / p.chunks_per_cta;  // CTAs that own at least one chunk (the others would write zeros)
+  {  // few chunk ranges (16x16 / 8x8 levels, the 77-token context): split the outer-product rounds over up to 5 CTAs per range
+    const int rounds = ((K > N ? K : N) / 64 + 3) / 4;
+    int g = 148 / used;
+    if (g > rounds) g = rounds;
+    p.groups = g < 1 ? 1 : g;
+  }
   if (const char* e = fp16 ? lora_grad_launch<__half>(p, K / 64, N / 64, used, st) : lora_grad_launch<__nv_bfloat16>(p, K / 64, N / 64, used, st)) return e;
   lora_grad_reduce_kernel<<<((N + K) * 16 + 255) / 256, 256, 0, st>>>(p.part_b, p.part_a, used, N, K, alpha, gB, gA);
   return cudaGetLastError() == cudaSuccess ? nullptr : "lora_grads launch failed";
