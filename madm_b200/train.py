@@ -49,6 +49,7 @@ class TrainContext:
         self.grad_src = None
         self.grad_flat: Optional[torch.Tensor] = None
         self.grad_views: Dict[str, torch.Tensor] = {}
+        self.grad_slices: Dict[str, Tuple[int, int, Tuple[int, ...]]] = {}
 
     # ------------------------------------------------------------------ gradient buffers (one flat fp32 buffer, views per parameter)
     def ensure_grads(self, eng, named: Sequence[Tuple[str, torch.Tensor]]):
@@ -61,6 +62,7 @@ class TrainContext:
         total = sum(t.numel() for _, t in named)
         self.grad_flat = torch.zeros(total, dtype=torch.float32, device=eng.device)
         self.grad_views = {}
+        self.grad_slices = {}
         arr = (MadmTensor * len(named))()
         keep = [n.encode() for n, _ in named]
         off = 0
@@ -68,6 +70,7 @@ class TrainContext:
             v = self.grad_flat[off:off + t.numel()].view(t.shape)
             off += t.numel()
             self.grad_views[n] = v
+            self.grad_slices[n] = (off - t.numel(), t.numel(), tuple(t.shape))
             arr[i].name, arr[i].data, arr[i].ndim = keep[i], v.data_ptr(), t.dim()
             for k, s in enumerate(t.shape):
                 arr[i].shape[k] = s
@@ -199,7 +202,13 @@ class _ExtractFn(torch.autograd.Function):
             b.workspace, b.workspace_bytes = slot.ws.data_ptr(), slot.ws.numel()
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             _lib.check(eng.lib.madm_backward(eng.ctx, C.byref(b), st), eng.ctx, "madm_backward")
-            grads = [tc.grad_views[n].clone() for n in ctx.names]  # the flat buffer is overwritten by the next backward
+            # the flat buffer is overwritten by the next backward: ONE copy of it, the returned gradients are views of that copy
+            # (306 per-tensor clones were 306 small launches per pass)
+            snap = tc.grad_flat.clone()
+            grads = []
+            for n in ctx.names:
+                off, cnt, shape = tc.grad_slices[n]
+                grads.append(snap[off:off + cnt].view(shape))
         finally:
             slot.busy = False
         ci_shape, ce_shape = ctx.cond_shapes
