@@ -227,29 +227,39 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_apply_kernel(const void* __
     }
   }
   const int p0 = slab * slab_pix, p1 = min(HW, p0 + slab_pix);
-  for (int p = p0 + pl; p < p1; p += geo.P) {
-    const size_t pix = size_t(b) * HW + p;
+  for (int p = p0 + pl; p < p1; p += 2 * geo.P) {  // two pixels per trip: all their loads are issued before the arithmetic of either
+    const size_t pixs[2] = {size_t(b) * HW + p, size_t(b) * HW + p + geo.P};
+    const bool two = p + geo.P < p1;
 #pragma unroll
     for (int k = 0; k < kGnKMax; ++k) {
       const int v = tx + k * geo.TX;
       if (k < geo.K && v < cv) {
         const int c = 2 * v;
-        const float2 xv = gn_load_x<IN16>(x0, C0, x1, C1, pix, c, fp16);
-        const float2 dv = ld2_16(dy + pix * C + c, fp16);
-        const float xh0 = (xv.x - ch[k].mean[0]) * ch[k].rstd[0], xh1 = (xv.y - ch[k].mean[1]) * ch[k].rstd[1];
-        const float g0 = dv.x * act_grad(fmaf(xh0, ch[k].ga[0], ch[k].be[0]), act);
-        const float g1 = dv.y * act_grad(fmaf(xh1, ch[k].ga[1], ch[k].be[1]), act);
-        float r0 = ch[k].rstd[0] * (g0 * ch[k].ga[0] - c1[k][0] - xh0 * c2[k][0]);
-        float r1 = ch[k].rstd[1] * (g1 * ch[k].ga[1] - c1[k][1] - xh1 * c2[k][1]);
-        if (extra) { const float2 e = *reinterpret_cast<const float2*>(extra + pix * C + c); r0 += e.x; r1 += e.y; }
-        if (out16) st2_16(out16 + pix * C + c, r0, r1, fp16);
-        float* dst = nullptr; int accf = 0;
-        if (c < C0) { if (dx0) { dst = dx0 + pix * C0 + c; accf = acc0; } }
-        else if (dx1) { dst = dx1 + pix * C1 + (c - C0); accf = acc1; }
-        if (dst) {
-          float2 o = make_float2(r0, r1);
-          if (accf) { const float2 old = *reinterpret_cast<const float2*>(dst); o.x += old.x; o.y += old.y; }
-          *reinterpret_cast<float2*>(dst) = o;
+        float2 xv[2], dv[2], ev[2], ov[2];
+        float* dst[2] = {nullptr, nullptr};
+        int accf = 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u == 1 && !two) continue;
+          const size_t pix = pixs[u];
+          xv[u] = gn_load_x<IN16>(x0, C0, x1, C1, pix, c, fp16);
+          dv[u] = ld2_16(dy + pix * C + c, fp16);
+          ev[u] = extra ? *reinterpret_cast<const float2*>(extra + pix * C + c) : make_float2(0.f, 0.f);
+          if (c < C0) { if (dx0) { dst[u] = dx0 + pix * C0 + c; accf = acc0; } }
+          else if (dx1) { dst[u] = dx1 + pix * C1 + (c - C0); accf = acc1; }
+          ov[u] = (dst[u] && accf) ? *reinterpret_cast<const float2*>(dst[u]) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u == 1 && !two) continue;
+          const size_t pix = pixs[u];
+          const float xh0 = (xv[u].x - ch[k].mean[0]) * ch[k].rstd[0], xh1 = (xv[u].y - ch[k].mean[1]) * ch[k].rstd[1];
+          const float g0 = dv[u].x * act_grad(fmaf(xh0, ch[k].ga[0], ch[k].be[0]), act);
+          const float g1 = dv[u].y * act_grad(fmaf(xh1, ch[k].ga[1], ch[k].be[1]), act);
+          const float r0 = ch[k].rstd[0] * (g0 * ch[k].ga[0] - c1[k][0] - xh0 * c2[k][0]) + ev[u].x;
+          const float r1 = ch[k].rstd[1] * (g1 * ch[k].ga[1] - c1[k][1] - xh1 * c2[k][1]) + ev[u].y;
+          if (out16) st2_16(out16 + pix * C + c, r0, r1, fp16);
+          if (dst[u]) *reinterpret_cast<float2*>(dst[u]) = make_float2(r0 + ov[u].x, r1 + ov[u].y);
         }
       }
     }
