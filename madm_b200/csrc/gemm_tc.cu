@@ -37,7 +37,7 @@ static constexpr int STG_LD = 36;                   // floats per staging row (3
 static constexpr int TMA_TILE_BYTES = 4096;
 static constexpr int STG_WARP_BYTES = EPI_NBUF * TMA_TILE_BYTES > 5120 ? EPI_NBUF * TMA_TILE_BYTES : 5120;
 static_assert(STG_WARP_BYTES >= 32 * STG_LD * 4 && STG_WARP_BYTES % 1024 == 0, "staging");
-enum { TMA_EPI_NONE = 0, TMA_EPI_F32 = 1, TMA_EPI_RED = 2, TMA_EPI_H16 = 3 };
+enum { TMA_EPI_NONE = 0, TMA_EPI_F32 = 1, TMA_EPI_RED = 2, TMA_EPI_H16 = 3, TMA_EPI_RES_H16 = 4 };
 #ifndef EPI_BATCH
 #define EPI_BATCH 4
 #endif
@@ -45,6 +45,7 @@ enum { TMA_EPI_NONE = 0, TMA_EPI_F32 = 1, TMA_EPI_RED = 2, TMA_EPI_H16 = 3 };
 struct GemmParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB;
+  CUtensorMap tmR;   // TMA_EPI_RES_H16: the out-of-place fp32 residual (box 32 x 32, 128B swizzle), loaded per chunk into the warp's staging
   CUtensorMap tmO;   // output tensor map of the TMA-store epilogue (box 32 columns x 32 rows; fp32 with 128B swizzle or 16-bit with 64B swizzle)
   int tma_epi;       // TMA_EPI_*: 0 = coalesced-store epilogue, else the epilogue hands 32x32 tiles to cp(.reduce).async.bulk.tensor
   int nseg;
@@ -225,11 +226,11 @@ __device__ __forceinline__ void colstats_rows32(const float (&v)[32], int lane, 
 // the L2, so the residual never enters the SM.  No ld.shared, no per-thread global loads / stores: the serial chain per chunk is
 // tcgen05.ld -> FMAs -> st.shared -> fence -> issue, and the next chunk starts while the TMA engine drains this one.
 // `buf` toggles between the EPI_NBUF staging tiles; the elected lane (elect.sync is deterministic for a full mask) owns the bulk groups.
-template <bool H16>
+template <bool H16, bool WAIT = true>
 __device__ __forceinline__ void tma_epi_tile(const float (&v)[32], uint32_t stg, int& buf, int lane, const CUtensorMap* tm, int mode, int col, int row,
                                              int fp16) {
   const uint32_t sb = stg + uint32_t(buf) * TMA_TILE_BYTES;
-  if (elect_one()) bulk_wait_read<EPI_NBUF - 1>();  // the store that last used this buffer has read it
+  if constexpr (WAIT) { if (elect_one()) bulk_wait_read<EPI_NBUF - 1>(); }  // the store that last used this buffer has read it
   __syncwarp();
   if constexpr (H16) {  // 32 rows x 64 B, SWIZZLE_64B: 16-byte unit index ^= address bits [7,9) = (row >> 1) & 3
     const uint32_t rowp = sb + uint32_t(lane) * 64u;
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
   auto tmem_full_bar = [&](int a) { return sBar + 8u * (2 * C::STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return sBar + 8u * (2 * C::STAGES + 2 + a); };
   const uint32_t tmem_slot = sBar + 8u * (2 * C::STAGES + 4);
+  auto res_bar = [&](int w) { return sBar + 8u * (2 * C::STAGES + 5 + w); };  // one per epilogue warp (residual tile landed)
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -294,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (p.nseg > 1) prefetch_tmap(&p.tmA[1]);
     prefetch_tmap(&p.tmB);
     if (p.tma_epi) prefetch_tmap(&p.tmO);
+    if (p.tma_epi == TMA_EPI_RES_H16) prefetch_tmap(&p.tmR);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -302,6 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
       mbar_init(tmem_full_bar(a), 1);
       mbar_init(tmem_empty_bar(a), PAIR ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(res_bar(w), 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -471,6 +475,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     constexpr bool TMA = (EPI & EPI_TMA) != 0;  // separate instantiation: neither path pays for the other's live registers
     const int tma_epi = TMA ? p.tma_epi : 0;
     int tbuf = 0;
+    uint32_t res_phase = 0;
+    const uint32_t rbar = res_bar(warp - 2);
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t r[32];
@@ -582,8 +588,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
           if constexpr (TMA) {  // (N % 32 == 0 on this path: a chunk is either inside the matrix or entirely outside)
             if (n0 + c >= N) break;
             __syncwarp();
-            tmem_ld32(taddr + c, r);
             const int n = n0 + c;
+            if (tma_epi == TMA_EPI_RES_H16 && row0 < M) {  // the residual tile of this chunk: TMA load into staging tile 0 (its latency overlaps the TMEM load)
+              if (elect_one()) {
+                bulk_wait_read<0>();  // (also frees staging tile 1 of the previous chunk's store)
+                mbar_arrive_expect_tx(rbar, TMA_TILE_BYTES);
+                tma_load_2d(stg, &p.tmR, rbar, n, row0);
+              }
+              __syncwarp();
+            }
+            tmem_ld32(taddr + c, r);
             const float* rb = rowbias ? rowbias + size_t(min(row0, M - 1) / rows_per_img) * ld_rowbias + n : nullptr;
             float v[32];
 #pragma unroll
@@ -603,6 +617,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
               if (act == ACT_SILU) x = silu_f(x);
               else if (act == ACT_RELU) x = fmaxf(x, 0.f);
               v[j] = x;
+            }
+            if (tma_epi == TMA_EPI_RES_H16) {  // v += residual (swizzled staging tile 0, rows past M zero-filled by TMA) -> 16-bit tile in staging tile 1
+              if (row0 < M) {
+                mbar_wait(rbar, res_phase);
+                res_phase ^= 1u;
+                const uint32_t rowp = stg + uint32_t(lane) * 128u;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const float4 r4 = ld_shared_f4(rowp + ((uint32_t(u) ^ (uint32_t(lane) & 7u)) << 4));
+                  v[4 * u] += r4.x; v[4 * u + 1] += r4.y; v[4 * u + 2] += r4.z; v[4 * u + 3] += r4.w;
+                }
+                int one = 1;  // staging tile 1
+                tma_epi_tile<true, false>(v, stg, one, lane, &p.tmO, TMA_EPI_H16, n, row0, fp16);
+              }
+              continue;
             }
             if (row0 < M) {
               if (tma_epi == TMA_EPI_H16) tma_epi_tile<true>(v, stg, tbuf, lane, &p.tmO, tma_epi, n, row0, fp16);
@@ -956,8 +985,8 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
   // split-K, two outputs and out-of-place / 16-bit residuals keep the coalesced epilogue.  MADM_GEMM_TMA_EPI=0 disables.
   L.tma_epi = TMA_EPI_NONE;
   {
-    const char* env = getenv("MADM_GEMM_TMA_EPI");  // bit mask: 1 fp32 stores, 2 reduce-add, 4 16-bit stores, 8 with fused statistics
-    const int mask = env ? atoi(env) : 15;
+    const char* env = getenv("MADM_GEMM_TMA_EPI");  // bit mask: 1 fp32 stores, 2 reduce-add, 4 16-bit stores, 8 with fused statistics, 16 residual load + 16-bit store
+    const int mask = env ? atoi(env) : 31;
     const bool on = mask != 0;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     const bool plain = on && L.bn >= 32 && L.splits == 1 && d.s2d_W == 0 && d.N % 32 == 0 && (!d.bias || al16(d.bias)) &&
@@ -969,11 +998,20 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
       else if (!d.res16 && d.residual == d.out_f32 && d.ldr == d.ldo32 && d.act == ACT_NONE && !d.colstats) L.tma_epi = TMA_EPI_RED;
     } else if (plain && d.out_bf16 && !d.out_f32 && !d.residual && al16(d.out_bf16) && d.ldo16 % 8 == 0) {
       L.tma_epi = TMA_EPI_H16;
+    } else if (plain && d.out_bf16 && !d.out_f32 && d.residual && !d.res16 && !d.colstats && d.act == ACT_NONE && al16(d.out_bf16) && d.ldo16 % 8 == 0 &&
+               al16(d.residual) && d.ldr % 4 == 0 && EPI_NBUF >= 2) {
+      L.tma_epi = TMA_EPI_RES_H16;  // out16 = 16-bit(GEMM + fp32 residual), residual out of place: the transformer's FF out-projection
     }
-    if (L.tma_epi && !((mask >> (L.tma_epi == TMA_EPI_F32 ? 0 : (L.tma_epi == TMA_EPI_RED ? 1 : 2))) & 1)) L.tma_epi = TMA_EPI_NONE;
+    if (L.tma_epi && !((mask >> (L.tma_epi == TMA_EPI_F32 ? 0 : (L.tma_epi == TMA_EPI_RED ? 1 : (L.tma_epi == TMA_EPI_H16 ? 2 : 4)))) & 1)) L.tma_epi = TMA_EPI_NONE;
     if (L.tma_epi && d.colstats && !(mask & 8)) L.tma_epi = TMA_EPI_NONE;
+    if (L.tma_epi == TMA_EPI_RES_H16) {
+      cuuint64_t dims[2] = {cuuint64_t(d.N), cuuint64_t(d.M)};
+      cuuint64_t strides[1] = {cuuint64_t(d.ldr) * 4};
+      cuuint32_t box[2] = {32, 32};
+      if (const char* e = encode_map(&L.tmR, d.residual, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    }
     if (L.tma_epi) {
-      const bool h16 = L.tma_epi == TMA_EPI_H16;
+      const bool h16 = L.tma_epi == TMA_EPI_H16 || L.tma_epi == TMA_EPI_RES_H16;
       cuuint64_t dims[2] = {cuuint64_t(d.N), cuuint64_t(d.M)};
       cuuint64_t strides[1] = {h16 ? cuuint64_t(d.ldo16) * 2 : cuuint64_t(d.ldo32) * 4};
       cuuint32_t box[2] = {32, 32};
@@ -1075,6 +1113,7 @@ const char* gemm_launch(const GemmLaunch& L, cudaStream_t stream) {
   p.tmB = L.tmB;
   p.tma_epi = L.tma_epi;
   if (L.tma_epi) p.tmO = L.tmO; else p.tmO = L.tmB;
+  p.tmR = L.tma_epi == TMA_EPI_RES_H16 ? L.tmR : L.tmB;
   p.nseg = d.nseg;
   for (int s = 0; s < 2; ++s) {
     p.kchunks[s] = s < d.nseg ? L.kchunks[s] : 0;

@@ -56,7 +56,8 @@ struct GemmLaunch {  // prepared launch: tensor maps encoded once, replayed per 
   alignas(64) CUtensorMap tmA[2];
   alignas(64) CUtensorMap tmB;
   alignas(64) CUtensorMap tmO;  // output map of the TMA-store epilogue (valid when tma_epi != 0)
-  int tma_epi = 0;           // 0 coalesced-store epilogue, 1 fp32 bulk store, 2 fp32 bulk reduce-add (in-place residual), 3 16-bit bulk store
+  alignas(64) CUtensorMap tmR;  // residual map (tma_epi == 4)
+  int tma_epi = 0;           // 0 coalesced-store epilogue, 1 fp32 bulk store, 2 fp32 bulk reduce-add (in-place residual), 3 16-bit bulk store, 4 fp32 residual tile by TMA load + 16-bit bulk store
   GemmDesc d;
   int bn = 128;
   int kchunks[2] = {0, 0};   // 64-wide K chunks per segment

@@ -164,6 +164,9 @@ def test_gemm_tma_store_epilogue_matches_coalesced(ops, cuda_device, monkeypatch
         o16 = torch.full((M, N + 32), 3.0, device=cuda_device, dtype=DT)
         ops.gemm([seg], M, N, w, bias=bias, out_bf16=o16, ldo16=N + 32, bn=bn, pair=pair)
         outs.append(o16)
+        o16r = torch.full((M, N + 32), 3.0, device=cuda_device, dtype=DT)  # out-of-place fp32 residual, 16-bit output (the FF out-projection)
+        ops.gemm([seg], M, N, w, bias=bias, residual=res, ldr=N + 32, out_bf16=o16r, ldo16=N + 32, bn=bn, pair=pair)
+        outs.append(o16r)
         if M % 32 == 0:  # fused GroupNorm column statistics next to either output kind
             for kind in ("f32", "h16"):
                 cs = torch.full((M // 32, N, 2), float("nan"), device=cuda_device)
@@ -179,7 +182,7 @@ def test_gemm_tma_store_epilogue_matches_coalesced(ops, cuda_device, monkeypatch
     monkeypatch.setenv("MADM_GEMM_TMA_EPI", "1")
     got = run_all()
     for i, (r_, g_) in enumerate(zip(ref, got)):
-        if i >= 3 and i % 2 == 0:  # statistics: another (fixed) summation order
+        if i >= 4 and i % 2 == 1:  # statistics: another (fixed) summation order
             assert relerr(g_, r_) < 1e-5
             o = got[i - 1].float() if got[i - 1].dtype == torch.float32 else None
             if o is not None:
@@ -189,6 +192,7 @@ def test_gemm_tma_store_epilogue_matches_coalesced(ops, cuda_device, monkeypatch
     assert relerr(got[0][:, :N], F.silu(a.float() @ w.float().t() + bias + (rowbias.repeat_interleave(HW, 0)[:M] if rowbias is not None else 0))) < 2e-3
     assert relerr(got[1][:, :N], 0.5 * (a.float() @ w.float().t()) + bias + res[:, :N]) < 2e-3
     assert torch.equal(got[1][:, N:], res[:, N:]) and bool((got[0][:, N:] == 7.0).all()) and bool((got[2][:, N:] == 3.0).all())
+    assert relerr(got[3][:, :N], a.float() @ w.float().t() + bias + res[:, :N]) < 1e-2 and bool((got[3][:, N:] == 3.0).all())
 
 
 def test_gemm_geglu_tma_store_matches_coalesced(ops, cuda_device, monkeypatch):

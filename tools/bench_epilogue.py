@@ -20,17 +20,18 @@ for name, M, K, N, mode, stats in [("conv_in 2.1Mx128x64 h16", 2097152, 64, 128,
                                    ("32768x960x320 h16 (qkv)", 32768, 320, 960, "h16", False), ("32768x320x320 res plain", 32768, 320, 320, "res", False),
                                    ("8192x640x640 res plain", 8192, 640, 640, "res", False), ("2048x1280x1280 res plain", 2048, 1280, 1280, "res", False),
                                    ("32768x320x320 f32", 32768, 320, 320, "f32", False), ("8192x1920x640 h16 (qkv)", 8192, 640, 1920, "h16", False),
-                                   ("2.1Mx128x128 f32 plain", 2097152, 128, 128, "f32", False)]:
+                                   ("2.1Mx128x128 f32 plain", 2097152, 128, 128, "f32", False), ("32768x320x1280 res->h16 (ff out)", 32768, 1280, 320, "resh16", False),
+                                   ("8192x640x2560 res->h16 (ff out)", 8192, 2560, 640, "resh16", False), ("2048x1280x5120 res->h16 (ff out)", 2048, 5120, 1280, "resh16", False)]:
     if only and only not in name:
         continue
     x = torch.randn(M, K, device=dev).to(DT)
     w = (torch.randn(N, K, device=dev) * 0.05).to(DT)
-    o16 = torch.empty(M, N, device=dev, dtype=DT) if mode == "h16" else None
+    o16 = torch.empty(M, N, device=dev, dtype=DT) if mode in ("h16", "resh16") else None
     o32 = torch.randn(M, N, device=dev) if mode != "h16" else None
     cs = torch.empty((M + 31) // 32, N, 2, device=dev) if stats else None
     seg = ops.make_seg(x, 1, 1, M, K)
-    kw = dict(out_bf16=o16, ldo16=N) if mode == "h16" else dict(out_f32=o32, ldo32=N)
-    if mode == "res":
+    kw = dict(out_bf16=o16, ldo16=N) if mode in ("h16", "resh16") else dict(out_f32=o32, ldo32=N)
+    if mode in ("res", "resh16"):
         kw.update(residual=o32, ldr=N)
     run = lambda: ops.gemm([seg], M, N, w, colstats=cs, stat_rows=32 if stats else 0, **kw)
     run(); torch.cuda.synchronize()
