@@ -114,6 +114,7 @@ struct Plan {
   float loss_scale = 1.0f, lora_scale = 0.f;
   std::string adapter;
   std::vector<int> stage_of;  // stage bit per op
+  std::vector<int> branch;    // 0 = the caller's stream; 1..4 = independent projection branches (run on side streams, forked / joined by events)
   std::vector<char> optional; // debug/taps ops that launch only when the caller asks for the extra output
   std::vector<int> kind;      // MADM_KIND_* per op
   std::vector<double> flops;  // algorithmic FLOPs per op (2*MAC of the reference's convs / linears: no K padding, no identity segments)
@@ -139,6 +140,8 @@ struct madm_ctx {
   bool layout_done = false;
   float* alphas_cumprod = nullptr;  // [1000] device
   bool profiling = false;
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // projection branches (created on first use)
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   Plan* last_plan = nullptr;
   int last_stages = 0;
   std::map<std::tuple<int, int, int, int>, std::unique_ptr<Plan>> plans;  // (B, ema, head_h, head_w)
@@ -178,6 +181,9 @@ struct Builder {
   uint8_t* ws = nullptr;
   const uint8_t* packed = nullptr;
   int cur_stage = MADM_STAGE_VAE;
+  int cur_branch = 0;            // branch tag of the ops being emitted (build_proj)
+  bool defer_free = false;       // concurrent branches must not recycle each other's buffers: frees are collected and released at the join
+  std::vector<std::pair<size_t, size_t>> deferred;
   int n_ops = 0;
   int head_h = 0, head_w = 0;  // grid of the head's first feature map (0 = the 512 x 512 crop's: 128 x 128, s0 variant 512 x 512)
   // ---- training plans: the forward keeps what the backward needs; every builder function records its backward on
@@ -251,8 +257,10 @@ struct Builder {
     if (a.f.bytes) pinned.push_back(a.f.off);
     if (a.h.bytes) pinned.push_back(a.h.off);
   }
-  void free(F32T& t) { if (keep()) return; if (!is_pinned(t.off, t.bytes)) release(t.off, t.bytes); t.bytes = 0; t.p = nullptr; }
-  void free(B16T& t) { if (keep()) return; if (!is_pinned(t.off, t.bytes)) release(t.off, t.bytes); t.bytes = 0; t.p = nullptr; }
+  void release_or_defer(size_t off, size_t bytes) { if (defer_free) deferred.push_back({off, bytes}); else release(off, bytes); }
+  void flush_deferred() { for (auto& d : deferred) release(d.first, d.second); deferred.clear(); }
+  void free(F32T& t) { if (keep()) return; if (!is_pinned(t.off, t.bytes)) release_or_defer(t.off, t.bytes); t.bytes = 0; t.p = nullptr; }
+  void free(B16T& t) { if (keep()) return; if (!is_pinned(t.off, t.bytes)) release_or_defer(t.off, t.bytes); t.bytes = 0; t.p = nullptr; }
   void free(Act& a) { free(a.f); free(a.h); }
   Act act(int B_, int H, int W, int C, bool with_f32, bool with_b16) {
     Act a; a.B = B_; a.H = H; a.W = W; a.C = C;
@@ -444,6 +452,7 @@ struct Builder {
     if (mode == PLAN) {
       plan->ops.push_back(std::move(op));
       plan->stage_of.push_back(cur_stage);
+      plan->branch.push_back(cur_branch);
       plan->optional.push_back(optional ? 1 : 0);
       plan->kind.push_back(kind);
       plan->flops.push_back(flops);
@@ -1884,7 +1893,13 @@ struct Model {
     std::shared_ptr<IoBind> io = dry() ? nullptr : b.plan->io;
     const std::string root = b.ema ? "ema_feature_projections." : "feature_projections.";
     const Act* taps[4] = {&enc_tap, &unet_tap[0], &unet_tap[1], &unet_tap[2]};
+    // The four bottleneck projections are independent chains of small launches (1.0 ms of latency-bound kernels at B = 8): they are tagged as
+    // branches 1..4, madm_extract runs them on four side streams between a fork and a join event (inside a CUDA-graph capture: parallel graph
+    // branches), and their buffers are not recycled until the join.  MADM_PROJ_STREAMS=0 keeps them on the caller's stream.
+    static const bool proj_streams = !(getenv("MADM_PROJ_STREAMS") && atoi(getenv("MADM_PROJ_STREAMS")) == 0);
+    b.defer_free = proj_streams;
     for (int i = 0; i < 4; ++i) {
+      b.cur_branch = proj_streams ? 1 + i : 0;
       const Act& x = *taps[i];
       const std::string p = root + std::to_string(i) + ".0.";
       const ParamRef* w1 = b.find(p + "conv1.weight"); const ParamRef* w3 = b.find(p + "conv3.weight");
@@ -1983,6 +1998,9 @@ struct Model {
       if (shortcut && !rgb3) b.free(sc);
       if (rgb3) { b.free(mom); b.free(coef1); b.free(coefs); }
     }
+    b.cur_branch = 0;
+    b.defer_free = false;
+    b.flush_deferred();
   }
 
   // ---- DAFormerHead.forward (reference modeling/sem_seg_head/daformer_head.py:702-749) on the feature dict
@@ -2249,6 +2267,11 @@ int madm_create(madm_ctx** out, int device) {
 int madm_destroy(madm_ctx* ctx) {
   if (!ctx) return MADM_OK;
   if (ctx->alphas_cumprod) cudaFree(ctx->alphas_cumprod);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int k = 0; k < 4; ++k) {
+    if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
+    if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+  }
   delete ctx;
   return MADM_OK;
 }
@@ -2549,12 +2572,43 @@ int madm_extract(madm_ctx* ctx, const madm_extract_args* a, madm_stream stream) 
     for (cudaEvent_t& e : plan->ev)
       if (cudaEventCreate(&e) != cudaSuccess) return set_err(ctx, MADM_ECUDA, "cudaEventCreate failed");
   }
+  // Branch ops (the four projections) run on side streams between a fork and a join event unless per-launch profiling is on
+  // (its per-family accounting assumes one stream).
+  bool use_side = !prof;
+  if (use_side) {
+    bool any = false;
+    for (size_t i = 0; i < plan->ops.size() && !any; ++i) any = plan->branch[i] != 0 && (plan->stage_of[i] & a->stages) && plan->ops[i];
+    use_side = any;
+  }
+  if (use_side && !ctx->ev_fork) {
+    bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 4 && ok; ++k)
+      ok = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return set_err(ctx, MADM_ECUDA, "madm_extract: could not create the projection streams");
+  }
+  unsigned forked = 0;  // bit k: side stream k has work of this call
+  auto join = [&]() {
+    for (int k = 0; k < 4; ++k)
+      if (forked & (1u << k)) { cudaEventRecord(ctx->ev_join[k], ctx->side[k]); cudaStreamWaitEvent(st, ctx->ev_join[k], 0); }
+    forked = 0;
+  };
   for (size_t i = 0; i < plan->ops.size(); ++i) {
     if (!(plan->stage_of[i] & a->stages) || !plan->ops[i]) continue;
-    if (prof) cudaEventRecord(plan->ev[2 * i], st);
-    if (const char* e = plan->ops[i](st)) return set_err(ctx, MADM_ECUDA, std::string(e) + " (op " + std::to_string(i) + ")");
-    if (prof) cudaEventRecord(plan->ev[2 * i + 1], st);
+    const int br = use_side ? plan->branch[i] : 0;
+    cudaStream_t s = st;
+    if (br > 0) {
+      if (!forked) cudaEventRecord(ctx->ev_fork, st);  // everything the branches read has been enqueued on the caller's stream
+      if (!(forked & (1u << (br - 1)))) { cudaStreamWaitEvent(ctx->side[br - 1], ctx->ev_fork, 0); forked |= 1u << (br - 1); }
+      s = ctx->side[br - 1];
+    } else if (forked) {
+      join();  // back on the caller's stream: the branches' results are consumed from here on
+    }
+    if (prof) cudaEventRecord(plan->ev[2 * i], s);
+    if (const char* e = plan->ops[i](s)) { join(); return set_err(ctx, MADM_ECUDA, std::string(e) + " (op " + std::to_string(i) + ")"); }
+    if (prof) cudaEventRecord(plan->ev[2 * i + 1], s);
   }
+  join();
   ctx->last_plan = plan;
   ctx->last_stages = a->stages;
   return MADM_OK;
