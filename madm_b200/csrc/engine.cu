@@ -141,7 +141,7 @@ struct madm_ctx {
   float* alphas_cumprod = nullptr;  // [1000] device
   bool profiling = false;
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};  // projection branches (created on first use)
-  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork[4] = {nullptr, nullptr, nullptr, nullptr}, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   Plan* last_plan = nullptr;
   int last_stages = 0;
   std::map<std::tuple<int, int, int, int>, std::unique_ptr<Plan>> plans;  // (B, ema, head_h, head_w)
@@ -1791,6 +1791,7 @@ struct Model {
           unet_tap[t] = x;
           b.pin(x);
           nchw_debug(x, 1 + t);
+          build_proj_early(1 + t);  // this tap's projection can run beside the rest of the UNet
         }
         ++idx;
       }
@@ -1888,18 +1889,35 @@ struct Model {
   static const char* nchw_to_nhwc4(const float* src, int Bn, int HW, float* dst, cudaStream_t st);
 
   // =========================================================================== feature projections
+  // The four bottleneck projections are independent chains of small launches (1.0 ms of latency-bound kernels at B = 8).  Each is tagged as a
+  // branch (1..4) and emitted as soon as its tap exists -- the encoder tap's right after the VAE stage, the UNet taps' after up layers 5 / 8 / 11 --
+  // so madm_extract can run it on a side stream that forks there and joins at the end of the plan (inside a CUDA-graph capture: parallel graph
+  // branches): the projections fill the SMs the under-filled 16x16 / 8x8 UNet levels leave idle.  A branch's buffers are not recycled before the
+  // end of the plan.  MADM_PROJ_STREAMS=0 keeps everything on the caller's stream, in the old order (after the UNet).
+  bool proj_built[4] = {false, false, false, false};
+  static bool proj_streams() {
+    static const bool on = !(getenv("MADM_PROJ_STREAMS") && atoi(getenv("MADM_PROJ_STREAMS")) == 0);
+    return on;
+  }
+  void build_proj_early(int i) {  // called where tap i has just been produced
+    static const bool early = !(getenv("MADM_PROJ_EARLY") && atoi(getenv("MADM_PROJ_EARLY")) == 0);
+    if (early && proj_streams() && !s0() && !b.train) build_proj_one(i);
+  }
   void build_proj() {
+    for (int i = 0; i < 4; ++i) build_proj_one(i);
+    b.flush_deferred();
+  }
+  void build_proj_one(int i) {
+    if (proj_built[i]) return;
+    proj_built[i] = true;
+    const int saved_stage = b.cur_stage;
     b.cur_stage = MADM_STAGE_PROJ;
     std::shared_ptr<IoBind> io = dry() ? nullptr : b.plan->io;
     const std::string root = b.ema ? "ema_feature_projections." : "feature_projections.";
     const Act* taps[4] = {&enc_tap, &unet_tap[0], &unet_tap[1], &unet_tap[2]};
-    // The four bottleneck projections are independent chains of small launches (1.0 ms of latency-bound kernels at B = 8): they are tagged as
-    // branches 1..4, madm_extract runs them on four side streams between a fork and a join event (inside a CUDA-graph capture: parallel graph
-    // branches), and their buffers are not recycled until the join.  MADM_PROJ_STREAMS=0 keeps them on the caller's stream.
-    static const bool proj_streams = !(getenv("MADM_PROJ_STREAMS") && atoi(getenv("MADM_PROJ_STREAMS")) == 0);
-    b.defer_free = proj_streams;
-    for (int i = 0; i < 4; ++i) {
-      b.cur_branch = proj_streams ? 1 + i : 0;
+    b.defer_free = proj_streams();
+    {
+      b.cur_branch = proj_streams() ? 1 + i : 0;
       const Act& x = *taps[i];
       const std::string p = root + std::to_string(i) + ".0.";
       const ParamRef* w1 = b.find(p + "conv1.weight"); const ParamRef* w3 = b.find(p + "conv3.weight");
@@ -2000,7 +2018,7 @@ struct Model {
     }
     b.cur_branch = 0;
     b.defer_free = false;
-    b.flush_deferred();
+    b.cur_stage = saved_stage;
   }
 
   // ---- DAFormerHead.forward (reference modeling/sem_seg_head/daformer_head.py:702-749) on the feature dict
@@ -2133,6 +2151,7 @@ struct Model {
     if (has_path() || !has_head()) {  // a context that holds only sem_seg_head.* runs the head alone
       enumerate_unet();
       build_vae();
+      build_proj_early(0);  // the encoder tap's projection overlaps the whole UNet
       build_unet();
       if (s0()) build_dec();
       build_proj();
@@ -2267,8 +2286,8 @@ int madm_create(madm_ctx** out, int device) {
 int madm_destroy(madm_ctx* ctx) {
   if (!ctx) return MADM_OK;
   if (ctx->alphas_cumprod) cudaFree(ctx->alphas_cumprod);
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   for (int k = 0; k < 4; ++k) {
+    if (ctx->ev_fork[k]) cudaEventDestroy(ctx->ev_fork[k]);
     if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]);
     if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
   }
@@ -2580,10 +2599,11 @@ int madm_extract(madm_ctx* ctx, const madm_extract_args* a, madm_stream stream) 
     for (size_t i = 0; i < plan->ops.size() && !any; ++i) any = plan->branch[i] != 0 && (plan->stage_of[i] & a->stages) && plan->ops[i];
     use_side = any;
   }
-  if (use_side && !ctx->ev_fork) {
-    bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  if (use_side && !ctx->ev_fork[0]) {
+    bool ok = true;
     for (int k = 0; k < 4 && ok; ++k)
       ok = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ctx->ev_fork[k], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) return set_err(ctx, MADM_ECUDA, "madm_extract: could not create the projection streams");
   }
@@ -2598,11 +2618,14 @@ int madm_extract(madm_ctx* ctx, const madm_extract_args* a, madm_stream stream) 
     const int br = use_side ? plan->branch[i] : 0;
     cudaStream_t s = st;
     if (br > 0) {
-      if (!forked) cudaEventRecord(ctx->ev_fork, st);  // everything the branches read has been enqueued on the caller's stream
-      if (!(forked & (1u << (br - 1)))) { cudaStreamWaitEvent(ctx->side[br - 1], ctx->ev_fork, 0); forked |= 1u << (br - 1); }
+      if (!(forked & (1u << (br - 1)))) {  // fork here: everything this branch reads (its tap) has been enqueued on the caller's stream
+        cudaEventRecord(ctx->ev_fork[br - 1], st);
+        cudaStreamWaitEvent(ctx->side[br - 1], ctx->ev_fork[br - 1], 0);
+        forked |= 1u << (br - 1);
+      }
       s = ctx->side[br - 1];
-    } else if (forked) {
-      join();  // back on the caller's stream: the branches' results are consumed from here on
+    } else if (forked && (plan->stage_of[i] & MADM_STAGE_HEAD)) {
+      join();  // the head consumes the projections' outputs
     }
     if (prof) cudaEventRecord(plan->ev[2 * i], s);
     if (const char* e = plan->ops[i](s)) { join(); return set_err(ctx, MADM_ECUDA, std::string(e) + " (op " + std::to_string(i) + ")"); }
