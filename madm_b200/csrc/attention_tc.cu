@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
     const uint32_t tmem_p = tmem + lane_base + C::S_COLS + g * 64;
     const float sl = p.scale_log2;
     constexpr int fp16 = FP16 ? 1 : 0;
+    constexpr int OC = C::ONES ? D + 1 : D;  // live accumulator columns: the head dim (+ the denominator column); d = 40: 41 of the 48 MMA columns
     float o_acc[C::DV];
 #pragma unroll
     for (int i = 0; i < C::DV; ++i) o_acc[i] = 0.f;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(FaCfg<D, NQT>::THREADS, 1) fa_tc_kernel(const 
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < OB; ++i)
-          if (c0 + i < C::DV) o_acc[c0 + i] = fmaf(o_acc[c0 + i], corr, __uint_as_float(ro[i]));
+          if (c0 + i < OC) o_acc[c0 + i] = fmaf(o_acc[c0 + i], corr, __uint_as_float(ro[i]));  // (columns past OC are head-dim padding: never kept)
       }
       tc_fence_before();
     };
