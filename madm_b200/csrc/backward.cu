@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_apply_kernel(const void* __
 // one warp per row: dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)), g = dy; statistics recomputed from x
 constexpr int kLnMaxPerLane = 40;  // C <= 1280
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma, float eps,
-                                                     const uint16_t* __restrict__ dy, int fp16, float* __restrict__ dx, int accumulate) {
+                                                     const uint16_t* __restrict__ dy, int fp16, float* __restrict__ dx, int accumulate,
+                                                     uint16_t* __restrict__ dx16) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
       float2 o = make_float2(rstd * (gg[i] - s1 - xv[i] * s2), rstd * (gg[i + 1] - s1 - xv[i + 1] * s2));
       if (accumulate) { const float2 old = *reinterpret_cast<const float2*>(orow + c); o.x += old.x; o.y += old.y; }
       *reinterpret_cast<float2*>(orow + c) = o;
+      if (dx16) st2_16(dx16 + size_t(row) * C + c, o.x, o.y, fp16);  // the 16-bit operand copy of the updated gradient (next dgrad GEMM)
     }
   }
 }
@@ -477,9 +479,9 @@ const char* groupnorm_bwd(const void* x0, int C0, const void* x1, int C1, int B,
 }
 
 const char* layernorm_bwd(const float* x, int M, int C, const float* gamma, float eps, const void* dy16, int fp16, float* dx, int accumulate,
-                          cudaStream_t st) {
+                          cudaStream_t st, void* dx16) {
   if (C % 64 != 0 || C > 32 * kLnMaxPerLane) return "layernorm_bwd: C must be a multiple of 64, <= 1280";
-  ln_bwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, M, C, gamma, eps, static_cast<const uint16_t*>(dy16), fp16, dx, accumulate);
+  ln_bwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, M, C, gamma, eps, static_cast<const uint16_t*>(dy16), fp16, dx, accumulate, static_cast<uint16_t*>(dx16));
   return cudaGetLastError() == cudaSuccess ? nullptr : "layernorm_bwd launch failed";
 }
 

@@ -1245,8 +1245,7 @@ struct Model {
       auto ln_bwd = [&](const std::string& name, const float* xs) {  // dh += LayerNorm'(xs) dl ; dh16 = 16-bit(dh)
         const float* g = P(name + ".weight", C); const bf16* dy = dl.p; float* dst = dh.p; bf16* d16 = dh16.p;
         b.emit([=](cudaStream_t st) -> const char* {
-          if (const char* e = layernorm_bwd(xs, Mi, C, g, 1e-5f, dy, h16, dst, 1, st)) return e;
-          return f32_to_bf16(dst, nullptr, M * C, ACT_NONE, d16, nullptr, h16, st);
+          return layernorm_bwd(xs, Mi, C, g, 1e-5f, dy, h16, dst, 1, st, d16);  // (writes the 16-bit copy of dh as well)
         });
       };
       ln_bwd(tb + ".norm3", hs2.p);

@@ -156,7 +156,7 @@ const char* groupnorm_bwd(const void* x0, int C0, const void* x1, int C1, int B,
                           float affine_scale, cudaStream_t st);
 // LayerNorm backward over rows of x fp32 [M,C] (statistics recomputed): dx stored or accumulated (fp32)
 const char* layernorm_bwd(const float* x, int M, int C, const float* gamma, float eps, const void* dy16, int fp16, float* dx, int accumulate,
-                          cudaStream_t st);
+                          cudaStream_t st, void* dx16 = nullptr /* optional 16-bit copy of the updated dx */);
 // GEGLU in natural column order: raw16 [M, 2H] = (hidden | gate) -> out16 [M,H] = hidden * gelu(gate); backward -> draw16 [M, 2H]
 const char* geglu_fwd(const void* raw16, long M, int H, void* out16, int fp16, cudaStream_t st);
 const char* geglu_bwd(const void* raw16, const void* dout16, long M, int H, void* draw16, int fp16, cudaStream_t st);
