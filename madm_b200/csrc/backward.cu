@@ -6,6 +6,8 @@
 #include "cvt.cuh"
 #include "kernels.h"
 
+#include <cooperative_groups.h>
+
 namespace madm {
 
 namespace {
@@ -359,25 +361,43 @@ __global__ void geglu_bwd_kernel(const uint16_t* __restrict__ raw, const uint16_
 }
 
 // ------------------------------------------------------------------------------------------------ small data-movement kernels
-// per-image column sums of a 16-bit [B, HW, C] tensor -> out[b * ldo + c] (fp32): the gradient of a per-image row bias (time embedding)
+// per-image column sums of a 16-bit [B, HW, C] tensor -> out[b * ldo + c] (fp32): the gradient of a per-image row bias (time embedding).
+// A thread-block cluster of S CTAs (gridDim.z = cluster dim z) splits the pixel axis; rank 0 adds the S partial sums in rank order through
+// distributed shared memory (deterministic, no atomics, no second launch).  At 2 images the unsplit version ran on B * C/64 = 10 CTAs.
 __global__ void __launch_bounds__(256) colsum_img_kernel(const uint16_t* __restrict__ x, int HW, int C, int fp16, float* __restrict__ out, int ldo) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int S = int(cluster.num_blocks()), slab = int(cluster.block_rank());
   const int b = blockIdx.y;
   const int cp = blockIdx.x * 32 + (threadIdx.x & 31);  // channel pair
   const int pl = threadIdx.x >> 5;                        // 8 pixel lanes
+  const int per = (HW + S - 1) / S;
+  const int p0 = slab * per, p1 = min(HW, p0 + per);
   float a0 = 0.f, a1 = 0.f;
   if (2 * cp < C)
-    for (int p = pl; p < HW; p += 8) {
+    for (int p = p0 + pl; p < p1; p += 8) {
       const float2 v = ld2_16(x + (size_t(b) * HW + p) * C + 2 * cp, fp16);
       a0 += v.x; a1 += v.y;
     }
   __shared__ float red[256 * 2];
+  __shared__ float tot[64];
   red[threadIdx.x * 2] = a0; red[threadIdx.x * 2 + 1] = a1;
   __syncthreads();
-  if (pl == 0 && 2 * cp < C) {
+  if (pl == 0) {
     float s0 = 0.f, s1 = 0.f;
-    for (int q = 0; q < 8; ++q) { s0 += red[(q * 32 + (threadIdx.x & 31)) * 2]; s1 += red[(q * 32 + (threadIdx.x & 31)) * 2 + 1]; }
+    for (int q = 0; q < 8; ++q) { s0 += red[(q * 32 + threadIdx.x) * 2]; s1 += red[(q * 32 + threadIdx.x) * 2 + 1]; }
+    tot[threadIdx.x * 2] = s0; tot[threadIdx.x * 2 + 1] = s1;
+  }
+  cluster.sync();  // every CTA's totals are in its shared memory
+  if (slab == 0 && pl == 0 && 2 * cp < C) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = 0; r < S; ++r) {
+      const float* t = cluster.map_shared_rank(tot, r);
+      s0 += t[threadIdx.x * 2]; s1 += t[threadIdx.x * 2 + 1];
+    }
     out[size_t(b) * ldo + 2 * cp] = s0; out[size_t(b) * ldo + 2 * cp + 1] = s1;
   }
+  cluster.sync();  // keep the peers' shared memory alive until rank 0 has read it
 }
 
 // 16-bit [B,h,w,C] -> [B,2h,2w,C] with the values at the even positions and zeros elsewhere (operand of a stride-2 conv's dgrad)
@@ -501,7 +521,19 @@ const char* geglu_bwd(const void* raw16, const void* dout16, long M, int H, void
 
 const char* colsum_per_image(const void* x16, int B, int HW, int C, int fp16, float* out, int ldo, cudaStream_t st) {
   if (C % 2 != 0) return "colsum_per_image: C must be even";
-  colsum_img_kernel<<<dim3((C / 2 + 31) / 32, B), 256, 0, st>>>(static_cast<const uint16_t*>(x16), HW, C, fp16, out, ldo);
+  int S = 8;  // cluster size (portable maximum): fewer slabs for small pixel counts
+  while (S > 1 && HW < 64 * S) S >>= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((C / 2 + 31) / 32, B, S);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = S;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, colsum_img_kernel, static_cast<const uint16_t*>(x16), HW, C, fp16, out, ldo) != cudaSuccess)
+    return "colsum_per_image launch failed";
   return cudaGetLastError() == cudaSuccess ? nullptr : "colsum_per_image launch failed";
 }
 
