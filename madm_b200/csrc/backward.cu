@@ -271,19 +271,22 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_apply_kernel(const void* __
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
 // one warp per row: dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)), g = dy; statistics recomputed from x
 constexpr int kLnMaxPerLane = 40;  // C <= 1280
+// PER = C / 32 elements per lane (10 / 20 / 40 for C = 320 / 640 / 1280): compile-time, so the row lives in exactly PER registers (a runtime bound
+// made every launch pay for the 1280-channel case: 80 live values, 2 CTAs per SM)
+template <int PER>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma, float eps,
                                                      const uint16_t* __restrict__ dy, int fp16, float* __restrict__ dx, int accumulate,
                                                      uint16_t* __restrict__ dx16) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const int per = C / 32;  // C % 64 == 0: every lane owns `per` (even) elements, interleaved in pairs for coalescing
+  constexpr int per = PER;  // C % 64 == 0: every lane owns `per` (even) elements, interleaved in pairs for coalescing
   const float* xr = x + size_t(row) * C;
   const uint16_t* dr = dy + size_t(row) * C;
-  float xv[kLnMaxPerLane];
+  float xv[PER];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; i += 2) {
+  for (int i = 0; i < PER; i += 2) {
     if (i < per) {
       const float2 t = *reinterpret_cast<const float2*>(xr + (i / 2) * 64 + lane * 2);
       xv[i] = t.x; xv[i + 1] = t.y;
@@ -295,15 +298,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
   const float mean = s / float(C);
   float vs = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; ++i)
+  for (int i = 0; i < PER; ++i)
     if (i < per) { const float d = xv[i] - mean; vs = fmaf(d, d, vs); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
   const float rstd = rsqrtf(vs / float(C) + eps);
-  float gg[kLnMaxPerLane];
+  float gg[PER];
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; i += 2) {
+  for (int i = 0; i < PER; i += 2) {
     if (i < per) {
       const int c = (i / 2) * 64 + lane * 2;
       const float2 d = ld2_16(dr + c, fp16);
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
   s1 /= float(C); s2 /= float(C);
   float* orow = dx + size_t(row) * C;
 #pragma unroll
-  for (int i = 0; i < kLnMaxPerLane; i += 2) {
+  for (int i = 0; i < PER; i += 2) {
     if (i < per) {
       const int c = (i / 2) * 64 + lane * 2;
       float2 o = make_float2(rstd * (gg[i] - s1 - xv[i] * s2), rstd * (gg[i + 1] - s1 - xv[i + 1] * s2));
@@ -501,7 +504,17 @@ const char* groupnorm_bwd(const void* x0, int C0, const void* x1, int C1, int B,
 const char* layernorm_bwd(const float* x, int M, int C, const float* gamma, float eps, const void* dy16, int fp16, float* dx, int accumulate,
                           cudaStream_t st, void* dx16) {
   if (C % 64 != 0 || C > 32 * kLnMaxPerLane) return "layernorm_bwd: C must be a multiple of 64, <= 1280";
-  ln_bwd_kernel<<<(M + 7) / 8, 256, 0, st>>>(x, M, C, gamma, eps, static_cast<const uint16_t*>(dy16), fp16, dx, accumulate, static_cast<uint16_t*>(dx16));
+  const uint16_t* dy = static_cast<const uint16_t*>(dy16);
+  uint16_t* d16 = static_cast<uint16_t*>(dx16);
+  const unsigned grid = (M + 7) / 8;
+  switch (C / 32) {
+    case 2: ln_bwd_kernel<2><<<grid, 256, 0, st>>>(x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
+    case 4: ln_bwd_kernel<4><<<grid, 256, 0, st>>>(x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
+    case 10: ln_bwd_kernel<10><<<grid, 256, 0, st>>>(x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
+    case 20: ln_bwd_kernel<20><<<grid, 256, 0, st>>>(x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
+    case 40: ln_bwd_kernel<40><<<grid, 256, 0, st>>>(x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
+    default: return "layernorm_bwd: C must be 64, 128, 320, 640 or 1280";
+  }
   return cudaGetLastError() == cudaSuccess ? nullptr : "layernorm_bwd launch failed";
 }
 
