@@ -86,7 +86,9 @@ __device__ __forceinline__ float2 gn_load_x(const void* x0, int C0, const void* 
 }
 
 // pass 1: partial[b][slab][c][2] = sum over the slab's pixels of (g, g * xhat)
-template <bool IN16>
+// KT = channel pairs per thread (geo.K, 1..5): compile-time, so a C = 320 launch carries one pair's constants and accumulators instead of five
+// (128 registers at 512 threads = one CTA per SM before)
+template <bool IN16, int KT>
 __global__ void __launch_bounds__(kGnThreads) gn_bwd_reduce_kernel(const void* __restrict__ x0, int C0, const void* __restrict__ x1, int C1, int HW,
                                                                    int slab_pix, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, float eps, int act,
@@ -97,10 +99,10 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_reduce_kernel(const void* _
   const int tx = threadIdx.x % geo.TX, pl = threadIdx.x / geo.TX;
   const bool active = pl < geo.P;
   const float inv_n = 1.0f / (float(HW) * float(cpg));
-  GnChan ch[kGnKMax];
-  float acc[kGnKMax][4];
+  GnChan ch[KT];
+  float acc[KT][4];
 #pragma unroll
-  for (int k = 0; k < kGnKMax; ++k) {
+  for (int k = 0; k < KT; ++k) {
     acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
     const int v = tx + k * geo.TX;
     if (k < geo.K && v < cv && active) gn_load_chan(stats + size_t(b) * 64, gamma, beta, 2 * v, cpg, inv_n, eps, ch[k]);
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_reduce_kernel(const void* _
       const bool two = p + geo.P < p1;
       const size_t pixb = two ? pixa + geo.P : pixa;
 #pragma unroll
-      for (int k = 0; k < kGnKMax; ++k) {
+      for (int k = 0; k < KT; ++k) {
         const int v = tx + k * geo.TX;
         if (k < geo.K && v < cv) {
           const float2 xa = gn_load_x<IN16>(x0, C0, x1, C1, pixa, 2 * v, fp16);
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_reduce_kernel(const void* _
   // fold the pixel lanes (fixed order) through shared memory, then one (g, g*xhat) pair per channel
   __shared__ float red[kGnThreads * 4];
 #pragma unroll
-  for (int k = 0; k < kGnKMax; ++k) {
+  for (int k = 0; k < KT; ++k) {
     if (k < geo.K) {  // (uniform across the CTA)
       __syncthreads();
       red[threadIdx.x * 4 + 0] = acc[k][0]; red[threadIdx.x * 4 + 1] = acc[k][1];
@@ -200,7 +202,7 @@ __global__ void gn_bwd_affine_kernel(const float* __restrict__ chan, int B, int 
 }
 
 // pass 3: dx (+ extra) -> 16-bit [B,HW,C], or fp32 split over the two concat sources (each stored or accumulated)
-template <bool IN16>
+template <bool IN16, int KT>
 __global__ void __launch_bounds__(kGnThreads) gn_bwd_apply_kernel(const void* __restrict__ x0, int C0, const void* __restrict__ x1, int C1, int HW,
                                                                   int slab_pix, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, float eps, int act,
@@ -213,10 +215,10 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_apply_kernel(const void* __
   const int tx = threadIdx.x % geo.TX, pl = threadIdx.x / geo.TX;
   if (pl >= geo.P) return;
   const float inv_n = 1.0f / (float(HW) * float(cpg));
-  GnChan ch[kGnKMax];
-  float c1[kGnKMax][2], c2[kGnKMax][2];
+  GnChan ch[KT];
+  float c1[KT][2], c2[KT][2];
 #pragma unroll
-  for (int k = 0; k < kGnKMax; ++k) {
+  for (int k = 0; k < KT; ++k) {
     const int v = tx + k * geo.TX;
     if (k < geo.K && v < cv) {
       gn_load_chan(stats + size_t(b) * 64, gamma, beta, 2 * v, cpg, inv_n, eps, ch[k]);
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_apply_kernel(const void* __
     const size_t pixs[2] = {size_t(b) * HW + p, size_t(b) * HW + p + geo.P};
     const bool two = p + geo.P < p1;
 #pragma unroll
-    for (int k = 0; k < kGnKMax; ++k) {
+    for (int k = 0; k < KT; ++k) {
       const int v = tx + k * geo.TX;
       if (k < geo.K && v < cv) {
         const int c = 2 * v;
@@ -489,15 +491,22 @@ const char* groupnorm_bwd(const void* x0, int C0, const void* x1, int C1, int B,
   const GnBwdGeo geo = gn_bwd_geo(C);
   const int threads = geo.TX * geo.P;
   const uint16_t* dy = static_cast<const uint16_t*>(dy16);
-  if (in16) gn_bwd_reduce_kernel<true><<<grid, threads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, fp16, partial);
-  else gn_bwd_reduce_kernel<false><<<grid, threads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, fp16, partial);
+#define GN_BWD_K(KERNEL, ...)                                                                     \
+  switch (geo.K) {                                                                                  \
+    case 1: if (in16) KERNEL<true, 1><<<grid, threads, 0, st>>>(__VA_ARGS__); else KERNEL<false, 1><<<grid, threads, 0, st>>>(__VA_ARGS__); break; \
+    case 2: if (in16) KERNEL<true, 2><<<grid, threads, 0, st>>>(__VA_ARGS__); else KERNEL<false, 2><<<grid, threads, 0, st>>>(__VA_ARGS__); break; \
+    case 3: if (in16) KERNEL<true, 3><<<grid, threads, 0, st>>>(__VA_ARGS__); else KERNEL<false, 3><<<grid, threads, 0, st>>>(__VA_ARGS__); break; \
+    case 4: if (in16) KERNEL<true, 4><<<grid, threads, 0, st>>>(__VA_ARGS__); else KERNEL<false, 4><<<grid, threads, 0, st>>>(__VA_ARGS__); break; \
+    default: if (in16) KERNEL<true, 5><<<grid, threads, 0, st>>>(__VA_ARGS__); else KERNEL<false, 5><<<grid, threads, 0, st>>>(__VA_ARGS__); break; \
+  }
+  GN_BWD_K(gn_bwd_reduce_kernel, x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, fp16, partial)
   gn_bwd_finalize_kernel<<<dim3(32, B), 128, 0, st>>>(partial, slabs, C, HW, gamma, coef, chan);
   if (dgamma || dbeta) gn_bwd_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(chan, B, C, affine_scale, dgamma, dbeta);
   if (out16 || dx0 || dx1) {
     uint16_t* o16 = static_cast<uint16_t*>(out16);
-    if (in16) gn_bwd_apply_kernel<true><<<grid, threads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, coef, extra, o16, dx0, acc0, dx1, acc1, fp16);
-    else gn_bwd_apply_kernel<false><<<grid, threads, 0, st>>>(x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, coef, extra, o16, dx0, acc0, dx1, acc1, fp16);
+    GN_BWD_K(gn_bwd_apply_kernel, x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, coef, extra, o16, dx0, acc0, dx1, acc1, fp16)
   }
+#undef GN_BWD_K
   return cudaGetLastError() == cudaSuccess ? nullptr : "groupnorm_bwd launch failed";
 }
 
