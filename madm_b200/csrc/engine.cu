@@ -11,6 +11,7 @@
 #include "../../include/madm_b200.h"
 #include "api_internal.h"
 #include "kernels.h"
+#include "launch.cuh"
 
 #include <cuda_bf16.h>
 #include <functional>
@@ -2694,6 +2695,7 @@ int extract_train(madm_ctx* ctx, const madm_extract_args* a, cudaStream_t st) {
     ctx->train_plans[tkey] = std::move(np);
   }
   plan->io->a = *a;
+  PdlTrainScope pdl;  // programmatic dependent launch for the training forward's ~550 small launches (launch.cuh)
   for (size_t i = 0; i < plan->ops.size(); ++i) {
     if (!plan->ops[i]) continue;
     if (const char* e = plan->ops[i](st)) return set_err(ctx, MADM_ECUDA, std::string(e) + " (training forward op " + std::to_string(i) + ")");
@@ -2848,6 +2850,7 @@ int madm_backward(madm_ctx* ctx, const madm_backward_args* a, madm_stream stream
     return set_err(ctx, MADM_ESTATE, "madm_backward: arguments differ from the MADM_FLAG_TRAIN forward this plan was built for");
   plan->io->b = *a;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PdlTrainScope pdl;  // programmatic dependent launch for the backward's ~640 small launches (launch.cuh)
   for (size_t i = 0; i < plan->bops.size(); ++i) {
     if (!plan->bops[i]) continue;
     if (const char* e = plan->bops[i](st)) return set_err(ctx, MADM_ECUDA, std::string(e) + " (backward op " + std::to_string(i) + ")");
