@@ -9,6 +9,7 @@
 // warp-level wmma (16x16x16, fp32 accumulate) on the context's 16-bit operand dtype.  This is the first backward of the path: it is sized
 // for the training step's 2 images per GPU, where attention backward is ~1.3 TFLOP per step, not for the tcgen05 peak of the forward kernel.
 #include "kernels.h"
+#include "launch.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -128,6 +129,8 @@ __device__ __forceinline__ void write_tile(const float* stage, uint16_t* dst, in
 // ------------------------------------------------------------------------------------------------ L and D
 template <typename T, int DP>
 __global__ void __launch_bounds__(AB_THREADS) attn_bwd_prep_kernel(const AttnBwdParams p) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int LD = DP + 8;
   T* Qs = reinterpret_cast<T*>(smem_raw);
@@ -185,6 +188,8 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_prep_kernel(const AttnBwd
 
 // D only (the forward kernel supplied L): one warp-quarter per row as above, no Q K^T pass
 __global__ void __launch_bounds__(AB_THREADS) attn_bwd_d_kernel(const AttnBwdParams p, int fp16) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const int ib = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int row = threadIdx.x >> 2, part = threadIdx.x & 3;
   const int i = ib * AB + row;
@@ -237,6 +242,8 @@ template <int DP> struct AttnSmem {
 // ------------------------------------------------------------------------------------------------ dK, dV
 template <typename T, int DP>
 __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const AttnBwdParams p) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int LD = DP + 8, NT = DP / 16, NTH = (NT + 1) / 2, FLD = DP + 4;
   T* Ks = reinterpret_cast<T*>(smem_raw);
@@ -341,6 +348,8 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dkv_kernel(const AttnBwdP
 // ------------------------------------------------------------------------------------------------ dQ
 template <typename T, int DP>
 __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dq_kernel(const AttnBwdParams p) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int LD = DP + 8, NT = DP / 16, NTH = (NT + 1) / 2, FLD = DP + 4;
   T* Kb = reinterpret_cast<T*>(smem_raw);  // [2][64][LD]
@@ -415,6 +424,8 @@ __global__ void __launch_bounds__(AB_THREADS) attn_bwd_dq_kernel(const AttnBwdPa
 // dk / dv = sum over the query splits of the fp32 partials (fixed order), unscaled, rounded to 16 bits
 template <typename T, int DP>
 __global__ void attn_bwd_kv_reduce_kernel(const AttnBwdParams p, int B) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const int kvrows = ((p.Nk + AB - 1) / AB) * AB;
   const long total = long(B) * p.heads * p.Nk * (p.d / 2);
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -447,19 +458,19 @@ const char* launch_all(const AttnBwdParams& p, int B, cudaStream_t st, bool have
     attr = true;
   }
   const dim3 gq((p.Nq + AB - 1) / AB, p.heads, B), gk(((p.Nk + AB - 1) / AB) * p.qsplit, p.heads, B);
-  if (have_lse) attn_bwd_d_kernel<<<gq, AB_THREADS, 0, st>>>(p, fp16);
-  else attn_bwd_prep_kernel<T, DP><<<gq, AB_THREADS, AttnSmem<DP>::PREP, st>>>(p);
+  if (have_lse) launch_k(attn_bwd_d_kernel, dim3(gq), dim3(AB_THREADS), 0, st, p, fp16);
+  else launch_k(attn_bwd_prep_kernel<T, DP>, dim3(gq), dim3(AB_THREADS), AttnSmem<DP>::PREP, st, p);
   if (p.L2out) {  // large self-attention: the tcgen05 / TMEM kernels (attention_bwd_tc.cu) take over after the L / D pass
     if (cudaGetLastError() != cudaSuccess) return "attention_bwd launch failed";
     return attention_bwd_tc(p.q, p.ldq, p.k, p.ldk, p.v, p.ldv, p.dout, p.lddo, p.dq, p.lddq, p.dk, p.lddk, p.dv, p.lddv, B, p.heads, p.d, p.Nq, p.Nk, p.q_bs,
                             p.k_bs, p.v_bs, p.do_bs, p.dq_bs, p.dk_bs, p.dv_bs, p.scale, p.L2out, p.D, fp16, st);
   }
-  attn_bwd_dkv_kernel<T, DP><<<gk, AB_THREADS, AttnSmem<DP>::DKV, st>>>(p);
+  launch_k(attn_bwd_dkv_kernel<T, DP>, dim3(gk), dim3(AB_THREADS), AttnSmem<DP>::DKV, st, p);
   if (p.qsplit > 1) {
     const long total = long(B) * p.heads * p.Nk * (p.d / 2);
-    attn_bwd_kv_reduce_kernel<T, DP><<<unsigned((total + 255) / 256), 256, 0, st>>>(p, B);
+    launch_k(attn_bwd_kv_reduce_kernel<T, DP>, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, p, B);
   }
-  attn_bwd_dq_kernel<T, DP><<<gq, AB_THREADS, AttnSmem<DP>::DQ, st>>>(p);
+  launch_k(attn_bwd_dq_kernel<T, DP>, dim3(gq), dim3(AB_THREADS), AttnSmem<DP>::DQ, st, p);
   return cudaGetLastError() == cudaSuccess ? nullptr : "attention_bwd launch failed";
 }
 

@@ -5,6 +5,7 @@
 // gradients are bit-reproducible run to run.
 #include "cvt.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 
 #include <cooperative_groups.h>
 
@@ -93,6 +94,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_reduce_kernel(const void* _
                                                                    int slab_pix, const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                    const float* __restrict__ beta, float eps, int act,
                                                                    const uint16_t* __restrict__ dy, int fp16, float* __restrict__ partial) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const int C = C0 + C1, cv = C / 2, cpg = C / 32;
   const GnBwdGeo geo = gn_bwd_geo(C);
   const int b = blockIdx.y, slab = blockIdx.x, slabs = gridDim.x;
@@ -165,6 +168,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_reduce_kernel(const void* _
 // butterfly reduction), coef[b][g] = (sum_c gamma_c A_c, sum_c gamma_c B_c) / n.  Warp w owns the group's channels w, w + 4, ...
 __global__ void __launch_bounds__(128) gn_bwd_finalize_kernel(const float* __restrict__ partial, int slabs, int C, int HW,
                                                               const float* __restrict__ gamma, float* __restrict__ coef, float* __restrict__ chan) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const int g = blockIdx.x, b = blockIdx.y, cpg = C / 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ float sw[4][2];
@@ -193,6 +198,8 @@ __global__ void __launch_bounds__(128) gn_bwd_finalize_kernel(const float* __res
 
 // dgamma_c = scale * sum_b B_c, dbeta_c = scale * sum_b A_c
 __global__ void gn_bwd_affine_kernel(const float* __restrict__ chan, int B, int C, float scale, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a = 0.f, bb = 0.f;
@@ -209,6 +216,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_bwd_apply_kernel(const void* __
                                                                   const uint16_t* __restrict__ dy, const float* __restrict__ coef,
                                                                   const float* __restrict__ extra, uint16_t* __restrict__ out16,
                                                                   float* __restrict__ dx0, int acc0, float* __restrict__ dx1, int acc1, int fp16) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const int C = C0 + C1, cv = C / 2, cpg = C / 32;
   const GnBwdGeo geo = gn_bwd_geo(C);
   const int b = blockIdx.y, slab = blockIdx.x;
@@ -279,6 +288,8 @@ template <int PER>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x, int M, int C, const float* __restrict__ gamma, float eps,
                                                      const uint16_t* __restrict__ dy, int fp16, float* __restrict__ dx, int accumulate,
                                                      uint16_t* __restrict__ dx16) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -338,6 +349,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ x
 // ------------------------------------------------------------------------------------------------ GEGLU (natural column order)
 // raw [M, 2H] = (hidden | gate) from ff.net.0.proj; out = hidden * gelu(gate) (exact erf GELU, as diffusers' GEGLU)
 __global__ void geglu_fwd_kernel(const uint16_t* __restrict__ raw, long M, int H, int fp16, uint16_t* __restrict__ out) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = (long(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
   if (i >= M * H) return;
   const long m = i / H; const int j = int(i - m * H);
@@ -354,6 +367,8 @@ __device__ __forceinline__ void geglu_grad(float h, float g, float d, float& dh,
 }
 __global__ void geglu_bwd_kernel(const uint16_t* __restrict__ raw, const uint16_t* __restrict__ dout, long M, int H, int fp16,
                                  uint16_t* __restrict__ draw) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = (long(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
   if (i >= M * H) return;
   const long m = i / H; const int j = int(i - m * H);
@@ -407,6 +422,8 @@ __global__ void __launch_bounds__(256) colsum_img_kernel(const uint16_t* __restr
 
 // 16-bit [B,h,w,C] -> [B,2h,2w,C] with the values at the even positions and zeros elsewhere (operand of a stride-2 conv's dgrad)
 __global__ void zero_stuff2x_kernel(const uint4* __restrict__ x, int h, int w, int C8, long total, uint4* __restrict__ out) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = int(i % C8);
@@ -420,6 +437,8 @@ __global__ void zero_stuff2x_kernel(const uint4* __restrict__ x, int h, int w, i
 
 // fp32 [B,2h,2w,C] -> [B,h,w,C]: sum of each 2x2 block (backward of nearest-2x upsampling), stored or accumulated
 __global__ void sum2x2_kernel(const float4* __restrict__ x, int h, int w, int C4, long total, float4* __restrict__ out, int accumulate) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = int(i % C4);
@@ -436,6 +455,8 @@ __global__ void sum2x2_kernel(const float4* __restrict__ x, int h, int w, int C4
 // dz[b,p,c] (16-bit NHWC) = scale * dout[b,c,p] * (out[b,c,p] > 0): ReLU backward of the projections' final pass + NCHW -> NHWC
 __global__ void __launch_bounds__(256) relu_bwd_nchw_kernel(const float* __restrict__ dout, const float* __restrict__ outv, int C, int HW, float scale,
                                                             int fp16, uint16_t* __restrict__ dz) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -458,12 +479,16 @@ __global__ void __launch_bounds__(256) relu_bwd_nchw_kernel(const float* __restr
 // d_cond_emb[b,j] = scale * d_act[b,j] * silu'(emb[b,j] + cond_emb[b,j])   (time path: emb_act = silu(emb + cond_emb))
 __global__ void temb_silu_bwd_kernel(const float* __restrict__ d_act, const float* __restrict__ emb, const float* __restrict__ cond_emb, long n,
                                      float scale, float* __restrict__ d_cond_emb) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   d_cond_emb[i] = scale * d_act[i] * act_grad(emb[i] + cond_emb[i], ACT_SILU);
 }
 
 __global__ void scale_copy_kernel(const float* __restrict__ src, long n, float scale, float* __restrict__ dst) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i] * scale;
 }
@@ -471,7 +496,7 @@ __global__ void scale_copy_kernel(const float* __restrict__ src, long n, float s
 }  // namespace
 
 const char* scale_copy_f32(const float* src, long n, float scale, float* dst, cudaStream_t st) {
-  scale_copy_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(src, n, scale, dst);
+  launch_k(scale_copy_kernel, dim3(unsigned((n + 255) / 256)), dim3(256), 0, st, src, n, scale, dst);
   return cudaGetLastError() == cudaSuccess ? nullptr : "scale_copy_f32 launch failed";
 }
 
@@ -493,15 +518,15 @@ const char* groupnorm_bwd(const void* x0, int C0, const void* x1, int C1, int B,
   const uint16_t* dy = static_cast<const uint16_t*>(dy16);
 #define GN_BWD_K(KERNEL, ...)                                                                     \
   switch (geo.K) {                                                                                  \
-    case 1: if (in16) KERNEL<true, 1><<<grid, threads, 0, st>>>(__VA_ARGS__); else KERNEL<false, 1><<<grid, threads, 0, st>>>(__VA_ARGS__); break; \
-    case 2: if (in16) KERNEL<true, 2><<<grid, threads, 0, st>>>(__VA_ARGS__); else KERNEL<false, 2><<<grid, threads, 0, st>>>(__VA_ARGS__); break; \
-    case 3: if (in16) KERNEL<true, 3><<<grid, threads, 0, st>>>(__VA_ARGS__); else KERNEL<false, 3><<<grid, threads, 0, st>>>(__VA_ARGS__); break; \
-    case 4: if (in16) KERNEL<true, 4><<<grid, threads, 0, st>>>(__VA_ARGS__); else KERNEL<false, 4><<<grid, threads, 0, st>>>(__VA_ARGS__); break; \
-    default: if (in16) KERNEL<true, 5><<<grid, threads, 0, st>>>(__VA_ARGS__); else KERNEL<false, 5><<<grid, threads, 0, st>>>(__VA_ARGS__); break; \
+    case 1: if (in16) launch_k(KERNEL<true, 1>, dim3(grid), dim3(threads), 0, st, __VA_ARGS__); else launch_k(KERNEL<false, 1>, dim3(grid), dim3(threads), 0, st, __VA_ARGS__); break; \
+    case 2: if (in16) launch_k(KERNEL<true, 2>, dim3(grid), dim3(threads), 0, st, __VA_ARGS__); else launch_k(KERNEL<false, 2>, dim3(grid), dim3(threads), 0, st, __VA_ARGS__); break; \
+    case 3: if (in16) launch_k(KERNEL<true, 3>, dim3(grid), dim3(threads), 0, st, __VA_ARGS__); else launch_k(KERNEL<false, 3>, dim3(grid), dim3(threads), 0, st, __VA_ARGS__); break; \
+    case 4: if (in16) launch_k(KERNEL<true, 4>, dim3(grid), dim3(threads), 0, st, __VA_ARGS__); else launch_k(KERNEL<false, 4>, dim3(grid), dim3(threads), 0, st, __VA_ARGS__); break; \
+    default: if (in16) launch_k(KERNEL<true, 5>, dim3(grid), dim3(threads), 0, st, __VA_ARGS__); else launch_k(KERNEL<false, 5>, dim3(grid), dim3(threads), 0, st, __VA_ARGS__); break; \
   }
   GN_BWD_K(gn_bwd_reduce_kernel, x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, fp16, partial)
-  gn_bwd_finalize_kernel<<<dim3(32, B), 128, 0, st>>>(partial, slabs, C, HW, gamma, coef, chan);
-  if (dgamma || dbeta) gn_bwd_affine_kernel<<<(C + 127) / 128, 128, 0, st>>>(chan, B, C, affine_scale, dgamma, dbeta);
+  launch_k(gn_bwd_finalize_kernel, dim3(dim3(32, B)), dim3(128), 0, st, partial, slabs, C, HW, gamma, coef, chan);
+  if (dgamma || dbeta) launch_k(gn_bwd_affine_kernel, dim3((C + 127) / 128), dim3(128), 0, st, chan, B, C, affine_scale, dgamma, dbeta);
   if (out16 || dx0 || dx1) {
     uint16_t* o16 = static_cast<uint16_t*>(out16);
     GN_BWD_K(gn_bwd_apply_kernel, x0, C0, x1, C1, HW, sp, stats, gamma, beta, eps, act, dy, coef, extra, o16, dx0, acc0, dx1, acc1, fp16)
@@ -517,11 +542,11 @@ const char* layernorm_bwd(const float* x, int M, int C, const float* gamma, floa
   uint16_t* d16 = static_cast<uint16_t*>(dx16);
   const unsigned grid = (M + 7) / 8;
   switch (C / 32) {
-    case 2: ln_bwd_kernel<2><<<grid, 256, 0, st>>>(x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
-    case 4: ln_bwd_kernel<4><<<grid, 256, 0, st>>>(x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
-    case 10: ln_bwd_kernel<10><<<grid, 256, 0, st>>>(x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
-    case 20: ln_bwd_kernel<20><<<grid, 256, 0, st>>>(x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
-    case 40: ln_bwd_kernel<40><<<grid, 256, 0, st>>>(x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
+    case 2: launch_k(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, st, x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
+    case 4: launch_k(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, st, x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
+    case 10: launch_k(ln_bwd_kernel<10>, dim3(grid), dim3(256), 0, st, x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
+    case 20: launch_k(ln_bwd_kernel<20>, dim3(grid), dim3(256), 0, st, x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
+    case 40: launch_k(ln_bwd_kernel<40>, dim3(grid), dim3(256), 0, st, x, M, C, gamma, eps, dy, fp16, dx, accumulate, d16); break;
     default: return "layernorm_bwd: C must be 64, 128, 320, 640 or 1280";
   }
   return cudaGetLastError() == cudaSuccess ? nullptr : "layernorm_bwd launch failed";
@@ -530,13 +555,13 @@ const char* layernorm_bwd(const float* x, int M, int C, const float* gamma, floa
 const char* geglu_fwd(const void* raw16, long M, int H, void* out16, int fp16, cudaStream_t st) {
   if (H % 2 != 0) return "geglu: H must be even";
   const long n = M * H / 2;
-  geglu_fwd_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(static_cast<const uint16_t*>(raw16), M, H, fp16, static_cast<uint16_t*>(out16));
+  launch_k(geglu_fwd_kernel, dim3(unsigned((n + 255) / 256)), dim3(256), 0, st, static_cast<const uint16_t*>(raw16), M, H, fp16, static_cast<uint16_t*>(out16));
   return cudaGetLastError() == cudaSuccess ? nullptr : "geglu_fwd launch failed";
 }
 const char* geglu_bwd(const void* raw16, const void* dout16, long M, int H, void* draw16, int fp16, cudaStream_t st) {
   if (H % 2 != 0) return "geglu: H must be even";
   const long n = M * H / 2;
-  geglu_bwd_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(static_cast<const uint16_t*>(raw16), static_cast<const uint16_t*>(dout16), M, H, fp16,
+  launch_k(geglu_bwd_kernel, dim3(unsigned((n + 255) / 256)), dim3(256), 0, st, static_cast<const uint16_t*>(raw16), static_cast<const uint16_t*>(dout16), M, H, fp16,
                                                             static_cast<uint16_t*>(draw16));
   return cudaGetLastError() == cudaSuccess ? nullptr : "geglu_bwd launch failed";
 }
@@ -562,25 +587,25 @@ const char* colsum_per_image(const void* x16, int B, int HW, int C, int fp16, fl
 const char* zero_stuff2x(const void* x16, int B, int h, int w, int C, void* out16, cudaStream_t st) {
   if (C % 8 != 0) return "zero_stuff2x: C must be a multiple of 8";
   const long total = long(B) * 2 * h * 2 * w * (C / 8);
-  zero_stuff2x_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(static_cast<const uint4*>(x16), h, w, C / 8, total, static_cast<uint4*>(out16));
+  launch_k(zero_stuff2x_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, static_cast<const uint4*>(x16), h, w, C / 8, total, static_cast<uint4*>(out16));
   return cudaGetLastError() == cudaSuccess ? nullptr : "zero_stuff2x launch failed";
 }
 
 const char* sum2x2(const float* x, int B, int h, int w, int C, float* out, int accumulate, cudaStream_t st) {
   if (C % 4 != 0) return "sum2x2: C must be a multiple of 4";
   const long total = long(B) * h * w * (C / 4);
-  sum2x2_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), h, w, C / 4, total, reinterpret_cast<float4*>(out),
+  launch_k(sum2x2_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(x), h, w, C / 4, total, reinterpret_cast<float4*>(out),
                                                              accumulate);
   return cudaGetLastError() == cudaSuccess ? nullptr : "sum2x2 launch failed";
 }
 
 const char* relu_bwd_nchw_to_nhwc16(const float* dout, const float* out, int B, int C, int HW, float scale, void* dz16, int fp16, cudaStream_t st) {
-  relu_bwd_nchw_kernel<<<dim3((HW + 31) / 32, (C + 31) / 32, B), 256, 0, st>>>(dout, out, C, HW, scale, fp16, static_cast<uint16_t*>(dz16));
+  launch_k(relu_bwd_nchw_kernel, dim3(dim3((HW + 31) / 32, (C + 31) / 32, B)), dim3(256), 0, st, dout, out, C, HW, scale, fp16, static_cast<uint16_t*>(dz16));
   return cudaGetLastError() == cudaSuccess ? nullptr : "relu_bwd_nchw_to_nhwc16 launch failed";
 }
 
 const char* temb_silu_bwd(const float* d_act, const float* emb, const float* cond_emb, long n, float scale, float* d_cond_emb, cudaStream_t st) {
-  temb_silu_bwd_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(d_act, emb, cond_emb, n, scale, d_cond_emb);
+  launch_k(temb_silu_bwd_kernel, dim3(unsigned((n + 255) / 256)), dim3(256), 0, st, d_act, emb, cond_emb, n, scale, d_cond_emb);
   return cudaGetLastError() == cudaSuccess ? nullptr : "temb_silu_bwd launch failed";
 }
 

@@ -6,6 +6,7 @@
 // warp-level tensor-core kernel (wmma 16x16x16, fp32 accumulate) with a deterministic split over M: every split writes its own fp32
 // partial tile, a second kernel reduces them in fixed order, scales, and scatters into the parameter's PyTorch layout.
 #include "kernels.h"
+#include "launch.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -36,6 +37,8 @@ struct WgradParams {
 
 template <typename T, int TK>
 __global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   __shared__ __align__(32) T As[WG_MC][WG_TN + WG_PAD];
   __shared__ __align__(32) T Bs[WG_MC][TK + WG_PAD];
   const int tilesK = p.K / TK;
@@ -106,6 +109,8 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgradParams p) {
 // out[layout(n, k, tap)] = alpha * sum_s part[s][tap][n][k]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int splits, int taps, int N, int K, float alpha, float* __restrict__ out,
                                     long so_n, long so_k, long so_tap) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   const long per = long(taps) * N * K;
   if (i >= per) return;
@@ -144,6 +149,8 @@ constexpr size_t LG_SMEM = size_t(2) * 64 * LG_LD * 2 + size_t(2) * 64 * 24 * 2 
 
 template <typename T, int KP, int NP>
 __global__ void __launch_bounds__(256, 1) lora_grad_kernel(const LoraGradParams p) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   constexpr int K = 64 * KP, N = 64 * NP, PMAX = KP > NP ? KP : NP, ROUNDS = (PMAX + 3) / 4;
   extern __shared__ __align__(128) unsigned char lg_smem[];
   T (*Xs)[LG_LD] = reinterpret_cast<T (*)[LG_LD]>(lg_smem);
@@ -243,6 +250,8 @@ __global__ void __launch_bounds__(256, 1) lora_grad_kernel(const LoraGradParams 
 // gB[n*16 + r] = alpha * sum_c part_b[c][n][r]   ;   gA[r*K + k] = alpha * sum_c part_a[c][k][r]
 __global__ void lora_grad_reduce_kernel(const float* __restrict__ part_b, const float* __restrict__ part_a, int ctas, int N, int K, float alpha,
                                         float* __restrict__ gB, float* __restrict__ gA) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N * 16) {
     if (!gB) return;
@@ -266,7 +275,7 @@ const char* lora_grad_launch_kn(const LoraGradParams& p, int ctas, cudaStream_t 
       return "lora_grads: cudaFuncSetAttribute failed";
     attr = true;
   }
-  lora_grad_kernel<T, KP, NP><<<dim3(ctas, p.groups), 256, LG_SMEM, st>>>(p);
+  launch_k(lora_grad_kernel<T, KP, NP>, dim3(dim3(ctas, p.groups)), dim3(256), LG_SMEM, st, p);
   return nullptr;
 }
 template <typename T, int KP>
@@ -318,12 +327,12 @@ const char* wgrad(const void* dy16, int lda, const void* x16, int ldb, int M, in
   const int tk = K % 64 == 0 ? 64 : 16;
   const dim3 grid(unsigned(taps * (K / tk)), unsigned(N / WG_TN), unsigned(splits));
   if (fp16) {
-    if (tk == 64) wgrad_kernel<__half, 64><<<grid, 128, 0, st>>>(p); else wgrad_kernel<__half, 16><<<grid, 128, 0, st>>>(p);
+    if (tk == 64) launch_k(wgrad_kernel<__half, 64>, dim3(grid), dim3(128), 0, st, p); else launch_k(wgrad_kernel<__half, 16>, dim3(grid), dim3(128), 0, st, p);
   } else {
-    if (tk == 64) wgrad_kernel<__nv_bfloat16, 64><<<grid, 128, 0, st>>>(p); else wgrad_kernel<__nv_bfloat16, 16><<<grid, 128, 0, st>>>(p);
+    if (tk == 64) launch_k(wgrad_kernel<__nv_bfloat16, 64>, dim3(grid), dim3(128), 0, st, p); else launch_k(wgrad_kernel<__nv_bfloat16, 16>, dim3(grid), dim3(128), 0, st, p);
   }
   const long per = long(taps) * N * K;
-  wgrad_reduce_kernel<<<unsigned((per + 255) / 256), 256, 0, st>>>(scratch, splits, taps, N, K, alpha, out, so_n, so_k, so_tap);
+  launch_k(wgrad_reduce_kernel, dim3(unsigned((per + 255) / 256)), dim3(256), 0, st, scratch, splits, taps, N, K, alpha, out, so_n, so_k, so_tap);
   return cudaGetLastError() == cudaSuccess ? nullptr : "wgrad launch failed";
 }
 
@@ -356,7 +365,7 @@ const char* lora_grads(const void* x16, int ldx, const void* dy16, int ldy, cons
     p.groups = g < 1 ? 1 : g;
   }
   if (const char* e = fp16 ? lora_grad_launch<__half>(p, K / 64, N / 64, used, st) : lora_grad_launch<__nv_bfloat16>(p, K / 64, N / 64, used, st)) return e;
-  lora_grad_reduce_kernel<<<((N + K) * 16 + 255) / 256, 256, 0, st>>>(p.part_b, p.part_a, used, N, K, alpha, gB, gA);
+  launch_k(lora_grad_reduce_kernel, dim3(((N + K) * 16 + 255) / 256), dim3(256), 0, st, p.part_b, p.part_a, used, N, K, alpha, gB, gA);
   return cudaGetLastError() == cudaSuccess ? nullptr : "lora_grads launch failed";
 }
 
