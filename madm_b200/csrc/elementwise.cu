@@ -136,6 +136,8 @@ const char* timestep_sinusoid(const int64_t* t, int B, void* out_bf16, int fp16,
 // ------------------------------------------------------------------ fp32 (+add) (+act) -> bf16 / fp32
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, const float* __restrict__ add, long n, int act, int fp16,
                                    uint16_t* __restrict__ y, float* __restrict__ yf) {
+  pdl_trigger();  // programmatic dependent launch (launch.cuh): no global access before pdl_wait()
+  pdl_wait();
   const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = x[i];
@@ -144,9 +146,29 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ x, const float* __r
   if (act == ACT_SILU) v = v / (1.0f + __expf(-v));
   if (y) y[i] = cvt_16(v, fp16);
 }
+// four elements per thread (n % 4 == 0, 16-byte aligned pointers)
+__global__ void f32_to_bf16_v4_kernel(const float4* __restrict__ x, const float4* __restrict__ add, long n4, int act, int fp16,
+                                      uint2* __restrict__ y, float4* __restrict__ yf) {
+  pdl_trigger();
+  pdl_wait();
+  const long i = long(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = x[i];
+  if (add) { const float4 a = add[i]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+  if (yf) yf[i] = v;
+  if (act == ACT_SILU) {
+    v.x = v.x / (1.0f + __expf(-v.x)); v.y = v.y / (1.0f + __expf(-v.y)); v.z = v.z / (1.0f + __expf(-v.z)); v.w = v.w / (1.0f + __expf(-v.w));
+  }
+  if (y) y[i] = pack4_16(v.x, v.y, v.z, v.w, fp16);
+}
 
 const char* f32_to_bf16(const float* x, const float* add, long n, int act, void* y, float* yf, int fp16, cudaStream_t st) {
-  f32_to_bf16_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(x, add, n, act, fp16, reinterpret_cast<uint16_t*>(y), yf);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(yf) | (reinterpret_cast<uintptr_t>(y) << 1);
+  if (n % 4 == 0 && (al & 15) == 0)
+    launch_k(f32_to_bf16_v4_kernel, dim3(unsigned((n / 4 + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(add),
+             n / 4, act, fp16, reinterpret_cast<uint2*>(y), reinterpret_cast<float4*>(yf));
+  else
+    launch_k(f32_to_bf16_kernel, dim3(unsigned((n + 255) / 256)), dim3(256), 0, st, x, add, n, act, fp16, reinterpret_cast<uint16_t*>(y), yf);
   return cudaGetLastError() == cudaSuccess ? nullptr : "f32_to_bf16 launch failed";
 }
 
