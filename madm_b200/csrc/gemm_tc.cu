@@ -100,7 +100,10 @@ struct Cfg {
   static constexpr int BUDGET = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - EPI_BYTES;
   static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
   static constexpr int ACC_STRIDE = BN <= 16 ? 16 : (BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256)));
-  static constexpr int TMEM_COLS = 2 * MT * ACC_STRIDE < 32 ? 32 : 2 * MT * ACC_STRIDE;  // two accumulator stages x MT sub-tiles
+  // two accumulator stages (the MMAs of tile i+1 overlap the epilogue of tile i) wherever they fit the 512 TMEM columns; the 512-row pair tile of the
+  // 160-wide layers (MT = 2, stride 256) has room for one: its drain is exposed, its W traffic per MMA is halved
+  static constexpr int NACC = (2 * MT * ACC_STRIDE <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = NACC * MT * ACC_STRIDE < 32 ? 32 : NACC * MT * ACC_STRIDE;
   static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + EPI_BYTES + 1024 + 256;
   static_assert(TMEM_COLS <= 512, "TMEM budget");
 };
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         if constexpr (PAIR) umma_commit_pair(tmem_full_bar(acc));  // accumulator complete -> epilogue (of both CTAs)
         else umma_commit(tmem_full_bar(acc));
-        if (++acc == 2) {
+        if (++acc == C::NACC) {
           acc = 0;
           acc_phase ^= 1u;
         }
@@ -776,7 +779,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if constexpr (PAIR) mbar_arrive_leader(tmem_empty_bar(acc));  // the issuing thread lives in the leader CTA
         else mbar_arrive(tmem_empty_bar(acc));
       }
-      if (++acc == 2) {
+      if (++acc == C::NACC) {
         acc = 0;
         acc_phase ^= 1u;
       }
@@ -950,6 +953,14 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
     const long tiles2 = long((d.M + 2 * BM - 1) / (2 * BM)) * n_tiles;
     if (d.mt == 2 || tiles2 >= 2L * num_sms()) L.mt = 2;
   }
+  // 160-wide layers with long K (the UNet's 64x64-level convs): 512-row pair tiles when there are at least two waves of them
+  {
+    static const int env160 = getenv("MADM_GEMM_MT160") ? atoi(getenv("MADM_GEMM_MT160")) : 0;
+    int ktot160 = 0;
+    for (int s = 0; s < d.nseg; ++s) ktot160 += d.seg[s].ntaps * d.seg[s].C;
+    const long ptiles = long((d.M + 4 * BM - 1) / (4 * BM)) * n_tiles;
+    if (L.bn == 160 && num_sms() % 2 == 0 && d.pair >= 0 && (d.mt == 2 || (env160 > 0 && d.mt != 1 && ktot160 >= 2304 && ptiles >= num_sms()))) L.mt = 2;
+  }
   int m_tiles = (d.M + BM * L.mt - 1) / (BM * L.mt);
   // CTA pairs: worthwhile when every pair still gets at least one full tile; needs an even CTA count
   L.pair = 0;
@@ -958,6 +969,8 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
     const bool shape_ok = L.bn >= 128 && num_sms() % 2 == 0;
     const long pair_tiles = long((m_tiles + 1) / 2) * n_tiles;
     if (shape_ok && d.pair >= 0 && (d.pair == 1 || (env_pair > 0 && pair_tiles >= num_sms() / 2))) L.pair = 1;
+    if (L.bn == 160 && L.mt == 2 && !L.pair) L.mt = 1;  // (the one-stage 512-row tile exists as a pair kernel only)
+    if (L.bn == 160 && L.mt == 1 && m_tiles != (d.M + BM - 1) / BM) m_tiles = (d.M + BM - 1) / BM;
   }
   if (L.pair) m_tiles = (m_tiles + 1) / 2;  // tiles of the pair
   {
@@ -1032,7 +1045,7 @@ const char* gemm_prepare(const GemmDesc& d, GemmLaunch* out) {
     case 32: L.smem = Cfg<32, 1>::SMEM; break;
     case 64: L.smem = Cfg<64, 1>::SMEM; break;
     case 128: L.smem = L.mt == 2 ? (L.pair ? Cfg<128, 2, true>::SMEM : Cfg<128, 2>::SMEM) : (L.pair ? Cfg<128, 1, true>::SMEM : Cfg<128, 1>::SMEM); break;
-    case 160: L.smem = L.pair ? Cfg<160, 1, true>::SMEM : Cfg<160, 1>::SMEM; break;
+    case 160: L.smem = L.mt == 2 ? Cfg<160, 2, true>::SMEM : (L.pair ? Cfg<160, 1, true>::SMEM : Cfg<160, 1>::SMEM); break;
     case 192: L.smem = L.pair ? Cfg<192, 1, true>::SMEM : Cfg<192, 1>::SMEM; break;
     case 256: L.smem = L.pair ? Cfg<256, 1, true>::SMEM : Cfg<256, 1>::SMEM; break;
     default: return "gemm: unsupported N tile";
@@ -1098,6 +1111,9 @@ template <int BN>
 static const char* launch_bn(const GemmLaunch& L, const GemmParams& p, cudaStream_t stream) {
   if constexpr (BN == 128) {
     if (L.mt == 2) return L.pair ? launch_epi<BN, 2, true>(L, p, stream) : launch_epi<BN, 2, false>(L, p, stream);
+  }
+  if constexpr (BN == 160) {
+    if (L.mt == 2) return launch_epi<BN, 2, true>(L, p, stream);
   }
   if constexpr (BN >= 128) {
     if (L.pair) return launch_epi<BN, 1, true>(L, p, stream);
