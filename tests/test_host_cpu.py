@@ -289,6 +289,33 @@ def test_lora_grad_allreduce_world_size_2_gloo():
         assert grads[5] is None
 
 
+def test_allreduce_grads_single_process_views_and_zeros():
+    """Without a process group the call still flattens: afterwards every trainable parameter's .grad is a VIEW of the returned flat buffer
+    (zeros where there was no gradient, the reference's add_zero_grad_on_unused_lora, mtmadise.py:149-157), frozen parameters stay out."""
+    import torch
+    from madm_b200.optim import allreduce_grads
+    a, b, c = torch.nn.Parameter(torch.zeros(4, 3)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+    a.grad = torch.arange(12.0).reshape(4, 3)
+    flat = allreduce_grads([a, b, c])
+    assert flat.numel() == 17 and torch.equal(flat[:12], torch.arange(12.0)) and torch.count_nonzero(flat[12:]) == 0
+    assert a.grad.data_ptr() == flat.data_ptr() and b.grad.data_ptr() == flat[12:].data_ptr() and c.grad is None
+    flat.mul_(2.0)  # the views follow the buffer
+    assert torch.equal(a.grad, 2.0 * torch.arange(12.0).reshape(4, 3))
+
+
+def test_host_only_size_queries_of_the_training_ops():
+    """Scratch-size entry points are plain host functions: they answer without a device, and the fused LoRA-gradient op reports the widths it
+    does not support (-1) instead of guessing."""
+    from madm_b200 import _lib
+    lib = _lib.load()
+    ctas = min((8192 + 63) // 64, 148)
+    assert lib.madm_op_lora_grads_scratch_floats(8192, 320, 320) == ctas * 16 * (320 + 320)
+    assert lib.madm_op_lora_grads_scratch_floats(154, 1280, 768) == 3 * 16 * (1280 + 768)
+    assert lib.madm_op_lora_grads_scratch_floats(8192, 96, 320) == -1 and lib.madm_op_lora_grads_scratch_floats(8192, 320, 100) == -1
+    assert lib.madm_op_attention_bwd_scratch_floats(2, 8, 40, 4096, 4096) >= 2 * 2 * 8 * 4096
+    assert lib.madm_op_wgrad_scratch_floats(8192, 320, 16, 1) > 0
+
+
 def test_optimizer_ops_have_no_cpu_path():
     from madm_b200 import _lib
     from madm_b200.optim import FusedAdamW, update_ema
